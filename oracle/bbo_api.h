@@ -1,0 +1,81 @@
+/*
+ * ORACLE (test infrastructure).  One C API, exported twice with identical symbols:
+ *
+ *   oracle/_ref/libbbo_ref.so   the UNMODIFIED reference sources (/root/reference/src/...)
+ *                               compiled in place behind oracle/ref_harness.cpp
+ *   oracle/libbbo_port.so       oracle/port/bbo_port.cpp, our CPU restatement of the same
+ *                               algorithms (pinned bit-for-bit against the library above by
+ *                               tests/test_oracle_pinning.py and tests/golden/)
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+ * may load either library.
+ */
+#ifndef BBO_API_H_
+#define BBO_API_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* which implementation is behind this library: "reference" or "port" */
+const char *bbo_kind(void);
+
+/* ---- process-global random engine (reference: src/random.hpp:677-680, one static mt19937) */
+void bbo_seed(uint32_t s);
+/* kind 0: count draws of N(0,1) from ONE std::normal_distribution object (keeps its cache)
+ * kind 1: uniform_real(a,b)   kind 2: uniform_int(a,b) (closed)   kind 3: raw engine u32 */
+void bbo_rng_draw(int kind, int count, double a, double b, double *out);
+
+/* ---- objectives (spec: oracle/objectives_ref.h) */
+double bbo_eval(int obj, int n, const double *x);
+
+/* ---- CMA-ES family.  kind: 0 Cmaes, 1 ActiveCmaes, 2 SepCmaes */
+void *bbo_cma_new(int kind, int mfev, double tol, int np, double sigma0, int bound,
+                  double eigenrate, double alphacov, int adjustlr);
+void bbo_cma_free(void *h);
+void bbo_cma_init(void *h, int obj, int n, const double *lower, const double *upper,
+                  const double *guess);
+void bbo_cma_set_params(void *h, int np, double sigma, int mfev);
+void bbo_cma_sample(void *h);
+void bbo_cma_evalsort(void *h);
+void bbo_cma_update(void *h);
+void bbo_cma_history(void *h); /* updateHistory(); _it++  (base_cmaes.cpp:150-156) */
+void bbo_cma_iterate(void *h);
+int bbo_cma_converged(void *h);
+/* full optimize(); writes best x (n) and returns converged; *fev receives evaluations */
+int bbo_cma_optimize(void *h, int obj, int n, const double *lower, const double *upper,
+                     const double *guess, double *xout, int *fev);
+int bbo_cma_geti(void *h, const char *name);
+double bbo_cma_getd(void *h, const char *name);
+/* copies up to cap doubles, returns the field length (call with cap=0 to size) */
+int bbo_cma_getv(void *h, const char *name, double *out, int cap);
+/* reset the optimizer's own normal_distribution cache (public _Z member) */
+void bbo_cma_reset_z(void *h);
+
+/* ---- restart drivers.  kind: 0 IPOP, 1 BIPOP; base = handle from bbo_cma_new.
+ * trace receives up to cap rows of {lambda, sigma, fx, fev_total, regime}; returns rows */
+int bbo_restart_optimize(int kind, void *base, int mfev, double sigma0, int flag /*nipop|nbipop*/,
+                         double ksigmadec, int boundlambda, int maxlargeruns, double kbudget,
+                         int obj, int n, const double *lower, const double *upper,
+                         const double *guess, double *xout, int *fev, double *trace, int cap);
+
+/* ---- DE family.  kind: 0 JADE, 1 L-SHADE */
+void *bbo_de_new(int kind, int mfev, int np, double tol, int archive, int repaircr,
+                 double pelite, double cdamp, double sigma, int h, int npmin);
+void bbo_de_free(void *h);
+void bbo_de_init(void *h, int obj, int n, const double *lower, const double *upper,
+                 const double *guess);
+void bbo_de_iterate(void *h);
+int bbo_de_converged(void *h);
+int bbo_de_optimize(void *h, int obj, int n, const double *lower, const double *upper,
+                    const double *guess, double *xout, int *fev);
+int bbo_de_geti(void *h, const char *name);
+double bbo_de_getd(void *h, const char *name);
+int bbo_de_getv(void *h, const char *name, double *out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

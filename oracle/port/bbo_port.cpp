@@ -1,0 +1,1334 @@
+/*
+ * ORACLE (test infrastructure, never shipped, never on the product path).
+ *
+ * CPU restatement of the reference's population hot path, written from the algorithm the
+ * reference implements (flat row-major arrays, one struct per family), exporting the same
+ * C API (oracle/bbo_api.h) as the compiled reference (oracle/_ref/libbbo_ref.so).
+ * Every function cites the reference file:line it follows.  The floating-point operation
+ * ORDER is kept identical to the reference on purpose: tests/test_oracle_pinning.py asserts
+ * this port is bit-identical to the compiled reference (state after every phase, every
+ * generation) and tests/golden/ holds vectors generated from the reference itself.
+ *
+ * It additionally records the DE family's *tagged draws* (the reference consumes a
+ * data-dependent number of draws per candidate: jade.cpp:105-183), which is what the GPU
+ * engine replays.
+ *
+ * Build: oracle/Makefile (g++ -O2 -ffp-contract=off).
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../bbo_api.h"
+#include "../objectives_ref.h"
+#include "bbo_rng.h"
+
+namespace {
+
+BboMt19937 g_eng;          /* the one process-global engine (random.hpp:677-680) */
+BboNormal g_test_normal;   /* only for bbo_rng_draw kind 0 */
+bool g_seeded = false;
+
+inline BboMt19937 &eng() {
+    if (!g_seeded) { g_eng.seed(5489u); g_seeded = true; }
+    return g_eng;
+}
+
+/* ---- src/blas.cpp:154-181 (scaled 2-norm, order dependent) */
+double port_nrm2(int n, const double *x) {
+    if (n < 1) return 0.0;
+    if (n == 1) return std::fabs(x[0]);
+    double scale = 0.0, ssq = 1.0;
+    for (int i = 0; i < n; i++) {
+        if (x[i] != 0.0) {
+            const double a = std::fabs(x[i]);
+            if (scale < a) {
+                ssq = 1.0 + ssq * (scale / a) * (scale / a);
+                scale = a;
+            } else {
+                ssq = ssq + (a / scale) * (a / scale);
+            }
+        }
+    }
+    return scale * std::sqrt(ssq);
+}
+
+/* ---- src/math_utils.tpp:27-29,39-51 */
+inline double port_sign(double x, double y) { return y >= 0.0 ? std::fabs(x) : -std::fabs(x); }
+/* NOTE: cmaes.cpp:411,433 call `hypot(p, x)` unqualified with double arguments; overload
+ * resolution picks libm's ::hypot (a non-template exact match) over the template in
+ * math_utils.tpp:39-51, so the reference's QL iteration uses glibc hypot.  Pinned by
+ * tests/test_oracle_pinning.py (using the template form instead breaks bit-equality). */
+inline double port_hypot(double a, double b) { return ::hypot(a, b); }
+
+struct Objective {
+    int id = 0, n = 0;
+    std::vector<double> aux;
+    void bind(int obj, int dim) {
+        id = obj;
+        n = dim;
+        aux.clear();
+        if (obj == BBO_ELLIPSOID) {
+            aux.resize(dim);
+            bbo_ellipsoid_coef(dim, aux.data());
+        }
+    }
+    double operator()(const double *x) const {
+        return bbo_objective(id, n, x, aux.empty() ? nullptr : aux.data());
+    }
+};
+
+/* ---- cma/base_cmaes.cpp:32-43 */
+struct Ring {
+    int cap = 0, head = -1, len = 0;
+    std::vector<double> v;
+    void reset(int c) { cap = c; head = -1; len = 0; v.assign(c, 0.0); }
+    void add(double x) {
+        head = (head + 1) % cap;
+        v[head] = x;
+        if (len < cap) len++;
+    }
+    double get(int i) const { return v[(cap + head - i) % cap]; }
+};
+
+struct RankRec {
+    int index;
+    double value;
+    static bool less(const RankRec &a, const RankRec &b) { return a.value < b.value; }
+};
+
+struct PortCma {
+    /* constructor arguments */
+    int kind, mfev, lambda;
+    double tol, sigma0, eigenrate, alphacov;
+    bool bound, adjustlr;
+    /* problem */
+    Objective f;
+    int n = 0;
+    std::vector<double> lower, upper;
+    /* BaseCmaes state (base_cmaes.h:52-63) */
+    int mit = 0, mu = 0, it = 0, hlen = 0, ik = 0, fev = 0;
+    double mueff = 0, cc = 0, cs = 0, c1 = 0, cmu = 0, damps = 0, chi = 0, sigma = 0, fbest = 0,
+            fworst = 0;
+    Ring best, kth;
+    int ibw[4] = { 0, 0, 0, 0 };
+    double ybw[4] = { 0, 0, 0, 0 };
+    std::vector<double> xmean, xold, weights, tmp, pc, ps, arx;
+    std::vector<RankRec> rank;
+    /* Cmaes / ActiveCmaes state (cmaes.h:42-46, active_cmaes.h:42-44) */
+    int flag = 0, eigenlastev = 0;
+    double eigenfreq = 0;
+    std::vector<double> d, B, C, isC;
+    double cm = 1, cneg = 0, alphaold = 0.5;
+    std::vector<double> ycoeff;
+    /* SepCmaes state (sep_cmaes.h:39-43): C and d are length n */
+    double ccov = 0;
+    BboNormal Z;
+
+    /* ---- cma/base_cmaes.cpp:54-134 */
+    void base_init(const double *guess) {
+        mu = lambda / 2;
+        mit = mfev / lambda;
+        arx.assign((size_t) lambda * n, 0.0);
+        for (int i = 0; i < 4; i++) { ibw[i] = 0; ybw[i] = 0.0; }
+        rank.assign(lambda, RankRec { 0, 0.0 });
+        weights.assign(mu, 0.0);
+        double sum = 0.0;
+        for (int i = 0; i < mu; i++) {
+            weights[i] = std::log(0.5 * (lambda + 1.0)) - std::log(i + 1.0);
+            sum += weights[i];
+        }
+        const double inv = 1.0 / sum;
+        for (int i = 0; i < mu; i++) weights[i] *= inv;
+        double lenw = 0.0;
+        for (int i = 0; i < mu; i++) lenw = lenw + weights[i] * weights[i];
+        mueff = 1.0 / lenw;
+        chi = std::sqrt(n) * (1.0 - 1.0 / (4.0 * n) + 1.0 / (21.0 * n * n));
+        sigma = sigma0;
+        cc = (4.0 + mueff / n) / (n + 4.0 + 2.0 * mueff / n);
+        cs = (mueff + 2.0) / (5.0 + n + mueff);
+        c1 = 2.0 / ((1.3 + n) * (1.3 + n) + mueff);
+        cmu = std::min(1.0 - c1, 2.0 * (mueff - 2.0 + 1.0 / mueff) / ((2.0 + n) * (2.0 + n) + mueff));
+        damps = 1.0 + cs + 2.0 * std::max(0.0, std::sqrt((mueff - 1.0) / (n + 1.0)) - 1.0);
+        pc.assign(n, 0.0);
+        ps.assign(n, 0.0);
+        tmp.assign(n, 0.0);
+        xold.assign(n, 0.0);
+        xmean.assign(guess, guess + n);
+        it = fev = 0;
+        hlen = 10 + (int) std::ceil((30.0 * n) / lambda);
+        ik = (int) std::ceil(0.1 + lambda / 4.0);
+        best.reset(hlen);
+        kth.reset(hlen);
+        fbest = -std::numeric_limits<double>::infinity();
+        fworst = std::numeric_limits<double>::infinity();
+    }
+
+    /* ---- cma/cmaes.cpp:44-63, cma/active_cmaes.cpp:42-69, cma/sep_cmaes.cpp:40-67 */
+    void init(const double *guess) {
+        base_init(guess);
+        if (kind == 2) {
+            cc = 4.0 / (n + 4.0);
+            cs = (mueff + 2.0) / (3.0 + n + mueff);
+            damps = 1.0 + cs + 2.0 * std::max(0.0, std::sqrt((mueff - 1.0) / (n + 1.0)) - 1.0);
+            ccov = 2.0 / ((n + std::sqrt(2.0)) * (n + std::sqrt(2.0)) * mueff);
+            ccov += std::min(1.0, (2.0 * mueff - 1.0) / ((n + 2.0) * (n + 2.0) + mueff))
+                    * (1.0 - 1.0 / mueff);
+            if (adjustlr) ccov *= ((n + 2.0) / 3.0);
+            d.assign(n, 1.0);
+            C.assign(n, 1.0);
+            flag = 0;
+            return;
+        }
+        eigenfreq = eigenrate * lambda / (c1 + cmu) / n;
+        eigenlastev = 0;
+        d.assign(n, 1.0);
+        /* cmaes.cpp:53-56: `_b.resize(...)` / `_c.resize(...)` do NOT clear an already sized
+         * matrix (only `_invsqrtc` is cleared first), so on a re-init of the same object -- every
+         * IPOP/BIPOP restart -- the off-diagonal entries of B and C survive and only the
+         * diagonals are reset to 1 (:58-60).  Reproduced, not fixed. */
+        if (B.size() != (size_t) n * n) B.assign((size_t) n * n, 0.0);
+        if (C.size() != (size_t) n * n) C.assign((size_t) n * n, 0.0);
+        isC.assign((size_t) n * n, 0.0);
+        for (int i = 0; i < n; i++) B[(size_t) i * n + i] = C[(size_t) i * n + i] = isC[(size_t) i * n + i] = 1.0;
+        flag = 0;
+        if (kind == 1) {
+            cm = 1.0;
+            alphaold = 0.5;
+            cc = (4.0 + 0.0 * mueff / n) / (n + 4.0 + 0.0 * 2.0 * mueff / n);
+            cs = (mueff + 2.0) / (3.0 + n + mueff);
+            c1 = alphacov * std::min(1.0, lambda / 6.0) / ((n + 1.3) * (n + 1.3) + mueff);
+            cmu = 1.0 - c1;
+            cmu = std::min(cmu, alphacov * (mueff - 2.0 + 1.0 / mueff)
+                    / ((2.0 + n) * (2.0 + n) + alphacov * mueff / 2.0));
+            cneg = (1.0 - cmu) * (alphacov / 8.0) * mueff / (std::pow(n + 2.0, 1.5) + 2.0 * mueff);
+            damps = 1.0 + cs + 2.0 * std::max(0.0, std::sqrt((mueff - 1.0) / (n + 1.0)) - 1.0);
+            eigenfreq = eigenrate * (1.0 / (c1 + cmu + cneg)) / n;
+            eigenlastev = 0;
+            ycoeff.assign(mu, 0.0);
+        }
+    }
+
+    /* ---- cma/base_cmaes.cpp:136-148 */
+    void set_params(int np, double sg, int mf) {
+        lambda = np;
+        sigma0 = sg;
+        mfev = mf;
+        bound = false;
+    }
+
+    /* ---- cma/cmaes.cpp:65-80 and cma/sep_cmaes.cpp:69-79 (draw order: candidate-major) */
+    void sample() {
+        for (int k = 0; k < lambda; k++) {
+            double *x = &arx[(size_t) k * n];
+            if (kind == 2) {
+                for (int i = 0; i < n; i++) {
+                    x[i] = xmean[i] + sigma * d[i] * Z.draw(eng());
+                    if (bound) x[i] = std::max(lower[i], std::min(x[i], upper[i]));
+                }
+            } else {
+                for (int i = 0; i < n; i++) tmp[i] = d[i] * Z.draw(eng());
+                for (int i = 0; i < n; i++) {
+                    const double *row = &B[(size_t) i * n];
+                    double s = 0.0;
+                    for (int j = 0; j < n; j++) s = s + row[j] * tmp[j];
+                    x[i] = xmean[i] + sigma * s;
+                    if (bound) x[i] = std::max(lower[i], std::min(x[i], upper[i]));
+                }
+            }
+        }
+    }
+
+    /* ---- cma/base_cmaes.cpp:211-230 */
+    void evalsort() {
+        for (int k = 0; k < lambda; k++) {
+            rank[k].index = k;
+            rank[k].value = f(&arx[(size_t) k * n]);
+        }
+        fev += lambda;
+        std::sort(rank.begin(), rank.end(), RankRec::less);
+        ibw[0] = rank[0].index;
+        ibw[1] = rank[1].index;
+        ibw[2] = rank[lambda - 2].index;
+        ibw[3] = rank[lambda - 1].index;
+        ybw[0] = rank[0].value;
+        ybw[1] = rank[1].value;
+        ybw[2] = rank[lambda - 2].value;
+        ybw[3] = rank[lambda - 1].value;
+    }
+
+    /* ---- cma/base_cmaes.cpp:176-189 */
+    void update_sigma() {
+        const double pslen = port_nrm2(n, ps.data());
+        sigma *= std::exp(std::min(1.0, (cs / damps) * (pslen / chi - 1.0)));
+        if (rank[0].value == rank[ik].value) sigma *= std::exp(0.2 + cs / damps);
+        if (it >= hlen && fworst - fbest == 0.0) sigma *= std::exp(0.2 + cs / damps);
+    }
+
+    /* weighted recombination, shared by the three variants
+     * (cmaes.cpp:85-96, active_cmaes.cpp:74-85, sep_cmaes.cpp:84-95) */
+    void recombine() {
+        std::copy(xmean.begin(), xmean.end(), xold.begin());
+        for (int i = 0; i < n; i++) {
+            double sum = 0.0;
+            for (int k = 0; k < mu; k++) sum += weights[k] * arx[(size_t) rank[k].index * n + i];
+            xmean[i] = (kind == 1) ? xold[i] * (1.0 - cm) + sum * cm : sum;
+            if (bound) xmean[i] = std::max(lower[i], std::min(xmean[i], upper[i]));
+        }
+    }
+
+    int hsig_flag() const {
+        const double pslen = port_nrm2(n, ps.data());
+        const double denom = 1.0 - std::pow(1.0 - cs, 2.0 * fev / lambda);
+        return (pslen / std::sqrt(denom) / chi < 1.4 + 2.0 / (n + 1.0)) ? 1 : 0;
+    }
+
+    /* ---- cma/cmaes.cpp:82-149 */
+    void update_vanilla() {
+        recombine();
+        const double csc = std::sqrt(cs * (2.0 - cs) * mueff);
+        for (int i = 0; i < n; i++) {
+            ps[i] *= (1.0 - cs);
+            for (int j = 0; j < n; j++) {
+                ps[i] += csc * isC[(size_t) i * n + j] * (xmean[j] - xold[j]) / sigma;
+            }
+        }
+        const int hsig = hsig_flag();
+        const double ccc = std::sqrt(cc * (2.0 - cc) * mueff);
+        for (int i = 0; i < n; i++) {
+            pc[i] = (1.0 - cc) * pc[i] + hsig * ccc * (xmean[i] - xold[i]) / sigma;
+        }
+        const double c2 = (1.0 - hsig) * cc * (2.0 - cc);
+        for (int i = 0; i < n; i++) {
+            for (int j = 0; j <= i; j++) {
+                double &cij = C[(size_t) i * n + j];
+                double sum = (1.0 - c1 - cmu) * cij + c1 * (pc[i] * pc[j] + c2 * cij);
+                for (int k = 0; k < mu; k++) {
+                    const double *x = &arx[(size_t) rank[k].index * n];
+                    const double di = (x[i] - xold[i]) / sigma;
+                    const double dj = (x[j] - xold[j]) / sigma;
+                    sum += cmu * weights[k] * di * dj;
+                }
+                cij = sum;
+            }
+        }
+        update_sigma();
+        eigen();
+    }
+
+    /* ---- cma/active_cmaes.cpp:71-168 */
+    void update_active() {
+        recombine();
+        const double csc = std::sqrt(cs * (2.0 - cs) * mueff);
+        for (int i = 0; i < n; i++) {
+            ps[i] *= (1.0 - cs);
+            for (int j = 0; j < n; j++) {
+                ps[i] += csc * isC[(size_t) i * n + j] * (xmean[j] - xold[j]) / (cm * sigma);
+            }
+        }
+        const int hsig = hsig_flag();
+        const double ccc = std::sqrt(cc * (2.0 - cc) * mueff);
+        for (int i = 0; i < n; i++) {
+            pc[i] = (1.0 - cc) * pc[i] + hsig * ccc * (xmean[i] - xold[i]) / (cm * sigma);
+        }
+        /* Mahalanobis-norm ratios for the negative update (:115-132) */
+        for (int q = 0; q < mu; q++) {
+            const double *xt = &arx[(size_t) rank[lambda - mu + 1 + q - 1].index * n];
+            const double *xb = &arx[(size_t) rank[lambda - q - 1].index * n];
+            double ssqtop = 0.0, ssqbot = 0.0;
+            for (int j = 0; j < n; j++) {
+                double tt = 0.0, tb = 0.0;
+                for (int l = 0; l < n; l++) {
+                    tt += isC[(size_t) j * n + l] * (xt[l] - xold[l]);
+                    tb += isC[(size_t) j * n + l] * (xb[l] - xold[l]);
+                }
+                ssqtop += tt * tt;
+                ssqbot += tb * tb;
+            }
+            ssqbot = std::max(ssqbot, 1e-8);
+            ycoeff[q] = ssqtop / ssqbot;
+        }
+        const double c2 = (1.0 - hsig) * cc * (2.0 - cc);
+        const double cmu1 = cmu + cneg * (1.0 - alphaold);
+        for (int i = 0; i < n; i++) {
+            for (int j = 0; j <= i; j++) {
+                double &cij = C[(size_t) i * n + j];
+                double sum = (1.0 - c1 - cmu + cneg * alphaold) * cij
+                        + c1 * (pc[i] * pc[j] + c2 * cij);
+                for (int k = 0; k < mu; k++) {
+                    const double *x = &arx[(size_t) rank[k].index * n];
+                    const double di = (x[i] - xold[i]) / sigma;
+                    const double dj = (x[j] - xold[j]) / sigma;
+                    sum += cmu1 * weights[k] * di * dj;
+                }
+                for (int k = 0; k < mu; k++) {
+                    const double *x = &arx[(size_t) rank[lambda - k - 1].index * n];
+                    const double di = (x[i] - xold[i]) / sigma;
+                    const double dj = (x[j] - xold[j]) / sigma;
+                    sum -= cneg * weights[k] * ycoeff[k] * di * dj;
+                }
+                cij = sum;
+            }
+        }
+        update_sigma();
+        eigen();
+    }
+
+    /* ---- cma/sep_cmaes.cpp:81-135 (note :101 multiplies by the VARIANCE c_i: kept) */
+    void update_sep() {
+        recombine();
+        const double csc = std::sqrt(cs * (2.0 - cs) * mueff);
+        for (int i = 0; i < n; i++) {
+            ps[i] *= (1.0 - cs);
+            ps[i] += csc * C[i] * (xmean[i] - xold[i]) / sigma;
+        }
+        const int hsig = hsig_flag();
+        const double ccc = std::sqrt(cc * (2.0 - cc) * mueff);
+        for (int i = 0; i < n; i++) {
+            pc[i] = (1.0 - cc) * pc[i] + hsig * ccc * (xmean[i] - xold[i]) / sigma;
+        }
+        for (int i = 0; i < n; i++) {
+            double sum = (1.0 - ccov) * C[i] + (ccov / mueff) * pc[i] * pc[i];
+            for (int k = 0; k < mu; k++) {
+                const double di = (arx[(size_t) rank[k].index * n + i] - xold[i]) / sigma;
+                sum += ccov * (1.0 - 1.0 / mueff) * weights[k] * di * di;
+            }
+            C[i] = sum;
+            d[i] = std::sqrt(C[i]);
+        }
+        update_sigma();
+    }
+
+    void update() {
+        if (kind == 0) update_vanilla();
+        else if (kind == 1) update_active();
+        else update_sep();
+    }
+
+    /* ---- cma/base_cmaes.cpp:191-209 */
+    void history() {
+        if (it >= mit) return;
+        best.add(rank[0].value);
+        kth.add(rank[ik].value);
+        if (best.len == best.cap) {
+            fbest = std::numeric_limits<double>::infinity();
+            fworst = -std::numeric_limits<double>::infinity();
+            for (double fx : best.v) {
+                fbest = std::min(fx, fbest);
+                fworst = std::max(fx, fworst);
+            }
+        }
+    }
+
+    void iterate() {
+        sample();
+        evalsort();
+        update();
+        history();
+        it++;
+    }
+
+    /* ---- Householder tridiagonalisation, cma/cmaes.cpp:285-381 (EISPACK tred2).
+     * V = B (row-major), d = eigenvalue work vector, e = tmp (off-diagonal). */
+    void tridiagonalize() {
+        double *V = B.data();
+        double *e = tmp.data();
+        auto at = [&](int r, int c) -> double& { return V[(size_t) r * n + c]; };
+        for (int j = 0; j < n; j++) d[j] = at(n - 1, j);
+        for (int i = n - 1; i > 0; i--) {
+            double scale = 0.0, h = 0.0;
+            for (int k = 0; k < i; k++) scale += std::fabs(d[k]);
+            if (scale == 0.0) {
+                e[i] = d[i - 1];
+                for (int j = 0; j < i; j++) {
+                    d[j] = at(i - 1, j);
+                    at(i, j) = 0.0;
+                    at(j, i) = 0.0;
+                }
+            } else {
+                for (int k = 0; k < i; k++) {
+                    d[k] /= scale;
+                    h += d[k] * d[k];
+                }
+                double fq = d[i - 1];
+                double g = std::sqrt(h);
+                if (fq > 0) g = -g;
+                e[i] = scale * g;
+                h = h - fq * g;
+                d[i - 1] = fq - g;
+                for (int j = 0; j < i; j++) e[j] = 0.0;
+                for (int j = 0; j < i; j++) {
+                    fq = d[j];
+                    at(j, i) = fq;
+                    g = e[j] + at(j, j) * fq;
+                    for (int k = j + 1; k <= i - 1; k++) {
+                        g += at(k, j) * d[k];
+                        e[k] += at(k, j) * fq;
+                    }
+                    e[j] = g;
+                }
+                const double invh = 1.0 / h;
+                for (int k = 0; k < i; k++) e[k] *= invh;
+                fq = 0.0;
+                for (int k = 0; k < i; k++) fq = fq + e[k] * d[k];
+                const double hh = fq / (h + h);
+                if (-hh != 0.0) {
+                    for (int k = 0; k < i; k++) e[k] += (-hh) * d[k];
+                }
+                for (int j = 0; j < i; j++) {
+                    fq = d[j];
+                    g = e[j];
+                    for (int k = j; k <= i - 1; k++) at(k, j) -= (fq * e[k] + g * d[k]);
+                    d[j] = at(i - 1, j);
+                    at(i, j) = 0.0;
+                }
+            }
+            d[i] = h;
+        }
+        for (int i = 0; i < n - 1; i++) {
+            at(n - 1, i) = at(i, i);
+            at(i, i) = 1.0;
+            const double h = d[i + 1];
+            if (h != 0.0) {
+                for (int k = 0; k <= i; k++) d[k] = at(k, i + 1) / h;
+                for (int j = 0; j <= i; j++) {
+                    double g = 0.0;
+                    for (int k = 0; k <= i; k++) g += at(k, i + 1) * at(k, j);
+                    for (int k = 0; k <= i; k++) at(k, j) -= g * d[k];
+                }
+            }
+            for (int k = 0; k <= i; k++) at(k, i + 1) = 0.0;
+        }
+        for (int j = 0; j < n; j++) {
+            d[j] = at(n - 1, j);
+            at(n - 1, j) = 0.0;
+        }
+        at(n - 1, n - 1) = 1.0;
+        e[0] = 0.0;
+    }
+
+    /* ---- implicit QL with eigenvector accumulation + ascending sort,
+     * cma/cmaes.cpp:383-478 (EISPACK tql2) */
+    void ql_implicit() {
+        double *V = B.data();
+        double *e = tmp.data();
+        auto at = [&](int r, int c) -> double& { return V[(size_t) r * n + c]; };
+        for (int i = 1; i < n; i++) e[i - 1] = e[i];
+        e[n - 1] = 0.0;
+        double shift = 0.0, tst1 = 0.0;
+        const double eps = std::pow(2.0, -52.0);
+        for (int l = 0; l < n; l++) {
+            tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+            int m = l;
+            for (m = l; m < n; m++) {
+                if (std::fabs(e[m]) <= eps * tst1) break;
+            }
+            if (m >= n) break;
+            if (m > l) {
+                do {
+                    double g = d[l];
+                    double p = (d[l + 1] - g) / (2.0 * e[l]);
+                    double r = port_hypot(p, 1.0);
+                    r = port_sign(r, p);
+                    d[l] = e[l] / (p + r);
+                    d[l + 1] = e[l] * (p + r);
+                    const double dl1 = d[l + 1];
+                    double h = g - d[l];
+                    for (int i = l + 2; i < n; i++) d[i] -= h;
+                    shift += h;
+                    p = d[m];
+                    double c = 1.0, c2 = c, c3 = c;
+                    const double el1 = e[l + 1];
+                    double s = 0.0, s2 = 0.0;
+                    for (int i = m - 1; i >= l; i--) {
+                        c3 = c2;
+                        c2 = c;
+                        s2 = s;
+                        g = c * e[i];
+                        h = c * p;
+                        r = port_hypot(p, e[i]);
+                        e[i + 1] = s * r;
+                        s = e[i] / r;
+                        c = p / r;
+                        p = c * d[i] - s * g;
+                        d[i + 1] = h + s * (c * g + s * d[i]);
+                        for (int k = 0; k < n; k++) {
+                            h = at(k, i + 1);
+                            at(k, i + 1) = s * at(k, i) + c * h;
+                            at(k, i) = c * at(k, i) - s * h;
+                        }
+                    }
+                    p = -s * s2 * c3 * el1 * e[l] / dl1;
+                    e[l] = s * p;
+                    d[l] = c * p;
+                } while (std::fabs(e[l]) > eps * tst1);
+            }
+            d[l] += shift;
+            e[l] = 0.0;
+        }
+        for (int i = 0; i < n - 1; i++) {
+            int k = i;
+            double p = d[i];
+            for (int j = i + 1; j < n; j++) {
+                if (d[j] < p) {
+                    k = j;
+                    p = d[j];
+                }
+            }
+            if (k != i) {
+                d[k] = d[i];
+                d[i] = p;
+                for (int j = 0; j < n; j++) std::swap(at(j, i), at(j, k));
+            }
+        }
+    }
+
+    /* ---- cma/cmaes.cpp:229-283 */
+    void eigen() {
+        if (fev - eigenlastev <= eigenfreq) return;
+        for (int i = 0; i < n; i++) {
+            for (int j = 0; j <= i; j++) {
+                B[(size_t) i * n + j] = B[(size_t) j * n + i] = C[(size_t) i * n + j];
+            }
+        }
+        eigenlastev = fev;
+        tridiagonalize();
+        ql_implicit();
+        if (d[0] <= 0.0) {
+            for (int i = 0; i < n; i++) d[i] = std::max(d[i], 0.0);
+            const double sh = d[n - 1] / 1e14;
+            for (int i = 0; i < n; i++) {
+                C[(size_t) i * n + i] += sh;
+                d[i] += sh;
+            }
+        }
+        if (d[n - 1] > 1e14 * d[0]) {
+            const double sh = d[n - 1] / 1e14 - d[0];
+            for (int i = 0; i < n; i++) {
+                C[(size_t) i * n + i] += sh;
+                d[i] += sh;
+            }
+        }
+        for (int i = 0; i < n; i++) d[i] = std::sqrt(d[i]);
+        for (int i = 0; i < n; i++) {
+            for (int j = 0; j <= i; j++) {
+                double sum = 0.0;
+                for (int k = 0; k < n; k++) sum += B[(size_t) i * n + k] / d[k] * B[(size_t) j * n + k];
+                isC[(size_t) i * n + j] = isC[(size_t) j * n + i] = sum;
+            }
+        }
+    }
+
+    /* ---- cma/cmaes.cpp:151-227 and cma/sep_cmaes.cpp:137-207 */
+    bool converged() {
+        if (it >= mit) { flag = 1; return true; }
+        if (it >= hlen && fworst - fbest < tol) { flag = 2; return true; }
+        if (best.len >= n && kth.len >= n) {
+            int eq = 0;
+            for (int i = 0; i < n; i++) {
+                if (best.get(i) == kth.get(i)) {
+                    eq++;
+                    if (3 * eq >= n) { flag = 3; return true; }
+                }
+            }
+        }
+        bool all = true;
+        for (int i = 0; i < n; i++) {
+            const double spread = (kind == 2) ? d[i] : std::sqrt(C[(size_t) i * n + i]);
+            if (std::max(pc[i], spread) * sigma / sigma0 >= tol) { all = false; break; }
+        }
+        if (all) { flag = 4; return true; }
+        if (sigma / sigma0 > 1.0e20 * d[n - 1]) { flag = 5; return true; }
+        if (d[n - 1] > 1.0e7 * d[0]) { flag = 7; return true; }
+        const int iaxis = n - 1 - ((it - 1) % n);
+        if (kind == 2) {
+            if (xmean[iaxis] == xmean[iaxis] + 0.1 * sigma * d[iaxis]) { flag = 8; return true; }
+            for (int i = 0; i < n; i++) {
+                if (xmean[i] == xmean[i] + 0.2 * sigma * d[i]) { flag = 9; return true; }
+            }
+            return false;
+        }
+        all = true;
+        for (int i = 0; i < n; i++) {
+            /* reads ROW iaxis of B, as the reference does (cmaes.cpp:205-217) */
+            if (xmean[i] != xmean[i] + 0.1 * sigma * d[iaxis] * B[(size_t) iaxis * n + i]) {
+                all = false;
+                break;
+            }
+        }
+        if (all) { flag = 8; return true; }
+        for (int i = 0; i < n; i++) {
+            if (xmean[i] == xmean[i] + 0.2 * sigma * std::sqrt(C[(size_t) i * n + i])) {
+                flag = 9;
+                return true;
+            }
+        }
+        return false;
+    }
+
+    /* ---- cma/base_cmaes.cpp:162-174,232-238 */
+    bool optimize(const double *guess, std::vector<double> &xout) {
+        init(guess);
+        bool conv = false;
+        while (fev < mfev) {
+            iterate();
+            if (converged()) { conv = true; break; }
+        }
+        best_solution(xout);
+        return conv;
+    }
+
+    void best_solution(std::vector<double> &xout) const {
+        if (it <= 0) xout = xmean;
+        else xout.assign(arx.begin() + (size_t) ibw[0] * n, arx.begin() + (size_t) (ibw[0] + 1) * n);
+    }
+};
+
+void cma_bind(PortCma *p, int obj, int n, const double *lower, const double *upper) {
+    p->n = n;
+    p->f.bind(obj, n);
+    p->lower.assign(lower, lower + n);
+    p->upper.assign(upper, upper + n);
+}
+
+int put(const std::vector<double> &v, double *out, int cap) {
+    for (int i = 0; i < (int) v.size() && i < cap; i++) out[i] = v[i];
+    return (int) v.size();
+}
+
+/* ======================================================================================
+ * DE family: JADE (de/jade.cpp) and L-SHADE (de/shade.cpp), with the tagged-draw recorder.
+ * ==================================================================================== */
+struct PortDe {
+    int kind, mfev, npinit, h, npmin;
+    double tol, pelite, cdamp, sigma_cr;
+    bool archive, repaircr;
+    Objective f;
+    int n = 0, np = 0, fev = 0, kslot = 1;
+    double mucr = 0.5, muf = 0.5;
+    std::vector<double> lower, upper, work, MCR, MF;
+    std::vector<double> sw_x, sw_f;           /* np x n, np */
+    std::vector<std::vector<double>> arch;
+    BboNormal Z;
+    /* tagged draws of the last generation (what the GPU engine replays) */
+    std::vector<double> t_zcr, t_cauchy, t_ibest, t_r1, t_r2, t_jrand, t_slot, t_succ, t_u,
+            t_ri, t_pi, t_trim, t_F, t_CR, t_ftrial;
+
+    double cauchy() { return std::tan(M_PI * (eng().uniform_real(0.0, 1.0) - 0.5)); } /* jade.cpp:292-294 */
+
+    /* std::sort(_swarm, point::compare_fitness): the permutation produced by introsort
+     * depends only on comparison outcomes, so sorting (f, position) records is equivalent */
+    void sort_swarm() {
+        struct Rec { double f; int pos; };
+        std::vector<Rec> rec(np);
+        for (int i = 0; i < np; i++) rec[i] = Rec { sw_f[i], i };
+        std::sort(rec.begin(), rec.end(), [](const Rec &a, const Rec &b) { return a.f < b.f; });
+        std::vector<double> nx((size_t) np * n), nf(np);
+        for (int i = 0; i < np; i++) {
+            nf[i] = rec[i].f;
+            std::copy(sw_x.begin() + (size_t) rec[i].pos * n, sw_x.begin() + (size_t) (rec[i].pos + 1) * n,
+                    nx.begin() + (size_t) i * n);
+        }
+        sw_x.swap(nx);
+        sw_f.swap(nf);
+    }
+
+    /* ---- de/jade.cpp:64-96, de/shade.cpp:56-94 */
+    void init() {
+        fev = 0;
+        mucr = muf = 0.5;
+        MCR.assign(h, 0.5);
+        MF.assign(h, 0.5);
+        work.assign(n, 0.0);
+        arch.clear();
+        kslot = 1;
+        np = npinit;
+        sw_x.assign((size_t) np * n, 0.0);
+        sw_f.assign(np, 0.0);
+        for (int i = 0; i < np; i++) {
+            double *x = &sw_x[(size_t) i * n];
+            for (int j = 0; j < n; j++) x[j] = eng().uniform_real(lower[j], upper[j]);
+            sw_f[i] = f(x);
+            fev++;
+        }
+        if (kind == 1) sort_swarm();
+    }
+
+    void clear_trace(int cnt) {
+        for (auto *v : { &t_zcr, &t_cauchy, &t_ibest, &t_r1, &t_r2, &t_jrand, &t_slot, &t_succ,
+                &t_ri, &t_pi, &t_F, &t_CR, &t_ftrial }) v->assign(cnt, 0.0);
+        t_u.assign((size_t) cnt * n, 0.0);
+        t_trim.clear();
+    }
+
+    /* ---- de/jade.cpp:247-264 == de/shade.cpp:277-294 */
+    double mutate(int i, const double *x, const double *bestx, const double *xr1,
+            const double *xr2, double F, double CR) {
+        const int jr = eng().uniform_int(0, n - 1);
+        t_jrand[i] = jr;
+        double cr1 = 0.0;
+        for (int j = 0; j < n; j++) {
+            bool cross = (j == jr);
+            if (!cross) {
+                const double u = eng().uniform_real(0.0, 1.0);
+                t_u[(size_t) i * n + j] = u;
+                cross = u < CR;
+            }
+            if (cross) {
+                work[j] = x[j] + F * (bestx[j] - x[j]) + F * (xr1[j] - xr2[j]);
+                cr1 += 1.0;
+            } else {
+                work[j] = x[j];
+            }
+        }
+        return repaircr ? cr1 / n : CR;
+    }
+
+    /* ---- de/jade.cpp:98-206 and de/shade.cpp:96-236 */
+    void iterate() {
+        if (kind == 0) sort_swarm();
+        clear_trace(np);
+        std::vector<double> scr, sf, sw;
+        for (int i = 0; i < np; i++) {
+            double CR, F;
+            int nelite;
+            if (kind == 0) {
+                const double z = Z.draw(eng());
+                t_zcr[i] = z;
+                CR = z * 0.1 + mucr;
+                CR = std::max(0.0, std::min(CR, 1.0));
+                F = -1.0;
+                double c = 0.0;
+                while (F < 0.0) {
+                    c = cauchy();
+                    F = c * 0.1 + muf;
+                    F = std::min(F, 1.0);
+                }
+                t_cauchy[i] = c;
+                nelite = std::max(1, (int) (pelite * np));
+            } else {
+                const int ri = eng().uniform_int(0, h - 1);
+                t_ri[i] = ri;
+                const double z = Z.draw(eng());
+                t_zcr[i] = z;
+                CR = std::max(0.0, std::min(z * 0.1 + MCR[ri], 1.0));
+                double c = cauchy();
+                F = std::min(1.0, c * 0.1 + MF[ri]);
+                while (F <= 0) {
+                    c = cauchy();
+                    F = std::min(1.0, c * 0.1 + MF[ri]);
+                }
+                t_cauchy[i] = c;
+                const double pi = eng().uniform_real(std::min(2.0 / n, 0.2), 0.2);
+                t_pi[i] = pi;
+                nelite = std::max(1, (int) (pi * np));
+            }
+            t_F[i] = F;
+            t_CR[i] = CR;
+            const int ibest = eng().uniform_int(0, nelite - 1);
+            int r1 = i;
+            while (r1 == i) r1 = eng().uniform_int(0, np - 1);
+            int r2 = i;
+            const int larch = (int) arch.size();
+            while (r2 == i || r2 == r1) r2 = eng().uniform_int(0, np + larch - 1);
+            t_ibest[i] = ibest;
+            t_r1[i] = r1;
+            t_r2[i] = r2;
+            t_slot[i] = -1;
+            double *xi = &sw_x[(size_t) i * n];
+            const double *x2 = (r2 >= np) ? arch[r2 - np].data() : &sw_x[(size_t) r2 * n];
+            const double cr1 = mutate(i, xi, &sw_x[(size_t) ibest * n], &sw_x[(size_t) r1 * n], x2, F, CR);
+            for (int j = 0; j < n; j++) {
+                if (work[j] < lower[j]) work[j] = (lower[j] + xi[j]) / 2.0;
+                else if (work[j] > upper[j]) work[j] = (upper[j] + xi[j]) / 2.0;
+            }
+            const double fw = f(work.data());
+            t_ftrial[i] = fw;
+            fev++;
+            if (fw <= sw_f[i]) {
+                t_succ[i] = 1;
+                const bool strict = fw < sw_f[i];
+                if (archive && (kind == 0 || strict)) {
+                    if (larch >= np) {
+                        const int slot = eng().uniform_int(0, np - 1);
+                        t_slot[i] = slot;
+                        std::copy(xi, xi + n, arch[slot].begin());
+                    } else {
+                        arch.emplace_back(xi, xi + n);
+                    }
+                }
+                if (kind == 0) {
+                    scr.push_back(cr1);
+                    sf.push_back(F);
+                } else if (strict) {
+                    t_succ[i] = 2;
+                    scr.push_back(cr1);
+                    sf.push_back(F);
+                    sw.push_back(sw_f[i] - fw);
+                }
+                sw_f[i] = fw;
+                std::copy(work.begin(), work.end(), xi);
+            }
+        }
+        const int ns = (int) scr.size();
+        if (kind == 0) {
+            /* jade.cpp:186-205 with meanPow :266-277 and std :279-290 (running means) */
+            double meancr = 0.0, meanf = 0.0;
+            if (ns > 0) {
+                double mean = 0.0, m2 = 0.0;
+                for (int i = 0; i < ns; i++) {
+                    const double dl = scr[i] - mean;
+                    mean += dl / (i + 1.0);
+                    m2 += dl * (scr[i] - mean);
+                }
+                const double sd = std::sqrt(m2 / ns);
+                double p1 = 0.0, p2 = 0.0;
+                for (int i = 0; i < ns; i++) {
+                    p1 += (scr[i] - p1) / (i + 1.0);
+                    p2 += (scr[i] * scr[i] - p2) / (i + 1.0);
+                }
+                meancr = (sd > sigma_cr) ? std::sqrt(p2) : p1;
+                double f1 = 0.0, f2 = 0.0;
+                for (int i = 0; i < ns; i++) {
+                    f1 += (sf[i] - f1) / (i + 1.0);
+                    f2 += (sf[i] * sf[i] - f2) / (i + 1.0);
+                }
+                meanf = f2 / f1;
+            }
+            mucr = (1.0 - cdamp) * mucr + cdamp * meancr;
+            muf = (1.0 - cdamp) * muf + cdamp * meanf;
+            return;
+        }
+        /* shade.cpp:186-235 */
+        if (ns > 0) {
+            double crn = 0.0, crd = 0.0, fn = 0.0, fd = 0.0;
+            for (int i = 0; i < ns; i++) {
+                crn += sw[i] * scr[i];
+                crd += sw[i];
+                fn += sw[i] * sf[i] * sf[i];
+                fd += sw[i] * sf[i];
+            }
+            MCR[kslot - 1] = crn / crd;
+            MF[kslot - 1] = fn / fd;
+            kslot++;
+            if (kslot > h) kslot = 1;
+        }
+        sort_swarm();
+        const int npnew = (int) std::round((npmin - npinit) * ((1.0 * fev) / mfev) + npinit);
+        if (npnew < np) {
+            sw_x.resize((size_t) npnew * n);
+            sw_f.resize(npnew);
+            np = npnew;
+        }
+        if (archive) {
+            int larch = (int) arch.size();
+            while (larch > npnew) {
+                const int r = eng().uniform_int(0, larch - 1);
+                t_trim.push_back(r);
+                arch.erase(arch.begin() + r);
+                --larch;
+            }
+        }
+    }
+
+    /* ---- de/jade.cpp:228-245 == de/shade.cpp:258-275 */
+    bool converged() const {
+        int count = 0;
+        double mean = 0.0, m2 = 0.0;
+        for (int i = 0; i < np; i++) {
+            const double r = port_nrm2(n, &sw_x[(size_t) i * n]);
+            count++;
+            const double dl = r - mean;
+            mean += dl / count;
+            m2 += dl * (r - mean);
+        }
+        return m2 <= (np - 1) * tol * tol;
+    }
+
+    bool optimize(std::vector<double> &xout) {
+        init();
+        bool conv = false;
+        while (fev < mfev) {
+            iterate();
+            if (converged()) { conv = true; break; }
+        }
+        sort_swarm();
+        xout.assign(sw_x.begin(), sw_x.begin() + n);
+        return conv;
+    }
+};
+
+} // namespace
+
+extern "C" {
+
+const char *bbo_kind(void) { return "port"; }
+
+void bbo_seed(uint32_t s) {
+    g_eng.seed(s);
+    g_seeded = true;
+    g_test_normal.reset();
+}
+
+void bbo_rng_draw(int kind, int count, double a, double b, double *out) {
+    for (int i = 0; i < count; i++) {
+        switch (kind) {
+        case 0: out[i] = g_test_normal.draw(eng()); break;
+        case 1: out[i] = eng().uniform_real(a, b); break;
+        case 2: out[i] = (double) eng().uniform_int((int) a, (int) b); break;
+        default: out[i] = (double) eng().next(); break;
+        }
+    }
+}
+
+double bbo_eval(int obj, int n, const double *x) {
+    Objective f;
+    f.bind(obj, n);
+    return f(x);
+}
+
+void *bbo_cma_new(int kind, int mfev, double tol, int np, double sigma0, int bound,
+        double eigenrate, double alphacov, int adjustlr) {
+    PortCma *p = new PortCma();
+    p->kind = kind;
+    p->mfev = mfev;
+    p->tol = tol;
+    p->lambda = np;
+    p->sigma0 = sigma0;
+    p->bound = bound != 0;
+    p->eigenrate = eigenrate;
+    p->alphacov = alphacov;
+    p->adjustlr = adjustlr != 0;
+    return p;
+}
+
+void bbo_cma_free(void *h) { delete static_cast<PortCma*>(h); }
+
+void bbo_cma_init(void *h, int obj, int n, const double *lower, const double *upper,
+        const double *guess) {
+    PortCma *p = static_cast<PortCma*>(h);
+    cma_bind(p, obj, n, lower, upper);
+    p->init(guess);
+}
+
+void bbo_cma_set_params(void *h, int np, double sigma, int mfev) {
+    static_cast<PortCma*>(h)->set_params(np, sigma, mfev);
+}
+void bbo_cma_sample(void *h) { static_cast<PortCma*>(h)->sample(); }
+void bbo_cma_evalsort(void *h) { static_cast<PortCma*>(h)->evalsort(); }
+void bbo_cma_update(void *h) { static_cast<PortCma*>(h)->update(); }
+void bbo_cma_history(void *h) {
+    PortCma *p = static_cast<PortCma*>(h);
+    p->history();
+    p->it++;
+}
+void bbo_cma_iterate(void *h) { static_cast<PortCma*>(h)->iterate(); }
+int bbo_cma_converged(void *h) { return static_cast<PortCma*>(h)->converged() ? 1 : 0; }
+
+int bbo_cma_optimize(void *h, int obj, int n, const double *lower, const double *upper,
+        const double *guess, double *xout, int *fev) {
+    PortCma *p = static_cast<PortCma*>(h);
+    cma_bind(p, obj, n, lower, upper);
+    std::vector<double> x;
+    const bool conv = p->optimize(guess, x);
+    for (int i = 0; i < n; i++) xout[i] = x[i];
+    *fev = p->fev;
+    return conv ? 1 : 0;
+}
+
+int bbo_cma_geti(void *h, const char *name) {
+    PortCma *p = static_cast<PortCma*>(h);
+    const std::string k(name);
+    if (k == "n") return p->n;
+    if (k == "lambda") return p->lambda;
+    if (k == "mu") return p->mu;
+    if (k == "it") return p->it;
+    if (k == "fev") return p->fev;
+    if (k == "mfev") return p->mfev;
+    if (k == "mit") return p->mit;
+    if (k == "hlen") return p->hlen;
+    if (k == "ik") return p->ik;
+    if (k == "bound") return p->bound ? 1 : 0;
+    if (k == "best_len") return p->best.len;
+    if (k == "flag") return p->flag;
+    if (k == "eigenlastev") return p->eigenlastev;
+    return -1;
+}
+
+double bbo_cma_getd(void *h, const char *name) {
+    PortCma *p = static_cast<PortCma*>(h);
+    const std::string k(name);
+    if (k == "sigma") return p->sigma;
+    if (k == "sigma0") return p->sigma0;
+    if (k == "tol") return p->tol;
+    if (k == "mueff") return p->mueff;
+    if (k == "cc") return p->cc;
+    if (k == "cs") return p->cs;
+    if (k == "c1") return p->c1;
+    if (k == "cmu") return p->cmu;
+    if (k == "damps") return p->damps;
+    if (k == "chi") return p->chi;
+    if (k == "fbest") return p->fbest;
+    if (k == "fworst") return p->fworst;
+    if (k == "eigenfreq") return p->eigenfreq;
+    if (k == "cneg") return p->cneg;
+    if (k == "cm") return p->cm;
+    if (k == "alphaold") return p->alphaold;
+    if (k == "ccov") return p->ccov;
+    return NAN;
+}
+
+int bbo_cma_getv(void *h, const char *name, double *out, int cap) {
+    PortCma *p = static_cast<PortCma*>(h);
+    const std::string k(name);
+    if (k == "xmean") return put(p->xmean, out, cap);
+    if (k == "xold") return put(p->xold, out, cap);
+    if (k == "pc") return put(p->pc, out, cap);
+    if (k == "ps") return put(p->ps, out, cap);
+    if (k == "weights") return put(p->weights, out, cap);
+    if (k == "arx") return put(p->arx, out, cap);
+    if (k == "hist_best") return put(p->best.v, out, cap);
+    if (k == "hist_kth") return put(p->kth.v, out, cap);
+    if (k == "D") return put(p->d, out, cap);
+    if (k == "C") return put(p->C, out, cap);
+    if (k == "B" && p->kind != 2) return put(p->B, out, cap);
+    if (k == "invsqrtC" && p->kind != 2) return put(p->isC, out, cap);
+    if (k == "ycoeff" && p->kind == 1) return put(p->ycoeff, out, cap);
+    if (k == "ybw") {
+        for (int i = 0; i < 4 && i < cap; i++) out[i] = p->ybw[i];
+        return 4;
+    }
+    if (k == "ibw") {
+        for (int i = 0; i < 4 && i < cap; i++) out[i] = p->ibw[i];
+        return 4;
+    }
+    if (k == "fit_val") {
+        for (int i = 0; i < p->lambda && i < cap; i++) out[i] = p->rank[i].value;
+        return p->lambda;
+    }
+    if (k == "fit_idx") {
+        for (int i = 0; i < p->lambda && i < cap; i++) out[i] = p->rank[i].index;
+        return p->lambda;
+    }
+    return -1;
+}
+
+void bbo_cma_reset_z(void *h) { static_cast<PortCma*>(h)->Z.reset(); }
+
+/* ---- restart drivers: cma/ipop_cmaes.cpp:65-189 and cma/bipop_cmaes.cpp:61-267 */
+int bbo_restart_optimize(int kind, void *base, int mfev, double sigma0, int flag,
+        double ksigmadec, int boundlambda, int maxlargeruns, double kbudget, int obj, int n,
+        const double *lower, const double *upper, const double *guess, double *xout, int *fevout,
+        double *trace, int cap) {
+    PortCma *b = static_cast<PortCma*>(base);
+    cma_bind(b, obj, n, lower, upper);
+    int rows = 0;
+    auto log_row = [&](int lam, double sg, double fx, int fevt, int regime) {
+        if (trace && rows < cap) {
+            double *r = trace + (size_t) rows * 5;
+            r[0] = lam; r[1] = sg; r[2] = fx; r[3] = fevt; r[4] = regime;
+        }
+        rows++;
+    };
+    int fev = 0;
+    auto max_evals = [&](int lam) {
+        const int maxit = (int) (100.0 + 50.0 * (n + 3) * (n + 3) / std::sqrt(1.0 * lam));
+        return std::min(maxit * lam, mfev - fev);
+    };
+    std::vector<double> x, xbest, x0(n);
+    double fx, fbest;
+    const int lambdadef = 4 + (int) (3.0 * std::log(1.0 * n));
+    auto run = [&](int lam, double sg, int budget, const double *start) {
+        b->set_params(lam, sg, budget);
+        b->optimize(start, x);
+        fx = b->f(x.data());
+        fev += b->fev + 1;
+        return b->fev;
+    };
+    if (kind == 0) {
+        /* IPOP / NIPOP */
+        int lambda = lambdadef;
+        const int lambdamax = 10 * n * n;
+        double sigma = sigma0;
+        run(lambdadef, sigma0, max_evals(lambdadef), guess);
+        fbest = fx;
+        xbest = x;
+        log_row(lambdadef, sigma0, fx, fev, 0);
+        while (fev < mfev) {
+            for (int i = 0; i < n; i++) x0[i] = eng().uniform_real(lower[i], upper[i]);
+            if (boundlambda) {
+                lambda <<= 1;
+                if (lambda > lambdamax) {
+                    if (lambda - lambdamax < lambdamax - (lambda >> 1)) lambda = lambdamax;
+                    else lambda = lambdadef;
+                }
+            } else {
+                lambda <<= 1;
+            }
+            if (flag) {
+                sigma /= ksigmadec;
+                sigma = std::max(sigma, 0.01 * sigma0);
+            }
+            run(lambda, sigma, max_evals(lambda), x0.data());
+            if (fx < fbest) {
+                fbest = fx;
+                xbest = x;
+            }
+            log_row(lambda, sigma, fx, fev, 0);
+        }
+    } else {
+        /* BIPOP / NBIPOP */
+        run(lambdadef, sigma0, max_evals(lambdadef), guess);
+        int largebudget = 0, smallbudget = 0, largerestarts = 0, bestregime = 1;
+        int largelambda = 0;
+        fbest = fx;
+        xbest = x;
+        log_row(lambdadef, sigma0, fx, fev, 0);
+        while (true) {
+            for (int i = 0; i < n; i++) x0[i] = eng().uniform_real(lower[i], upper[i]);
+            int regime;
+            if (flag) {
+                if (bestregime == 1) regime = (largebudget <= smallbudget * kbudget) ? 1 : 2;
+                else regime = (smallbudget <= kbudget * largebudget) ? 2 : 1;
+            } else {
+                regime = (largebudget <= smallbudget) ? 1 : 2;
+            }
+            if (regime == 1) {
+                largelambda = (int) (lambdadef * std::pow(2, largerestarts + 1));
+                double largesigma = sigma0;
+                if (flag) {
+                    largesigma = sigma0 * std::pow(1.0 / ksigmadec, largerestarts + 1);
+                    largesigma = std::max(largesigma, 0.01 * sigma0);
+                }
+                const int used = run(largelambda, largesigma, max_evals(largelambda), x0.data());
+                if (fx < fbest) { fbest = fx; xbest = x; bestregime = 1; }
+                largebudget += used;
+                largerestarts++;
+                log_row(largelambda, largesigma, fx, fev, 1);
+            } else {
+                const double u = eng().uniform_real(0.0, 1.0);
+                const int smalllambda = (int) (lambdadef * std::pow((0.5 * largelambda) / lambdadef, u * u));
+                const double smallsigma = sigma0 * std::pow(10.0, -2.0 * eng().uniform_real(0.0, 1.0));
+                int budget = max_evals(smalllambda);
+                budget = std::min(budget, largebudget >> 1);
+                const int used = run(smalllambda, smallsigma, budget, x0.data());
+                if (fx < fbest) { fbest = fx; xbest = x; bestregime = 2; }
+                smallbudget += used;
+                log_row(smalllambda, smallsigma, fx, fev, 2);
+            }
+            if (largerestarts >= maxlargeruns) break;
+            if (fev >= mfev) break;
+        }
+    }
+    for (int i = 0; i < n; i++) xout[i] = xbest[i];
+    *fevout = fev;
+    return rows;
+}
+
+void *bbo_de_new(int kind, int mfev, int np, double tol, int archive, int repaircr,
+        double pelite, double cdamp, double sigma, int h, int npmin) {
+    PortDe *p = new PortDe();
+    p->kind = kind;
+    p->mfev = mfev;
+    p->npinit = np;
+    p->tol = tol;
+    p->archive = archive != 0;
+    p->repaircr = repaircr != 0;
+    p->pelite = pelite;
+    p->cdamp = cdamp;
+    p->sigma_cr = sigma;
+    p->h = (kind == 1) ? h : 1;
+    p->npmin = npmin;
+    return p;
+}
+
+void bbo_de_free(void *h) { delete static_cast<PortDe*>(h); }
+
+static void de_bind(PortDe *p, int obj, int n, const double *lower, const double *upper) {
+    p->n = n;
+    p->f.bind(obj, n);
+    p->lower.assign(lower, lower + n);
+    p->upper.assign(upper, upper + n);
+}
+
+void bbo_de_init(void *h, int obj, int n, const double *lower, const double *upper,
+        const double *guess) {
+    (void) guess; /* unused by the reference too (jade.cpp:64-96) */
+    PortDe *p = static_cast<PortDe*>(h);
+    de_bind(p, obj, n, lower, upper);
+    p->init();
+}
+
+void bbo_de_iterate(void *h) { static_cast<PortDe*>(h)->iterate(); }
+int bbo_de_converged(void *h) { return static_cast<PortDe*>(h)->converged() ? 1 : 0; }
+
+int bbo_de_optimize(void *h, int obj, int n, const double *lower, const double *upper,
+        const double *guess, double *xout, int *fev) {
+    (void) guess;
+    PortDe *p = static_cast<PortDe*>(h);
+    de_bind(p, obj, n, lower, upper);
+    std::vector<double> x;
+    const bool conv = p->optimize(x);
+    for (int i = 0; i < n; i++) xout[i] = x[i];
+    *fev = p->fev;
+    return conv ? 1 : 0;
+}
+
+int bbo_de_geti(void *h, const char *name) {
+    PortDe *p = static_cast<PortDe*>(h);
+    const std::string k(name);
+    if (k == "n") return p->n;
+    if (k == "np") return p->np;
+    if (k == "fev") return p->fev;
+    if (k == "larch") return (int) p->arch.size();
+    if (k == "k") return p->kslot;
+    return -1;
+}
+
+double bbo_de_getd(void *h, const char *name) {
+    PortDe *p = static_cast<PortDe*>(h);
+    const std::string k(name);
+    if (k == "mucr") return p->mucr;
+    if (k == "muf") return p->muf;
+    return NAN;
+}
+
+int bbo_de_getv(void *h, const char *name, double *out, int cap) {
+    PortDe *p = static_cast<PortDe*>(h);
+    const std::string k(name);
+    if (k == "swarm_x") return put(p->sw_x, out, cap);
+    if (k == "swarm_f") return put(p->sw_f, out, cap);
+    if (k == "arch") {
+        int len = 0;
+        for (const auto &row : p->arch)
+            for (double v : row) {
+                if (len < cap) out[len] = v;
+                len++;
+            }
+        return len;
+    }
+    if (k == "MCR" && p->kind == 1) return put(p->MCR, out, cap);
+    if (k == "MF" && p->kind == 1) return put(p->MF, out, cap);
+    /* tagged draws of the generation just run (port only) */
+    if (k == "t_zcr") return put(p->t_zcr, out, cap);
+    if (k == "t_cauchy") return put(p->t_cauchy, out, cap);
+    if (k == "t_ibest") return put(p->t_ibest, out, cap);
+    if (k == "t_r1") return put(p->t_r1, out, cap);
+    if (k == "t_r2") return put(p->t_r2, out, cap);
+    if (k == "t_jrand") return put(p->t_jrand, out, cap);
+    if (k == "t_slot") return put(p->t_slot, out, cap);
+    if (k == "t_succ") return put(p->t_succ, out, cap);
+    if (k == "t_u") return put(p->t_u, out, cap);
+    if (k == "t_ri") return put(p->t_ri, out, cap);
+    if (k == "t_pi") return put(p->t_pi, out, cap);
+    if (k == "t_trim") return put(p->t_trim, out, cap);
+    if (k == "t_F") return put(p->t_F, out, cap);
+    if (k == "t_CR") return put(p->t_CR, out, cap);
+    if (k == "t_ftrial") return put(p->t_ftrial, out, cap);
+    return -1;
+}
+
+} // extern "C"
