@@ -1,0 +1,350 @@
+"""ctypes view of the C ABI in include/bbgpu.h (libbbgpu.so, built in-tree by build.py).
+
+This is the thinnest possible binding: argument types, status checking, numpy in/out.  It is
+what the parity tests and bench.py call so that they exercise exactly the symbols a host
+language binding would.  There is no fallback of any kind: if the library is missing or no CUDA
+device is usable, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbbgpu.so")
+
+OBJ_SPHERE, OBJ_ELLIPSOID, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY = range(5)
+CMA_FULL, CMA_ACTIVE, CMA_SEP = range(3)
+DE_JADE, DE_SHADE = range(2)
+(F_XMEAN, F_XOLD, F_PC, F_PS, F_C, F_B, F_D, F_INVSQRTC, F_ARX, F_Z, F_FITNESS, F_RANKVAL, F_YCOEFF,
+ F_WEIGHTS) = range(14)
+
+c_dp = ctypes.c_void_p
+
+
+class BbgpuError(RuntimeError):
+    pass
+
+
+class CmaConfig(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("n", ctypes.c_int), ("lambda_", ctypes.c_int), ("mu", ctypes.c_int),
+                ("bound", ctypes.c_int), ("shard_rank", ctypes.c_int), ("shard_count", ctypes.c_int),
+                ("seed", ctypes.c_uint64),
+                ("cc", ctypes.c_double), ("cs", ctypes.c_double), ("c1", ctypes.c_double), ("cmu", ctypes.c_double),
+                ("mueff", ctypes.c_double), ("chi", ctypes.c_double),
+                ("cneg", ctypes.c_double), ("alphaold", ctypes.c_double), ("cm", ctypes.c_double),
+                ("ccov", ctypes.c_double)]
+
+
+class CmaReport(ctypes.Structure):
+    _fields_ = [("ibw", ctypes.c_int32 * 4), ("ybw", ctypes.c_double * 4), ("f_kth", ctypes.c_double),
+                ("pslen", ctypes.c_double), ("hsig", ctypes.c_int32), ("eig_info", ctypes.c_int32),
+                ("d_min", ctypes.c_double), ("d_max", ctypes.c_double), ("tolx_max", ctypes.c_double),
+                ("noeffect_axis", ctypes.c_int32), ("noeffect_coor", ctypes.c_int32), ("eig_resid", ctypes.c_double)]
+
+
+class DeConfig(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("n", ctypes.c_int), ("np", ctypes.c_int), ("archive", ctypes.c_int),
+                ("repaircr", ctypes.c_int), ("h", ctypes.c_int), ("npmin", ctypes.c_int), ("mfev", ctypes.c_int),
+                ("pelite", ctypes.c_double), ("cdamp", ctypes.c_double), ("sigma", ctypes.c_double),
+                ("seed", ctypes.c_uint64)]
+
+
+class DeDraws(ctypes.Structure):
+    _fields_ = [("zcr", c_dp), ("cauchy", c_dp), ("ibest", c_dp), ("r1", c_dp), ("r2", c_dp), ("jrand", c_dp),
+                ("slot", c_dp), ("u", c_dp), ("ri", c_dp), ("pi", c_dp), ("trim", c_dp), ("ntrim", ctypes.c_int)]
+
+
+class DeReport(ctypes.Structure):
+    _fields_ = [("np", ctypes.c_int32), ("larch", ctypes.c_int32), ("nsucc", ctypes.c_int32), ("fev", ctypes.c_int32),
+                ("rounds", ctypes.c_int32), ("kslot", ctypes.c_int32), ("mucr", ctypes.c_double),
+                ("muf", ctypes.c_double), ("fbest", ctypes.c_double), ("radius_m2", ctypes.c_double)]
+
+
+DEVICE_OBJECTIVE_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_dp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_dp, c_dp, c_dp)
+HOST_OBJECTIVE_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_dp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_dp, c_dp)
+
+_lib = None
+
+
+def symbols_in_header():
+    """Every function name declared in include/bbgpu.h (used by the CPU export test)."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(_HERE), "include", "bbgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(bbgpu_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def lib():
+    """Load libbbgpu.so (no GPU needed to load; every compute entry point needs one)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BbgpuError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                         "There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    i, i64, u64, d, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
+    P = ctypes.POINTER
+    L.bbgpu_version.restype = i
+    L.bbgpu_last_error.restype = ctypes.c_char_p
+    L.bbgpu_ctx_create.argtypes = [i, vp, P(vp)]
+    L.bbgpu_ctx_destroy.argtypes = [vp]
+    L.bbgpu_ctx_sync.argtypes = [vp]
+    L.bbgpu_ctx_stream.argtypes = [vp]
+    L.bbgpu_ctx_stream.restype = vp
+    L.bbgpu_ctx_launch_count.argtypes = [vp]
+    L.bbgpu_ctx_launch_count.restype = i64
+    L.bbgpu_objective_builtin.argtypes = [vp, i, i, P(vp)]
+    L.bbgpu_objective_device.argtypes = [vp, DEVICE_OBJECTIVE_FN, vp, i, P(vp)]
+    L.bbgpu_objective_host.argtypes = [vp, HOST_OBJECTIVE_FN, vp, i, P(vp)]
+    L.bbgpu_objective_destroy.argtypes = [vp]
+    L.bbgpu_eval.argtypes = [vp, vp, vp, i64, i, vp]
+    L.bbgpu_eval_host.argtypes = [vp, vp, vp, i, vp]
+    L.bbgpu_cma_create.argtypes = [vp, P(CmaConfig), vp, vp, vp, P(vp)]
+    L.bbgpu_cma_destroy.argtypes = [vp]
+    L.bbgpu_cma_reset.argtypes = [vp, vp, i]
+    L.bbgpu_cma_set.argtypes = [vp, i, vp, i64]
+    L.bbgpu_cma_get.argtypes = [vp, i, vp, i64]
+    L.bbgpu_cma_get_rank.argtypes = [vp, vp, i]
+    L.bbgpu_cma_device_ptr.argtypes = [vp, i, P(vp), P(i64)]
+    L.bbgpu_cma_sample.argtypes = [vp, d, u64, vp]
+    L.bbgpu_cma_sample_dev.argtypes = [vp, d, vp]
+    L.bbgpu_cma_evaluate.argtypes = [vp, vp]
+    L.bbgpu_cma_rank.argtypes = [vp, i]
+    L.bbgpu_cma_update.argtypes = [vp, d, i]
+    L.bbgpu_cma_eig.argtypes = [vp, vp, vp]
+    L.bbgpu_cma_probe.argtypes = [vp, d, i]
+    L.bbgpu_cma_fetch.argtypes = [vp, P(CmaReport)]
+    L.bbgpu_cma_generation.argtypes = [vp, vp, d, u64, i, i]
+    L.bbgpu_dgemm_host.argtypes = [vp, i, i, i, vp, vp, vp]
+    L.bbgpu_dsyrk_host.argtypes = [vp, i, i, d, vp, vp, vp]
+    L.bbgpu_rank_host.argtypes = [vp, i, vp, vp]
+    L.bbgpu_philox_normal_host.argtypes = [vp, u64, u64, i, i, vp]
+    L.bbgpu_bench_dgemm.argtypes = [vp, i, i, i, i, P(ctypes.c_float)]
+    L.bbgpu_de_create.argtypes = [vp, P(DeConfig), vp, vp, P(vp)]
+    L.bbgpu_de_destroy.argtypes = [vp]
+    L.bbgpu_de_init.argtypes = [vp, vp, vp]
+    L.bbgpu_de_generation.argtypes = [vp, vp, P(DeDraws), P(DeReport)]
+    L.bbgpu_de_get_swarm.argtypes = [vp, vp, vp]
+    L.bbgpu_de_get_archive.argtypes = [vp, vp, P(i)]
+    L.bbgpu_de_get_memory.argtypes = [vp, vp, vp]
+    L.bbgpu_de_get_trace.argtypes = [vp, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != 0:
+        raise BbgpuError(f"bbgpu status {status}: {lib().bbgpu_last_error().decode()}")
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self.L = lib()
+        self.h = ctypes.c_void_p()
+        check(self.L.bbgpu_ctx_create(device, stream, ctypes.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.bbgpu_ctx_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.L.bbgpu_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.L.bbgpu_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return self.L.bbgpu_ctx_launch_count(self.h)
+
+    # ---- standalone kernels
+    def dgemm(self, A, B):
+        A, B = f64(A), f64(B)
+        M, K = A.shape
+        K2, N = B.shape
+        assert K == K2
+        C = np.empty((M, N))
+        check(self.L.bbgpu_dgemm_host(self.h, M, N, K, A.ctypes.data, B.ctypes.data, C.ctypes.data))
+        return C
+
+    def dsyrk(self, Y, coef, C, alpha):
+        Y, coef = f64(Y), f64(coef)
+        C = f64(C).copy()
+        K, n = Y.shape
+        check(self.L.bbgpu_dsyrk_host(self.h, n, K, alpha, Y.ctypes.data, coef.ctypes.data, C.ctypes.data))
+        return C
+
+    def rank(self, f):
+        f = f64(f)
+        idx = np.empty(f.size, dtype=np.int32)
+        check(self.L.bbgpu_rank_host(self.h, f.size, f.ctypes.data, idx.ctypes.data))
+        return idx
+
+    def philox_normal(self, seed, generation, rows, cols):
+        z = np.empty((rows, cols))
+        check(self.L.bbgpu_philox_normal_host(self.h, seed, generation, rows, cols, z.ctypes.data))
+        return z
+
+    def bench_dgemm(self, M, N, K, reps=10):
+        ms = ctypes.c_float(0)
+        check(self.L.bbgpu_bench_dgemm(self.h, M, N, K, reps, ctypes.byref(ms)))
+        return ms.value
+
+
+class Objective:
+    def __init__(self, ctx, n, builtin=None, device_fn=None, host_fn=None, user=None):
+        self.ctx, self.L, self.n = ctx, ctx.L, n
+        self.h = ctypes.c_void_p()
+        self._keep = None
+        if builtin is not None:
+            check(self.L.bbgpu_objective_builtin(ctx.h, builtin, n, ctypes.byref(self.h)))
+        elif device_fn is not None:
+            self._keep = device_fn if isinstance(device_fn, DEVICE_OBJECTIVE_FN) else DEVICE_OBJECTIVE_FN(device_fn)
+            check(self.L.bbgpu_objective_device(ctx.h, self._keep, user, n, ctypes.byref(self.h)))
+        elif host_fn is not None:
+            self._keep = host_fn if isinstance(host_fn, HOST_OBJECTIVE_FN) else HOST_OBJECTIVE_FN(host_fn)
+            check(self.L.bbgpu_objective_host(ctx.h, self._keep, user, n, ctypes.byref(self.h)))
+        else:
+            raise ValueError("one of builtin / device_fn / host_fn is required")
+
+    @classmethod
+    def from_python(cls, ctx, n, fn, batched=False):
+        """Batched host-callback bridge around a Python callable f(x)->float (or f(X)->array)."""
+        def cb(h_X, ld, n_, count, h_f, _user):
+            try:
+                X = np.ctypeslib.as_array(ctypes.cast(h_X, ctypes.POINTER(ctypes.c_double)), shape=(count, ld))[:, :n_]
+                out = np.ctypeslib.as_array(ctypes.cast(h_f, ctypes.POINTER(ctypes.c_double)), shape=(count,))
+                if batched:
+                    out[:] = np.asarray(fn(X), dtype=np.float64)
+                else:
+                    for k in range(count):
+                        out[k] = fn(X[k].copy())
+                return 0
+            except Exception:  # surfaced as BBGPU_ERR_OBJECTIVE
+                import traceback
+                traceback.print_exc()
+                return 1
+        return cls(ctx, n, host_fn=cb)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.bbgpu_objective_destroy(self.h)
+        except Exception:
+            pass
+
+    def eval(self, X):
+        X = f64(X)
+        X2 = X.reshape(-1, self.n)
+        f = np.empty(X2.shape[0])
+        check(self.L.bbgpu_eval_host(self.ctx.h, self.h, X2.ctypes.data, X2.shape[0], f.ctypes.data))
+        return f
+
+
+class Cma:
+    """Device state + phases of one CMA-ES run (see include/bbgpu.h)."""
+
+    def __init__(self, ctx, kind, n, lam, weights, consts, bound=False, lower=None, upper=None, seed=0):
+        self.ctx, self.L = ctx, ctx.L
+        self.kind, self.n, self.lam, self.mu = kind, n, lam, len(weights)
+        cfg = CmaConfig()
+        cfg.kind, cfg.n, cfg.lambda_, cfg.mu, cfg.bound = kind, n, lam, self.mu, int(bound)
+        cfg.shard_rank, cfg.shard_count, cfg.seed = 0, 1, seed
+        for k in ("cc", "cs", "c1", "cmu", "mueff", "chi", "cneg", "alphaold", "cm", "ccov"):
+            setattr(cfg, k, float(consts.get(k, 0.0)))
+        if kind == CMA_ACTIVE and "cm" not in consts:
+            cfg.cm = 1.0
+        self.cfg = cfg
+        w = f64(weights)
+        lo = f64(lower) if lower is not None else None
+        hi = f64(upper) if upper is not None else None
+        self.h = ctypes.c_void_p()
+        check(self.L.bbgpu_cma_create(ctx.h, ctypes.byref(cfg), w.ctypes.data, lo.ctypes.data if lo is not None else None,
+                                      hi.ctypes.data if hi is not None else None, ctypes.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.bbgpu_cma_destroy(self.h)
+        except Exception:
+            pass
+
+    def _len(self, field):
+        n, lam = self.n, self.lam
+        full = self.kind != CMA_SEP
+        return {F_XMEAN: n, F_XOLD: n, F_PC: n, F_PS: n, F_D: n, F_C: n * n if full else n, F_B: n * n,
+                F_INVSQRTC: n * n, F_ARX: lam * n, F_Z: lam * n, F_FITNESS: lam, F_RANKVAL: lam, F_YCOEFF: self.mu,
+                F_WEIGHTS: self.mu}[field]
+
+    def reset(self, guess, keep_offdiag=False):
+        g = f64(guess)
+        check(self.L.bbgpu_cma_reset(self.h, g.ctypes.data, int(keep_offdiag)))
+
+    def set(self, field, arr):
+        a = f64(arr).ravel()
+        check(self.L.bbgpu_cma_set(self.h, field, a.ctypes.data, a.size))
+
+    def get(self, field):
+        out = np.empty(self._len(field))
+        check(self.L.bbgpu_cma_get(self.h, field, out.ctypes.data, out.size))
+        if field in (F_B, F_INVSQRTC, F_ARX, F_Z) or (field == F_C and self.kind != CMA_SEP):
+            return out.reshape(-1, self.n)
+        return out
+
+    def rank_idx(self):
+        idx = np.empty(self.lam, dtype=np.int32)
+        check(self.L.bbgpu_cma_get_rank(self.h, idx.ctypes.data, self.lam))
+        return idx
+
+    def sample(self, sigma, generation=0, z=None):
+        if z is not None:
+            z = f64(z)
+            assert z.size == self.lam * self.n
+            check(self.L.bbgpu_cma_sample(self.h, sigma, generation, z.ctypes.data))
+        else:
+            check(self.L.bbgpu_cma_sample(self.h, sigma, generation, None))
+
+    def evaluate(self, obj):
+        check(self.L.bbgpu_cma_evaluate(self.h, obj.h))
+
+    def rank(self, ik):
+        check(self.L.bbgpu_cma_rank(self.h, ik))
+
+    def update(self, sigma, fev):
+        check(self.L.bbgpu_cma_update(self.h, sigma, fev))
+
+    def eig(self, B=None, D=None):
+        if B is None:
+            check(self.L.bbgpu_cma_eig(self.h, None, None))
+        else:
+            B, D = f64(B), f64(D)
+            check(self.L.bbgpu_cma_eig(self.h, B.ctypes.data, D.ctypes.data))
+
+    def probe(self, sigma, iaxis):
+        check(self.L.bbgpu_cma_probe(self.h, sigma, iaxis))
+
+    def fetch(self):
+        rep = CmaReport()
+        check(self.L.bbgpu_cma_fetch(self.h, ctypes.byref(rep)))
+        return rep
+
+    def generation(self, obj, sigma, generation, ik, fev_after):
+        check(self.L.bbgpu_cma_generation(self.h, obj.h, sigma, generation, ik, fev_after))

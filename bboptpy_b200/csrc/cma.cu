@@ -1,0 +1,935 @@
+// CMA-ES device engine: state + the per-generation phases behind the C ABI (include/bbgpu.h).
+//
+// Reference being replaced (paths under /root/reference/src/multivariate/cma):
+//   sample      cmaes.cpp:65-80, sep_cmaes.cpp:69-79
+//   evaluate    base_cmaes.cpp:211-219            rank   base_cmaes.cpp:221-229
+//   update      cmaes.cpp:82-142, active_cmaes.cpp:71-161, sep_cmaes.cpp:81-131
+//   eig         cmaes.cpp:229-283 (tred2/tql2 -> cuSOLVER syevd, or a replayed basis)
+//   probe       cmaes.cpp:184-229, sep_cmaes.cpp:170-205 (the O(n) parts of converged())
+//
+// HBM layout (fp64, row-major, row pitch ldn = n rounded up to 8 doubles = 64 B; pad columns
+// stay zero):  X, Z [lambda x ldn] candidate-major like the reference's _arx;  C, Bt, BDt,
+// BDit, isC [n x ldn];  Ysel [2mu x ldn] the selected, centred, sigma-scaled steps that feed the
+// covariance SYRK.  Bt is the TRANSPOSE of the reference's _b (row j = eigenvector j): that is what
+// syevd leaves in memory and what both tensor-core operand forms want (k-major rows).
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "gemm_f64.cuh"
+#include "objectives.cuh"
+#include "philox.cuh"
+#include "rank.cuh"
+
+struct bbgpu_cma {
+    bbgpu_ctx *ctx = nullptr;
+    bbgpu_cma_config cfg;
+    int n = 0, lambda = 0, mu = 0, nsel = 0;
+    int64_t ldn = 0;
+    bool full = false, active = false;
+    // vectors
+    double *xmean = nullptr, *xold = nullptr, *pc = nullptr, *ps = nullptr, *D = nullptr, *weights = nullptr,
+            *lower = nullptr, *upper = nullptr, *dm = nullptr, *W = nullptr, *coef = nullptr, *ycoeff = nullptr,
+            *ssq = nullptr, *dscal = nullptr, *tmpn = nullptr;
+    // matrices
+    double *C = nullptr, *Bt = nullptr, *BDt = nullptr, *BDit = nullptr, *isC = nullptr;
+    double *X = nullptr, *Z = nullptr, *Ysel = nullptr, *fit = nullptr, *rank_val = nullptr;
+    int *rank_idx = nullptr;
+    // reductions
+    double *part = nullptr; // [splits][2][n] partial sums for mean / sep variance
+    int splits = 1;
+    double *rowsq_part = nullptr; // [tiles_n][mu]
+    int rowsq_tiles_cap = 0;
+    // eigensolver workspace
+    double *solver_work = nullptr;
+    int solver_lwork = 0;
+    int *dev_info = nullptr;
+    // report
+    bbgpu_cma_report *d_report = nullptr;
+    bbgpu_cma_report *h_report = nullptr; // pinned
+};
+
+namespace bb {
+
+void destroy_solver(bbgpu_ctx *ctx) {
+    if (ctx->solver) {
+        cusolverDnDestroy((cusolverDnHandle_t) ctx->solver);
+        ctx->solver = nullptr;
+    }
+}
+
+static int get_solver(bbgpu_ctx *ctx, cusolverDnHandle_t *out) {
+    if (!ctx->solver) {
+        cusolverDnHandle_t h;
+        if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnCreate failed");
+        if (cusolverDnSetStream(h, ctx->stream) != CUSOLVER_STATUS_SUCCESS) {
+            cusolverDnDestroy(h);
+            return fail(BBGPU_ERR_SOLVER, "cusolverDnSetStream failed");
+        }
+        ctx->solver = (cusolverDnContext*) h;
+    }
+    *out = (cusolverDnHandle_t) ctx->solver;
+    return BBGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sampling
+// ------------------------------------------------------------------------------------------
+
+// Z[k][2jp], Z[k][2jp+1] <- Box-Muller pair of Philox block (jp, k0+k, generation)
+__global__ void __launch_bounds__(256) philox_normal_kernel(double *__restrict__ Z, int64_t ld, int rows, int cols,
+        int row0, uint64_t seed, uint64_t generation, uint32_t stream_tag) {
+    const int pairs = (cols + 1) >> 1;
+    const int64_t gid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t) rows * pairs) return;
+    const int k = (int) (gid / pairs), jp = (int) (gid % pairs);
+    const Philox4 r = philox4x32_10((uint32_t) jp, (uint32_t) (row0 + k), (uint32_t) generation,
+            (uint32_t) (generation >> 32) ^ stream_tag, (uint32_t) seed, (uint32_t) (seed >> 32));
+    double z0, z1;
+    normal_pair(r, z0, z1);
+    double *dst = Z + (int64_t) k * ld + 2 * jp;
+    dst[0] = z0;
+    if (2 * jp + 1 < cols) dst[1] = z1;
+}
+
+// SepCmaes::samplePopulation (sep_cmaes.cpp:69-79): x = m + sigma d z, clipped. HBM-bound.
+__global__ void __launch_bounds__(256) sep_sample_kernel(double *__restrict__ X, const double *__restrict__ Z,
+        int64_t ld, int rows, int n, const double *__restrict__ m, const double *__restrict__ d, double sigma,
+        const double *__restrict__ lo, const double *__restrict__ hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mi = m[i], sd = __dmul_rn(sigma, d[i]);
+    const bool clip = lo != nullptr;
+    const double l = clip ? lo[i] : 0.0, h = clip ? hi[i] : 0.0;
+    for (int k = blockIdx.y; k < rows; k += gridDim.y) {
+        double v = __dadd_rn(mi, __dmul_rn(sd, Z[(int64_t) k * ld + i]));
+        if (clip) v = fmax(l, fmin(v, h));
+        X[(int64_t) k * ld + i] = v;
+    }
+}
+
+// BDt[j][i] = D[j] Bt[j][i],  BDit[j][i] = Bt[j][i] / D[j]
+__global__ void __launch_bounds__(256) scale_basis_kernel(const double *__restrict__ Bt, const double *__restrict__ D,
+        double *__restrict__ BDt, double *__restrict__ BDit, int n, int64_t ld) {
+    const int j = blockIdx.x;
+    const double d = D[j];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double b = Bt[(int64_t) j * ld + i];
+        BDt[(int64_t) j * ld + i] = d * b;
+        BDit[(int64_t) j * ld + i] = b / d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ranking report
+// ------------------------------------------------------------------------------------------
+__global__ void rank_report_kernel(const int *__restrict__ idx, const double *__restrict__ val, int lambda, int ik,
+        bbgpu_cma_report *rep) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int pos[4] = { 0, lambda > 1 ? 1 : 0, lambda > 1 ? lambda - 2 : 0, lambda - 1 };
+    for (int q = 0; q < 4; q++) {
+        rep->ibw[q] = idx[pos[q]];
+        rep->ybw[q] = val[pos[q]];
+    }
+    rep->f_kth = val[ik < lambda ? ik : lambda - 1];
+}
+
+// ------------------------------------------------------------------------------------------
+// update: selection gather, recombination, evolution paths
+// ------------------------------------------------------------------------------------------
+
+// Ysel[r][:] = (X[src(r)][:] - m_old) / sigma.  r < mu: r-th best.  r >= mu (active): (r-mu)-th worst.
+__global__ void __launch_bounds__(256) gather_steps_kernel(double *__restrict__ Ysel, const double *__restrict__ X,
+        int64_t ld, int n, int mu, int lambda, const int *__restrict__ rank_idx, const double *__restrict__ mold,
+        double sigma) {
+    const int r = blockIdx.x;
+    const int src = r < mu ? rank_idx[r] : rank_idx[lambda - 1 - (r - mu)];
+    const double *x = X + (int64_t) src * ld;
+    double *y = Ysel + (int64_t) r * ld;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = __ddiv_rn(__dsub_rn(x[i], mold[i]), sigma);
+}
+
+// partial[s][i] = sum over rows k of split s of w_k X[idx_k][i]  (+ sep: w_k ((x - m_old)/sigma)^2)
+template<bool SEP>
+__global__ void __launch_bounds__(256) recombine_partial_kernel(double *__restrict__ part, const double *__restrict__ X,
+        int64_t ld, int n, int mu, int splits, const int *__restrict__ rank_idx, const double *__restrict__ w,
+        const double *__restrict__ mold, double sigma) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= n) return;
+    const int per = (mu + splits - 1) / splits;
+    const int k0 = s * per, k1 = min(mu, k0 + per);
+    double am = 0.0, ac = 0.0;
+    const double mo = SEP ? mold[i] : 0.0;
+    for (int k = k0; k < k1; k++) {
+        const double x = X[(int64_t) rank_idx[k] * ld + i];
+        const double wk = w[k];
+        am = __dadd_rn(am, __dmul_rn(wk, x));
+        if (SEP) {
+            const double y = __ddiv_rn(__dsub_rn(x, mo), sigma);
+            ac = __dadd_rn(ac, __dmul_rn(wk, __dmul_rn(y, y)));
+        }
+    }
+    part[((int64_t) s * 2 + 0) * n + i] = am;
+    if (SEP) part[((int64_t) s * 2 + 1) * n + i] = ac;
+}
+
+// m_new = sum_s partial (active: m_old (1-cm) + sum cm), clip, dm = (m_new - m_old)/(cm sigma).
+// sep additionally: ps_i = (1-cs) ps_i + csc C_i dm_i  (sep_cmaes.cpp:99-102: the VARIANCE c_i, kept)
+// and tmpn_i = sum_s partial variance term.
+template<bool SEP>
+__global__ void __launch_bounds__(256) recombine_final_kernel(const double *__restrict__ part, int n, int splits,
+        double *__restrict__ xmean, const double *__restrict__ xold, double *__restrict__ dm, double cm, double sigma,
+        const double *__restrict__ lo, const double *__restrict__ hi, bool active, double *__restrict__ ps,
+        const double *__restrict__ Cdiag, double cs, double csc, double *__restrict__ tmpn) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sm = 0.0, sc = 0.0;
+    for (int s = 0; s < splits; s++) {
+        sm = __dadd_rn(sm, part[((int64_t) s * 2 + 0) * n + i]);
+        if (SEP) sc = __dadd_rn(sc, part[((int64_t) s * 2 + 1) * n + i]);
+    }
+    const double mo = xold[i];
+    double mn = active ? __dadd_rn(__dmul_rn(mo, 1.0 - cm), __dmul_rn(sm, cm)) : sm;
+    if (lo != nullptr) mn = fmax(lo[i], fmin(mn, hi[i]));
+    xmean[i] = mn;
+    const double step = __ddiv_rn(__dsub_rn(mn, mo), active ? __dmul_rn(cm, sigma) : sigma);
+    dm[i] = step;
+    if (SEP) {
+        ps[i] = __dadd_rn(__dmul_rn(ps[i], 1.0 - cs), __dmul_rn(__dmul_rn(csc, Cdiag[i]), step));
+        tmpn[i] = sc;
+    }
+}
+
+// p_sigma <- (1-cs) p_sigma + csc C^-1/2 dm   (cmaes.cpp:99-105); one warp per row
+__global__ void __launch_bounds__(256) ps_gemv_kernel(const double *__restrict__ isC, int64_t ld, int n,
+        const double *__restrict__ dm, double *__restrict__ ps, double cs, double csc) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31;
+    const double *a = isC + (int64_t) row * ld;
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) acc = fma(a[j], dm[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) ps[row] = __dadd_rn(__dmul_rn(ps[row], 1.0 - cs), __dmul_rn(csc, acc));
+}
+
+// ||p_sigma||, hsig, p_c (cmaes.cpp:107-122); sep also finishes c_i, d_i (sep_cmaes.cpp:118-131).
+// denom = 1 - (1-cs)^(2 fev/lambda) is computed by the host with libm pow, as the reference does.
+template<bool SEP>
+__global__ void __launch_bounds__(1024) paths_kernel(int n, const double *__restrict__ ps, double *__restrict__ pc,
+        const double *__restrict__ dm, double denom, double chi, double cc, double ccc, double *__restrict__ dscal,
+        bbgpu_cma_report *rep, double *__restrict__ Cdiag, double *__restrict__ D, const double *__restrict__ tmpn,
+        double ccov, double mueff) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s = fma(ps[i], ps[i], s);
+    s = block_sum(s, red);
+    const double pslen = sqrt(s);
+    const int hsig = (pslen / sqrt(denom) / chi < 1.4 + 2.0 / (n + 1.0)) ? 1 : 0;
+    if (threadIdx.x == 0) {
+        rep->pslen = pslen;
+        rep->hsig = hsig;
+        *dscal = (1.0 - hsig) * cc * (2.0 - cc);
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double p = __dadd_rn(__dmul_rn(1.0 - cc, pc[i]), __dmul_rn(__dmul_rn((double) hsig, ccc), dm[i]));
+        pc[i] = p;
+        if (SEP) {
+            double c = __dadd_rn(__dmul_rn(1.0 - ccov, Cdiag[i]), __dmul_rn(__dmul_rn(ccov / mueff, p), p));
+            c = __dadd_rn(c, __dmul_rn(ccov * (1.0 - 1.0 / mueff), tmpn[i]));
+            Cdiag[i] = c;
+            D[i] = sqrt(c);
+        }
+    }
+}
+
+// active: ycoeff and the signed SYRK coefficients (active_cmaes.cpp:115-132,146-158)
+__global__ void __launch_bounds__(256) active_coef_kernel(const double *__restrict__ rowsq_part, int tiles_n, int mu,
+        double sigma, const double *__restrict__ w, double cmu1, double cneg, double *__restrict__ ycoeff,
+        double *__restrict__ coef) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mu) return;
+    // Ysel row mu+q is the q-th worst candidate; rowsq holds ||C^-1/2 y||^2 with y = (x-m_old)/sigma
+    auto ssq = [&](int q) {
+        double s = 0.0;
+        for (int tnl = 0; tnl < tiles_n; tnl++) s = __dadd_rn(s, rowsq_part[(int64_t) tnl * mu + q]);
+        return __dmul_rn(__dmul_rn(sigma, sigma), s);
+    };
+    const double top = ssq(mu - 1 - i);   // rank lambda-mu+i
+    const double bot = fmax(ssq(i), 1e-8);// rank lambda-1-i
+    const double yc = __ddiv_rn(top, bot);
+    ycoeff[i] = yc;
+    coef[i] = __dmul_rn(cmu1, w[i]);
+    coef[mu + i] = -__dmul_rn(__dmul_rn(cneg, w[i]), yc);
+}
+
+__global__ void __launch_bounds__(256) plain_coef_kernel(int mu, const double *__restrict__ w, double cmu,
+        double *__restrict__ coef) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < mu) coef[i] = __dmul_rn(cmu, w[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// eigen decomposition helpers
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) symmetrize_kernel(const double *__restrict__ C, double *__restrict__ V, int n,
+        int64_t ld) {
+    const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    V[(int64_t) i * ld + j] = j <= i ? C[(int64_t) i * ld + j] : C[(int64_t) j * ld + i];
+}
+
+// eigenvalue clamps + D = sqrt (cmaes.cpp:249-271); single CTA
+__global__ void __launch_bounds__(1024) eig_post_kernel(double *__restrict__ W, double *__restrict__ D,
+        double *__restrict__ C, int n, int64_t ld, const int *__restrict__ info, bbgpu_cma_report *rep) {
+    __shared__ double shift_s;
+    if (threadIdx.x == 0) {
+        rep->eig_info = *info;
+        shift_s = 0.0;
+    }
+    __syncthreads();
+    if (W[0] <= 0.0) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) W[i] = fmax(W[i], 0.0);
+        __syncthreads();
+        const double sh = W[n - 1] / 1e14;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            C[(int64_t) i * ld + i] += sh;
+            W[i] += sh;
+        }
+        __syncthreads();
+    }
+    if (W[n - 1] > 1e14 * W[0]) {
+        const double sh = W[n - 1] / 1e14 - W[0];
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            C[(int64_t) i * ld + i] += sh;
+            W[i] += sh;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) D[i] = sqrt(W[i]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rep->d_min = D[0];
+        rep->d_max = D[n - 1];
+    }
+}
+
+__global__ void ends_report_kernel(const double *__restrict__ D, int n, bbgpu_cma_report *rep) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        rep->d_min = D[0];
+        rep->d_max = D[n - 1];
+    }
+}
+
+__global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int n,
+        int64_t ld) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = by + r, j = bx + threadIdx.x;
+        tile[r][threadIdx.x] = (i < n && j < n) ? in[(int64_t) i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = bx + r, j = by + threadIdx.x;
+        if (i < n && j < n) out[(int64_t) i * ld + j] = tile[threadIdx.x][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// convergence probe (the O(n) tests of converged())
+// ------------------------------------------------------------------------------------------
+template<bool SEP>
+__global__ void __launch_bounds__(1024) probe_kernel(int n, int64_t ld, const double *__restrict__ xmean,
+        const double *__restrict__ pc, const double *__restrict__ C, const double *__restrict__ D,
+        const double *__restrict__ Bt, double sigma, int iaxis, bbgpu_cma_report *rep) {
+    __shared__ double red[32];
+    double tol = -INFINITY;
+    int axis_all = 1, coor_any = 0;
+    const double da = D[iaxis];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double m = xmean[i];
+        const double spread = SEP ? D[i] : sqrt(C[(int64_t) i * ld + i]);
+        tol = fmax(tol, fmax(pc[i], spread));
+        if (!SEP) {
+            // row iaxis of the reference's _b == column iaxis of Bt (cmaes.cpp:211: _b[iaxis][i])
+            const double b = Bt[(int64_t) i * ld + iaxis];
+            const double step = __dmul_rn(__dmul_rn(__dmul_rn(0.1, sigma), da), b);
+            if (m != __dadd_rn(m, step)) axis_all = 0;
+        }
+        const double cstep = __dmul_rn(__dmul_rn(0.2, sigma), spread);
+        if (m == __dadd_rn(m, cstep)) coor_any = 1;
+    }
+    tol = block_max(tol, red);
+    axis_all = __syncthreads_and(axis_all);
+    coor_any = __syncthreads_or(coor_any);
+    if (threadIdx.x == 0) {
+        rep->tolx_max = tol;
+        if (SEP) {
+            const double m = xmean[iaxis];
+            rep->noeffect_axis = (m == __dadd_rn(m, __dmul_rn(__dmul_rn(0.1, sigma), da))) ? 1 : 0;
+        } else {
+            rep->noeffect_axis = axis_all;
+        }
+        rep->noeffect_coor = coor_any;
+        rep->d_min = D[0];
+        rep->d_max = D[n - 1];
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_identity_kernel(double *__restrict__ M, int n, int64_t ld, bool keep_offdiag) {
+    const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (i == j) M[(int64_t) i * ld + j] = 1.0;
+    else if (!keep_offdiag) M[(int64_t) i * ld + j] = 0.0;
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(double *__restrict__ v, int n, double x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = x;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side phase drivers
+// ------------------------------------------------------------------------------------------
+static int refresh_basis_products(bbgpu_cma *h) {
+    bbgpu_ctx *ctx = h->ctx;
+    const int n = h->n;
+    scale_basis_kernel<<<n, 256, 0, ctx->stream>>>(h->Bt, h->D, h->BDt, h->BDit, n, h->ldn);
+    BB_TRY(launched(ctx, "scale_basis_kernel"));
+    // C^-1/2[i][l] = sum_j Bt[j][i] * (Bt[j][l] / D[j])          (cmaes.cpp:274-282)
+    GemmArgs g {};
+    g.A = h->Bt; g.lda = h->ldn; g.B = h->BDit; g.ldb = h->ldn;
+    g.M = n; g.N = n; g.K = n; g.kscale = nullptr;
+    g.C = h->isC; g.ldc = h->ldn;
+    return launch_gemm<2, EPI_STORE>(ctx, g);
+}
+
+static int do_sample(bbgpu_cma *h, double sigma) {
+    bbgpu_ctx *ctx = h->ctx;
+    const double *lo = h->cfg.bound ? h->lower : nullptr, *hi = h->cfg.bound ? h->upper : nullptr;
+    if (!h->full) {
+        dim3 grid(ceil_div(h->n, 256), std::min(h->lambda, 64));
+        sep_sample_kernel<<<grid, 256, 0, ctx->stream>>>(h->X, h->Z, h->ldn, h->lambda, h->n, h->xmean, h->D, sigma, lo, hi);
+        return launched(ctx, "sep_sample_kernel");
+    }
+    // X[k][i] = m_i + sigma * sum_j Z[k][j] * (D_j Bt[j][i]), clipped in the epilogue
+    GemmArgs g {};
+    g.A = h->Z; g.lda = h->ldn; g.B = h->BDt; g.ldb = h->ldn;
+    g.M = h->lambda; g.N = h->n; g.K = h->n;
+    g.C = h->X; g.ldc = h->ldn; g.vec = h->xmean; g.lo = lo; g.hi = hi; g.s0 = sigma;
+    return launch_gemm<1, EPI_SAMPLE>(ctx, g);
+}
+
+static int do_philox(bbgpu_cma *h, uint64_t generation) {
+    bbgpu_ctx *ctx = h->ctx;
+    const int64_t total = (int64_t) h->lambda * ((h->n + 1) / 2);
+    philox_normal_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(h->Z, h->ldn, h->lambda, h->n, 0, h->cfg.seed,
+            generation, 0u);
+    return launched(ctx, "philox_normal_kernel");
+}
+
+static int do_rank(bbgpu_cma *h, int ik) {
+    BB_TRY(rank_fitness(h->ctx, h->fit, h->lambda, h->rank_idx, h->rank_val));
+    rank_report_kernel<<<1, 32, 0, h->ctx->stream>>>(h->rank_idx, h->rank_val, h->lambda, ik, h->d_report);
+    return launched(h->ctx, "rank_report_kernel");
+}
+
+static int do_update(bbgpu_cma *h, double sigma, int fev) {
+    bbgpu_ctx *ctx = h->ctx;
+    const bbgpu_cma_config &c = h->cfg;
+    const int n = h->n, mu = h->mu;
+    cudaStream_t st = ctx->stream;
+    const double *lo = c.bound ? h->lower : nullptr, *hi = c.bound ? h->upper : nullptr;
+    BB_CUDA(cudaMemcpyAsync(h->xold, h->xmean, (size_t) n * 8, cudaMemcpyDeviceToDevice, st));
+    const double csc = std::sqrt(c.cs * (2.0 - c.cs) * c.mueff);
+    const double ccc = std::sqrt(c.cc * (2.0 - c.cc) * c.mueff);
+    const double denom = 1.0 - std::pow(1.0 - c.cs, 2.0 * fev / h->lambda); // cmaes.cpp:109
+    dim3 pgrid(ceil_div(n, 256), h->splits);
+    if (!h->full) {
+        recombine_partial_kernel<true><<<pgrid, 256, 0, st>>>(h->part, h->X, h->ldn, n, mu, h->splits, h->rank_idx,
+                h->weights, h->xold, sigma);
+        BB_TRY(launched(ctx, "recombine_partial_kernel<sep>"));
+        recombine_final_kernel<true><<<ceil_div(n, 256), 256, 0, st>>>(h->part, n, h->splits, h->xmean, h->xold, h->dm, 1.0,
+                sigma, lo, hi, false, h->ps, h->C, c.cs, csc, h->tmpn);
+        BB_TRY(launched(ctx, "recombine_final_kernel<sep>"));
+        paths_kernel<true><<<1, 1024, 0, st>>>(n, h->ps, h->pc, h->dm, denom, c.chi, c.cc, ccc, h->dscal, h->d_report, h->C,
+                h->D, h->tmpn, c.ccov, c.mueff);
+        return launched(ctx, "paths_kernel<sep>");
+    }
+    gather_steps_kernel<<<h->nsel, 256, 0, st>>>(h->Ysel, h->X, h->ldn, n, mu, h->lambda, h->rank_idx, h->xold, sigma);
+    BB_TRY(launched(ctx, "gather_steps_kernel"));
+    recombine_partial_kernel<false><<<pgrid, 256, 0, st>>>(h->part, h->X, h->ldn, n, mu, h->splits, h->rank_idx, h->weights,
+            h->xold, sigma);
+    BB_TRY(launched(ctx, "recombine_partial_kernel"));
+    recombine_final_kernel<false><<<ceil_div(n, 256), 256, 0, st>>>(h->part, n, h->splits, h->xmean, h->xold, h->dm, c.cm,
+            sigma, lo, hi, h->active, h->ps, nullptr, c.cs, csc, nullptr);
+    BB_TRY(launched(ctx, "recombine_final_kernel"));
+    ps_gemv_kernel<<<ceil_div(n, 8), 256, 0, st>>>(h->isC, h->ldn, n, h->dm, h->ps, c.cs, csc);
+    BB_TRY(launched(ctx, "ps_gemv_kernel"));
+    paths_kernel<false><<<1, 1024, 0, st>>>(n, h->ps, h->pc, h->dm, denom, c.chi, c.cc, ccc, h->dscal, h->d_report, nullptr,
+            nullptr, nullptr, 0.0, c.mueff);
+    BB_TRY(launched(ctx, "paths_kernel"));
+    double decay;
+    if (h->active) {
+        // Mahalanobis norms of the mu worst steps: rows [mu, 2mu) of Ysel times C^-1/2
+        GemmArgs g {};
+        g.A = h->Ysel + (int64_t) mu * h->ldn; g.lda = h->ldn; g.B = h->isC; g.ldb = h->ldn;
+        g.M = mu; g.N = n; g.K = n; g.partial = h->rowsq_part;
+        int tiles_n = 0;
+        BB_TRY((launch_gemm<1, EPI_ROWSQ>(ctx, g, &tiles_n)));
+        if (tiles_n > h->rowsq_tiles_cap) return fail(BBGPU_ERR_ARG, "rowsq partial buffer too small");
+        const double cmu1 = c.cmu + c.cneg * (1.0 - c.alphaold);
+        active_coef_kernel<<<ceil_div(mu, 256), 256, 0, st>>>(h->rowsq_part, tiles_n, mu, sigma, h->weights, cmu1, c.cneg,
+                h->ycoeff, h->coef);
+        BB_TRY(launched(ctx, "active_coef_kernel"));
+        decay = 1.0 - c.c1 - c.cmu + c.cneg * c.alphaold;
+    } else {
+        plain_coef_kernel<<<ceil_div(mu, 256), 256, 0, st>>>(mu, h->weights, c.cmu, h->coef);
+        BB_TRY(launched(ctx, "plain_coef_kernel"));
+        decay = 1.0 - c.c1 - c.cmu;
+    }
+    // C (lower) <- decay C + c1 (pc pc^T + c2 C) + sum_r coef_r y_r y_r^T
+    GemmArgs g {};
+    g.A = h->Ysel; g.lda = h->ldn; g.B = h->Ysel; g.ldb = h->ldn;
+    g.M = n; g.N = n; g.K = h->nsel; g.kscale = h->coef;
+    g.C = h->C; g.ldc = h->ldn; g.vec = h->pc; g.s0 = decay; g.s1 = c.c1; g.dscal = h->dscal;
+    return launch_gemm<2, EPI_SYRK>(ctx, g);
+}
+
+static int do_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
+    bbgpu_ctx *ctx = h->ctx;
+    const int n = h->n;
+    cudaStream_t st = ctx->stream;
+    if (h_B != nullptr) {
+        // eigenbasis replay: adopt the oracle's (B, D); Bt = B^T
+        void *hp = nullptr;
+        BB_TRY(ctx->pinned((size_t) n * n * 8, &hp));
+        double *hb = (double*) hp;
+        BB_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) hb[(size_t) j * n + i] = h_B[(size_t) i * n + j];
+        BB_CUDA(cudaMemcpy2DAsync(h->Bt, (size_t) h->ldn * 8, hb, (size_t) n * 8, (size_t) n * 8, n, cudaMemcpyHostToDevice, st));
+        BB_CUDA(cudaMemcpyAsync(h->D, h_D, (size_t) n * 8, cudaMemcpyHostToDevice, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        ends_report_kernel<<<1, 32, 0, st>>>(h->D, n, h->d_report);
+        BB_TRY(launched(ctx, "ends_report_kernel"));
+        return refresh_basis_products(h);
+    }
+    cusolverDnHandle_t sv;
+    BB_TRY(get_solver(ctx, &sv));
+    dim3 grid(ceil_div(n, 256), n);
+    symmetrize_kernel<<<grid, 256, 0, st>>>(h->C, h->Bt, n, h->ldn);
+    BB_TRY(launched(ctx, "symmetrize_kernel"));
+    if (h->solver_work == nullptr) {
+        int lwork = 0;
+        if (cusolverDnDsyevd_bufferSize(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->Bt, (int) h->ldn, h->W,
+                &lwork) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "syevd_bufferSize failed");
+        BB_TRY(dev_alloc(&h->solver_work, (size_t) lwork));
+        h->solver_lwork = lwork;
+    }
+    const cusolverStatus_t rc = cusolverDnDsyevd(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->Bt, (int) h->ldn,
+            h->W, h->solver_work, h->solver_lwork, h->dev_info);
+    if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDsyevd failed with status %d", (int) rc);
+    eig_post_kernel<<<1, 1024, 0, st>>>(h->W, h->D, h->C, n, h->ldn, h->dev_info, h->d_report);
+    BB_TRY(launched(ctx, "eig_post_kernel"));
+    return refresh_basis_products(h);
+}
+
+static int field_info(bbgpu_cma *h, int field, double **ptr, int64_t *rows, int64_t *cols, int64_t *ld) {
+    const int n = h->n;
+    *ld = 0;
+    switch (field) {
+    case BBGPU_CMA_XMEAN: *ptr = h->xmean; *rows = 1; *cols = n; break;
+    case BBGPU_CMA_XOLD: *ptr = h->xold; *rows = 1; *cols = n; break;
+    case BBGPU_CMA_PC: *ptr = h->pc; *rows = 1; *cols = n; break;
+    case BBGPU_CMA_PS: *ptr = h->ps; *rows = 1; *cols = n; break;
+    case BBGPU_CMA_D: *ptr = h->D; *rows = 1; *cols = n; break;
+    case BBGPU_CMA_C:
+        if (h->full) { *ptr = h->C; *rows = n; *cols = n; *ld = h->ldn; }
+        else { *ptr = h->C; *rows = 1; *cols = n; }
+        break;
+    case BBGPU_CMA_INVSQRTC:
+        if (!h->full) return fail(BBGPU_ERR_ARG, "separable CMA-ES has no C^-1/2");
+        *ptr = h->isC; *rows = n; *cols = n; *ld = h->ldn; break;
+    case BBGPU_CMA_B:
+        if (!h->full) return fail(BBGPU_ERR_ARG, "separable CMA-ES has no eigenbasis");
+        *ptr = h->Bt; *rows = n; *cols = n; *ld = h->ldn; break;
+    case BBGPU_CMA_ARX: *ptr = h->X; *rows = h->lambda; *cols = n; *ld = h->ldn; break;
+    case BBGPU_CMA_Z: *ptr = h->Z; *rows = h->lambda; *cols = n; *ld = h->ldn; break;
+    case BBGPU_CMA_FITNESS: *ptr = h->fit; *rows = 1; *cols = h->lambda; break;
+    case BBGPU_CMA_RANKVAL: *ptr = h->rank_val; *rows = 1; *cols = h->lambda; break;
+    case BBGPU_CMA_YCOEFF:
+        if (!h->active) return fail(BBGPU_ERR_ARG, "ycoeff exists only for active CMA-ES");
+        *ptr = h->ycoeff; *rows = 1; *cols = h->mu; break;
+    case BBGPU_CMA_WEIGHTS: *ptr = h->weights; *rows = 1; *cols = h->mu; break;
+    default: return fail(BBGPU_ERR_ARG, "unknown CMA field %d", field);
+    }
+    if (*ld == 0) *ld = *cols;
+    return BBGPU_OK;
+}
+
+} // namespace bb
+
+using namespace bb;
+
+extern "C" {
+
+int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *h_weights, const double *h_lower,
+        const double *h_upper, bbgpu_cma **out) {
+    BB_ARG(ctx && cfg && h_weights && out);
+    BB_ARG(cfg->n >= 1 && cfg->lambda >= 2 && cfg->mu >= 1 && cfg->mu <= cfg->lambda);
+    BB_ARG(cfg->kind >= BBGPU_CMA_FULL && cfg->kind <= BBGPU_CMA_SEP);
+    BB_ARG(!cfg->bound || (h_lower && h_upper));
+    if (cfg->shard_count > 1) return fail(BBGPU_ERR_ARG, "candidate sharding is driven by bbgpu_cma_shard_* (not configured here)");
+    BB_CUDA(cudaSetDevice(ctx->device));
+    bbgpu_cma *h = new bbgpu_cma();
+    h->ctx = ctx;
+    h->cfg = *cfg;
+    h->n = cfg->n;
+    h->lambda = cfg->lambda;
+    h->mu = cfg->mu;
+    h->full = cfg->kind != BBGPU_CMA_SEP;
+    h->active = cfg->kind == BBGPU_CMA_ACTIVE;
+    h->nsel = h->active ? 2 * h->mu : h->mu;
+    if (h->active && 2 * h->mu > h->lambda) { delete h; return fail(BBGPU_ERR_ARG, "active CMA-ES needs 2 mu <= lambda"); }
+    h->ldn = round_up(h->n, 8);
+    const int n = h->n;
+    const size_t ldn = (size_t) h->ldn, lam = (size_t) h->lambda;
+    h->splits = std::max(1, std::min(64, std::min(h->mu / 16, ceil_div(2 * ctx->sm_count, ceil_div(n, 256)))));
+    int rc = BBGPU_OK;
+    auto A = [&](double **p, size_t count) {
+        if (rc != BBGPU_OK) return;
+        rc = dev_alloc(p, count);
+        if (rc == BBGPU_OK && count) {
+            if (cudaMemsetAsync(*p, 0, count * 8, ctx->stream) != cudaSuccess) rc = fail(BBGPU_ERR_CUDA, "memset failed");
+        }
+    };
+    A(&h->xmean, ldn); A(&h->xold, ldn); A(&h->pc, ldn); A(&h->ps, ldn); A(&h->D, ldn); A(&h->dm, ldn);
+    A(&h->tmpn, ldn); A(&h->W, ldn); A(&h->weights, h->mu); A(&h->lower, ldn); A(&h->upper, ldn);
+    A(&h->coef, (size_t) h->nsel); A(&h->ycoeff, (size_t) h->mu); A(&h->dscal, 8);
+    A(&h->X, lam * ldn); A(&h->Z, lam * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
+    A(&h->part, (size_t) h->splits * 2 * n);
+    if (h->full) {
+        A(&h->C, (size_t) n * ldn); A(&h->Bt, (size_t) n * ldn); A(&h->BDt, (size_t) n * ldn);
+        A(&h->BDit, (size_t) n * ldn); A(&h->isC, (size_t) n * ldn);
+        A(&h->Ysel, (size_t) h->nsel * ldn);
+        if (h->active) {
+            h->rowsq_tiles_cap = ceil_div(n, 112);
+            A(&h->rowsq_part, (size_t) h->rowsq_tiles_cap * h->mu);
+        }
+    } else {
+        A(&h->C, ldn);
+    }
+    if (rc == BBGPU_OK) rc = dev_alloc(&h->rank_idx, lam);
+    if (rc == BBGPU_OK) rc = dev_alloc(&h->dev_info, 1);
+    if (rc == BBGPU_OK) rc = dev_alloc(&h->d_report, 1);
+    if (rc == BBGPU_OK && cudaMallocHost((void**) &h->h_report, sizeof(bbgpu_cma_report)) != cudaSuccess)
+        rc = fail(BBGPU_ERR_CUDA, "cudaMallocHost(report) failed");
+    if (rc != BBGPU_OK) { bbgpu_cma_destroy(h); return rc; }
+    memset(h->h_report, 0, sizeof(bbgpu_cma_report));
+    cudaMemsetAsync(h->d_report, 0, sizeof(bbgpu_cma_report), ctx->stream);
+    cudaMemsetAsync(h->dev_info, 0, sizeof(int), ctx->stream);
+    cudaMemcpyAsync(h->weights, h_weights, (size_t) h->mu * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (h_lower && h_upper) {
+        cudaMemcpyAsync(h->lower, h_lower, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(h->upper, h_upper, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = h;
+    return BBGPU_OK;
+}
+
+int bbgpu_cma_destroy(bbgpu_cma *h) {
+    if (!h) return BBGPU_OK;
+    cudaStreamSynchronize(h->ctx->stream);
+    double *bufs[] = { h->xmean, h->xold, h->pc, h->ps, h->D, h->dm, h->tmpn, h->W, h->weights, h->lower, h->upper, h->coef,
+            h->ycoeff, h->dscal, h->X, h->Z, h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
+            h->rowsq_part, h->solver_work, h->ssq };
+    for (double *b : bufs) if (b) cudaFree(b);
+    if (h->rank_idx) cudaFree(h->rank_idx);
+    if (h->dev_info) cudaFree(h->dev_info);
+    if (h->d_report) cudaFree(h->d_report);
+    if (h->h_report) cudaFreeHost(h->h_report);
+    delete h;
+    return BBGPU_OK;
+}
+
+int bbgpu_cma_reset(bbgpu_cma *h, const double *h_guess, int keep_offdiag) {
+    BB_ARG(h && h_guess);
+    bbgpu_ctx *ctx = h->ctx;
+    const int n = h->n;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaMemcpyAsync(h->xmean, h_guess, (size_t) n * 8, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemsetAsync(h->xold, 0, (size_t) n * 8, st));
+    BB_CUDA(cudaMemsetAsync(h->pc, 0, (size_t) n * 8, st));
+    BB_CUDA(cudaMemsetAsync(h->ps, 0, (size_t) n * 8, st));
+    fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(h->D, n, 1.0);
+    BB_TRY(launched(ctx, "fill_kernel"));
+    if (h->full) {
+        dim3 grid(ceil_div(n, 256), n);
+        // B and C keep their off-diagonal entries on a re-init of the same object in the
+        // reference (cmaes.cpp:53-60 resize without clear); C^-1/2 is cleared (:55-56)
+        fill_identity_kernel<<<grid, 256, 0, st>>>(h->C, n, h->ldn, keep_offdiag != 0);
+        BB_TRY(launched(ctx, "fill_identity_kernel"));
+        // Bt is the transpose of _b: resetting the diagonal commutes with the transpose
+        fill_identity_kernel<<<grid, 256, 0, st>>>(h->Bt, n, h->ldn, keep_offdiag != 0);
+        BB_TRY(launched(ctx, "fill_identity_kernel"));
+        fill_identity_kernel<<<grid, 256, 0, st>>>(h->isC, n, h->ldn, false);
+        BB_TRY(launched(ctx, "fill_identity_kernel"));
+        scale_basis_kernel<<<n, 256, 0, st>>>(h->Bt, h->D, h->BDt, h->BDit, n, h->ldn);
+        BB_TRY(launched(ctx, "scale_basis_kernel"));
+    } else {
+        fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(h->C, n, 1.0);
+        BB_TRY(launched(ctx, "fill_kernel"));
+    }
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BBGPU_OK;
+}
+
+int bbgpu_cma_set(bbgpu_cma *h, int field, const double *h_src, int64_t count) {
+    BB_ARG(h && h_src);
+    double *ptr;
+    int64_t rows, cols, ld;
+    BB_TRY(field_info(h, field, &ptr, &rows, &cols, &ld));
+    BB_ARG(count == rows * cols);
+    cudaStream_t st = h->ctx->stream;
+    if (field == BBGPU_CMA_B) {
+        std::vector<double> t((size_t) count);
+        const int n = h->n;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) t[(size_t) j * n + i] = h_src[(size_t) i * n + j];
+        BB_CUDA(cudaMemcpy2DAsync(ptr, (size_t) ld * 8, t.data(), (size_t) cols * 8, (size_t) cols * 8, rows, cudaMemcpyHostToDevice, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        scale_basis_kernel<<<n, 256, 0, st>>>(h->Bt, h->D, h->BDt, h->BDit, n, h->ldn);
+        BB_TRY(launched(h->ctx, "scale_basis_kernel"));
+        BB_CUDA(cudaStreamSynchronize(st));
+        return BBGPU_OK;
+    }
+    BB_CUDA(cudaMemcpy2DAsync(ptr, (size_t) ld * 8, h_src, (size_t) cols * 8, (size_t) cols * 8, rows, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    if (field == BBGPU_CMA_D && h->full) {
+        scale_basis_kernel<<<h->n, 256, 0, st>>>(h->Bt, h->D, h->BDt, h->BDit, h->n, h->ldn);
+        BB_TRY(launched(h->ctx, "scale_basis_kernel"));
+        BB_CUDA(cudaStreamSynchronize(st));
+    }
+    return BBGPU_OK;
+}
+
+int bbgpu_cma_get(bbgpu_cma *h, int field, double *h_dst, int64_t count) {
+    BB_ARG(h && h_dst);
+    double *ptr;
+    int64_t rows, cols, ld;
+    BB_TRY(field_info(h, field, &ptr, &rows, &cols, &ld));
+    BB_ARG(count == rows * cols);
+    cudaStream_t st = h->ctx->stream;
+    BB_CUDA(cudaMemcpy2DAsync(h_dst, (size_t) cols * 8, ptr, (size_t) ld * 8, (size_t) cols * 8, rows, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    if (field == BBGPU_CMA_B) {
+        const int n = h->n;
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j < n; j++) std::swap(h_dst[(size_t) i * n + j], h_dst[(size_t) j * n + i]);
+    }
+    return BBGPU_OK;
+}
+
+int bbgpu_cma_get_rank(bbgpu_cma *h, int32_t *h_idx, int count) {
+    BB_ARG(h && h_idx && count == h->lambda);
+    BB_CUDA(cudaMemcpyAsync(h_idx, h->rank_idx, (size_t) count * 4, cudaMemcpyDeviceToHost, h->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(h->ctx->stream));
+    return BBGPU_OK;
+}
+
+int bbgpu_cma_device_ptr(bbgpu_cma *h, int field, void **d_ptr, int64_t *ld) {
+    BB_ARG(h && d_ptr && ld);
+    double *ptr;
+    int64_t rows, cols;
+    BB_TRY(field_info(h, field, &ptr, &rows, &cols, ld));
+    *d_ptr = ptr;
+    return BBGPU_OK;
+}
+
+int bbgpu_cma_sample(bbgpu_cma *h, double sigma, uint64_t generation, const double *h_z) {
+    BB_ARG(h);
+    if (h_z != nullptr) {
+        BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, h_z, (size_t) h->n * 8, (size_t) h->n * 8, h->lambda,
+                cudaMemcpyHostToDevice, h->ctx->stream));
+    } else {
+        BB_TRY(do_philox(h, generation));
+    }
+    return do_sample(h, sigma);
+}
+
+int bbgpu_cma_sample_dev(bbgpu_cma *h, double sigma, const double *d_z) {
+    BB_ARG(h && d_z);
+    BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, d_z, (size_t) h->n * 8, (size_t) h->n * 8, h->lambda,
+            cudaMemcpyDeviceToDevice, h->ctx->stream));
+    return do_sample(h, sigma);
+}
+
+int bbgpu_cma_evaluate(bbgpu_cma *h, bbgpu_objective *obj) {
+    BB_ARG(h && obj && obj->n == h->n);
+    return evaluate(h->ctx, obj, h->X, h->ldn, h->lambda, h->fit);
+}
+
+int bbgpu_cma_rank(bbgpu_cma *h, int ik) {
+    BB_ARG(h && ik >= 0);
+    return do_rank(h, ik);
+}
+
+int bbgpu_cma_update(bbgpu_cma *h, double sigma, int fev) {
+    BB_ARG(h && sigma > 0.0);
+    return do_update(h, sigma, fev);
+}
+
+int bbgpu_cma_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
+    BB_ARG(h && h->full);
+    BB_ARG((h_B == nullptr) == (h_D == nullptr));
+    return do_eig(h, h_B, h_D);
+}
+
+int bbgpu_cma_probe(bbgpu_cma *h, double sigma, int iaxis) {
+    BB_ARG(h && iaxis >= 0 && iaxis < h->n);
+    if (h->full) probe_kernel<false><<<1, 1024, 0, h->ctx->stream>>>(h->n, h->ldn, h->xmean, h->pc, h->C, h->D, h->Bt, sigma, iaxis, h->d_report);
+    else probe_kernel<true><<<1, 1024, 0, h->ctx->stream>>>(h->n, h->ldn, h->xmean, h->pc, h->C, h->D, nullptr, sigma, iaxis, h->d_report);
+    return launched(h->ctx, "probe_kernel");
+}
+
+int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *out) {
+    BB_ARG(h && out);
+    BB_CUDA(cudaMemcpyAsync(h->h_report, h->d_report, sizeof(bbgpu_cma_report), cudaMemcpyDeviceToHost, h->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(h->ctx->stream));
+    *out = *h->h_report;
+    if (out->eig_info != 0) return fail(BBGPU_ERR_SOLVER, "syevd reported info = %d", out->eig_info);
+    return BBGPU_OK;
+}
+
+int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint64_t generation, int ik, int fev_after) {
+    BB_ARG(h && obj && obj->n == h->n);
+    BB_TRY(do_philox(h, generation));
+    BB_TRY(do_sample(h, sigma));
+    BB_TRY(evaluate(h->ctx, obj, h->X, h->ldn, h->lambda, h->fit));
+    BB_TRY(do_rank(h, ik));
+    return do_update(h, sigma, fev_after);
+}
+
+// ---- standalone kernels, host-buffer form -----------------------------------------------
+static int upload_padded(bbgpu_ctx *ctx, const double *h, int rows, int cols, double **d, int64_t *ld) {
+    *ld = round_up(cols, 8);
+    BB_TRY(dev_alloc(d, (size_t) rows * *ld));
+    BB_CUDA(cudaMemsetAsync(*d, 0, (size_t) rows * *ld * 8, ctx->stream));
+    if (h) BB_CUDA(cudaMemcpy2DAsync(*d, (size_t) *ld * 8, h, (size_t) cols * 8, (size_t) cols * 8, rows, cudaMemcpyHostToDevice, ctx->stream));
+    return BBGPU_OK;
+}
+
+int bbgpu_dgemm_host(bbgpu_ctx *ctx, int M, int N, int K, const double *h_A, const double *h_B, double *h_C) {
+    BB_ARG(ctx && h_A && h_B && h_C && M > 0 && N > 0 && K > 0);
+    double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    int64_t lda, ldb, ldc;
+    int rc = upload_padded(ctx, h_A, M, K, &dA, &lda);
+    if (rc == BBGPU_OK) rc = upload_padded(ctx, h_B, K, N, &dB, &ldb);
+    if (rc == BBGPU_OK) rc = upload_padded(ctx, nullptr, M, N, &dC, &ldc);
+    if (rc == BBGPU_OK) {
+        GemmArgs g {};
+        g.A = dA; g.lda = lda; g.B = dB; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.C = dC; g.ldc = ldc;
+        rc = launch_gemm<1, EPI_STORE>(ctx, g);
+    }
+    if (rc == BBGPU_OK && cudaMemcpy2DAsync(h_C, (size_t) N * 8, dC, (size_t) ldc * 8, (size_t) N * 8, M, cudaMemcpyDeviceToHost,
+            ctx->stream) != cudaSuccess) rc = fail(BBGPU_ERR_CUDA, "copy back failed");
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == BBGPU_OK) rc = fail(BBGPU_ERR_CUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return rc;
+}
+
+int bbgpu_dsyrk_host(bbgpu_ctx *ctx, int n, int K, double alpha, const double *h_Y, const double *h_coef, double *h_C) {
+    BB_ARG(ctx && h_Y && h_coef && h_C && n > 0 && K > 0);
+    double *dY = nullptr, *dC = nullptr, *dcoef = nullptr, *dzero = nullptr;
+    int64_t ldy, ldc;
+    int rc = upload_padded(ctx, h_Y, K, n, &dY, &ldy);
+    if (rc == BBGPU_OK) rc = upload_padded(ctx, h_C, n, n, &dC, &ldc);
+    if (rc == BBGPU_OK) rc = dev_alloc(&dcoef, (size_t) K);
+    if (rc == BBGPU_OK) rc = dev_alloc(&dzero, (size_t) round_up(n, 8) + 8);
+    if (rc == BBGPU_OK) {
+        cudaMemcpyAsync(dcoef, h_coef, (size_t) K * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemsetAsync(dzero, 0, ((size_t) round_up(n, 8) + 8) * 8, ctx->stream);
+        GemmArgs g {};
+        g.A = dY; g.lda = ldy; g.B = dY; g.ldb = ldy; g.M = n; g.N = n; g.K = K; g.kscale = dcoef;
+        g.C = dC; g.ldc = ldc; g.vec = dzero; g.s0 = alpha; g.s1 = 0.0; g.dscal = dzero;
+        rc = launch_gemm<2, EPI_SYRK>(ctx, g);
+    }
+    if (rc == BBGPU_OK && cudaMemcpy2DAsync(h_C, (size_t) n * 8, dC, (size_t) ldc * 8, (size_t) n * 8, n, cudaMemcpyDeviceToHost,
+            ctx->stream) != cudaSuccess) rc = fail(BBGPU_ERR_CUDA, "copy back failed");
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == BBGPU_OK) rc = fail(BBGPU_ERR_CUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(dY); cudaFree(dC); cudaFree(dcoef); cudaFree(dzero);
+    return rc;
+}
+
+int bbgpu_rank_host(bbgpu_ctx *ctx, int count, const double *h_f, int32_t *h_idx) {
+    BB_ARG(ctx && h_f && h_idx && count > 0);
+    double *df = nullptr, *dv = nullptr;
+    int *di = nullptr;
+    int rc = dev_alloc(&df, (size_t) count);
+    if (rc == BBGPU_OK) rc = dev_alloc(&dv, (size_t) count);
+    if (rc == BBGPU_OK) rc = dev_alloc(&di, (size_t) count);
+    if (rc == BBGPU_OK) {
+        cudaMemcpyAsync(df, h_f, (size_t) count * 8, cudaMemcpyHostToDevice, ctx->stream);
+        rc = rank_fitness(ctx, df, count, di, dv);
+    }
+    if (rc == BBGPU_OK) cudaMemcpyAsync(h_idx, di, (size_t) count * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == BBGPU_OK) rc = fail(BBGPU_ERR_CUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(df); cudaFree(dv); cudaFree(di);
+    return rc;
+}
+
+int bbgpu_philox_normal_host(bbgpu_ctx *ctx, uint64_t seed, uint64_t generation, int rows, int cols, double *h_z) {
+    BB_ARG(ctx && h_z && rows > 0 && cols > 0);
+    double *dz = nullptr;
+    int64_t ld;
+    int rc = upload_padded(ctx, nullptr, rows, cols, &dz, &ld);
+    if (rc == BBGPU_OK) {
+        const int64_t total = (int64_t) rows * ((cols + 1) / 2);
+        philox_normal_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dz, ld, rows, cols, 0, seed, generation, 0u);
+        rc = launched(ctx, "philox_normal_kernel");
+    }
+    if (rc == BBGPU_OK) cudaMemcpy2DAsync(h_z, (size_t) cols * 8, dz, (size_t) ld * 8, (size_t) cols * 8, rows, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == BBGPU_OK) rc = fail(BBGPU_ERR_CUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(dz);
+    return rc;
+}
+
+int bbgpu_bench_dgemm(bbgpu_ctx *ctx, int M, int N, int K, int reps, float *ms_per_launch) {
+    BB_ARG(ctx && ms_per_launch && M > 0 && N > 0 && K > 0 && reps > 0);
+    double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    int64_t lda, ldb, ldc;
+    int rc = upload_padded(ctx, nullptr, M, K, &dA, &lda);
+    if (rc == BBGPU_OK) rc = upload_padded(ctx, nullptr, K, N, &dB, &ldb);
+    if (rc == BBGPU_OK) rc = upload_padded(ctx, nullptr, M, N, &dC, &ldc);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    if (rc == BBGPU_OK) {
+        fill_kernel<<<ceil_div((int64_t) M * lda, 256), 256, 0, ctx->stream>>>(dA, (int) ((int64_t) M * lda), 1.0);
+        fill_kernel<<<ceil_div((int64_t) K * ldb, 256), 256, 0, ctx->stream>>>(dB, (int) ((int64_t) K * ldb), 0.5);
+        GemmArgs g {};
+        g.A = dA; g.lda = lda; g.B = dB; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.C = dC; g.ldc = ldc;
+        for (int i = 0; i < 3 && rc == BBGPU_OK; i++) rc = launch_gemm<1, EPI_STORE>(ctx, g);
+        cudaEventRecord(e0, ctx->stream);
+        for (int i = 0; i < reps && rc == BBGPU_OK; i++) rc = launch_gemm<1, EPI_STORE>(ctx, g);
+        cudaEventRecord(e1, ctx->stream);
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == BBGPU_OK) rc = fail(BBGPU_ERR_CUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    float ms = 0.f;
+    if (rc == BBGPU_OK) cudaEventElapsedTime(&ms, e0, e1);
+    *ms_per_launch = ms / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return rc;
+}
+
+} // extern "C"

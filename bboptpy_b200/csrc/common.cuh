@@ -1,0 +1,138 @@
+// Shared plumbing for libbbgpu.so: error reporting, the context object, small device helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bbgpu.h"
+
+namespace bb {
+
+// thread-local last-error string behind bbgpu_last_error()
+inline std::string &last_error() {
+    static thread_local std::string e;
+    return e;
+}
+
+inline int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+
+#define BB_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return bb::fail(BBGPU_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,   \
+                            cudaGetErrorString(e__));                                      \
+    } while (0)
+
+#define BB_TRY(call)                                                                       \
+    do {                                                                                   \
+        int s__ = (call);                                                                  \
+        if (s__ != BBGPU_OK) return s__;                                                   \
+    } while (0)
+
+#define BB_ARG(cond)                                                                       \
+    do {                                                                                   \
+        if (!(cond)) return bb::fail(BBGPU_ERR_ARG, "%s:%d invalid argument: %s", __FILE__, \
+                                     __LINE__, #cond);                                     \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int ceil_div(int64_t a, int64_t b) { return (int) ((a + b - 1) / b); }
+
+} // namespace bb
+
+struct cusolverDnContext;
+
+// One device + one stream.  Everything the library launches goes through launches++ so the
+// bench can report how many of OUR kernels ran in the timed region.
+struct bbgpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    cusolverDnContext *solver = nullptr; // created lazily by the eig path
+    // scratch: pinned host staging + device staging, grown on demand
+    void *h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    void *d_scratch = nullptr;
+    size_t d_scratch_bytes = 0;
+
+    int pinned(size_t bytes, void **out);
+    int scratch(size_t bytes, void **out);
+};
+
+namespace bb {
+
+// after every kernel launch: count it and surface launch-configuration errors early
+inline int launched(bbgpu_ctx *ctx, const char *what) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BBGPU_ERR_CUDA, "launch %s -> %s", what, cudaGetErrorString(e));
+    return BBGPU_OK;
+}
+
+template<typename T> int dev_alloc(T **p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return BBGPU_OK;
+    cudaError_t e = cudaMalloc((void**) p, count * sizeof(T));
+    if (e != cudaSuccess) return fail(BBGPU_ERR_CUDA, "cudaMalloc(%zu bytes) -> %s", count * sizeof(T),
+                                      cudaGetErrorString(e));
+    return BBGPU_OK;
+}
+
+// ---- device helpers ------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+    // xor butterfly 16,8,4,2,1: every lane ends with the same bits (a+b == b+a in IEEE)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+// deterministic block sum (blockDim.x multiple of 32, <= 1024); result valid in all threads
+__device__ __forceinline__ double block_sum(double v, double *smem32) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem32[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = (lane < nw) ? smem32[lane] : 0.0;
+    t = warp_sum(t);
+    return t;
+}
+
+__device__ __forceinline__ double block_max(double v, double *smem32) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) smem32[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = (lane < nw) ? smem32[lane] : -INFINITY;
+    t = warp_max(t);
+    return t;
+}
+#endif
+
+} // namespace bb

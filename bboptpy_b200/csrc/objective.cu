@@ -1,0 +1,125 @@
+// Objective registry entry points + the batched evaluation kernel (see objectives.cuh).
+#include <cmath>
+
+#include "objectives.cuh"
+
+namespace bb {
+
+// One warp per candidate row; 8 rows per 256-thread CTA.  HBM-bound: count*n*8 bytes read once.
+__global__ void __launch_bounds__(256) eval_rows_kernel(int id, int n, int count, const double *__restrict__ X,
+        int64_t ld, const double *__restrict__ aux, double *__restrict__ f) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= count) return;
+    const double *x = X + (int64_t) row * ld;
+    const double v = warp_objective(id, n, x, aux);
+    if ((threadIdx.x & 31) == 0) f[row] = v;
+}
+
+int evaluate(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *d_X, int64_t ld, int count, double *d_f) {
+    if (count <= 0) return BBGPU_OK;
+    obj->evals += count;
+    if (obj->mode == 0) {
+        eval_rows_kernel<<<ceil_div(count, 8), 256, 0, ctx->stream>>>(obj->id, obj->n, count, d_X, ld,
+                obj->d_aux, d_f);
+        return launched(ctx, "eval_rows_kernel");
+    }
+    if (obj->mode == 1) {
+        const int rc = obj->dev_fn(d_X, ld, obj->n, count, d_f, (void*) ctx->stream, obj->user);
+        if (rc != 0) return fail(BBGPU_ERR_OBJECTIVE, "user device objective returned %d", rc);
+        return BBGPU_OK;
+    }
+    // batched host callback bridge: device -> pinned host -> callback -> device
+    const int n = obj->n;
+    void *hp = nullptr;
+    BB_TRY(ctx->pinned(((size_t) count * n + count) * sizeof(double), &hp));
+    double *hX = (double*) hp, *hf = hX + (size_t) count * n;
+    BB_CUDA(cudaMemcpy2DAsync(hX, (size_t) n * 8, d_X, (size_t) ld * 8, (size_t) n * 8, count,
+            cudaMemcpyDeviceToHost, ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int rc = obj->host_fn(hX, n, n, count, hf, obj->user);
+    if (rc != 0) return fail(BBGPU_ERR_OBJECTIVE, "host objective callback returned %d", rc);
+    BB_CUDA(cudaMemcpyAsync(d_f, hf, (size_t) count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->stream)); // the pinned buffer is reused by later calls
+    return BBGPU_OK;
+}
+
+} // namespace bb
+
+extern "C" {
+
+int bbgpu_objective_builtin(bbgpu_ctx *ctx, int id, int n, bbgpu_objective **out) {
+    BB_ARG(ctx && out && n >= 1);
+    BB_ARG(id >= BBGPU_OBJ_SPHERE && id <= BBGPU_OBJ_ACKLEY);
+    bbgpu_objective *o = new bbgpu_objective();
+    o->ctx = ctx;
+    o->mode = 0;
+    o->id = id;
+    o->n = n;
+    if (id == BBGPU_OBJ_ELLIPSOID) {
+        // coefficient table 10^(6 i/(n-1)), computed once on the host with libm pow -- the same
+        // expression the oracle uses, so both sides read identical coefficients
+        std::vector<double> coef(n);
+        for (int i = 0; i < n; i++) coef[i] = (n > 1) ? std::pow(10.0, 6.0 * (double) i / ((double) n - 1.0)) : 1.0;
+        int s = bb::dev_alloc(&o->d_aux, (size_t) n);
+        if (s != BBGPU_OK) { delete o; return s; }
+        cudaError_t e = cudaMemcpy(o->d_aux, coef.data(), (size_t) n * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(o->d_aux); delete o; return bb::fail(BBGPU_ERR_CUDA, "memcpy coef: %s", cudaGetErrorString(e)); }
+    }
+    *out = o;
+    return BBGPU_OK;
+}
+
+int bbgpu_objective_device(bbgpu_ctx *ctx, bbgpu_device_objective_fn fn, void *user, int n,
+        bbgpu_objective **out) {
+    BB_ARG(ctx && out && fn && n >= 1);
+    bbgpu_objective *o = new bbgpu_objective();
+    o->ctx = ctx;
+    o->mode = 1;
+    o->n = n;
+    o->dev_fn = fn;
+    o->user = user;
+    *out = o;
+    return BBGPU_OK;
+}
+
+int bbgpu_objective_host(bbgpu_ctx *ctx, bbgpu_host_objective_fn fn, void *user, int n,
+        bbgpu_objective **out) {
+    BB_ARG(ctx && out && fn && n >= 1);
+    bbgpu_objective *o = new bbgpu_objective();
+    o->ctx = ctx;
+    o->mode = 2;
+    o->n = n;
+    o->host_fn = fn;
+    o->user = user;
+    *out = o;
+    return BBGPU_OK;
+}
+
+int bbgpu_objective_destroy(bbgpu_objective *obj) {
+    if (!obj) return BBGPU_OK;
+    if (obj->d_aux) cudaFree(obj->d_aux);
+    delete obj;
+    return BBGPU_OK;
+}
+
+int bbgpu_eval(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *d_X, int64_t ld, int count,
+        double *d_f) {
+    BB_ARG(ctx && obj && d_X && d_f && ld >= obj->n && count >= 0);
+    return bb::evaluate(ctx, obj, d_X, ld, count, d_f);
+}
+
+int bbgpu_eval_host(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *h_X, int count, double *h_f) {
+    BB_ARG(ctx && obj && h_X && h_f && count >= 0);
+    if (count == 0) return BBGPU_OK;
+    const size_t nx = (size_t) count * obj->n;
+    void *dp = nullptr;
+    BB_TRY(ctx->scratch((nx + count) * sizeof(double), &dp));
+    double *dX = (double*) dp, *df = dX + nx;
+    BB_CUDA(cudaMemcpyAsync(dX, h_X, nx * 8, cudaMemcpyHostToDevice, ctx->stream));
+    BB_TRY(bb::evaluate(ctx, obj, dX, obj->n, count, df));
+    BB_CUDA(cudaMemcpyAsync(h_f, df, (size_t) count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BBGPU_OK;
+}
+
+} // extern "C"

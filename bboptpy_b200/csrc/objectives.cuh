@@ -1,0 +1,161 @@
+// Device objective registry: Sphere, Ellipsoid, Rosenbrock, Rastrigin, Ackley.
+//
+// Replaces the per-candidate callback `_f._f(&x[0])` of the reference
+// (cma/base_cmaes.cpp:214-217, de/jade.cpp:159, de/shade.cpp:159) by batched evaluation:
+// one warp per candidate, coalesced 256-byte row segments, warp-shuffle reduction.
+//
+// Fitness drives every ranking and every greedy DE selection, so the arithmetic follows a
+// fixed SPEC (DESIGN.md "Objective spec") that a CPU can reproduce bit for bit:
+//   * 32 interleaved accumulators: lane l adds term(i) for i = l, l+32, ... in ascending i;
+//   * xor butterfly 16,8,4,2,1 to combine the lanes;
+//   * every multiply/add is an explicitly rounded __dmul_rn/__dadd_rn (never contracted to FMA);
+//   * cos(2 pi x) and exp(x) are fixed polynomials over + - * rint (no libdevice calls).
+#pragma once
+
+#include "common.cuh"
+
+namespace bb {
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+
+// cos(2 pi x): reduce to r = x - rint(x) in [-1/2, 1/2], fold to [0, 1/8] with the quarter- and
+// eighth-period symmetries, then a degree-18 Taylor polynomial in t = 2 pi * folded (t <= pi/4).
+__device__ __forceinline__ double cos2pi(double x) {
+    const double r = sub(x, rint(x));
+    double a = fabs(r);
+    bool neg = false;
+    if (a > 0.25) { a = sub(0.5, a); neg = true; }
+    double v;
+    if (a > 0.125) {
+        const double t = mul(sub(0.25, a), 6.283185307179586);
+        const double u = mul(t, t);
+        double s = -8.22063524662433e-18;
+        s = add(mul(s, u), 2.8114572543455206e-15);
+        s = add(mul(s, u), -7.647163731819816e-13);
+        s = add(mul(s, u), 1.6059043836821613e-10);
+        s = add(mul(s, u), -2.505210838544172e-08);
+        s = add(mul(s, u), 2.7557319223985893e-06);
+        s = add(mul(s, u), -0.0001984126984126984);
+        s = add(mul(s, u), 0.008333333333333333);
+        s = add(mul(s, u), -0.16666666666666666);
+        s = add(mul(s, u), 1.0);
+        v = mul(s, t);
+    } else {
+        const double t = mul(a, 6.283185307179586);
+        const double u = mul(t, t);
+        double c = -1.5619206968586225e-16;
+        c = add(mul(c, u), 4.779477332387385e-14);
+        c = add(mul(c, u), -1.1470745597729725e-11);
+        c = add(mul(c, u), 2.08767569878681e-09);
+        c = add(mul(c, u), -2.755731922398589e-07);
+        c = add(mul(c, u), 2.48015873015873e-05);
+        c = add(mul(c, u), -0.001388888888888889);
+        c = add(mul(c, u), 0.041666666666666664);
+        c = add(mul(c, u), -0.5);
+        c = add(mul(c, u), 1.0);
+        v = c;
+    }
+    return neg ? -v : v;
+}
+
+// exp(x) = 2^k * P13(r), k = rint(x log2 e), r = x - k ln2 (two-part), |r| <= 0.35
+__device__ __forceinline__ double exp_poly(double x) {
+    if (x < -700.0) return 0.0;
+    if (x > 700.0) x = 700.0;
+    const double k = rint(mul(x, 1.4426950408889634));
+    double r = sub(x, mul(k, 0.6931471803691238));
+    r = sub(r, mul(k, 1.9082149292705877e-10));
+    double p = 1.6059043836821613e-10;
+    p = add(mul(p, r), 2.08767569878681e-09);
+    p = add(mul(p, r), 2.505210838544172e-08);
+    p = add(mul(p, r), 2.755731922398589e-07);
+    p = add(mul(p, r), 2.7557319223985893e-06);
+    p = add(mul(p, r), 2.48015873015873e-05);
+    p = add(mul(p, r), 0.0001984126984126984);
+    p = add(mul(p, r), 0.001388888888888889);
+    p = add(mul(p, r), 0.008333333333333333);
+    p = add(mul(p, r), 0.041666666666666664);
+    p = add(mul(p, r), 0.16666666666666666);
+    p = add(mul(p, r), 0.5);
+    p = add(mul(p, r), 1.0);
+    p = add(mul(p, r), 1.0);
+    const long long ki = (long long) k;
+    const double two_k = __longlong_as_double((ki + 1023LL) << 52);
+    return mul(p, two_k);
+}
+
+// Per-lane partial of the objective sum over a candidate row held in global or shared memory.
+// All 32 lanes of the warp call this with the same (id, n, x); returns the full objective value
+// in every lane.  `aux` = ellipsoid coefficient table (device, length n) or nullptr.
+template<typename Ptr>
+__device__ __forceinline__ double warp_objective(int id, int n, Ptr x, const double *__restrict__ aux) {
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    switch (id) {
+    case BBGPU_OBJ_SPHERE:
+        for (int i = lane; i < n; i += 32) {
+            const double v = x[i];
+            acc = add(acc, mul(v, v));
+        }
+        return warp_sum(acc);
+    case BBGPU_OBJ_ELLIPSOID:
+        for (int i = lane; i < n; i += 32) {
+            const double v = x[i];
+            acc = add(acc, mul(aux[i], mul(v, v)));
+        }
+        return warp_sum(acc);
+    case BBGPU_OBJ_ROSENBROCK:
+        for (int i = lane; i + 1 < n; i += 32) {
+            const double v = x[i], w = x[i + 1];
+            const double t1 = sub(w, mul(v, v));
+            const double t2 = sub(1.0, v);
+            acc = add(acc, add(mul(100.0, mul(t1, t1)), mul(t2, t2)));
+        }
+        return warp_sum(acc);
+    case BBGPU_OBJ_RASTRIGIN: {
+        for (int i = lane; i < n; i += 32) {
+            const double v = x[i];
+            acc = add(acc, sub(mul(v, v), mul(10.0, cos2pi(v))));
+        }
+        const double s = warp_sum(acc);
+        return add(mul(10.0, (double) n), s);
+    }
+    case BBGPU_OBJ_ACKLEY: {
+        double acc2 = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            const double v = x[i];
+            acc = add(acc, mul(v, v));
+            acc2 = add(acc2, cos2pi(v));
+        }
+        const double s1 = warp_sum(acc);
+        const double s2 = warp_sum(acc2);
+        const double t1 = mul(20.0, exp_poly(mul(-0.2, sqrt(__ddiv_rn(s1, (double) n)))));
+        const double t2 = exp_poly(__ddiv_rn(s2, (double) n));
+        return add(sub(20.0, t1), sub(2.718281828459045, t2));
+    }
+    default:
+        return nan("");
+    }
+}
+
+} // namespace bb
+
+// Objective handle behind the C ABI.
+struct bbgpu_objective {
+    bbgpu_ctx *ctx = nullptr;
+    int mode = 0; // 0 builtin, 1 user device function, 2 batched host callback
+    int id = 0;
+    int n = 0;
+    double *d_aux = nullptr; // ellipsoid coefficients
+    bbgpu_device_objective_fn dev_fn = nullptr;
+    bbgpu_host_objective_fn host_fn = nullptr;
+    void *user = nullptr;
+    int64_t evals = 0;
+};
+
+namespace bb {
+// enqueue evaluation of `count` rows (leading dimension ld) on the ctx stream
+int evaluate(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *d_X, int64_t ld, int count, double *d_f);
+}

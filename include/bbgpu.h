@@ -1,0 +1,270 @@
+/*
+ * bbgpu.h -- C ABI of the B200 population engine (libbbgpu.so).
+ *
+ * This is the drop-in boundary for the reference's data-parallel hot path: the
+ * per-generation sample -> evaluate -> rank -> update loop of the CMA-ES family and the
+ * JADE / L-SHADE generation.  The reference has no FFI for this path (it is straight C++
+ * behind pybind11), so each entry point below names the reference code it replaces
+ * (paths relative to /root/reference).  The host classes in bboptpy_b200/host/ keep the
+ * reference's MultivariateOptimizer interface (src/multivariate/multivariate.h:132-146) and
+ * call only these functions; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function returns an
+ * int status (0 = BBGPU_OK) and bbgpu_last_error() describes the last failure on the calling
+ * thread; handles own their device memory; host pointers are borrowed for the call only;
+ * one ctx <-> one device + one stream; not thread-safe per handle (like the reference,
+ * src/random.hpp:168).  There is NO CPU fallback: without a CUDA device bbgpu_ctx_create
+ * fails with BBGPU_ERR_NODEVICE and nothing else can be constructed.
+ *
+ * All matrices crossing this ABI are dense row-major fp64 with the reference's index
+ * meaning (e.g. B[i*n+j] = component i of eigenvector j, cma/cmaes.cpp:65-80).
+ */
+#ifndef BBGPU_H_
+#define BBGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define BBGPU_VERSION 100
+
+enum bbgpu_status {
+    BBGPU_OK = 0,
+    BBGPU_ERR_CUDA = 1,     /* a CUDA runtime / driver call failed */
+    BBGPU_ERR_ARG = 2,      /* invalid argument */
+    BBGPU_ERR_NODEVICE = 3, /* no usable CUDA device (no CPU fallback exists) */
+    BBGPU_ERR_SOLVER = 4,   /* cuSOLVER failure / eigensolver did not converge */
+    BBGPU_ERR_OBJECTIVE = 5 /* a user objective returned non-zero */
+};
+
+typedef struct bbgpu_ctx bbgpu_ctx;
+typedef struct bbgpu_objective bbgpu_objective;
+typedef struct bbgpu_cma bbgpu_cma;
+typedef struct bbgpu_de bbgpu_de;
+
+int bbgpu_version(void);
+const char *bbgpu_last_error(void);
+
+/* ---- context: device + stream.  stream == NULL -> the ctx creates and owns a stream. */
+int bbgpu_ctx_create(int device, void *cuda_stream, bbgpu_ctx **out);
+int bbgpu_ctx_destroy(bbgpu_ctx *ctx);
+int bbgpu_ctx_sync(bbgpu_ctx *ctx);
+void *bbgpu_ctx_stream(bbgpu_ctx *ctx);
+/* number of kernels this library has launched on ctx since creation (bench.py gpu_launches) */
+int64_t bbgpu_ctx_launch_count(bbgpu_ctx *ctx);
+
+/* ---- objectives.  Replaces the per-candidate callback `_f._f(const double*)`
+ * (cma/base_cmaes.cpp:214-217, de/jade.cpp:159) by batched device evaluation. */
+enum bbgpu_builtin_objective {
+    BBGPU_OBJ_SPHERE = 0,
+    BBGPU_OBJ_ELLIPSOID = 1,
+    BBGPU_OBJ_ROSENBROCK = 2, /* README form, examples/multivariate.py:6-10 */
+    BBGPU_OBJ_RASTRIGIN = 3,
+    BBGPU_OBJ_ACKLEY = 4
+};
+/* user CUDA objective: evaluate `count` candidates stored row-major with leading dimension
+ * ld (doubles) at d_X, write d_f[count]; must enqueue on `cuda_stream`; return 0 on success */
+typedef int (*bbgpu_device_objective_fn)(const double *d_X, int64_t ld, int n, int count,
+                                         double *d_f, void *cuda_stream, void *user);
+/* batched host callback bridge (for callers that only have a CPU function, e.g. the Python
+ * callable of py/multivariate_py.cpp:385-388): X and f are pinned host buffers */
+typedef int (*bbgpu_host_objective_fn)(const double *h_X, int64_t ld, int n, int count,
+                                       double *h_f, void *user);
+int bbgpu_objective_builtin(bbgpu_ctx *ctx, int id, int n, bbgpu_objective **out);
+int bbgpu_objective_device(bbgpu_ctx *ctx, bbgpu_device_objective_fn fn, void *user, int n,
+                           bbgpu_objective **out);
+int bbgpu_objective_host(bbgpu_ctx *ctx, bbgpu_host_objective_fn fn, void *user, int n,
+                         bbgpu_objective **out);
+int bbgpu_objective_destroy(bbgpu_objective *obj);
+/* device-pointer evaluation (async on the ctx stream) and host-buffer convenience form */
+int bbgpu_eval(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *d_X, int64_t ld, int count,
+               double *d_f);
+int bbgpu_eval_host(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *h_X, int count,
+                    double *h_f);
+
+/* ---- CMA-ES engine (Cmaes / ActiveCmaes / SepCmaes device state and phases) */
+enum bbgpu_cma_kind { BBGPU_CMA_FULL = 0, BBGPU_CMA_ACTIVE = 1, BBGPU_CMA_SEP = 2 };
+
+typedef struct bbgpu_cma_config {
+    int kind;       /* bbgpu_cma_kind */
+    int n;          /* dimension */
+    int lambda;     /* population size */
+    int mu;         /* parents = lambda/2 (cma/base_cmaes.cpp:71) */
+    int bound;      /* clip samples and mean to [lower,upper] (cma/cmaes.cpp:74-77,92-94) */
+    int shard_rank; /* candidate sharding for one large-lambda run: this GPU owns candidates */
+    int shard_count;/*   [rank*lambda/count, (rank+1)*lambda/count); 0/1 = unsharded */
+    uint64_t seed;  /* Philox key for free-running sampling */
+    /* strategy constants computed by the host class exactly as the reference does
+     * (cma/base_cmaes.cpp:94-117, cma/active_cmaes.cpp:48-60, cma/sep_cmaes.cpp:44-58) */
+    double cc, cs, c1, cmu, mueff, chi;
+    double cneg, alphaold, cm; /* active only */
+    double ccov;               /* sep only */
+} bbgpu_cma_config;
+
+enum bbgpu_cma_field {
+    BBGPU_CMA_XMEAN = 0, /* n */
+    BBGPU_CMA_XOLD = 1,  /* n */
+    BBGPU_CMA_PC = 2,    /* n */
+    BBGPU_CMA_PS = 3,    /* n */
+    BBGPU_CMA_C = 4,     /* full/active: n*n (lower triangle authoritative, cma/cmaes.cpp:127);
+                            sep: n */
+    BBGPU_CMA_B = 5,     /* n*n, B[i*n+j] = component i of eigenvector j */
+    BBGPU_CMA_D = 6,     /* n, sqrt of eigenvalues ascending (sep: sqrt(c_i)) */
+    BBGPU_CMA_INVSQRTC = 7, /* n*n */
+    BBGPU_CMA_ARX = 8,   /* lambda*n, candidate-major (cma/base_cmaes.h:61) */
+    BBGPU_CMA_Z = 9,     /* lambda*n, the standard-normal draws of the last sample() */
+    BBGPU_CMA_FITNESS = 10, /* lambda, fitness by candidate index */
+    BBGPU_CMA_RANKVAL = 11, /* lambda, fitness ascending */
+    BBGPU_CMA_YCOEFF = 12,  /* mu (active) */
+    BBGPU_CMA_WEIGHTS = 13  /* mu */
+};
+
+/* everything the host class needs back per generation; filled by bbgpu_cma_fetch */
+typedef struct bbgpu_cma_report {
+    int32_t ibw[4]; /* indices of best, 2nd best, 2nd worst, worst (cma/base_cmaes.cpp:222-229) */
+    double ybw[4];
+    double f_kth;   /* fitness[_ik] for the flat-fitness test and the history ring (:183,:198) */
+    double pslen;   /* ||p_sigma||_2 after the path update (dnrm2 in cma/base_cmaes.cpp:179) */
+    int32_t hsig;
+    int32_t eig_info;     /* 0 = ok */
+    double d_min, d_max;  /* D[0], D[n-1] after the last decomposition (sep: c-ordered ends) */
+    double tolx_max;      /* max_i max(pc_i, sqrt(C_ii))        (cma/cmaes.cpp:184-194) */
+    int32_t noeffect_axis;/* 1 if NoEffectAxis holds            (cma/cmaes.cpp:208-221) */
+    int32_t noeffect_coor;/* 1 if NoEffectCoor holds            (cma/cmaes.cpp:223-229) */
+    double eig_resid;     /* max |B D^2 B^T - C| / max|C| when a replayed basis is validated */
+} bbgpu_cma_report;
+
+/* weights[mu]; lower/upper[n] may be NULL when bound == 0 */
+int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *h_weights,
+                     const double *h_lower, const double *h_upper, bbgpu_cma **out);
+int bbgpu_cma_destroy(bbgpu_cma *h);
+/* reset to the reference's init state: m = guess, C = B = C^-1/2 = I, D = 1, paths = 0
+ * (cma/base_cmaes.cpp:119-124, cma/cmaes.cpp:52-60).  keep_offdiag != 0 reproduces the
+ * reference's re-init quirk (only the diagonals of B and C are reset; cma/cmaes.cpp:53-60) */
+int bbgpu_cma_reset(bbgpu_cma *h, const double *h_guess, int keep_offdiag);
+int bbgpu_cma_set(bbgpu_cma *h, int field, const double *h_src, int64_t count);
+int bbgpu_cma_get(bbgpu_cma *h, int field, double *h_dst, int64_t count);
+int bbgpu_cma_get_rank(bbgpu_cma *h, int32_t *h_idx, int count);
+/* device pointer + leading dimension of a field (for user kernels / collectives) */
+int bbgpu_cma_device_ptr(bbgpu_cma *h, int field, void **d_ptr, int64_t *ld);
+
+/* sample(): cma/cmaes.cpp:65-80, cma/sep_cmaes.cpp:69-79.
+ * h_z == NULL: draws come from the device Philox stream (key = cfg.seed, counter =
+ * (generation, candidate, coordinate)).  h_z != NULL: DRAW REPLAY -- lambda*n standard
+ * normals in the reference's draw order (candidate-major) are consumed instead. */
+int bbgpu_cma_sample(bbgpu_cma *h, double sigma, uint64_t generation, const double *h_z);
+/* same with the draws already on the device (ld = n) */
+int bbgpu_cma_sample_dev(bbgpu_cma *h, double sigma, const double *d_z);
+/* evaluateAndSortPopulation(): cma/base_cmaes.cpp:211-230.  Ties are ordered by index. */
+int bbgpu_cma_evaluate(bbgpu_cma *h, bbgpu_objective *obj);
+int bbgpu_cma_rank(bbgpu_cma *h, int ik);
+/* updateDistribution() up to and excluding updateSigma()/eigenDecomposition():
+ * cma/cmaes.cpp:82-142, cma/active_cmaes.cpp:71-161, cma/sep_cmaes.cpp:81-131.
+ * fev = evaluation count AFTER this generation (the hsig exponent, cma/cmaes.cpp:109). */
+int bbgpu_cma_update(bbgpu_cma *h, double sigma, int fev);
+/* eigenDecomposition() body, cma/cmaes.cpp:236-282 (the host applies the gate :233).
+ * h_B/h_D == NULL: cuSOLVER syevd + clamps + D = sqrt + C^-1/2 = B D^-1 B^T on the device.
+ * h_B/h_D != NULL: EIGENBASIS REPLAY -- adopt the given basis (validated against C, see
+ * report.eig_resid) and rebuild C^-1/2 from it. */
+int bbgpu_cma_eig(bbgpu_cma *h, const double *h_B, const double *h_D);
+/* quantities for converged(): cma/cmaes.cpp:184-229, cma/sep_cmaes.cpp:170-205 */
+int bbgpu_cma_probe(bbgpu_cma *h, double sigma, int iaxis);
+/* synchronise the stream and return the report of everything enqueued so far */
+int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *out);
+/* one whole generation without host round trips in between (sample -> evaluate -> rank ->
+ * update); used by bench.py and by the host classes' fast path */
+int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint64_t generation,
+                         int ik, int fev_after);
+
+/* ---- standalone fp64 tensor-core kernels, host-buffer form (unit tests, peak probes) */
+/* C[M,N] = A[M,K] * B[K,N], all row-major */
+int bbgpu_dgemm_host(bbgpu_ctx *ctx, int M, int N, int K, const double *h_A, const double *h_B,
+                     double *h_C);
+/* C[n,n] (lower triangle) = alpha*C + sum_k coef[k] * Y[k,:]^T Y[k,:], Y is K x n row-major */
+int bbgpu_dsyrk_host(bbgpu_ctx *ctx, int n, int K, double alpha, const double *h_Y,
+                     const double *h_coef, double *h_C);
+/* sort fitness ascending, ties by index; writes the permutation */
+int bbgpu_rank_host(bbgpu_ctx *ctx, int count, const double *h_f, int32_t *h_idx);
+/* fill count standard normals from the Philox stream (key seed, counter (generation, i)) */
+int bbgpu_philox_normal_host(bbgpu_ctx *ctx, uint64_t seed, uint64_t generation, int rows,
+                             int cols, double *h_z);
+/* time `reps` launches of the sampling GEMM shape (M=lambda,N=n,K=n) with CUDA events; ms */
+int bbgpu_bench_dgemm(bbgpu_ctx *ctx, int M, int N, int K, int reps, float *ms_per_launch);
+
+/* ---- DE engine: JADE (de/jade.cpp:98-206) and L-SHADE (de/shade.cpp:96-236) generations */
+enum bbgpu_de_kind { BBGPU_DE_JADE = 0, BBGPU_DE_SHADE = 1 };
+
+typedef struct bbgpu_de_config {
+    int kind;
+    int n;
+    int np;        /* (initial) population size */
+    int archive;   /* use the external archive */
+    int repaircr;  /* record the realised crossover rate (de/jade.cpp:259-263) */
+    int h;         /* L-SHADE memory size */
+    int npmin;     /* L-SHADE minimum population */
+    int mfev;      /* budget (drives L-SHADE's population reduction, de/shade.cpp:218-225) */
+    double pelite; /* JADE */
+    double cdamp;  /* JADE */
+    double sigma;  /* JADE: CR power-mean switch (de/jade.cpp:188) */
+    uint64_t seed;
+} bbgpu_de_config;
+
+/* tagged draws of one generation, host arrays of length np unless noted (DRAW REPLAY).
+ * The reference consumes a data-dependent number of engine draws per candidate
+ * (de/jade.cpp:105-183); the oracle's recorder tags the accepted ones. */
+typedef struct bbgpu_de_draws {
+    const double *zcr;    /* N(0,1) variate behind CR (de/jade.cpp:108) */
+    const double *cauchy; /* accepted tan(pi(u-1/2)) variate behind F (de/jade.cpp:112-116) */
+    const int32_t *ibest; /* de/jade.cpp:119-120 */
+    const int32_t *r1;    /* de/jade.cpp:123-126 */
+    const int32_t *r2;    /* de/jade.cpp:127-131 (>= np: archive row r2-np) */
+    const int32_t *jrand; /* de/jade.cpp:249 */
+    const int32_t *slot;  /* archive slot replaced on success with a full archive (:165-166) */
+    const double *u;      /* np*n crossover uniforms (entry jrand unused) (de/jade.cpp:252) */
+    const int32_t *ri;    /* L-SHADE memory slot (de/shade.cpp:105) */
+    const double *pi;     /* L-SHADE greediness draw (de/shade.cpp:116) -- informational */
+    const int32_t *trim;  /* L-SHADE archive trimming draws, ntrim entries (de/shade.cpp:228-235) */
+    int ntrim;
+} bbgpu_de_draws;
+
+typedef struct bbgpu_de_report {
+    int32_t np;       /* population size after the generation */
+    int32_t larch;    /* archive size after the generation */
+    int32_t nsucc;    /* trials accepted (f_trial <= f_parent) */
+    int32_t fev;      /* evaluations so far */
+    int32_t rounds;   /* dependency-resolution rounds the generation needed */
+    int32_t kslot;    /* L-SHADE memory cursor */
+    double mucr, muf; /* JADE adaptive means */
+    double fbest;
+    double radius_m2; /* Welford M2 of ||x_i||_2 over the swarm (de/jade.cpp:228-245) */
+} bbgpu_de_report;
+
+int bbgpu_de_create(bbgpu_ctx *ctx, const bbgpu_de_config *cfg, const double *h_lower,
+                    const double *h_upper, bbgpu_de **out);
+int bbgpu_de_destroy(bbgpu_de *h);
+/* init(): de/jade.cpp:64-96, de/shade.cpp:56-94.  h_x == NULL: uniform Philox points;
+ * h_x != NULL: np*n replayed initial points.  Evaluates the swarm. */
+int bbgpu_de_init(bbgpu_de *h, bbgpu_objective *obj, const double *h_x);
+/* one generation with the reference's sequential in-place semantics, resolved in parallel.
+ * draws == NULL -> Philox. */
+int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws *draws,
+                        bbgpu_de_report *out);
+/* swarm in the reference's order after the generation (sorted for L-SHADE; JADE sorts at the
+ * start of the next generation, de/jade.cpp:101) */
+int bbgpu_de_get_swarm(bbgpu_de *h, double *h_x, double *h_f);
+int bbgpu_de_get_archive(bbgpu_de *h, double *h_arch, int *rows);
+int bbgpu_de_get_memory(bbgpu_de *h, double *h_mcr, double *h_mf);
+int bbgpu_de_get_trace(bbgpu_de *h, int32_t *h_succ, double *h_ftrial, double *h_F, double *h_CR);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBGPU_H_ */

@@ -117,6 +117,7 @@ struct PortCma {
     int ibw[4] = { 0, 0, 0, 0 };
     double ybw[4] = { 0, 0, 0, 0 };
     std::vector<double> xmean, xold, weights, tmp, pc, ps, arx;
+    std::vector<double> last_z; /* the N(0,1) draws of the last sample(), draw order (replay feed) */
     std::vector<RankRec> rank;
     /* Cmaes / ActiveCmaes state (cmaes.h:42-46, active_cmaes.h:42-44) */
     int flag = 0, eigenlastev = 0;
@@ -222,15 +223,21 @@ struct PortCma {
 
     /* ---- cma/cmaes.cpp:65-80 and cma/sep_cmaes.cpp:69-79 (draw order: candidate-major) */
     void sample() {
+        last_z.resize((size_t) lambda * n);
         for (int k = 0; k < lambda; k++) {
             double *x = &arx[(size_t) k * n];
+            double *zrow = &last_z[(size_t) k * n];
             if (kind == 2) {
                 for (int i = 0; i < n; i++) {
-                    x[i] = xmean[i] + sigma * d[i] * Z.draw(eng());
+                    zrow[i] = Z.draw(eng());
+                    x[i] = xmean[i] + sigma * d[i] * zrow[i];
                     if (bound) x[i] = std::max(lower[i], std::min(x[i], upper[i]));
                 }
             } else {
-                for (int i = 0; i < n; i++) tmp[i] = d[i] * Z.draw(eng());
+                for (int i = 0; i < n; i++) {
+                    zrow[i] = Z.draw(eng());
+                    tmp[i] = d[i] * zrow[i];
+                }
                 for (int i = 0; i < n; i++) {
                     const double *row = &B[(size_t) i * n];
                     double s = 0.0;
@@ -1090,6 +1097,7 @@ int bbo_cma_getv(void *h, const char *name, double *out, int cap) {
     if (k == "ps") return put(p->ps, out, cap);
     if (k == "weights") return put(p->weights, out, cap);
     if (k == "arx") return put(p->arx, out, cap);
+    if (k == "z") return put(p->last_z, out, cap);
     if (k == "hist_best") return put(p->best.v, out, cap);
     if (k == "hist_kth") return put(p->kth.v, out, cap);
     if (k == "D") return put(p->d, out, cap);

@@ -1,0 +1,171 @@
+"""Teacher-forced per-generation parity of the CMA-ES device phases against the oracle
+(tier T1), through the C ABI.
+
+Each generation: load the oracle's state -> replay the oracle's own N(0,1) draws -> compare
+X (1e-10), fitness bits and ranking (bit-exact), then m, p_sigma, p_c, C (1e-10), sigma, and the
+eigen path (own solver: invariants; replayed basis: C^-1/2 at 1e-10)."""
+import numpy as np
+import pytest
+
+from bboptpy_b200 import _cabi
+from oracle import oracle as O
+from util import REL, assert_close, oracle_constants, update_sigma_host
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return _cabi.Context(0)
+
+
+def load_state(g, s, kind):
+    g.set(_cabi.F_XMEAN, s["xmean"])
+    g.set(_cabi.F_PC, s["pc"])
+    g.set(_cabi.F_PS, s["ps"])
+    g.set(_cabi.F_C, s["C"])
+    if kind != O.SEP:
+        g.set(_cabi.F_INVSQRTC, s["invsqrtC"])
+        g.set(_cabi.F_D, s["D"])
+        g.set(_cabi.F_B, s["B"])
+    else:
+        g.set(_cabi.F_D, s["D"])
+
+
+CASES = [
+    # kind, obj, n, lambda, gens, bound, box
+    (O.VANILLA, O.ROSENBROCK, 10, 20, 40, False, 10.0),
+    (O.ACTIVE, O.ROSENBROCK, 10, 20, 40, False, 10.0),
+    (O.SEP, O.ELLIPSOID, 10, 20, 40, False, 10.0),
+    (O.VANILLA, O.RASTRIGIN, 40, 15, 25, False, 5.12),
+    (O.ACTIVE, O.ACKLEY, 33, 64, 15, True, 32.768),
+    (O.SEP, O.SPHERE, 100, 32, 15, True, 10.0),
+    (O.VANILLA, O.ROSENBROCK, 200, 300, 4, False, 10.0),
+    (O.ACTIVE, O.RASTRIGIN, 130, 257, 4, True, 5.12),
+    (O.SEP, O.ELLIPSOID, 1000, 512, 4, False, 10.0),
+]
+
+
+@pytest.mark.parametrize("kind,obj,n,lam,gens,bound,box", CASES)
+def test_teacher_forced_generations(ctx, port_oracle, kind, obj, n, lam, gens, bound, box):
+    P = port_oracle
+    P.seed(42)
+    lo, hi = -box * np.ones(n), box * np.ones(n)
+    guess = P.uniform(-box, box, n)
+    h = P.cma(kind, 10 ** 9, 1e-12, lam, bound=bound)
+    h.init(obj, lo, hi, guess)
+    consts = oracle_constants(h, kind)
+    damps = h.getd("damps")
+    g = _cabi.Cma(ctx, kind, n, lam, h.getv("weights"), consts, bound=bound, lower=lo, upper=hi)
+    g.reset(guess)
+    objective = _cabi.Objective(ctx, n, builtin=obj)
+    ik, hlen = h.geti("ik"), h.geti("hlen")
+    for gen in range(gens):
+        s0 = h.snapshot()
+        load_state(g, s0, kind)
+        # ---- sample with replayed draws
+        h.sample()
+        z = h.getv("z")
+        g.sample(s0["sigma"], gen, z=z)
+        X = h.mat("arx")
+        assert_close(g.get(_cabi.F_ARX), X, what=f"gen {gen} arx")
+        assert np.array_equal(g.get(_cabi.F_Z).ravel(), z)
+        # ---- evaluate + rank on the oracle's X (teacher forced): bit-exact
+        g.set(_cabi.F_ARX, X)
+        h.evalsort()
+        g.evaluate(objective)
+        g.rank(ik)
+        fit_sorted, fit_idx = h.getv("fit_val"), h.getv("fit_idx").astype(np.int32)
+        assert len(set(fit_sorted.tolist())) == lam, "parity cases must be tie-free"
+        fit = g.get(_cabi.F_FITNESS)
+        assert np.array_equal(fit[fit_idx], fit_sorted), f"gen {gen} fitness bits"
+        assert np.array_equal(g.rank_idx(), fit_idx), f"gen {gen} ranking"
+        assert np.array_equal(g.get(_cabi.F_RANKVAL), fit_sorted)
+        # ---- update
+        fev_after = h.geti("fev")
+        eig_before = h.geti("eigenlastev") if kind != O.SEP else 0
+        fworst, fbest, it = h.getd("fworst"), h.getd("fbest"), h.geti("it")
+        h.update()
+        g.update(s0["sigma"], fev_after)
+        rep = g.fetch()
+        s1 = h.snapshot()
+        assert list(rep.ibw) == [int(v) for v in h.getv("ibw")]
+        assert list(rep.ybw) == h.getv("ybw").tolist()
+        assert rep.f_kth == fit_sorted[ik]
+        assert_close(g.get(_cabi.F_XMEAN), s1["xmean"], what=f"gen {gen} xmean")
+        assert_close(g.get(_cabi.F_XOLD), s1["xold"], what=f"gen {gen} xold")
+        assert_close(g.get(_cabi.F_PS), s1["ps"], what=f"gen {gen} ps")
+        assert_close(g.get(_cabi.F_PC), s1["pc"], what=f"gen {gen} pc")
+        assert_close(rep.pslen, np.linalg.norm(s1["ps"]), what="pslen")
+        sigma = update_sigma_host(s0["sigma"], rep.pslen, consts["cs"], damps, consts["chi"], fit_sorted[0],
+                                  fit_sorted[ik], it, hlen, fworst, fbest)
+        assert_close(sigma, s1["sigma"], rel=1e-12, what=f"gen {gen} sigma")
+        if kind == O.SEP:
+            assert_close(g.get(_cabi.F_C), s1["C"], what=f"gen {gen} C")
+            assert_close(g.get(_cabi.F_D), s1["D"], what=f"gen {gen} D")
+        else:
+            lower = np.tril_indices(n)
+            Cg = g.get(_cabi.F_C)
+            eig_fired = s1["eigenlastev"] != eig_before
+            if kind == O.ACTIVE:
+                assert_close(g.get(_cabi.F_YCOEFF), s1["ycoeff"], rel=1e-9, what=f"gen {gen} ycoeff")
+            if not eig_fired:
+                assert_close(Cg[lower], s1["C"][lower], what=f"gen {gen} C")
+            else:
+                # the decomposition may shift the diagonal (cmaes.cpp:249-266); compare after our own eig
+                g.eig()
+                rep = g.fetch()
+                assert rep.eig_info == 0
+                Cg = g.get(_cabi.F_C)
+                assert_close(Cg[lower], s1["C"][lower], what=f"gen {gen} C after eig")
+                Bg, Dg = g.get(_cabi.F_B), g.get(_cabi.F_D)
+                Cfull = np.tril(Cg) + np.tril(Cg, -1).T
+                cs = np.abs(Cfull).max()
+                assert np.abs(Bg.T @ Bg - np.eye(n)).max() < 1e-12 * n
+                assert np.abs((Bg * Dg ** 2) @ Bg.T - Cfull).max() < 1e-12 * n * cs
+                assert np.all(np.diff(Dg) >= 0)
+                assert_close(Dg ** 2, s1["D"] ** 2, rel=1e-10, what=f"gen {gen} eigenvalues")
+                assert rep.d_min == Dg[0] and rep.d_max == Dg[-1]
+                # C^-1/2 is basis independent, but ill-conditioned by the small eigenvalues
+                cond = (Dg[-1] / Dg[0]) ** 2
+                assert_close(g.get(_cabi.F_INVSQRTC), s1["invsqrtC"], rel=1e-12 * n * max(cond, 1.0),
+                             what=f"gen {gen} invsqrtC (own basis)")
+                # eigenbasis replay: adopt the oracle's (B, D)
+                g.eig(s1["B"], s1["D"])
+                assert_close(g.get(_cabi.F_INVSQRTC), s1["invsqrtC"], what=f"gen {gen} invsqrtC (replayed basis)")
+                assert np.array_equal(g.get(_cabi.F_B), s1["B"])
+        # ---- convergence probe quantities
+        iaxis = n - 1 - (it % n)  # converged() runs after _it++ (base_cmaes.cpp:155): n-1-((it+1-1) % n)
+        g.probe(s1["sigma"], iaxis)
+        rep = g.fetch()
+        spread = s1["D"] if kind == O.SEP else np.sqrt(np.diag(g.get(_cabi.F_C)))
+        assert_close(rep.tolx_max, np.max(np.maximum(g.get(_cabi.F_PC), spread)), rel=1e-14, what="tolx")
+        h.history()
+
+
+def test_philox_generation_is_a_valid_cma_step(ctx, port_oracle):
+    """Free-running mode (device Philox): one generation from the identity state moves the mean
+    toward lower fitness and keeps C symmetric positive definite on its lower triangle."""
+    n, lam = 64, 128
+    P = port_oracle
+    h = P.cma(O.VANILLA, 10 ** 9, 1e-12, lam)
+    guess = 3.0 * np.ones(n)
+    h.init(O.SPHERE, -10 * np.ones(n), 10 * np.ones(n), guess)
+    g = _cabi.Cma(ctx, O.VANILLA, n, lam, h.getv("weights"), oracle_constants(h, O.VANILLA), seed=99)
+    g.reset(guess)
+    obj = _cabi.Objective(ctx, n, builtin=O.SPHERE)
+    sigma, fev = 2.0, 0
+    f_first = None
+    for gen in range(30):
+        fev += lam
+        g.generation(obj, sigma, gen, h.geti("ik"), fev)
+        rep = g.fetch()
+        f_first = rep.ybw[0] if f_first is None else f_first
+        sigma = update_sigma_host(sigma, rep.pslen, h.getd("cs"), h.getd("damps"), h.getd("chi"), rep.ybw[0], rep.f_kth,
+                                  gen, 10 ** 9, 0.0, 1.0)
+        g.eig()
+    rep = g.fetch()
+    assert rep.ybw[0] < 0.2 * f_first
+    C = g.get(_cabi.F_C)
+    Cf = np.tril(C) + np.tril(C, -1).T
+    assert np.linalg.eigvalsh(Cf).min() > 0
