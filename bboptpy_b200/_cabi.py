@@ -348,3 +348,82 @@ class Cma:
 
     def generation(self, obj, sigma, generation, ik, fev_after):
         check(self.L.bbgpu_cma_generation(self.h, obj.h, sigma, generation, ik, fev_after))
+
+
+class De:
+    """Device state + generation of one JADE / L-SHADE run (see include/bbgpu.h)."""
+
+    def __init__(self, ctx, kind, n, np_, lower, upper, mfev=10 ** 9, archive=True, repaircr=True, pelite=0.05,
+                 cdamp=0.1, sigma=0.07, h=100, npmin=4, seed=0):
+        self.ctx, self.L = ctx, ctx.L
+        self.kind, self.n, self.npcap = kind, n, np_
+        cfg = DeConfig()
+        cfg.kind, cfg.n, cfg.np, cfg.archive, cfg.repaircr = kind, n, np_, int(archive), int(repaircr)
+        cfg.h, cfg.npmin, cfg.mfev = h, npmin, mfev
+        cfg.pelite, cfg.cdamp, cfg.sigma, cfg.seed = pelite, cdamp, sigma, seed
+        self.cfg = cfg
+        lo, hi = f64(lower), f64(upper)
+        self.h = ctypes.c_void_p()
+        check(self.L.bbgpu_de_create(ctx.h, ctypes.byref(cfg), lo.ctypes.data, hi.ctypes.data, ctypes.byref(self.h)))
+        self.np = np_
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.bbgpu_de_destroy(self.h)
+        except Exception:
+            pass
+
+    def init(self, obj, x=None):
+        if x is not None:
+            x = f64(x)
+            assert x.shape == (self.npcap, self.n)
+        check(self.L.bbgpu_de_init(self.h, obj.h, x.ctypes.data if x is not None else None))
+        self.np = self.npcap
+
+    def generation(self, obj, draws=None, want_report=True):
+        """draws: dict with the oracle recorder's tagged draws (zcr, cauchy, ibest, r1, r2, jrand, slot, u[, ri, pi, trim])."""
+        rep = DeReport()
+        dd = None
+        if draws is not None:
+            keep = {}
+            dd = DeDraws()
+            for k in ("zcr", "cauchy", "u", "pi"):
+                if k in draws and draws[k] is not None:
+                    keep[k] = f64(draws[k])
+                    setattr(dd, k, keep[k].ctypes.data)
+            for k in ("ibest", "r1", "r2", "jrand", "slot", "ri", "trim"):
+                if k in draws and draws[k] is not None and len(draws[k]):
+                    keep[k] = i32(np.asarray(draws[k]).astype(np.int64))
+                    setattr(dd, k, keep[k].ctypes.data)
+            dd.ntrim = len(draws.get("trim", [])) if draws.get("trim") is not None else 0
+            self._keep = keep
+        check(self.L.bbgpu_de_generation(self.h, obj.h, ctypes.byref(dd) if dd is not None else None,
+                                         ctypes.byref(rep) if want_report else None))
+        if want_report:
+            self.np = rep.np
+        return rep
+
+    def swarm(self):
+        x, f = np.empty((self.np, self.n)), np.empty(self.np)
+        check(self.L.bbgpu_de_get_swarm(self.h, x.ctypes.data, f.ctypes.data))
+        return x, f
+
+    def archive(self):
+        rows = ctypes.c_int(0)
+        buf = np.empty((self.npcap, self.n))
+        check(self.L.bbgpu_de_get_archive(self.h, buf.ctypes.data, ctypes.byref(rows)))
+        return buf[:rows.value].copy()
+
+    def memory(self):
+        h = max(1, self.cfg.h)
+        mcr, mf = np.empty(h), np.empty(h)
+        check(self.L.bbgpu_de_get_memory(self.h, mcr.ctypes.data, mf.ctypes.data))
+        return mcr, mf
+
+    def trace(self, np_gen):
+        succ = np.empty(np_gen, dtype=np.int32)
+        ft, F, CR = np.empty(np_gen), np.empty(np_gen), np.empty(np_gen)
+        check(self.L.bbgpu_de_get_trace(self.h, succ.ctypes.data, ft.ctypes.data, F.ctypes.data, CR.ctypes.data))
+        return succ, ft, F, CR

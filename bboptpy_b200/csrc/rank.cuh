@@ -25,7 +25,7 @@ __device__ __forceinline__ bool tuple_greater(unsigned long long ka, unsigned ia
 
 constexpr int RANK_SMEM_MAX = 16384;
 
-__global__ void __launch_bounds__(1024) rank_smem_kernel(const double *__restrict__ f, int count, int npad,
+static __global__ void __launch_bounds__(1024) rank_smem_kernel(const double *__restrict__ f, int count, int npad,
         int *__restrict__ idx_out, double *__restrict__ val_out) {
     extern __shared__ __align__(16) unsigned char raw[];
     unsigned long long *keys = (unsigned long long*) raw;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(1024) rank_smem_kernel(const double *__restric
     }
 }
 
-__global__ void rank_global_init(const double *__restrict__ f, int count, int npad, unsigned long long *keys,
+static __global__ void rank_global_init(const double *__restrict__ f, int count, int npad, unsigned long long *keys,
         unsigned *ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npad) return;
@@ -66,7 +66,7 @@ __global__ void rank_global_init(const double *__restrict__ f, int count, int np
     ids[i] = i < count ? (unsigned) i : 0xffffffffu;
 }
 
-__global__ void rank_global_step(unsigned long long *keys, unsigned *ids, int npad, int k, int j) {
+static __global__ void rank_global_step(unsigned long long *keys, unsigned *ids, int npad, int k, int j) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (npad >> 1)) return;
     const int lo = 2 * j * (p / j) + (p % j);
@@ -80,7 +80,7 @@ __global__ void rank_global_step(unsigned long long *keys, unsigned *ids, int np
     }
 }
 
-__global__ void rank_global_finish(const double *__restrict__ f, const unsigned *__restrict__ ids, int count,
+static __global__ void rank_global_finish(const double *__restrict__ f, const unsigned *__restrict__ ids, int count,
         int *__restrict__ idx_out, double *__restrict__ val_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;

@@ -1,0 +1,107 @@
+"""Tagged-draw replay parity of the JADE / L-SHADE device generation against the oracle
+(tier T3), through the C ABI.
+
+The oracle's recorder (oracle/port, pinned bit-for-bit to the compiled reference) emits the
+draws the reference consumed; the engine replays them and must reproduce, per generation:
+success mask / indices bit-exact, swarm order bit-exact, positions and fitness within 1e-10
+(the first generation bit-exact), archive, and the adaptive means within 1e-10."""
+import numpy as np
+import pytest
+
+from bboptpy_b200 import _cabi
+from oracle import oracle as O
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return _cabi.Context(0)
+
+
+CASES = [
+    # kind, obj, n, np, gens, box, mfev, kwargs
+    (O.JADE, O.RASTRIGIN, 30, 50, 60, 5.12, 10 ** 6, {}),
+    (O.SHADE, O.RASTRIGIN, 30, 50, 60, 5.12, 20000, {"h": 10}),
+    (O.JADE, O.ROSENBROCK, 10, 20, 80, 10.0, 10 ** 6, {"archive": False, "repaircr": False}),
+    (O.SHADE, O.ACKLEY, 8, 30, 60, 32.768, 4000, {"h": 5}),
+    (O.JADE, O.SPHERE, 64, 200, 25, 5.0, 10 ** 6, {"pelite": 0.2}),
+    (O.JADE, O.RASTRIGIN, 1000, 1000, 4, 5.12, 10 ** 7, {}),
+    (O.SHADE, O.RASTRIGIN, 1000, 1000, 4, 5.12, 10 ** 7, {}),
+]
+
+
+@pytest.mark.parametrize("kind,obj,n,np_,gens,box,mfev,kw", CASES)
+def test_tagged_draw_replay(ctx, port_oracle, kind, obj, n, np_, gens, box, mfev, kw):
+    P = port_oracle
+    P.seed(7)
+    lo, hi = -box * np.ones(n), box * np.ones(n)
+    h = P.de(kind, mfev, np_, 1e-12, **kw)
+    h.init(obj, lo, hi)
+    x0, f0 = h.swarm()
+    g = _cabi.De(ctx, kind, n, np_, lo, hi, mfev=mfev, archive=kw.get("archive", True), repaircr=kw.get("repaircr", True),
+                 pelite=kw.get("pelite", 0.05), h=kw.get("h", 100))
+    objective = _cabi.Objective(ctx, n, builtin=obj)
+    g.init(objective, x0)
+    xg, fg = g.swarm()
+    assert np.array_equal(xg, x0) and np.array_equal(fg, f0)
+    max_rounds = 0
+    for gen in range(gens):
+        np_gen = h.geti("np")
+        h.iterate()
+        t = h.trace()
+        rep = g.generation(objective, t)
+        max_rounds = max(max_rounds, rep.rounds)
+        succ, ft, F, CR = g.trace(np_gen)
+        assert np.array_equal(succ > 0, t["succ"] > 0), f"gen {gen} success mask"
+        if kind == O.SHADE:
+            assert np.array_equal(succ == 2, t["succ"] == 2), f"gen {gen} strict-improvement mask"
+        assert_close(F, t["F"], what=f"gen {gen} F")
+        assert_close(CR, t["CR"], what=f"gen {gen} CR")
+        assert_close(ft, t["ftrial"], what=f"gen {gen} trial fitness")
+        if gen == 0:
+            assert np.array_equal(ft, t["ftrial"]), "first generation is bit-exact"
+        xo, fo = h.swarm()
+        xg, fg = g.swarm()
+        assert rep.np == h.geti("np") and rep.fev == h.geti("fev") and rep.larch == h.geti("larch")
+        assert rep.nsucc == int((t["succ"] > 0).sum())
+        assert_close(fg, fo, what=f"gen {gen} swarm fitness")
+        assert_close(xg, xo, what=f"gen {gen} swarm positions")
+        ao, ag = h.archive(), g.archive()
+        assert ao.shape == ag.shape
+        if ao.size:
+            assert_close(ag, ao, what=f"gen {gen} archive")
+        if kind == O.JADE:
+            assert_close(rep.mucr, h.getd("mucr"), what="mucr")
+            assert_close(rep.muf, h.getd("muf"), what="muf")
+        else:
+            mcr, mf = g.memory()
+            hh = kw.get("h", 100)
+            assert_close(mcr[:hh], h.getv("MCR"), what="MCR")
+            assert_close(mf[:hh], h.getv("MF"), what="MF")
+            assert rep.kslot == h.geti("k")
+        # Welford M2 of the radii (de/jade.cpp:228-245) from the device norms
+        r = np.linalg.norm(xo, axis=1)
+        assert_close(rep.radius_m2, np.sum((r - r.mean()) ** 2), rel=1e-8, what="radius M2")
+        assert rep.fbest == fg.min()
+    assert max_rounds >= 2  # the in-place dependencies really were exercised
+
+
+@pytest.mark.parametrize("kind", [O.JADE, O.SHADE])
+def test_free_running_philox_de_converges(ctx, kind):
+    n, np_ = 20, 64
+    lo, hi = -5.0 * np.ones(n), 5.0 * np.ones(n)
+    g = _cabi.De(ctx, kind, n, np_, lo, hi, mfev=40000, seed=5)
+    obj = _cabi.Objective(ctx, n, builtin=O.SPHERE)
+    g.init(obj)
+    x, f = g.swarm()
+    assert (x >= -5).all() and (x <= 5).all()
+    f0 = f.min()
+    rep = None
+    for _ in range(150):
+        rep = g.generation(obj)
+    assert rep.fbest < 1e-3 * f0
+    x, f = g.swarm()
+    assert (x >= -5).all() and (x <= 5).all()
+    assert np.allclose(f, (x * x).sum(1), rtol=1e-12)
