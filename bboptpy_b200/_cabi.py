@@ -95,6 +95,12 @@ def lib():
     L.bbgpu_ctx_stream.restype = vp
     L.bbgpu_ctx_launch_count.argtypes = [vp]
     L.bbgpu_ctx_launch_count.restype = i64
+    L.bbgpu_ctx_profile_enable.argtypes = [vp, i]
+    L.bbgpu_ctx_profile_read.argtypes = [vp, i, P(d), P(i64)]
+    L.bbgpu_ctx_profile_reset.argtypes = [vp]
+    L.bbgpu_ctx_timer_start.argtypes = [vp]
+    L.bbgpu_ctx_timer_stop.argtypes = [vp, P(ctypes.c_float)]
+    L.bbgpu_ctx_flush_l2.argtypes = [vp]
     L.bbgpu_objective_builtin.argtypes = [vp, i, i, P(vp)]
     L.bbgpu_objective_device.argtypes = [vp, DEVICE_OBJECTIVE_FN, vp, i, P(vp)]
     L.bbgpu_objective_host.argtypes = [vp, HOST_OBJECTIVE_FN, vp, i, P(vp)]
@@ -107,6 +113,7 @@ def lib():
     L.bbgpu_cma_set.argtypes = [vp, i, vp, i64]
     L.bbgpu_cma_get.argtypes = [vp, i, vp, i64]
     L.bbgpu_cma_get_rank.argtypes = [vp, vp, i]
+    L.bbgpu_cma_get_rows.argtypes = [vp, i, i64, i64, vp]
     L.bbgpu_cma_device_ptr.argtypes = [vp, i, P(vp), P(i64)]
     L.bbgpu_cma_sample.argtypes = [vp, d, u64, vp]
     L.bbgpu_cma_sample_dev.argtypes = [vp, d, vp]
@@ -174,6 +181,36 @@ class Context:
     @property
     def launches(self):
         return self.L.bbgpu_ctx_launch_count(self.h)
+
+    # ---- measurement helpers
+    PROF_TAGS = ("sample_gemm", "cov_syrk", "norm_gemm", "eval", "rank", "philox", "eig", "update_misc", "sep_sample",
+                 "de_round", "de_misc")
+
+    def profile(self, on=True):
+        check(self.L.bbgpu_ctx_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        check(self.L.bbgpu_ctx_profile_reset(self.h))
+
+    def profile_read(self):
+        out = {}
+        for tag, name in enumerate(self.PROF_TAGS):
+            ms, cnt = ctypes.c_double(0), ctypes.c_int64(0)
+            check(self.L.bbgpu_ctx_profile_read(self.h, tag, ctypes.byref(ms), ctypes.byref(cnt)))
+            if cnt.value:
+                out[name] = {"ms_total": ms.value, "launches": cnt.value, "ms_avg": ms.value / cnt.value}
+        return out
+
+    def timer_start(self):
+        check(self.L.bbgpu_ctx_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float(0)
+        check(self.L.bbgpu_ctx_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        check(self.L.bbgpu_ctx_flush_l2(self.h))
 
     # ---- standalone kernels
     def dgemm(self, A, B):

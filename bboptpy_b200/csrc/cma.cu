@@ -412,6 +412,7 @@ static int refresh_basis_products(bbgpu_cma *h) {
 
 static int do_sample(bbgpu_cma *h, double sigma) {
     bbgpu_ctx *ctx = h->ctx;
+    ProfScope prof(ctx, h->full ? BBGPU_PROF_SAMPLE_GEMM : BBGPU_PROF_SEP_SAMPLE);
     const double *lo = h->cfg.bound ? h->lower : nullptr, *hi = h->cfg.bound ? h->upper : nullptr;
     if (!h->full) {
         dim3 grid(ceil_div(h->n, 256), std::min(h->lambda, 64));
@@ -428,6 +429,7 @@ static int do_sample(bbgpu_cma *h, double sigma) {
 
 static int do_philox(bbgpu_cma *h, uint64_t generation) {
     bbgpu_ctx *ctx = h->ctx;
+    ProfScope prof(ctx, BBGPU_PROF_PHILOX);
     const int64_t total = (int64_t) h->lambda * ((h->n + 1) / 2);
     philox_normal_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(h->Z, h->ldn, h->lambda, h->n, 0, h->cfg.seed,
             generation, 0u);
@@ -435,6 +437,7 @@ static int do_philox(bbgpu_cma *h, uint64_t generation) {
 }
 
 static int do_rank(bbgpu_cma *h, int ik) {
+    ProfScope prof(h->ctx, BBGPU_PROF_RANK);
     BB_TRY(rank_fitness(h->ctx, h->fit, h->lambda, h->rank_idx, h->rank_val));
     rank_report_kernel<<<1, 32, 0, h->ctx->stream>>>(h->rank_idx, h->rank_val, h->lambda, ik, h->d_report);
     return launched(h->ctx, "rank_report_kernel");
@@ -451,6 +454,8 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
     const double ccc = std::sqrt(c.cc * (2.0 - c.cc) * c.mueff);
     const double denom = 1.0 - std::pow(1.0 - c.cs, 2.0 * fev / h->lambda); // cmaes.cpp:109
     dim3 pgrid(ceil_div(n, 256), h->splits);
+    ProfScope *misc = new ProfScope(ctx, BBGPU_PROF_UPDATE_MISC);
+    struct MiscGuard { ProfScope *&p; ~MiscGuard() { delete p; p = nullptr; } } guard { misc };
     if (!h->full) {
         recombine_partial_kernel<true><<<pgrid, 256, 0, st>>>(h->part, h->X, h->ldn, n, mu, h->splits, h->rank_idx,
                 h->weights, h->xold, sigma);
@@ -475,6 +480,8 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
     paths_kernel<false><<<1, 1024, 0, st>>>(n, h->ps, h->pc, h->dm, denom, c.chi, c.cc, ccc, h->dscal, h->d_report, nullptr,
             nullptr, nullptr, 0.0, c.mueff);
     BB_TRY(launched(ctx, "paths_kernel"));
+    delete misc;
+    misc = nullptr;
     double decay;
     if (h->active) {
         // Mahalanobis norms of the mu worst steps: rows [mu, 2mu) of Ysel times C^-1/2
@@ -482,7 +489,10 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
         g.A = h->Ysel + (int64_t) mu * h->ldn; g.lda = h->ldn; g.B = h->isC; g.ldb = h->ldn;
         g.M = mu; g.N = n; g.K = n; g.partial = h->rowsq_part;
         int tiles_n = 0;
-        BB_TRY((launch_gemm<1, EPI_ROWSQ>(ctx, g, &tiles_n)));
+        {
+            ProfScope prof(ctx, BBGPU_PROF_NORM_GEMM);
+            BB_TRY((launch_gemm<1, EPI_ROWSQ>(ctx, g, &tiles_n)));
+        }
         if (tiles_n > h->rowsq_tiles_cap) return fail(BBGPU_ERR_ARG, "rowsq partial buffer too small");
         const double cmu1 = c.cmu + c.cneg * (1.0 - c.alphaold);
         active_coef_kernel<<<ceil_div(mu, 256), 256, 0, st>>>(h->rowsq_part, tiles_n, mu, sigma, h->weights, cmu1, c.cneg,
@@ -499,11 +509,13 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
     g.A = h->Ysel; g.lda = h->ldn; g.B = h->Ysel; g.ldb = h->ldn;
     g.M = n; g.N = n; g.K = h->nsel; g.kscale = h->coef;
     g.C = h->C; g.ldc = h->ldn; g.vec = h->pc; g.s0 = decay; g.s1 = c.c1; g.dscal = h->dscal;
+    ProfScope prof(ctx, BBGPU_PROF_COV_SYRK);
     return launch_gemm<2, EPI_SYRK>(ctx, g);
 }
 
 static int do_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
     bbgpu_ctx *ctx = h->ctx;
+    ProfScope prof(ctx, BBGPU_PROF_EIG);
     const int n = h->n;
     cudaStream_t st = ctx->stream;
     if (h_B != nullptr) {
@@ -745,6 +757,18 @@ int bbgpu_cma_get_rank(bbgpu_cma *h, int32_t *h_idx, int count) {
     return BBGPU_OK;
 }
 
+int bbgpu_cma_get_rows(bbgpu_cma *h, int field, int64_t row0, int64_t rows, double *h_dst) {
+    BB_ARG(h && h_dst && field != BBGPU_CMA_B);
+    double *ptr;
+    int64_t nrows, cols, ld;
+    BB_TRY(field_info(h, field, &ptr, &nrows, &cols, &ld));
+    BB_ARG(row0 >= 0 && rows >= 0 && row0 + rows <= nrows);
+    cudaStream_t st = h->ctx->stream;
+    BB_CUDA(cudaMemcpy2DAsync(h_dst, (size_t) cols * 8, ptr + row0 * ld, (size_t) ld * 8, (size_t) cols * 8, rows, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BBGPU_OK;
+}
+
 int bbgpu_cma_device_ptr(bbgpu_cma *h, int field, void **d_ptr, int64_t *ld) {
     BB_ARG(h && d_ptr && ld);
     double *ptr;
@@ -774,6 +798,7 @@ int bbgpu_cma_sample_dev(bbgpu_cma *h, double sigma, const double *d_z) {
 
 int bbgpu_cma_evaluate(bbgpu_cma *h, bbgpu_objective *obj) {
     BB_ARG(h && obj && obj->n == h->n);
+    ProfScope prof(h->ctx, BBGPU_PROF_EVAL);
     return evaluate(h->ctx, obj, h->X, h->ldn, h->lambda, h->fit);
 }
 
@@ -813,7 +838,10 @@ int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint6
     BB_ARG(h && obj && obj->n == h->n);
     BB_TRY(do_philox(h, generation));
     BB_TRY(do_sample(h, sigma));
-    BB_TRY(evaluate(h->ctx, obj, h->X, h->ldn, h->lambda, h->fit));
+    {
+        ProfScope prof(h->ctx, BBGPU_PROF_EVAL);
+        BB_TRY(evaluate(h->ctx, obj, h->X, h->ldn, h->lambda, h->fit));
+    }
     BB_TRY(do_rank(h, ik));
     return do_update(h, sigma, fev_after);
 }

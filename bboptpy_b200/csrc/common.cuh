@@ -70,6 +70,14 @@ struct bbgpu_ctx {
     size_t h_pinned_bytes = 0;
     void *d_scratch = nullptr;
     size_t d_scratch_bytes = 0;
+    // measurement
+    bool profiling = false;
+    struct ProfRec { int tag; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+    double prof_ms[16] = { 0 };
+    int64_t prof_n[16] = { 0 };
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    void *d_flush = nullptr;
 
     int pinned(size_t bytes, void **out);
     int scratch(size_t bytes, void **out);
@@ -84,6 +92,24 @@ inline int launched(bbgpu_ctx *ctx, const char *what) {
     if (e != cudaSuccess) return fail(BBGPU_ERR_CUDA, "launch %s -> %s", what, cudaGetErrorString(e));
     return BBGPU_OK;
 }
+
+// device-time accounting for one (group of) launch(es); active only in profiling mode
+struct ProfScope {
+    bbgpu_ctx *ctx;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int tag;
+    ProfScope(bbgpu_ctx *c, int t) : ctx(c), tag(t) {
+        if (!ctx->profiling) return;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+    }
+    ~ProfScope() {
+        if (!e0) return;
+        cudaEventRecord(e1, ctx->stream);
+        ctx->prof.push_back({ tag, e0, e1 });
+    }
+};
 
 template<typename T> int dev_alloc(T **p, size_t count) {
     *p = nullptr;

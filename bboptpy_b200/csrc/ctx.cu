@@ -82,6 +82,9 @@ int bbgpu_ctx_destroy(bbgpu_ctx *ctx) {
     bb::destroy_solver(ctx);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_flush) cudaFree(ctx->d_flush);
+    for (auto &r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BBGPU_OK;
@@ -90,6 +93,68 @@ int bbgpu_ctx_destroy(bbgpu_ctx *ctx) {
 int bbgpu_ctx_sync(bbgpu_ctx *ctx) {
     BB_ARG(ctx);
     BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BBGPU_OK;
+}
+
+static void prof_collect(bbgpu_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &r : ctx->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.tag >= 0 && r.tag < 16) {
+            ctx->prof_ms[r.tag] += ms;
+            ctx->prof_n[r.tag] += 1;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    ctx->prof.clear();
+}
+
+int bbgpu_ctx_profile_enable(bbgpu_ctx *ctx, int on) {
+    BB_ARG(ctx);
+    if (!on) prof_collect(ctx);
+    ctx->profiling = on != 0;
+    return BBGPU_OK;
+}
+
+int bbgpu_ctx_profile_read(bbgpu_ctx *ctx, int tag, double *total_ms, int64_t *count) {
+    BB_ARG(ctx && tag >= 0 && tag < BBGPU_PROF_TAGS && total_ms && count);
+    prof_collect(ctx);
+    *total_ms = ctx->prof_ms[tag];
+    *count = ctx->prof_n[tag];
+    return BBGPU_OK;
+}
+
+int bbgpu_ctx_profile_reset(bbgpu_ctx *ctx) {
+    BB_ARG(ctx);
+    prof_collect(ctx);
+    for (int i = 0; i < 16; i++) { ctx->prof_ms[i] = 0.0; ctx->prof_n[i] = 0; }
+    return BBGPU_OK;
+}
+
+int bbgpu_ctx_timer_start(bbgpu_ctx *ctx) {
+    BB_ARG(ctx);
+    if (!ctx->timer0) {
+        BB_CUDA(cudaEventCreate(&ctx->timer0));
+        BB_CUDA(cudaEventCreate(&ctx->timer1));
+    }
+    BB_CUDA(cudaEventRecord(ctx->timer0, ctx->stream));
+    return BBGPU_OK;
+}
+
+int bbgpu_ctx_timer_stop(bbgpu_ctx *ctx, float *ms) {
+    BB_ARG(ctx && ms && ctx->timer0);
+    BB_CUDA(cudaEventRecord(ctx->timer1, ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    BB_CUDA(cudaEventElapsedTime(ms, ctx->timer0, ctx->timer1));
+    return BBGPU_OK;
+}
+
+int bbgpu_ctx_flush_l2(bbgpu_ctx *ctx) {
+    BB_ARG(ctx);
+    const size_t bytes = (size_t) 256 << 20;
+    if (!ctx->d_flush) BB_CUDA(cudaMalloc(&ctx->d_flush, bytes));
+    BB_CUDA(cudaMemsetAsync(ctx->d_flush, 0, bytes, ctx->stream));
     return BBGPU_OK;
 }
 

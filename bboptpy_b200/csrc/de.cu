@@ -599,6 +599,7 @@ int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws 
     while (done_round < 0) {
         const int first = round;
         for (int b = 0; b < batch && round < DE_MAX_ROUNDS; b++, round++) {
+            ProfScope prof(ctx, BBGPU_PROF_DE_ROUND);
             de_round_kernel<<<ceil_div(np, 8), 256, smem, st>>>(d, round);
             BB_TRY(launched(ctx, "de_round_kernel"));
         }

@@ -1,0 +1,412 @@
+// Host logic of the CMA-ES family (see cma.h).  Strategy constants and control flow follow the
+// reference line by line (citations inline); every O(lambda n^2) / O(n^3) step is a C-ABI call.
+#include "cma.h"
+
+#include <algorithm>
+#include <cmath>
+#include <iostream>
+#include <limits>
+
+using bbopt::gpu_check;
+
+void cmaes_history::add(double value) {
+    _buffer = (_buffer + 1) % _cap;
+    _hist[_buffer] = value;
+    if (_len < _cap) _len++;
+}
+
+double cmaes_history::get(int i) {
+    return _hist[(_cap + _buffer - i) % _cap];
+}
+
+BaseCmaes::BaseCmaes(int mfev, double tol, int np, double sigma0, bool bound) {
+    _tol = tol;
+    _lambda = np;
+    _sigma0 = sigma0;
+    _mfev = mfev;
+    _adaptpop = _adaptit = false;
+    _bound = bound;
+    _n = _mit = _mu = _it = _hlen = _ik = _fev = 0;
+    _mueff = _cc = _cs = _c1 = _cmu = _damps = _chi = _sigma = _fbest = _fworst = 0.;
+    _stream_key = bbopt::Random::next_stream_key();
+    _rep = bbgpu_cma_report();
+}
+
+BaseCmaes::~BaseCmaes() {
+    if (_dev) bbgpu_cma_destroy(_dev);
+}
+
+// host half of BaseCmaes::init (cma/base_cmaes.cpp:54-134)
+void BaseCmaes::init(const multivariate_problem &f, const double *guess) {
+    if (f._hasc || f._hasbbc) {
+        std::cerr << "Warning [CMA]: problem constraints will be ignored." << std::endl;
+    }
+    _f = f;
+    _n = f._n;
+    _lower = std::vector<double>(f._lower, f._lower + _n);
+    _upper = std::vector<double>(f._upper, f._upper + _n);
+    if (_adaptpop) _lambda = 4 + static_cast<int>(3. * std::log(_n));
+    _mu = _lambda / 2;
+    if (_adaptit) {
+        _mit = static_cast<int>(100 + 50 * (_n + 3) * (_n + 3) / std::sqrt(1. * _lambda));
+        _mfev = _mit * _lambda;
+    } else {
+        _mit = _mfev / _lambda;
+    }
+    _ibw.assign(4, 0);
+    _ybw.assign(4, 0.);
+    // log-linear recombination weights, normalised (:94-100)
+    _weights.assign(_mu, 0.);
+    double sum = 0.;
+    for (int i = 0; i < _mu; i++) {
+        _weights[i] = std::log(0.5 * (_lambda + 1.)) - std::log(i + 1.);
+        sum += _weights[i];
+    }
+    const double inv = 1. / sum;
+    for (int i = 0; i < _mu; i++) _weights[i] *= inv;
+    double lenw = 0.;
+    for (int i = 0; i < _mu; i++) lenw = lenw + _weights[i] * _weights[i];
+    _mueff = 1. / lenw;
+    // strategy parameters (:107-117)
+    _chi = std::sqrt(_n) * (1. - 1. / (4. * _n) + 1. / (21. * _n * _n));
+    _sigma = _sigma0;
+    _cc = (4. + _mueff / _n) / (_n + 4. + 2. * _mueff / _n);
+    _cs = (_mueff + 2.) / (5. + _n + _mueff);
+    _c1 = 2. / ((1.3 + _n) * (1.3 + _n) + _mueff);
+    _cmu = std::min(1. - _c1, 2. * (_mueff - 2. + 1. / _mueff) / ((2. + _n) * (2. + _n) + _mueff));
+    _damps = 1. + _cs + 2. * std::max(0., std::sqrt((_mueff - 1.) / (_n + 1.)) - 1.);
+    _it = _fev = 0;
+    _hlen = 10 + static_cast<int>(std::ceil((30. * _n) / _lambda));
+    _ik = static_cast<int>(std::ceil(0.1 + _lambda / 4.));
+    _best = cmaes_history { _hlen, -1, 0, std::vector<double>(_hlen, 0.) };
+    _kth = cmaes_history { _hlen, -1, 0, std::vector<double>(_hlen, 0.) };
+    _fbest = -std::numeric_limits<double>::infinity();
+    _fworst = std::numeric_limits<double>::infinity();
+    _fkth = 0.;
+    _rep = bbgpu_cma_report();
+    _rep_fresh = false;
+    _zbuf.clear();
+    // the guess is uploaded by ensureDevice(), called at the end of the most-derived init()
+    _ybw[0] = 0.;
+    _xguess.assign(guess, guess + _n);
+    _obj.bind(_f);
+}
+
+void BaseCmaes::fillConfig(bbgpu_cma_config &cfg) const {
+    cfg.kind = deviceKind();
+    cfg.n = _n;
+    cfg.lambda = _lambda;
+    cfg.mu = _mu;
+    cfg.bound = _bound ? 1 : 0;
+    cfg.shard_rank = 0;
+    cfg.shard_count = 1;
+    cfg.seed = _stream_key;
+    cfg.cc = _cc; cfg.cs = _cs; cfg.c1 = _c1; cfg.cmu = _cmu; cfg.mueff = _mueff; cfg.chi = _chi;
+    cfg.cneg = 0.; cfg.alphaold = 0.; cfg.cm = 1.; cfg.ccov = 0.;
+}
+
+// (re)create the device state for the current (kind, n, lambda, constants) and reset it to the
+// reference's init state.  The reference re-inits the SAME object on every IPOP/BIPOP restart and
+// its `_b` / `_c` keep their off-diagonal entries (cmaes.cpp:53-60 `resize` without clear; only
+// the diagonals are set back to 1, and `_invsqrtc` is cleared): carried over here.
+void BaseCmaes::ensureDevice() {
+    bbgpu_ctx *ctx = bbopt::device_context();
+    const bool full = deviceKind() != BBGPU_CMA_SEP;
+    std::vector<double> oldC, oldB;
+    const bool carry = full && _dev != nullptr && _dev_used && _dev_n == _n && _dev_kind != BBGPU_CMA_SEP;
+    if (carry) {
+        oldC.resize((size_t) _n * _n);
+        oldB.resize((size_t) _n * _n);
+        gpu_check(bbgpu_cma_get(_dev, BBGPU_CMA_C, oldC.data(), (int64_t) oldC.size()));
+        gpu_check(bbgpu_cma_get(_dev, BBGPU_CMA_B, oldB.data(), (int64_t) oldB.size()));
+    }
+    if (_dev) {
+        bbgpu_cma_destroy(_dev);
+        _dev = nullptr;
+    }
+    bbgpu_cma_config cfg;
+    fillConfig(cfg);
+    gpu_check(bbgpu_cma_create(ctx, &cfg, _weights.data(), _lower.data(), _upper.data(), &_dev));
+    _dev_kind = cfg.kind;
+    _dev_n = _n;
+    _dev_lambda = _lambda;
+    if (carry) {
+        gpu_check(bbgpu_cma_set(_dev, BBGPU_CMA_C, oldC.data(), (int64_t) oldC.size()));
+        gpu_check(bbgpu_cma_set(_dev, BBGPU_CMA_B, oldB.data(), (int64_t) oldB.size()));
+    }
+    gpu_check(bbgpu_cma_reset(_dev, _xguess.data(), carry ? 1 : 0));
+    _dev_used = false;
+}
+
+void BaseCmaes::setParams(int np, double sigma, int mfev) {
+    _lambda = np;
+    _sigma0 = sigma;
+    _mfev = mfev;
+    _adaptpop = _adaptit = false;
+    if (_bound) {
+        _bound = false;
+        std::cerr << "Warning [CMA]: box bounding is no longer enabled." << std::endl;
+    }
+}
+
+// cma/base_cmaes.cpp:150-156
+void BaseCmaes::iterate() {
+    samplePopulation();
+    evaluateAndSortPopulation();
+    updateDistribution();
+    updateHistory();
+    _it++;
+}
+
+multivariate_solution BaseCmaes::solution() {
+    return {bestSolution(), _fev, converged()};
+}
+
+// cma/base_cmaes.cpp:162-174
+multivariate_solution BaseCmaes::optimize(const multivariate_problem &f, const double *guess) {
+    init(f, guess);
+    bool converge = false;
+    while (_fev < _mfev) {
+        iterate();
+        if (converged()) {
+            converge = true;
+            break;
+        }
+    }
+    return {bestSolution(), _fev, converge};
+}
+
+// sample(): cmaes.cpp:65-80 / sep_cmaes.cpp:69-79 on the device.  Draws: the device Philox
+// stream keyed by (instance key, generation counter), or -- in replay mode -- lambda*n host
+// normals in the reference's candidate-major draw order.
+void BaseCmaes::samplePopulation() {
+    _dev_used = true;
+    if (_replay.enabled) {
+        _zbuf.resize((size_t) _lambda * _n);
+        _replay.fill_normals(_zbuf);
+        gpu_check(bbgpu_cma_sample(_dev, _sigma, _gen, _zbuf.data()));
+    } else {
+        gpu_check(bbgpu_cma_sample(_dev, _sigma, _gen, nullptr));
+    }
+    _gen++;
+}
+
+// cma/base_cmaes.cpp:211-230: evaluation and ranking stay on the device; ibw/ybw come back
+// with the per-generation report
+void BaseCmaes::evaluateAndSortPopulation() {
+    gpu_check(bbgpu_cma_evaluate(_dev, _obj.get()));
+    _fev += _lambda;
+    gpu_check(bbgpu_cma_rank(_dev, _ik));
+    _rep_fresh = false;
+}
+
+void BaseCmaes::fetchReport() {
+    gpu_check(bbgpu_cma_fetch(_dev, &_rep));
+    for (int q = 0; q < 4; q++) {
+        _ibw[q] = _rep.ibw[q];
+        _ybw[q] = _rep.ybw[q];
+    }
+    _fkth = _rep.f_kth;
+    _rep_fresh = true;
+}
+
+// cma/base_cmaes.cpp:176-189 with ||p_sigma|| computed on the device
+void BaseCmaes::updateSigma() {
+    const double pslen = _rep.pslen;
+    _sigma *= std::exp(std::min(1., (_cs / _damps) * (pslen / _chi - 1.)));
+    if (_ybw[0] == _fkth) _sigma *= std::exp(0.2 + _cs / _damps);
+    if (_it >= _hlen && _fworst - _fbest == 0.) _sigma *= std::exp(0.2 + _cs / _damps);
+}
+
+// cma/base_cmaes.cpp:191-209
+void BaseCmaes::updateHistory() {
+    if (_it >= _mit) return;
+    if (!_rep_fresh) fetchReport();
+    _best.add(_ybw[0]);
+    _kth.add(_fkth);
+    if (_best._len == _best._cap) {
+        _fbest = std::numeric_limits<double>::infinity();
+        _fworst = -std::numeric_limits<double>::infinity();
+        for (double fx : _best._hist) {
+            _fbest = std::min(fx, _fbest);
+            _fworst = std::max(fx, _fworst);
+        }
+    }
+}
+
+// cma/base_cmaes.cpp:232-238
+std::vector<double> BaseCmaes::bestSolution() {
+    std::vector<double> x(_n);
+    if (_it <= 0) {
+        gpu_check(bbgpu_cma_get(_dev, BBGPU_CMA_XMEAN, x.data(), _n));
+    } else {
+        if (!_rep_fresh) fetchReport();
+        gpu_check(bbgpu_cma_get_rows(_dev, BBGPU_CMA_ARX, _ibw[0], 1, x.data()));
+    }
+    return x;
+}
+
+std::vector<double> BaseCmaes::state(const std::string &name) {
+    struct Entry { const char *key; int field; int64_t len; };
+    const bool full = deviceKind() != BBGPU_CMA_SEP;
+    const int64_t n = _n, lam = _lambda;
+    const Entry table[] = { { "xmean", BBGPU_CMA_XMEAN, n }, { "xold", BBGPU_CMA_XOLD, n }, { "pc", BBGPU_CMA_PC, n },
+            { "ps", BBGPU_CMA_PS, n }, { "D", BBGPU_CMA_D, n }, { "C", BBGPU_CMA_C, full ? n * n : n },
+            { "B", BBGPU_CMA_B, n * n }, { "invsqrtC", BBGPU_CMA_INVSQRTC, n * n }, { "arx", BBGPU_CMA_ARX, lam * n },
+            { "z", BBGPU_CMA_Z, lam * n }, { "fitness", BBGPU_CMA_FITNESS, lam }, { "rankval", BBGPU_CMA_RANKVAL, lam },
+            { "ycoeff", BBGPU_CMA_YCOEFF, (int64_t) _mu }, { "weights", BBGPU_CMA_WEIGHTS, (int64_t) _mu } };
+    if (name == "rank") {
+        std::vector<int32_t> idx(_lambda);
+        gpu_check(bbgpu_cma_get_rank(_dev, idx.data(), _lambda));
+        return std::vector<double>(idx.begin(), idx.end());
+    }
+    for (const Entry &e : table) {
+        if (name == e.key) {
+            std::vector<double> out((size_t) e.len);
+            gpu_check(bbgpu_cma_get(_dev, e.field, out.data(), e.len));
+            return out;
+        }
+    }
+    throw bbopt::GpuError("unknown state field: " + name);
+}
+
+// ---------------------------------------------------------------------------------------
+// Cmaes
+// ---------------------------------------------------------------------------------------
+
+// cma/cmaes.cpp:44-63
+void Cmaes::init(const multivariate_problem &f, const double *guess) {
+    BaseCmaes::init(f, guess);
+    _eigenfreq = _eigenrate * _lambda / (_c1 + _cmu) / _n;
+    _eigenlastev = 0;
+    _flag = 0;
+    if (deviceKind() == BBGPU_CMA_FULL) ensureDevice();
+}
+
+// cma/cmaes.cpp:82-149 (the same flow serves ActiveCmaes, active_cmaes.cpp:71-168: the
+// variant-specific arithmetic is selected by the device handle's kind)
+void Cmaes::updateDistribution() {
+    gpu_check(bbgpu_cma_update(_dev, _sigma, _fev));
+    fetchReport();
+    updateSigma();
+    eigenDecomposition();
+}
+
+// cma/cmaes.cpp:229-283: the gate stays on the host, the decomposition runs on the device
+void Cmaes::eigenDecomposition() {
+    if (_fev - _eigenlastev <= _eigenfreq) return;
+    _eigenlastev = _fev;
+    _eigcount++;
+    if (_eigreplay) {
+        std::vector<double> B, D;
+        if (_eigreplay(_fev, _n, B, D)) {
+            if ((int) B.size() != _n * _n || (int) D.size() != _n) throw bbopt::GpuError("eigen replay: wrong basis shape");
+            gpu_check(bbgpu_cma_eig(_dev, B.data(), D.data()));
+            return;
+        }
+    }
+    gpu_check(bbgpu_cma_eig(_dev, nullptr, nullptr));
+}
+
+// cma/cmaes.cpp:151-227
+bool Cmaes::converged() {
+    if (_it >= _mit) { _flag = 1; return true; }                                  // MaxIter
+    if (_it >= _hlen && _fworst - _fbest < _tol) { _flag = 2; return true; }      // TolHistFun
+    if (_best._len >= _n && _kth._len >= _n) {                                    // EqualFunVals
+        int countEq = 0;
+        for (int i = 0; i < _n; i++) {
+            if (_best.get(i) == _kth.get(i)) {
+                countEq++;
+                if (3 * countEq >= _n) { _flag = 3; return true; }
+            }
+        }
+    }
+    int iaxis = _n - 1 - ((_it - 1) % _n);
+    iaxis = std::max(0, std::min(iaxis, _n - 1)); // _it == 0 indexes out of range in the reference
+    gpu_check(bbgpu_cma_probe(_dev, _sigma, iaxis));
+    gpu_check(bbgpu_cma_fetch(_dev, &_rep));
+    // TolX: all_i max(pc_i, sqrt(C_ii)) sigma/sigma0 < tol  <=>  the max satisfies it
+    if (!(_rep.tolx_max * _sigma / _sigma0 >= _tol)) { _flag = 4; return true; }
+    if (_sigma / _sigma0 > 1.0e20 * _rep.d_max) { _flag = 5; return true; }       // TolUpSigma
+    if (_rep.d_max > 1.0e7 * _rep.d_min) { _flag = 7; return true; }              // ConditionCov
+    if (_rep.noeffect_axis) { _flag = 8; return true; }                           // NoEffectAxis
+    if (_rep.noeffect_coor) { _flag = 9; return true; }                           // NoEffectCoor
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// ActiveCmaes -- cma/active_cmaes.cpp:42-69
+// ---------------------------------------------------------------------------------------
+void ActiveCmaes::init(const multivariate_problem &f, const double *guess) {
+    Cmaes::init(f, guess);
+    _cm = 1.;
+    _alphaold = 0.5;
+    _cc = (4. + 0. * _mueff / _n) / (_n + 4. + 0. * 2. * _mueff / _n);
+    _cs = (_mueff + 2.) / (3. + _n + _mueff);
+    _c1 = _alphacov * std::min(1., _lambda / 6.) / ((_n + 1.3) * (_n + 1.3) + _mueff);
+    _cmu = 1. - _c1;
+    _cmu = std::min(_cmu, _alphacov * (_mueff - 2. + 1. / _mueff) / ((2. + _n) * (2. + _n) + _alphacov * _mueff / 2.));
+    _cneg = (1. - _cmu) * (_alphacov / 8.) * _mueff / (std::pow(_n + 2., 1.5) + 2. * _mueff);
+    _damps = 1. + _cs + 2. * std::max(0., std::sqrt((_mueff - 1.) / (_n + 1.)) - 1.);
+    _eigenfreq = _eigenrate * (1. / (_c1 + _cmu + _cneg)) / _n;
+    _eigenlastev = 0;
+    ensureDevice();
+}
+
+void ActiveCmaes::fillConfig(bbgpu_cma_config &cfg) const {
+    BaseCmaes::fillConfig(cfg);
+    cfg.cneg = _cneg;
+    cfg.alphaold = _alphaold;
+    cfg.cm = _cm;
+}
+
+// ---------------------------------------------------------------------------------------
+// SepCmaes -- cma/sep_cmaes.cpp:40-67, 81-135, 137-207
+// ---------------------------------------------------------------------------------------
+void SepCmaes::init(const multivariate_problem &f, const double *guess) {
+    BaseCmaes::init(f, guess);
+    _cc = 4. / (_n + 4.);
+    _cs = (_mueff + 2.) / (3. + _n + _mueff);
+    _damps = 1. + _cs + 2. * std::max(0., std::sqrt((_mueff - 1.) / (_n + 1.)) - 1.);
+    _ccov = 2. / ((_n + std::sqrt(2.)) * (_n + std::sqrt(2.)) * _mueff);
+    _ccov += std::min(1., (2. * _mueff - 1.) / ((_n + 2.) * (_n + 2.) + _mueff)) * (1. - 1. / _mueff);
+    if (_adjustlr) _ccov *= ((_n + 2.) / 3.);
+    _flag = 0;
+    ensureDevice();
+}
+
+void SepCmaes::fillConfig(bbgpu_cma_config &cfg) const {
+    BaseCmaes::fillConfig(cfg);
+    cfg.ccov = _ccov;
+}
+
+void SepCmaes::updateDistribution() {
+    gpu_check(bbgpu_cma_update(_dev, _sigma, _fev));
+    fetchReport();
+    updateSigma();
+}
+
+bool SepCmaes::converged() {
+    if (_it >= _mit) { _flag = 1; return true; }
+    if (_it >= _hlen && _fworst - _fbest < _tol) { _flag = 2; return true; }
+    if (_best._len >= _n && _kth._len >= _n) {
+        int countEq = 0;
+        for (int i = 0; i < _n; i++) {
+            if (_best.get(i) == _kth.get(i)) {
+                countEq++;
+                if (3 * countEq >= _n) { _flag = 3; return true; }
+            }
+        }
+    }
+    int iaxis = _n - 1 - ((_it - 1) % _n);
+    iaxis = std::max(0, std::min(iaxis, _n - 1));
+    gpu_check(bbgpu_cma_probe(_dev, _sigma, iaxis));
+    gpu_check(bbgpu_cma_fetch(_dev, &_rep));
+    if (!(_rep.tolx_max * _sigma / _sigma0 >= _tol)) { _flag = 4; return true; }
+    // the reference indexes the UNSORTED ends _diagd[n-1] / _diagd[0] here (sep_cmaes.cpp:181,187)
+    if (_sigma / _sigma0 > 1.0e20 * _rep.d_max) { _flag = 5; return true; }
+    if (_rep.d_max > 1.0e7 * _rep.d_min) { _flag = 7; return true; }
+    if (_rep.noeffect_axis) { _flag = 8; return true; }
+    if (_rep.noeffect_coor) { _flag = 9; return true; }
+    return false;
+}

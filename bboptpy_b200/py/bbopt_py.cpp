@@ -1,0 +1,194 @@
+// pybind11 module `_bboptpy` of the accelerated path.
+//
+// Exposes the reference's Python surface for the classes on the hot path with the same class
+// names, constructor keywords and defaults (/root/reference/py/multivariate_py.cpp:99-171) and
+// the same generic methods optimize / initialize / iterate / solution (:357-420).  `f` may be
+//   * a registry objective (bboptpy_b200.Rosenbrock, ...) or a user CUDA objective -> evaluated on
+//     the GPU, the whole population per launch;
+//   * any Python callable f(x: ndarray) -> float, exactly as in the reference -> driven through the
+//     batched host-callback bridge (one device->host copy per generation).
+#include <pybind11/functional.h>
+#include <pybind11/iostream.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "cma.h"
+#include "de.h"
+#include "restart.h"
+
+namespace py = pybind11;
+using namespace pybind11::literals;
+
+namespace {
+
+multivariate_problem make_problem(py::object &py_f, py::array_t<double> &py_lower, py::array_t<double> &py_upper) {
+    const int n = (int) py_lower.size();
+    double *lower = static_cast<double*>(py_lower.request().ptr);
+    double *upper = static_cast<double*>(py_upper.request().ptr);
+    if (py::isinstance<device_objective>(py_f)) {
+        return multivariate_problem(py_f.cast<device_objective>(), n, lower, upper);
+    }
+    if (!PyCallable_Check(py_f.ptr())) throw py::type_error("f must be a registry/CUDA Objective or a callable f(x) -> float");
+    py::function fn = py::reinterpret_borrow<py::function>(py_f);
+    multivariate f = [fn, n](const double *x) -> double {
+        const auto py_x = py::array_t<double>(n, x);
+        return fn(py_x).cast<double>();
+    };
+    return multivariate_problem(f, n, lower, upper);
+}
+
+py::array_t<double> as_array(const std::vector<double> &v) {
+    return py::array_t<double>(v.size(), v.data());
+}
+
+} // namespace
+
+PYBIND11_MODULE(_bboptpy, m) {
+    m.doc() = "B200-native population engine behind bboptpy's optimizer API";
+    m.def("seed", [](unsigned s) { bbopt::Random::seed(s); }, "s"_a,
+            "Seed the host engine and the device Philox streams (the reference exposes no seed).");
+    m.def("uniform", [](double a, double b) { return bbopt::Random::get(a, b); }, "a"_a, "b"_a,
+            "One uniform_real draw from the host engine (the restart drivers' stream).");
+
+    py::class_<device_objective>(m, "Objective")
+        .def_static("builtin", [](int id) { device_objective d; d._builtin = id; return d; }, "id"_a)
+        .def_static("from_pointer", [](std::uintptr_t fn, std::uintptr_t user) {
+            device_objective d;
+            d._fn = reinterpret_cast<bbgpu_device_objective_fn>(fn);
+            d._user = reinterpret_cast<void*>(user);
+            return d;
+        }, "fn"_a, "user"_a = 0,
+        "User CUDA objective: address of `int fn(const double* d_X, int64 ld, int n, int count, double* d_f, void* stream, void* user)`")
+        .def_property_readonly("id", [](const device_objective &d) { return d._builtin; });
+    auto reg = [&](const char *name, int id) { device_objective d; d._builtin = id; m.attr(name) = d; };
+    reg("Sphere", BBGPU_OBJ_SPHERE);
+    reg("Ellipsoid", BBGPU_OBJ_ELLIPSOID);
+    reg("Rosenbrock", BBGPU_OBJ_ROSENBROCK);
+    reg("Rastrigin", BBGPU_OBJ_RASTRIGIN);
+    reg("Ackley", BBGPU_OBJ_ACKLEY);
+
+    py::class_<multivariate_solution> solution(m, "MultivariateSolution");
+    solution.def("__str__", &multivariate_solution::toString);
+    solution.def_property_readonly("x", [](multivariate_solution &self) { return as_array(self._sol); });
+    solution.def_property_readonly("converged", [](multivariate_solution &self) { return self._converged; });
+    solution.def_property_readonly("n_evals", [](multivariate_solution &self) { return self._fev; });
+
+    py::class_<MultivariateOptimizer> solver(m, "MultivariateSearch");
+    solver.def("optimize", [](MultivariateOptimizer &self, py::object py_f, py::array_t<double> py_lower,
+            py::array_t<double> py_upper, py::array_t<double> py_guess) {
+        multivariate_problem prob = make_problem(py_f, py_lower, py_upper);
+        double *guess = static_cast<double*>(py_guess.request().ptr);
+        return self.optimize(prob, guess);
+    }, "f"_a, "lower"_a, "upper"_a, "guess"_a, py::call_guard<py::scoped_ostream_redirect, py::scoped_estream_redirect>());
+    solver.def("initialize", [](MultivariateOptimizer &self, py::object py_f, py::array_t<double> py_lower,
+            py::array_t<double> py_upper, py::array_t<double> py_guess) {
+        multivariate_problem prob = make_problem(py_f, py_lower, py_upper);
+        double *guess = static_cast<double*>(py_guess.request().ptr);
+        return self.init(prob, guess);
+    }, "f"_a, "lower"_a, "upper"_a, "guess"_a, py::call_guard<py::scoped_ostream_redirect, py::scoped_estream_redirect>());
+    solver.def("iterate", &MultivariateOptimizer::iterate);
+    solver.def("solution", &MultivariateOptimizer::solution);
+
+    py::class_<BaseCmaes, MultivariateOptimizer>(m, "BaseCMAES")
+        .def("state", [](BaseCmaes &self, const std::string &name) { return as_array(self.state(name)); }, "name"_a)
+        .def("set_draw_replay", &BaseCmaes::setDrawReplay, "seed"_a,
+             "Draw replay: consume the reference's N(0,1) stream (std::mt19937(seed) + normal_distribution) in its own draw order")
+        .def("set_draw_replay_global", &BaseCmaes::setDrawReplayGlobal)
+        .def("burn_uniforms", &BaseCmaes::burnUniforms, "count"_a)
+        .def("converged", &BaseCmaes::converged)
+        .def_property_readonly("sigma", &BaseCmaes::sigma)
+        .def_property_readonly("n_evals", &BaseCmaes::evaluations)
+        .def_property_readonly("n_iters", &BaseCmaes::iterations)
+        .def_property_readonly("popsize", &BaseCmaes::lambda);
+
+    py::class_<Cmaes, BaseCmaes>(m, "CMAES")
+        .def(py::init<int, double, int, double, bool, double>(), "mfev"_a, "tol"_a, "np"_a, "sigma0"_a = 2.,
+             "bound"_a = false, "eigenrate"_a = 0.25)
+        .def("set_eigen_replay", [](Cmaes &self, py::object fn) {
+            if (fn.is_none()) { self.setEigenReplay(nullptr); return; }
+            self.setEigenReplay([fn](int fev, int n, std::vector<double> &B, std::vector<double> &D) {
+                py::object r = fn(fev, n);
+                if (r.is_none()) return false;
+                py::tuple t = r.cast<py::tuple>();
+                auto b = t[0].cast<py::array_t<double, py::array::c_style | py::array::forcecast>>();
+                auto d = t[1].cast<py::array_t<double, py::array::c_style | py::array::forcecast>>();
+                B.assign(b.data(), b.data() + b.size());
+                D.assign(d.data(), d.data() + d.size());
+                return true;
+            });
+        }, "fn"_a, "Eigenbasis replay: fn(fev, n) -> None or (B, D) imposed at each decomposition event")
+        .def_property_readonly("flag", &Cmaes::flag)
+        .def_property_readonly("n_decompositions", &Cmaes::decompositions);
+
+    py::class_<ActiveCmaes, Cmaes>(m, "ActiveCMAES")
+        .def(py::init<int, double, int, double, bool, double, double>(), "mfev"_a, "tol"_a, "np"_a, "sigma0"_a = 2.,
+             "bound"_a = false, "alphacov"_a = 2., "eigenrate"_a = 0.25);
+
+    py::class_<SepCmaes, BaseCmaes>(m, "SepCMAES")
+        .def(py::init<int, double, int, double, bool, bool>(), "mfev"_a, "tol"_a, "np"_a, "sigma0"_a = 2.,
+             "bound"_a = false, "adjustlr"_a = true)
+        .def_property_readonly("flag", &SepCmaes::flag);
+
+    py::class_<IPopCmaes, MultivariateOptimizer>(m, "IPopCMAES")
+        .def(py::init<BaseCmaes*, int, bool, double, bool, double, bool>(), "base"_a, "mfev"_a, "print"_a = false,
+             "sigma0"_a = 2., "nipop"_a = true, "ksigmadec"_a = 1.6, "boundlambda"_a = true, py::keep_alive<1, 2>())
+        .def_property_readonly("n_evals", &IPopCmaes::evaluations);
+
+    py::class_<BiPopCmaes, MultivariateOptimizer>(m, "BiPopCMAES")
+        .def(py::init<BaseCmaes*, int, bool, double, int, bool, double, double>(), "base"_a, "mfev"_a, "print"_a = false,
+             "sigma0"_a = 2., "maxlargeruns"_a = 9, "nbipop"_a = true, "ksigmadec"_a = 1.6, "kbudget"_a = 2.,
+             py::keep_alive<1, 2>())
+        .def_property_readonly("n_evals", &BiPopCmaes::evaluations)
+        .def_property_readonly("large_restarts", &BiPopCmaes::largeRestarts)
+        .def_property_readonly("small_restarts", &BiPopCmaes::smallRestarts);
+
+    py::class_<DeSearchBase, MultivariateOptimizer>(m, "BaseDE")
+        .def("swarm", [](DeSearchBase &self) {
+            std::vector<double> x = self.swarm();
+            const int np = self.population();
+            py::array_t<double> a({ (py::ssize_t) np, (py::ssize_t) (np ? x.size() / np : 0) });
+            std::copy(x.begin(), x.end(), a.mutable_data());
+            return a;
+        })
+        .def("fitness", [](DeSearchBase &self) { return as_array(self.fitness()); })
+        .def("set_initial_population", [](DeSearchBase &self, py::array_t<double, py::array::c_style | py::array::forcecast> x) {
+            self.setInitialPopulation(std::vector<double>(x.data(), x.data() + x.size()));
+        }, "x"_a)
+        .def("set_draw_replay", [](DeSearchBase &self, py::object fn) {
+            if (fn.is_none()) { self.setDrawReplay(nullptr); return; }
+            self.setDrawReplay([fn](int gen, de_generation_draws &d) {
+                py::object r = fn(gen);
+                if (r.is_none()) return false;
+                py::dict t = r.cast<py::dict>();
+                auto dv = [&](const char *k, std::vector<double> &out) {
+                    if (!t.contains(k)) return;
+                    auto a = t[k].cast<py::array_t<double, py::array::c_style | py::array::forcecast>>();
+                    out.assign(a.data(), a.data() + a.size());
+                };
+                auto iv = [&](const char *k, std::vector<int32_t> &out) {
+                    if (!t.contains(k)) return;
+                    auto a = t[k].cast<py::array_t<double, py::array::c_style | py::array::forcecast>>();
+                    out.resize(a.size());
+                    for (py::ssize_t i = 0; i < a.size(); i++) out[i] = (int32_t) a.data()[i];
+                };
+                dv("zcr", d.zcr); dv("cauchy", d.cauchy); dv("u", d.u); dv("pi", d.pi);
+                iv("ibest", d.ibest); iv("r1", d.r1); iv("r2", d.r2); iv("jrand", d.jrand); iv("slot", d.slot);
+                iv("ri", d.ri); iv("trim", d.trim);
+                return true;
+            });
+        }, "fn"_a, "Draw replay: fn(generation) -> None or the oracle recorder's tagged-draw dict")
+        .def_property_readonly("n_evals", &DeSearchBase::evaluations)
+        .def_property_readonly("popsize", &DeSearchBase::population)
+        .def_property_readonly("rounds", [](DeSearchBase &self) { return self.report().rounds; })
+        .def_property_readonly("mucr", [](DeSearchBase &self) { return self.report().mucr; })
+        .def_property_readonly("muf", [](DeSearchBase &self) { return self.report().muf; });
+
+    py::class_<JadeSearch, DeSearchBase>(m, "JADE")
+        .def(py::init<int, int, double, bool, bool, double, double, double>(), "mfev"_a, "np"_a, "tol"_a,
+             "archive"_a = true, "repaircr"_a = true, "pelite"_a = 0.05, "cdamp"_a = 0.1, "sigma"_a = 0.07);
+
+    py::class_<ShadeSearch, DeSearchBase>(m, "SHADE")
+        .def(py::init<int, int, double, bool, bool, int, int>(), "mfev"_a, "npinit"_a, "tol"_a, "archive"_a = true,
+             "repaircr"_a = true, "h"_a = 100, "npmin"_a = 4);
+}

@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl own|reference]
+
+Workload (BASELINE.json `metric`): full-covariance CMA-ES (reference class `Cmaes`), n = 1000,
+lambda = 4096, Rosenbrock on [-10,10]^n, synthetic data.  A step = one generation of the hot path
+(sample -> evaluate -> rank -> update, sigma update on the host from the per-generation report).
+The lazy eigendecomposition is off the per-generation path and timed separately, as the north star
+specifies; `eig` carries its time and the generations/s including it at the reference's cadence.
+The same JSON line also carries the DE half of the metric (JADE / L-SHADE candidate-evals/s,
+n = 1000, np = 1000, Rastrigin) under "de".
+
+N > 1 (torchrun, one rank per GPU): independent runs sharded per GPU (weak scaling), max over
+ranks of the device time, final best-of reduce over NCCL.
+
+--impl reference: the reference's own CPU implementation (oracle/_ref, the unmodified sources
+compiled in place; else the pinned port) on the host cores, same metric/config, each step a
+bounded sample (lambda_s = 256 candidates, linearly scaled; see cpu_sample()).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DIM, LAMBDA, BOX = 1000, 4096, 10.0
+DE_N, DE_NP, DE_BOX = 1000, 1000, 5.12
+METRIC = "CMA-ES generations/s (n=1000, lambda=4096)"
+UNIT = "generations/s"
+WORKLOAD = "Cmaes n=1000 lambda=4096 mu=2048 Rosenbrock box=[-10,10]^n fp64 (BASELINE.json metric config)"
+
+
+def fp64_peak():
+    """fp64 denominator: MEASURED_PEAKS.json has no fp64 entry and the profiling guide states no fp64
+    fallback, so the denominator is our own cuBLAS DGEMM 8192^3 measurement on this pool's B200
+    (tools/measure_fp64_peak.py -> profiles/r01_fp64_peak.json)."""
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "fp64_tflops" in mp:
+            return float(mp["fp64_tflops"]), "MEASURED_PEAKS.json fp64_tflops (of measured)"
+    except Exception:
+        pass
+    try:
+        pk = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))
+        return float(pk["cublas_dgemm_8192_tflops_burst"]), ("profiles/r01_fp64_peak.json: cuBLAS DGEMM 8192^3 burst on "
+                                                             "this pool's B200 (of measured; MEASURED_PEAKS.json has no fp64 entry)")
+    except Exception:
+        return 37.0, "nominal B200 fp64 (no measurement available)"
+
+
+def hbm_peak():
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def all_max(dist, local, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def all_min_with_owner(dist, local, rank, value):
+    """final best-of reduce over NCCL: (min fitness, owning rank)"""
+    if dist is None:
+        return value, rank
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    gathered = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(gathered, t)
+    vals = [float(g.item()) for g in gathered]
+    owner = int(np.argmin(vals))
+    return vals[owner], owner
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize(local)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the reference (or the pinned port) on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle():
+    from oracle import oracle as O
+    if O.have_ref():
+        return O.ref(), "reference"
+    O.build(("port",))
+    return O.port(), "port"
+
+
+def cpu_sample(o, lam_s=256, seed=1):
+    """One generation of the CPU implementation at (n=1000, lambda_s) timed by phase, scaled to lambda=4096:
+    sampling, evaluation and the mean/rank-mu loops are linear in lambda; the eigendecomposition (every
+    generation at this configuration, cma/cmaes.cpp:48,233) and the O(n^2) path updates are not."""
+    from oracle import oracle as O
+    o.seed(seed)
+    n = N_DIM
+    h = o.cma(O.VANILLA, 10 ** 9, 1e-12, lam_s)
+    guess = o.uniform(-BOX, BOX, n)
+    h.init(O.ROSENBROCK, -BOX * np.ones(n), BOX * np.ones(n), guess)
+    t0 = time.perf_counter()
+    h.sample()
+    t1 = time.perf_counter()
+    h.evalsort()
+    t2 = time.perf_counter()
+    h.update()
+    t3 = time.perf_counter()
+    t_eig = h.time_eig()
+    scale = LAMBDA / lam_s
+    lin = (t1 - t0) + (t2 - t1) + max((t3 - t2) - t_eig, 0.0)
+    t_gen = lin * scale + t_eig
+    return {"t_sample": t1 - t0, "t_evalsort": t2 - t1, "t_update_incl_eig": t3 - t2, "t_eig": t_eig, "scale": scale,
+            "t_generation_scaled": t_gen, "gens_per_s": 1.0 / t_gen, "gens_per_s_excl_eig": 1.0 / (lin * scale)}
+
+
+def cpu_de_sample(o, kind, gens=3, seed=1):
+    from oracle import oracle as O
+    o.seed(seed)
+    h = o.de(kind, 10 ** 7, DE_NP, 1e-12)
+    h.init(O.RASTRIGIN, -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N))
+    t0 = time.perf_counter()
+    for _ in range(gens):
+        h.iterate()
+    return DE_NP * gens / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    o, kind = cpu_oracle()
+    budget = 200.0
+    t_start = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(o)
+    samples = []
+    for k in range(args.steps):
+        samples.append(cpu_sample(o, seed=1 + k))
+        if time.perf_counter() - t_start > budget:
+            break
+    t_gen = float(np.mean([s["t_generation_scaled"] for s in samples]))
+    value = 1.0 / t_gen
+    de = {"jade_evals_per_s": cpu_de_sample(o, 0), "shade_evals_per_s": cpu_de_sample(o, 1), "unit": "candidate-evals/s",
+          "sample": "3 generations each, n=1000 np=1000 Rastrigin, 1 thread"}
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(samples),
+        "warmup": min(args.warmup, 1), "ms_per_step": t_gen * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": "each step: one generation of the CPU implementation at n=1000 with lambda_s=256 candidates, timed by "
+                                   "phase; the lambda-linear phases scaled x16 to lambda=4096, the eigendecomposition (every generation at "
+                                   "this configuration) counted once; the reference is single-threaded (process-global RNG)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "eig": {"ms": float(np.mean([s["t_eig"] for s in samples])) * 1e3, "cadence_generations": 1,
+                "gens_per_s_excl_eig": float(np.mean([s["gens_per_s_excl_eig"] for s in samples]))},
+        "de": de,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def bench_cma_device(ctx, steps, warmup, seed):
+    """`value`: generations/s with everything resident in HBM; one fetch of the 104-byte report per generation."""
+    from bboptpy_b200 import _cabi
+    from bboptpy_b200.strategy import cma_constants, flops_per_generation, update_sigma
+    n, lam = N_DIM, LAMBDA
+    w, c = cma_constants(0, n, lam)
+    rng = np.random.default_rng(seed)
+    guess = rng.uniform(-BOX, BOX, n)
+    g = _cabi.Cma(ctx, _cabi.CMA_FULL, n, lam, w, c, seed=seed)
+    g.reset(guess)
+    obj = _cabi.Objective(ctx, n, builtin=_cabi.OBJ_ROSENBROCK)
+    state = {"sigma": 2.0, "fev": 0, "gen": 0}
+
+    def step():
+        state["fev"] += lam
+        g.generation(obj, state["sigma"], state["gen"], c["ik"], state["fev"])
+        rep = g.fetch()
+        state["sigma"] = update_sigma(state["sigma"], rep.pslen, c, rep.ybw[0], rep.f_kth)
+        state["gen"] += 1
+        return rep
+
+    for i in range(warmup):
+        step()
+        if i == 0:
+            g.eig()  # a dense basis from here on
+    g.fetch()
+    ctx.profile_reset()
+    ctx.profile(True)
+    launches0 = ctx.launches
+    times = []
+    rep = None
+    for _ in range(steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        rep = step()
+        times.append(ctx.timer_stop())
+    launches = ctx.launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    # the decomposition, timed separately (north star): syevd + clamps + C^-1/2 rebuild
+    eig_ms = []
+    for _ in range(3):
+        ctx.timer_start()
+        g.eig()
+        eig_ms.append(ctx.timer_stop())
+    g.fetch()
+    return {"times_ms": times, "launches": launches, "prof": prof, "eig_ms": float(np.median(eig_ms)), "fbest": rep.ybw[0],
+            "flops": flops_per_generation(0, n, lam)}
+
+
+def bench_cma_e2e(pkg, gens, seed):
+    """Through the reference-facing API with host buffers: optimize(f, lower, upper, guess) -> solution.
+    Includes init uploads, the eigendecomposition at the reference's cadence (every generation here), the per-generation
+    report reads and the final solution download."""
+    n, lam = N_DIM, LAMBDA
+    rng = np.random.default_rng(seed)
+    lower, upper, guess = -BOX * np.ones(n), BOX * np.ones(n), rng.uniform(-BOX, BOX, n)
+    alg = pkg.CMAES(mfev=gens * lam, tol=0.0, np=lam)
+    t0 = time.perf_counter()
+    sol = alg.optimize(pkg.Rosenbrock, lower, upper, guess)
+    dt = time.perf_counter() - t0
+    done = sol.n_evals // lam
+    h2d = (3 * n + lam // 2) * 8 / max(done, 1)           # lower, upper, guess, weights per optimize()
+    d2h = 2 * 104 + n * 8 / max(done, 1)                  # report after update + after probe; final x once
+    return done / dt, dt, done, h2d, d2h, alg.n_decompositions
+
+
+def bench_de_device(ctx, kind, steps, warmup, seed):
+    from bboptpy_b200 import _cabi
+    lo, hi = -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N)
+    g = _cabi.De(ctx, kind, DE_N, DE_NP, lo, hi, mfev=10 ** 7, seed=seed)
+    obj = _cabi.Objective(ctx, DE_N, builtin=_cabi.OBJ_RASTRIGIN)
+    g.init(obj)
+    for _ in range(warmup):
+        g.generation(obj)
+    ctx.profile_reset()
+    ctx.profile(True)
+    times, rounds, evals = [], [], 0
+    for _ in range(steps):
+        npop = g.np
+        ctx.flush_l2()
+        ctx.timer_start()
+        rep = g.generation(obj)
+        times.append(ctx.timer_stop())
+        rounds.append(rep.rounds)
+        evals += npop
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    return {"evals_per_s": evals / (sum(times) / 1e3), "ms_per_generation": float(np.mean(times)), "rounds_mean": float(np.mean(rounds)),
+            "round_kernel_ms_avg": prof.get("de_round", {}).get("ms_avg"), "fbest": rep.fbest}
+
+
+def bench_de_e2e(pkg, cls, gens, seed):
+    lo, hi = -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N)
+    if cls == "JADE":
+        alg = pkg.JADE(mfev=DE_NP * (gens + 1), np=DE_NP, tol=0.0)
+    else:
+        alg = pkg.SHADE(mfev=DE_NP * (gens + 1), npinit=DE_NP, tol=0.0, npmin=DE_NP)
+    t0 = time.perf_counter()
+    sol = alg.optimize(pkg.Rastrigin, lo, hi, lo)
+    dt = time.perf_counter() - t0
+    return sol.n_evals / dt
+
+
+def run_own(args):
+    rank, world, local, dist = dist_setup(args.gpus)
+    import __graft_entry__ as entry
+    if rank == 0 and not os.path.exists(os.path.join(ROOT, "bboptpy_b200", "libbbgpu.so")):
+        entry.build()
+    barrier(dist, local)
+    os.environ["BBOPT_DEVICE"] = str(local)
+    import bboptpy_b200 as pkg
+    from bboptpy_b200 import _cabi
+    ctx = _cabi.Context(local)  # raises without a GPU: there is no CPU path to fall back to
+    pkg.seed(1000 + rank)
+    sampler = ClockSampler(local)
+    barrier(dist, local)
+    sampler.start()
+    res = bench_cma_device(ctx, args.steps, args.warmup, seed=1 + rank)
+    clocks = sampler.stop()
+    barrier(dist, local)
+    t_local = sum(res["times_ms"]) / 1e3
+    t_max = all_max(dist, local, t_local)
+    value = world * args.steps / t_max
+    fbest, owner = all_min_with_owner(dist, local, rank, res["fbest"])
+    # e2e through the public API
+    e2e_gens = max(3, min(args.steps, 10))
+    bench_cma_e2e(pkg, 2, seed=1 + rank)  # first-call costs (cuSOLVER handle, workspace) are not part of a step
+    barrier(dist, local)
+    e_val, e_dt, e_done, h2d, d2h, ndec = bench_cma_e2e(pkg, e2e_gens, seed=1 + rank)
+    e_dt_max = all_max(dist, local, e_dt)
+    e2e_value = world * e_done / e_dt_max
+    # DE half of the metric
+    de = {}
+    de_steps = max(10, min(5 * args.steps, 100))
+    for name, kind in (("jade", 0), ("shade", 1)):
+        r = bench_de_device(ctx, kind, de_steps, max(args.warmup, 3), seed=7 + rank)
+        t_de = all_max(dist, local, DE_NP * de_steps / r["evals_per_s"])
+        r["evals_per_s"] = world * DE_NP * de_steps / t_de
+        r["e2e_evals_per_s"] = bench_de_e2e(pkg, name.upper(), de_steps, seed=7 + rank) * world
+        de[name] = r
+    if rank != 0:
+        return
+    peak, peak_src = fp64_peak()
+    hbm, hbm_src = hbm_peak()
+    sg = res["prof"].get("sample_gemm", {})
+    sg_ms = sg.get("ms_avg")
+    achieved = 2.0 * LAMBDA * N_DIM * N_DIM / (sg_ms * 1e-3) / 1e12 if sg_ms else None
+    ms_step = t_max * 1e3 / args.steps
+    step_flops = res["flops"]
+    shares = {k: v["ms_total"] / sum(res["times_ms"]) for k, v in res["prof"].items()}
+    for name in ("jade", "shade"):
+        de[name]["roofline"] = {"bound": "hbm", "achieved": de[name]["evals_per_s"] / world * 5 * 8 * DE_N / 1e9, "peak": hbm,
+                                "unit": "GB/s", "frac": de[name]["evals_per_s"] / world * 5 * 8 * DE_N / 1e9 / hbm, "traffic": None,
+                                "peak_source": hbm_src, "algorithmic_bytes_per_eval": 5 * 8 * DE_N}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": "sample -> evaluate -> rank -> update; sigma on the host from the 104-byte report",
+                   "draws": "device Philox4x32-10 + Box-Muller", "parallelism": f"independent runs x{world}" if world > 1 else "single run",
+                   "l2": "L2 flushed (256 MB memset) before every timed generation, outside the event bracket"},
+        "clocks": clocks, "gpu_launches": int(res["launches"]),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": f"optimize(f, lower, upper, guess) through the pybind API, {e_done} generations, "
+                        f"{ndec} eigendecompositions inside the timed region (reference cadence)"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "kernel": "gemm_f64_kernel<FORM1,SAMPLE> (DMMA.8x8x4): X = m + sigma Z (B D)^T", "kernel_ms_avg": sg_ms,
+                     "algorithmic_flops_per_launch": 2.0 * LAMBDA * N_DIM * N_DIM, "peak_source": peak_src,
+                     "generation_tflops": step_flops / (ms_step * 1e-3) / 1e12 * world,
+                     "generation_frac_of_peak": step_flops / (ms_step * 1e-3) / 1e12 / peak,
+                     "kernel_share_of_step": shares},
+        "eig": {"ms": res["eig_ms"], "cadence_generations": 1, "solver": "cuSOLVER syevd + DMMA C^-1/2 rebuild",
+                "gens_per_s_incl_eig": world / ((ms_step + res["eig_ms"]) * 1e-3)},
+        "best_of": {"f": fbest, "rank": owner},
+        "de": de,
+    }
+    if world == 1:
+        o, kind = cpu_oracle()
+        cs = cpu_sample(o)
+        line["cpu_baseline"] = {"value": cs["gens_per_s"], "unit": UNIT, "cores": 1, "kind": kind,
+                                "sample": "one generation of the CPU implementation at n=1000, lambda_s=256, timed by phase; lambda-linear "
+                                          "phases scaled x16 to lambda=4096, eigendecomposition counted once per generation",
+                                "gens_per_s_excl_eig": cs["gens_per_s_excl_eig"], "t_eig_s": cs["t_eig"],
+                                "de_jade_evals_per_s": cpu_de_sample(o, 0), "de_shade_evals_per_s": cpu_de_sample(o, 1)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,30 @@ void *bbgpu_ctx_stream(bbgpu_ctx *ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py gpu_launches) */
 int64_t bbgpu_ctx_launch_count(bbgpu_ctx *ctx);
 
+/* ---- measurement helpers (bench.py): CUDA-event timers on the ctx stream, per-kernel device-time
+ * accounting, and an L2 flush (writes a buffer larger than the 126 MB L2). */
+enum bbgpu_profile_tag {
+    BBGPU_PROF_SAMPLE_GEMM = 0, /* X = m + sigma Z (B D)^T                 */
+    BBGPU_PROF_COV_SYRK = 1,    /* rank-mu / active covariance update      */
+    BBGPU_PROF_NORM_GEMM = 2,   /* active: Mahalanobis norms               */
+    BBGPU_PROF_EVAL = 3,
+    BBGPU_PROF_RANK = 4,
+    BBGPU_PROF_PHILOX = 5,
+    BBGPU_PROF_EIG = 6,         /* syevd + C^-1/2 rebuild                  */
+    BBGPU_PROF_UPDATE_MISC = 7, /* gather, recombination, paths            */
+    BBGPU_PROF_SEP_SAMPLE = 8,
+    BBGPU_PROF_DE_ROUND = 9,
+    BBGPU_PROF_DE_MISC = 10,
+    BBGPU_PROF_TAGS = 11
+};
+int bbgpu_ctx_profile_enable(bbgpu_ctx *ctx, int on);
+/* synchronises, then returns summed device milliseconds and number of timed launches for tag */
+int bbgpu_ctx_profile_read(bbgpu_ctx *ctx, int tag, double *total_ms, int64_t *count);
+int bbgpu_ctx_profile_reset(bbgpu_ctx *ctx);
+int bbgpu_ctx_timer_start(bbgpu_ctx *ctx);
+int bbgpu_ctx_timer_stop(bbgpu_ctx *ctx, float *ms); /* records, synchronises, returns elapsed */
+int bbgpu_ctx_flush_l2(bbgpu_ctx *ctx);
+
 /* ---- objectives.  Replaces the per-candidate callback `_f._f(const double*)`
  * (cma/base_cmaes.cpp:214-217, de/jade.cpp:159) by batched device evaluation. */
 enum bbgpu_builtin_objective {
@@ -150,6 +174,9 @@ int bbgpu_cma_reset(bbgpu_cma *h, const double *h_guess, int keep_offdiag);
 int bbgpu_cma_set(bbgpu_cma *h, int field, const double *h_src, int64_t count);
 int bbgpu_cma_get(bbgpu_cma *h, int field, double *h_dst, int64_t count);
 int bbgpu_cma_get_rank(bbgpu_cma *h, int32_t *h_idx, int count);
+/* rows [row0, row0+rows) of a matrix field (e.g. one candidate of ARX: bestSolution(),
+ * cma/base_cmaes.cpp:232-238) */
+int bbgpu_cma_get_rows(bbgpu_cma *h, int field, int64_t row0, int64_t rows, double *h_dst);
 /* device pointer + leading dimension of a field (for user kernels / collectives) */
 int bbgpu_cma_device_ptr(bbgpu_cma *h, int field, void **d_ptr, int64_t *ld);
 

@@ -51,6 +51,9 @@ int bbo_cma_geti(void *h, const char *name);
 double bbo_cma_getd(void *h, const char *name);
 /* copies up to cap doubles, returns the field length (call with cap=0 to size) */
 int bbo_cma_getv(void *h, const char *name, double *out, int cap);
+/* CPU-baseline helper: force one eigenDecomposition() of the current C (cma/cmaes.cpp:229-283)
+ * past the lazy gate and return its wall time in seconds (0 for the separable variant) */
+double bbo_cma_time_eig(void *h);
 /* reset the optimizer's own normal_distribution cache (public _Z member) */
 void bbo_cma_reset_z(void *h);
 

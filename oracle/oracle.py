@@ -45,6 +45,8 @@ def _bind(lib):
     lib.bbo_cma_set_params.argtypes = [vp, i, d, i]
     for name in ("sample", "evalsort", "update", "history", "iterate", "reset_z"):
         getattr(lib, "bbo_cma_" + name).argtypes = [vp]
+    lib.bbo_cma_time_eig.argtypes = [vp]
+    lib.bbo_cma_time_eig.restype = d
     lib.bbo_cma_converged.argtypes = [vp]
     lib.bbo_cma_converged.restype = i
     lib.bbo_cma_optimize.argtypes = [vp, i, i, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.POINTER(i)]
@@ -171,6 +173,9 @@ class OracleCma:
 
     def reset_z(self):
         self.lib.bbo_cma_reset_z(self.h)
+
+    def time_eig(self):
+        return self.lib.bbo_cma_time_eig(self.h)
 
     def converged(self):
         return bool(self.lib.bbo_cma_converged(self.h))

@@ -16,6 +16,7 @@
  * Build: oracle/Makefile (g++ -O2 -ffp-contract=off).
  */
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -1125,6 +1126,15 @@ int bbo_cma_getv(void *h, const char *name, double *out, int cap) {
 }
 
 void bbo_cma_reset_z(void *h) { static_cast<PortCma*>(h)->Z.reset(); }
+
+double bbo_cma_time_eig(void *h) {
+    PortCma *p = static_cast<PortCma*>(h);
+    if (p->kind == 2) return 0.0;
+    p->eigenlastev = p->fev - static_cast<int>(p->eigenfreq) - 1;
+    const auto t0 = std::chrono::steady_clock::now();
+    p->eigen();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 
 /* ---- restart drivers: cma/ipop_cmaes.cpp:65-189 and cma/bipop_cmaes.cpp:61-267 */
 int bbo_restart_optimize(int kind, void *base, int mfev, double sigma0, int flag,

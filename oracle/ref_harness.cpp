@@ -13,6 +13,7 @@
  * process-global engine (random.hpp:677-680).
  */
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -74,6 +75,7 @@ struct CmaProbe {
     virtual double getd(const std::string &k) = 0;
     virtual int getv(const std::string &k, double *out, int cap) = 0;
     virtual void reset_z() = 0;
+    virtual double time_eig() { return 0.0; }
     std::vector<double> lower, upper, guess;
     multivariate_problem prob;
 };
@@ -133,6 +135,12 @@ template<class T> struct FullProbe: public T, public CmaProbe {
     using T::T;
     BaseCmaes *base() override { return this; }
     void reset_z() override { this->_Z.reset(); }
+    double time_eig() override {
+        this->_eigenlastev = this->_fev - static_cast<int>(this->_eigenfreq) - 1;
+        const auto t0 = std::chrono::steady_clock::now();
+        this->eigenDecomposition();
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
     int geti(const std::string &k) override {
         BASE_GETI(k)
         if (k == "eigenlastev") return this->_eigenlastev;
@@ -359,6 +367,7 @@ int bbo_cma_getv(void *h, const char *name, double *out, int cap) {
     return static_cast<CmaProbe*>(h)->getv(name, out, cap);
 }
 void bbo_cma_reset_z(void *h) { static_cast<CmaProbe*>(h)->reset_z(); }
+double bbo_cma_time_eig(void *h) { return static_cast<CmaProbe*>(h)->time_eig(); }
 
 int bbo_restart_optimize(int kind, void *base, int mfev, double sigma0, int flag,
         double ksigmadec, int boundlambda, int maxlargeruns, double kbudget, int obj, int n,
