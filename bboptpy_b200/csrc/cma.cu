@@ -632,7 +632,7 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
         A(&h->BDit, (size_t) n * ldn); A(&h->isC, (size_t) n * ldn);
         A(&h->Ysel, (size_t) h->nsel * ldn);
         if (h->active) {
-            h->rowsq_tiles_cap = ceil_div(n, 112);
+            h->rowsq_tiles_cap = ceil_div(n, 64);
             A(&h->rowsq_part, (size_t) h->rowsq_tiles_cap * h->mu);
         }
     } else {

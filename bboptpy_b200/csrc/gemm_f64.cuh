@@ -21,17 +21,16 @@
 // store (covariance).
 #pragma once
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace bb {
 
-constexpr int G_BM = 128;     // CTA tile rows
 constexpr int G_BK = 16;      // k chunk per pipeline stage
 constexpr int G_STAGES = 4;
 constexpr int G_THREADS = 256;
 constexpr int G_LDA1 = G_BK + 4;  // FORM1 A tile pitch  [BM][20]
-constexpr int G_LDA2 = G_BM + 4;  // FORM2 A tile pitch  [BK][132]
-constexpr int G_ASZ = (G_BM * G_LDA1 > G_BK * G_LDA2) ? G_BM * G_LDA1 : G_BK * G_LDA2;
 
 enum { EPI_STORE = 0, EPI_SAMPLE = 1, EPI_ROWSQ = 2, EPI_SYRK = 3 };
 
@@ -52,11 +51,15 @@ struct GemmArgs {
     double *partial;      // ROWSQ: partial[tileN * M + row]
 };
 
-template<int NA> struct GemmSmem {
+// CTA = 8 warps as 4 (M) x 2 (N); a warp owns MA x NA DMMA atoms -> CTA tile (32 MA) x (16 NA)
+template<int MA, int NA> struct GemmSmem {
+    static constexpr int BM = MA * 32;
     static constexpr int BN = NA * 16;
+    static constexpr int LDA2 = BM + 4; // FORM2 A tile pitch [BK][BM+4]
     static constexpr int LDB = BN + 4;
+    static constexpr int ASZ = (BM * G_LDA1 > G_BK * LDA2) ? BM * G_LDA1 : G_BK * LDA2;
     static constexpr int BSZ = G_BK * LDB;
-    static constexpr int STAGE = G_ASZ + BSZ + G_BK; // doubles per stage (A, B, kscale)
+    static constexpr int STAGE = ASZ + BSZ + G_BK; // doubles per stage (A, B, kscale)
     static constexpr size_t BYTES = (size_t) STAGE * G_STAGES * sizeof(double);
 };
 
@@ -96,10 +99,13 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int64_t
     }
 }
 
-template<int FORM, int NA, int EPI>
-__global__ void __launch_bounds__(G_THREADS, 1) gemm_f64_kernel(const GemmArgs p) {
-    using S = GemmSmem<NA>;
+template<int FORM, int MA, int NA, int EPI>
+__global__ void __launch_bounds__(G_THREADS, (MA * NA <= 8) ? 2 : 1) gemm_f64_kernel(const GemmArgs p) {
+    using S = GemmSmem<MA, NA>;
     constexpr int BN = S::BN;
+    constexpr int G_BM = S::BM;
+    constexpr int G_LDA2 = S::LDA2;
+    constexpr int G_ASZ = S::ASZ;
     extern __shared__ __align__(16) double smem[];
 
     const int tiles_n = (p.N + BN - 1) / BN;
@@ -111,9 +117,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_f64_kernel(const GemmArgs p
     const int wm = warp >> 1, wn = warp & 1; // 4 x 2 warps
     const int g = lane >> 2, t = lane & 3;
 
-    double acc[4][NA][2];
+    double acc[MA][NA][2];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < MA; i++)
 #pragma unroll
         for (int j = 0; j < NA; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -147,20 +153,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_f64_kernel(const GemmArgs p
         const double *Ks = Bs + S::BSZ;
 #pragma unroll
         for (int ks = 0; ks < G_BK / 4; ks++) {
-            double a[4], b[NA];
+            double a[MA], b[NA];
             const int kk = ks * 4 + t;
             if (FORM == 1) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) a[i] = As[(wm * 32 + i * 8 + g) * G_LDA1 + kk];
+                for (int i = 0; i < MA; i++) a[i] = As[(wm * (MA * 8) + i * 8 + g) * G_LDA1 + kk];
             } else {
                 const double sc = (p.kscale != nullptr) ? Ks[kk] : 1.0;
 #pragma unroll
-                for (int i = 0; i < 4; i++) a[i] = As[kk * G_LDA2 + wm * 32 + i * 8 + g] * sc;
+                for (int i = 0; i < MA; i++) a[i] = As[kk * G_LDA2 + wm * (MA * 8) + i * 8 + g] * sc;
             }
 #pragma unroll
             for (int j = 0; j < NA; j++) b[j] = Bs[kk * S::LDB + wn * (NA * 8) + j * 8 + g];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int i = 0; i < MA; i++)
 #pragma unroll
                 for (int j = 0; j < NA; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
@@ -170,9 +176,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_f64_kernel(const GemmArgs p
     // ---- epilogue.  Lane (g,t) holds C[row g][cols 2t, 2t+1] of every atom.
     if (EPI == EPI_ROWSQ) {
         __syncthreads(); // all warps are done reading the operand ring; reuse it
-        double *rs = smem; // [2][128]
+        double *rs = smem; // [2][BM]
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < MA; i++) {
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < NA; j++) {
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_f64_kernel(const GemmArgs p
             }
             s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
             s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 2));
-            if (t == 0) rs[wn * G_BM + wm * 32 + i * 8 + g] = s;
+            if (t == 0) rs[wn * G_BM + wm * (MA * 8) + i * 8 + g] = s;
         }
         __syncthreads();
         if (threadIdx.x < G_BM) {
@@ -194,8 +200,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_f64_kernel(const GemmArgs p
     double c2 = 0.0;
     if (EPI == EPI_SYRK) c2 = *p.dscal;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int row = m0 + wm * 32 + i * 8 + g;
+    for (int i = 0; i < MA; i++) {
+        const int row = m0 + wm * (MA * 8) + i * 8 + g;
         if (row >= p.M) continue;
 #pragma unroll
         for (int j = 0; j < NA; j++) {
@@ -223,32 +229,50 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_f64_kernel(const GemmArgs p
     }
 }
 
-template<int FORM, int NA, int EPI>
-inline int launch_gemm_na(bbgpu_ctx *ctx, const GemmArgs &a) {
-    using S = GemmSmem<NA>;
-    BB_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<FORM, NA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template<int FORM, int MA, int NA, int EPI>
+inline int launch_gemm_tile(bbgpu_ctx *ctx, const GemmArgs &a) {
+    using S = GemmSmem<MA, NA>;
+    BB_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<FORM, MA, NA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) S::BYTES));
-    const int tiles = ceil_div(a.M, G_BM) * ceil_div(a.N, S::BN);
-    gemm_f64_kernel<FORM, NA, EPI><<<tiles, G_THREADS, S::BYTES, ctx->stream>>>(a);
+    const int tiles = ceil_div(a.M, S::BM) * ceil_div(a.N, S::BN);
+    gemm_f64_kernel<FORM, MA, NA, EPI><<<tiles, G_THREADS, S::BYTES, ctx->stream>>>(a);
     return launched(ctx, "gemm_f64_kernel");
 }
 
-// pick the N-tile width (112 or 128) that wastes fewer tile-waves on this device
+// number of tiles the kernel actually works on (SYRK skips tiles strictly above the diagonal)
+inline int64_t live_tiles(int M, int N, int BM, int BN, bool lower_only) {
+    const int64_t tm = ceil_div(M, BM), tn = ceil_div(N, BN);
+    if (!lower_only) return tm * tn;
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < tm; i++) cnt += std::min<int64_t>(tn, (i * BM + BM - 1) / BN + 1);
+    return cnt;
+}
+
+// pick the CTA tile (128x112, 128x128 or 64x64) that needs the least tile-waves x tile-area on this
+// device.  The small tile matters for the covariance SYRK: n = 1000 has only 44 lower 128x112 tiles
+// for 148 SMs, but 136 lower 64x64 tiles (one full wave).
 template<int FORM, int EPI>
 inline int launch_gemm(bbgpu_ctx *ctx, const GemmArgs &a, int *tiles_n_out = nullptr) {
     if (a.M <= 0 || a.N <= 0) return BBGPU_OK;
     if ((a.lda & 1) || (a.ldb & 1) || (((uintptr_t) a.A) & 15) || (((uintptr_t) a.B) & 15))
         return fail(BBGPU_ERR_ARG, "gemm operands must be 16-byte aligned with even leading dimensions");
-    const int64_t tm = ceil_div(a.M, G_BM);
-    const int64_t t7 = tm * ceil_div(a.N, 112), t8 = tm * ceil_div(a.N, 128);
-    const int64_t cost7 = (int64_t) ceil_div(t7, ctx->sm_count) * 112, cost8 = (int64_t) ceil_div(t8, ctx->sm_count) * 128;
-    // ROWSQ consumers need to know the partial count, so the choice is reported back
-    if (cost7 < cost8) {
+    const bool lower = EPI == EPI_SYRK;
+    const int sms = ctx->sm_count;
+    auto cost = [&](int BM, int BN, int per_sm) {
+        const int64_t t = live_tiles(a.M, a.N, BM, BN, lower);
+        return (double) ceil_div(t, (int64_t) sms * per_sm) * BM * BN * per_sm;
+    };
+    const double c7 = cost(128, 112, 1), c8 = cost(128, 128, 1), c4 = cost(64, 64, 2) * 1.15; // small tiles: lower DMMA/LDS ratio
+    if (c4 < c7 && c4 < c8) {
+        if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 64);
+        return launch_gemm_tile<FORM, 2, 4, EPI>(ctx, a);
+    }
+    if (c7 < c8) {
         if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 112);
-        return launch_gemm_na<FORM, 7, EPI>(ctx, a);
+        return launch_gemm_tile<FORM, 4, 7, EPI>(ctx, a);
     }
     if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 128);
-    return launch_gemm_na<FORM, 8, EPI>(ctx, a);
+    return launch_gemm_tile<FORM, 4, 8, EPI>(ctx, a);
 }
 
 } // namespace bb

@@ -6,8 +6,8 @@
 // reference's std::sort is unstable (tie order is implementation defined); parity cases are
 // tie-free and tests assert that.  NaN sorts last.
 //
-// lambda <= 16384: one CTA, keys + indices live in shared memory (12 B x 16384 = 192 KB).
-// larger: the same bitonic network over global memory, one launch per (k, j) stage.
+// lambda <= 65536: counting rank over the whole chip (see rank_count_kernel).
+// larger: a bitonic network over global memory, one launch per (k, j) stage.
 #pragma once
 
 #include "common.cuh"
@@ -23,39 +23,39 @@ __device__ __forceinline__ bool tuple_greater(unsigned long long ka, unsigned ia
     return ka > kb || (ka == kb && ia > ib);
 }
 
-constexpr int RANK_SMEM_MAX = 16384;
+constexpr int RANK_COUNT_MAX = 65536;
 
-static __global__ void __launch_bounds__(1024) rank_smem_kernel(const double *__restrict__ f, int count, int npad,
-        int *__restrict__ idx_out, double *__restrict__ val_out) {
-    extern __shared__ __align__(16) unsigned char raw[];
-    unsigned long long *keys = (unsigned long long*) raw;
-    unsigned *ids = (unsigned*) (keys + npad);
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-        keys[i] = i < count ? sortable_key(f[i]) : ~0ull;
-        ids[i] = i < count ? (unsigned) i : 0xffffffffu;
-    }
+// Counting rank: rank_i = #{ j : (key_j, j) < (key_i, i) }.  O(lambda^2) compares, but spread over the
+// whole chip (grid = lambda/256 x lambda/256 CTAs, keys of the j-slice staged in shared memory) it is a
+// few microseconds at lambda = 4096 where a single-CTA bitonic network took 70.  Integer atomics only,
+// so the result is deterministic; (key, index) is a total order, so the ranks are a permutation.
+static __global__ void __launch_bounds__(256) rank_count_kernel(const double *__restrict__ f, int count,
+        int *__restrict__ ranks) {
+    __shared__ unsigned long long sk[256];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int j0 = blockIdx.y * 256;
+    const int j = j0 + threadIdx.x;
+    sk[threadIdx.x] = j < count ? sortable_key(f[j]) : ~0ull;
     __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int p = threadIdx.x; p < (npad >> 1); p += blockDim.x) {
-                const int lo = 2 * j * (p / j) + (p % j);
-                const int hi = lo + j;
-                const bool asc = (lo & k) == 0;
-                const unsigned long long ka = keys[lo], kb = keys[hi];
-                const unsigned ia = ids[lo], ib = ids[hi];
-                if (tuple_greater(ka, ia, kb, ib) == asc) {
-                    keys[lo] = kb; keys[hi] = ka;
-                    ids[lo] = ib; ids[hi] = ia;
-                }
-            }
-            __syncthreads();
-        }
+    if (i >= count) return;
+    const unsigned long long ki = sortable_key(f[i]);
+    const int lim = min(256, count - j0);
+    int cnt = 0;
+#pragma unroll 8
+    for (int q = 0; q < lim; q++) {
+        const unsigned long long kj = sk[q];
+        cnt += (kj < ki) || (kj == ki && (j0 + q) < i);
     }
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const unsigned id = ids[i];
-        idx_out[i] = (int) id;
-        val_out[i] = f[id];
-    }
+    if (cnt) atomicAdd(ranks + i, cnt);
+}
+
+static __global__ void __launch_bounds__(256) rank_scatter_kernel(const double *__restrict__ f, int count,
+        const int *__restrict__ ranks, int *__restrict__ idx_out, double *__restrict__ val_out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= count) return;
+    const int r = ranks[i];
+    idx_out[r] = i;
+    val_out[r] = f[i];
 }
 
 static __global__ void rank_global_init(const double *__restrict__ f, int count, int npad, unsigned long long *keys,
@@ -92,15 +92,19 @@ static __global__ void rank_global_finish(const double *__restrict__ f, const un
 // d_f[count] -> d_idx[count] (permutation, ascending fitness), d_val[count] (sorted fitness)
 inline int rank_fitness(bbgpu_ctx *ctx, const double *d_f, int count, int *d_idx, double *d_val) {
     if (count <= 0) return BBGPU_OK;
+    if (count <= RANK_COUNT_MAX) {
+        void *sp = nullptr;
+        BB_TRY(ctx->scratch((size_t) count * sizeof(int), &sp));
+        int *ranks = (int*) sp;
+        BB_CUDA(cudaMemsetAsync(ranks, 0, (size_t) count * sizeof(int), ctx->stream));
+        const int blocks = ceil_div(count, 256);
+        rank_count_kernel<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(d_f, count, ranks);
+        BB_TRY(launched(ctx, "rank_count_kernel"));
+        rank_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(d_f, count, ranks, d_idx, d_val);
+        return launched(ctx, "rank_scatter_kernel");
+    }
     int npad = 2;
     while (npad < count) npad <<= 1;
-    if (npad <= RANK_SMEM_MAX) {
-        const size_t bytes = (size_t) npad * 12;
-        BB_CUDA(cudaFuncSetAttribute(rank_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (RANK_SMEM_MAX * 12)));
-        const int threads = npad / 2 < 1024 ? (npad / 2 < 32 ? 32 : npad / 2) : 1024;
-        rank_smem_kernel<<<1, threads, bytes, ctx->stream>>>(d_f, count, npad, d_idx, d_val);
-        return launched(ctx, "rank_smem_kernel");
-    }
     void *sp = nullptr;
     BB_TRY(ctx->scratch((size_t) npad * 12, &sp));
     unsigned long long *keys = (unsigned long long*) sp;
