@@ -68,10 +68,15 @@ def build_host(force=False):
     deps = srcs + glob.glob(os.path.join(HERE, "host", "*.h*")) + [os.path.join(ROOT, "include", "bbgpu.h")]
     ext = os.path.join(HERE, "_bboptpy" + sysconfig.get_config_var("EXT_SUFFIX"))
     if force or _newer(ext, deps) or _newer(ext, [LIB]):
-        cxx = os.environ.get("CXX", "g++")
+        # the system g++: the image's CXX wrapper (/opt/gcc/bin/g++) resolves -lstdc++ to the static archive,
+        # and a private copy of libstdc++ inside a Python extension crashes in iostream/locale code
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++")
         _run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I" + pybind11.get_include(),
               "-I" + sysconfig.get_paths()["include"], "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "host")]
              + srcs + ["-L" + HERE, "-lbbgpu", "-Wl,-rpath,$ORIGIN", "-o", ext])
+        deps_out = subprocess.run(["ldd", ext], stdout=subprocess.PIPE, text=True).stdout
+        if "libstdc++.so" not in deps_out:
+            raise RuntimeError("the pybind module linked libstdc++ statically; refusing to ship it")
     return ext
 
 

@@ -22,15 +22,13 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace bb {
 
-constexpr int G_BK = 16;      // k chunk per pipeline stage
-constexpr int G_STAGES = 4;
 constexpr int G_THREADS = 256;
-constexpr int G_LDA1 = G_BK + 4;  // FORM1 A tile pitch  [BM][20]
 
 enum { EPI_STORE = 0, EPI_SAMPLE = 1, EPI_ROWSQ = 2, EPI_SYRK = 3 };
 
@@ -52,15 +50,17 @@ struct GemmArgs {
 };
 
 // CTA = 8 warps as 4 (M) x 2 (N); a warp owns MA x NA DMMA atoms -> CTA tile (32 MA) x (16 NA)
-template<int MA, int NA> struct GemmSmem {
+// BK = k chunk per pipeline stage, STAGES = depth of the cp.async ring
+template<int MA, int NA, int BK, int STAGES> struct GemmSmem {
     static constexpr int BM = MA * 32;
     static constexpr int BN = NA * 16;
-    static constexpr int LDA2 = BM + 4; // FORM2 A tile pitch [BK][BM+4]
+    static constexpr int LDA1 = BK + 4; // FORM1 A tile pitch [BM][BK+4]   (pitch = 4 mod 16 doubles:
+    static constexpr int LDA2 = BM + 4; // FORM2 A tile pitch [BK][BM+4]    conflict-free fragment loads)
     static constexpr int LDB = BN + 4;
-    static constexpr int ASZ = (BM * G_LDA1 > G_BK * LDA2) ? BM * G_LDA1 : G_BK * LDA2;
-    static constexpr int BSZ = G_BK * LDB;
-    static constexpr int STAGE = ASZ + BSZ + G_BK; // doubles per stage (A, B, kscale)
-    static constexpr size_t BYTES = (size_t) STAGE * G_STAGES * sizeof(double);
+    static constexpr int ASZ = (BM * LDA1 > BK * LDA2) ? BM * LDA1 : BK * LDA2;
+    static constexpr int BSZ = BK * LDB;
+    static constexpr int STAGE = ASZ + BSZ + BK; // doubles per stage (A, B, kscale)
+    static constexpr size_t BYTES = (size_t) STAGE * STAGES * sizeof(double);
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
@@ -99,11 +99,14 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int64_t
     }
 }
 
-template<int FORM, int MA, int NA, int EPI>
-__global__ void __launch_bounds__(G_THREADS, (MA * NA <= 8) ? 2 : 1) gemm_f64_kernel(const GemmArgs p) {
-    using S = GemmSmem<MA, NA>;
+template<int FORM, int MA, int NA, int BK, int STAGES, int EPI>
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_f64_kernel(const GemmArgs p) {
+    using S = GemmSmem<MA, NA, BK, STAGES>;
     constexpr int BN = S::BN;
     constexpr int G_BM = S::BM;
+    constexpr int G_BK = BK;
+    constexpr int G_STAGES = STAGES;
+    constexpr int G_LDA1 = S::LDA1;
     constexpr int G_LDA2 = S::LDA2;
     constexpr int G_ASZ = S::ASZ;
     extern __shared__ __align__(16) double smem[];
@@ -229,13 +232,13 @@ __global__ void __launch_bounds__(G_THREADS, (MA * NA <= 8) ? 2 : 1) gemm_f64_ke
     }
 }
 
-template<int FORM, int MA, int NA, int EPI>
+template<int FORM, int MA, int NA, int BK, int STAGES, int EPI>
 inline int launch_gemm_tile(bbgpu_ctx *ctx, const GemmArgs &a) {
-    using S = GemmSmem<MA, NA>;
-    BB_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<FORM, MA, NA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    using S = GemmSmem<MA, NA, BK, STAGES>;
+    BB_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<FORM, MA, NA, BK, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) S::BYTES));
     const int tiles = ceil_div(a.M, S::BM) * ceil_div(a.N, S::BN);
-    gemm_f64_kernel<FORM, MA, NA, EPI><<<tiles, G_THREADS, S::BYTES, ctx->stream>>>(a);
+    gemm_f64_kernel<FORM, MA, NA, BK, STAGES, EPI><<<tiles, G_THREADS, S::BYTES, ctx->stream>>>(a);
     return launched(ctx, "gemm_f64_kernel");
 }
 
@@ -262,17 +265,28 @@ inline int launch_gemm(bbgpu_ctx *ctx, const GemmArgs &a, int *tiles_n_out = nul
         const int64_t t = live_tiles(a.M, a.N, BM, BN, lower);
         return (double) ceil_div(t, (int64_t) sms * per_sm) * BM * BN * per_sm;
     };
-    const double c7 = cost(128, 112, 1), c8 = cost(128, 128, 1), c4 = cost(64, 64, 2) * 1.15; // small tiles: lower DMMA/LDS ratio
-    if (c4 < c7 && c4 < c8) {
+    const double c7 = cost(128, 112, 1), c8 = cost(128, 128, 1), c4 = cost(64, 64, 1) * 1.15; // small tiles: lower DMMA/LDS ratio
+    int pick = (c4 < c7 && c4 < c8) ? 2 : (c7 < c8 ? 0 : 1);
+    // experiment hook: BBGPU_GEMM_VARIANT=0..4 forces a tile configuration (tools/measure_fp64_peak.py)
+    static const int forced = [] { const char *e = std::getenv("BBGPU_GEMM_VARIANT"); return e ? std::atoi(e) : -1; }();
+    if (forced >= 0) pick = forced;
+    switch (pick) {
+    case 2:
         if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 64);
-        return launch_gemm_tile<FORM, 2, 4, EPI>(ctx, a);
-    }
-    if (c7 < c8) {
+        return launch_gemm_tile<FORM, 2, 4, 32, 4, EPI>(ctx, a);
+    case 3:
         if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 112);
-        return launch_gemm_tile<FORM, 4, 7, EPI>(ctx, a);
+        return launch_gemm_tile<FORM, 4, 7, 32, 3, EPI>(ctx, a);
+    case 4:
+        if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 128);
+        return launch_gemm_tile<FORM, 4, 8, 32, 3, EPI>(ctx, a);
+    case 1:
+        if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 128);
+        return launch_gemm_tile<FORM, 4, 8, 16, 4, EPI>(ctx, a);
+    default:
+        if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 112);
+        return launch_gemm_tile<FORM, 4, 7, 16, 4, EPI>(ctx, a);
     }
-    if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 128);
-    return launch_gemm_tile<FORM, 4, 8, EPI>(ctx, a);
 }
 
 } // namespace bb

@@ -13,6 +13,10 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include "cma.h"
 #include "de.h"
 #include "restart.h"
@@ -44,8 +48,20 @@ py::array_t<double> as_array(const std::vector<double> &v) {
 
 } // namespace
 
+namespace {
+// BBOPT_BACKTRACE=1: print a native backtrace on SIGSEGV (debug aid; off by default)
+void segv_backtrace(int sig) {
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    backtrace_symbols_fd(frames, n, STDERR_FILENO);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+} // namespace
+
 PYBIND11_MODULE(_bboptpy, m) {
     m.doc() = "B200-native population engine behind bboptpy's optimizer API";
+    if (std::getenv("BBOPT_BACKTRACE")) signal(SIGSEGV, segv_backtrace);
     m.def("seed", [](unsigned s) { bbopt::Random::seed(s); }, "s"_a,
             "Seed the host engine and the device Philox streams (the reference exposes no seed).");
     m.def("uniform", [](double a, double b) { return bbopt::Random::get(a, b); }, "a"_a, "b"_a,

@@ -1,0 +1,91 @@
+// TEST INFRASTRUCTURE: a CPU stand-in for libbbgpu.so's C ABI, just enough to drive the HOST logic
+// (restart schedules, budgets, history rings, printing) under sanitizers without a GPU.  It does no
+// optimisation: fitness improves geometrically with the generation count.  Never shipped.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bbgpu.h"
+
+struct bbgpu_ctx { int launches = 0; };
+struct bbgpu_objective { int n; bbgpu_host_objective_fn host; void *user; };
+struct bbgpu_cma { bbgpu_cma_config cfg; std::vector<double> mean; int gen = 0; double f = 100.0; };
+struct bbgpu_de { bbgpu_de_config cfg; int fev = 0; int gen = 0; };
+
+extern "C" {
+int bbgpu_version(void) { return BBGPU_VERSION; }
+const char *bbgpu_last_error(void) { return "mock"; }
+int bbgpu_ctx_create(int, void *, bbgpu_ctx **out) { *out = new bbgpu_ctx(); return 0; }
+int bbgpu_ctx_destroy(bbgpu_ctx *c) { delete c; return 0; }
+int bbgpu_ctx_sync(bbgpu_ctx *) { return 0; }
+void *bbgpu_ctx_stream(bbgpu_ctx *) { return nullptr; }
+int64_t bbgpu_ctx_launch_count(bbgpu_ctx *c) { return c->launches; }
+int bbgpu_ctx_profile_enable(bbgpu_ctx *, int) { return 0; }
+int bbgpu_ctx_profile_read(bbgpu_ctx *, int, double *t, int64_t *c) { *t = 0; *c = 0; return 0; }
+int bbgpu_ctx_profile_reset(bbgpu_ctx *) { return 0; }
+int bbgpu_ctx_timer_start(bbgpu_ctx *) { return 0; }
+int bbgpu_ctx_timer_stop(bbgpu_ctx *, float *ms) { *ms = 1.f; return 0; }
+int bbgpu_ctx_flush_l2(bbgpu_ctx *) { return 0; }
+int bbgpu_objective_builtin(bbgpu_ctx *, int, int n, bbgpu_objective **out) { *out = new bbgpu_objective{n, nullptr, nullptr}; return 0; }
+int bbgpu_objective_device(bbgpu_ctx *, bbgpu_device_objective_fn, void *, int n, bbgpu_objective **out) { *out = new bbgpu_objective{n, nullptr, nullptr}; return 0; }
+int bbgpu_objective_host(bbgpu_ctx *, bbgpu_host_objective_fn fn, void *user, int n, bbgpu_objective **out) { *out = new bbgpu_objective{n, fn, user}; return 0; }
+int bbgpu_objective_destroy(bbgpu_objective *o) { delete o; return 0; }
+int bbgpu_eval(bbgpu_ctx *, bbgpu_objective *, const double *, int64_t, int, double *) { return 0; }
+int bbgpu_eval_host(bbgpu_ctx *, bbgpu_objective *o, const double *x, int count, double *f) {
+    if (o->host) return o->host(x, o->n, o->n, count, f, o->user);
+    for (int k = 0; k < count; k++) { double s = 0; for (int i = 0; i < o->n; i++) s += x[k * o->n + i] * x[k * o->n + i]; f[k] = s; }
+    return 0;
+}
+int bbgpu_cma_create(bbgpu_ctx *, const bbgpu_cma_config *cfg, const double *, const double *, const double *, bbgpu_cma **out) {
+    bbgpu_cma *h = new bbgpu_cma(); h->cfg = *cfg; h->mean.assign(cfg->n, 0.0); *out = h; return 0;
+}
+int bbgpu_cma_destroy(bbgpu_cma *h) { delete h; return 0; }
+int bbgpu_cma_reset(bbgpu_cma *h, const double *g, int) { h->mean.assign(g, g + h->cfg.n); h->gen = 0; h->f = 100.0; return 0; }
+int bbgpu_cma_set(bbgpu_cma *, int, const double *, int64_t) { return 0; }
+int bbgpu_cma_get(bbgpu_cma *h, int field, double *dst, int64_t count) {
+    for (int64_t i = 0; i < count; i++) dst[i] = (field == BBGPU_CMA_XMEAN && i < (int64_t) h->mean.size()) ? h->mean[i] : 0.0;
+    return 0;
+}
+int bbgpu_cma_get_rank(bbgpu_cma *, int32_t *idx, int count) { for (int i = 0; i < count; i++) idx[i] = i; return 0; }
+int bbgpu_cma_get_rows(bbgpu_cma *h, int, int64_t, int64_t rows, double *dst) {
+    for (int64_t r = 0; r < rows; r++) for (int i = 0; i < h->cfg.n; i++) dst[r * h->cfg.n + i] = h->mean[i] * std::pow(0.9, h->gen);
+    return 0;
+}
+int bbgpu_cma_device_ptr(bbgpu_cma *, int, void **p, int64_t *ld) { *p = nullptr; *ld = 0; return 0; }
+int bbgpu_cma_sample(bbgpu_cma *, double, uint64_t, const double *) { return 0; }
+int bbgpu_cma_sample_dev(bbgpu_cma *, double, const double *) { return 0; }
+int bbgpu_cma_evaluate(bbgpu_cma *, bbgpu_objective *) { return 0; }
+int bbgpu_cma_rank(bbgpu_cma *, int) { return 0; }
+int bbgpu_cma_update(bbgpu_cma *h, double, int) { h->gen++; h->f *= 0.8; return 0; }
+int bbgpu_cma_eig(bbgpu_cma *, const double *, const double *) { return 0; }
+int bbgpu_cma_probe(bbgpu_cma *, double, int) { return 0; }
+int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *r) {
+    std::memset(r, 0, sizeof(*r));
+    for (int q = 0; q < 4; q++) { r->ibw[q] = q; r->ybw[q] = h->f * (1 + q); }
+    r->f_kth = h->f * 1.5; r->pslen = h->cfg.chi; r->hsig = 1; r->d_min = 1; r->d_max = 1; r->tolx_max = std::pow(0.8, h->gen);
+    return 0;
+}
+int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *, double, uint64_t, int, int) { h->gen++; return 0; }
+int bbgpu_dgemm_host(bbgpu_ctx *, int, int, int, const double *, const double *, double *) { return 0; }
+int bbgpu_dsyrk_host(bbgpu_ctx *, int, int, double, const double *, const double *, double *) { return 0; }
+int bbgpu_rank_host(bbgpu_ctx *, int, const double *, int32_t *) { return 0; }
+int bbgpu_philox_normal_host(bbgpu_ctx *, uint64_t, uint64_t, int, int, double *) { return 0; }
+int bbgpu_bench_dgemm(bbgpu_ctx *, int, int, int, int, float *) { return 0; }
+int bbgpu_de_create(bbgpu_ctx *, const bbgpu_de_config *cfg, const double *, const double *, bbgpu_de **out) { bbgpu_de *h = new bbgpu_de(); h->cfg = *cfg; *out = h; return 0; }
+int bbgpu_de_destroy(bbgpu_de *h) { delete h; return 0; }
+int bbgpu_de_init(bbgpu_de *h, bbgpu_objective *, const double *) { h->fev = h->cfg.np; h->gen = 0; return 0; }
+int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *, const bbgpu_de_draws *, bbgpu_de_report *r) {
+    h->fev += h->cfg.np; h->gen++;
+    if (r) { std::memset(r, 0, sizeof(*r)); r->np = h->cfg.np; r->fev = h->fev; r->rounds = 3; r->radius_m2 = std::pow(0.5, h->gen); }
+    return 0;
+}
+int bbgpu_de_get_swarm(bbgpu_de *h, double *x, double *f) {
+    if (x) for (int i = 0; i < h->cfg.np * h->cfg.n; i++) x[i] = 0.01 * i;
+    if (f) for (int i = 0; i < h->cfg.np; i++) f[i] = 10.0 - 0.001 * i;
+    return 0;
+}
+int bbgpu_de_get_archive(bbgpu_de *, double *, int *rows) { *rows = 0; return 0; }
+int bbgpu_de_get_memory(bbgpu_de *, double *, double *) { return 0; }
+int bbgpu_de_get_trace(bbgpu_de *, int32_t *, double *, double *, double *) { return 0; }
+}
