@@ -17,7 +17,7 @@
 #include <algorithm>
 #include <cmath>
 
-#include "gemm_f64.cuh"
+#include "gemm_tma.cuh"
 #include "objectives.cuh"
 #include "philox.cuh"
 #include "rank.cuh"

@@ -254,22 +254,14 @@ inline int64_t live_tiles(int M, int N, int BM, int BN, bool lower_only) {
 // pick the CTA tile (128x112, 128x128 or 64x64) that needs the least tile-waves x tile-area on this
 // device.  The small tile matters for the covariance SYRK: n = 1000 has only 44 lower 128x112 tiles
 // for 148 SMs, but 136 lower 64x64 tiles (one full wave).
+inline int pick_tile(bbgpu_ctx *ctx, const GemmArgs &a, bool lower);
+
 template<int FORM, int EPI>
-inline int launch_gemm(bbgpu_ctx *ctx, const GemmArgs &a, int *tiles_n_out = nullptr) {
+inline int launch_gemm_cpasync(bbgpu_ctx *ctx, const GemmArgs &a, int *tiles_n_out = nullptr) {
     if (a.M <= 0 || a.N <= 0) return BBGPU_OK;
     if ((a.lda & 1) || (a.ldb & 1) || (((uintptr_t) a.A) & 15) || (((uintptr_t) a.B) & 15))
         return fail(BBGPU_ERR_ARG, "gemm operands must be 16-byte aligned with even leading dimensions");
-    const bool lower = EPI == EPI_SYRK;
-    const int sms = ctx->sm_count;
-    auto cost = [&](int BM, int BN, int per_sm) {
-        const int64_t t = live_tiles(a.M, a.N, BM, BN, lower);
-        return (double) ceil_div(t, (int64_t) sms * per_sm) * BM * BN * per_sm;
-    };
-    const double c7 = cost(128, 112, 1), c8 = cost(128, 128, 1), c4 = cost(64, 64, 1) * 1.15; // small tiles: lower DMMA/LDS ratio
-    int pick = (c4 < c7 && c4 < c8) ? 2 : (c7 < c8 ? 0 : 1);
-    // experiment hook: BBGPU_GEMM_VARIANT=0..4 forces a tile configuration (tools/measure_fp64_peak.py)
-    static const int forced = [] { const char *e = std::getenv("BBGPU_GEMM_VARIANT"); return e ? std::atoi(e) : -1; }();
-    if (forced >= 0) pick = forced;
+    const int pick = pick_tile(ctx, a, EPI == EPI_SYRK);
     switch (pick) {
     case 2:
         if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 64);
@@ -287,6 +279,24 @@ inline int launch_gemm(bbgpu_ctx *ctx, const GemmArgs &a, int *tiles_n_out = nul
         if (tiles_n_out) *tiles_n_out = ceil_div(a.N, 112);
         return launch_gemm_tile<FORM, 4, 7, 16, 4, EPI>(ctx, a);
     }
+}
+
+// CTA tile choice: 0/3 = 128x112 (BK 16/32), 1/4 = 128x128 (BK 16/32), 2 = 64x64 (BK 32).  Least
+// tile-waves x tile-area on this device; measured on B200 at 4096x1000x1000 (cp.async ring): 128x112
+// BK=32/3 stages 28.2 TF, BK=16/4 stages 27.2 TF, 128x128 24.7-25.2 TF.  The small tile serves the
+// covariance SYRK: n = 1000 has only 44 lower 128x112 tiles for 148 SMs but 136 lower 64x64 tiles.
+inline int pick_tile(bbgpu_ctx *ctx, const GemmArgs &a, bool lower) {
+    const int sms = ctx->sm_count;
+    auto cost = [&](int BM, int BN) {
+        const int64_t t = live_tiles(a.M, a.N, BM, BN, lower);
+        return (double) ceil_div(t, (int64_t) sms) * BM * BN;
+    };
+    const double c7 = cost(128, 112), c8 = cost(128, 128), c4 = cost(64, 64) * 1.15;
+    int pick = (c4 < c7 && c4 < c8) ? 2 : (c7 < c8 ? 3 : 4);
+    // experiment hook: BBGPU_GEMM_VARIANT=0..4 forces a tile configuration (tools/gemm_variant.py)
+    static const int forced = [] { const char *e = std::getenv("BBGPU_GEMM_VARIANT"); return e ? std::atoi(e) : -1; }();
+    if (forced >= 0) pick = forced;
+    return pick;
 }
 
 } // namespace bb
