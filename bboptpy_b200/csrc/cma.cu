@@ -45,6 +45,14 @@ struct bbgpu_cma {
     double *solver_work = nullptr;
     int solver_lwork = 0;
     int *dev_info = nullptr;
+    // draw prefetch: Z is double buffered; the draws of generation g+1 are generated on the ctx's side
+    // stream while generation g runs its update (counter-based Philox: they depend on nothing)
+    double *Zbuf[2] = { nullptr, nullptr };
+    int zcur = 0;
+    long long zgen[2] = { -1, -1 };      // generation whose draws a buffer holds (or is being filled with)
+    cudaEvent_t ev_z[2] = { nullptr, nullptr };    // buffer filled (recorded on aux)
+    cudaEvent_t ev_used[2] = { nullptr, nullptr }; // buffer consumed by sample() (recorded on the main stream)
+    bool used_rec[2] = { false, false };
     // report
     bbgpu_cma_report *d_report = nullptr;
     bbgpu_cma_report *h_report = nullptr; // pinned
@@ -150,6 +158,28 @@ __global__ void __launch_bounds__(256) gather_steps_kernel(double *__restrict__ 
     for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = __ddiv_rn(__dsub_rn(x[i], mold[i]), sigma);
 }
 
+// Full-covariance kinds, one pass over the selected rows: writes the centred, sigma-scaled steps
+// Ysel[r][:] = (X[src(r)][:] - m_old)/sigma (the SYRK operand; r < mu: r-th best, r >= mu: (r-mu)-th worst,
+// Active only) and the recombination partials  part[s][i] = sum_{k in split s, k < mu} w_k X[idx_k][i].
+__global__ void __launch_bounds__(256) select_steps_kernel(double *__restrict__ part, double *__restrict__ Ysel,
+        const double *__restrict__ X, int64_t ld, int n, int mu, int nsel, int lambda, int splits,
+        const int *__restrict__ rank_idx, const double *__restrict__ w, const double *__restrict__ mold, double sigma) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= n) return;
+    const int per = (nsel + splits - 1) / splits;
+    const int r0 = s * per, r1 = min(nsel, r0 + per);
+    const double mo = mold[i];
+    double am = 0.0;
+    for (int r = r0; r < r1; r++) {
+        const int src = r < mu ? rank_idx[r] : rank_idx[lambda - 1 - (r - mu)];
+        const double x = X[(int64_t) src * ld + i];
+        Ysel[(int64_t) r * ld + i] = __ddiv_rn(__dsub_rn(x, mo), sigma);
+        if (r < mu) am = __dadd_rn(am, __dmul_rn(w[r], x));
+    }
+    part[((int64_t) s * 2 + 0) * n + i] = am;
+}
+
 // partial[s][i] = sum over rows k of split s of w_k X[idx_k][i]  (+ sep: w_k ((x - m_old)/sigma)^2)
 template<bool SEP>
 __global__ void __launch_bounds__(256) recombine_partial_kernel(double *__restrict__ part, const double *__restrict__ X,
@@ -221,8 +251,11 @@ template<bool SEP>
 __global__ void __launch_bounds__(1024) paths_kernel(int n, const double *__restrict__ ps, double *__restrict__ pc,
         const double *__restrict__ dm, double denom, double chi, double cc, double ccc, double *__restrict__ dscal,
         bbgpu_cma_report *rep, double *__restrict__ Cdiag, double *__restrict__ D, const double *__restrict__ tmpn,
-        double ccov, double mueff) {
+        double ccov, double mueff, double *__restrict__ coef, const double *__restrict__ w, int mu, double cmu) {
     __shared__ double red[32];
+    // non-active full covariance: SYRK coefficients cmu * w_k (cmaes.cpp:139)
+    if (coef != nullptr)
+        for (int k = threadIdx.x; k < mu; k += blockDim.x) coef[k] = __dmul_rn(cmu, w[k]);
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s = fma(ps[i], ps[i], s);
     s = block_sum(s, red);
@@ -427,17 +460,54 @@ static int do_sample(bbgpu_cma *h, double sigma) {
     return launch_gemm<1, EPI_SAMPLE>(ctx, g);
 }
 
+static int launch_philox(bbgpu_cma *h, cudaStream_t st, double *Z, uint64_t generation) {
+    const int64_t total = (int64_t) h->lambda * ((h->n + 1) / 2);
+    philox_normal_kernel<<<ceil_div(total, 256), 256, 0, st>>>(Z, h->ldn, h->lambda, h->n, 0, h->cfg.seed, generation, 0u);
+    return launched(h->ctx, "philox_normal_kernel");
+}
+
+// make h->Z hold the draws of `generation` (prefetched on the side stream if possible)
 static int do_philox(bbgpu_cma *h, uint64_t generation) {
     bbgpu_ctx *ctx = h->ctx;
     ProfScope prof(ctx, BBGPU_PROF_PHILOX);
-    const int64_t total = (int64_t) h->lambda * ((h->n + 1) / 2);
-    philox_normal_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(h->Z, h->ldn, h->lambda, h->n, 0, h->cfg.seed,
-            generation, 0u);
-    return launched(ctx, "philox_normal_kernel");
+    for (int b = 0; b < 2; b++) {
+        if (h->zgen[b] == (long long) generation) {
+            BB_CUDA(cudaStreamWaitEvent(ctx->stream, h->ev_z[b], 0));
+            h->zcur = b;
+            h->Z = h->Zbuf[b];
+            return BBGPU_OK;
+        }
+    }
+    const int b = h->zcur ^ 1;
+    if (h->zgen[b] >= 0) BB_CUDA(cudaStreamWaitEvent(ctx->stream, h->ev_z[b], 0)); // an unused prefetch may still be writing it
+    h->zgen[b] = -1;
+    BB_TRY(launch_philox(h, ctx->stream, h->Zbuf[b], generation));
+    h->zcur = b;
+    h->Z = h->Zbuf[b];
+    return BBGPU_OK;
+}
+
+// after sample(generation) has been enqueued: start generating the next generation's draws
+static int prefetch_philox(bbgpu_cma *h, uint64_t generation) {
+    bbgpu_ctx *ctx = h->ctx;
+    if (!ctx->aux) BB_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    const int cur = h->zcur, other = cur ^ 1;
+    BB_CUDA(cudaEventRecord(h->ev_used[cur], ctx->stream));
+    h->used_rec[cur] = true;
+    if (h->used_rec[other]) BB_CUDA(cudaStreamWaitEvent(ctx->aux, h->ev_used[other], 0));
+    BB_TRY(launch_philox(h, ctx->aux, h->Zbuf[other], generation + 1));
+    BB_CUDA(cudaEventRecord(h->ev_z[other], ctx->aux));
+    h->zgen[other] = (long long) generation + 1;
+    return BBGPU_OK;
 }
 
 static int do_rank(bbgpu_cma *h, int ik) {
     ProfScope prof(h->ctx, BBGPU_PROF_RANK);
+    if (h->lambda <= RANK_COUNT_MAX) {
+        // ibw / ybw / f_kth are written by the scatter kernel itself (base_cmaes.cpp:222-229)
+        RankEnds ends { h->d_report->ibw, h->d_report->ybw, &h->d_report->f_kth, ik };
+        return rank_fitness(h->ctx, h->fit, h->lambda, h->rank_idx, h->rank_val, &ends);
+    }
     BB_TRY(rank_fitness(h->ctx, h->fit, h->lambda, h->rank_idx, h->rank_val));
     rank_report_kernel<<<1, 32, 0, h->ctx->stream>>>(h->rank_idx, h->rank_val, h->lambda, ik, h->d_report);
     return launched(h->ctx, "rank_report_kernel");
@@ -464,21 +534,19 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
                 sigma, lo, hi, false, h->ps, h->C, c.cs, csc, h->tmpn);
         BB_TRY(launched(ctx, "recombine_final_kernel<sep>"));
         paths_kernel<true><<<1, 1024, 0, st>>>(n, h->ps, h->pc, h->dm, denom, c.chi, c.cc, ccc, h->dscal, h->d_report, h->C,
-                h->D, h->tmpn, c.ccov, c.mueff);
+                h->D, h->tmpn, c.ccov, c.mueff, nullptr, nullptr, 0, 0.0);
         return launched(ctx, "paths_kernel<sep>");
     }
-    gather_steps_kernel<<<h->nsel, 256, 0, st>>>(h->Ysel, h->X, h->ldn, n, mu, h->lambda, h->rank_idx, h->xold, sigma);
-    BB_TRY(launched(ctx, "gather_steps_kernel"));
-    recombine_partial_kernel<false><<<pgrid, 256, 0, st>>>(h->part, h->X, h->ldn, n, mu, h->splits, h->rank_idx, h->weights,
-            h->xold, sigma);
-    BB_TRY(launched(ctx, "recombine_partial_kernel"));
+    select_steps_kernel<<<pgrid, 256, 0, st>>>(h->part, h->Ysel, h->X, h->ldn, n, mu, h->nsel, h->lambda, h->splits,
+            h->rank_idx, h->weights, h->xold, sigma);
+    BB_TRY(launched(ctx, "select_steps_kernel"));
     recombine_final_kernel<false><<<ceil_div(n, 256), 256, 0, st>>>(h->part, n, h->splits, h->xmean, h->xold, h->dm, c.cm,
             sigma, lo, hi, h->active, h->ps, nullptr, c.cs, csc, nullptr);
     BB_TRY(launched(ctx, "recombine_final_kernel"));
     ps_gemv_kernel<<<ceil_div(n, 8), 256, 0, st>>>(h->isC, h->ldn, n, h->dm, h->ps, c.cs, csc);
     BB_TRY(launched(ctx, "ps_gemv_kernel"));
     paths_kernel<false><<<1, 1024, 0, st>>>(n, h->ps, h->pc, h->dm, denom, c.chi, c.cc, ccc, h->dscal, h->d_report, nullptr,
-            nullptr, nullptr, 0.0, c.mueff);
+            nullptr, nullptr, 0.0, c.mueff, h->active ? nullptr : h->coef, h->weights, mu, c.cmu);
     BB_TRY(launched(ctx, "paths_kernel"));
     delete misc;
     misc = nullptr;
@@ -500,8 +568,6 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
         BB_TRY(launched(ctx, "active_coef_kernel"));
         decay = 1.0 - c.c1 - c.cmu + c.cneg * c.alphaold;
     } else {
-        plain_coef_kernel<<<ceil_div(mu, 256), 256, 0, st>>>(mu, h->weights, c.cmu, h->coef);
-        BB_TRY(launched(ctx, "plain_coef_kernel"));
         decay = 1.0 - c.c1 - c.cmu;
     }
     // C (lower) <- decay C + c1 (pc pc^T + c2 C) + sum_r coef_r y_r y_r^T
@@ -613,7 +679,7 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     h->ldn = round_up(h->n, 8);
     const int n = h->n;
     const size_t ldn = (size_t) h->ldn, lam = (size_t) h->lambda;
-    h->splits = std::max(1, std::min(64, std::min(h->mu / 16, ceil_div(2 * ctx->sm_count, ceil_div(n, 256)))));
+    h->splits = std::max(1, std::min(64, std::min(h->nsel / 16, ceil_div(2 * ctx->sm_count, ceil_div(n, 256)))));
     int rc = BBGPU_OK;
     auto A = [&](double **p, size_t count) {
         if (rc != BBGPU_OK) return;
@@ -625,7 +691,7 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     A(&h->xmean, ldn); A(&h->xold, ldn); A(&h->pc, ldn); A(&h->ps, ldn); A(&h->D, ldn); A(&h->dm, ldn);
     A(&h->tmpn, ldn); A(&h->W, ldn); A(&h->weights, h->mu); A(&h->lower, ldn); A(&h->upper, ldn);
     A(&h->coef, (size_t) h->nsel); A(&h->ycoeff, (size_t) h->mu); A(&h->dscal, 8);
-    A(&h->X, lam * ldn); A(&h->Z, lam * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
+    A(&h->X, lam * ldn); A(&h->Zbuf[0], lam * ldn); A(&h->Zbuf[1], lam * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
     A(&h->part, (size_t) h->splits * 2 * n);
     if (h->full) {
         A(&h->C, (size_t) n * ldn); A(&h->Bt, (size_t) n * ldn); A(&h->BDt, (size_t) n * ldn);
@@ -637,6 +703,12 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
         }
     } else {
         A(&h->C, ldn);
+    }
+    h->Z = h->Zbuf[0];
+    for (int b = 0; b < 2 && rc == BBGPU_OK; b++) {
+        if (cudaEventCreateWithFlags(&h->ev_z[b], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev_used[b], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(BBGPU_ERR_CUDA, "cudaEventCreate failed");
     }
     if (rc == BBGPU_OK) rc = dev_alloc(&h->rank_idx, lam);
     if (rc == BBGPU_OK) rc = dev_alloc(&h->dev_info, 1);
@@ -660,8 +732,13 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
 int bbgpu_cma_destroy(bbgpu_cma *h) {
     if (!h) return BBGPU_OK;
     cudaStreamSynchronize(h->ctx->stream);
+    if (h->ctx->aux) cudaStreamSynchronize(h->ctx->aux);
+    for (int b = 0; b < 2; b++) {
+        if (h->ev_z[b]) cudaEventDestroy(h->ev_z[b]);
+        if (h->ev_used[b]) cudaEventDestroy(h->ev_used[b]);
+    }
     double *bufs[] = { h->xmean, h->xold, h->pc, h->ps, h->D, h->dm, h->tmpn, h->W, h->weights, h->lower, h->upper, h->coef,
-            h->ycoeff, h->dscal, h->X, h->Z, h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
+            h->ycoeff, h->dscal, h->X, h->Zbuf[0], h->Zbuf[1], h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
             h->rowsq_part, h->solver_work, h->ssq };
     for (double *b : bufs) if (b) cudaFree(b);
     if (h->rank_idx) cudaFree(h->rank_idx);
@@ -783,16 +860,19 @@ int bbgpu_cma_sample(bbgpu_cma *h, double sigma, uint64_t generation, const doub
     if (h_z != nullptr) {
         BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, h_z, (size_t) h->n * 8, (size_t) h->n * 8, h->lambda,
                 cudaMemcpyHostToDevice, h->ctx->stream));
-    } else {
-        BB_TRY(do_philox(h, generation));
+        h->zgen[h->zcur] = -1;
+        return do_sample(h, sigma);
     }
-    return do_sample(h, sigma);
+    BB_TRY(do_philox(h, generation));
+    BB_TRY(do_sample(h, sigma));
+    return prefetch_philox(h, generation);
 }
 
 int bbgpu_cma_sample_dev(bbgpu_cma *h, double sigma, const double *d_z) {
     BB_ARG(h && d_z);
     BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, d_z, (size_t) h->n * 8, (size_t) h->n * 8, h->lambda,
             cudaMemcpyDeviceToDevice, h->ctx->stream));
+    h->zgen[h->zcur] = -1;
     return do_sample(h, sigma);
 }
 
@@ -838,6 +918,7 @@ int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint6
     BB_ARG(h && obj && obj->n == h->n);
     BB_TRY(do_philox(h, generation));
     BB_TRY(do_sample(h, sigma));
+    BB_TRY(prefetch_philox(h, generation));
     {
         ProfScope prof(h->ctx, BBGPU_PROF_EVAL);
         BB_TRY(evaluate(h->ctx, obj, h->X, h->ldn, h->lambda, h->fit));

@@ -78,6 +78,8 @@ struct bbgpu_ctx {
     int64_t prof_n[16] = { 0 };
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     void *d_flush = nullptr;
+    void *d_ranks = nullptr;        // persistent zeroed counting-rank buffer (rank.cuh)
+    cudaStream_t aux = nullptr;     // side stream: next generation's draws overlap the covariance update
 
     int pinned(size_t bytes, void **out);
     int scratch(size_t bytes, void **out);

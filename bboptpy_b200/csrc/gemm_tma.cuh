@@ -45,6 +45,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 // bounded wait: a broken pipeline traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, int parity) {
     const unsigned addr = (unsigned) __cvta_generic_to_shared(bar);
+#pragma unroll 1
     for (unsigned spin = 0; spin < (1u << 28); spin++) {
         unsigned done;
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"

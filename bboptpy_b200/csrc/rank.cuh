@@ -49,13 +49,32 @@ static __global__ void __launch_bounds__(256) rank_count_kernel(const double *__
     if (cnt) atomicAdd(ranks + i, cnt);
 }
 
+// optional per-call report of the ends of the ranking (fused into the scatter kernel)
+struct RankEnds {
+    int *ibw;      // [4] indices of best, 2nd best, 2nd worst, worst   (nullptr -> no report)
+    double *ybw;   // [4] their fitness
+    double *f_kth; // fitness at sorted position ik
+    int ik;
+};
+
+// scatter by rank; re-zeroes the rank buffer for the next call (so no memset launch is needed)
 static __global__ void __launch_bounds__(256) rank_scatter_kernel(const double *__restrict__ f, int count,
-        const int *__restrict__ ranks, int *__restrict__ idx_out, double *__restrict__ val_out) {
+        int *__restrict__ ranks, int *__restrict__ idx_out, double *__restrict__ val_out, RankEnds ends) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= count) return;
     const int r = ranks[i];
+    ranks[i] = 0;
+    const double v = f[i];
     idx_out[r] = i;
-    val_out[r] = f[i];
+    val_out[r] = v;
+    if (ends.ibw != nullptr) {
+        const int last = count - 1, second_last = count > 1 ? count - 2 : 0, second = count > 1 ? 1 : 0;
+        if (r == 0) { ends.ibw[0] = i; ends.ybw[0] = v; }
+        if (r == second) { ends.ibw[1] = i; ends.ybw[1] = v; }
+        if (r == second_last) { ends.ibw[2] = i; ends.ybw[2] = v; }
+        if (r == last) { ends.ibw[3] = i; ends.ybw[3] = v; }
+        if (r == (ends.ik < count ? ends.ik : last)) *ends.f_kth = v;
+    }
 }
 
 static __global__ void rank_global_init(const double *__restrict__ f, int count, int npad, unsigned long long *keys,
@@ -90,17 +109,20 @@ static __global__ void rank_global_finish(const double *__restrict__ f, const un
 }
 
 // d_f[count] -> d_idx[count] (permutation, ascending fitness), d_val[count] (sorted fitness)
-inline int rank_fitness(bbgpu_ctx *ctx, const double *d_f, int count, int *d_idx, double *d_val) {
+inline int rank_fitness(bbgpu_ctx *ctx, const double *d_f, int count, int *d_idx, double *d_val,
+        const RankEnds *ends = nullptr) {
     if (count <= 0) return BBGPU_OK;
     if (count <= RANK_COUNT_MAX) {
-        void *sp = nullptr;
-        BB_TRY(ctx->scratch((size_t) count * sizeof(int), &sp));
-        int *ranks = (int*) sp;
-        BB_CUDA(cudaMemsetAsync(ranks, 0, (size_t) count * sizeof(int), ctx->stream));
+        if (ctx->d_ranks == nullptr) { // persistent, zero on entry to every call (the scatter kernel re-zeroes it)
+            BB_CUDA(cudaMalloc(&ctx->d_ranks, (size_t) RANK_COUNT_MAX * sizeof(int)));
+            BB_CUDA(cudaMemsetAsync(ctx->d_ranks, 0, (size_t) RANK_COUNT_MAX * sizeof(int), ctx->stream));
+        }
+        int *ranks = (int*) ctx->d_ranks;
         const int blocks = ceil_div(count, 256);
         rank_count_kernel<<<dim3(blocks, blocks), 256, 0, ctx->stream>>>(d_f, count, ranks);
         BB_TRY(launched(ctx, "rank_count_kernel"));
-        rank_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(d_f, count, ranks, d_idx, d_val);
+        RankEnds e = ends ? *ends : RankEnds { nullptr, nullptr, nullptr, 0 };
+        rank_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(d_f, count, ranks, d_idx, d_val, e);
         return launched(ctx, "rank_scatter_kernel");
     }
     int npad = 2;
