@@ -573,7 +573,7 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
     // C (lower) <- decay C + c1 (pc pc^T + c2 C) + sum_r coef_r y_r y_r^T
     GemmArgs g {};
     g.A = h->Ysel; g.lda = h->ldn; g.B = h->Ysel; g.ldb = h->ldn;
-    g.M = n; g.N = n; g.K = h->nsel; g.kscale = h->coef;
+    g.M = n; g.N = n; g.K = h->nsel; g.kscale = h->coef; g.kscale_padded = true;
     g.C = h->C; g.ldc = h->ldn; g.vec = h->pc; g.s0 = decay; g.s1 = c.c1; g.dscal = h->dscal;
     ProfScope prof(ctx, BBGPU_PROF_COV_SYRK);
     return launch_gemm<2, EPI_SYRK>(ctx, g);
@@ -679,7 +679,7 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     h->ldn = round_up(h->n, 8);
     const int n = h->n;
     const size_t ldn = (size_t) h->ldn, lam = (size_t) h->lambda;
-    h->splits = std::max(1, std::min(64, std::min(h->nsel / 16, ceil_div(2 * ctx->sm_count, ceil_div(n, 256)))));
+    h->splits = std::max(1, std::min(128, std::min(h->nsel / 16, ceil_div(4 * ctx->sm_count, ceil_div(n, 256)))));
     int rc = BBGPU_OK;
     auto A = [&](double **p, size_t count) {
         if (rc != BBGPU_OK) return;
@@ -690,7 +690,7 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     };
     A(&h->xmean, ldn); A(&h->xold, ldn); A(&h->pc, ldn); A(&h->ps, ldn); A(&h->D, ldn); A(&h->dm, ldn);
     A(&h->tmpn, ldn); A(&h->W, ldn); A(&h->weights, h->mu); A(&h->lower, ldn); A(&h->upper, ldn);
-    A(&h->coef, (size_t) h->nsel); A(&h->ycoeff, (size_t) h->mu); A(&h->dscal, 8);
+    A(&h->coef, (size_t) round_up(h->nsel, 32) + 32); A(&h->ycoeff, (size_t) h->mu); A(&h->dscal, 8);
     A(&h->X, lam * ldn); A(&h->Zbuf[0], lam * ldn); A(&h->Zbuf[1], lam * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
     A(&h->part, (size_t) h->splits * 2 * n);
     if (h->full) {
@@ -961,13 +961,14 @@ int bbgpu_dsyrk_host(bbgpu_ctx *ctx, int n, int K, double alpha, const double *h
     int64_t ldy, ldc;
     int rc = upload_padded(ctx, h_Y, K, n, &dY, &ldy);
     if (rc == BBGPU_OK) rc = upload_padded(ctx, h_C, n, n, &dC, &ldc);
-    if (rc == BBGPU_OK) rc = dev_alloc(&dcoef, (size_t) K);
+    if (rc == BBGPU_OK) rc = dev_alloc(&dcoef, (size_t) round_up(K, 32) + 32);
     if (rc == BBGPU_OK) rc = dev_alloc(&dzero, (size_t) round_up(n, 8) + 8);
     if (rc == BBGPU_OK) {
+        cudaMemsetAsync(dcoef, 0, ((size_t) round_up(K, 32) + 32) * 8, ctx->stream);
         cudaMemcpyAsync(dcoef, h_coef, (size_t) K * 8, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemsetAsync(dzero, 0, ((size_t) round_up(n, 8) + 8) * 8, ctx->stream);
         GemmArgs g {};
-        g.A = dY; g.lda = ldy; g.B = dY; g.ldb = ldy; g.M = n; g.N = n; g.K = K; g.kscale = dcoef;
+        g.A = dY; g.lda = ldy; g.B = dY; g.ldb = ldy; g.M = n; g.N = n; g.K = K; g.kscale = dcoef; g.kscale_padded = true;
         g.C = dC; g.ldc = ldc; g.vec = dzero; g.s0 = alpha; g.s1 = 0.0; g.dscal = dzero;
         rc = launch_gemm<2, EPI_SYRK>(ctx, g);
     }

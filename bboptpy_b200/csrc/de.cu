@@ -23,6 +23,9 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
+
+#include <cooperative_groups.h>
 
 #include "objectives.cuh"
 #include "philox.cuh"
@@ -61,9 +64,7 @@ __device__ __forceinline__ int de_int(const DeDev &d, int cand, int slot, int ta
 }
 
 // per-candidate control parameters for the generation (de/jade.cpp:107-126, de/shade.cpp:104-126)
-__global__ void __launch_bounds__(256) de_params_kernel(DeDev d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.np) return;
+__device__ __forceinline__ void de_params_one(const DeDev &d, int i) {
     int ri = 0;
     if (d.kind == BBGPU_DE_SHADE) ri = d.replay ? d.ri[i] : de_int(d, i, 0, TAG_RI, d.h);
     const double mcr = d.kind == BBGPU_DE_JADE ? d.mu[0] : d.MCR[ri];
@@ -106,12 +107,19 @@ __global__ void __launch_bounds__(256) de_params_kernel(DeDev d) {
     d.trbuf[0][i] = 0;
 }
 
-// CTA-wide: push flags -> exclusive prefix counts `pre` and archive targets `tgt` (both in smem)
+__global__ void __launch_bounds__(256) de_params_kernel(DeDev d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.np) de_params_one(d, i);
+}
+
+// CTA-wide (256 threads): push flags -> exclusive prefix counts `pre` and archive targets `tgt` (both in
+// smem, np ints each); wsum[0..8] scratch, wsum[8] = total pushes
 __device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__restrict__ succ, int larch0, int *pre, int *tgt,
-        int *chunk_tot) {
+        int *wsum) {
     const int np = d.np, T = blockDim.x;
     const int per = (np + T - 1) / T;
     const int b = threadIdx.x * per, e = min(np, b + per);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int local = 0;
     for (int i = b; i < e; i++) {
         const int s = succ[i];
@@ -119,19 +127,27 @@ __device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__res
         tgt[i] = push;
         local += push;
     }
-    chunk_tot[threadIdx.x] = local;
+    int incl = local;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    __syncthreads(); // previous users of wsum are done
+    if (lane == 31) wsum[wid] = incl;
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
-        for (int t = 0; t < T; t++) {
-            const int v = chunk_tot[t];
-            chunk_tot[t] = run;
+        const int nw = T >> 5;
+        for (int w = 0; w < nw; w++) {
+            const int v = wsum[w];
+            wsum[w] = run;
             run += v;
         }
-        chunk_tot[T] = run;
+        wsum[8] = run;
     }
     __syncthreads();
-    int run = chunk_tot[threadIdx.x];
+    int run = wsum[wid] + incl - local;
     for (int i = b; i < e; i++) {
         const int push = tgt[i];
         pre[i] = run;
@@ -142,15 +158,9 @@ __device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__res
     __syncthreads();
 }
 
-// one resolution round; 8 candidates (warps) per CTA
-__global__ void __launch_bounds__(256) de_round_kernel(DeDev d, int round) {
-    extern __shared__ int sm[];
-    int *pre = sm, *tgt = sm + d.np, *chunk_tot = sm + 2 * d.np;
+// one candidate (one warp) in one resolution round
+__device__ __forceinline__ void de_candidate(const DeDev &d, int i, int round, int larch0, const int *pre, const int *tgt) {
     const int cur = round & 1, nxt = cur ^ 1;
-    const int larch0 = *d.larch;
-    de_scan_targets(d, d.succ[cur], larch0, pre, tgt, chunk_tot);
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= d.np) return;
     const int lane = threadIdx.x & 31;
     const int np = d.np, n = d.n;
     const int *succ = d.succ[cur], *ver = d.ver[cur], *trb = d.trbuf[cur];
@@ -244,15 +254,18 @@ __global__ void __launch_bounds__(256) de_round_kernel(DeDev d, int round) {
     }
 }
 
-// after the fixed point: archive rows (last writer per slot), new archive size
-__global__ void __launch_bounds__(256) de_archive_kernel(DeDev d, int fin, int *larch_new) {
+// one resolution round; 8 candidates (warps) per CTA
+__global__ void __launch_bounds__(256) de_round_kernel(DeDev d, int round) {
     extern __shared__ int sm[];
-    int *pre = sm, *tgt = sm + d.np, *chunk_tot = sm + 2 * d.np;
+    int *pre = sm, *tgt = sm + d.np, *wsum = sm + 2 * d.np;
     const int larch0 = *d.larch;
-    de_scan_targets(d, d.succ[fin], larch0, pre, tgt, chunk_tot);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *larch_new = d.archive ? min(d.npA, larch0 + chunk_tot[blockDim.x]) : 0;
-    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (j >= d.np) return;
+    de_scan_targets(d, d.succ[round & 1], larch0, pre, tgt, wsum);
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i < d.np) de_candidate(d, i, round, larch0, pre, tgt);
+}
+
+// after the fixed point: archive rows (last writer per slot wins; the value is the OLD parent row)
+__device__ __forceinline__ void de_archive_one(const DeDev &d, int j, const int *tgt) {
     const int lane = threadIdx.x & 31;
     const int a = tgt[j];
     if (a < 0) return;
@@ -265,9 +278,19 @@ __global__ void __launch_bounds__(256) de_archive_kernel(DeDev d, int fin, int *
     for (int c = lane; c < d.n; c += 32) dst[c] = src[c];
 }
 
+__global__ void __launch_bounds__(256) de_archive_kernel(DeDev d, int fin, int *larch_new) {
+    extern __shared__ int sm[];
+    int *pre = sm, *tgt = sm + d.np, *wsum = sm + 2 * d.np;
+    const int larch0 = *d.larch;
+    de_scan_targets(d, d.succ[fin], larch0, pre, tgt, wsum);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *larch_new = d.archive ? min(d.npA, larch0 + wsum[8]) : 0;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j < d.np) de_archive_one(d, j, tgt);
+}
+
 // parameter adaptation (de/jade.cpp:185-205, de/shade.cpp:186-212); reads the OLD parent fitness
-__global__ void __launch_bounds__(1024) de_adapt_kernel(DeDev d, int fin, double cdamp, double sigma_cr, int *nsucc_out) {
-    __shared__ double red[32];
+__device__ __forceinline__ void de_adapt_block(const DeDev &d, int fin, double cdamp, double sigma_cr, int *nsucc_out,
+        double *red) {
     const int *succ = d.succ[fin];
     const bool jade = d.kind == BBGPU_DE_JADE;
     double cnt = 0, s_cr = 0, s_cr2 = 0, s_f = 0, s_f2 = 0, s_w = 0, s_wcr = 0, s_wf = 0, s_wf2 = 0, acc = 0;
@@ -318,16 +341,24 @@ __global__ void __launch_bounds__(1024) de_adapt_kernel(DeDev d, int fin, double
     }
 }
 
+__global__ void __launch_bounds__(1024) de_adapt_kernel(DeDev d, int fin, double cdamp, double sigma_cr, int *nsucc_out) {
+    __shared__ double red[32];
+    de_adapt_block(d, fin, cdamp, sigma_cr, nsucc_out, red);
+}
+
 // greedy replacement (de/jade.cpp:174-176)
-__global__ void __launch_bounds__(256) de_replace_kernel(DeDev d, int fin) {
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= d.np) return;
+__device__ __forceinline__ void de_replace_one(const DeDev &d, int i, int fin) {
     if (d.succ[fin][i] == 0) return;
     const int lane = threadIdx.x & 31;
     const double *src = d.TR[d.trbuf[fin][i]] + (int64_t) i * d.ld;
     double *dst = d.SW + (int64_t) i * d.ld;
     for (int c = lane; c < d.n; c += 32) dst[c] = src[c];
     if (lane == 0) d.F[i] = d.FT[i];
+}
+
+__global__ void __launch_bounds__(256) de_replace_kernel(DeDev d, int fin) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i < d.np) de_replace_one(d, i, fin);
 }
 
 __global__ void __launch_bounds__(256) de_gather_rows_kernel(const double *__restrict__ src, double *__restrict__ dst,
@@ -340,8 +371,7 @@ __global__ void __launch_bounds__(256) de_gather_rows_kernel(const double *__res
 }
 
 // archive trimming by random erase (de/shade.cpp:228-235) on the row-index indirection
-__global__ void de_trim_kernel(DeDev d, int *larch, int npnew, const int *trim, int ntrim) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void de_trim_thread(const DeDev &d, int *larch, int npnew, const int *trim, int ntrim) {
     int la = *larch, t = 0;
     while (la > npnew) {
         int r;
@@ -356,6 +386,10 @@ __global__ void de_trim_kernel(DeDev d, int *larch, int npnew, const int *trim, 
     *larch = la;
 }
 
+__global__ void de_trim_kernel(DeDev d, int *larch, int npnew, const int *trim, int ntrim) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) de_trim_thread(d, larch, npnew, trim, ntrim);
+}
+
 // ||x_i||_2 per member, then Welford-equivalent M2 of the radii and the best fitness
 __global__ void __launch_bounds__(256) de_norms_kernel(const double *__restrict__ SW, int np, int n, int64_t ld,
         double *__restrict__ radius) {
@@ -368,9 +402,8 @@ __global__ void __launch_bounds__(256) de_norms_kernel(const double *__restrict_
     if ((threadIdx.x & 31) == 0) radius[i] = sqrt(s);
 }
 
-__global__ void __launch_bounds__(1024) de_report_kernel(DeDev d, const double *__restrict__ radius, int np, const int *larch,
-        const int *nsucc, bbgpu_de_report *rep) {
-    __shared__ double red[32];
+__device__ __forceinline__ void de_report_block(const DeDev &d, const double *__restrict__ radius, int np, const int *larch,
+        const int *nsucc, bbgpu_de_report *rep, double *red) {
     double s = 0.0, fb = INFINITY;
     for (int i = threadIdx.x; i < np; i += blockDim.x) {
         s += radius[i];
@@ -394,6 +427,117 @@ __global__ void __launch_bounds__(1024) de_report_kernel(DeDev d, const double *
         rep->muf = d.mu[1];
         rep->fbest = fb;
         rep->radius_m2 = m2;
+    }
+}
+
+__global__ void __launch_bounds__(1024) de_report_kernel(DeDev d, const double *__restrict__ radius, int np, const int *larch,
+        const int *nsucc, bbgpu_de_report *rep) {
+    __shared__ double red[32];
+    de_report_block(d, radius, np, larch, nsucc, rep, red);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// The whole generation as ONE cooperative kernel: sort -> parameters -> resolution rounds (grid.sync
+// between rounds, loop until a round rebuilds nothing) -> archive -> adaptation -> replacement ->
+// (L-SHADE: sort, population reduction, archive trimming) -> radii -> report.  No host round trip
+// inside a generation, and none between generations unless the caller asks for the report.
+// ------------------------------------------------------------------------------------------
+struct DeCoop {
+    double *SWalt, *Falt, *radius;
+    int *nsucc, *rounds_out;
+    bbgpu_de_report *rep;
+    double cdamp, sigma_cr;
+    const int *trim;
+    int ntrim, npnew;
+};
+
+// counting rank + row scatter: (SW, F) -> (SWalt, Falt) sorted ascending by (fitness, index)
+__device__ __forceinline__ void de_sort_rows(const double *__restrict__ SW, const double *__restrict__ F,
+        double *__restrict__ SWalt, double *__restrict__ Falt, int np, int n, int64_t ld, int gw, int W) {
+    const int lane = threadIdx.x & 31;
+    for (int i = gw; i < np; i += W) {
+        const double fi = F[i];
+        const unsigned long long ki = sortable_key(fi);
+        int cnt = 0;
+        for (int j = lane; j < np; j += 32) {
+            const unsigned long long kj = sortable_key(F[j]);
+            cnt += (kj < ki) || (kj == ki && j < i);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        const double *src = SW + (int64_t) i * ld;
+        double *dst = SWalt + (int64_t) cnt * ld;
+        for (int c = lane; c < n; c += 32) dst[c] = src[c];
+        if (lane == 0) Falt[cnt] = fi;
+    }
+}
+
+__global__ void __launch_bounds__(256) de_generation_kernel(DeDev d, DeCoop c) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ int sm[];
+    int *pre = sm, *tgt = sm + d.np, *wsum = sm + 2 * d.np;
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31;
+    const int W = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int GT = gridDim.x * 256, gtid = blockIdx.x * 256 + threadIdx.x;
+    const int np = d.np, n = d.n;
+
+    if (d.kind == BBGPU_DE_JADE) { // de/jade.cpp:101
+        de_sort_rows(d.SW, d.F, c.SWalt, c.Falt, np, n, d.ld, gw, W);
+        grid.sync();
+        double *t = d.SW; d.SW = c.SWalt; c.SWalt = t;
+        t = d.F; d.F = c.Falt; c.Falt = t;
+    }
+    for (int i = gtid; i < np; i += GT) de_params_one(d, i);
+    grid.sync();
+
+    const int larch0 = *d.larch;
+    int round = 0;
+    while (true) {
+        de_scan_targets(d, d.succ[round & 1], larch0, pre, tgt, wsum);
+        for (int i = gw; i < np; i += W) de_candidate(d, i, round, larch0, pre, tgt);
+        grid.sync();
+        const int rebuilt = *((volatile int*) (d.nrecomp + round));
+        round++;
+        if (rebuilt == 0 || round >= DE_MAX_ROUNDS) break;
+    }
+    const int fin = round & 1;
+
+    de_scan_targets(d, d.succ[fin], larch0, pre, tgt, wsum);
+    for (int j = gw; j < np; j += W) de_archive_one(d, j, tgt);
+    if (blockIdx.x == 0) de_adapt_block(d, fin, c.cdamp, c.sigma_cr, c.nsucc, red);
+    grid.sync(); // archive rows and adaptation read the OLD parents; replacement comes after
+
+    for (int i = gw; i < np; i += W) de_replace_one(d, i, fin);
+    if (gtid == 0) {
+        *d.larch = d.archive ? min(d.npA, larch0 + wsum[8]) : 0;
+        for (int r = 0; r < round; r++) d.nrecomp[r] = 0;
+        *c.rounds_out = round;
+    }
+    grid.sync();
+
+    int np_after = np;
+    if (d.kind == BBGPU_DE_SHADE) { // de/shade.cpp:215-235
+        de_sort_rows(d.SW, d.F, c.SWalt, c.Falt, np, n, d.ld, gw, W);
+        grid.sync();
+        double *t = d.SW; d.SW = c.SWalt; c.SWalt = t;
+        t = d.F; d.F = c.Falt; c.Falt = t;
+        np_after = min(np, c.npnew);
+        if (gtid == 0 && d.archive) de_trim_thread(d, d.larch, c.npnew, c.trim, c.ntrim);
+    }
+    for (int i = gw; i < np_after; i += W) {
+        const double *x = d.SW + (int64_t) i * d.ld;
+        double s = 0.0;
+        for (int q = lane; q < n; q += 32) s = fma(x[q], x[q], s);
+        s = warp_sum(s);
+        if (lane == 0) c.radius[i] = sqrt(s);
+    }
+    grid.sync();
+    if (blockIdx.x == 0) {
+        de_report_block(d, c.radius, np_after, d.larch, c.nsucc, c.rep, red);
+        if (threadIdx.x == 0) c.rep->rounds = round;
     }
 }
 
@@ -424,7 +568,9 @@ struct bbgpu_de {
     int last_rounds = 6;
     DeDev d;
     double *SWalt = nullptr, *Falt = nullptr, *radius = nullptr, *Ubuf = nullptr, *zbuf = nullptr, *cbuf = nullptr;
-    int *perm = nullptr, *ribuf = nullptr, *trimbuf = nullptr, *larch_new = nullptr, *nsucc = nullptr;
+    int *perm = nullptr, *ribuf = nullptr, *trimbuf = nullptr, *larch_new = nullptr, *nsucc = nullptr, *rounds_dev = nullptr;
+    int coop_blocks = 0;
+    bool use_coop = true;
     int trim_cap = 0;
     int *h_nrecomp = nullptr; // pinned
     bbgpu_de_report *d_rep = nullptr, *h_rep = nullptr;
@@ -481,7 +627,7 @@ int bbgpu_de_create(bbgpu_ctx *ctx, const bbgpu_de_config *cfg, const double *h_
     DA(d.TR[0], rows * ld); DA(d.TR[1], rows * ld); DA(d.FT, rows); DA(d.CR, rows); DA(d.Fm, rows); DA(d.CR1, rows);
     DA(d.MCR, hh); DA(d.MF, hh); DA(d.mu, 2); DA(h->radius, rows);
     DA(d.ibest, rows); DA(d.r1, rows); DA(d.r2, rows); DA(d.jrand, rows); DA(d.slot, rows); DA(d.ri, rows); DA(d.arch_row, rows);
-    DA(d.larch, 1); DA(h->larch_new, 1); DA(h->nsucc, 1); DA(d.kslot, 1);
+    DA(d.larch, 1); DA(h->larch_new, 1); DA(h->nsucc, 1); DA(d.kslot, 1); DA(h->rounds_dev, 1);
     DA(d.succ[0], rows); DA(d.succ[1], rows); DA(d.ver[0], rows); DA(d.ver[1], rows); DA(d.trbuf[0], rows); DA(d.trbuf[1], rows);
     DA(d.sig, rows * 4); DA(d.nrecomp, DE_MAX_ROUNDS); DA(h->perm, rows);
     DA(h->zbuf, rows); DA(h->cbuf, rows); DA(h->ribuf, rows);
@@ -502,6 +648,18 @@ int bbgpu_de_create(bbgpu_ctx *ctx, const bbgpu_de_config *cfg, const double *h_
     cudaMemcpyAsync(d.kslot, &one, 4, cudaMemcpyHostToDevice, st);
     de_iota_kernel<<<ceil_div(h->npcap, 256), 256, 0, st>>>(d.arch_row, h->npcap);
     rc = launched(ctx, "de_iota_kernel");
+    {
+        // cooperative launch geometry: all CTAs must be co-resident
+        const char *e = std::getenv("BBGPU_DE_COOP");
+        h->use_coop = e ? std::atoi(e) != 0 : true;
+        const size_t smem = ((size_t) 2 * h->npcap + 16) * sizeof(int);
+        int supported = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(de_generation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, de_generation_kernel, 256, smem);
+        h->coop_blocks = std::min(ceil_div(h->npcap, 8), per_sm * ctx->sm_count);
+        if (!supported || h->coop_blocks < 1) h->use_coop = false;
+    }
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == BBGPU_OK) rc = fail(BBGPU_ERR_CUDA, "de create sync failed");
     if (rc != BBGPU_OK) { bbgpu_de_destroy(h); return rc; }
     *out = h;
@@ -560,7 +718,7 @@ int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws 
     const int np = h->np, n = h->n;
     d.np = np; d.npA = np; d.gen = h->gen; d.obj_id = obj->id; d.aux = obj->d_aux;
     d.replay = draws != nullptr;
-    if (h->cfg.kind == BBGPU_DE_JADE) BB_TRY(de_sort(h)); // de/jade.cpp:101
+    if (h->cfg.kind == BBGPU_DE_JADE && !h->use_coop) BB_TRY(de_sort(h)); // de/jade.cpp:101 (the cooperative kernel sorts itself)
     if (draws) {
         BB_ARG(draws->zcr && draws->cauchy && draws->ibest && draws->r1 && draws->r2 && draws->jrand && draws->slot && draws->u);
         BB_ARG(h->cfg.kind == BBGPU_DE_JADE || draws->ri);
@@ -584,6 +742,37 @@ int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws 
             BB_CUDA(cudaMemcpyAsync(h->trimbuf, draws->trim, (size_t) draws->ntrim * 4, cudaMemcpyHostToDevice, st));
         }
         d.zcr = h->zbuf; d.cauchy = h->cbuf; d.U = h->Ubuf;
+    }
+    if (h->use_coop) {
+        // ---- single cooperative launch per generation
+        DeCoop c;
+        c.SWalt = h->SWalt; c.Falt = h->Falt; c.radius = h->radius; c.nsucc = h->nsucc; c.rounds_out = h->rounds_dev;
+        c.rep = h->d_rep; c.cdamp = h->cfg.cdamp; c.sigma_cr = h->cfg.sigma;
+        c.trim = h->trimbuf; c.ntrim = draws ? draws->ntrim : 0;
+        const int fev_after = h->fev + np;
+        c.npnew = h->cfg.kind == BBGPU_DE_SHADE
+                ? (int) std::round((h->cfg.npmin - h->npcap) * ((1.0 * fev_after) / h->cfg.mfev) + h->npcap) : np;
+        const size_t smem = ((size_t) 2 * np + 16) * sizeof(int);
+        void *args[] = { (void*) &d, (void*) &c };
+        {
+            ProfScope prof(ctx, BBGPU_PROF_DE_ROUND);
+            BB_CUDA(cudaLaunchCooperativeKernel((const void*) de_generation_kernel, dim3(h->coop_blocks), dim3(256), args, smem, st));
+            BB_TRY(launched(ctx, "de_generation_kernel"));
+        }
+        // the kernel sorted once (JADE: at the start, L-SHADE: at the end): the live buffers swapped
+        std::swap(h->d.SW, h->SWalt);
+        std::swap(h->d.F, h->Falt);
+        h->fev = fev_after;
+        h->gen++;
+        if (h->cfg.kind == BBGPU_DE_SHADE && c.npnew < h->np) h->np = c.npnew;
+        h->fin = -1; // resolved from rounds_dev on demand
+        if (out) {
+            BB_CUDA(cudaMemcpyAsync(h->h_rep, h->d_rep, sizeof(bbgpu_de_report), cudaMemcpyDeviceToHost, st));
+            BB_CUDA(cudaStreamSynchronize(st));
+            *out = *h->h_rep;
+            out->fev = h->fev;
+        }
+        return BBGPU_OK;
     }
     BB_CUDA(cudaMemsetAsync(d.nrecomp, 0, DE_MAX_ROUNDS * sizeof(int), st));
     de_params_kernel<<<ceil_div(np, 256), 256, 0, st>>>(d);
@@ -685,6 +874,12 @@ int bbgpu_de_get_trace(bbgpu_de *h, int32_t *h_succ, double *h_ftrial, double *h
     BB_ARG(h);
     cudaStream_t st = h->ctx->stream;
     const int np = h->d.np;
+    if (h->fin < 0) {
+        int rounds = 0;
+        BB_CUDA(cudaMemcpyAsync(&rounds, h->rounds_dev, 4, cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        h->fin = rounds & 1;
+    }
     if (h_succ) BB_CUDA(cudaMemcpyAsync(h_succ, h->d.succ[h->fin], (size_t) np * 4, cudaMemcpyDeviceToHost, st));
     if (h_ftrial) BB_CUDA(cudaMemcpyAsync(h_ftrial, h->d.FT, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
     if (h_F) BB_CUDA(cudaMemcpyAsync(h_F, h->d.Fm, (size_t) np * 8, cudaMemcpyDeviceToHost, st));

@@ -39,6 +39,7 @@ struct GemmArgs {
     int64_t ldb;
     int M, N, K;
     const double *kscale; // FORM2: per-k coefficient applied to the A operand (nullptr -> 1)
+    bool kscale_padded;   // kscale is readable (and zero) up to the next multiple of 32 past K: TMA path allowed
     // epilogue
     double *C;
     int64_t ldc;

@@ -29,7 +29,7 @@ template<int MA, int NA, int BK, int STAGES> struct TmaSmem {
     static constexpr int BN = NA * 16;
     static constexpr int ASZ = BM * BK;
     static constexpr int BSZ = BK * BN;
-    static constexpr int STAGE = ASZ + BSZ;
+    static constexpr int STAGE = ASZ + BSZ + BK; // A tile, B tile, per-k coefficients (FORM 2)
     static constexpr size_t BYTES = (size_t) STAGE * STAGES * sizeof(double) + 2 * STAGES * sizeof(unsigned long long) + 128;
 };
 
@@ -53,6 +53,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, int parity) {
         if (done) return;
     }
     __trap();
+}
+// 1-D bulk copy global -> shared, completing on the same transaction barrier (SASS UBLKCP)
+__device__ __forceinline__ void bulk_load_1d(void *smem, const void *gmem, int bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+            :: "r"((unsigned) __cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes),
+               "r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, int c0, int c1, unsigned long long *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
@@ -91,7 +97,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
     if (warp == T_CONSUMERS / 32) {
         // ===== TMA producer (one elected lane) =====
         if (lane == 0) {
-            constexpr int TX = S::STAGE * (int) sizeof(double);
+            const bool scaled = FORM == 2 && p.kscale != nullptr;
+            const int TX = (S::ASZ + S::BSZ + (scaled ? BK : 0)) * (int) sizeof(double);
             for (int kc = 0; kc < nk; kc++) {
                 const int s = kc % STAGES, ph = (kc / STAGES) & 1;
                 mbar_wait(empty + s, ph ^ 1);
@@ -108,6 +115,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
                 }
 #pragma unroll
                 for (int q = 0; q < BN / 8; q++) tma_load_2d(Bs + q * (BK * 8), &mapB, n0 + q * 8, k0, full + s);
+                // per-k coefficients of this chunk (the caller pads kscale to a multiple of BK doubles)
+                if (scaled) bulk_load_1d(Bs + S::BSZ, p.kscale + k0, BK * (int) sizeof(double), full + s);
             }
         }
         return;
@@ -127,6 +136,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
         mbar_wait(full + s, ph);
         const double *As = smem + (size_t) s * S::STAGE;
         const double *Bs = As + S::ASZ;
+        const double *Ks = Bs + S::BSZ;
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ks++) {
             double a[MA], b[NA];
@@ -134,8 +144,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
 #pragma unroll
                 for (int i = 0; i < MA; i++) a[i] = As[ks * (BM * 4) + (wm * (MA * 8) + i * 8 + g) * 4 + t];
             } else {
-                const int k = kc * BK + ks * 4 + t;
-                const double sc = (p.kscale != nullptr && k < p.K) ? p.kscale[k] : 1.0;
+                // rows k >= K of the operands are zero-filled by TMA, so a stale coefficient there is harmless
+                // as long as it is finite: the pad of kscale is zero
+                const double sc = (p.kscale != nullptr) ? Ks[ks * 4 + t] : 1.0;
 #pragma unroll
                 for (int i = 0; i < MA; i++) a[i] = As[(wm * MA + i) * (BK * 8) + (ks * 4 + t) * 8 + g] * sc;
             }
@@ -273,7 +284,7 @@ inline int launch_gemm_tma_tile(bbgpu_ctx *ctx, const GemmArgs &a) {
 // 256-byte cudaMalloc alignment, pitch = multiple of 8 doubles)
 inline bool tma_ok(const GemmArgs &a) {
     return tma_encoder() != nullptr && (a.lda % 2 == 0) && (a.ldb % 2 == 0) && (((uintptr_t) a.A) % 16 == 0) &&
-            (((uintptr_t) a.B) % 16 == 0);
+            (((uintptr_t) a.B) % 16 == 0) && (a.kscale == nullptr || (a.kscale_padded && ((uintptr_t) a.kscale) % 16 == 0));
 }
 
 // The one entry point the engine uses.  TMA path by default; BBGPU_GEMM_TMA=0 selects the cp.async
