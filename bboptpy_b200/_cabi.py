@@ -137,6 +137,8 @@ def lib():
     L.bbgpu_de_get_archive.argtypes = [vp, vp, P(i)]
     L.bbgpu_de_get_memory.argtypes = [vp, vp, vp]
     L.bbgpu_de_get_trace.argtypes = [vp, vp, vp, vp, vp]
+    L.bbgpu_de_phase_times.argtypes = [vp, vp]
+    L.bbgpu_de_generation_batch.argtypes = [vp, i, vp, vp]
     _lib = L
     return L
 
@@ -458,6 +460,23 @@ class De:
         mcr, mf = np.empty(h), np.empty(h)
         check(self.L.bbgpu_de_get_memory(self.h, mcr.ctypes.data, mf.ctypes.data))
         return mcr, mf
+
+    @staticmethod
+    def generation_batch(runs, obj, want_report=True):
+        """One generation of several independent runs (same configuration) in one launch."""
+        L = runs[0].L
+        hs = (ctypes.c_void_p * len(runs))(*[r.h for r in runs])
+        reps = (DeReport * len(runs))() if want_report else None
+        check(L.bbgpu_de_generation_batch(hs, len(runs), obj.h, reps))
+        if want_report:
+            for r, rep in zip(runs, reps):
+                r.np = rep.np
+        return reps
+
+    def phase_times(self):
+        t = np.zeros(32, dtype=np.uint64)
+        check(self.L.bbgpu_de_phase_times(self.h, t.ctypes.data))
+        return t
 
     def trace(self, np_gen):
         succ = np.empty(np_gen, dtype=np.int32)

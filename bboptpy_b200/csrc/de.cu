@@ -7,19 +7,25 @@
 // draws.  A one-shot synchronous kernel is not equivalent.  The engine keeps the exact
 // sequential semantics and resolves them in parallel as a fixed point:
 //
-//   round r: every candidate (one warp each) derives the *signature* of what the sequential
-//            loop would have shown it -- for each parent j < i either "old row" or "trial of j,
-//            version v", the archive writer of its slot, its r2 -- from the previous round's
-//            success flags.  If the signature changed it rebuilds its trial (mutation, binomial
-//            crossover, midpoint bound repair), evaluates it with the registry objective in the
-//            same warp, and publishes (success, version).  Candidate 0 is final after round 1,
-//            candidate i once its predecessors are; a round with no rebuild is the fixed point,
-//            which equals the sequential result by induction on i.
+//   round r: every candidate derives the *signature* of what the sequential loop would have
+//            shown it -- for each parent j < i either "old row" or "trial of j, version v", the
+//            archive writer of its slot, its r2 -- from the previous round's success flags.  If
+//            the signature changed it rebuilds its trial (mutation, binomial crossover, midpoint
+//            bound repair), evaluates it with the registry objective in the same pass, and
+//            publishes (success, version).  Candidate 0 is final after round 1, candidate i once
+//            its predecessors are; a round with no rebuild is the fixed point, which equals the
+//            sequential result by induction on i.
 //
-// Trials are double buffered per candidate so a reader never sees a row being rewritten.
-// After the fixed point: archive writes (last writer per slot wins, old rows), parameter
-// adaptation, greedy replacement, and for L-SHADE the end-of-generation sort, population
-// reduction and archive trimming.  Memory-bound: 5 row passes of n doubles per evaluation.
+// Layout: every row (swarm member, archive entry, trial) lives in ONE pool of 4*np rows and is
+// addressed through row ids (srow / arch_row / trow).  Greedy replacement, the archive push, the
+// sort and L-SHADE's population reduction therefore move ids, never rows: the only row traffic of
+// a generation is the 4 parent reads + 1 trial write of every (re)built trial -- the
+// 5 * 8n bytes per candidate-evaluation the roofline counts.
+//
+// One cooperative launch runs a whole generation for one run or for a batch of independent runs
+// (same configuration, different seeds): sort + parameters -> rounds (grid.sync between rounds)
+// -> finalize (id swaps, adaptation) -> [L-SHADE sort] -> report.  A candidate is built by a
+// group of 128 threads with 32-byte row accesses; 4 groups per CTA, 2 CTAs per SM.
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -34,19 +40,44 @@
 namespace bb {
 
 constexpr int DE_MAX_ROUNDS = 4096;
+constexpr int DE_GROUP = 128;                 // threads that build one candidate
+constexpr int DE_GROUPS = 4;                  // candidates in flight per CTA
+constexpr int DE_CTA = DE_GROUP * DE_GROUPS;  // 512
+constexpr int DE_TILE = 1024;                 // objective terms staged in shared memory per pass
 enum { TAG_CR = 1, TAG_F = 2, TAG_IBEST = 3, TAG_R1 = 4, TAG_R2 = 5, TAG_JRAND = 6, TAG_SLOT = 7, TAG_CROSS = 8,
        TAG_RI = 9, TAG_PI = 10, TAG_TRIM = 11, TAG_INIT = 12 };
 
+// One run's device-resident state.  The struct itself lives in device memory; the generation
+// kernel advances the evolving scalars (np, fev, gen, cur), so a free-running run needs no host
+// traffic between generations.
 struct DeDev {
-    int kind, n, np, npA /* archive capacity == current np */, h, archive, repaircr, replay, obj_id;
+    // configuration
+    int kind, n, npcap, h, archive, repaircr, npmin, mfev;
     int64_t ld;
-    uint64_t seed, gen;
-    double pelite;
-    const double *aux, *lower, *upper;
-    double *SW, *F, *ARCH, *TR[2], *FT, *CR, *Fm, *CR1, *MCR, *MF, *mu /* [mucr, muf] */;
+    uint64_t seed;
+    double pelite, cdamp, sigma_cr;
+    const double *lower, *upper;
+    // evolving scalars
+    int np, fev, cur /* live side of the double-buffered (srow, F, R) */, last_fin, last_rounds, last_np;
+    uint64_t gen;
+    // rows
+    double *POOL;
+    int *srow[2], *trow[2], *arch_row;
+    // per member / per candidate
+    double *F[2], *R[2] /* ||x_i|| */, *FT, *RT, *DF /* f_parent - f_trial */, *CR, *Fm, *CR1, *MCR, *MF, *mu /* [mucr, muf] */;
     const double *zcr, *cauchy, *U;
-    int *ibest, *r1, *r2, *jrand, *slot, *ri, *arch_row, *larch /* device scalar */;
-    int *succ[2], *ver[2], *trbuf[2], *sig, *nrecomp, *kslot;
+    int *ibest, *r1, *r2, *jrand, *slot, *ri;
+    const int *trim;
+    int *larch, *larch_new, *nsucc, *kslot;
+    int *succ[2], *ver[2], *trbuf[2], *sig;
+    bbgpu_de_report *rep;
+};
+
+struct DeLaunch {
+    int nruns, cpr /* CTAs per run */, kind, obj_id, replay, ntrim, npnew;
+    const double *aux;
+    int *nrecomp;                 // [DE_MAX_ROUNDS] rebuilds per round, over all runs of the launch
+    unsigned long long *phase_ns; // [32] %globaltimer at phase boundaries (diagnostics)
 };
 
 __device__ __forceinline__ uint32_t de_u32(const DeDev &d, int cand, int slot, int tag) {
@@ -63,14 +94,18 @@ __device__ __forceinline__ int de_int(const DeDev &d, int cand, int slot, int ta
     return (int) __umulhi(de_u32(d, cand, slot, tag), (uint32_t) range);
 }
 
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "r"(DE_GROUP) : "memory");
+}
+
 // per-candidate control parameters for the generation (de/jade.cpp:107-126, de/shade.cpp:104-126)
-__device__ __forceinline__ void de_params_one(const DeDev &d, int i) {
+__device__ __forceinline__ void de_params_one(const DeDev &d, int replay, int i) {
     int ri = 0;
-    if (d.kind == BBGPU_DE_SHADE) ri = d.replay ? d.ri[i] : de_int(d, i, 0, TAG_RI, d.h);
+    if (d.kind == BBGPU_DE_SHADE) ri = replay ? d.ri[i] : de_int(d, i, 0, TAG_RI, d.h);
     const double mcr = d.kind == BBGPU_DE_JADE ? d.mu[0] : d.MCR[ri];
     const double mf = d.kind == BBGPU_DE_JADE ? d.mu[1] : d.MF[ri];
     double z, c, F;
-    if (d.replay) {
+    if (replay) {
         z = d.zcr[i];
         c = d.cauchy[i];
         F = fmin(__dadd_rn(__dmul_rn(c, 0.1), mf), 1.0);
@@ -107,13 +142,8 @@ __device__ __forceinline__ void de_params_one(const DeDev &d, int i) {
     d.trbuf[0][i] = 0;
 }
 
-__global__ void __launch_bounds__(256) de_params_kernel(DeDev d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < d.np) de_params_one(d, i);
-}
-
-// CTA-wide (256 threads): push flags -> exclusive prefix counts `pre` and archive targets `tgt` (both in
-// smem, np ints each); wsum[0..8] scratch, wsum[8] = total pushes
+// CTA-wide: push flags -> exclusive prefix counts `pre` and archive targets `tgt` (both in smem, np
+// ints each); wsum[0..nwarps) scratch, wsum[32] = total pushes
 __device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__restrict__ succ, int larch0, int *pre, int *tgt,
         int *wsum) {
     const int np = d.np, T = blockDim.x;
@@ -121,6 +151,7 @@ __device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__res
     const int b = threadIdx.x * per, e = min(np, b + per);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int local = 0;
+    __syncthreads(); // previous readers of pre / tgt are done
     for (int i = b; i < e; i++) {
         const int s = succ[i];
         const int push = d.archive && (d.kind == BBGPU_DE_JADE ? (s >= 1) : (s == 2));
@@ -133,7 +164,6 @@ __device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__res
         const int v = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += v;
     }
-    __syncthreads(); // previous users of wsum are done
     if (lane == 31) wsum[wid] = incl;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -144,7 +174,7 @@ __device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__res
             wsum[w] = run;
             run += v;
         }
-        wsum[8] = run;
+        wsum[32] = run;
     }
     __syncthreads();
     int run = wsum[wid] + incl - local;
@@ -152,31 +182,62 @@ __device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__res
         const int push = tgt[i];
         pre[i] = run;
         const int la = larch0 + run;
-        tgt[i] = push ? (la < d.npA ? la : d.slot[i]) : -1;
+        tgt[i] = push ? (la < np ? la : d.slot[i]) : -1;
         run += push;
     }
     __syncthreads();
 }
 
-// one candidate (one warp) in one resolution round
-__device__ __forceinline__ void de_candidate(const DeDev &d, int i, int round, int larch0, const int *pre, const int *tgt) {
+// Trial coordinate j of candidate i: binomial crossover + current-to-pbest/1 mutation + midpoint repair.
+struct DeBuild {
+    const double *xi, *xb, *x1, *x2, *lo, *hi, *U;
+    double F, CR;
+    int jr, replay;
+};
+
+__device__ __forceinline__ double de_trial_coord(const DeBuild &b, int j, double x, double vb, double v1, double v2,
+        double lo, double hi, double u, int &cnt) {
+    const bool cross = (j == b.jr) || (u < b.CR);
+    double v = x;
+    if (cross) {
+        // x + F*(best - x) + F*(xr1 - xr2), left to right, no contraction (de/jade.cpp:253)
+        v = __dadd_rn(__dadd_rn(x, __dmul_rn(b.F, __dsub_rn(vb, x))), __dmul_rn(b.F, __dsub_rn(v1, v2)));
+        cnt++;
+    }
+    if (v < lo) v = __dmul_rn(__dadd_rn(lo, x), 0.5);       // midpoint repair (de/jade.cpp:150-156)
+    else if (v > hi) v = __dmul_rn(__dadd_rn(hi, x), 0.5);
+    return v;
+}
+
+__device__ __forceinline__ double u32_unit(uint32_t w) { return (double) w * (1.0 / 4294967296.0); }
+
+__device__ __forceinline__ Philox4 de_cross_block(const DeDev &d, int i, int quad) {
+    return philox4x32_10((uint32_t) quad, (uint32_t) i, (uint32_t) d.gen,
+            ((uint32_t) (d.gen >> 32)) ^ ((uint32_t) TAG_CROSS << 24), (uint32_t) d.seed, (uint32_t) (d.seed >> 32));
+}
+
+// one candidate (one 128-thread group) in one resolution round.  T1/T2: this group's term buffers.
+template<int ID, bool REPLAY>
+__device__ __noinline__ void de_candidate(const DeDev &d, const DeLaunch &L, int cj, int i, int round, int larch0,
+        const int *pre, const int *tgt, int g, double *T1, double *T2, double *gred) {
     const int cur = round & 1, nxt = cur ^ 1;
-    const int lane = threadIdx.x & 31;
+    const int gt = threadIdx.x & (DE_GROUP - 1), lane = threadIdx.x & 31, gwarp = gt >> 5;
     const int np = d.np, n = d.n;
     const int *succ = d.succ[cur], *ver = d.ver[cur], *trb = d.trbuf[cur];
-    const int larch_i = d.archive ? min(d.npA, larch0 + pre[i]) : 0;
+    const int larch_i = d.archive ? min(np, larch0 + pre[i]) : 0;
     const int jb = d.ibest[i], j1 = d.r1[i];
     int j2;
-    if (d.replay) {
+    if (REPLAY) {
         j2 = d.r2[i];
     } else {
         j2 = i;
         int t = 0;
         while ((j2 == i || j2 == j1) && (np + larch_i > 2)) j2 = de_int(d, i, t++, TAG_R2, np + larch_i);
     }
-    int s0 = (jb < i && succ[jb]) ? ver[jb] : 0;
-    int s1 = (j1 < i && succ[j1]) ? ver[j1] : 0;
-    int s2, writer = -1;
+    const int sb = jb < i ? succ[jb] : 0, s1f = j1 < i ? succ[j1] : 0;
+    const int s0 = sb ? ver[jb] : 0;
+    const int s1 = s1f ? ver[j1] : 0;
+    int s2, writer = -1, s2f = 0;
     if (j2 >= np) {
         const int a = j2 - np;
         for (int j = lane; j < i; j += 32)
@@ -185,13 +246,13 @@ __device__ __forceinline__ void de_candidate(const DeDev &d, int i, int round, i
         for (int off = 16; off >= 1; off >>= 1) writer = max(writer, __shfl_xor_sync(0xffffffffu, writer, off));
         s2 = -2 - writer;
     } else {
-        s2 = (j2 < i && succ[j2]) ? ver[j2] : 0;
+        s2f = j2 < i ? succ[j2] : 0;
+        s2 = s2f ? ver[j2] : 0;
     }
     int *sg = d.sig + 4 * i;
     const bool same = sg[0] == s0 && sg[1] == s1 && sg[2] == s2 && sg[3] == j2;
-    __syncwarp();
-    if (same) {
-        if (lane == 0) {
+    if (same) { // group-uniform
+        if (gt == 0) {
             d.succ[nxt][i] = succ[i];
             d.ver[nxt][i] = ver[i];
             d.trbuf[nxt][i] = trb[i];
@@ -199,98 +260,138 @@ __device__ __forceinline__ void de_candidate(const DeDev &d, int i, int round, i
         return;
     }
     const int64_t ld = d.ld;
-    const double *xi = d.SW + (int64_t) i * ld;
-    const double *xb = (jb < i && succ[jb]) ? d.TR[trb[jb]] + (int64_t) jb * ld : d.SW + (int64_t) jb * ld;
-    const double *x1 = (j1 < i && succ[j1]) ? d.TR[trb[j1]] + (int64_t) j1 * ld : d.SW + (int64_t) j1 * ld;
-    const double *x2;
-    if (j2 >= np) x2 = writer >= 0 ? d.SW + (int64_t) writer * ld : d.ARCH + (int64_t) d.arch_row[j2 - np] * ld;
-    else x2 = (j2 < i && succ[j2]) ? d.TR[trb[j2]] + (int64_t) j2 * ld : d.SW + (int64_t) j2 * ld;
+    const int *srow = d.srow[cj];
+    DeBuild b;
+    b.xi = d.POOL + (int64_t) srow[i] * ld;
+    b.xb = d.POOL + (int64_t) (sb ? d.trow[trb[jb]][jb] : srow[jb]) * ld;
+    b.x1 = d.POOL + (int64_t) (s1f ? d.trow[trb[j1]][j1] : srow[j1]) * ld;
+    if (j2 >= np) b.x2 = d.POOL + (int64_t) (writer >= 0 ? srow[writer] : d.arch_row[j2 - np]) * ld;
+    else b.x2 = d.POOL + (int64_t) (s2f ? d.trow[trb[j2]][j2] : srow[j2]) * ld;
     const int mybuf = 1 - trb[i];
-    double *out = d.TR[mybuf] + (int64_t) i * ld;
-    const double F = d.Fm[i], CR = d.CR[i];
-    const int jr = d.jrand[i];
+    double *out = d.POOL + (int64_t) d.trow[mybuf][i] * ld;
+    b.lo = d.lower; b.hi = d.upper; b.U = d.U + (int64_t) i * n;
+    b.F = d.Fm[i]; b.CR = d.CR[i]; b.jr = d.jrand[i]; b.replay = REPLAY;
+    constexpr int id = ID;
+    const int nt = obj_term_count(id, n);
+    const bool rosen = id == BBGPU_OBJ_ROSENBROCK, ackley = id == BBGPU_OBJ_ACKLEY, ellip = id == BBGPU_OBJ_ELLIPSOID;
     int cnt = 0;
-    for (int j = lane; j < n; j += 32) {
-        bool cross = (j == jr);
-        if (!cross) {
-            double u;
-            if (d.replay) {
-                u = d.U[(int64_t) i * n + j];
-            } else {
-                const Philox4 r = philox4x32_10((uint32_t) (j >> 2), (uint32_t) i, (uint32_t) d.gen,
-                        ((uint32_t) (d.gen >> 32)) ^ ((uint32_t) TAG_CROSS << 24), (uint32_t) d.seed, (uint32_t) (d.seed >> 32));
-                const uint32_t w = (j & 3) == 0 ? r.x : (j & 3) == 1 ? r.y : (j & 3) == 2 ? r.z : r.w;
-                u = (double) w * (1.0 / 4294967296.0);
+    double nrm = 0.0, acc = 0.0, acc2 = 0.0;
+    for (int t0 = 0; t0 < n; t0 += DE_TILE) {
+        if (t0 > 0) group_sync(g); // the previous tile's terms have been consumed
+        const int tl = min(DE_TILE, n - t0);
+        for (int q = gt; 4 * q < tl; q += DE_GROUP) {
+            // one Philox block per 4 coordinates; the quad is processed as two 16-byte halves to bound registers
+            Philox4 r = { 0u, 0u, 0u, 0u };
+            if (!REPLAY) r = de_cross_block(d, i, (t0 >> 2) + q);
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                const int j = t0 + 4 * q + 2 * h; // rows are 64-byte aligned and padded to a multiple of 8 doubles
+                if (j >= n) break;
+                const double2 xa = *(const double2*) (b.xi + j);
+                const double2 ba = *(const double2*) (b.xb + j);
+                const double2 pa = *(const double2*) (b.x1 + j);
+                const double2 qa = *(const double2*) (b.x2 + j);
+                const double2 la = *(const double2*) (b.lo + j);
+                const double2 ha = *(const double2*) (b.hi + j);
+                double u0, u1;
+                if (REPLAY) {
+                    u0 = b.U[j]; u1 = j + 1 < n ? b.U[j + 1] : 2.0;
+                } else {
+                    u0 = u32_unit(h ? r.z : r.x); u1 = u32_unit(h ? r.w : r.y);
+                }
+                const double v0 = de_trial_coord(b, j, xa.x, ba.x, pa.x, qa.x, la.x, ha.x, u0, cnt);
+                double v1 = 0.0;
+                if (j + 1 < n) v1 = de_trial_coord(b, j + 1, xa.y, ba.y, pa.y, qa.y, la.y, ha.y, u1, cnt);
+                *(double2*) (out + j) = make_double2(v0, v1);
+                nrm = fma(v0, v0, fma(v1, v1, nrm));
+                double v2 = 0.0;
+                if (rosen && j + 2 < n) { // the next coordinate, rebuilt here (same inputs, same bits)
+                    double u2;
+                    if (REPLAY) u2 = b.U[j + 2];
+                    else u2 = u32_unit(h ? de_cross_block(d, i, (t0 >> 2) + q + 1).x : r.z);
+                    int dummy = 0;
+                    v2 = de_trial_coord(b, j + 2, b.xi[j + 2], b.xb[j + 2], b.x1[j + 2], b.x2[j + 2], b.lo[j + 2], b.hi[j + 2], u2, dummy);
+                }
+                double a0 = 0.0, a1 = 0.0;
+                if (ellip) {
+                    const double2 ea = *(const double2*) (L.aux + j);
+                    a0 = ea.x; a1 = ea.y;
+                }
+                double e0 = 0.0, e1 = 0.0;
+                const double t0v = obj_term(id, v0, v1, a0, e0);
+                const double t1v = obj_term(id, v1, v2, a1, e1);
+                *(double2*) (T1 + 4 * q + 2 * h) = make_double2(t0v, t1v);
+                if (ackley) *(double2*) (T2 + 4 * q + 2 * h) = make_double2(e0, e1);
             }
-            cross = u < CR;
         }
-        const double x = xi[j];
-        double v = x;
-        if (cross) {
-            // x + F*(best - x) + F*(xr1 - xr2), left to right, no contraction (de/jade.cpp:253)
-            v = __dadd_rn(__dadd_rn(x, __dmul_rn(F, __dsub_rn(xb[j], x))), __dmul_rn(F, __dsub_rn(x1[j], x2[j])));
-            cnt++;
+        group_sync(g);
+        if (gwarp == 0) { // spec order: lane l adds term(i) for i = l, l+32, ... ascending (t0 is a multiple of 32)
+            const int kend = min(tl, nt - t0);
+            for (int k = lane; k < kend; k += 32) {
+                acc = add(acc, T1[k]);
+                if (ackley) acc2 = add(acc2, T2[k]);
+            }
         }
-        const double lo = d.lower[j], hi = d.upper[j];
-        if (v < lo) v = __dmul_rn(__dadd_rn(lo, x), 0.5);       // midpoint repair (de/jade.cpp:150-156)
-        else if (v > hi) v = __dmul_rn(__dadd_rn(hi, x), 0.5);
-        out[j] = v;
     }
-    __syncwarp();
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-    const double ft = warp_objective(d.obj_id, n, (const double*) out, d.aux);
+    for (int off = 16; off >= 1; off >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        nrm += __shfl_xor_sync(0xffffffffu, nrm, off);
+    }
+    if (lane == 0) { gred[2 * gwarp] = (double) cnt; gred[2 * gwarp + 1] = nrm; }
+    group_sync(g);
+    if (gwarp == 0) {
+        const double sum1 = warp_sum(acc);
+        const double sum2 = ackley ? warp_sum(acc2) : 0.0;
+        const double ft = obj_finish(id, n, sum1, sum2);
+        if (lane == 0) {
+            double cn = 0.0, nr = 0.0;
+            for (int w = 0; w < DE_GROUP / 32; w++) { cn += gred[2 * w]; nr += gred[2 * w + 1]; }
+            const double fi = d.F[cj][i];
+            const int s = ft <= fi ? (ft < fi ? 2 : 1) : 0;
+            d.FT[i] = ft;
+            d.DF[i] = fi - ft;
+            d.RT[i] = sqrt(nr);
+            d.CR1[i] = d.repaircr ? __ddiv_rn(cn, (double) n) : b.CR;
+            d.succ[nxt][i] = s;
+            d.trbuf[nxt][i] = mybuf;
+            d.ver[nxt][i] = ver[i] + ((s != succ[i] || s > 0) ? 1 : 0);
+            sg[0] = s0; sg[1] = s1; sg[2] = s2; sg[3] = j2;
+            d.r2[i] = j2;
+            atomicAdd(L.nrecomp + round, 1);
+        }
+    }
+    group_sync(g); // gred / T1 are free again
+}
+
+// after the fixed point, one warp per successful candidate: the greedy replacement and the archive push
+// as row-id swaps (de/jade.cpp:161-176).  Last writer per archive slot wins; the archived row is the OLD parent.
+__device__ __forceinline__ void de_finalize_one(const DeDev &d, int cj, int i, int fin, const int *tgt) {
+    if (d.succ[fin][i] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int a = tgt[i];
+    int later = 0;
+    if (a >= 0) {
+        for (int q = i + 1 + lane; q < d.np; q += 32) later |= (tgt[q] == a);
+        later = __any_sync(0xffffffffu, later);
+    }
     if (lane == 0) {
-        const double fi = d.F[i];
-        const int s = ft <= fi ? (ft < fi ? 2 : 1) : 0;
-        d.FT[i] = ft;
-        d.CR1[i] = d.repaircr ? __ddiv_rn((double) cnt, (double) n) : CR;
-        d.succ[nxt][i] = s;
-        d.trbuf[nxt][i] = mybuf;
-        d.ver[nxt][i] = ver[i] + ((s != succ[i] || s > 0) ? 1 : 0);
-        sg[0] = s0; sg[1] = s1; sg[2] = s2; sg[3] = j2;
-        d.r2[i] = j2;
-        atomicAdd(d.nrecomp + round, 1);
+        const int tb = d.trbuf[fin][i];
+        const int t = d.trow[tb][i], p = d.srow[cj][i];
+        int freed = p;
+        if (a >= 0 && !later) {
+            freed = d.arch_row[a];
+            d.arch_row[a] = p;
+        }
+        d.srow[cj][i] = t;
+        d.trow[tb][i] = freed;
+        d.F[cj][i] = d.FT[i];
+        d.R[cj][i] = d.RT[i];
     }
 }
 
-// one resolution round; 8 candidates (warps) per CTA
-__global__ void __launch_bounds__(256) de_round_kernel(DeDev d, int round) {
-    extern __shared__ int sm[];
-    int *pre = sm, *tgt = sm + d.np, *wsum = sm + 2 * d.np;
-    const int larch0 = *d.larch;
-    de_scan_targets(d, d.succ[round & 1], larch0, pre, tgt, wsum);
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i < d.np) de_candidate(d, i, round, larch0, pre, tgt);
-}
-
-// after the fixed point: archive rows (last writer per slot wins; the value is the OLD parent row)
-__device__ __forceinline__ void de_archive_one(const DeDev &d, int j, const int *tgt) {
-    const int lane = threadIdx.x & 31;
-    const int a = tgt[j];
-    if (a < 0) return;
-    int later = 0;
-    for (int q = j + 1 + lane; q < d.np; q += 32) later |= (tgt[q] == a);
-    later = __any_sync(0xffffffffu, later);
-    if (later) return;
-    const double *src = d.SW + (int64_t) j * d.ld;
-    double *dst = d.ARCH + (int64_t) d.arch_row[a] * d.ld;
-    for (int c = lane; c < d.n; c += 32) dst[c] = src[c];
-}
-
-__global__ void __launch_bounds__(256) de_archive_kernel(DeDev d, int fin, int *larch_new) {
-    extern __shared__ int sm[];
-    int *pre = sm, *tgt = sm + d.np, *wsum = sm + 2 * d.np;
-    const int larch0 = *d.larch;
-    de_scan_targets(d, d.succ[fin], larch0, pre, tgt, wsum);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *larch_new = d.archive ? min(d.npA, larch0 + wsum[8]) : 0;
-    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (j < d.np) de_archive_one(d, j, tgt);
-}
-
-// parameter adaptation (de/jade.cpp:185-205, de/shade.cpp:186-212); reads the OLD parent fitness
-__device__ __forceinline__ void de_adapt_block(const DeDev &d, int fin, double cdamp, double sigma_cr, int *nsucc_out,
-        double *red) {
+// parameter adaptation (de/jade.cpp:185-205, de/shade.cpp:186-212)
+__device__ __forceinline__ void de_adapt_block(const DeDev &d, int fin, int *nsucc_out, double *red) {
     const int *succ = d.succ[fin];
     const bool jade = d.kind == BBGPU_DE_JADE;
     double cnt = 0, s_cr = 0, s_cr2 = 0, s_f = 0, s_f2 = 0, s_w = 0, s_wcr = 0, s_wf = 0, s_wf2 = 0, acc = 0;
@@ -302,7 +403,7 @@ __device__ __forceinline__ void de_adapt_block(const DeDev &d, int fin, double c
             cnt += 1.0;
             s_cr += cr; s_cr2 += cr * cr; s_f += f; s_f2 += f * f;
             if (!jade) {
-                const double w = d.F[i] - d.FT[i];
+                const double w = d.DF[i];
                 s_w += w; s_wcr += w * cr; s_wf += w * f; s_wf2 += w * f * f;
             }
         }
@@ -325,11 +426,11 @@ __device__ __forceinline__ void de_adapt_block(const DeDev &d, int fin, double c
             double meancr = 0.0, meanf = 0.0;
             if (cnt > 0) {
                 const double sd = sqrt(dev2 / cnt);
-                meancr = sd > sigma_cr ? sqrt(s_cr2 / cnt) : s_cr / cnt;
+                meancr = sd > d.sigma_cr ? sqrt(s_cr2 / cnt) : s_cr / cnt;
                 meanf = (s_f2 / cnt) / (s_f / cnt);
             }
-            d.mu[0] = (1.0 - cdamp) * d.mu[0] + cdamp * meancr;
-            d.mu[1] = (1.0 - cdamp) * d.mu[1] + cdamp * meanf;
+            d.mu[0] = (1.0 - d.cdamp) * d.mu[0] + d.cdamp * meancr;
+            d.mu[1] = (1.0 - d.cdamp) * d.mu[1] + d.cdamp * meanf;
         } else if (cnt > 0) {
             int k = *d.kslot;
             d.MCR[k - 1] = s_wcr / s_w;
@@ -341,41 +442,12 @@ __device__ __forceinline__ void de_adapt_block(const DeDev &d, int fin, double c
     }
 }
 
-__global__ void __launch_bounds__(1024) de_adapt_kernel(DeDev d, int fin, double cdamp, double sigma_cr, int *nsucc_out) {
-    __shared__ double red[32];
-    de_adapt_block(d, fin, cdamp, sigma_cr, nsucc_out, red);
-}
-
-// greedy replacement (de/jade.cpp:174-176)
-__device__ __forceinline__ void de_replace_one(const DeDev &d, int i, int fin) {
-    if (d.succ[fin][i] == 0) return;
-    const int lane = threadIdx.x & 31;
-    const double *src = d.TR[d.trbuf[fin][i]] + (int64_t) i * d.ld;
-    double *dst = d.SW + (int64_t) i * d.ld;
-    for (int c = lane; c < d.n; c += 32) dst[c] = src[c];
-    if (lane == 0) d.F[i] = d.FT[i];
-}
-
-__global__ void __launch_bounds__(256) de_replace_kernel(DeDev d, int fin) {
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i < d.np) de_replace_one(d, i, fin);
-}
-
-__global__ void __launch_bounds__(256) de_gather_rows_kernel(const double *__restrict__ src, double *__restrict__ dst,
-        const int *__restrict__ perm, int rows, int n, int64_t ld) {
-    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (r >= rows) return;
-    const double *s = src + (int64_t) perm[r] * ld;
-    double *t = dst + (int64_t) r * ld;
-    for (int c = threadIdx.x & 31; c < n; c += 32) t[c] = s[c];
-}
-
 // archive trimming by random erase (de/shade.cpp:228-235) on the row-index indirection
-__device__ __forceinline__ void de_trim_thread(const DeDev &d, int *larch, int npnew, const int *trim, int ntrim) {
-    int la = *larch, t = 0;
+__device__ __forceinline__ int de_trim_thread(const DeDev &d, int la, int replay, int npnew, int ntrim) {
+    int t = 0;
     while (la > npnew) {
         int r;
-        if (d.replay) r = t < ntrim ? trim[t] : 0;
+        if (replay) r = t < ntrim ? d.trim[t] : 0;
         else r = de_int(d, 0, t, TAG_TRIM, la);
         t++;
         const int saved = d.arch_row[r];
@@ -383,80 +455,15 @@ __device__ __forceinline__ void de_trim_thread(const DeDev &d, int *larch, int n
         d.arch_row[la - 1] = saved;
         la--;
     }
-    *larch = la;
+    return la;
 }
 
-__global__ void de_trim_kernel(DeDev d, int *larch, int npnew, const int *trim, int ntrim) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) de_trim_thread(d, larch, npnew, trim, ntrim);
-}
-
-// ||x_i||_2 per member, then Welford-equivalent M2 of the radii and the best fitness
-__global__ void __launch_bounds__(256) de_norms_kernel(const double *__restrict__ SW, int np, int n, int64_t ld,
-        double *__restrict__ radius) {
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= np) return;
-    const double *x = SW + (int64_t) i * ld;
-    double s = 0.0;
-    for (int c = threadIdx.x & 31; c < n; c += 32) s = fma(x[c], x[c], s);
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) radius[i] = sqrt(s);
-}
-
-__device__ __forceinline__ void de_report_block(const DeDev &d, const double *__restrict__ radius, int np, const int *larch,
-        const int *nsucc, bbgpu_de_report *rep, double *red) {
-    double s = 0.0, fb = INFINITY;
-    for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        s += radius[i];
-        fb = fmin(fb, d.F[i]);
-    }
-    s = block_sum(s, red);
-    fb = -block_max(-fb, red);
-    const double mean = s / np;
-    double m2 = 0.0;
-    for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        const double t = radius[i] - mean;
-        m2 += t * t;
-    }
-    m2 = block_sum(m2, red);
-    if (threadIdx.x == 0) {
-        rep->np = np;
-        rep->larch = *larch;
-        rep->nsucc = *nsucc;
-        rep->kslot = *d.kslot;
-        rep->mucr = d.mu[0];
-        rep->muf = d.mu[1];
-        rep->fbest = fb;
-        rep->radius_m2 = m2;
-    }
-}
-
-__global__ void __launch_bounds__(1024) de_report_kernel(DeDev d, const double *__restrict__ radius, int np, const int *larch,
-        const int *nsucc, bbgpu_de_report *rep) {
-    __shared__ double red[32];
-    de_report_block(d, radius, np, larch, nsucc, rep, red);
-}
-
-
-// ------------------------------------------------------------------------------------------
-// The whole generation as ONE cooperative kernel: sort -> parameters -> resolution rounds (grid.sync
-// between rounds, loop until a round rebuilds nothing) -> archive -> adaptation -> replacement ->
-// (L-SHADE: sort, population reduction, archive trimming) -> radii -> report.  No host round trip
-// inside a generation, and none between generations unless the caller asks for the report.
-// ------------------------------------------------------------------------------------------
-struct DeCoop {
-    double *SWalt, *Falt, *radius;
-    int *nsucc, *rounds_out;
-    bbgpu_de_report *rep;
-    double cdamp, sigma_cr;
-    const int *trim;
-    int ntrim, npnew;
-};
-
-// counting rank + row scatter: (SW, F) -> (SWalt, Falt) sorted ascending by (fitness, index)
-__device__ __forceinline__ void de_sort_rows(const double *__restrict__ SW, const double *__restrict__ F,
-        double *__restrict__ SWalt, double *__restrict__ Falt, int np, int n, int64_t ld, int gw, int W) {
-    const int lane = threadIdx.x & 31;
-    for (int i = gw; i < np; i += W) {
+// counting rank of the members [first, np) stride `step` (one warp each) and id scatter:
+// side `from` -> side `to`, ascending by (fitness, index)
+__device__ __forceinline__ void de_sort_ids(const DeDev &d, int from, int to, int first, int step) {
+    const int lane = threadIdx.x & 31, np = d.np;
+    const double *F = d.F[from];
+    for (int i = first; i < np; i += step) {
         const double fi = F[i];
         const unsigned long long ki = sortable_key(fi);
         int cnt = 0;
@@ -466,79 +473,175 @@ __device__ __forceinline__ void de_sort_rows(const double *__restrict__ SW, cons
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-        const double *src = SW + (int64_t) i * ld;
-        double *dst = SWalt + (int64_t) cnt * ld;
-        for (int c = lane; c < n; c += 32) dst[c] = src[c];
-        if (lane == 0) Falt[cnt] = fi;
+        if (lane == 0) {
+            d.F[to][cnt] = fi;
+            d.R[to][cnt] = d.R[from][i];
+            d.srow[to][cnt] = d.srow[from][i];
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) de_generation_kernel(DeDev d, DeCoop c) {
+// end of the generation, one CTA per run: swarm statistics for converged() (de/jade.cpp:228-245), the
+// report, L-SHADE's archive trimming, and the run's evolving scalars
+__device__ __forceinline__ void de_report_block(DeDev *dg, const DeDev &d, const DeLaunch &L, int side, int np_after, int fin,
+        int rounds, double *red) {
+    const double *radius = d.R[side], *F = d.F[side];
+    double s = 0.0, fb = INFINITY;
+    for (int i = threadIdx.x; i < np_after; i += blockDim.x) {
+        s += radius[i];
+        fb = fmin(fb, F[i]);
+    }
+    s = block_sum(s, red);
+    fb = -block_max(-fb, red);
+    const double mean = s / np_after;
+    double m2 = 0.0;
+    for (int i = threadIdx.x; i < np_after; i += blockDim.x) {
+        const double t = radius[i] - mean;
+        m2 += t * t;
+    }
+    m2 = block_sum(m2, red);
+    if (threadIdx.x == 0) {
+        int la = *d.larch_new;
+        if (d.kind == BBGPU_DE_SHADE && d.archive) la = de_trim_thread(d, la, L.replay, L.npnew, L.ntrim);
+        *d.larch = la;
+        bbgpu_de_report *rep = d.rep;
+        rep->np = np_after;
+        rep->larch = la;
+        rep->nsucc = *d.nsucc;
+        rep->fev = d.fev + d.np;
+        rep->rounds = rounds;
+        rep->kslot = *d.kslot;
+        rep->mucr = d.mu[0];
+        rep->muf = d.mu[1];
+        rep->fbest = fb;
+        rep->radius_m2 = m2;
+        dg->fev = d.fev + d.np;
+        dg->np = np_after;
+        dg->gen = d.gen + 1;
+        dg->cur = side;
+        dg->last_fin = fin;
+        dg->last_rounds = rounds;
+        dg->last_np = d.np;
+    }
+}
+
+__global__ void __launch_bounds__(DE_CTA, 2) de_generation_kernel(DeDev *const *__restrict__ runs, DeLaunch L) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ int sm[];
-    int *pre = sm, *tgt = sm + d.np, *wsum = sm + 2 * d.np;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ DeDev d;
     __shared__ double red[32];
-    const int lane = threadIdx.x & 31;
-    const int W = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int GT = gridDim.x * 256, gtid = blockIdx.x * 256 + threadIdx.x;
-    const int np = d.np, n = d.n;
+    __shared__ double gredbuf[DE_GROUPS][2 * (DE_GROUP / 32)];
+    __shared__ int wsum[33];
+    double *terms = (double*) smraw;                           // [DE_GROUPS][2][DE_TILE]
+    int *pre = (int*) (terms + DE_GROUPS * 2 * DE_TILE);       // [np]
+    const int tid = threadIdx.x, warp = tid >> 5, g = tid / DE_GROUP;
+    constexpr int WARPS = DE_CTA / 32;
+    const int ntasks = L.nruns * L.cpr;
+    int loaded = -1;
+    auto load_run = [&](int run) {
+        if (run == loaded) return;
+        __syncthreads();
+        const int *src = (const int*) runs[run];
+        int *dst = (int*) &d;
+        for (int w = tid; w < (int) (sizeof(DeDev) / sizeof(int)); w += DE_CTA) dst[w] = src[w];
+        __syncthreads();
+        loaded = run;
+    };
+    int mark = 0;
+    auto stamp = [&]() {
+        if (L.phase_ns && blockIdx.x == 0 && tid == 0 && mark < 32) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            L.phase_ns[mark] = t;
+        }
+        mark++;
+    };
+    stamp(); // 0 start
 
-    if (d.kind == BBGPU_DE_JADE) { // de/jade.cpp:101
-        de_sort_rows(d.SW, d.F, c.SWalt, c.Falt, np, n, d.ld, gw, W);
-        grid.sync();
-        double *t = d.SW; d.SW = c.SWalt; c.SWalt = t;
-        t = d.F; d.F = c.Falt; c.Falt = t;
+    // ---- phase 0: JADE sorts the swarm (de/jade.cpp:101); control parameters of the generation
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int run = task / L.cpr, part = task % L.cpr;
+        load_run(run);
+        if (d.kind == BBGPU_DE_JADE) de_sort_ids(d, d.cur, d.cur ^ 1, part * WARPS + warp, L.cpr * WARPS);
+        for (int i = part * DE_CTA + tid; i < d.np; i += L.cpr * DE_CTA) de_params_one(d, L.replay, i);
     }
-    for (int i = gtid; i < np; i += GT) de_params_one(d, i);
     grid.sync();
+    stamp(); // 1 sorted + parameters
 
-    const int larch0 = *d.larch;
+    // ---- resolution rounds
     int round = 0;
     while (true) {
-        de_scan_targets(d, d.succ[round & 1], larch0, pre, tgt, wsum);
-        for (int i = gw; i < np; i += W) de_candidate(d, i, round, larch0, pre, tgt);
+        for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+            const int run = task / L.cpr, part = task % L.cpr;
+            load_run(run);
+            int *tgt = pre + d.np;
+            const int cj = d.kind == BBGPU_DE_JADE ? d.cur ^ 1 : d.cur;
+            const int larch0 = *d.larch;
+            de_scan_targets(d, d.succ[round & 1], larch0, pre, tgt, wsum);
+            for (int i0 = part * DE_GROUPS; i0 < d.np; i0 += L.cpr * DE_GROUPS) {
+                const int i = i0 + g;
+                if (i < d.np) {
+                    double *T1 = terms + (size_t) g * 2 * DE_TILE, *T2 = T1 + DE_TILE;
+#define DE_CASE(ID) case ID: if (L.replay) de_candidate<ID, true>(d, L, cj, i, round, larch0, pre, tgt, g, T1, T2, gredbuf[g]); \
+                             else de_candidate<ID, false>(d, L, cj, i, round, larch0, pre, tgt, g, T1, T2, gredbuf[g]); break;
+                    switch (L.obj_id) {
+                    DE_CASE(BBGPU_OBJ_SPHERE) DE_CASE(BBGPU_OBJ_ELLIPSOID) DE_CASE(BBGPU_OBJ_ROSENBROCK)
+                    DE_CASE(BBGPU_OBJ_RASTRIGIN) DE_CASE(BBGPU_OBJ_ACKLEY)
+                    default: break;
+                    }
+#undef DE_CASE
+                }
+            }
+        }
         grid.sync();
-        const int rebuilt = *((volatile int*) (d.nrecomp + round));
+        const int rebuilt = *((volatile int*) (L.nrecomp + round));
         round++;
+        if (round <= 12) stamp(); // 2.. after each of the first 12 rounds
         if (rebuilt == 0 || round >= DE_MAX_ROUNDS) break;
     }
     const int fin = round & 1;
+    mark = 16;
 
-    de_scan_targets(d, d.succ[fin], larch0, pre, tgt, wsum);
-    for (int j = gw; j < np; j += W) de_archive_one(d, j, tgt);
-    if (blockIdx.x == 0) de_adapt_block(d, fin, c.cdamp, c.sigma_cr, c.nsucc, red);
-    grid.sync(); // archive rows and adaptation read the OLD parents; replacement comes after
-
-    for (int i = gw; i < np; i += W) de_replace_one(d, i, fin);
-    if (gtid == 0) {
-        *d.larch = d.archive ? min(d.npA, larch0 + wsum[8]) : 0;
-        for (int r = 0; r < round; r++) d.nrecomp[r] = 0;
-        *c.rounds_out = round;
+    // ---- finalize: row-id swaps for replacement + archive, parameter adaptation
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int run = task / L.cpr, part = task % L.cpr;
+        load_run(run);
+        int *tgt = pre + d.np;
+        const int cj = d.kind == BBGPU_DE_JADE ? d.cur ^ 1 : d.cur;
+        const int larch0 = *d.larch;
+        de_scan_targets(d, d.succ[fin], larch0, pre, tgt, wsum);
+        if (part == 0) {
+            // DF / CR1 / Fm, not the fitness being replaced below, feed the adaptation
+            de_adapt_block(d, fin, d.nsucc, red);
+            if (tid == 0) *d.larch_new = d.archive ? min(d.np, larch0 + wsum[32]) : 0;
+        }
+        for (int i = part * WARPS + warp; i < d.np; i += L.cpr * WARPS) de_finalize_one(d, cj, i, fin, tgt);
     }
+    if (blockIdx.x == 0 && tid == 0)
+        for (int r = 0; r < round; r++) L.nrecomp[r] = 0;
     grid.sync();
+    stamp(); // 16 finalized
 
-    int np_after = np;
-    if (d.kind == BBGPU_DE_SHADE) { // de/shade.cpp:215-235
-        de_sort_rows(d.SW, d.F, c.SWalt, c.Falt, np, n, d.ld, gw, W);
+    // ---- L-SHADE: sort, then the population shrinks from the tail (de/shade.cpp:215-225)
+    if (L.kind == BBGPU_DE_SHADE) { // every run of a launch has the same kind
+        for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+            const int run = task / L.cpr, part = task % L.cpr;
+            load_run(run);
+            de_sort_ids(d, d.cur, d.cur ^ 1, part * WARPS + warp, L.cpr * WARPS);
+        }
         grid.sync();
-        double *t = d.SW; d.SW = c.SWalt; c.SWalt = t;
-        t = d.F; d.F = c.Falt; c.Falt = t;
-        np_after = min(np, c.npnew);
-        if (gtid == 0 && d.archive) de_trim_thread(d, d.larch, c.npnew, c.trim, c.ntrim);
     }
-    for (int i = gw; i < np_after; i += W) {
-        const double *x = d.SW + (int64_t) i * d.ld;
-        double s = 0.0;
-        for (int q = lane; q < n; q += 32) s = fma(x[q], x[q], s);
-        s = warp_sum(s);
-        if (lane == 0) c.radius[i] = sqrt(s);
+    stamp(); // 17 sorted
+
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int run = task / L.cpr, part = task % L.cpr;
+        if (part != 0) continue;
+        load_run(run);
+        const int np_after = d.kind == BBGPU_DE_SHADE ? min(d.np, L.npnew) : d.np;
+        de_report_block(runs[run], d, L, d.cur ^ 1, np_after, fin, round, red);
     }
-    grid.sync();
-    if (blockIdx.x == 0) {
-        de_report_block(d, c.radius, np_after, d.larch, c.nsucc, c.rep, red);
-        if (threadIdx.x == 0) c.rep->rounds = round;
-    }
+    stamp(); // 18 end
 }
 
 __global__ void __launch_bounds__(256) de_uniform_init_kernel(DeDev d) {
@@ -547,12 +650,44 @@ __global__ void __launch_bounds__(256) de_uniform_init_kernel(DeDev d) {
     const int i = (int) (gid / d.n), j = (int) (gid % d.n);
     const Philox4 r = philox4x32_10((uint32_t) j, (uint32_t) i, 0u, (uint32_t) TAG_INIT << 24, (uint32_t) d.seed, (uint32_t) (d.seed >> 32));
     const double u = u53(r.x, r.y);
-    d.SW[(int64_t) i * d.ld + j] = u * (d.upper[j] - d.lower[j]) + d.lower[j];
+    d.POOL[(int64_t) i * d.ld + j] = u * (d.upper[j] - d.lower[j]) + d.lower[j];
 }
 
-__global__ void de_iota_kernel(int *v, int n) {
+// row ids of a fresh run: swarm rows [0, np), archive pool [np, 2np), trial buffers [2np, 4np)
+__global__ void de_init_ids_kernel(DeDev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = i;
+    if (i >= d.npcap) return;
+    d.srow[0][i] = i;
+    d.srow[1][i] = i;
+    d.arch_row[i] = d.npcap + i;
+    d.trow[0][i] = 2 * d.npcap + i;
+    d.trow[1][i] = 3 * d.npcap + i;
+}
+
+// ||x_i||_2 of the initial members (contiguous pool rows)
+__global__ void __launch_bounds__(256) de_norms_kernel(DeDev d) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= d.np) return;
+    const double *x = d.POOL + (int64_t) i * d.ld;
+    double s = 0.0;
+    for (int c = threadIdx.x & 31; c < d.n; c += 32) s = fma(x[c], x[c], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) d.R[0][i] = sqrt(s);
+}
+
+// L-SHADE sorts the initial swarm (de/shade.cpp:93): ids only, one CTA
+__global__ void __launch_bounds__(1024) de_init_sort_kernel(DeDev d) {
+    de_sort_ids(d, 0, 1, threadIdx.x >> 5, 32);
+}
+
+// members in swarm order -> contiguous staging rows (for the getters)
+__global__ void __launch_bounds__(256) de_gather_rows_kernel(const double *__restrict__ pool, const int *__restrict__ ids,
+        double *__restrict__ dst, int rows, int n, int64_t ld) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const double *s = pool + (int64_t) ids[r] * ld;
+    double *t = dst + (int64_t) r * n;
+    for (int c = threadIdx.x & 31; c < n; c += 32) t[c] = s[c];
 }
 
 } // namespace bb
@@ -565,17 +700,18 @@ struct bbgpu_de {
     int n = 0, npcap = 0, np = 0, fev = 0;
     int64_t ld = 0;
     uint64_t gen = 0;
-    int last_rounds = 6;
-    DeDev d;
-    double *SWalt = nullptr, *Falt = nullptr, *radius = nullptr, *Ubuf = nullptr, *zbuf = nullptr, *cbuf = nullptr;
-    int *perm = nullptr, *ribuf = nullptr, *trimbuf = nullptr, *larch_new = nullptr, *nsucc = nullptr, *rounds_dev = nullptr;
-    int coop_blocks = 0;
-    bool use_coop = true;
+    DeDev d;                    // host mirror of the device struct (pointers + configuration)
+    DeDev *d_dev = nullptr;     // the device-resident struct the kernel reads and advances
+    DeDev **d_self = nullptr;   // device array of one pointer: the single-run launch
+    DeDev **d_batch = nullptr;  // device array of pointers for the last batch this handle led
+    std::vector<bbgpu_de*> batch_members;
+    double *stage = nullptr, *Ubuf = nullptr, *zbuf = nullptr, *cbuf = nullptr;
+    int *trimbuf = nullptr, *nrecomp = nullptr;
     int trim_cap = 0;
-    int *h_nrecomp = nullptr; // pinned
+    unsigned long long *phase_ns = nullptr;
+    int blocks_per_sm = 0;
     bbgpu_de_report *d_rep = nullptr, *h_rep = nullptr;
     std::vector<void*> allocs;
-    int fin = 0;
 };
 
 namespace {
@@ -587,13 +723,54 @@ template<typename T> int de_alloc(bbgpu_de *h, T **p, size_t count, bool zero = 
     return BBGPU_OK;
 }
 
-int de_sort(bbgpu_de *h) {
-    bbgpu_ctx *ctx = h->ctx;
-    BB_TRY(rank_fitness(ctx, h->d.F, h->np, h->perm, h->Falt));
-    de_gather_rows_kernel<<<ceil_div(h->np, 8), 256, 0, ctx->stream>>>(h->d.SW, h->SWalt, h->perm, h->np, h->n, h->ld);
-    BB_TRY(launched(ctx, "de_gather_rows_kernel"));
-    std::swap(h->d.SW, h->SWalt);
-    std::swap(h->d.F, h->Falt);
+size_t de_smem_bytes(int np) { return (size_t) DE_GROUPS * 2 * DE_TILE * sizeof(double) + (size_t) 2 * np * sizeof(int); }
+
+// the device struct as the kernel left it (np, cur, last_fin, ...)
+int de_pull(bbgpu_de *h) {
+    BB_CUDA(cudaMemcpyAsync(&h->d, h->d_dev, sizeof(DeDev), cudaMemcpyDeviceToHost, h->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(h->ctx->stream));
+    return BBGPU_OK;
+}
+
+int de_push(bbgpu_de *h) {
+    BB_CUDA(cudaMemcpyAsync(h->d_dev, &h->d, sizeof(DeDev), cudaMemcpyHostToDevice, h->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(h->ctx->stream)); // h->d is pageable and about to change again
+    return BBGPU_OK;
+}
+
+int de_npnew(const bbgpu_de *h, int fev_after) {
+    if (h->cfg.kind != BBGPU_DE_SHADE) return h->np;
+    return (int) std::round((h->cfg.npmin - h->npcap) * ((1.0 * fev_after) / h->cfg.mfev) + h->npcap);
+}
+
+// one cooperative launch over `count` runs that share a configuration; lead = hs[0] owns the scratch
+int de_launch(bbgpu_de *const *hs, int count, bbgpu_objective *obj, DeDev **d_runs, int replay, int ntrim) {
+    bbgpu_de *lead = hs[0];
+    bbgpu_ctx *ctx = lead->ctx;
+    const int np = lead->np;
+    DeLaunch L;
+    L.nruns = count;
+    const int resident = lead->blocks_per_sm * ctx->sm_count;
+    const int want = ceil_div(np, DE_GROUPS);
+    L.cpr = std::max(1, std::min(want, resident / count));
+    L.kind = lead->cfg.kind; L.obj_id = obj->id; L.aux = obj->d_aux; L.replay = replay; L.ntrim = ntrim;
+    L.npnew = de_npnew(lead, lead->fev + np);
+    L.nrecomp = lead->nrecomp;
+    L.phase_ns = lead->phase_ns;
+    const int grid = std::min(resident, count * L.cpr);
+    const size_t smem = de_smem_bytes(np);
+    void *args[] = { (void*) &d_runs, (void*) &L };
+    {
+        ProfScope prof(ctx, BBGPU_PROF_DE_ROUND);
+        BB_CUDA(cudaLaunchCooperativeKernel((const void*) de_generation_kernel, dim3(grid), dim3(DE_CTA), args, smem, ctx->stream));
+        BB_TRY(launched(ctx, "de_generation_kernel"));
+    }
+    for (int r = 0; r < count; r++) {
+        bbgpu_de *h = hs[r];
+        h->fev += np;
+        h->gen++;
+        if (h->cfg.kind == BBGPU_DE_SHADE && L.npnew < h->np) h->np = L.npnew;
+    }
     return BBGPU_OK;
 }
 
@@ -607,6 +784,9 @@ int bbgpu_de_create(bbgpu_ctx *ctx, const bbgpu_de_config *cfg, const double *h_
     BB_ARG(cfg->kind == BBGPU_DE_JADE || cfg->kind == BBGPU_DE_SHADE);
     BB_ARG(cfg->kind == BBGPU_DE_JADE || (cfg->h >= 1 && cfg->npmin >= 4 && cfg->mfev > 0));
     BB_CUDA(cudaSetDevice(ctx->device));
+    int supported = 0;
+    cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (!supported) return fail(BBGPU_ERR_NODEVICE, "the DE engine needs cooperative kernel launch");
     bbgpu_de *h = new bbgpu_de();
     h->ctx = ctx;
     h->cfg = *cfg;
@@ -617,48 +797,40 @@ int bbgpu_de_create(bbgpu_ctx *ctx, const bbgpu_de_config *cfg, const double *h_
     const int hh = std::max(1, cfg->h);
     DeDev &d = h->d;
     memset(&d, 0, sizeof(d));
-    d.kind = cfg->kind; d.n = cfg->n; d.np = h->np; d.npA = h->np; d.h = hh; d.archive = cfg->archive; d.repaircr = cfg->repaircr;
-    d.ld = h->ld; d.seed = cfg->seed; d.pelite = cfg->pelite;
+    d.kind = cfg->kind; d.n = cfg->n; d.npcap = h->npcap; d.np = h->np; d.h = hh; d.archive = cfg->archive; d.repaircr = cfg->repaircr;
+    d.npmin = cfg->npmin; d.mfev = cfg->mfev;
+    d.ld = h->ld; d.seed = cfg->seed; d.pelite = cfg->pelite; d.cdamp = cfg->cdamp; d.sigma_cr = cfg->sigma;
     int rc = BBGPU_OK;
     double *lo = nullptr, *hi = nullptr;
 #define DA(ptr, count) if (rc == BBGPU_OK) rc = de_alloc(h, &(ptr), (size_t) (count))
     DA(lo, ld); DA(hi, ld);
-    DA(d.SW, rows * ld); DA(h->SWalt, rows * ld); DA(d.F, rows); DA(h->Falt, rows); DA(d.ARCH, rows * ld);
-    DA(d.TR[0], rows * ld); DA(d.TR[1], rows * ld); DA(d.FT, rows); DA(d.CR, rows); DA(d.Fm, rows); DA(d.CR1, rows);
-    DA(d.MCR, hh); DA(d.MF, hh); DA(d.mu, 2); DA(h->radius, rows);
-    DA(d.ibest, rows); DA(d.r1, rows); DA(d.r2, rows); DA(d.jrand, rows); DA(d.slot, rows); DA(d.ri, rows); DA(d.arch_row, rows);
-    DA(d.larch, 1); DA(h->larch_new, 1); DA(h->nsucc, 1); DA(d.kslot, 1); DA(h->rounds_dev, 1);
+    DA(d.POOL, 4 * rows * ld); DA(h->stage, rows * (size_t) h->n);
+    DA(d.srow[0], rows); DA(d.srow[1], rows); DA(d.trow[0], rows); DA(d.trow[1], rows); DA(d.arch_row, rows);
+    DA(d.F[0], rows); DA(d.F[1], rows); DA(d.R[0], rows); DA(d.R[1], rows);
+    DA(d.FT, rows); DA(d.RT, rows); DA(d.DF, rows); DA(d.CR, rows); DA(d.Fm, rows); DA(d.CR1, rows);
+    DA(d.MCR, hh); DA(d.MF, hh); DA(d.mu, 2);
+    DA(d.ibest, rows); DA(d.r1, rows); DA(d.r2, rows); DA(d.jrand, rows); DA(d.slot, rows); DA(d.ri, rows);
+    DA(d.larch, 1); DA(d.larch_new, 1); DA(d.nsucc, 1); DA(d.kslot, 1); DA(h->phase_ns, 32);
     DA(d.succ[0], rows); DA(d.succ[1], rows); DA(d.ver[0], rows); DA(d.ver[1], rows); DA(d.trbuf[0], rows); DA(d.trbuf[1], rows);
-    DA(d.sig, rows * 4); DA(d.nrecomp, DE_MAX_ROUNDS); DA(h->perm, rows);
-    DA(h->zbuf, rows); DA(h->cbuf, rows); DA(h->ribuf, rows);
-    DA(h->d_rep, 1);
+    DA(d.sig, rows * 4); DA(h->nrecomp, DE_MAX_ROUNDS);
+    DA(h->zbuf, rows); DA(h->cbuf, rows);
+    DA(h->d_rep, 1); DA(h->d_dev, 1); DA(h->d_self, 1);
 #undef DA
     if (rc == BBGPU_OK && cudaMallocHost((void**) &h->h_rep, sizeof(bbgpu_de_report)) != cudaSuccess) rc = fail(BBGPU_ERR_CUDA, "pinned alloc failed");
-    if (rc == BBGPU_OK && cudaMallocHost((void**) &h->h_nrecomp, DE_MAX_ROUNDS * sizeof(int)) != cudaSuccess) rc = fail(BBGPU_ERR_CUDA, "pinned alloc failed");
     if (rc != BBGPU_OK) { bbgpu_de_destroy(h); return rc; }
-    d.lower = lo; d.upper = hi;
+    d.lower = lo; d.upper = hi; d.rep = h->d_rep;
+    d.zcr = h->zbuf; d.cauchy = h->cbuf;
     cudaStream_t st = ctx->stream;
     cudaMemcpyAsync(lo, h_lower, (size_t) h->n * 8, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(hi, h_upper, (size_t) h->n * 8, cudaMemcpyHostToDevice, st);
-    std::vector<double> half(std::max(hh, 2), 0.5);
-    cudaMemcpyAsync(d.MCR, half.data(), (size_t) hh * 8, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d.MF, half.data(), (size_t) hh * 8, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d.mu, half.data(), 16, cudaMemcpyHostToDevice, st);
-    const int one = 1;
-    cudaMemcpyAsync(d.kslot, &one, 4, cudaMemcpyHostToDevice, st);
-    de_iota_kernel<<<ceil_div(h->npcap, 256), 256, 0, st>>>(d.arch_row, h->npcap);
-    rc = launched(ctx, "de_iota_kernel");
+    cudaMemcpyAsync(h->d_self, &h->d_dev, sizeof(DeDev*), cudaMemcpyHostToDevice, st);
     {
         // cooperative launch geometry: all CTAs must be co-resident
-        const char *e = std::getenv("BBGPU_DE_COOP");
-        h->use_coop = e ? std::atoi(e) != 0 : true;
-        const size_t smem = ((size_t) 2 * h->npcap + 16) * sizeof(int);
-        int supported = 0, per_sm = 0;
-        cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, ctx->device);
-        if (smem > 48 * 1024) cudaFuncSetAttribute(de_generation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, de_generation_kernel, 256, smem);
-        h->coop_blocks = std::min(ceil_div(h->npcap, 8), per_sm * ctx->sm_count);
-        if (!supported || h->coop_blocks < 1) h->use_coop = false;
+        const size_t smem = de_smem_bytes(h->npcap);
+        if (smem > 48 * 1024 && cudaFuncSetAttribute(de_generation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
+            rc = fail(BBGPU_ERR_ARG, "np = %d needs %zu bytes of shared memory per CTA", h->npcap, smem);
+        if (rc == BBGPU_OK) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, de_generation_kernel, DE_CTA, smem);
+        if (rc == BBGPU_OK && h->blocks_per_sm < 1) rc = fail(BBGPU_ERR_ARG, "the DE generation kernel does not fit on an SM at np = %d", h->npcap);
     }
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == BBGPU_OK) rc = fail(BBGPU_ERR_CUDA, "de create sync failed");
     if (rc != BBGPU_OK) { bbgpu_de_destroy(h); return rc; }
@@ -672,8 +844,8 @@ int bbgpu_de_destroy(bbgpu_de *h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->Ubuf) cudaFree(h->Ubuf);
     if (h->trimbuf) cudaFree(h->trimbuf);
+    if (h->d_batch) cudaFree(h->d_batch);
     if (h->h_rep) cudaFreeHost(h->h_rep);
-    if (h->h_nrecomp) cudaFreeHost(h->h_nrecomp);
     delete h;
     return BBGPU_OK;
 }
@@ -684,7 +856,8 @@ int bbgpu_de_init(bbgpu_de *h, bbgpu_objective *obj, const double *h_x) {
     cudaStream_t st = ctx->stream;
     DeDev &d = h->d;
     h->np = h->npcap;
-    d.np = d.npA = h->np;
+    d.np = h->np;
+    d.fev = 0; d.gen = 0; d.cur = 0; d.last_fin = 0; d.last_rounds = 0; d.last_np = h->np;
     h->fev = 0;
     h->gen = 0;
     const int hh = d.h;
@@ -695,17 +868,27 @@ int bbgpu_de_init(bbgpu_de *h, bbgpu_objective *obj, const double *h_x) {
     const int one = 1;
     BB_CUDA(cudaMemcpyAsync(d.kslot, &one, 4, cudaMemcpyHostToDevice, st));
     BB_CUDA(cudaMemsetAsync(d.larch, 0, 4, st));
+    BB_CUDA(cudaMemsetAsync(h->nrecomp, 0, DE_MAX_ROUNDS * sizeof(int), st));
     BB_CUDA(cudaStreamSynchronize(st)); // `half` / `one` are stack temporaries
+    de_init_ids_kernel<<<ceil_div(h->npcap, 256), 256, 0, st>>>(d);
+    BB_TRY(launched(ctx, "de_init_ids_kernel"));
     if (h_x) {
-        BB_CUDA(cudaMemcpy2DAsync(d.SW, (size_t) h->ld * 8, h_x, (size_t) h->n * 8, (size_t) h->n * 8, h->np, cudaMemcpyHostToDevice, st));
+        BB_CUDA(cudaMemcpy2DAsync(d.POOL, (size_t) h->ld * 8, h_x, (size_t) h->n * 8, (size_t) h->n * 8, h->np, cudaMemcpyHostToDevice, st));
     } else {
         de_uniform_init_kernel<<<ceil_div((int64_t) h->np * h->n, 256), 256, 0, st>>>(d);
         BB_TRY(launched(ctx, "de_uniform_init_kernel"));
     }
-    BB_TRY(evaluate(ctx, obj, d.SW, h->ld, h->np, d.F));
+    BB_TRY(evaluate(ctx, obj, d.POOL, h->ld, h->np, d.F[0]));
+    de_norms_kernel<<<ceil_div(h->np, 8), 256, 0, st>>>(d);
+    BB_TRY(launched(ctx, "de_norms_kernel"));
     h->fev += h->np;
-    if (h->cfg.kind == BBGPU_DE_SHADE) BB_TRY(de_sort(h)); // de/shade.cpp:93
-    BB_CUDA(cudaStreamSynchronize(st));
+    d.fev = h->fev;
+    if (h->cfg.kind == BBGPU_DE_SHADE) { // de/shade.cpp:93
+        de_init_sort_kernel<<<1, 1024, 0, st>>>(d);
+        BB_TRY(launched(ctx, "de_init_sort_kernel"));
+        d.cur = 1;
+    }
+    BB_TRY(de_push(h));
     return BBGPU_OK;
 }
 
@@ -716,13 +899,30 @@ int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws 
     cudaStream_t st = ctx->stream;
     DeDev &d = h->d;
     const int np = h->np, n = h->n;
-    d.np = np; d.npA = np; d.gen = h->gen; d.obj_id = obj->id; d.aux = obj->d_aux;
-    d.replay = draws != nullptr;
-    if (h->cfg.kind == BBGPU_DE_JADE && !h->use_coop) BB_TRY(de_sort(h)); // de/jade.cpp:101 (the cooperative kernel sorts itself)
     if (draws) {
         BB_ARG(draws->zcr && draws->cauchy && draws->ibest && draws->r1 && draws->r2 && draws->jrand && draws->slot && draws->u);
         BB_ARG(h->cfg.kind == BBGPU_DE_JADE || draws->ri);
-        if (!h->Ubuf) BB_TRY(dev_alloc(&h->Ubuf, (size_t) h->npcap * n));
+        bool repush = false;
+        if (!h->Ubuf) {
+            BB_TRY(dev_alloc(&h->Ubuf, (size_t) h->npcap * n));
+            d.U = h->Ubuf;
+            repush = true;
+        }
+        if (draws->ntrim > h->trim_cap) {
+            if (h->trimbuf) cudaFree(h->trimbuf);
+            BB_TRY(dev_alloc(&h->trimbuf, (size_t) draws->ntrim));
+            h->trim_cap = draws->ntrim;
+            d.trim = h->trimbuf;
+            repush = true;
+        }
+        if (repush) { // only the replay pointers changed; keep the scalars the kernel advanced
+            DeDev live;
+            BB_CUDA(cudaMemcpyAsync(&live, h->d_dev, sizeof(DeDev), cudaMemcpyDeviceToHost, st));
+            BB_CUDA(cudaStreamSynchronize(st));
+            live.U = d.U; live.trim = d.trim;
+            d = live;
+            BB_TRY(de_push(h));
+        }
         BB_CUDA(cudaMemcpyAsync(h->zbuf, draws->zcr, (size_t) np * 8, cudaMemcpyHostToDevice, st));
         BB_CUDA(cudaMemcpyAsync(h->cbuf, draws->cauchy, (size_t) np * 8, cudaMemcpyHostToDevice, st));
         BB_CUDA(cudaMemcpyAsync(d.ibest, draws->ibest, (size_t) np * 4, cudaMemcpyHostToDevice, st));
@@ -734,102 +934,48 @@ int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws 
         if (draws->ri) BB_CUDA(cudaMemcpyAsync(d.ri, draws->ri, (size_t) np * 4, cudaMemcpyHostToDevice, st));
         if (draws->ntrim > 0) {
             BB_ARG(draws->trim);
-            if (draws->ntrim > h->trim_cap) {
-                if (h->trimbuf) cudaFree(h->trimbuf);
-                BB_TRY(dev_alloc(&h->trimbuf, (size_t) draws->ntrim));
-                h->trim_cap = draws->ntrim;
-            }
             BB_CUDA(cudaMemcpyAsync(h->trimbuf, draws->trim, (size_t) draws->ntrim * 4, cudaMemcpyHostToDevice, st));
         }
-        d.zcr = h->zbuf; d.cauchy = h->cbuf; d.U = h->Ubuf;
     }
-    if (h->use_coop) {
-        // ---- single cooperative launch per generation
-        DeCoop c;
-        c.SWalt = h->SWalt; c.Falt = h->Falt; c.radius = h->radius; c.nsucc = h->nsucc; c.rounds_out = h->rounds_dev;
-        c.rep = h->d_rep; c.cdamp = h->cfg.cdamp; c.sigma_cr = h->cfg.sigma;
-        c.trim = h->trimbuf; c.ntrim = draws ? draws->ntrim : 0;
-        const int fev_after = h->fev + np;
-        c.npnew = h->cfg.kind == BBGPU_DE_SHADE
-                ? (int) std::round((h->cfg.npmin - h->npcap) * ((1.0 * fev_after) / h->cfg.mfev) + h->npcap) : np;
-        const size_t smem = ((size_t) 2 * np + 16) * sizeof(int);
-        void *args[] = { (void*) &d, (void*) &c };
-        {
-            ProfScope prof(ctx, BBGPU_PROF_DE_ROUND);
-            BB_CUDA(cudaLaunchCooperativeKernel((const void*) de_generation_kernel, dim3(h->coop_blocks), dim3(256), args, smem, st));
-            BB_TRY(launched(ctx, "de_generation_kernel"));
-        }
-        // the kernel sorted once (JADE: at the start, L-SHADE: at the end): the live buffers swapped
-        std::swap(h->d.SW, h->SWalt);
-        std::swap(h->d.F, h->Falt);
-        h->fev = fev_after;
-        h->gen++;
-        if (h->cfg.kind == BBGPU_DE_SHADE && c.npnew < h->np) h->np = c.npnew;
-        h->fin = -1; // resolved from rounds_dev on demand
-        if (out) {
-            BB_CUDA(cudaMemcpyAsync(h->h_rep, h->d_rep, sizeof(bbgpu_de_report), cudaMemcpyDeviceToHost, st));
-            BB_CUDA(cudaStreamSynchronize(st));
-            *out = *h->h_rep;
-            out->fev = h->fev;
-        }
-        return BBGPU_OK;
-    }
-    BB_CUDA(cudaMemsetAsync(d.nrecomp, 0, DE_MAX_ROUNDS * sizeof(int), st));
-    de_params_kernel<<<ceil_div(np, 256), 256, 0, st>>>(d);
-    BB_TRY(launched(ctx, "de_params_kernel"));
-    const size_t smem = ((size_t) 2 * np + 257 + 8) * sizeof(int);
-    if (smem > 48 * 1024) {
-        BB_CUDA(cudaFuncSetAttribute(de_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        BB_CUDA(cudaFuncSetAttribute(de_archive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    }
-    // resolution rounds, launched in batches; a round that rebuilt nothing is the fixed point
-    int round = 0, done_round = -1;
-    int batch = std::max(2, h->last_rounds + 1);
-    while (done_round < 0) {
-        const int first = round;
-        for (int b = 0; b < batch && round < DE_MAX_ROUNDS; b++, round++) {
-            ProfScope prof(ctx, BBGPU_PROF_DE_ROUND);
-            de_round_kernel<<<ceil_div(np, 8), 256, smem, st>>>(d, round);
-            BB_TRY(launched(ctx, "de_round_kernel"));
-        }
-        BB_CUDA(cudaMemcpyAsync(h->h_nrecomp + first, d.nrecomp + first, (size_t) (round - first) * sizeof(int), cudaMemcpyDeviceToHost, st));
-        BB_CUDA(cudaStreamSynchronize(st));
-        for (int r = first; r < round; r++)
-            if (h->h_nrecomp[r] == 0) { done_round = r; break; }
-        if (done_round < 0 && round >= DE_MAX_ROUNDS) return fail(BBGPU_ERR_ARG, "DE dependency resolution did not converge");
-        batch = 2;
-    }
-    h->last_rounds = done_round;
-    const int fin = round & 1; // buffers written by the last launched round (identical past the fixed point)
-    h->fin = fin;
-    de_archive_kernel<<<ceil_div(np, 8), 256, smem, st>>>(d, fin, h->larch_new);
-    BB_TRY(launched(ctx, "de_archive_kernel"));
-    de_adapt_kernel<<<1, 1024, 0, st>>>(d, fin, h->cfg.cdamp, h->cfg.sigma, h->nsucc);
-    BB_TRY(launched(ctx, "de_adapt_kernel"));
-    de_replace_kernel<<<ceil_div(np, 8), 256, 0, st>>>(d, fin);
-    BB_TRY(launched(ctx, "de_replace_kernel"));
-    BB_CUDA(cudaMemcpyAsync(d.larch, h->larch_new, 4, cudaMemcpyDeviceToDevice, st));
-    h->fev += np;
-    h->gen++;
-    if (h->cfg.kind == BBGPU_DE_SHADE) {
-        BB_TRY(de_sort(h)); // de/shade.cpp:215
-        const int npnew = (int) std::round((h->cfg.npmin - h->npcap) * ((1.0 * h->fev) / h->cfg.mfev) + h->npcap);
-        if (npnew < h->np) h->np = npnew; // pop_back on the sorted swarm (de/shade.cpp:218-225)
-        if (h->cfg.archive) {
-            de_trim_kernel<<<1, 32, 0, st>>>(d, d.larch, npnew, h->trimbuf, draws ? draws->ntrim : 0);
-            BB_TRY(launched(ctx, "de_trim_kernel"));
-        }
-    }
-    de_norms_kernel<<<ceil_div(h->np, 8), 256, 0, st>>>(d.SW, h->np, n, h->ld, h->radius);
-    BB_TRY(launched(ctx, "de_norms_kernel"));
-    de_report_kernel<<<1, 1024, 0, st>>>(d, h->radius, h->np, d.larch, h->nsucc, h->d_rep);
-    BB_TRY(launched(ctx, "de_report_kernel"));
+    bbgpu_de *one[1] = { h };
+    BB_TRY(de_launch(one, 1, obj, h->d_self, draws != nullptr, draws ? draws->ntrim : 0));
     if (out) {
         BB_CUDA(cudaMemcpyAsync(h->h_rep, h->d_rep, sizeof(bbgpu_de_report), cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaStreamSynchronize(st));
         *out = *h->h_rep;
-        out->fev = h->fev;
-        out->rounds = done_round + 1;
+    }
+    return BBGPU_OK;
+}
+
+// One generation of `count` independent runs (same configuration, their own seeds and state) in ONE
+// cooperative launch: the rows of all runs stream through the same kernel, so the chip is filled even
+// when a single run's dependency rounds are latency bound.  Each run's result is bit-identical to
+// bbgpu_de_generation on that handle.
+int bbgpu_de_generation_batch(bbgpu_de *const *hs, int count, bbgpu_objective *obj, bbgpu_de_report *out) {
+    BB_ARG(hs && count >= 1 && obj);
+    if (obj->mode != 0) return fail(BBGPU_ERR_ARG, "the fused DE generation needs a registry objective");
+    bbgpu_de *lead = hs[0];
+    BB_ARG(lead && obj->n == lead->n);
+    for (int r = 1; r < count; r++) {
+        const bbgpu_de *h = hs[r];
+        BB_ARG(h && h->ctx == lead->ctx && h->n == lead->n && h->np == lead->np && h->npcap == lead->npcap && h->fev == lead->fev);
+        BB_ARG(h->cfg.kind == lead->cfg.kind && h->cfg.mfev == lead->cfg.mfev && h->cfg.npmin == lead->cfg.npmin);
+    }
+    cudaStream_t st = lead->ctx->stream;
+    if ((int) lead->batch_members.size() != count || !std::equal(hs, hs + count, lead->batch_members.begin())) {
+        std::vector<DeDev*> ptrs((size_t) count);
+        for (int r = 0; r < count; r++) ptrs[r] = hs[r]->d_dev;
+        BB_CUDA(cudaStreamSynchronize(st));
+        if (lead->d_batch) cudaFree(lead->d_batch);
+        BB_TRY(dev_alloc(&lead->d_batch, (size_t) count));
+        BB_CUDA(cudaMemcpy(lead->d_batch, ptrs.data(), (size_t) count * sizeof(DeDev*), cudaMemcpyHostToDevice));
+        lead->batch_members.assign(hs, hs + count);
+    }
+    BB_TRY(de_launch(hs, count, obj, lead->d_batch, 0, 0));
+    if (out) {
+        for (int r = 0; r < count; r++)
+            BB_CUDA(cudaMemcpyAsync(out + r, hs[r]->d_rep, sizeof(bbgpu_de_report), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaStreamSynchronize(st));
     }
     return BBGPU_OK;
 }
@@ -837,8 +983,14 @@ int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws 
 int bbgpu_de_get_swarm(bbgpu_de *h, double *h_x, double *h_f) {
     BB_ARG(h);
     cudaStream_t st = h->ctx->stream;
-    if (h_x) BB_CUDA(cudaMemcpy2DAsync(h_x, (size_t) h->n * 8, h->d.SW, (size_t) h->ld * 8, (size_t) h->n * 8, h->np, cudaMemcpyDeviceToHost, st));
-    if (h_f) BB_CUDA(cudaMemcpyAsync(h_f, h->d.F, (size_t) h->np * 8, cudaMemcpyDeviceToHost, st));
+    BB_TRY(de_pull(h));
+    const DeDev &d = h->d;
+    if (h_x) {
+        de_gather_rows_kernel<<<ceil_div(d.np, 8), 256, 0, st>>>(d.POOL, d.srow[d.cur], h->stage, d.np, h->n, h->ld);
+        BB_TRY(launched(h->ctx, "de_gather_rows_kernel"));
+        BB_CUDA(cudaMemcpyAsync(h_x, h->stage, (size_t) d.np * h->n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_f) BB_CUDA(cudaMemcpyAsync(h_f, d.F[d.cur], (size_t) d.np * 8, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
     return BBGPU_OK;
 }
@@ -848,13 +1000,12 @@ int bbgpu_de_get_archive(bbgpu_de *h, double *h_arch, int *rows) {
     cudaStream_t st = h->ctx->stream;
     int larch = 0;
     BB_CUDA(cudaMemcpyAsync(&larch, h->d.larch, 4, cudaMemcpyDeviceToHost, st));
-    std::vector<int> rowmap((size_t) h->npcap);
-    BB_CUDA(cudaMemcpyAsync(rowmap.data(), h->d.arch_row, (size_t) h->npcap * 4, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
     *rows = larch;
-    if (h_arch) {
-        for (int a = 0; a < larch; a++)
-            BB_CUDA(cudaMemcpyAsync(h_arch + (size_t) a * h->n, h->d.ARCH + (size_t) rowmap[a] * h->ld, (size_t) h->n * 8, cudaMemcpyDeviceToHost, st));
+    if (h_arch && larch > 0) {
+        de_gather_rows_kernel<<<ceil_div(larch, 8), 256, 0, st>>>(h->d.POOL, h->d.arch_row, h->stage, larch, h->n, h->ld);
+        BB_TRY(launched(h->ctx, "de_gather_rows_kernel"));
+        BB_CUDA(cudaMemcpyAsync(h_arch, h->stage, (size_t) larch * h->n * 8, cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaStreamSynchronize(st));
     }
     return BBGPU_OK;
@@ -869,21 +1020,26 @@ int bbgpu_de_get_memory(bbgpu_de *h, double *h_mcr, double *h_mf) {
     return BBGPU_OK;
 }
 
-// per-candidate outcome of the generation just run, in the pre-sort candidate order
+// diagnostics: %globaltimer stamps (ns) of the last generation launch this handle led
+// [0] start [1] sorted + parameters [2..13] rounds [16] finalized [17] L-SHADE sort [18] end
+int bbgpu_de_phase_times(bbgpu_de *h, uint64_t *out32) {
+    BB_ARG(h && out32);
+    BB_CUDA(cudaMemcpyAsync(out32, h->phase_ns, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(h->ctx->stream));
+    return BBGPU_OK;
+}
+
+// per-candidate outcome of the generation just run, in the candidate order of that generation
 int bbgpu_de_get_trace(bbgpu_de *h, int32_t *h_succ, double *h_ftrial, double *h_F, double *h_CR) {
     BB_ARG(h);
     cudaStream_t st = h->ctx->stream;
-    const int np = h->d.np;
-    if (h->fin < 0) {
-        int rounds = 0;
-        BB_CUDA(cudaMemcpyAsync(&rounds, h->rounds_dev, 4, cudaMemcpyDeviceToHost, st));
-        BB_CUDA(cudaStreamSynchronize(st));
-        h->fin = rounds & 1;
-    }
-    if (h_succ) BB_CUDA(cudaMemcpyAsync(h_succ, h->d.succ[h->fin], (size_t) np * 4, cudaMemcpyDeviceToHost, st));
-    if (h_ftrial) BB_CUDA(cudaMemcpyAsync(h_ftrial, h->d.FT, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
-    if (h_F) BB_CUDA(cudaMemcpyAsync(h_F, h->d.Fm, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
-    if (h_CR) BB_CUDA(cudaMemcpyAsync(h_CR, h->d.CR, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
+    BB_TRY(de_pull(h));
+    const DeDev &d = h->d;
+    const int np = d.last_np, fin = d.last_fin;
+    if (h_succ) BB_CUDA(cudaMemcpyAsync(h_succ, d.succ[fin], (size_t) np * 4, cudaMemcpyDeviceToHost, st));
+    if (h_ftrial) BB_CUDA(cudaMemcpyAsync(h_ftrial, d.FT, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
+    if (h_F) BB_CUDA(cudaMemcpyAsync(h_F, d.Fm, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
+    if (h_CR) BB_CUDA(cudaMemcpyAsync(h_CR, d.CR, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
     return BBGPU_OK;
 }

@@ -60,7 +60,7 @@ int bbgpu_objective_builtin(bbgpu_ctx *ctx, int id, int n, bbgpu_objective **out
         // expression the oracle uses, so both sides read identical coefficients
         std::vector<double> coef(n);
         for (int i = 0; i < n; i++) coef[i] = (n > 1) ? std::pow(10.0, 6.0 * (double) i / ((double) n - 1.0)) : 1.0;
-        int s = bb::dev_alloc(&o->d_aux, (size_t) n);
+        int s = bb::dev_alloc(&o->d_aux, (size_t) bb::round_up(n, 8)); // padded like the rows: 32-byte vector reads
         if (s != BBGPU_OK) { delete o; return s; }
         cudaError_t e = cudaMemcpy(o->d_aux, coef.data(), (size_t) n * 8, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { cudaFree(o->d_aux); delete o; return bb::fail(BBGPU_ERR_CUDA, "memcpy coef: %s", cudaGetErrorString(e)); }

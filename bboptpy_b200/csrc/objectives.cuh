@@ -27,36 +27,22 @@ __device__ __forceinline__ double cos2pi(double x) {
     double a = fabs(r);
     bool neg = false;
     if (a > 0.25) { a = sub(0.5, a); neg = true; }
-    double v;
-    if (a > 0.125) {
-        const double t = mul(sub(0.25, a), 6.283185307179586);
-        const double u = mul(t, t);
-        double s = -8.22063524662433e-18;
-        s = add(mul(s, u), 2.8114572543455206e-15);
-        s = add(mul(s, u), -7.647163731819816e-13);
-        s = add(mul(s, u), 1.6059043836821613e-10);
-        s = add(mul(s, u), -2.505210838544172e-08);
-        s = add(mul(s, u), 2.7557319223985893e-06);
-        s = add(mul(s, u), -0.0001984126984126984);
-        s = add(mul(s, u), 0.008333333333333333);
-        s = add(mul(s, u), -0.16666666666666666);
-        s = add(mul(s, u), 1.0);
-        v = mul(s, t);
-    } else {
-        const double t = mul(a, 6.283185307179586);
-        const double u = mul(t, t);
-        double c = -1.5619206968586225e-16;
-        c = add(mul(c, u), 4.779477332387385e-14);
-        c = add(mul(c, u), -1.1470745597729725e-11);
-        c = add(mul(c, u), 2.08767569878681e-09);
-        c = add(mul(c, u), -2.755731922398589e-07);
-        c = add(mul(c, u), 2.48015873015873e-05);
-        c = add(mul(c, u), -0.001388888888888889);
-        c = add(mul(c, u), 0.041666666666666664);
-        c = add(mul(c, u), -0.5);
-        c = add(mul(c, u), 1.0);
-        v = c;
-    }
+    // the sine branch (a > 1/8) and the cosine branch share one Horner recurrence: only the
+    // coefficients and the final multiply differ, so lanes never diverge (same bits as two branches)
+    const bool big = a > 0.125;
+    const double t = mul(big ? sub(0.25, a) : a, 6.283185307179586);
+    const double u = mul(t, t);
+    double p = big ? -8.22063524662433e-18 : -1.5619206968586225e-16;
+    p = add(mul(p, u), big ? 2.8114572543455206e-15 : 4.779477332387385e-14);
+    p = add(mul(p, u), big ? -7.647163731819816e-13 : -1.1470745597729725e-11);
+    p = add(mul(p, u), big ? 1.6059043836821613e-10 : 2.08767569878681e-09);
+    p = add(mul(p, u), big ? -2.505210838544172e-08 : -2.755731922398589e-07);
+    p = add(mul(p, u), big ? 2.7557319223985893e-06 : 2.48015873015873e-05);
+    p = add(mul(p, u), big ? -0.0001984126984126984 : -0.001388888888888889);
+    p = add(mul(p, u), big ? 0.008333333333333333 : 0.041666666666666664);
+    p = add(mul(p, u), big ? -0.16666666666666666 : -0.5);
+    p = add(mul(p, u), 1.0);
+    const double v = big ? mul(p, t) : p;
     return neg ? -v : v;
 }
 
@@ -86,58 +72,81 @@ __device__ __forceinline__ double exp_poly(double x) {
     return mul(p, two_k);
 }
 
-// Per-lane partial of the objective sum over a candidate row held in global or shared memory.
-// All 32 lanes of the warp call this with the same (id, n, x); returns the full objective value
-// in every lane.  `aux` = ellipsoid coefficient table (device, length n) or nullptr.
-template<typename Ptr>
-__device__ __forceinline__ double warp_objective(int id, int n, Ptr x, const double *__restrict__ aux) {
-    const int lane = threadIdx.x & 31;
-    double acc = 0.0;
+// term(i) of the objective sum (spec: DESIGN.md "Objective spec").  `xn` = x[i+1] (only Rosenbrock reads
+// it).  Objectives with two sums (Ackley) return the second term through t2.  Sums run over i in
+// [0, obj_terms(id, n)).
+__device__ __forceinline__ int obj_term_count(int id, int n) { return id == BBGPU_OBJ_ROSENBROCK ? n - 1 : n; }
+
+__device__ __forceinline__ double obj_term(int id, double v, double xn, double auxi, double &t2) {
     switch (id) {
     case BBGPU_OBJ_SPHERE:
-        for (int i = lane; i < n; i += 32) {
-            const double v = x[i];
-            acc = add(acc, mul(v, v));
-        }
-        return warp_sum(acc);
+        return mul(v, v);
     case BBGPU_OBJ_ELLIPSOID:
-        for (int i = lane; i < n; i += 32) {
-            const double v = x[i];
-            acc = add(acc, mul(aux[i], mul(v, v)));
-        }
-        return warp_sum(acc);
-    case BBGPU_OBJ_ROSENBROCK:
-        for (int i = lane; i + 1 < n; i += 32) {
-            const double v = x[i], w = x[i + 1];
-            const double t1 = sub(w, mul(v, v));
-            const double t2 = sub(1.0, v);
-            acc = add(acc, add(mul(100.0, mul(t1, t1)), mul(t2, t2)));
-        }
-        return warp_sum(acc);
-    case BBGPU_OBJ_RASTRIGIN: {
-        for (int i = lane; i < n; i += 32) {
-            const double v = x[i];
-            acc = add(acc, sub(mul(v, v), mul(10.0, cos2pi(v))));
-        }
-        const double s = warp_sum(acc);
-        return add(mul(10.0, (double) n), s);
+        return mul(auxi, mul(v, v));
+    case BBGPU_OBJ_ROSENBROCK: {
+        const double t1 = sub(xn, mul(v, v));
+        const double tt = sub(1.0, v);
+        return add(mul(100.0, mul(t1, t1)), mul(tt, tt));
     }
+    case BBGPU_OBJ_RASTRIGIN:
+        return sub(mul(v, v), mul(10.0, cos2pi(v)));
+    case BBGPU_OBJ_ACKLEY:
+        t2 = cos2pi(v);
+        return mul(v, v);
+    default:
+        return nan("");
+    }
+}
+
+// objective value from the reduced sum(s)
+__device__ __forceinline__ double obj_finish(int id, int n, double s1, double s2) {
+    switch (id) {
+    case BBGPU_OBJ_RASTRIGIN:
+        return add(mul(10.0, (double) n), s1);
     case BBGPU_OBJ_ACKLEY: {
-        double acc2 = 0.0;
-        for (int i = lane; i < n; i += 32) {
-            const double v = x[i];
-            acc = add(acc, mul(v, v));
-            acc2 = add(acc2, cos2pi(v));
-        }
-        const double s1 = warp_sum(acc);
-        const double s2 = warp_sum(acc2);
         const double t1 = mul(20.0, exp_poly(mul(-0.2, sqrt(__ddiv_rn(s1, (double) n)))));
         const double t2 = exp_poly(__ddiv_rn(s2, (double) n));
         return add(sub(20.0, t1), sub(2.718281828459045, t2));
     }
     default:
-        return nan("");
+        return s1;
     }
+}
+
+// One warp evaluates one candidate row (global or shared memory): lane l accumulates term(i) for
+// i = l, l+32, ... in ascending order, then the xor butterfly.  All 32 lanes return the value.
+// `aux` = ellipsoid coefficient table (device, length n) or nullptr.
+template<typename Ptr>
+__device__ __forceinline__ double warp_objective(int id, int n, Ptr x, const double *__restrict__ aux) {
+    const int lane = threadIdx.x & 31;
+    const int nt = obj_term_count(id, n);
+    double acc = 0.0, acc2 = 0.0;
+    for (int i = lane; i < nt; i += 32) {
+        const double v = x[i];
+        const double xn = id == BBGPU_OBJ_ROSENBROCK ? x[i + 1] : 0.0;
+        const double a = id == BBGPU_OBJ_ELLIPSOID ? aux[i] : 0.0;
+        double t2 = 0.0;
+        acc = add(acc, obj_term(id, v, xn, a, t2));
+        if (id == BBGPU_OBJ_ACKLEY) acc2 = add(acc2, t2);
+    }
+    const double s1 = warp_sum(acc);
+    const double s2 = id == BBGPU_OBJ_ACKLEY ? warp_sum(acc2) : 0.0;
+    return obj_finish(id, n, s1, s2);
+}
+
+// The same value from per-term buffers in shared memory (terms computed by a whole CTA in parallel):
+// called by ONE warp; t1/t2 hold term(i) for i < obj_term_count.  Same accumulation order as above.
+__device__ __forceinline__ double warp_reduce_terms(int id, int n, const double *t1, const double *t2) {
+    const int lane = threadIdx.x & 31;
+    const int nt = obj_term_count(id, n);
+    double acc = 0.0, acc2 = 0.0;
+    for (int i = lane; i < nt; i += 32) {
+        acc = add(acc, t1[i]);
+        if (id == BBGPU_OBJ_ACKLEY) acc2 = add(acc2, t2[i]);
+    }
+    const double s1 = warp_sum(acc);
+    const double s2 = id == BBGPU_OBJ_ACKLEY ? warp_sum(acc2) : 0.0;
+    return obj_finish(id, n, s1, s2);
 }
 
 } // namespace bb

@@ -281,12 +281,20 @@ int bbgpu_de_init(bbgpu_de *h, bbgpu_objective *obj, const double *h_x);
  * draws == NULL -> Philox. */
 int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws *draws,
                         bbgpu_de_report *out);
+/* One generation of `count` independent runs in ONE launch: same configuration (kind, n, np, budget),
+ * their own seeds and state; Philox draws only.  Every run's result is bit-identical to
+ * bbgpu_de_generation on its handle.  out: NULL or `count` reports. */
+int bbgpu_de_generation_batch(bbgpu_de *const *hs, int count, bbgpu_objective *obj,
+                              bbgpu_de_report *out);
 /* swarm in the reference's order after the generation (sorted for L-SHADE; JADE sorts at the
  * start of the next generation, de/jade.cpp:101) */
 int bbgpu_de_get_swarm(bbgpu_de *h, double *h_x, double *h_f);
 int bbgpu_de_get_archive(bbgpu_de *h, double *h_arch, int *rows);
 int bbgpu_de_get_memory(bbgpu_de *h, double *h_mcr, double *h_mf);
 int bbgpu_de_get_trace(bbgpu_de *h, int32_t *h_succ, double *h_ftrial, double *h_F, double *h_CR);
+/* diagnostics: device timestamps (ns) at the phase boundaries of the last generation kernel:
+ * [0] start [1] sorted + parameters [2..13] rounds [16] finalized [17] L-SHADE sort [18] end */
+int bbgpu_de_phase_times(bbgpu_de *h, uint64_t *out32);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -88,4 +88,6 @@ int bbgpu_de_get_swarm(bbgpu_de *h, double *x, double *f) {
 int bbgpu_de_get_archive(bbgpu_de *, double *, int *rows) { *rows = 0; return 0; }
 int bbgpu_de_get_memory(bbgpu_de *, double *, double *) { return 0; }
 int bbgpu_de_get_trace(bbgpu_de *, int32_t *, double *, double *, double *) { return 0; }
+int bbgpu_de_phase_times(bbgpu_de *, uint64_t *) { return 0; }
+int bbgpu_de_generation_batch(bbgpu_de *const *, int, bbgpu_objective *, bbgpu_de_report *) { return 0; }
 }

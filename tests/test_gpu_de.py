@@ -105,3 +105,54 @@ def test_free_running_philox_de_converges(ctx, kind):
     x, f = g.swarm()
     assert (x >= -5).all() and (x <= 5).all()
     assert np.allclose(f, (x * x).sum(1), rtol=1e-12)
+
+
+@pytest.mark.parametrize("kind,obj", [(O.JADE, O.RASTRIGIN), (O.SHADE, O.ROSENBROCK), (O.JADE, O.ACKLEY)])
+def test_batched_runs_equal_single_runs(ctx, kind, obj):
+    """bbgpu_de_generation_batch: R independent runs in one launch are bit-identical to the same runs
+    stepped one handle at a time (same seeds)."""
+    n, np_, R, gens = 50, 64, 5, 12
+    lo, hi = -5.0 * np.ones(n), 5.0 * np.ones(n)
+    objective = _cabi.Objective(ctx, n, builtin=obj)
+    single = [_cabi.De(ctx, kind, n, np_, lo, hi, mfev=3000, seed=100 + r) for r in range(R)]
+    batch = [_cabi.De(ctx, kind, n, np_, lo, hi, mfev=3000, seed=100 + r) for r in range(R)]
+    for g in single + batch:
+        g.init(objective)
+    for gen in range(gens):
+        reps1 = [g.generation(objective) for g in single]
+        reps2 = _cabi.De.generation_batch(batch, objective)
+        for r in range(R):
+            assert (reps1[r].np, reps1[r].larch, reps1[r].nsucc, reps1[r].fev) == \
+                   (reps2[r].np, reps2[r].larch, reps2[r].nsucc, reps2[r].fev)
+            assert reps1[r].fbest == reps2[r].fbest and reps1[r].radius_m2 == reps2[r].radius_m2
+            x1, f1 = single[r].swarm()
+            x2, f2 = batch[r].swarm()
+            assert np.array_equal(x1, x2) and np.array_equal(f1, f2), f"gen {gen} run {r}"
+            assert np.array_equal(single[r].archive(), batch[r].archive())
+    # different seeds really are different runs
+    assert not np.array_equal(batch[0].swarm()[1], batch[1].swarm()[1])
+
+
+def test_de_large_n_tiles(ctx, port_oracle):
+    """n > 1024 exercises the tiled term staging (Rosenbrock's neighbour coordinate across the tile edge)."""
+    P = port_oracle
+    P.seed(3)
+    n, np_ = 2500, 24
+    lo, hi = -10.0 * np.ones(n), 10.0 * np.ones(n)
+    for obj in (O.ROSENBROCK, O.ACKLEY):
+        h = P.de(O.JADE, 10 ** 6, np_, 1e-12)
+        h.init(obj, lo, hi)
+        x0, f0 = h.swarm()
+        g = _cabi.De(ctx, O.JADE, n, np_, lo, hi, mfev=10 ** 6)
+        objective = _cabi.Objective(ctx, n, builtin=obj)
+        g.init(objective, x0)
+        for gen in range(3):
+            h.iterate()
+            t = h.trace()
+            g.generation(objective, t)
+            succ, ft, F, CR = g.trace(np_)
+            assert np.array_equal(succ > 0, t["succ"] > 0)
+            assert_close(ft, t["ftrial"], what="trial fitness")
+            xo, fo = h.swarm()
+            xg, fg = g.swarm()
+            assert_close(xg, xo, what="swarm")
