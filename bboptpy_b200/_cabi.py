@@ -474,7 +474,7 @@ class De:
         return reps
 
     def phase_times(self):
-        t = np.zeros(32, dtype=np.uint64)
+        t = np.zeros(64, dtype=np.uint64)
         check(self.L.bbgpu_de_phase_times(self.h, t.ctypes.data))
         return t
 

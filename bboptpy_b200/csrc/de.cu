@@ -69,7 +69,7 @@ struct DeDev {
     int *ibest, *r1, *r2, *jrand, *slot, *ri;
     const int *trim;
     int *larch, *larch_new, *nsucc, *kslot;
-    int *succ[2], *ver[2], *trbuf[2], *sig;
+    int *st[2] /* per candidate: version << 3 | trial buffer << 2 | success (0, 1: <=, 2: <) */, *sig;
     bbgpu_de_report *rep;
 };
 
@@ -99,7 +99,7 @@ __device__ __forceinline__ void group_sync(int g) {
 }
 
 // per-candidate control parameters for the generation (de/jade.cpp:107-126, de/shade.cpp:104-126)
-__device__ __forceinline__ void de_params_one(const DeDev &d, int replay, int i) {
+__device__ __noinline__ void de_params_one(const DeDev &d, int replay, int i) {
     int ri = 0;
     if (d.kind == BBGPU_DE_SHADE) ri = replay ? d.ri[i] : de_int(d, i, 0, TAG_RI, d.h);
     const double mcr = d.kind == BBGPU_DE_JADE ? d.mu[0] : d.MCR[ri];
@@ -137,25 +137,24 @@ __device__ __forceinline__ void de_params_one(const DeDev &d, int replay, int i)
     d.CR[i] = fmax(0.0, fmin(__dadd_rn(__dmul_rn(z, 0.1), mcr), 1.0));
     d.Fm[i] = F;
     d.sig[4 * i + 0] = INT_MIN; // force a build in round 0
-    d.succ[0][i] = 0;
-    d.ver[0][i] = 0;
-    d.trbuf[0][i] = 0;
+    d.st[0][i] = 0;
 }
 
 // CTA-wide: push flags -> exclusive prefix counts `pre` and archive targets `tgt` (both in smem, np
-// ints each); wsum[0..nwarps) scratch, wsum[32] = total pushes
-__device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__restrict__ succ, int larch0, int *pre, int *tgt,
-        int *wsum) {
+// entries each) and, per archive slot, the first and last candidate that writes it (minw / maxw);
+// wsum[0..nwarps) scratch, wsum[32] = total pushes
+__device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__restrict__ st, int larch0, unsigned short *pre,
+        unsigned short *tgt, int *minw, int *maxw, int *wsum) {
     const int np = d.np, T = blockDim.x;
     const int per = (np + T - 1) / T;
     const int b = threadIdx.x * per, e = min(np, b + per);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int local = 0;
-    __syncthreads(); // previous readers of pre / tgt are done
+    unsigned mask = 0; // per <= 32 (np <= 8192 and T = 512)
     for (int i = b; i < e; i++) {
-        const int s = succ[i];
+        const int s = st[i] & 3;
         const int push = d.archive && (d.kind == BBGPU_DE_JADE ? (s >= 1) : (s == 2));
-        tgt[i] = push;
+        mask |= (unsigned) push << (i - b);
         local += push;
     }
     int incl = local;
@@ -164,25 +163,36 @@ __device__ __forceinline__ void de_scan_targets(const DeDev &d, const int *__res
         const int v = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += v;
     }
+    __syncthreads(); // previous readers of the tables are done
     if (lane == 31) wsum[wid] = incl;
+    for (int a = threadIdx.x; a < np; a += T) { minw[a] = INT_MAX; maxw[a] = -1; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
+    if (wid == 0) { // exclusive scan of the warp totals
         const int nw = T >> 5;
-        for (int w = 0; w < nw; w++) {
-            const int v = wsum[w];
-            wsum[w] = run;
-            run += v;
+        const int v = lane < nw ? wsum[lane] : 0;
+        int x = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
         }
-        wsum[32] = run;
+        if (lane < nw) wsum[lane] = x - v;
+        if (lane == 31) wsum[32] = x;
     }
     __syncthreads();
     int run = wsum[wid] + incl - local;
     for (int i = b; i < e; i++) {
-        const int push = tgt[i];
-        pre[i] = run;
-        const int la = larch0 + run;
-        tgt[i] = push ? (la < np ? la : d.slot[i]) : -1;
+        const int push = (mask >> (i - b)) & 1;
+        pre[i] = (unsigned short) run;
+        int t = 0xFFFF;
+        if (push) {
+            const int la = larch0 + run;
+            t = la < np ? la : d.slot[i];
+            // replayed slot draws exist only where the sequential loop drew one; a transient round may ask elsewhere
+            if ((unsigned) t >= (unsigned) np) t = 0xFFFF;
+            else { atomicMin(minw + t, i); atomicMax(maxw + t, i); }
+        }
+        tgt[i] = (unsigned short) t;
         run += push;
     }
     __syncthreads();
@@ -216,61 +226,105 @@ __device__ __forceinline__ Philox4 de_cross_block(const DeDev &d, int i, int qua
             ((uint32_t) (d.gen >> 32)) ^ ((uint32_t) TAG_CROSS << 24), (uint32_t) d.seed, (uint32_t) (d.seed >> 32));
 }
 
-// one candidate (one 128-thread group) in one resolution round.  T1/T2: this group's term buffers.
-template<int ID, bool REPLAY>
-__device__ __noinline__ void de_candidate(const DeDev &d, const DeLaunch &L, int cj, int i, int round, int larch0,
-        const int *pre, const int *tgt, int g, double *T1, double *T2, double *gred) {
+// A candidate whose inputs changed, queued for a rebuild in this round (48 bytes, shared memory)
+struct DeItem {
+    int i, j2, s0, s1, s2, mine /* its state word before the rebuild */;
+    int rxi, rxb, rx1, rx2, rout /* pool rows: parent, pbest, r1, r2, trial */, jr;
+};
+
+__device__ __forceinline__ int st_succ(int w) { return w & 3; }
+__device__ __forceinline__ int st_buf(int w) { return (w >> 2) & 1; }
+__device__ __forceinline__ int st_ver(int w) { return w >> 3; }
+
+// one THREAD per candidate: derive what the sequential loop would have shown candidate i from the
+// previous round's states; unchanged -> carry the state over, changed -> queue a rebuild
+template<bool REPLAY>
+__device__ __forceinline__ void de_signature(const DeDev &d, int cj, int i, bool valid, int round, int larch0,
+        const unsigned short *pre, const unsigned short *tgt, const int *minw, const int *maxw, DeItem *work, int *nwork) {
     const int cur = round & 1, nxt = cur ^ 1;
-    const int gt = threadIdx.x & (DE_GROUP - 1), lane = threadIdx.x & 31, gwarp = gt >> 5;
-    const int np = d.np, n = d.n;
-    const int *succ = d.succ[cur], *ver = d.ver[cur], *trb = d.trbuf[cur];
-    const int larch_i = d.archive ? min(np, larch0 + pre[i]) : 0;
-    const int jb = d.ibest[i], j1 = d.r1[i];
-    int j2;
-    if (REPLAY) {
-        j2 = d.r2[i];
-    } else {
-        j2 = i;
-        int t = 0;
-        while ((j2 == i || j2 == j1) && (np + larch_i > 2)) j2 = de_int(d, i, t++, TAG_R2, np + larch_i);
-    }
-    const int sb = jb < i ? succ[jb] : 0, s1f = j1 < i ? succ[j1] : 0;
-    const int s0 = sb ? ver[jb] : 0;
-    const int s1 = s1f ? ver[j1] : 0;
-    int s2, writer = -1, s2f = 0;
-    if (j2 >= np) {
-        const int a = j2 - np;
-        for (int j = lane; j < i; j += 32)
-            if (tgt[j] == a) writer = j;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) writer = max(writer, __shfl_xor_sync(0xffffffffu, writer, off));
-        s2 = -2 - writer;
-    } else {
-        s2f = j2 < i ? succ[j2] : 0;
-        s2 = s2f ? ver[j2] : 0;
-    }
-    int *sg = d.sig + 4 * i;
-    const bool same = sg[0] == s0 && sg[1] == s1 && sg[2] == s2 && sg[3] == j2;
-    if (same) { // group-uniform
-        if (gt == 0) {
-            d.succ[nxt][i] = succ[i];
-            d.ver[nxt][i] = ver[i];
-            d.trbuf[nxt][i] = trb[i];
+    const int np = d.np, lane = threadIdx.x & 31;
+    const int *st = d.st[cur];
+    int jb = 0, j1 = 0, j2 = 0, mine = 0, stb = 0, st1 = 0, st2 = 0, writer = -1, wa = 0, wlo = 0;
+    int4 sg = make_int4(0, 0, 0, 0);
+    bool search = false;
+    if (valid) {
+        jb = d.ibest[i]; j1 = d.r1[i];
+        sg = *(const int4*) (d.sig + 4 * i);
+        mine = st[i];
+        stb = jb < i ? st[jb] : 0;
+        st1 = j1 < i ? st[j1] : 0;
+        const int larch_i = d.archive ? min(np, larch0 + pre[i]) : 0;
+        if (REPLAY) {
+            j2 = d.r2[i];
+        } else {
+            j2 = i;
+            int t = 0;
+            while ((j2 == i || j2 == j1) && (np + larch_i > 2)) j2 = de_int(d, i, t++, TAG_R2, np + larch_i);
         }
+        if (j2 >= np) { // archive pick: the last candidate before i that writes this slot in the sequential loop
+            wa = j2 - np;
+            wlo = minw[wa];
+            const int hi = maxw[wa];
+            if (wlo >= i) writer = -1;      // nobody before i (INT_MAX: nobody at all)
+            else if (hi < i) writer = hi;
+            else search = true;             // several writers straddle i: rare
+        } else {
+            st2 = j2 < i ? st[j2] : 0;
+        }
+    }
+    // the rare straddled slots are searched by the whole warp, one query at a time
+    unsigned need = __ballot_sync(0xffffffffu, search);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int qa = __shfl_sync(0xffffffffu, wa, src), qi = __shfl_sync(0xffffffffu, i, src), qlo = __shfl_sync(0xffffffffu, wlo, src);
+        int best = qlo;
+        for (int j = qlo + 1 + lane; j < qi; j += 32)
+            if (tgt[j] == qa) best = j;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, off));
+        if (lane == src) writer = best;
+    }
+    if (!valid) return;
+    const int s0 = st_succ(stb) ? st_ver(stb) : 0;
+    const int s1 = st_succ(st1) ? st_ver(st1) : 0;
+    const int s2 = j2 >= np ? -2 - writer : (st_succ(st2) ? st_ver(st2) : 0);
+    if (sg.x == s0 && sg.y == s1 && sg.z == s2 && sg.w == j2) {
+        d.st[nxt][i] = mine;
         return;
     }
-    const int64_t ld = d.ld;
     const int *srow = d.srow[cj];
+    DeItem it;
+    it.i = i; it.j2 = j2; it.s0 = s0; it.s1 = s1; it.s2 = s2; it.mine = mine;
+    it.rxi = srow[i];
+    it.rxb = st_succ(stb) ? d.trow[st_buf(stb)][jb] : srow[jb];
+    it.rx1 = st_succ(st1) ? d.trow[st_buf(st1)][j1] : srow[j1];
+    if (j2 >= np) it.rx2 = writer >= 0 ? srow[writer] : d.arch_row[j2 - np];
+    else it.rx2 = st_succ(st2) ? d.trow[st_buf(st2)][j2] : srow[j2];
+    it.rout = d.trow[1 - st_buf(mine)][i];
+    it.jr = d.jrand[i];
+    work[atomicAdd(nwork, 1)] = it;
+}
+
+// one queued candidate, one 128-thread group: mutation + crossover + repair + objective + greedy test.
+// T1/T2: this group's term buffers.
+template<int ID, bool REPLAY>
+__device__ __noinline__ void de_build(const DeDev &d, const DeLaunch &L, int cj, const DeItem &it, int round, int g,
+        double *T1, double *T2, double *gred) {
+    const int nxt = (round & 1) ^ 1;
+    const int gt = threadIdx.x & (DE_GROUP - 1), lane = threadIdx.x & 31, gwarp = gt >> 5;
+    const int n = d.n, i = it.i;
+    const int64_t ld = d.ld;
     DeBuild b;
-    b.xi = d.POOL + (int64_t) srow[i] * ld;
-    b.xb = d.POOL + (int64_t) (sb ? d.trow[trb[jb]][jb] : srow[jb]) * ld;
-    b.x1 = d.POOL + (int64_t) (s1f ? d.trow[trb[j1]][j1] : srow[j1]) * ld;
-    if (j2 >= np) b.x2 = d.POOL + (int64_t) (writer >= 0 ? srow[writer] : d.arch_row[j2 - np]) * ld;
-    else b.x2 = d.POOL + (int64_t) (s2f ? d.trow[trb[j2]][j2] : srow[j2]) * ld;
-    const int mybuf = 1 - trb[i];
-    double *out = d.POOL + (int64_t) d.trow[mybuf][i] * ld;
+    b.xi = d.POOL + (int64_t) it.rxi * ld;
+    b.xb = d.POOL + (int64_t) it.rxb * ld;
+    b.x1 = d.POOL + (int64_t) it.rx1 * ld;
+    b.x2 = d.POOL + (int64_t) it.rx2 * ld;
+    double *out = d.POOL + (int64_t) it.rout * ld;
     b.lo = d.lower; b.hi = d.upper; b.U = d.U + (int64_t) i * n;
-    b.F = d.Fm[i]; b.CR = d.CR[i]; b.jr = d.jrand[i]; b.replay = REPLAY;
+    b.F = d.Fm[i]; b.CR = d.CR[i]; b.jr = it.jr; b.replay = REPLAY;
+    const double fi = d.F[cj][i];
+
     constexpr int id = ID;
     const int nt = obj_term_count(id, n);
     const bool rosen = id == BBGPU_OBJ_ROSENBROCK, ackley = id == BBGPU_OBJ_ACKLEY, ellip = id == BBGPU_OBJ_ELLIPSOID;
@@ -283,7 +337,7 @@ __device__ __noinline__ void de_candidate(const DeDev &d, const DeLaunch &L, int
             // one Philox block per 4 coordinates; the quad is processed as two 16-byte halves to bound registers
             Philox4 r = { 0u, 0u, 0u, 0u };
             if (!REPLAY) r = de_cross_block(d, i, (t0 >> 2) + q);
-#pragma unroll 1
+#pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int j = t0 + 4 * q + 2 * h; // rows are 64-byte aligned and padded to a multiple of 8 doubles
                 if (j >= n) break;
@@ -347,56 +401,47 @@ __device__ __noinline__ void de_candidate(const DeDev &d, const DeLaunch &L, int
         if (lane == 0) {
             double cn = 0.0, nr = 0.0;
             for (int w = 0; w < DE_GROUP / 32; w++) { cn += gred[2 * w]; nr += gred[2 * w + 1]; }
-            const double fi = d.F[cj][i];
             const int s = ft <= fi ? (ft < fi ? 2 : 1) : 0;
             d.FT[i] = ft;
             d.DF[i] = fi - ft;
             d.RT[i] = sqrt(nr);
             d.CR1[i] = d.repaircr ? __ddiv_rn(cn, (double) n) : b.CR;
-            d.succ[nxt][i] = s;
-            d.trbuf[nxt][i] = mybuf;
-            d.ver[nxt][i] = ver[i] + ((s != succ[i] || s > 0) ? 1 : 0);
-            sg[0] = s0; sg[1] = s1; sg[2] = s2; sg[3] = j2;
-            d.r2[i] = j2;
-            atomicAdd(L.nrecomp + round, 1);
+            const int ver = st_ver(it.mine) + ((s != st_succ(it.mine) || s > 0) ? 1 : 0);
+            d.st[nxt][i] = (ver << 3) | ((1 - st_buf(it.mine)) << 2) | s;
+            if (s != st_succ(it.mine) || s > 0) atomicAdd(L.nrecomp + round, 1); // later candidates may see a change
+            *(int4*) (d.sig + 4 * i) = make_int4(it.s0, it.s1, it.s2, it.j2);
+            d.r2[i] = it.j2;
         }
     }
     group_sync(g); // gred / T1 are free again
 }
 
-// after the fixed point, one warp per successful candidate: the greedy replacement and the archive push
+// after the fixed point, one thread per successful candidate: the greedy replacement and the archive push
 // as row-id swaps (de/jade.cpp:161-176).  Last writer per archive slot wins; the archived row is the OLD parent.
-__device__ __forceinline__ void de_finalize_one(const DeDev &d, int cj, int i, int fin, const int *tgt) {
-    if (d.succ[fin][i] == 0) return;
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void de_finalize_one(const DeDev &d, int cj, int i, int fin, const unsigned short *tgt, const int *maxw) {
+    const int w = d.st[fin][i];
+    if (st_succ(w) == 0) return;
     const int a = tgt[i];
-    int later = 0;
-    if (a >= 0) {
-        for (int q = i + 1 + lane; q < d.np; q += 32) later |= (tgt[q] == a);
-        later = __any_sync(0xffffffffu, later);
+    const int tb = st_buf(w);
+    const int t = d.trow[tb][i], p = d.srow[cj][i];
+    int freed = p;
+    if (a != 0xFFFF && maxw[a] == i) { // the last writer of the slot archives its parent
+        freed = d.arch_row[a];
+        d.arch_row[a] = p;
     }
-    if (lane == 0) {
-        const int tb = d.trbuf[fin][i];
-        const int t = d.trow[tb][i], p = d.srow[cj][i];
-        int freed = p;
-        if (a >= 0 && !later) {
-            freed = d.arch_row[a];
-            d.arch_row[a] = p;
-        }
-        d.srow[cj][i] = t;
-        d.trow[tb][i] = freed;
-        d.F[cj][i] = d.FT[i];
-        d.R[cj][i] = d.RT[i];
-    }
+    d.srow[cj][i] = t;
+    d.trow[tb][i] = freed;
+    d.F[cj][i] = d.FT[i];
+    d.R[cj][i] = d.RT[i];
 }
 
 // parameter adaptation (de/jade.cpp:185-205, de/shade.cpp:186-212)
-__device__ __forceinline__ void de_adapt_block(const DeDev &d, int fin, int *nsucc_out, double *red) {
-    const int *succ = d.succ[fin];
+__device__ __noinline__ void de_adapt_block(const DeDev &d, int fin, int *nsucc_out, double *red) {
+    const int *st = d.st[fin];
     const bool jade = d.kind == BBGPU_DE_JADE;
     double cnt = 0, s_cr = 0, s_cr2 = 0, s_f = 0, s_f2 = 0, s_w = 0, s_wcr = 0, s_wf = 0, s_wf2 = 0, acc = 0;
     for (int i = threadIdx.x; i < d.np; i += blockDim.x) {
-        const int s = succ[i];
+        const int s = st[i] & 3;
         if (s >= 1) acc += 1.0;
         if (jade ? (s >= 1) : (s == 2)) {
             const double cr = d.CR1[i], f = d.Fm[i];
@@ -417,7 +462,7 @@ __device__ __forceinline__ void de_adapt_block(const DeDev &d, int fin, int *nsu
     if (jade && cnt > 0) {
         const double mean = s_cr / cnt;
         for (int i = threadIdx.x; i < d.np; i += blockDim.x)
-            if (succ[i] >= 1) { const double t = d.CR1[i] - mean; dev2 += t * t; }
+            if ((st[i] & 3) >= 1) { const double t = d.CR1[i] - mean; dev2 += t * t; }
         dev2 = block_sum(dev2, red);
     }
     if (threadIdx.x == 0) {
@@ -460,7 +505,7 @@ __device__ __forceinline__ int de_trim_thread(const DeDev &d, int la, int replay
 
 // counting rank of the members [first, np) stride `step` (one warp each) and id scatter:
 // side `from` -> side `to`, ascending by (fitness, index)
-__device__ __forceinline__ void de_sort_ids(const DeDev &d, int from, int to, int first, int step) {
+__device__ __noinline__ void de_sort_ids(const DeDev &d, int from, int to, int first, int step) {
     const int lane = threadIdx.x & 31, np = d.np;
     const double *F = d.F[from];
     for (int i = first; i < np; i += step) {
@@ -483,7 +528,7 @@ __device__ __forceinline__ void de_sort_ids(const DeDev &d, int from, int to, in
 
 // end of the generation, one CTA per run: swarm statistics for converged() (de/jade.cpp:228-245), the
 // report, L-SHADE's archive trimming, and the run's evolving scalars
-__device__ __forceinline__ void de_report_block(DeDev *dg, const DeDev &d, const DeLaunch &L, int side, int np_after, int fin,
+__device__ __noinline__ void de_report_block(DeDev *dg, const DeDev &d, const DeLaunch &L, int side, int np_after, int fin,
         int rounds, double *red) {
     const double *radius = d.R[side], *F = d.F[side];
     double s = 0.0, fb = INFINITY;
@@ -525,7 +570,7 @@ __device__ __forceinline__ void de_report_block(DeDev *dg, const DeDev &d, const
     }
 }
 
-__global__ void __launch_bounds__(DE_CTA, 2) de_generation_kernel(DeDev *const *__restrict__ runs, DeLaunch L) {
+__global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *__restrict__ runs, DeLaunch L) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -534,7 +579,9 @@ __global__ void __launch_bounds__(DE_CTA, 2) de_generation_kernel(DeDev *const *
     __shared__ double gredbuf[DE_GROUPS][2 * (DE_GROUP / 32)];
     __shared__ int wsum[33];
     double *terms = (double*) smraw;                           // [DE_GROUPS][2][DE_TILE]
-    int *pre = (int*) (terms + DE_GROUPS * 2 * DE_TILE);       // [np]
+    DeItem *work = (DeItem*) (terms + DE_GROUPS * 2 * DE_TILE); // [DE_CTA]
+    int *minw = (int*) (work + DE_CTA);                        // [np], then maxw [np], pre [np] u16, tgt [np] u16
+    __shared__ int nwork;
     const int tid = threadIdx.x, warp = tid >> 5, g = tid / DE_GROUP;
     constexpr int WARPS = DE_CTA / 32;
     const int ntasks = L.nruns * L.cpr;
@@ -557,6 +604,13 @@ __global__ void __launch_bounds__(DE_CTA, 2) de_generation_kernel(DeDev *const *
         }
         mark++;
     };
+    auto fine = [&](int round, int k) { // [32 + 4*round + k], rounds 0..7: after scan / signatures / builds / grid.sync
+        if (L.phase_ns && blockIdx.x == 0 && tid == 0 && round < 8) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            L.phase_ns[32 + 4 * round + k] = t;
+        }
+    };
     stamp(); // 0 start
 
     // ---- phase 0: JADE sorts the swarm (de/jade.cpp:101); control parameters of the generation
@@ -575,16 +629,28 @@ __global__ void __launch_bounds__(DE_CTA, 2) de_generation_kernel(DeDev *const *
         for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
             const int run = task / L.cpr, part = task % L.cpr;
             load_run(run);
-            int *tgt = pre + d.np;
+            int *maxw = minw + d.np;
+            unsigned short *pre = (unsigned short*) (maxw + d.np), *tgt = pre + d.np;
             const int cj = d.kind == BBGPU_DE_JADE ? d.cur ^ 1 : d.cur;
             const int larch0 = *d.larch;
-            de_scan_targets(d, d.succ[round & 1], larch0, pre, tgt, wsum);
-            for (int i0 = part * DE_GROUPS; i0 < d.np; i0 += L.cpr * DE_GROUPS) {
-                const int i = i0 + g;
-                if (i < d.np) {
-                    double *T1 = terms + (size_t) g * 2 * DE_TILE, *T2 = T1 + DE_TILE;
-#define DE_CASE(ID) case ID: if (L.replay) de_candidate<ID, true>(d, L, cj, i, round, larch0, pre, tgt, g, T1, T2, gredbuf[g]); \
-                             else de_candidate<ID, false>(d, L, cj, i, round, larch0, pre, tgt, g, T1, T2, gredbuf[g]); break;
+            de_scan_targets(d, d.st[round & 1], larch0, pre, tgt, minw, maxw, wsum);
+            fine(round, 0);
+            // candidates of this CTA: part, part + cpr, ...; DE_CTA of them per chunk
+            for (int k0 = 0; part + (int64_t) k0 * L.cpr < d.np; k0 += DE_CTA) {
+                __syncthreads(); // the previous chunk's work list has been consumed
+                if (tid == 0) nwork = 0;
+                __syncthreads();
+                const int64_t i = part + (int64_t) (k0 + tid) * L.cpr;
+                const bool valid = i < d.np;
+                if (L.replay) de_signature<true>(d, cj, (int) min(i, (int64_t) d.np - 1), valid, round, larch0, pre, tgt, minw, maxw, work, &nwork);
+                else de_signature<false>(d, cj, (int) min(i, (int64_t) d.np - 1), valid, round, larch0, pre, tgt, minw, maxw, work, &nwork);
+                __syncthreads();
+                fine(round, 1);
+                const int todo = nwork;
+                double *T1 = terms + (size_t) g * 2 * DE_TILE, *T2 = T1 + DE_TILE;
+                for (int w = g; w < todo; w += DE_GROUPS) {
+#define DE_CASE(ID) case ID: if (L.replay) de_build<ID, true>(d, L, cj, work[w], round, g, T1, T2, gredbuf[g]); \
+                             else de_build<ID, false>(d, L, cj, work[w], round, g, T1, T2, gredbuf[g]); break;
                     switch (L.obj_id) {
                     DE_CASE(BBGPU_OBJ_SPHERE) DE_CASE(BBGPU_OBJ_ELLIPSOID) DE_CASE(BBGPU_OBJ_ROSENBROCK)
                     DE_CASE(BBGPU_OBJ_RASTRIGIN) DE_CASE(BBGPU_OBJ_ACKLEY)
@@ -594,7 +660,9 @@ __global__ void __launch_bounds__(DE_CTA, 2) de_generation_kernel(DeDev *const *
                 }
             }
         }
+        fine(round, 2);
         grid.sync();
+        fine(round, 3);
         const int rebuilt = *((volatile int*) (L.nrecomp + round));
         round++;
         if (round <= 12) stamp(); // 2.. after each of the first 12 rounds
@@ -607,16 +675,17 @@ __global__ void __launch_bounds__(DE_CTA, 2) de_generation_kernel(DeDev *const *
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
         const int run = task / L.cpr, part = task % L.cpr;
         load_run(run);
-        int *tgt = pre + d.np;
+        int *maxw = minw + d.np;
+        unsigned short *pre = (unsigned short*) (maxw + d.np), *tgt = pre + d.np;
         const int cj = d.kind == BBGPU_DE_JADE ? d.cur ^ 1 : d.cur;
         const int larch0 = *d.larch;
-        de_scan_targets(d, d.succ[fin], larch0, pre, tgt, wsum);
+        de_scan_targets(d, d.st[fin], larch0, pre, tgt, minw, maxw, wsum);
         if (part == 0) {
             // DF / CR1 / Fm, not the fitness being replaced below, feed the adaptation
             de_adapt_block(d, fin, d.nsucc, red);
             if (tid == 0) *d.larch_new = d.archive ? min(d.np, larch0 + wsum[32]) : 0;
         }
-        for (int i = part * WARPS + warp; i < d.np; i += L.cpr * WARPS) de_finalize_one(d, cj, i, fin, tgt);
+        for (int i = part * DE_CTA + tid; i < d.np; i += L.cpr * DE_CTA) de_finalize_one(d, cj, i, fin, tgt, maxw);
     }
     if (blockIdx.x == 0 && tid == 0)
         for (int r = 0; r < round; r++) L.nrecomp[r] = 0;
@@ -723,7 +792,9 @@ template<typename T> int de_alloc(bbgpu_de *h, T **p, size_t count, bool zero = 
     return BBGPU_OK;
 }
 
-size_t de_smem_bytes(int np) { return (size_t) DE_GROUPS * 2 * DE_TILE * sizeof(double) + (size_t) 2 * np * sizeof(int); }
+size_t de_smem_bytes(int np) {
+    return (size_t) DE_GROUPS * 2 * DE_TILE * sizeof(double) + (size_t) DE_CTA * sizeof(DeItem) + (size_t) np * (2 * sizeof(int) + 2 * sizeof(unsigned short));
+}
 
 // the device struct as the kernel left it (np, cur, last_fin, ...)
 int de_pull(bbgpu_de *h) {
@@ -780,7 +851,7 @@ extern "C" {
 
 int bbgpu_de_create(bbgpu_ctx *ctx, const bbgpu_de_config *cfg, const double *h_lower, const double *h_upper, bbgpu_de **out) {
     BB_ARG(ctx && cfg && h_lower && h_upper && out);
-    BB_ARG(cfg->n >= 1 && cfg->np >= 4 && cfg->np <= 16384);
+    BB_ARG(cfg->n >= 1 && cfg->np >= 4 && cfg->np <= 8192);
     BB_ARG(cfg->kind == BBGPU_DE_JADE || cfg->kind == BBGPU_DE_SHADE);
     BB_ARG(cfg->kind == BBGPU_DE_JADE || (cfg->h >= 1 && cfg->npmin >= 4 && cfg->mfev > 0));
     BB_CUDA(cudaSetDevice(ctx->device));
@@ -810,8 +881,8 @@ int bbgpu_de_create(bbgpu_ctx *ctx, const bbgpu_de_config *cfg, const double *h_
     DA(d.FT, rows); DA(d.RT, rows); DA(d.DF, rows); DA(d.CR, rows); DA(d.Fm, rows); DA(d.CR1, rows);
     DA(d.MCR, hh); DA(d.MF, hh); DA(d.mu, 2);
     DA(d.ibest, rows); DA(d.r1, rows); DA(d.r2, rows); DA(d.jrand, rows); DA(d.slot, rows); DA(d.ri, rows);
-    DA(d.larch, 1); DA(d.larch_new, 1); DA(d.nsucc, 1); DA(d.kslot, 1); DA(h->phase_ns, 32);
-    DA(d.succ[0], rows); DA(d.succ[1], rows); DA(d.ver[0], rows); DA(d.ver[1], rows); DA(d.trbuf[0], rows); DA(d.trbuf[1], rows);
+    DA(d.larch, 1); DA(d.larch_new, 1); DA(d.nsucc, 1); DA(d.kslot, 1); DA(h->phase_ns, 64);
+    DA(d.st[0], rows); DA(d.st[1], rows);
     DA(d.sig, rows * 4); DA(h->nrecomp, DE_MAX_ROUNDS);
     DA(h->zbuf, rows); DA(h->cbuf, rows);
     DA(h->d_rep, 1); DA(h->d_dev, 1); DA(h->d_self, 1);
@@ -1021,10 +1092,11 @@ int bbgpu_de_get_memory(bbgpu_de *h, double *h_mcr, double *h_mf) {
 }
 
 // diagnostics: %globaltimer stamps (ns) of the last generation launch this handle led
-// [0] start [1] sorted + parameters [2..13] rounds [16] finalized [17] L-SHADE sort [18] end
-int bbgpu_de_phase_times(bbgpu_de *h, uint64_t *out32) {
-    BB_ARG(h && out32);
-    BB_CUDA(cudaMemcpyAsync(out32, h->phase_ns, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->ctx->stream));
+// [0] start [1] sorted + parameters [2..13] rounds [16] finalized [17] L-SHADE sort [18] end;
+// [32 + 4r + k], r < 8: round r after scan / signatures / builds / grid.sync (CTA 0)
+int bbgpu_de_phase_times(bbgpu_de *h, uint64_t *out64) {
+    BB_ARG(h && out64);
+    BB_CUDA(cudaMemcpyAsync(out64, h->phase_ns, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->ctx->stream));
     BB_CUDA(cudaStreamSynchronize(h->ctx->stream));
     return BBGPU_OK;
 }
@@ -1036,11 +1108,13 @@ int bbgpu_de_get_trace(bbgpu_de *h, int32_t *h_succ, double *h_ftrial, double *h
     BB_TRY(de_pull(h));
     const DeDev &d = h->d;
     const int np = d.last_np, fin = d.last_fin;
-    if (h_succ) BB_CUDA(cudaMemcpyAsync(h_succ, d.succ[fin], (size_t) np * 4, cudaMemcpyDeviceToHost, st));
+    if (h_succ) BB_CUDA(cudaMemcpyAsync(h_succ, d.st[fin], (size_t) np * 4, cudaMemcpyDeviceToHost, st));
     if (h_ftrial) BB_CUDA(cudaMemcpyAsync(h_ftrial, d.FT, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
     if (h_F) BB_CUDA(cudaMemcpyAsync(h_F, d.Fm, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
     if (h_CR) BB_CUDA(cudaMemcpyAsync(h_CR, d.CR, (size_t) np * 8, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
+    if (h_succ)
+        for (int i = 0; i < np; i++) h_succ[i] &= 3; // state word -> success code
     return BBGPU_OK;
 }
 

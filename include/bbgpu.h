@@ -293,8 +293,9 @@ int bbgpu_de_get_archive(bbgpu_de *h, double *h_arch, int *rows);
 int bbgpu_de_get_memory(bbgpu_de *h, double *h_mcr, double *h_mf);
 int bbgpu_de_get_trace(bbgpu_de *h, int32_t *h_succ, double *h_ftrial, double *h_F, double *h_CR);
 /* diagnostics: device timestamps (ns) at the phase boundaries of the last generation kernel:
- * [0] start [1] sorted + parameters [2..13] rounds [16] finalized [17] L-SHADE sort [18] end */
-int bbgpu_de_phase_times(bbgpu_de *h, uint64_t *out32);
+ * [0] start [1] sorted + parameters [2..13] rounds [16] finalized [17] L-SHADE sort [18] end;
+ * [32 + 4r + k], r < 8: round r after scan / signatures / builds / grid.sync.  64 entries. */
+int bbgpu_de_phase_times(bbgpu_de *h, uint64_t *out64);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

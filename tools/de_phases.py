@@ -21,3 +21,9 @@ for kind in (0, 1):
             parts.append("%s=%.1f" % (name, (t[idx] - prev) / 1e3))
             prev = t[idx]
         print("kind", kind, "gen", gen, "rounds", rounds, "total_us %.1f |" % ((t[18] - t0) / 1e3), " ".join(parts))
+        if gen == 5:
+            for r in range(min(rounds, 8)):
+                base = t[1] if r == 0 else t[32 + 4 * (r - 1) + 3]
+                q = t[32 + 4 * r: 36 + 4 * r]
+                print("   round %d: scan %.1f  signatures %.1f  builds %.1f  grid.sync %.1f" %
+                      (r, (q[0] - base) / 1e3, (q[1] - q[0]) / 1e3, (q[2] - q[1]) / 1e3, (q[3] - q[2]) / 1e3))
