@@ -17,7 +17,8 @@ OBJ_SPHERE, OBJ_ELLIPSOID, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY = range(5)
 CMA_FULL, CMA_ACTIVE, CMA_SEP = range(3)
 DE_JADE, DE_SHADE = range(2)
 (F_XMEAN, F_XOLD, F_PC, F_PS, F_C, F_B, F_D, F_INVSQRTC, F_ARX, F_Z, F_FITNESS, F_RANKVAL, F_YCOEFF,
- F_WEIGHTS) = range(14)
+ F_WEIGHTS, F_NORMS, F_SHARD_RED) = range(16)
+COMM_ID_BYTES = 128
 
 c_dp = ctypes.c_void_p
 
@@ -124,6 +125,17 @@ def lib():
     L.bbgpu_cma_probe.argtypes = [vp, d, i]
     L.bbgpu_cma_fetch.argtypes = [vp, P(CmaReport)]
     L.bbgpu_cma_generation.argtypes = [vp, vp, d, u64, i, i]
+    L.bbgpu_cma_attach_comm.argtypes = [vp, vp]
+    L.bbgpu_cma_shard_partial.argtypes = [vp]
+    L.bbgpu_cma_shard_finish.argtypes = [vp, d, i]
+    L.bbgpu_cma_get_candidate.argtypes = [vp, i, vp]
+    L.bbgpu_comm_unique_id.argtypes = [vp]
+    L.bbgpu_comm_create.argtypes = [vp, i, i, vp, P(vp)]
+    L.bbgpu_comm_destroy.argtypes = [vp]
+    L.bbgpu_comm_rank.argtypes = [vp]
+    L.bbgpu_comm_world.argtypes = [vp]
+    L.bbgpu_comm_allreduce_sum.argtypes = [vp, vp, i64]
+    L.bbgpu_comm_best_of.argtypes = [vp, vp, vp, i, P(d), P(i)]
     L.bbgpu_dgemm_host.argtypes = [vp, i, i, i, vp, vp, vp]
     L.bbgpu_dsyrk_host.argtypes = [vp, i, i, d, vp, vp, vp]
     L.bbgpu_rank_host.argtypes = [vp, i, vp, vp]
@@ -186,7 +198,7 @@ class Context:
 
     # ---- measurement helpers
     PROF_TAGS = ("sample_gemm", "cov_syrk", "norm_gemm", "eval", "rank", "philox", "eig", "update_misc", "sep_sample",
-                 "de_round", "de_misc")
+                 "de_round", "de_misc", "comm")
 
     def profile(self, on=True):
         check(self.L.bbgpu_ctx_profile_enable(self.h, int(on)))
@@ -298,15 +310,47 @@ class Objective:
         return f
 
 
+class Comm:
+    """One rank of an NCCL communicator (include/bbgpu.h, bbgpu_comm_*)."""
+
+    @staticmethod
+    def unique_id(L=None):
+        L = L or lib()
+        buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+        check(L.bbgpu_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, ctx, world, rank, unique_id):
+        self.ctx, self.L, self.world, self.rank = ctx, ctx.L, world, rank
+        assert len(unique_id) == COMM_ID_BYTES
+        self.h = ctypes.c_void_p()
+        check(self.L.bbgpu_comm_create(ctx.h, world, rank, ctypes.create_string_buffer(unique_id, COMM_ID_BYTES),
+                                       ctypes.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.bbgpu_comm_destroy(self.h)
+        except Exception:
+            pass
+
+    def best_of(self, d_f_ptr, d_x_ptr, n):
+        f, owner = ctypes.c_double(0), ctypes.c_int(0)
+        check(self.L.bbgpu_comm_best_of(self.h, d_f_ptr, d_x_ptr, n, ctypes.byref(f), ctypes.byref(owner)))
+        return f.value, owner.value
+
+
 class Cma:
     """Device state + phases of one CMA-ES run (see include/bbgpu.h)."""
 
-    def __init__(self, ctx, kind, n, lam, weights, consts, bound=False, lower=None, upper=None, seed=0):
+    def __init__(self, ctx, kind, n, lam, weights, consts, bound=False, lower=None, upper=None, seed=0, shard=(0, 1)):
         self.ctx, self.L = ctx, ctx.L
         self.kind, self.n, self.lam, self.mu = kind, n, lam, len(weights)
+        self.shard_rank, self.shards = shard
+        self.lam_loc = lam // self.shards
         cfg = CmaConfig()
         cfg.kind, cfg.n, cfg.lambda_, cfg.mu, cfg.bound = kind, n, lam, self.mu, int(bound)
-        cfg.shard_rank, cfg.shard_count, cfg.seed = 0, 1, seed
+        cfg.shard_rank, cfg.shard_count, cfg.seed = self.shard_rank, self.shards, seed
         for k in ("cc", "cs", "c1", "cmu", "mueff", "chi", "cneg", "alphaold", "cm", "ccov"):
             setattr(cfg, k, float(consts.get(k, 0.0)))
         if kind == CMA_ACTIVE and "cm" not in consts:
@@ -329,9 +373,10 @@ class Cma:
     def _len(self, field):
         n, lam = self.n, self.lam
         full = self.kind != CMA_SEP
+        ld = (n + 7) // 8 * 8
         return {F_XMEAN: n, F_XOLD: n, F_PC: n, F_PS: n, F_D: n, F_C: n * n if full else n, F_B: n * n,
-                F_INVSQRTC: n * n, F_ARX: lam * n, F_Z: lam * n, F_FITNESS: lam, F_RANKVAL: lam, F_YCOEFF: self.mu,
-                F_WEIGHTS: self.mu}[field]
+                F_INVSQRTC: n * n, F_ARX: self.lam_loc * n, F_Z: self.lam_loc * n, F_FITNESS: lam, F_RANKVAL: lam,
+                F_YCOEFF: self.mu, F_WEIGHTS: self.mu, F_NORMS: lam, F_SHARD_RED: n * ld + ld}[field]
 
     def reset(self, guess, keep_offdiag=False):
         g = f64(guess)
@@ -387,6 +432,27 @@ class Cma:
 
     def generation(self, obj, sigma, generation, ik, fev_after):
         check(self.L.bbgpu_cma_generation(self.h, obj.h, sigma, generation, ik, fev_after))
+
+    # ---- candidate-sharded handles
+    def attach_comm(self, comm):
+        check(self.L.bbgpu_cma_attach_comm(self.h, comm.h if comm is not None else None))
+        self._comm = comm
+
+    def shard_partial(self):
+        check(self.L.bbgpu_cma_shard_partial(self.h))
+
+    def shard_finish(self, sigma, fev):
+        check(self.L.bbgpu_cma_shard_finish(self.h, sigma, fev))
+
+    def candidate(self, index):
+        x = np.empty(self.n)
+        check(self.L.bbgpu_cma_get_candidate(self.h, index, x.ctypes.data))
+        return x
+
+    def device_ptr(self, field):
+        p, ld = ctypes.c_void_p(), ctypes.c_int64(0)
+        check(self.L.bbgpu_cma_device_ptr(self.h, field, ctypes.byref(p), ctypes.byref(ld)))
+        return p.value, ld.value
 
 
 class De:

@@ -53,12 +53,28 @@ struct bbgpu_cma {
     cudaEvent_t ev_z[2] = { nullptr, nullptr };    // buffer filled (recorded on aux)
     cudaEvent_t ev_used[2] = { nullptr, nullptr }; // buffer consumed by sample() (recorded on the main stream)
     bool used_rec[2] = { false, false };
+    // candidate sharding of one run over several GPUs: this handle owns candidates
+    // [row0, row0 + lam_loc); X / Z hold only those rows, fitness and ranking cover all lambda
+    int shards = 1, shard = 0, lam_loc = 0, row0 = 0;
+    bbgpu_comm *comm = nullptr;
+    double last_sigma = 0.0;
+    double *Yloc = nullptr, *coef_loc = nullptr, *wm_loc = nullptr, *norm_all = nullptr, *red = nullptr, *rowsq_loc = nullptr;
+    int rowsq_loc_tiles = 0;
     // report
     bbgpu_cma_report *d_report = nullptr;
     bbgpu_cma_report *h_report = nullptr; // pinned
 };
 
 namespace bb {
+
+// comm.cu
+int comm_allreduce_sum(bbgpu_comm *c, double *d_buf, size_t count);
+int comm_allgather(bbgpu_comm *c, double *d_buf, size_t per);
+int comm_allgather2(bbgpu_comm *c, double *d_a, double *d_b, size_t per);
+int comm_broadcast(bbgpu_comm *c, double *d_buf, size_t count, int root);
+int comm_rank(const bbgpu_comm *c);
+int comm_world(const bbgpu_comm *c);
+bbgpu_ctx *comm_ctx(const bbgpu_comm *c);
 
 void destroy_solver(bbgpu_ctx *ctx) {
     if (ctx->solver) {
@@ -305,6 +321,92 @@ __global__ void __launch_bounds__(256) plain_coef_kernel(int mu, const double *_
 }
 
 // ------------------------------------------------------------------------------------------
+// candidate-sharded update (one run over several GPUs)
+// ------------------------------------------------------------------------------------------
+
+// Y[k][:] = (X[k][:] - m)/sigma for every local candidate (the SYRK / norm operand)
+__global__ void __launch_bounds__(256) shard_steps_kernel(double *__restrict__ Y, const double *__restrict__ X, int64_t ld,
+        int n, int rows, const double *__restrict__ m, double sigma) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mo = m[i];
+    for (int k = blockIdx.y; k < rows; k += gridDim.y)
+        Y[(int64_t) k * ld + i] = __ddiv_rn(__dsub_rn(X[(int64_t) k * ld + i], mo), sigma);
+}
+
+// norm_all[row0 + k] = sigma^2 * sum over N tiles of the row-sum-of-squares partials = ||C^-1/2 (x_k - m)||^2
+__global__ void __launch_bounds__(256) shard_norms_kernel(const double *__restrict__ part, int tiles_n, int rows, double sigma,
+        double *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= rows) return;
+    double s = 0.0;
+    for (int t = 0; t < tiles_n; t++) s = __dadd_rn(s, part[(int64_t) t * rows + k]);
+    out[k] = __dmul_rn(__dmul_rn(sigma, sigma), s);
+}
+
+// From the (replicated) ranking: recombination weight and covariance coefficient of every LOCAL candidate
+// (cmaes.cpp:139; active_cmaes.cpp:115-132,146-158).  One thread per sorted position r.
+__global__ void __launch_bounds__(256) shard_coef_kernel(const int *__restrict__ rank_idx, int lambda, int mu, int row0,
+        int lam_loc, const double *__restrict__ w, bool active, double cpos, double cneg, const double *__restrict__ norm_all,
+        double *__restrict__ coef_loc, double *__restrict__ wm_loc, double *__restrict__ ycoeff) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= lambda) return;
+    double yc = 0.0;
+    const bool worst = active && r >= lambda - mu;
+    const int i = lambda - 1 - r; // i-th worst
+    if (worst) {
+        const double top = norm_all[rank_idx[lambda - mu + i]];
+        const double bot = fmax(norm_all[rank_idx[lambda - 1 - i]], 1e-8);
+        yc = __ddiv_rn(top, bot);
+        ycoeff[i] = yc;
+    }
+    const int loc = rank_idx[r] - row0;
+    if (loc < 0 || loc >= lam_loc) return;
+    double c = 0.0, wm = 0.0;
+    if (r < mu) { wm = w[r]; c = __dmul_rn(cpos, w[r]); }
+    else if (worst) c = -__dmul_rn(__dmul_rn(cneg, w[i]), yc);
+    coef_loc[loc] = c;
+    wm_loc[loc] = wm;
+}
+
+// part[s][i] = sum over the local rows k of split s of wm[k] X[k][i]
+__global__ void __launch_bounds__(256) shard_mean_partial_kernel(double *__restrict__ part, const double *__restrict__ X,
+        int64_t ld, int n, int rows, int splits, const double *__restrict__ wm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= n) return;
+    const int per = (rows + splits - 1) / splits;
+    const int k0 = s * per, k1 = min(rows, k0 + per);
+    double am = 0.0;
+    for (int k = k0; k < k1; k++) {
+        const double wk = wm[k];
+        if (wk != 0.0) am = __dadd_rn(am, __dmul_rn(wk, X[(int64_t) k * ld + i]));
+    }
+    part[(int64_t) s * n + i] = am;
+}
+
+__global__ void __launch_bounds__(256) shard_mean_final_kernel(const double *__restrict__ part, int n, int splits,
+        double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sm = 0.0;
+    for (int s = 0; s < splits; s++) sm = __dadd_rn(sm, part[(int64_t) s * n + i]);
+    out[i] = sm;
+}
+
+// C (lower) <- decay C + c1 (pc pc^T + c2 C) + S, S = the all-reduced sum of the per-GPU rank-mu partials
+__global__ void __launch_bounds__(256) shard_cov_finish_kernel(double *__restrict__ C, const double *__restrict__ S, int64_t ld,
+        int n, const double *__restrict__ pc, double decay, double c1, const double *__restrict__ dscal) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (col > row || col >= n) return;
+    const double c2 = *dscal;
+    const int64_t o = (int64_t) row * ld + col;
+    const double old = C[o];
+    C[o] = (decay * old + c1 * (pc[row] * pc[col] + c2 * old)) + S[o];
+}
+
+// ------------------------------------------------------------------------------------------
 // eigen decomposition helpers
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) symmetrize_kernel(const double *__restrict__ C, double *__restrict__ V, int n,
@@ -445,24 +547,26 @@ static int refresh_basis_products(bbgpu_cma *h) {
 
 static int do_sample(bbgpu_cma *h, double sigma) {
     bbgpu_ctx *ctx = h->ctx;
+    h->last_sigma = sigma;
     ProfScope prof(ctx, h->full ? BBGPU_PROF_SAMPLE_GEMM : BBGPU_PROF_SEP_SAMPLE);
     const double *lo = h->cfg.bound ? h->lower : nullptr, *hi = h->cfg.bound ? h->upper : nullptr;
     if (!h->full) {
-        dim3 grid(ceil_div(h->n, 256), std::min(h->lambda, 64));
-        sep_sample_kernel<<<grid, 256, 0, ctx->stream>>>(h->X, h->Z, h->ldn, h->lambda, h->n, h->xmean, h->D, sigma, lo, hi);
+        dim3 grid(ceil_div(h->n, 256), std::min(h->lam_loc, 64));
+        sep_sample_kernel<<<grid, 256, 0, ctx->stream>>>(h->X, h->Z, h->ldn, h->lam_loc, h->n, h->xmean, h->D, sigma, lo, hi);
         return launched(ctx, "sep_sample_kernel");
     }
     // X[k][i] = m_i + sigma * sum_j Z[k][j] * (D_j Bt[j][i]), clipped in the epilogue
     GemmArgs g {};
     g.A = h->Z; g.lda = h->ldn; g.B = h->BDt; g.ldb = h->ldn;
-    g.M = h->lambda; g.N = h->n; g.K = h->n;
+    g.M = h->lam_loc; g.N = h->n; g.K = h->n;
     g.C = h->X; g.ldc = h->ldn; g.vec = h->xmean; g.lo = lo; g.hi = hi; g.s0 = sigma;
     return launch_gemm<1, EPI_SAMPLE>(ctx, g);
 }
 
 static int launch_philox(bbgpu_cma *h, cudaStream_t st, double *Z, uint64_t generation) {
-    const int64_t total = (int64_t) h->lambda * ((h->n + 1) / 2);
-    philox_normal_kernel<<<ceil_div(total, 256), 256, 0, st>>>(Z, h->ldn, h->lambda, h->n, 0, h->cfg.seed, generation, 0u);
+    // counters carry the GLOBAL candidate id: a sharded run draws exactly what the unsharded run draws
+    const int64_t total = (int64_t) h->lam_loc * ((h->n + 1) / 2);
+    philox_normal_kernel<<<ceil_div(total, 256), 256, 0, st>>>(Z, h->ldn, h->lam_loc, h->n, h->row0, h->cfg.seed, generation, 0u);
     return launched(h->ctx, "philox_normal_kernel");
 }
 
@@ -579,6 +683,106 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
     return launch_gemm<2, EPI_SYRK>(ctx, g);
 }
 
+// ---- candidate-sharded generation: the three local phases around the two exchange steps ----
+
+// after sampling: fitness of the local candidates into their slice of the full fitness array, the steps
+// Y = (X - m)/sigma, and (Active) the Mahalanobis norms of all local candidates
+static int shard_evaluate(bbgpu_cma *h, bbgpu_objective *obj) {
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    const int n = h->n;
+    if (h->last_sigma <= 0.0) return fail(BBGPU_ERR_ARG, "sharded evaluate needs a preceding sample()");
+    {
+        ProfScope prof(ctx, BBGPU_PROF_EVAL);
+        BB_TRY(evaluate(ctx, obj, h->X, h->ldn, h->lam_loc, h->fit + h->row0));
+    }
+    ProfScope prof(ctx, BBGPU_PROF_UPDATE_MISC);
+    dim3 grid(ceil_div(n, 256), std::min(h->lam_loc, 128));
+    shard_steps_kernel<<<grid, 256, 0, st>>>(h->Yloc, h->X, h->ldn, n, h->lam_loc, h->xmean, h->last_sigma);
+    BB_TRY(launched(ctx, "shard_steps_kernel"));
+    if (h->active) {
+        GemmArgs g {};
+        g.A = h->Yloc; g.lda = h->ldn; g.B = h->isC; g.ldb = h->ldn;
+        g.M = h->lam_loc; g.N = n; g.K = n; g.partial = h->rowsq_loc;
+        int tiles_n = 0;
+        BB_TRY((launch_gemm<1, EPI_ROWSQ>(ctx, g, &tiles_n)));
+        if (tiles_n > h->rowsq_loc_tiles) return fail(BBGPU_ERR_ARG, "rowsq partial buffer too small");
+        shard_norms_kernel<<<ceil_div(h->lam_loc, 256), 256, 0, st>>>(h->rowsq_loc, tiles_n, h->lam_loc, h->last_sigma,
+                h->norm_all + h->row0);
+        BB_TRY(launched(ctx, "shard_norms_kernel"));
+    }
+    return BBGPU_OK;
+}
+
+// exchange step 1: everybody gets every candidate's fitness (and Active norm)
+static int shard_exchange_fitness(bbgpu_cma *h) {
+    if (!h->comm) return fail(BBGPU_ERR_ARG, "sharded handle without a communicator: exchange BBGPU_CMA_FITNESS yourself");
+    ProfScope prof(h->ctx, BBGPU_PROF_COMM);
+    if (h->active) return comm_allgather2(h->comm, h->fit, h->norm_all, (size_t) h->lam_loc);
+    return comm_allgather(h->comm, h->fit, (size_t) h->lam_loc);
+}
+
+// after the (replicated) ranking: this GPU's share of sum w x and of the rank-mu (and active) sum
+static int shard_partial(bbgpu_cma *h) {
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    const bbgpu_cma_config &c = h->cfg;
+    const int n = h->n;
+    {
+        ProfScope prof(ctx, BBGPU_PROF_UPDATE_MISC);
+        const double cpos = h->active ? c.cmu + c.cneg * (1.0 - c.alphaold) : c.cmu;
+        shard_coef_kernel<<<ceil_div(h->lambda, 256), 256, 0, st>>>(h->rank_idx, h->lambda, h->mu, h->row0, h->lam_loc, h->weights,
+                h->active, cpos, c.cneg, h->norm_all, h->coef_loc, h->wm_loc, h->ycoeff);
+        BB_TRY(launched(ctx, "shard_coef_kernel"));
+        dim3 pgrid(ceil_div(n, 256), h->splits);
+        shard_mean_partial_kernel<<<pgrid, 256, 0, st>>>(h->part, h->X, h->ldn, n, h->lam_loc, h->splits, h->wm_loc);
+        BB_TRY(launched(ctx, "shard_mean_partial_kernel"));
+        shard_mean_final_kernel<<<ceil_div(n, 256), 256, 0, st>>>(h->part, n, h->splits, h->red + (size_t) n * h->ldn);
+        BB_TRY(launched(ctx, "shard_mean_final_kernel"));
+        BB_CUDA(cudaMemsetAsync(h->red, 0, (size_t) n * h->ldn * 8, st));
+    }
+    // S_local (lower) = sum_k coef_k y_k y_k^T over the local candidates (zero coefficient: not selected)
+    GemmArgs g {};
+    g.A = h->Yloc; g.lda = h->ldn; g.B = h->Yloc; g.ldb = h->ldn;
+    g.M = n; g.N = n; g.K = h->lam_loc; g.kscale = h->coef_loc; g.kscale_padded = true;
+    g.C = h->red; g.ldc = h->ldn; g.vec = h->pc; g.s0 = 0.0; g.s1 = 0.0; g.dscal = h->dscal;
+    ProfScope prof(ctx, BBGPU_PROF_COV_SYRK);
+    return launch_gemm<2, EPI_SYRK>(ctx, g);
+}
+
+// exchange step 2: sum of the partials over the GPUs (n*ldn covariance entries + the n-vector)
+static int shard_exchange_partials(bbgpu_cma *h) {
+    if (!h->comm) return fail(BBGPU_ERR_ARG, "sharded handle without a communicator: exchange BBGPU_CMA_SHARD_RED yourself");
+    ProfScope prof(h->ctx, BBGPU_PROF_COMM);
+    return comm_allreduce_sum(h->comm, h->red, (size_t) h->n * h->ldn + h->ldn);
+}
+
+// from the summed partials: mean, paths, covariance -- identical on every GPU
+static int shard_finish(bbgpu_cma *h, double sigma, int fev) {
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    const bbgpu_cma_config &c = h->cfg;
+    const int n = h->n;
+    const double *lo = c.bound ? h->lower : nullptr, *hi = c.bound ? h->upper : nullptr;
+    ProfScope prof(ctx, BBGPU_PROF_UPDATE_MISC);
+    BB_CUDA(cudaMemcpyAsync(h->xold, h->xmean, (size_t) n * 8, cudaMemcpyDeviceToDevice, st));
+    const double csc = std::sqrt(c.cs * (2.0 - c.cs) * c.mueff);
+    const double ccc = std::sqrt(c.cc * (2.0 - c.cc) * c.mueff);
+    const double denom = 1.0 - std::pow(1.0 - c.cs, 2.0 * fev / h->lambda); // cmaes.cpp:109
+    recombine_final_kernel<false><<<ceil_div(n, 256), 256, 0, st>>>(h->red + (size_t) n * h->ldn, n, 1, h->xmean, h->xold, h->dm,
+            c.cm, sigma, lo, hi, h->active, h->ps, nullptr, c.cs, csc, nullptr);
+    BB_TRY(launched(ctx, "recombine_final_kernel"));
+    ps_gemv_kernel<<<ceil_div(n, 8), 256, 0, st>>>(h->isC, h->ldn, n, h->dm, h->ps, c.cs, csc);
+    BB_TRY(launched(ctx, "ps_gemv_kernel"));
+    paths_kernel<false><<<1, 1024, 0, st>>>(n, h->ps, h->pc, h->dm, denom, c.chi, c.cc, ccc, h->dscal, h->d_report, nullptr,
+            nullptr, nullptr, 0.0, c.mueff, nullptr, h->weights, h->mu, c.cmu);
+    BB_TRY(launched(ctx, "paths_kernel"));
+    const double decay = h->active ? 1.0 - c.c1 - c.cmu + c.cneg * c.alphaold : 1.0 - c.c1 - c.cmu;
+    dim3 grid(ceil_div(n, 256), n);
+    shard_cov_finish_kernel<<<grid, 256, 0, st>>>(h->C, h->red, h->ldn, n, h->pc, decay, c.c1, h->dscal);
+    return launched(ctx, "shard_cov_finish_kernel");
+}
+
 static int do_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
     bbgpu_ctx *ctx = h->ctx;
     ProfScope prof(ctx, BBGPU_PROF_EIG);
@@ -638,8 +842,14 @@ static int field_info(bbgpu_cma *h, int field, double **ptr, int64_t *rows, int6
     case BBGPU_CMA_B:
         if (!h->full) return fail(BBGPU_ERR_ARG, "separable CMA-ES has no eigenbasis");
         *ptr = h->Bt; *rows = n; *cols = n; *ld = h->ldn; break;
-    case BBGPU_CMA_ARX: *ptr = h->X; *rows = h->lambda; *cols = n; *ld = h->ldn; break;
-    case BBGPU_CMA_Z: *ptr = h->Z; *rows = h->lambda; *cols = n; *ld = h->ldn; break;
+    case BBGPU_CMA_ARX: *ptr = h->X; *rows = h->lam_loc; *cols = n; *ld = h->ldn; break;
+    case BBGPU_CMA_Z: *ptr = h->Z; *rows = h->lam_loc; *cols = n; *ld = h->ldn; break;
+    case BBGPU_CMA_NORMS:
+        if (!(h->active && h->shards > 1)) return fail(BBGPU_ERR_ARG, "norms exist only for a sharded active CMA-ES");
+        *ptr = h->norm_all; *rows = 1; *cols = h->lambda; break;
+    case BBGPU_CMA_SHARD_RED:
+        if (h->shards <= 1) return fail(BBGPU_ERR_ARG, "not a sharded handle");
+        *ptr = h->red; *rows = 1; *cols = (int64_t) n * h->ldn + h->ldn; break;
     case BBGPU_CMA_FITNESS: *ptr = h->fit; *rows = 1; *cols = h->lambda; break;
     case BBGPU_CMA_RANKVAL: *ptr = h->rank_val; *rows = 1; *cols = h->lambda; break;
     case BBGPU_CMA_YCOEFF:
@@ -664,7 +874,12 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     BB_ARG(cfg->n >= 1 && cfg->lambda >= 2 && cfg->mu >= 1 && cfg->mu <= cfg->lambda);
     BB_ARG(cfg->kind >= BBGPU_CMA_FULL && cfg->kind <= BBGPU_CMA_SEP);
     BB_ARG(!cfg->bound || (h_lower && h_upper));
-    if (cfg->shard_count > 1) return fail(BBGPU_ERR_ARG, "candidate sharding is driven by bbgpu_cma_shard_* (not configured here)");
+    if (cfg->shard_count > 1) {
+        BB_ARG(cfg->shard_rank >= 0 && cfg->shard_rank < cfg->shard_count);
+        if (cfg->kind == BBGPU_CMA_SEP) return fail(BBGPU_ERR_ARG, "candidate sharding covers the full-covariance kinds");
+        if (cfg->lambda % cfg->shard_count != 0 || cfg->lambda / cfg->shard_count < 2)
+            return fail(BBGPU_ERR_ARG, "lambda = %d does not split into %d equal shards of at least 2", cfg->lambda, cfg->shard_count);
+    }
     BB_CUDA(cudaSetDevice(ctx->device));
     bbgpu_cma *h = new bbgpu_cma();
     h->ctx = ctx;
@@ -677,8 +892,12 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     h->nsel = h->active ? 2 * h->mu : h->mu;
     if (h->active && 2 * h->mu > h->lambda) { delete h; return fail(BBGPU_ERR_ARG, "active CMA-ES needs 2 mu <= lambda"); }
     h->ldn = round_up(h->n, 8);
+    h->shards = std::max(1, cfg->shard_count);
+    h->shard = h->shards > 1 ? cfg->shard_rank : 0;
+    h->lam_loc = h->lambda / h->shards;
+    h->row0 = h->shard * h->lam_loc;
     const int n = h->n;
-    const size_t ldn = (size_t) h->ldn, lam = (size_t) h->lambda;
+    const size_t ldn = (size_t) h->ldn, lam = (size_t) h->lambda, laml = (size_t) h->lam_loc;
     h->splits = std::max(1, std::min(128, std::min(h->nsel / 16, ceil_div(4 * ctx->sm_count, ceil_div(n, 256)))));
     int rc = BBGPU_OK;
     auto A = [&](double **p, size_t count) {
@@ -691,15 +910,24 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     A(&h->xmean, ldn); A(&h->xold, ldn); A(&h->pc, ldn); A(&h->ps, ldn); A(&h->D, ldn); A(&h->dm, ldn);
     A(&h->tmpn, ldn); A(&h->W, ldn); A(&h->weights, h->mu); A(&h->lower, ldn); A(&h->upper, ldn);
     A(&h->coef, (size_t) round_up(h->nsel, 32) + 32); A(&h->ycoeff, (size_t) h->mu); A(&h->dscal, 8);
-    A(&h->X, lam * ldn); A(&h->Zbuf[0], lam * ldn); A(&h->Zbuf[1], lam * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
+    A(&h->X, laml * ldn); A(&h->Zbuf[0], laml * ldn); A(&h->Zbuf[1], laml * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
     A(&h->part, (size_t) h->splits * 2 * n);
     if (h->full) {
         A(&h->C, (size_t) n * ldn); A(&h->Bt, (size_t) n * ldn); A(&h->BDt, (size_t) n * ldn);
         A(&h->BDit, (size_t) n * ldn); A(&h->isC, (size_t) n * ldn);
-        A(&h->Ysel, (size_t) h->nsel * ldn);
-        if (h->active) {
-            h->rowsq_tiles_cap = ceil_div(n, 64);
-            A(&h->rowsq_part, (size_t) h->rowsq_tiles_cap * h->mu);
+        if (h->shards > 1) {
+            A(&h->Yloc, laml * ldn); A(&h->coef_loc, (size_t) round_up(h->lam_loc, 32) + 32); A(&h->wm_loc, laml);
+            A(&h->red, (size_t) n * ldn + ldn);
+            if (h->active) {
+                h->rowsq_loc_tiles = ceil_div(n, 64);
+                A(&h->norm_all, lam); A(&h->rowsq_loc, (size_t) h->rowsq_loc_tiles * laml);
+            }
+        } else {
+            A(&h->Ysel, (size_t) h->nsel * ldn);
+            if (h->active) {
+                h->rowsq_tiles_cap = ceil_div(n, 64);
+                A(&h->rowsq_part, (size_t) h->rowsq_tiles_cap * h->mu);
+            }
         }
     } else {
         A(&h->C, ldn);
@@ -739,7 +967,7 @@ int bbgpu_cma_destroy(bbgpu_cma *h) {
     }
     double *bufs[] = { h->xmean, h->xold, h->pc, h->ps, h->D, h->dm, h->tmpn, h->W, h->weights, h->lower, h->upper, h->coef,
             h->ycoeff, h->dscal, h->X, h->Zbuf[0], h->Zbuf[1], h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
-            h->rowsq_part, h->solver_work, h->ssq };
+            h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc };
     for (double *b : bufs) if (b) cudaFree(b);
     if (h->rank_idx) cudaFree(h->rank_idx);
     if (h->dev_info) cudaFree(h->dev_info);
@@ -857,9 +1085,9 @@ int bbgpu_cma_device_ptr(bbgpu_cma *h, int field, void **d_ptr, int64_t *ld) {
 
 int bbgpu_cma_sample(bbgpu_cma *h, double sigma, uint64_t generation, const double *h_z) {
     BB_ARG(h);
-    if (h_z != nullptr) {
-        BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, h_z, (size_t) h->n * 8, (size_t) h->n * 8, h->lambda,
-                cudaMemcpyHostToDevice, h->ctx->stream));
+    if (h_z != nullptr) { // lambda*n draws; a sharded handle consumes its own candidates' rows
+        BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, h_z + (size_t) h->row0 * h->n, (size_t) h->n * 8, (size_t) h->n * 8,
+                h->lam_loc, cudaMemcpyHostToDevice, h->ctx->stream));
         h->zgen[h->zcur] = -1;
         return do_sample(h, sigma);
     }
@@ -870,14 +1098,18 @@ int bbgpu_cma_sample(bbgpu_cma *h, double sigma, uint64_t generation, const doub
 
 int bbgpu_cma_sample_dev(bbgpu_cma *h, double sigma, const double *d_z) {
     BB_ARG(h && d_z);
-    BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, d_z, (size_t) h->n * 8, (size_t) h->n * 8, h->lambda,
-            cudaMemcpyDeviceToDevice, h->ctx->stream));
+    BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, d_z + (size_t) h->row0 * h->n, (size_t) h->n * 8, (size_t) h->n * 8,
+            h->lam_loc, cudaMemcpyDeviceToDevice, h->ctx->stream));
     h->zgen[h->zcur] = -1;
     return do_sample(h, sigma);
 }
 
 int bbgpu_cma_evaluate(bbgpu_cma *h, bbgpu_objective *obj) {
     BB_ARG(h && obj && obj->n == h->n);
+    if (h->shards > 1) { // local slice, then (with a communicator) the fitness all-gather
+        BB_TRY(shard_evaluate(h, obj));
+        return h->comm ? shard_exchange_fitness(h) : BBGPU_OK;
+    }
     ProfScope prof(h->ctx, BBGPU_PROF_EVAL);
     return evaluate(h->ctx, obj, h->X, h->ldn, h->lambda, h->fit);
 }
@@ -889,7 +1121,51 @@ int bbgpu_cma_rank(bbgpu_cma *h, int ik) {
 
 int bbgpu_cma_update(bbgpu_cma *h, double sigma, int fev) {
     BB_ARG(h && sigma > 0.0);
+    if (h->shards > 1) {
+        if (!h->comm) return fail(BBGPU_ERR_ARG, "sharded handle without a communicator: use bbgpu_cma_shard_partial / _finish");
+        BB_TRY(shard_partial(h));
+        BB_TRY(shard_exchange_partials(h));
+        return shard_finish(h, sigma, fev);
+    }
     return do_update(h, sigma, fev);
+}
+
+int bbgpu_cma_attach_comm(bbgpu_cma *h, bbgpu_comm *comm) {
+    BB_ARG(h);
+    if (comm) {
+        if (h->shards <= 1) return fail(BBGPU_ERR_ARG, "the handle was not created with shard_count > 1");
+        BB_ARG(comm_ctx(comm) == h->ctx && comm_world(comm) == h->shards && comm_rank(comm) == h->shard);
+    }
+    h->comm = comm;
+    return BBGPU_OK;
+}
+
+int bbgpu_cma_shard_partial(bbgpu_cma *h) {
+    BB_ARG(h && h->shards > 1);
+    return shard_partial(h);
+}
+
+int bbgpu_cma_shard_finish(bbgpu_cma *h, double sigma, int fev) {
+    BB_ARG(h && h->shards > 1 && sigma > 0.0);
+    return shard_finish(h, sigma, fev);
+}
+
+// one candidate by GLOBAL index; on a sharded handle with a communicator every rank must call this
+// (the owner broadcasts the row)
+int bbgpu_cma_get_candidate(bbgpu_cma *h, int index, double *h_dst) {
+    BB_ARG(h && h_dst && index >= 0 && index < h->lambda);
+    cudaStream_t st = h->ctx->stream;
+    const int owner = index / h->lam_loc, loc = index - owner * h->lam_loc;
+    if (h->shards > 1 && h->comm) {
+        if (owner == h->shard) BB_CUDA(cudaMemcpyAsync(h->tmpn, h->X + (int64_t) loc * h->ldn, (size_t) h->n * 8, cudaMemcpyDeviceToDevice, st));
+        BB_TRY(comm_broadcast(h->comm, h->tmpn, (size_t) h->n, owner));
+        BB_CUDA(cudaMemcpyAsync(h_dst, h->tmpn, (size_t) h->n * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (owner != h->shard) return fail(BBGPU_ERR_ARG, "candidate %d lives on shard %d", index, owner);
+        BB_CUDA(cudaMemcpyAsync(h_dst, h->X + (int64_t) loc * h->ldn, (size_t) h->n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BBGPU_OK;
 }
 
 int bbgpu_cma_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
@@ -919,6 +1195,17 @@ int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint6
     BB_TRY(do_philox(h, generation));
     BB_TRY(do_sample(h, sigma));
     BB_TRY(prefetch_philox(h, generation));
+    if (h->shards > 1) {
+        // sample/evaluate the local candidates -> fitness all-gather -> replicated ranking -> local rank-mu
+        // partial -> all-reduce -> replicated paths and covariance; no host round trip
+        if (!h->comm) return fail(BBGPU_ERR_ARG, "sharded handle without a communicator");
+        BB_TRY(shard_evaluate(h, obj));
+        BB_TRY(shard_exchange_fitness(h));
+        BB_TRY(do_rank(h, ik));
+        BB_TRY(shard_partial(h));
+        BB_TRY(shard_exchange_partials(h));
+        return shard_finish(h, sigma, fev_after);
+    }
     {
         ProfScope prof(h->ctx, BBGPU_PROF_EVAL);
         BB_TRY(evaluate(h->ctx, obj, h->X, h->ldn, h->lambda, h->fit));

@@ -1,0 +1,193 @@
+// Communicator: one rank per GPU, NCCL over NVLink / NVSwitch for the two exchange steps of a
+// candidate-sharded CMA-ES run (fitness all-gather, rank-mu partial all-reduce) and for the
+// best-of reduce over independent runs.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2), not at link time: a process that already
+// loaded a libnccl (e.g. torch.distributed) shares that copy, and libbbgpu.so still loads on a
+// box without NCCL -- creating a communicator then fails loudly.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "common.cuh"
+
+struct bbgpu_comm {
+    bbgpu_ctx *ctx = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    double *d_pair = nullptr; // [2*world] scratch for best-of
+};
+
+namespace {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string why;
+};
+
+NcclApi &nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        const char *names[] = { "libnccl.so.2", "libnccl.so" };
+        for (const char *nm : names) {
+            a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (a.lib) break;
+        }
+        if (!a.lib) {
+            a.why = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "unknown");
+            return a;
+        }
+#define BB_SYM(field, name) \
+        a.field = (decltype(a.field)) dlsym(a.lib, name); \
+        if (!a.field && a.why.empty()) a.why = std::string("libnccl lacks ") + name;
+        BB_SYM(GetUniqueId, "ncclGetUniqueId")
+        BB_SYM(CommInitRank, "ncclCommInitRank")
+        BB_SYM(CommDestroy, "ncclCommDestroy")
+        BB_SYM(AllReduce, "ncclAllReduce")
+        BB_SYM(AllGather, "ncclAllGather")
+        BB_SYM(Broadcast, "ncclBroadcast")
+        BB_SYM(GroupStart, "ncclGroupStart")
+        BB_SYM(GroupEnd, "ncclGroupEnd")
+        BB_SYM(GetErrorString, "ncclGetErrorString")
+#undef BB_SYM
+        return a;
+    }();
+    return api;
+}
+
+int nccl_ready() {
+    NcclApi &a = nccl();
+    if (!a.why.empty()) return bb::fail(BBGPU_ERR_NODEVICE, "NCCL unavailable: %s", a.why.c_str());
+    return BBGPU_OK;
+}
+
+#define BB_NCCL(call)                                                                          \
+    do {                                                                                       \
+        ncclResult_t r__ = (call);                                                             \
+        if (r__ != ncclSuccess)                                                                \
+            return bb::fail(BBGPU_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,       \
+                            nccl().GetErrorString(r__));                                       \
+    } while (0)
+
+__global__ void best_pair_kernel(const double *f, double *pair, int rank) {
+    pair[0] = *f;
+    pair[1] = (double) rank;
+}
+
+} // namespace
+
+namespace bb {
+
+// used by the sharded CMA path (cma.cu); all on the ctx stream, in place
+int comm_allreduce_sum(bbgpu_comm *c, double *d_buf, size_t count) {
+    BB_NCCL(nccl().AllReduce(d_buf, d_buf, count, ncclFloat64, ncclSum, c->comm, c->ctx->stream));
+    return BBGPU_OK;
+}
+
+// every rank contributes d_buf[rank*per .. rank*per+per)
+int comm_allgather(bbgpu_comm *c, double *d_buf, size_t per) {
+    BB_NCCL(nccl().AllGather(d_buf + (size_t) c->rank * per, d_buf, per, ncclFloat64, c->comm, c->ctx->stream));
+    return BBGPU_OK;
+}
+
+int comm_allgather2(bbgpu_comm *c, double *d_a, double *d_b, size_t per) {
+    BB_NCCL(nccl().GroupStart());
+    BB_NCCL(nccl().AllGather(d_a + (size_t) c->rank * per, d_a, per, ncclFloat64, c->comm, c->ctx->stream));
+    BB_NCCL(nccl().AllGather(d_b + (size_t) c->rank * per, d_b, per, ncclFloat64, c->comm, c->ctx->stream));
+    BB_NCCL(nccl().GroupEnd());
+    return BBGPU_OK;
+}
+
+int comm_broadcast(bbgpu_comm *c, double *d_buf, size_t count, int root) {
+    BB_NCCL(nccl().Broadcast(d_buf, d_buf, count, ncclFloat64, root, c->comm, c->ctx->stream));
+    return BBGPU_OK;
+}
+
+int comm_rank(const bbgpu_comm *c) { return c->rank; }
+int comm_world(const bbgpu_comm *c) { return c->world; }
+bbgpu_ctx *comm_ctx(const bbgpu_comm *c) { return c->ctx; }
+
+} // namespace bb
+
+extern "C" {
+
+int bbgpu_comm_unique_id(void *out128) {
+    BB_ARG(out128);
+    BB_TRY(nccl_ready());
+    static_assert(sizeof(ncclUniqueId) == BBGPU_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    BB_NCCL(nccl().GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return BBGPU_OK;
+}
+
+int bbgpu_comm_create(bbgpu_ctx *ctx, int world, int rank, const void *id128, bbgpu_comm **out) {
+    BB_ARG(ctx && out && id128 && world >= 1 && rank >= 0 && rank < world);
+    *out = nullptr;
+    BB_TRY(nccl_ready());
+    BB_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    bbgpu_comm *c = new bbgpu_comm();
+    c->ctx = ctx; c->rank = rank; c->world = world;
+    ncclResult_t r = nccl().CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        return bb::fail(BBGPU_ERR_CUDA, "ncclCommInitRank -> %s", nccl().GetErrorString(r));
+    }
+    if (cudaMalloc((void**) &c->d_pair, (size_t) 2 * world * sizeof(double)) != cudaSuccess) {
+        nccl().CommDestroy(c->comm);
+        delete c;
+        return bb::fail(BBGPU_ERR_CUDA, "cudaMalloc failed");
+    }
+    *out = c;
+    return BBGPU_OK;
+}
+
+int bbgpu_comm_destroy(bbgpu_comm *c) {
+    if (!c) return BBGPU_OK;
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->comm) nccl().CommDestroy(c->comm);
+    if (c->d_pair) cudaFree(c->d_pair);
+    delete c;
+    return BBGPU_OK;
+}
+
+int bbgpu_comm_rank(bbgpu_comm *c) { return c ? c->rank : 0; }
+int bbgpu_comm_world(bbgpu_comm *c) { return c ? c->world : 1; }
+
+int bbgpu_comm_allreduce_sum(bbgpu_comm *c, double *d_buf, int64_t count) {
+    BB_ARG(c && d_buf && count >= 0);
+    return bb::comm_allreduce_sum(c, d_buf, (size_t) count);
+}
+
+// Best-of over independent runs: every rank passes the device scalar holding its best fitness; returns
+// (on every rank) the winning fitness and its rank, ties to the lowest rank, and broadcasts the winner's
+// n-vector d_x in place.
+int bbgpu_comm_best_of(bbgpu_comm *c, const double *d_f, double *d_x, int n, double *h_fbest, int *h_owner) {
+    BB_ARG(c && d_f && h_fbest && h_owner);
+    cudaStream_t st = c->ctx->stream;
+    best_pair_kernel<<<1, 1, 0, st>>>(d_f, c->d_pair + 2 * c->rank, c->rank);
+    BB_TRY(bb::launched(c->ctx, "best_pair_kernel"));
+    BB_NCCL(nccl().AllGather(c->d_pair + 2 * c->rank, c->d_pair, 2, ncclFloat64, c->comm, st));
+    std::vector<double> pairs((size_t) 2 * c->world);
+    BB_CUDA(cudaMemcpyAsync(pairs.data(), c->d_pair, pairs.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    int owner = 0;
+    for (int r = 1; r < c->world; r++)
+        if (pairs[2 * r] < pairs[2 * owner]) owner = r;
+    *h_fbest = pairs[2 * owner];
+    *h_owner = owner;
+    if (d_x && n > 0) BB_TRY(bb::comm_broadcast(c, d_x, (size_t) n, owner));
+    return BBGPU_OK;
+}
+
+} // extern "C"

@@ -72,7 +72,8 @@ enum bbgpu_profile_tag {
     BBGPU_PROF_SEP_SAMPLE = 8,
     BBGPU_PROF_DE_ROUND = 9,
     BBGPU_PROF_DE_MISC = 10,
-    BBGPU_PROF_TAGS = 11
+    BBGPU_PROF_COMM = 11,       /* NCCL exchange steps of a sharded run    */
+    BBGPU_PROF_TAGS = 12
 };
 int bbgpu_ctx_profile_enable(bbgpu_ctx *ctx, int on);
 /* synchronises, then returns summed device milliseconds and number of timed launches for tag */
@@ -145,7 +146,11 @@ enum bbgpu_cma_field {
     BBGPU_CMA_FITNESS = 10, /* lambda, fitness by candidate index */
     BBGPU_CMA_RANKVAL = 11, /* lambda, fitness ascending */
     BBGPU_CMA_YCOEFF = 12,  /* mu (active) */
-    BBGPU_CMA_WEIGHTS = 13  /* mu */
+    BBGPU_CMA_WEIGHTS = 13, /* mu */
+    /* candidate-sharded handles only (the two buffers the exchange steps move) */
+    BBGPU_CMA_NORMS = 14,     /* lambda, ||C^-1/2 (x_k - m)||^2 by candidate index (active) */
+    BBGPU_CMA_SHARD_RED = 15  /* n*ld + ld: this GPU's rank-mu partial (lower triangle, row pitch
+                                 ld = ceil(n/8)*8) followed by its partial sum_k w_k x_k */
 };
 
 /* everything the host class needs back per generation; filled by bbgpu_cma_fetch */
@@ -207,6 +212,35 @@ int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *out);
  * update); used by bench.py and by the host classes' fast path */
 int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint64_t generation,
                          int ik, int fev_after);
+
+/* ---- one large-lambda run sharded by candidates over several GPUs.
+ * Create every rank's handle with cfg.shard_count = world, cfg.shard_rank = rank: state is
+ * replicated, the handle samples and evaluates candidates [rank*lambda/world, (rank+1)*lambda/world)
+ * from Philox counters keyed by the GLOBAL candidate id, and BBGPU_CMA_ARX / _Z hold only those
+ * rows.  With a communicator attached, bbgpu_cma_evaluate ends with the fitness all-gather,
+ * bbgpu_cma_update = local partial -> all-reduce -> replicated finish, and bbgpu_cma_generation
+ * runs the whole generation without a host round trip.  Without one (single-GPU tests, custom
+ * transports) the caller exchanges BBGPU_CMA_FITNESS (+ _NORMS) after evaluate and sums
+ * BBGPU_CMA_SHARD_RED between bbgpu_cma_shard_partial and bbgpu_cma_shard_finish. */
+#define BBGPU_COMM_ID_BYTES 128
+typedef struct bbgpu_comm bbgpu_comm;
+/* rank 0 creates the id and hands the 128 bytes to the other ranks (any side channel) */
+int bbgpu_comm_unique_id(void *out128);
+int bbgpu_comm_create(bbgpu_ctx *ctx, int world, int rank, const void *id128, bbgpu_comm **out);
+int bbgpu_comm_destroy(bbgpu_comm *comm);
+int bbgpu_comm_rank(bbgpu_comm *comm);
+int bbgpu_comm_world(bbgpu_comm *comm);
+int bbgpu_comm_allreduce_sum(bbgpu_comm *comm, double *d_buf, int64_t count);
+/* best-of reduce over independent runs (ipop_cmaes.cpp:150-158 keeps the best run): d_f = device
+ * scalar with this rank's best fitness, d_x = its n-vector (overwritten with the winner's) */
+int bbgpu_comm_best_of(bbgpu_comm *comm, const double *d_f, double *d_x, int n, double *h_fbest,
+                       int *h_owner);
+int bbgpu_cma_attach_comm(bbgpu_cma *h, bbgpu_comm *comm);
+int bbgpu_cma_shard_partial(bbgpu_cma *h);
+int bbgpu_cma_shard_finish(bbgpu_cma *h, double sigma, int fev);
+/* candidate by GLOBAL index (bestSolution(), cma/base_cmaes.cpp:232-238); collective on a sharded
+ * handle with a communicator */
+int bbgpu_cma_get_candidate(bbgpu_cma *h, int index, double *h_dst);
 
 /* ---- standalone fp64 tensor-core kernels, host-buffer form (unit tests, peak probes) */
 /* C[M,N] = A[M,K] * B[K,N], all row-major */

@@ -89,5 +89,16 @@ int bbgpu_de_get_archive(bbgpu_de *, double *, int *rows) { *rows = 0; return 0;
 int bbgpu_de_get_memory(bbgpu_de *, double *, double *) { return 0; }
 int bbgpu_de_get_trace(bbgpu_de *, int32_t *, double *, double *, double *) { return 0; }
 int bbgpu_de_phase_times(bbgpu_de *, uint64_t *) { return 0; }
+int bbgpu_comm_unique_id(void *) { return 0; }
+int bbgpu_comm_create(bbgpu_ctx *, int, int, const void *, bbgpu_comm **) { return 0; }
+int bbgpu_comm_destroy(bbgpu_comm *) { return 0; }
+int bbgpu_comm_rank(bbgpu_comm *) { return 0; }
+int bbgpu_comm_world(bbgpu_comm *) { return 1; }
+int bbgpu_comm_allreduce_sum(bbgpu_comm *, double *, int64_t) { return 0; }
+int bbgpu_comm_best_of(bbgpu_comm *, const double *, double *, int, double *, int *) { return 0; }
+int bbgpu_cma_attach_comm(bbgpu_cma *, bbgpu_comm *) { return 0; }
+int bbgpu_cma_shard_partial(bbgpu_cma *) { return 0; }
+int bbgpu_cma_shard_finish(bbgpu_cma *, double, int) { return 0; }
+int bbgpu_cma_get_candidate(bbgpu_cma *, int, double *) { return 0; }
 int bbgpu_de_generation_batch(bbgpu_de *const *, int, bbgpu_objective *, bbgpu_de_report *) { return 0; }
 }

@@ -1,0 +1,89 @@
+"""NCCL transport of the candidate-sharded CMA-ES run: launched with one process per GPU
+(`python -m torch.distributed.run --nproc-per-node G tests/multi_gpu_shard.py`), needs G >= 2 GPUs.
+
+Every rank also steps the UNSHARDED handle with the same Philox seed: draws, fitness and ranking must be
+bit-identical, mean / paths / covariance within 1e-10, and the replicated state bit-identical across ranks."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from bboptpy_b200 import _cabi, strategy  # noqa: E402
+from util import assert_close, update_sigma_host  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _cabi.Context(local)
+    ids = [_cabi.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm = _cabi.Comm(ctx, world, rank, ids[0])
+    for kind in (_cabi.CMA_FULL, _cabi.CMA_ACTIVE):
+        n, lam = 96, 64 * world
+        w, consts = strategy.cma_constants(kind, n, lam)
+        st = consts
+        obj = _cabi.Objective(ctx, n, builtin=_cabi.OBJ_ROSENBROCK)
+        guess = np.linspace(-3, 3, n)
+        one = _cabi.Cma(ctx, kind, n, lam, w, consts, seed=2024)
+        sh = _cabi.Cma(ctx, kind, n, lam, w, consts, seed=2024, shard=(rank, world))
+        sh.attach_comm(comm)
+        one.reset(guess)
+        sh.reset(guess)
+        sigma1 = sigma2 = 2.0
+        fev, ik, ll = 0, st["ik"], lam // world
+        lower = np.tril_indices(n)
+        for gen in range(8):
+            fev += lam
+            one.generation(obj, sigma1, gen, ik, fev)
+            sh.generation(obj, sigma2, gen, ik, fev)
+            r1, r2 = one.fetch(), sh.fetch()
+            assert np.array_equal(sh.get(_cabi.F_ARX), one.get(_cabi.F_ARX)[rank * ll:(rank + 1) * ll]), "draws / sample rows"
+            assert np.array_equal(sh.get(_cabi.F_FITNESS), one.get(_cabi.F_FITNESS)), "all-gathered fitness"
+            assert np.array_equal(sh.rank_idx(), one.rank_idx()), "ranking"
+            assert list(r1.ibw) == list(r2.ibw) and r1.hsig == r2.hsig
+            assert_close(sh.get(_cabi.F_XMEAN), one.get(_cabi.F_XMEAN), what="xmean")
+            assert_close(sh.get(_cabi.F_PS), one.get(_cabi.F_PS), what="ps")
+            assert_close(sh.get(_cabi.F_PC), one.get(_cabi.F_PC), what="pc")
+            assert_close(sh.get(_cabi.F_C)[lower], one.get(_cabi.F_C)[lower], what="C")
+            # replicated state must be bit-identical on every rank
+            mine = torch.from_numpy(np.concatenate([sh.get(_cabi.F_C).ravel(), sh.get(_cabi.F_XMEAN)])).cuda()
+            ref = mine.clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(mine, ref), "replicated state diverged between ranks"
+            best = sh.candidate(int(r2.ibw[0]))
+            assert np.array_equal(best, one.get(_cabi.F_ARX)[int(r1.ibw[0])])
+            sigma1 = update_sigma_host(sigma1, r1.pslen, consts["cs"], st["damps"], consts["chi"], r1.ybw[0], r1.f_kth, gen, 10 ** 9, 0.0, 1.0)
+            sigma2 = update_sigma_host(sigma2, r2.pslen, consts["cs"], st["damps"], consts["chi"], r2.ybw[0], r2.f_kth, gen, 10 ** 9, 0.0, 1.0)
+            one.eig()
+            sh.eig()
+            # continue the sharded run from the unsharded state: rounding differences must not reach the ranking
+            for f in (_cabi.F_XMEAN, _cabi.F_PC, _cabi.F_PS, _cabi.F_C):
+                sh.set(f, one.get(f))
+            sh.eig()
+            sigma2 = sigma1
+        if rank == 0:
+            print("sharded", "active" if kind == _cabi.CMA_ACTIVE else "vanilla", "over", world, "GPUs: ok", flush=True)
+    # best-of reduce
+    f_dev = torch.tensor([10.0 - rank if rank != 1 else -5.0], dtype=torch.float64, device="cuda")
+    x_dev = torch.full((7,), float(rank), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    fb, owner = comm.best_of(f_dev.data_ptr(), x_dev.data_ptr(), 7)
+    exp_owner = 1 if world > 1 else 0
+    assert owner == exp_owner and fb == (-5.0 if world > 1 else 10.0), (fb, owner)
+    ctx.sync()
+    assert torch.equal(x_dev.cpu(), torch.full((7,), float(exp_owner), dtype=torch.float64))
+    if rank == 0:
+        print("best-of reduce: ok", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
