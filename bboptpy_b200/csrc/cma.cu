@@ -133,6 +133,80 @@ __global__ void __launch_bounds__(256) sep_sample_kernel(double *__restrict__ X,
     }
 }
 
+// SepCmaes with free-running draws, the whole sample -> evaluate front of the generation in ONE pass:
+// Philox block -> Box-Muller pair -> x = m + sigma d z (clipped) -> X written once (16-byte stores) -> objective.
+// One CTA (8 warps) per candidate: the warps share the Philox / Box-Muller work of a 1024-column tile (lane l of a warp
+// owns columns 2l, 2l+1 of a 64-column block) and stage the objective terms in shared memory; warp 0 then adds them in
+// the objective's fixed order (lane a: term(i) for i = a, a + 32, ... ascending; objectives.cuh) while the other warps
+// already work on the next tile, so the fitness bits equal eval_rows_kernel's on the same X.  HBM traffic: 8 n bytes
+// per candidate, the algorithmic minimum (the draws never touch memory).  Objectives whose terms read a neighbour
+// coordinate (Rosenbrock) take the unfused path.
+constexpr int SEP_TILE = 1024;
+
+template<int ID>
+__global__ void __launch_bounds__(256) sep_sample_eval_kernel(double *__restrict__ X, int64_t ld, int rows, int n, int row0,
+        const double *__restrict__ m, const double *__restrict__ d, double sigma, const double *__restrict__ lo,
+        const double *__restrict__ hi, const double *__restrict__ aux, uint64_t seed, uint64_t generation,
+        double *__restrict__ f) {
+    constexpr int NB = ID == BBGPU_OBJ_ACKLEY ? 2 : 1;
+    __shared__ __align__(16) double T[2][NB][SEP_TILE];
+    const int k = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool clip = lo != nullptr;
+    double *xrow = X + (int64_t) k * ld;
+    double acc = 0.0, acc2 = 0.0;
+    int buf = 0;
+    for (int tile0 = 0; tile0 < n; tile0 += SEP_TILE, buf ^= 1) {
+        const int tl = min(SEP_TILE, n - tile0);
+        for (int j = warp; 64 * j < tl; j += 16) {
+            // two 64-column blocks (j and j + 8) per trip: two independent Philox -> Box-Muller chains in flight per lane
+            int c[2];
+            bool ok[2];
+            double z[2][2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                c[u] = tile0 + 64 * (j + 8 * u) + 2 * lane;
+                ok[u] = 64 * (j + 8 * u) < tl && c[u] < n;
+                const Philox4 r = philox4x32_10((uint32_t) (c[u] >> 1), (uint32_t) (row0 + k), (uint32_t) generation,
+                        (uint32_t) (generation >> 32), (uint32_t) seed, (uint32_t) (seed >> 32));
+                normal_pair(r, z[u][0], z[u][1]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (!ok[u]) continue;
+                const int c0 = c[u];
+                const bool two = c0 + 1 < n;
+                double x0 = __dadd_rn(m[c0], __dmul_rn(__dmul_rn(sigma, d[c0]), z[u][0]));
+                double x1 = two ? __dadd_rn(m[c0 + 1], __dmul_rn(__dmul_rn(sigma, d[c0 + 1]), z[u][1])) : 0.0;
+                if (clip) {
+                    x0 = fmax(lo[c0], fmin(x0, hi[c0]));
+                    if (two) x1 = fmax(lo[c0 + 1], fmin(x1, hi[c0 + 1]));
+                }
+                if (two) *reinterpret_cast<double2*>(xrow + c0) = make_double2(x0, x1); // c0 even, ld multiple of 8
+                else xrow[c0] = x0;
+                double e0 = 0.0, e1 = 0.0;
+                const double t0 = obj_term(ID, x0, 0.0, ID == BBGPU_OBJ_ELLIPSOID ? aux[c0] : 0.0, e0);
+                const double t1 = two ? obj_term(ID, x1, 0.0, ID == BBGPU_OBJ_ELLIPSOID ? aux[c0 + 1] : 0.0, e1) : 0.0;
+                *reinterpret_cast<double2*>(&T[buf][0][c0 - tile0]) = make_double2(t0, t1);
+                if (ID == BBGPU_OBJ_ACKLEY) *reinterpret_cast<double2*>(&T[buf][NB - 1][c0 - tile0]) = make_double2(e0, e1);
+            }
+        }
+        __syncthreads();
+        if (warp == 0) { // tile0 is a multiple of 32: lane a keeps adding the terms of its residue class, ascending
+            for (int q = lane; q < tl; q += 32) {
+                acc = add(acc, T[buf][0][q]);
+                if (ID == BBGPU_OBJ_ACKLEY) acc2 = add(acc2, T[buf][NB - 1][q]);
+            }
+        }
+        // the buffer written two tiles from now is this one: warp 0 is past the next barrier by then
+    }
+    if (warp == 0) {
+        const double s1 = warp_sum(acc);
+        const double s2 = ID == BBGPU_OBJ_ACKLEY ? warp_sum(acc2) : 0.0;
+        if (lane == 0) f[k] = obj_finish(ID, n, s1, s2);
+    }
+}
+
 // BDt[j][i] = D[j] Bt[j][i],  BDit[j][i] = Bt[j][i] / D[j]
 __global__ void __launch_bounds__(256) scale_basis_kernel(const double *__restrict__ Bt, const double *__restrict__ D,
         double *__restrict__ BDt, double *__restrict__ BDit, int n, int64_t ld) {
@@ -208,6 +282,7 @@ __global__ void __launch_bounds__(256) recombine_partial_kernel(double *__restri
     const int k0 = s * per, k1 = min(mu, k0 + per);
     double am = 0.0, ac = 0.0;
     const double mo = SEP ? mold[i] : 0.0;
+#pragma unroll 8
     for (int k = k0; k < k1; k++) {
         const double x = X[(int64_t) rank_idx[k] * ld + i];
         const double wk = w[k];
@@ -229,13 +304,23 @@ __global__ void __launch_bounds__(256) recombine_final_kernel(const double *__re
         double *__restrict__ xmean, const double *__restrict__ xold, double *__restrict__ dm, double cm, double sigma,
         const double *__restrict__ lo, const double *__restrict__ hi, bool active, double *__restrict__ ps,
         const double *__restrict__ Cdiag, double cs, double csc, double *__restrict__ tmpn) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    // 8 columns per warp: lanes = 4 split groups x 8 columns, so a warp reads 64-byte row segments of `part`
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int i = warp * 8 + (lane & 7), sg = lane >> 3;
     double sm = 0.0, sc = 0.0;
-    for (int s = 0; s < splits; s++) {
-        sm = __dadd_rn(sm, part[((int64_t) s * 2 + 0) * n + i]);
-        if (SEP) sc = __dadd_rn(sc, part[((int64_t) s * 2 + 1) * n + i]);
+    if (i < n) {
+        for (int s = sg; s < splits; s += 4) {
+            sm = __dadd_rn(sm, part[((int64_t) s * 2 + 0) * n + i]);
+            if (SEP) sc = __dadd_rn(sc, part[((int64_t) s * 2 + 1) * n + i]);
+        }
     }
+    sm = __dadd_rn(sm, __shfl_xor_sync(0xffffffffu, sm, 8));
+    sm = __dadd_rn(sm, __shfl_xor_sync(0xffffffffu, sm, 16));
+    if (SEP) {
+        sc = __dadd_rn(sc, __shfl_xor_sync(0xffffffffu, sc, 8));
+        sc = __dadd_rn(sc, __shfl_xor_sync(0xffffffffu, sc, 16));
+    }
+    if (i >= n || sg != 0) return;
     const double mo = xold[i];
     double mn = active ? __dadd_rn(__dmul_rn(mo, 1.0 - cm), __dmul_rn(sm, cm)) : sm;
     if (lo != nullptr) mn = fmax(lo[i], fmin(mn, hi[i]));
@@ -248,17 +333,27 @@ __global__ void __launch_bounds__(256) recombine_final_kernel(const double *__re
     }
 }
 
-// p_sigma <- (1-cs) p_sigma + csc C^-1/2 dm   (cmaes.cpp:99-105); one warp per row
+// p_sigma <- (1-cs) p_sigma + csc C^-1/2 dm   (cmaes.cpp:99-105); 4 warps per row, 2 rows per CTA
 __global__ void __launch_bounds__(256) ps_gemv_kernel(const double *__restrict__ isC, int64_t ld, int n,
         const double *__restrict__ dm, double *__restrict__ ps, double cs, double csc) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= n) return;
-    const int lane = threadIdx.x & 31;
-    const double *a = isC + (int64_t) row * ld;
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * 2 + (warp >> 2), q = warp & 3;
     double acc = 0.0;
-    for (int j = lane; j < n; j += 32) acc = fma(a[j], dm[j], acc);
+    if (row < n) {
+        const double *a = isC + (int64_t) row * ld;
+        for (int j = q * 32 + lane; j < n; j += 128) acc = fma(a[j], dm[j], acc);
+    }
     acc = warp_sum(acc);
-    if (lane == 0) ps[row] = __dadd_rn(__dmul_rn(ps[row], 1.0 - cs), __dmul_rn(csc, acc));
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const int r = blockIdx.x * 2 + threadIdx.x;
+        if (r < n) {
+            const double t = ((red[4 * threadIdx.x] + red[4 * threadIdx.x + 1]) + red[4 * threadIdx.x + 2]) + red[4 * threadIdx.x + 3];
+            ps[r] = __dadd_rn(__dmul_rn(ps[r], 1.0 - cs), __dmul_rn(csc, t));
+        }
+    }
 }
 
 // ||p_sigma||, hsig, p_c (cmaes.cpp:107-122); sep also finishes c_i, d_i (sep_cmaes.cpp:118-131).
@@ -273,6 +368,7 @@ __global__ void __launch_bounds__(1024) paths_kernel(int n, const double *__rest
     if (coef != nullptr)
         for (int k = threadIdx.x; k < mu; k += blockDim.x) coef[k] = __dmul_rn(cmu, w[k]);
     double s = 0.0;
+#pragma unroll 4
     for (int i = threadIdx.x; i < n; i += blockDim.x) s = fma(ps[i], ps[i], s);
     s = block_sum(s, red);
     const double pslen = sqrt(s);
@@ -282,6 +378,7 @@ __global__ void __launch_bounds__(1024) paths_kernel(int n, const double *__rest
         rep->hsig = hsig;
         *dscal = (1.0 - hsig) * cc * (2.0 - cc);
     }
+#pragma unroll 4
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double p = __dadd_rn(__dmul_rn(1.0 - cc, pc[i]), __dmul_rn(__dmul_rn((double) hsig, ccc), dm[i]));
         pc[i] = p;
@@ -634,7 +731,7 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
         recombine_partial_kernel<true><<<pgrid, 256, 0, st>>>(h->part, h->X, h->ldn, n, mu, h->splits, h->rank_idx,
                 h->weights, h->xold, sigma);
         BB_TRY(launched(ctx, "recombine_partial_kernel<sep>"));
-        recombine_final_kernel<true><<<ceil_div(n, 256), 256, 0, st>>>(h->part, n, h->splits, h->xmean, h->xold, h->dm, 1.0,
+        recombine_final_kernel<true><<<ceil_div(n, 64), 256, 0, st>>>(h->part, n, h->splits, h->xmean, h->xold, h->dm, 1.0,
                 sigma, lo, hi, false, h->ps, h->C, c.cs, csc, h->tmpn);
         BB_TRY(launched(ctx, "recombine_final_kernel<sep>"));
         paths_kernel<true><<<1, 1024, 0, st>>>(n, h->ps, h->pc, h->dm, denom, c.chi, c.cc, ccc, h->dscal, h->d_report, h->C,
@@ -644,10 +741,10 @@ static int do_update(bbgpu_cma *h, double sigma, int fev) {
     select_steps_kernel<<<pgrid, 256, 0, st>>>(h->part, h->Ysel, h->X, h->ldn, n, mu, h->nsel, h->lambda, h->splits,
             h->rank_idx, h->weights, h->xold, sigma);
     BB_TRY(launched(ctx, "select_steps_kernel"));
-    recombine_final_kernel<false><<<ceil_div(n, 256), 256, 0, st>>>(h->part, n, h->splits, h->xmean, h->xold, h->dm, c.cm,
+    recombine_final_kernel<false><<<ceil_div(n, 64), 256, 0, st>>>(h->part, n, h->splits, h->xmean, h->xold, h->dm, c.cm,
             sigma, lo, hi, h->active, h->ps, nullptr, c.cs, csc, nullptr);
     BB_TRY(launched(ctx, "recombine_final_kernel"));
-    ps_gemv_kernel<<<ceil_div(n, 8), 256, 0, st>>>(h->isC, h->ldn, n, h->dm, h->ps, c.cs, csc);
+    ps_gemv_kernel<<<ceil_div(n, 2), 256, 0, st>>>(h->isC, h->ldn, n, h->dm, h->ps, c.cs, csc);
     BB_TRY(launched(ctx, "ps_gemv_kernel"));
     paths_kernel<false><<<1, 1024, 0, st>>>(n, h->ps, h->pc, h->dm, denom, c.chi, c.cc, ccc, h->dscal, h->d_report, nullptr,
             nullptr, nullptr, 0.0, c.mueff, h->active ? nullptr : h->coef, h->weights, mu, c.cmu);
@@ -769,10 +866,10 @@ static int shard_finish(bbgpu_cma *h, double sigma, int fev) {
     const double csc = std::sqrt(c.cs * (2.0 - c.cs) * c.mueff);
     const double ccc = std::sqrt(c.cc * (2.0 - c.cc) * c.mueff);
     const double denom = 1.0 - std::pow(1.0 - c.cs, 2.0 * fev / h->lambda); // cmaes.cpp:109
-    recombine_final_kernel<false><<<ceil_div(n, 256), 256, 0, st>>>(h->red + (size_t) n * h->ldn, n, 1, h->xmean, h->xold, h->dm,
+    recombine_final_kernel<false><<<ceil_div(n, 64), 256, 0, st>>>(h->red + (size_t) n * h->ldn, n, 1, h->xmean, h->xold, h->dm,
             c.cm, sigma, lo, hi, h->active, h->ps, nullptr, c.cs, csc, nullptr);
     BB_TRY(launched(ctx, "recombine_final_kernel"));
-    ps_gemv_kernel<<<ceil_div(n, 8), 256, 0, st>>>(h->isC, h->ldn, n, h->dm, h->ps, c.cs, csc);
+    ps_gemv_kernel<<<ceil_div(n, 2), 256, 0, st>>>(h->isC, h->ldn, n, h->dm, h->ps, c.cs, csc);
     BB_TRY(launched(ctx, "ps_gemv_kernel"));
     paths_kernel<false><<<1, 1024, 0, st>>>(n, h->ps, h->pc, h->dm, denom, c.chi, c.cc, ccc, h->dscal, h->d_report, nullptr,
             nullptr, nullptr, 0.0, c.mueff, nullptr, h->weights, h->mu, c.cmu);
@@ -898,7 +995,7 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     h->row0 = h->shard * h->lam_loc;
     const int n = h->n;
     const size_t ldn = (size_t) h->ldn, lam = (size_t) h->lambda, laml = (size_t) h->lam_loc;
-    h->splits = std::max(1, std::min(128, std::min(h->nsel / 16, ceil_div(4 * ctx->sm_count, ceil_div(n, 256)))));
+    h->splits = std::max(1, std::min(128, std::min(h->nsel / 16, ceil_div(16 * ctx->sm_count, ceil_div(n, 256)))));
     int rc = BBGPU_OK;
     auto A = [&](double **p, size_t count) {
         if (rc != BBGPU_OK) return;
@@ -1192,6 +1289,28 @@ int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *out) {
 
 int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint64_t generation, int ik, int fev_after) {
     BB_ARG(h && obj && obj->n == h->n);
+    if (!h->full && obj->mode == 0 && obj->id != BBGPU_OBJ_ROSENBROCK) {
+        // separable kind, registry objective: draws, sampling and evaluation fused into one pass over X
+        bbgpu_ctx *ctx = h->ctx;
+        const double *lo = h->cfg.bound ? h->lower : nullptr, *hi = h->cfg.bound ? h->upper : nullptr;
+        const int grid = h->lam_loc;
+        h->last_sigma = sigma;
+        h->zgen[0] = h->zgen[1] = -1; // Z is not materialised on this path
+        obj->evals += h->lam_loc;
+        {
+            ProfScope prof(ctx, BBGPU_PROF_SEP_SAMPLE);
+#define BB_SEP_CASE(ID) case ID: sep_sample_eval_kernel<ID><<<grid, 256, 0, ctx->stream>>>(h->X, h->ldn, h->lam_loc, h->n, h->row0, \
+            h->xmean, h->D, sigma, lo, hi, obj->d_aux, h->cfg.seed, generation, h->fit); break;
+            switch (obj->id) {
+            BB_SEP_CASE(BBGPU_OBJ_SPHERE) BB_SEP_CASE(BBGPU_OBJ_ELLIPSOID) BB_SEP_CASE(BBGPU_OBJ_RASTRIGIN) BB_SEP_CASE(BBGPU_OBJ_ACKLEY)
+            default: return fail(BBGPU_ERR_ARG, "unknown registry objective %d", obj->id);
+            }
+#undef BB_SEP_CASE
+            BB_TRY(launched(ctx, "sep_sample_eval_kernel"));
+        }
+        BB_TRY(do_rank(h, ik));
+        return do_update(h, sigma, fev_after);
+    }
     BB_TRY(do_philox(h, generation));
     BB_TRY(do_sample(h, sigma));
     BB_TRY(prefetch_philox(h, generation));

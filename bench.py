@@ -34,6 +34,9 @@ sys.path.insert(0, ROOT)
 
 N_DIM, LAMBDA, BOX = 1000, 4096, 10.0
 DE_N, DE_NP, DE_BOX = 1000, 1000, 5.12
+DE_BATCH = 16          # independent DE runs per launch for the HBM-resident figure
+SEP_N = 10000          # BASELINE config 3
+SHARD_LAMBDA = 16384   # BASELINE config 4
 METRIC = "CMA-ES generations/s (n=1000, lambda=4096)"
 UNIT = "generations/s"
 WORKLOAD = "Cmaes n=1000 lambda=4096 mu=2048 Rosenbrock box=[-10,10]^n fp64 (BASELINE.json metric config)"
@@ -322,6 +325,105 @@ def bench_de_device(ctx, kind, steps, warmup, seed):
             "round_kernel_ms_avg": prof.get("de_round", {}).get("ms_avg"), "fbest": rep.fbest}
 
 
+def bench_de_batched(ctx, kind, runs, steps, warmup, seed):
+    """R independent runs (same configuration, their own Philox seeds) per launch: the rows of all runs stream
+    through one cooperative kernel, so the working set (R x 32 MB) is HBM resident, not L2 resident."""
+    from bboptpy_b200 import _cabi
+    lo, hi = -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N)
+    obj = _cabi.Objective(ctx, DE_N, builtin=_cabi.OBJ_RASTRIGIN)
+    gs = [_cabi.De(ctx, kind, DE_N, DE_NP, lo, hi, mfev=10 ** 7, seed=seed + 1000 * r) for r in range(runs)]
+    for g in gs:
+        g.init(obj)
+    for _ in range(warmup):
+        _cabi.De.generation_batch(gs, obj, want_report=False)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(steps):
+        _cabi.De.generation_batch(gs, obj, want_report=False)
+    ms = ctx.timer_stop()
+    reps = _cabi.De.generation_batch(gs, obj)
+    return {"runs": runs, "evals_per_s": runs * DE_NP * steps / (ms * 1e-3), "ms_per_generation": ms / steps,
+            "rounds_last": int(reps[0].rounds), "fbest_min": float(min(r.fbest for r in reps)),
+            "working_set_mb": runs * 4 * DE_NP * DE_N * 8 / 1e6}
+
+
+def bench_sep_device(ctx, steps, warmup, seed):
+    """BASELINE config 3: separable CMA-ES, n = 10^4, lambda = 4096, Ellipsoid: the bandwidth-bound path."""
+    from bboptpy_b200 import _cabi
+    from bboptpy_b200.strategy import cma_constants, update_sigma
+    n, lam = SEP_N, LAMBDA
+    w, c = cma_constants(2, n, lam)
+    rng = np.random.default_rng(seed)
+    guess = rng.uniform(-BOX, BOX, n)
+    g = _cabi.Cma(ctx, _cabi.CMA_SEP, n, lam, w, c, seed=seed)
+    g.reset(guess)
+    obj = _cabi.Objective(ctx, n, builtin=_cabi.OBJ_ELLIPSOID)
+    state = {"sigma": 2.0, "fev": 0, "gen": 0}
+
+    def step():
+        state["fev"] += lam
+        g.generation(obj, state["sigma"], state["gen"], c["ik"], state["fev"])
+        rep = g.fetch()
+        state["sigma"] = update_sigma(state["sigma"], rep.pslen, c, rep.ybw[0], rep.f_kth)
+        state["gen"] += 1
+        return rep
+
+    for _ in range(warmup):
+        step()
+    ctx.profile_reset()
+    ctx.profile(True)
+    times = []
+    for _ in range(steps):
+        ctx.timer_start()
+        rep = step()
+        times.append(ctx.timer_stop())
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    ms = float(np.mean(times))
+    return {"gens_per_s": 1e3 / ms, "ms_per_generation": ms, "fbest": rep.ybw[0], "bytes_per_generation": 8.0 * n * (lam + lam // 2),
+            "kernel_share_of_step": {k: v["ms_total"] / sum(times) for k, v in prof.items()}}
+
+
+def bench_sharded(ctx, comm, kind, lam, steps, warmup, seed):
+    """BASELINE config 4: ONE run, candidates sharded over the GPUs of the communicator (fitness all-gather + rank-mu
+    all-reduce per generation).  Strong scaling: lambda is fixed, every GPU owns lambda/world candidates."""
+    from bboptpy_b200 import _cabi
+    from bboptpy_b200.strategy import cma_constants, flops_per_generation, update_sigma
+    n = N_DIM
+    w, c = cma_constants(kind, n, lam)
+    guess = np.random.default_rng(seed).uniform(-BOX, BOX, n)   # same seed on every rank: replicated state
+    g = _cabi.Cma(ctx, kind, n, lam, w, c, seed=seed, shard=(comm.rank, comm.world))
+    g.attach_comm(comm)
+    g.reset(guess)
+    obj = _cabi.Objective(ctx, n, builtin=_cabi.OBJ_ROSENBROCK)
+    state = {"sigma": 2.0, "fev": 0, "gen": 0}
+
+    def step():
+        state["fev"] += lam
+        g.generation(obj, state["sigma"], state["gen"], c["ik"], state["fev"])
+        rep = g.fetch()
+        state["sigma"] = update_sigma(state["sigma"], rep.pslen, c, rep.ybw[0], rep.f_kth)
+        state["gen"] += 1
+        return rep
+
+    for i in range(warmup):
+        step()
+        if i == 0:
+            g.eig()
+    g.fetch()
+    ctx.profile_reset()
+    ctx.profile(True)
+    times = []
+    for _ in range(steps):
+        ctx.timer_start()
+        rep = step()
+        times.append(ctx.timer_stop())
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    return {"times_ms": times, "fbest": rep.ybw[0], "flops": flops_per_generation(kind, n, lam),
+            "shares": {k: v["ms_total"] / sum(times) for k, v in prof.items()}}
+
+
 def bench_de_e2e(pkg, cls, gens, seed):
     lo, hi = -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N)
     if cls == "JADE":
@@ -356,7 +458,7 @@ def run_own(args):
     value = world * args.steps / t_max
     fbest, owner = all_min_with_owner(dist, local, rank, res["fbest"])
     # e2e through the public API
-    e2e_gens = max(3, min(args.steps, 10))
+    e2e_gens = max(3, min(2 * args.steps, 40))  # enough generations to amortise optimize()'s allocations and uploads
     bench_cma_e2e(pkg, 2, seed=1 + rank)  # first-call costs (cuSOLVER handle, workspace) are not part of a step
     barrier(dist, local)
     e_val, e_dt, e_done, h2d, d2h, ndec = bench_cma_e2e(pkg, e2e_gens, seed=1 + rank)
@@ -370,7 +472,33 @@ def run_own(args):
         t_de = all_max(dist, local, DE_NP * de_steps / r["evals_per_s"])
         r["evals_per_s"] = world * DE_NP * de_steps / t_de
         r["e2e_evals_per_s"] = bench_de_e2e(pkg, name.upper(), de_steps, seed=7 + rank) * world
+        b = bench_de_batched(ctx, kind, DE_BATCH, max(5, de_steps // 4), 3, seed=7 + rank)
+        t_b = all_max(dist, local, b["ms_per_generation"])
+        b["evals_per_s"] = world * DE_BATCH * DE_NP / (t_b * 1e-3)
+        r["batched"] = b
         de[name] = r
+    # separable CMA-ES on the bandwidth-bound configuration
+    sep = bench_sep_device(ctx, max(5, args.steps // 2), 3, seed=1 + rank)
+    t_sep = all_max(dist, local, sep["ms_per_generation"])
+    sep["gens_per_s"] = world * 1e3 / t_sep
+    # one large-lambda run sharded by candidates over all GPUs of the job (N > 1 only)
+    sharded = None
+    if world > 1:
+        import torch
+        import torch.distributed as tdist
+        ids = [_cabi.Comm.unique_id() if rank == 0 else None]
+        tdist.broadcast_object_list(ids, src=0)
+        comm = _cabi.Comm(ctx, world, rank, ids[0])
+        sharded = {}
+        for kname, kind in (("cmaes", _cabi.CMA_FULL), ("active_cmaes", _cabi.CMA_ACTIVE)):
+            barrier(dist, local)
+            sr = bench_sharded(ctx, comm, kind, SHARD_LAMBDA, max(5, args.steps // 2), 3, seed=77)
+            t_sh = all_max(dist, local, sum(sr["times_ms"]) / 1e3)
+            gps = len(sr["times_ms"]) / t_sh
+            sharded[kname] = {"lambda": SHARD_LAMBDA, "gpus": world, "gens_per_s": gps, "ms_per_generation": 1e3 / gps,
+                              "scaling": "strong", "tflops": sr["flops"] * gps / 1e12, "share_of_step": sr["shares"],
+                              "collectives": "ncclAllGather(fitness) + ncclAllReduce(n*ld + ld doubles) per generation"}
+        del comm
     if rank != 0:
         return
     peak, peak_src = fp64_peak()
@@ -384,7 +512,17 @@ def run_own(args):
     for name in ("jade", "shade"):
         de[name]["roofline"] = {"bound": "hbm", "achieved": de[name]["evals_per_s"] / world * 5 * 8 * DE_N / 1e9, "peak": hbm,
                                 "unit": "GB/s", "frac": de[name]["evals_per_s"] / world * 5 * 8 * DE_N / 1e9 / hbm, "traffic": None,
-                                "peak_source": hbm_src, "algorithmic_bytes_per_eval": 5 * 8 * DE_N}
+                                "peak_source": hbm_src, "algorithmic_bytes_per_eval": 5 * 8 * DE_N,
+                                "note": "single run: 8 MB swarm (L2 resident), one cooperative launch per generation, bounded by the "
+                                        "sequential dependency rounds of the in-place update, not by bandwidth"}
+        bb = de[name]["batched"]
+        bb["roofline"] = {"bound": "hbm", "achieved": bb["evals_per_s"] / world * 5 * 8 * DE_N / 1e9, "peak": hbm, "unit": "GB/s",
+                          "frac": bb["evals_per_s"] / world * 5 * 8 * DE_N / 1e9 / hbm, "traffic": None, "peak_source": hbm_src,
+                          "algorithmic_bytes_per_eval": 5 * 8 * DE_N}
+    sep["roofline"] = {"bound": "hbm", "achieved": sep["bytes_per_generation"] * sep["gens_per_s"] / world / 1e9, "peak": hbm,
+                       "unit": "GB/s", "frac": sep["bytes_per_generation"] * sep["gens_per_s"] / world / 1e9 / hbm, "traffic": None,
+                       "peak_source": hbm_src, "algorithmic_bytes_per_generation": sep["bytes_per_generation"]}
+    sep["workload"] = f"SepCmaes n={SEP_N} lambda={LAMBDA} Ellipsoid adjustlr=True (BASELINE config 3); working set > L2"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -407,7 +545,10 @@ def run_own(args):
                 "gens_per_s_incl_eig": world / ((ms_step + res["eig_ms"]) * 1e-3)},
         "best_of": {"f": fbest, "rank": owner},
         "de": de,
+        "sep": sep,
     }
+    if sharded is not None:
+        line["sharded_run"] = sharded
     if world == 1:
         o, kind = cpu_oracle()
         cs = cpu_sample(o)

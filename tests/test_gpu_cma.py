@@ -169,3 +169,39 @@ def test_philox_generation_is_a_valid_cma_step(ctx, port_oracle):
     C = g.get(_cabi.F_C)
     Cf = np.tril(C) + np.tril(C, -1).T
     assert np.linalg.eigvalsh(Cf).min() > 0
+
+
+@pytest.mark.parametrize("obj,n,lam,bound", [(O.ELLIPSOID, 1000, 64, False), (O.RASTRIGIN, 77, 40, True),
+                                             (O.ACKLEY, 10, 16, True), (O.SPHERE, 129, 24, False), (O.ROSENBROCK, 50, 16, False)])
+def test_sep_fused_generation_equals_phases(ctx, obj, n, lam, bound):
+    """SepCmaes free-running: the fused Philox -> sample -> evaluate pass (bbgpu_cma_generation) writes the same X and
+    the same fitness bits as the separate phases, and the generation ends in the same state (Rosenbrock: unfused path)."""
+    from bboptpy_b200.strategy import cma_constants
+    w, c = cma_constants(2, n, lam)
+    box = 5.0
+    lo, hi = -box * np.ones(n), box * np.ones(n)
+    guess = np.linspace(-4.0, 4.5, n)
+    objective = _cabi.Objective(ctx, n, builtin=obj)
+    a = _cabi.Cma(ctx, _cabi.CMA_SEP, n, lam, w, c, bound=bound, lower=lo, upper=hi, seed=31)
+    b = _cabi.Cma(ctx, _cabi.CMA_SEP, n, lam, w, c, bound=bound, lower=lo, upper=hi, seed=31)
+    a.reset(guess)
+    b.reset(guess)
+    sigma, fev = 3.0, 0
+    for gen in range(4):
+        fev += lam
+        a.sample(sigma, gen)
+        a.evaluate(objective)
+        a.rank(c["ik"])
+        a.update(sigma, fev)
+        b.generation(objective, sigma, gen, c["ik"], fev)
+        ra, rb = a.fetch(), b.fetch()
+        assert np.array_equal(a.get(_cabi.F_ARX), b.get(_cabi.F_ARX)), f"gen {gen} X"
+        assert np.array_equal(a.get(_cabi.F_FITNESS), b.get(_cabi.F_FITNESS)), f"gen {gen} fitness bits"
+        assert np.array_equal(a.rank_idx(), b.rank_idx())
+        for f in (_cabi.F_XMEAN, _cabi.F_C, _cabi.F_D, _cabi.F_PS, _cabi.F_PC):
+            assert np.array_equal(a.get(f), b.get(f)), f"gen {gen} field {f}"
+        assert ra.pslen == rb.pslen and list(ra.ibw) == list(rb.ibw)
+        if bound:
+            X = b.get(_cabi.F_ARX)
+            assert (X >= -box).all() and (X <= box).all()
+        sigma *= 0.9
