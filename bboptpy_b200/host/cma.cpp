@@ -98,8 +98,8 @@ void BaseCmaes::fillConfig(bbgpu_cma_config &cfg) const {
     cfg.lambda = _lambda;
     cfg.mu = _mu;
     cfg.bound = _bound ? 1 : 0;
-    cfg.shard_rank = 0;
-    cfg.shard_count = 1;
+    cfg.shard_rank = _comm ? bbgpu_comm_rank(_comm) : 0;
+    cfg.shard_count = _comm ? bbgpu_comm_world(_comm) : 1;
     cfg.seed = _stream_key;
     cfg.cc = _cc; cfg.cs = _cs; cfg.c1 = _c1; cfg.cmu = _cmu; cfg.mueff = _mueff; cfg.chi = _chi;
     cfg.cneg = 0.; cfg.alphaold = 0.; cfg.cm = 1.; cfg.ccov = 0.;
@@ -135,6 +135,7 @@ void BaseCmaes::ensureDevice() {
         gpu_check(bbgpu_cma_set(_dev, BBGPU_CMA_B, oldB.data(), (int64_t) oldB.size()));
     }
     gpu_check(bbgpu_cma_reset(_dev, _xguess.data(), carry ? 1 : 0));
+    if (_comm && bbgpu_comm_world(_comm) > 1) gpu_check(bbgpu_cma_attach_comm(_dev, _comm));
     _dev_used = false;
 }
 
@@ -241,7 +242,7 @@ std::vector<double> BaseCmaes::bestSolution() {
         gpu_check(bbgpu_cma_get(_dev, BBGPU_CMA_XMEAN, x.data(), _n));
     } else {
         if (!_rep_fresh) fetchReport();
-        gpu_check(bbgpu_cma_get_rows(_dev, BBGPU_CMA_ARX, _ibw[0], 1, x.data()));
+        gpu_check(bbgpu_cma_get_candidate(_dev, _ibw[0], x.data())); // collective on a sharded run
     }
     return x;
 }

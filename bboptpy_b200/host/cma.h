@@ -46,6 +46,7 @@ protected:
     bbopt::ReplayStream _replay;
     std::vector<double> _zbuf, _xguess;
     uint64_t _gen = 0; // generation counter of the Philox stream; never reset, so restarts draw fresh values
+    bbgpu_comm *_comm = nullptr; // candidate sharding over the ranks of this communicator (not owned)
 
     virtual int deviceKind() const = 0;
     virtual void fillConfig(bbgpu_cma_config &cfg) const;
@@ -84,6 +85,12 @@ public:
     int iterations() const { return _it; }
     int lambda() const { return _lambda; }
     bbopt::ObjectiveHandle &objective() { return _obj; }
+    // One large-lambda run sharded by candidates over the GPUs of `comm` (one process per GPU): every rank
+    // constructs the same optimizer, calls this, then optimize()/iterate() with the same arguments; state is
+    // replicated, each rank samples and evaluates lambda/world candidates.  Needs setStreamKey() with one
+    // common key so that all ranks draw from the same Philox stream.  Call before init().
+    void setCommunicator(bbgpu_comm *comm) { _comm = comm; }
+    void setStreamKey(uint64_t key) { _stream_key = key; }
 };
 
 class Cmaes: public BaseCmaes {

@@ -106,7 +106,33 @@ PYBIND11_MODULE(_bboptpy, m) {
     solver.def("iterate", &MultivariateOptimizer::iterate);
     solver.def("solution", &MultivariateOptimizer::solution);
 
+    // one rank of an NCCL communicator (bbgpu_comm_*): candidate-sharded runs and best-of reduces
+    struct PyComm {
+        bbgpu_comm *h = nullptr;
+        PyComm(int world, int rank, py::bytes id) {
+            std::string raw = id;
+            if ((int) raw.size() != BBGPU_COMM_ID_BYTES) throw std::invalid_argument("unique id must be 128 bytes");
+            bbopt::gpu_check(bbgpu_comm_create(bbopt::device_context(), world, rank, raw.data(), &h));
+        }
+        ~PyComm() { if (h) bbgpu_comm_destroy(h); }
+    };
+    py::class_<PyComm>(m, "Communicator")
+        .def(py::init<int, int, py::bytes>(), "world"_a, "rank"_a, "unique_id"_a)
+        .def_static("unique_id", []() {
+            char buf[BBGPU_COMM_ID_BYTES];
+            bbopt::gpu_check(bbgpu_comm_unique_id(buf));
+            return py::bytes(buf, BBGPU_COMM_ID_BYTES);
+        }, "rank 0 creates the id and hands it to the other ranks (e.g. torch.distributed.broadcast_object_list)")
+        .def_property_readonly("rank", [](PyComm &c) { return bbgpu_comm_rank(c.h); })
+        .def_property_readonly("world", [](PyComm &c) { return bbgpu_comm_world(c.h); });
+
     py::class_<BaseCmaes, MultivariateOptimizer>(m, "BaseCMAES")
+        .def("set_communicator", [](BaseCmaes &self, PyComm &c, uint64_t stream_key) {
+            self.setCommunicator(c.h);
+            self.setStreamKey(stream_key);
+        }, "comm"_a, "stream_key"_a = 0, py::keep_alive<1, 2>(),
+             "Shard the candidates of this run over the ranks of `comm` (call on every rank, before optimize/initialize)")
+        .def("set_stream_key", &BaseCmaes::setStreamKey, "key"_a, "Philox key of the free-running draws (default: a fresh key per object)")
         .def("state", [](BaseCmaes &self, const std::string &name) { return as_array(self.state(name)); }, "name"_a)
         .def("set_draw_replay", &BaseCmaes::setDrawReplay, "seed"_a,
              "Draw replay: consume the reference's N(0,1) stream (std::mt19937(seed) + normal_distribution) in its own draw order")

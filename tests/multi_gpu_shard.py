@@ -70,6 +70,30 @@ def main():
             sigma2 = sigma1
         if rank == 0:
             print("sharded", "active" if kind == _cabi.CMA_ACTIVE else "vanilla", "over", world, "GPUs: ok", flush=True)
+    # ---- the same through the reference-facing Python API: CMAES.set_communicator + optimize
+    os.environ["BBOPT_DEVICE"] = str(local)
+    import bboptpy_b200 as pkg
+    n, lam, gens = 64, 32 * world, 12
+    lo, hi, guess = -10.0 * np.ones(n), 10.0 * np.ones(n), np.linspace(-2, 2, n)
+    ids2 = [pkg.Communicator.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids2, src=0)
+    pcomm = pkg.Communicator(world, rank, ids2[0])
+    for cls in (pkg.CMAES, pkg.ActiveCMAES):
+        single = cls(mfev=gens * lam, tol=0.0, np=lam)
+        single.set_stream_key(4242)
+        s1 = single.optimize(pkg.Rosenbrock, lo, hi, guess)
+        shard = cls(mfev=gens * lam, tol=0.0, np=lam)
+        shard.set_communicator(pcomm, 4242)
+        s2 = shard.optimize(pkg.Rosenbrock, lo, hi, guess)
+        assert s1.n_evals == s2.n_evals == gens * lam
+        f1, f2 = float(np.sum(100 * (s1.x[1:] - s1.x[:-1] ** 2) ** 2 + (1 - s1.x[:-1]) ** 2)), \
+            float(np.sum(100 * (s2.x[1:] - s2.x[:-1] ** 2) ** 2 + (1 - s2.x[:-1]) ** 2))
+        assert abs(f1 - f2) <= 1e-8 * abs(f1), (f1, f2)
+        assert_close(s2.x, s1.x, rel=1e-8, what="solution of the sharded optimize()")
+        assert_close(shard.state("C"), single.state("C"), rel=1e-8, what="C after the sharded optimize()")
+        if rank == 0:
+            print(cls.__name__, "optimize() sharded over", world, "GPUs: ok", f1, f2, flush=True)
+    del pcomm
     # best-of reduce
     f_dev = torch.tensor([10.0 - rank if rank != 1 else -5.0], dtype=torch.float64, device="cuda")
     x_dev = torch.full((7,), float(rank), dtype=torch.float64, device="cuda")
