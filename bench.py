@@ -437,6 +437,9 @@ def bench_de_e2e(pkg, cls, gens, seed):
 
 
 def run_own(args):
+    # libraries (NCCL's version banner) write to fd 1: keep the real stdout for the ONE JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local, dist = dist_setup(args.gpus)
     import __graft_entry__ as entry
     if rank == 0 and not os.path.exists(os.path.join(ROOT, "bboptpy_b200", "libbbgpu.so")):
@@ -557,7 +560,7 @@ def run_own(args):
                                           "phases scaled x16 to lambda=4096, eigendecomposition counted once per generation",
                                 "gens_per_s_excl_eig": cs["gens_per_s_excl_eig"], "t_eig_s": cs["t_eig"],
                                 "de_jade_evals_per_s": cpu_de_sample(o, 0), "de_shade_evals_per_s": cpu_de_sample(o, 1)}
-    print(json.dumps(line))
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 def main():
