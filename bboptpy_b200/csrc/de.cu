@@ -33,6 +33,7 @@
 
 #include <cooperative_groups.h>
 
+#include "gemm_tma.cuh" // mbarrier + 1-D bulk copy helpers
 #include "objectives.cuh"
 #include "philox.cuh"
 #include "rank.cuh"
@@ -43,7 +44,8 @@ constexpr int DE_MAX_ROUNDS = 4096;
 constexpr int DE_GROUP = 128;                 // threads that build one candidate
 constexpr int DE_GROUPS = 4;                  // candidates in flight per CTA
 constexpr int DE_CTA = DE_GROUP * DE_GROUPS;  // 512
-constexpr int DE_TILE = 1024;                 // objective terms staged in shared memory per pass
+constexpr int DE_TILE = 512;                  // coordinates per bulk-copy stage (4 parent rows x 4 KB)
+constexpr int DE_STAGES = 2;                  // stages per group: the next tile / candidate loads while this one computes
 enum { TAG_CR = 1, TAG_F = 2, TAG_IBEST = 3, TAG_R1 = 4, TAG_R2 = 5, TAG_JRAND = 6, TAG_SLOT = 7, TAG_CROSS = 8,
        TAG_RI = 9, TAG_PI = 10, TAG_TRIM = 11, TAG_INIT = 12 };
 
@@ -219,7 +221,7 @@ __device__ __forceinline__ double de_trial_coord(const DeBuild &b, int j, double
     return v;
 }
 
-__device__ __forceinline__ double u32_unit(uint32_t w) { return (double) w * (1.0 / 4294967296.0); }
+__device__ __forceinline__ double u32_unit(uint32_t w) { return u32_to_double(w) * (1.0 / 4294967296.0); }
 
 __device__ __forceinline__ Philox4 de_cross_block(const DeDev &d, int i, int quad) {
     return philox4x32_10((uint32_t) quad, (uint32_t) i, (uint32_t) d.gen,
@@ -306,114 +308,161 @@ __device__ __forceinline__ void de_signature(const DeDev &d, int cj, int i, bool
     work[atomicAdd(nwork, 1)] = it;
 }
 
-// one queued candidate, one 128-thread group: mutation + crossover + repair + objective + greedy test.
-// T1/T2: this group's term buffers.
+// The queued candidates of one 128-thread group (items g, g + 4, ... of the CTA's work list): mutation + crossover +
+// repair + objective + greedy test.  The four parent rows of a 512-coordinate tile arrive in shared memory by 1-D bulk
+// copies (cp.async.bulk, one elected thread, completion on an mbarrier); the tile after it -- of this candidate or the
+// next -- is already in flight while this one is computed, so the loads need no registers and never stall the math.
+// The objective terms are written over the consumed parent rows of the stage and added by warp 0 in the objective's
+// fixed order before the stage is refilled.
 template<int ID, bool REPLAY>
-__device__ __noinline__ void de_build(const DeDev &d, const DeLaunch &L, int cj, const DeItem &it, int round, int g,
-        double *T1, double *T2, double *gred) {
+__device__ __noinline__ void de_build_list(const DeDev &d, const DeLaunch &L, int cj, const DeItem *work, int todo, int round,
+        int g, double *stage, unsigned long long *full, unsigned &uses, double *gred) {
+    const int nmine = todo > g ? (todo - g + DE_GROUPS - 1) / DE_GROUPS : 0;
+    if (nmine == 0) return;
     const int nxt = (round & 1) ^ 1;
     const int gt = threadIdx.x & (DE_GROUP - 1), lane = threadIdx.x & 31, gwarp = gt >> 5;
-    const int n = d.n, i = it.i;
+    const int n = d.n;
     const int64_t ld = d.ld;
-    DeBuild b;
-    b.xi = d.POOL + (int64_t) it.rxi * ld;
-    b.xb = d.POOL + (int64_t) it.rxb * ld;
-    b.x1 = d.POOL + (int64_t) it.rx1 * ld;
-    b.x2 = d.POOL + (int64_t) it.rx2 * ld;
-    double *out = d.POOL + (int64_t) it.rout * ld;
-    b.lo = d.lower; b.hi = d.upper; b.U = d.U + (int64_t) i * n;
-    b.F = d.Fm[i]; b.CR = d.CR[i]; b.jr = it.jr; b.replay = REPLAY;
-    const double fi = d.F[cj][i];
-
+    const int ntiles = (n + DE_TILE - 1) / DE_TILE;
+    const int U = nmine * ntiles;
     constexpr int id = ID;
     const int nt = obj_term_count(id, n);
-    const bool rosen = id == BBGPU_OBJ_ROSENBROCK, ackley = id == BBGPU_OBJ_ACKLEY, ellip = id == BBGPU_OBJ_ELLIPSOID;
+    constexpr bool rosen = id == BBGPU_OBJ_ROSENBROCK, ackley = id == BBGPU_OBJ_ACKLEY, ellip = id == BBGPU_OBJ_ELLIPSOID;
+    const unsigned base = uses;
+    auto issue = [&](int u) { // elected thread: the 4 parent rows of (item u / ntiles, tile u % ntiles) -> stage (base + u) & 1
+        const DeItem &it = work[g + DE_GROUPS * (u / ntiles)];
+        const int t0 = (u % ntiles) * DE_TILE;
+        const int cnt = min(DE_TILE, (int) ld - t0); // padded row length: a multiple of 8 doubles
+        const unsigned s = (base + u) & (DE_STAGES - 1);
+        double *dst = stage + (size_t) s * 4 * DE_TILE;
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); // earlier generic writes to this stage (the terms)
+        mbar_expect_tx(full + s, 4 * cnt * 8);
+        bulk_load_1d(dst, d.POOL + (int64_t) it.rxi * ld + t0, cnt * 8, full + s);
+        bulk_load_1d(dst + DE_TILE, d.POOL + (int64_t) it.rxb * ld + t0, cnt * 8, full + s);
+        bulk_load_1d(dst + 2 * DE_TILE, d.POOL + (int64_t) it.rx1 * ld + t0, cnt * 8, full + s);
+        bulk_load_1d(dst + 3 * DE_TILE, d.POOL + (int64_t) it.rx2 * ld + t0, cnt * 8, full + s);
+    };
+    if (gt == 0) {
+        issue(0);
+        if (U > 1) issue(1);
+    }
+    DeBuild b;
+    b.lo = d.lower; b.hi = d.upper; b.replay = REPLAY;
     int cnt = 0;
-    double nrm = 0.0, acc = 0.0, acc2 = 0.0;
-    for (int t0 = 0; t0 < n; t0 += DE_TILE) {
-        if (t0 > 0) group_sync(g); // the previous tile's terms have been consumed
+    double nrm = 0.0, acc = 0.0, acc2 = 0.0, fi = 0.0;
+    for (int u = 0; u < U; u++) {
+        const DeItem &it = work[g + DE_GROUPS * (u / ntiles)];
+        const int t = u % ntiles, t0 = t * DE_TILE, i = it.i;
         const int tl = min(DE_TILE, n - t0);
-        for (int q = gt; 4 * q < tl; q += DE_GROUP) {
-            // one Philox block per 4 coordinates; the quad is processed as two 16-byte halves to bound registers
-            Philox4 r = { 0u, 0u, 0u, 0u };
-            if (!REPLAY) r = de_cross_block(d, i, (t0 >> 2) + q);
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int j = t0 + 4 * q + 2 * h; // rows are 64-byte aligned and padded to a multiple of 8 doubles
-                if (j >= n) break;
-                const double2 xa = *(const double2*) (b.xi + j);
-                const double2 ba = *(const double2*) (b.xb + j);
-                const double2 pa = *(const double2*) (b.x1 + j);
-                const double2 qa = *(const double2*) (b.x2 + j);
-                const double2 la = *(const double2*) (b.lo + j);
-                const double2 ha = *(const double2*) (b.hi + j);
-                double u0, u1;
-                if (REPLAY) {
-                    u0 = b.U[j]; u1 = j + 1 < n ? b.U[j + 1] : 2.0;
-                } else {
-                    u0 = u32_unit(h ? r.z : r.x); u1 = u32_unit(h ? r.w : r.y);
-                }
-                const double v0 = de_trial_coord(b, j, xa.x, ba.x, pa.x, qa.x, la.x, ha.x, u0, cnt);
-                double v1 = 0.0;
-                if (j + 1 < n) v1 = de_trial_coord(b, j + 1, xa.y, ba.y, pa.y, qa.y, la.y, ha.y, u1, cnt);
-                *(double2*) (out + j) = make_double2(v0, v1);
-                nrm = fma(v0, v0, fma(v1, v1, nrm));
-                double v2 = 0.0;
-                if (rosen && j + 2 < n) { // the next coordinate, rebuilt here (same inputs, same bits)
-                    double u2;
-                    if (REPLAY) u2 = b.U[j + 2];
-                    else u2 = u32_unit(h ? de_cross_block(d, i, (t0 >> 2) + q + 1).x : r.z);
-                    int dummy = 0;
-                    v2 = de_trial_coord(b, j + 2, b.xi[j + 2], b.xb[j + 2], b.x1[j + 2], b.x2[j + 2], b.lo[j + 2], b.hi[j + 2], u2, dummy);
-                }
-                double a0 = 0.0, a1 = 0.0;
-                if (ellip) {
-                    const double2 ea = *(const double2*) (L.aux + j);
-                    a0 = ea.x; a1 = ea.y;
-                }
-                double e0 = 0.0, e1 = 0.0;
-                const double t0v = obj_term(id, v0, v1, a0, e0);
-                const double t1v = obj_term(id, v1, v2, a1, e1);
-                *(double2*) (T1 + 4 * q + 2 * h) = make_double2(t0v, t1v);
-                if (ackley) *(double2*) (T2 + 4 * q + 2 * h) = make_double2(e0, e1);
+        if (t == 0) {
+            b.F = d.Fm[i]; b.CR = d.CR[i]; b.jr = it.jr; b.U = d.U + (int64_t) i * n;
+            fi = d.F[cj][i];
+            cnt = 0; nrm = 0.0; acc = 0.0; acc2 = 0.0;
+        }
+        const unsigned s = (base + u) & (DE_STAGES - 1);
+        double *S = stage + (size_t) s * 4 * DE_TILE; // rows: parent, pbest, r1, r2
+        double *out = d.POOL + (int64_t) it.rout * ld;
+        mbar_wait(full + s, ((base + u) / DE_STAGES) & 1);
+        double t0v = 0.0, t1v = 0.0, t2v = 0.0, t3v = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+        const int q = gt; // DE_TILE / 4 == DE_GROUP: one quad per thread and tile
+        const bool mine = 4 * q < tl;
+        if (mine) {
+            const int j = t0 + 4 * q; // rows are 64-byte aligned and padded to a multiple of 8 doubles
+            const double2 xa = *(const double2*) (S + 4 * q), xc = *(const double2*) (S + 4 * q + 2);
+            const double2 ba = *(const double2*) (S + DE_TILE + 4 * q), bc = *(const double2*) (S + DE_TILE + 4 * q + 2);
+            const double2 pa = *(const double2*) (S + 2 * DE_TILE + 4 * q), pc = *(const double2*) (S + 2 * DE_TILE + 4 * q + 2);
+            const double2 qa = *(const double2*) (S + 3 * DE_TILE + 4 * q), qc = *(const double2*) (S + 3 * DE_TILE + 4 * q + 2);
+            const double2 la = *(const double2*) (b.lo + j), lc = *(const double2*) (b.lo + j + 2);
+            const double2 ha = *(const double2*) (b.hi + j), hc = *(const double2*) (b.hi + j + 2);
+            double u0, u1, u2, u3;
+            if (REPLAY) {
+                u0 = b.U[j]; u1 = j + 1 < n ? b.U[j + 1] : 2.0; u2 = j + 2 < n ? b.U[j + 2] : 2.0; u3 = j + 3 < n ? b.U[j + 3] : 2.0;
+            } else {
+                const Philox4 r = de_cross_block(d, i, j >> 2);
+                u0 = u32_unit(r.x); u1 = u32_unit(r.y); u2 = u32_unit(r.z); u3 = u32_unit(r.w);
             }
+            double v0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            v0 = de_trial_coord(b, j, xa.x, ba.x, pa.x, qa.x, la.x, ha.x, u0, cnt);
+            if (j + 1 < n) v1 = de_trial_coord(b, j + 1, xa.y, ba.y, pa.y, qa.y, la.y, ha.y, u1, cnt);
+            if (j + 2 < n) v2 = de_trial_coord(b, j + 2, xc.x, bc.x, pc.x, qc.x, lc.x, hc.x, u2, cnt);
+            if (j + 3 < n) v3 = de_trial_coord(b, j + 3, xc.y, bc.y, pc.y, qc.y, lc.y, hc.y, u3, cnt);
+            *(double2*) (out + j) = make_double2(v0, v1);
+            *(double2*) (out + j + 2) = make_double2(v2, v3);
+            nrm = fma(v0, v0, fma(v1, v1, fma(v2, v2, fma(v3, v3, nrm))));
+            double v4 = 0.0;
+            if (rosen && j + 4 < n) { // the neighbour's first coordinate, rebuilt here (same inputs, same bits)
+                double x4, b4, p4, q4, u4;
+                if (4 * q + 4 < tl) { x4 = S[4 * q + 4]; b4 = S[DE_TILE + 4 * q + 4]; p4 = S[2 * DE_TILE + 4 * q + 4]; q4 = S[3 * DE_TILE + 4 * q + 4]; }
+                else { // first coordinate of the next tile: not staged yet
+                    x4 = d.POOL[(int64_t) it.rxi * ld + j + 4]; b4 = d.POOL[(int64_t) it.rxb * ld + j + 4];
+                    p4 = d.POOL[(int64_t) it.rx1 * ld + j + 4]; q4 = d.POOL[(int64_t) it.rx2 * ld + j + 4];
+                }
+                if (REPLAY) u4 = b.U[j + 4];
+                else u4 = u32_unit(de_cross_block(d, i, (j >> 2) + 1).x);
+                int dummy = 0;
+                v4 = de_trial_coord(b, j + 4, x4, b4, p4, q4, b.lo[j + 4], b.hi[j + 4], u4, dummy);
+            }
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            if (ellip) {
+                const double2 ea = *(const double2*) (L.aux + j), ec = *(const double2*) (L.aux + j + 2);
+                a0 = ea.x; a1 = ea.y; a2 = ec.x; a3 = ec.y;
+            }
+            t0v = obj_term(id, v0, v1, a0, e0);
+            t1v = obj_term(id, v1, v2, a1, e1);
+            t2v = obj_term(id, v2, v3, a2, e2);
+            t3v = obj_term(id, v3, v4, a3, e3);
+        }
+        if (rosen) group_sync(g); // neighbours have read their look-ahead coordinate from the parent rows
+        if (mine) { // terms over the consumed rows: T1 -> pbest row, T2 -> r1 row
+            *(double2*) (S + DE_TILE + 4 * q) = make_double2(t0v, t1v);
+            *(double2*) (S + DE_TILE + 4 * q + 2) = make_double2(t2v, t3v);
+            if (ackley) {
+                *(double2*) (S + 2 * DE_TILE + 4 * q) = make_double2(e0, e1);
+                *(double2*) (S + 2 * DE_TILE + 4 * q + 2) = make_double2(e2, e3);
+            }
+        }
+        const bool last = t == ntiles - 1;
+        if (last) { // the group's crossover count and squared norm ride on the tile barrier
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+                nrm += __shfl_xor_sync(0xffffffffu, nrm, off);
+            }
+            // double buffered by tile parity: warp 0 may still be reading the previous candidate's sums
+            if (lane == 0) { gred[8 * (u & 1) + 2 * gwarp] = (double) cnt; gred[8 * (u & 1) + 2 * gwarp + 1] = nrm; }
         }
         group_sync(g);
         if (gwarp == 0) { // spec order: lane l adds term(i) for i = l, l+32, ... ascending (t0 is a multiple of 32)
             const int kend = min(tl, nt - t0);
+            const double *T1 = S + DE_TILE, *T2 = S + 2 * DE_TILE;
             for (int k = lane; k < kend; k += 32) {
                 acc = add(acc, T1[k]);
                 if (ackley) acc2 = add(acc2, T2[k]);
             }
+            __syncwarp();
+            if (lane == 0 && u + DE_STAGES < U) issue(u + DE_STAGES); // the stage is free: refill it
+            if (last) {
+                const double sum1 = warp_sum(acc);
+                const double sum2 = ackley ? warp_sum(acc2) : 0.0;
+                const double ft = obj_finish(id, n, sum1, sum2);
+                if (lane == 0) {
+                    double cn = 0.0, nr = 0.0;
+                    for (int w = 0; w < DE_GROUP / 32; w++) { cn += gred[8 * (u & 1) + 2 * w]; nr += gred[8 * (u & 1) + 2 * w + 1]; }
+                    const int sx = ft <= fi ? (ft < fi ? 2 : 1) : 0;
+                    d.FT[i] = ft;
+                    d.DF[i] = fi - ft;
+                    d.RT[i] = sqrt(nr);
+                    d.CR1[i] = d.repaircr ? __ddiv_rn(cn, (double) n) : b.CR;
+                    const int ver = st_ver(it.mine) + ((sx != st_succ(it.mine) || sx > 0) ? 1 : 0);
+                    d.st[nxt][i] = (ver << 3) | ((1 - st_buf(it.mine)) << 2) | sx;
+                    if (sx != st_succ(it.mine) || sx > 0) atomicAdd(L.nrecomp + round, 1); // later candidates may see a change
+                    *(int4*) (d.sig + 4 * i) = make_int4(it.s0, it.s1, it.s2, it.j2);
+                    d.r2[i] = it.j2;
+                }
+            }
         }
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-        nrm += __shfl_xor_sync(0xffffffffu, nrm, off);
-    }
-    if (lane == 0) { gred[2 * gwarp] = (double) cnt; gred[2 * gwarp + 1] = nrm; }
-    group_sync(g);
-    if (gwarp == 0) {
-        const double sum1 = warp_sum(acc);
-        const double sum2 = ackley ? warp_sum(acc2) : 0.0;
-        const double ft = obj_finish(id, n, sum1, sum2);
-        if (lane == 0) {
-            double cn = 0.0, nr = 0.0;
-            for (int w = 0; w < DE_GROUP / 32; w++) { cn += gred[2 * w]; nr += gred[2 * w + 1]; }
-            const int s = ft <= fi ? (ft < fi ? 2 : 1) : 0;
-            d.FT[i] = ft;
-            d.DF[i] = fi - ft;
-            d.RT[i] = sqrt(nr);
-            d.CR1[i] = d.repaircr ? __ddiv_rn(cn, (double) n) : b.CR;
-            const int ver = st_ver(it.mine) + ((s != st_succ(it.mine) || s > 0) ? 1 : 0);
-            d.st[nxt][i] = (ver << 3) | ((1 - st_buf(it.mine)) << 2) | s;
-            if (s != st_succ(it.mine) || s > 0) atomicAdd(L.nrecomp + round, 1); // later candidates may see a change
-            *(int4*) (d.sig + 4 * i) = make_int4(it.s0, it.s1, it.s2, it.j2);
-            d.r2[i] = it.j2;
-        }
-    }
-    group_sync(g); // gred / T1 are free again
+    uses = base + U;
 }
 
 // after the fixed point, one thread per successful candidate: the greedy replacement and the archive push
@@ -576,10 +625,17 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ DeDev d;
     __shared__ double red[32];
-    __shared__ double gredbuf[DE_GROUPS][2 * (DE_GROUP / 32)];
+    __shared__ double gredbuf[DE_GROUPS][2 * 2 * (DE_GROUP / 32)];
     __shared__ int wsum[33];
-    double *terms = (double*) smraw;                           // [DE_GROUPS][2][DE_TILE]
-    DeItem *work = (DeItem*) (terms + DE_GROUPS * 2 * DE_TILE); // [DE_CTA]
+    double *stages = (double*) smraw;                          // [DE_GROUPS][DE_STAGES][4 rows][DE_TILE]
+    DeItem *work = (DeItem*) (stages + DE_GROUPS * DE_STAGES * 4 * DE_TILE); // [DE_CTA]
+    __shared__ __align__(8) unsigned long long fullbar[DE_GROUPS][DE_STAGES];
+    unsigned uses = 0; // bulk-copy stages this thread's group has consumed so far (stage = uses & 1, parity = uses / 2 & 1)
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < DE_GROUPS * DE_STAGES; q++) mbar_init(&fullbar[0][0] + q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
     int *minw = (int*) (work + DE_CTA);                        // [np], then maxw [np], pre [np] u16, tgt [np] u16
     __shared__ int nwork;
     const int tid = threadIdx.x, warp = tid >> 5, g = tid / DE_GROUP;
@@ -647,17 +703,15 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
                 __syncthreads();
                 fine(round, 1);
                 const int todo = nwork;
-                double *T1 = terms + (size_t) g * 2 * DE_TILE, *T2 = T1 + DE_TILE;
-                for (int w = g; w < todo; w += DE_GROUPS) {
-#define DE_CASE(ID) case ID: if (L.replay) de_build<ID, true>(d, L, cj, work[w], round, g, T1, T2, gredbuf[g]); \
-                             else de_build<ID, false>(d, L, cj, work[w], round, g, T1, T2, gredbuf[g]); break;
-                    switch (L.obj_id) {
-                    DE_CASE(BBGPU_OBJ_SPHERE) DE_CASE(BBGPU_OBJ_ELLIPSOID) DE_CASE(BBGPU_OBJ_ROSENBROCK)
-                    DE_CASE(BBGPU_OBJ_RASTRIGIN) DE_CASE(BBGPU_OBJ_ACKLEY)
-                    default: break;
-                    }
-#undef DE_CASE
+                double *stage = stages + (size_t) g * DE_STAGES * 4 * DE_TILE;
+#define DE_CASE(ID) case ID: if (L.replay) de_build_list<ID, true>(d, L, cj, work, todo, round, g, stage, fullbar[g], uses, gredbuf[g]); \
+                             else de_build_list<ID, false>(d, L, cj, work, todo, round, g, stage, fullbar[g], uses, gredbuf[g]); break;
+                switch (L.obj_id) {
+                DE_CASE(BBGPU_OBJ_SPHERE) DE_CASE(BBGPU_OBJ_ELLIPSOID) DE_CASE(BBGPU_OBJ_ROSENBROCK)
+                DE_CASE(BBGPU_OBJ_RASTRIGIN) DE_CASE(BBGPU_OBJ_ACKLEY)
+                default: break;
                 }
+#undef DE_CASE
             }
         }
         fine(round, 2);
@@ -793,7 +847,7 @@ template<typename T> int de_alloc(bbgpu_de *h, T **p, size_t count, bool zero = 
 }
 
 size_t de_smem_bytes(int np) {
-    return (size_t) DE_GROUPS * 2 * DE_TILE * sizeof(double) + (size_t) DE_CTA * sizeof(DeItem) + (size_t) np * (2 * sizeof(int) + 2 * sizeof(unsigned short));
+    return (size_t) DE_GROUPS * DE_STAGES * 4 * DE_TILE * sizeof(double) + (size_t) DE_CTA * sizeof(DeItem) + (size_t) np * (2 * sizeof(int) + 2 * sizeof(unsigned short));
 }
 
 // the device struct as the kernel left it (np, cur, last_fin, ...)
@@ -851,7 +905,7 @@ extern "C" {
 
 int bbgpu_de_create(bbgpu_ctx *ctx, const bbgpu_de_config *cfg, const double *h_lower, const double *h_upper, bbgpu_de **out) {
     BB_ARG(ctx && cfg && h_lower && h_upper && out);
-    BB_ARG(cfg->n >= 1 && cfg->np >= 4 && cfg->np <= 8192);
+    BB_ARG(cfg->n >= 1 && cfg->np >= 4 && cfg->np <= 6144); // shared-memory tables of the generation kernel
     BB_ARG(cfg->kind == BBGPU_DE_JADE || cfg->kind == BBGPU_DE_SHADE);
     BB_ARG(cfg->kind == BBGPU_DE_JADE || (cfg->h >= 1 && cfg->npmin >= 4 && cfg->mfev > 0));
     BB_CUDA(cudaSetDevice(ctx->device));

@@ -20,10 +20,18 @@ __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, 
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
 
+// rint(x) (round to nearest, ties to even) on the fp64 pipe: adding and subtracting 2^52 with the sign of x rounds at
+// the unit place.  Same value as rint for every finite x (|x| >= 2^52 is already integral); the FRND instruction it
+// replaces issues on the quarter-rate XU pipe.
+__device__ __forceinline__ double rint_rn(double x) {
+    const double t = copysign(4503599627370496.0, x);
+    return fabs(x) < 4503599627370496.0 ? sub(add(x, t), t) : x;
+}
+
 // cos(2 pi x): reduce to r = x - rint(x) in [-1/2, 1/2], fold to [0, 1/8] with the quarter- and
 // eighth-period symmetries, then a degree-18 Taylor polynomial in t = 2 pi * folded (t <= pi/4).
 __device__ __forceinline__ double cos2pi(double x) {
-    const double r = sub(x, rint(x));
+    const double r = sub(x, rint_rn(x));
     double a = fabs(r);
     bool neg = false;
     if (a > 0.25) { a = sub(0.5, a); neg = true; }

@@ -38,9 +38,24 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return Philox4 { c0, c1, c2, c3 };
 }
 
-// 53-bit uniform in [0,1)
+// (double) w, exactly, without the conversion unit: the integer is dropped into the mantissa of 2^52 and 2^52 is
+// subtracted (one DADD).  I2F.F64 issues on the quarter-rate XU pipe, which ncu showed saturated (134 %) in the
+// DE build and the fused Sep sampling kernel when every coordinate converted its uniform draw there.
+__host__ __device__ __forceinline__ double u32_to_double(uint32_t w) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(0x43300000, (int) w) - 4503599627370496.0;
+#else
+    return (double) w;
+#endif
+}
+
+// 53-bit uniform in [0,1): (a >> 5) * 2^26 + (b >> 6), an exact 53-bit integer, times 2^-53
 __host__ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return fma(u32_to_double(a >> 5), 67108864.0, u32_to_double(b >> 6)) * (1.0 / 9007199254740992.0);
+#else
     return (double) ((((uint64_t) (a >> 5)) << 26) | (uint64_t) (b >> 6)) * (1.0 / 9007199254740992.0);
+#endif
 }
 
 #ifdef __CUDACC__
