@@ -42,10 +42,12 @@ namespace bb {
 
 constexpr int DE_MAX_ROUNDS = 4096;
 constexpr int DE_GROUP = 128;                 // threads that build one candidate
-constexpr int DE_GROUPS = 4;                  // candidates in flight per CTA
+constexpr int DE_GROUPS = 4;                  // candidates in flight per CTA (8 x 64 registers measured no faster: the
+                                              // build is bound by HBM traffic and issue slots, not by resident warps)
 constexpr int DE_CTA = DE_GROUP * DE_GROUPS;  // 512
+constexpr int DE_CHUNK = 512;                 // candidates whose signatures are checked per pass (work-list capacity)
 constexpr int DE_TILE = 512;                  // coordinates per bulk-copy stage (4 parent rows x 4 KB)
-constexpr int DE_STAGES = 2;                  // stages per group: the next tile / candidate loads while this one computes
+constexpr int DE_STAGES = 2;                  // bulk-copy stages per group: the next tile / candidate loads while this one computes
 enum { TAG_CR = 1, TAG_F = 2, TAG_IBEST = 3, TAG_R1 = 4, TAG_R2 = 5, TAG_JRAND = 6, TAG_SLOT = 7, TAG_CROSS = 8,
        TAG_RI = 9, TAG_PI = 10, TAG_TRIM = 11, TAG_INIT = 12 };
 
@@ -316,7 +318,7 @@ __device__ __forceinline__ void de_signature(const DeDev &d, int cj, int i, bool
 // fixed order before the stage is refilled.
 template<int ID, bool REPLAY>
 __device__ __noinline__ void de_build_list(const DeDev &d, const DeLaunch &L, int cj, const DeItem *work, int todo, int round,
-        int g, double *stage, unsigned long long *full, unsigned &uses, double *gred) {
+        int g, double *stage, unsigned long long *full, unsigned &uses, double *gred, int *changed) {
     const int nmine = todo > g ? (todo - g + DE_GROUPS - 1) / DE_GROUPS : 0;
     if (nmine == 0) return;
     const int nxt = (round & 1) ^ 1;
@@ -342,10 +344,8 @@ __device__ __noinline__ void de_build_list(const DeDev &d, const DeLaunch &L, in
         bulk_load_1d(dst + 2 * DE_TILE, d.POOL + (int64_t) it.rx1 * ld + t0, cnt * 8, full + s);
         bulk_load_1d(dst + 3 * DE_TILE, d.POOL + (int64_t) it.rx2 * ld + t0, cnt * 8, full + s);
     };
-    if (gt == 0) {
-        issue(0);
-        if (U > 1) issue(1);
-    }
+    if (gt == 0)
+        for (int u = 0; u < DE_STAGES && u < U; u++) issue(u);
     DeBuild b;
     b.lo = d.lower; b.hi = d.upper; b.replay = REPLAY;
     int cnt = 0;
@@ -455,7 +455,7 @@ __device__ __noinline__ void de_build_list(const DeDev &d, const DeLaunch &L, in
                     d.CR1[i] = d.repaircr ? __ddiv_rn(cn, (double) n) : b.CR;
                     const int ver = st_ver(it.mine) + ((sx != st_succ(it.mine) || sx > 0) ? 1 : 0);
                     d.st[nxt][i] = (ver << 3) | ((1 - st_buf(it.mine)) << 2) | sx;
-                    if (sx != st_succ(it.mine) || sx > 0) atomicAdd(L.nrecomp + round, 1); // later candidates may see a change
+                    if (sx != st_succ(it.mine) || sx > 0) atomicAdd(changed, 1); // later candidates may see a change
                     *(int4*) (d.sig + 4 * i) = make_int4(it.s0, it.s1, it.s2, it.j2);
                     d.r2[i] = it.j2;
                 }
@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
     __shared__ double gredbuf[DE_GROUPS][2 * 2 * (DE_GROUP / 32)];
     __shared__ int wsum[33];
     double *stages = (double*) smraw;                          // [DE_GROUPS][DE_STAGES][4 rows][DE_TILE]
-    DeItem *work = (DeItem*) (stages + DE_GROUPS * DE_STAGES * 4 * DE_TILE); // [DE_CTA]
+    DeItem *work = (DeItem*) (stages + DE_GROUPS * DE_STAGES * 4 * DE_TILE); // [DE_CHUNK]
     __shared__ __align__(8) unsigned long long fullbar[DE_GROUPS][DE_STAGES];
     unsigned uses = 0; // bulk-copy stages this thread's group has consumed so far (stage = uses & 1, parity = uses / 2 & 1)
     if (threadIdx.x == 0) {
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
-    int *minw = (int*) (work + DE_CTA);                        // [np], then maxw [np], pre [np] u16, tgt [np] u16
+    int *minw = (int*) (work + DE_CHUNK);                        // [np], then maxw [np], pre [np] u16, tgt [np] u16
     __shared__ int nwork;
     const int tid = threadIdx.x, warp = tid >> 5, g = tid / DE_GROUP;
     constexpr int WARPS = DE_CTA / 32;
@@ -669,6 +669,85 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
     };
     stamp(); // 0 start
 
+    // one resolution round of one (run, part) task; `changed` counts the rebuilds later candidates can observe
+    auto round_task = [&](int run, int part, int round, int *changed) {
+        int *maxw = minw + d.np;
+        unsigned short *pre = (unsigned short*) (maxw + d.np), *tgt = pre + d.np;
+        const int cj = d.kind == BBGPU_DE_JADE ? d.cur ^ 1 : d.cur;
+        const int larch0 = *d.larch;
+        de_scan_targets(d, d.st[round & 1], larch0, pre, tgt, minw, maxw, wsum);
+        fine(round, 0);
+        // candidates of this CTA: part, part + cpr, ...; DE_CHUNK of them per pass
+        for (int k0 = 0; part + (int64_t) k0 * L.cpr < d.np; k0 += DE_CHUNK) {
+            __syncthreads(); // the previous chunk's work list has been consumed
+            if (tid == 0) nwork = 0;
+            __syncthreads();
+            const int64_t i = part + (int64_t) (k0 + tid) * L.cpr;
+            const bool valid = i < d.np && tid < DE_CHUNK;
+            if (L.replay) de_signature<true>(d, cj, (int) min(i, (int64_t) d.np - 1), valid, round, larch0, pre, tgt, minw, maxw, work, &nwork);
+            else de_signature<false>(d, cj, (int) min(i, (int64_t) d.np - 1), valid, round, larch0, pre, tgt, minw, maxw, work, &nwork);
+            __syncthreads();
+            fine(round, 1);
+            const int todo = nwork;
+            double *stage = stages + (size_t) g * DE_STAGES * 4 * DE_TILE;
+#define DE_CASE(ID) case ID: if (L.replay) de_build_list<ID, true>(d, L, cj, work, todo, round, g, stage, fullbar[g], uses, gredbuf[g], changed); \
+                         else de_build_list<ID, false>(d, L, cj, work, todo, round, g, stage, fullbar[g], uses, gredbuf[g], changed); break;
+            switch (L.obj_id) {
+            DE_CASE(BBGPU_OBJ_SPHERE) DE_CASE(BBGPU_OBJ_ELLIPSOID) DE_CASE(BBGPU_OBJ_ROSENBROCK)
+            DE_CASE(BBGPU_OBJ_RASTRIGIN) DE_CASE(BBGPU_OBJ_ACKLEY)
+            default: break;
+            }
+#undef DE_CASE
+        }
+    };
+    auto finalize_task = [&](int part, int fin) {
+        int *maxw = minw + d.np;
+        unsigned short *pre = (unsigned short*) (maxw + d.np), *tgt = pre + d.np;
+        const int cj = d.kind == BBGPU_DE_JADE ? d.cur ^ 1 : d.cur;
+        const int larch0 = *d.larch;
+        de_scan_targets(d, d.st[fin], larch0, pre, tgt, minw, maxw, wsum);
+        if (part == 0) {
+            // DF / CR1 / Fm, not the fitness being replaced below, feed the adaptation
+            de_adapt_block(d, fin, d.nsucc, red);
+            if (tid == 0) *d.larch_new = d.archive ? min(d.np, larch0 + wsum[32]) : 0;
+        }
+        for (int i = part * DE_CTA + tid; i < d.np; i += L.cpr * DE_CTA) de_finalize_one(d, cj, i, fin, tgt, maxw);
+    };
+
+    // ---- as many runs as CTAs (or more): a CTA owns whole runs.  Nothing is shared between CTAs, so every phase
+    // boundary is a CTA barrier, runs drift apart freely and no CTA ever waits for another run's slowest candidate.
+    if (L.cpr == 1 && L.nruns >= (int) gridDim.x) {
+        __shared__ int solo_changed[2];
+        for (int run = blockIdx.x; run < L.nruns; run += gridDim.x) {
+            load_run(run);
+            if (d.kind == BBGPU_DE_JADE) de_sort_ids(d, d.cur, d.cur ^ 1, warp, WARPS);
+            for (int i = tid; i < d.np; i += DE_CTA) de_params_one(d, L.replay, i);
+            if (tid < 2) solo_changed[tid] = 0;
+            __syncthreads();
+            int round = 0;
+            while (true) {
+                round_task(run, 0, round, &solo_changed[round & 1]);
+                __syncthreads();
+                const int rebuilt = solo_changed[round & 1];
+                round++;
+                if (tid == 0) solo_changed[round & 1] = 0;
+                __syncthreads();
+                if (rebuilt == 0 || round >= DE_MAX_ROUNDS) break;
+            }
+            const int fin = round & 1;
+            finalize_task(0, fin);
+            __syncthreads();
+            if (d.kind == BBGPU_DE_SHADE) {
+                de_sort_ids(d, d.cur, d.cur ^ 1, warp, WARPS);
+                __syncthreads();
+            }
+            const int np_after = d.kind == BBGPU_DE_SHADE ? min(d.np, L.npnew) : d.np;
+            de_report_block(runs[run], d, L, d.cur ^ 1, np_after, fin, round, red);
+            __syncthreads();
+        }
+        return;
+    }
+
     // ---- phase 0: JADE sorts the swarm (de/jade.cpp:101); control parameters of the generation
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
         const int run = task / L.cpr, part = task % L.cpr;
@@ -685,34 +764,7 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
         for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
             const int run = task / L.cpr, part = task % L.cpr;
             load_run(run);
-            int *maxw = minw + d.np;
-            unsigned short *pre = (unsigned short*) (maxw + d.np), *tgt = pre + d.np;
-            const int cj = d.kind == BBGPU_DE_JADE ? d.cur ^ 1 : d.cur;
-            const int larch0 = *d.larch;
-            de_scan_targets(d, d.st[round & 1], larch0, pre, tgt, minw, maxw, wsum);
-            fine(round, 0);
-            // candidates of this CTA: part, part + cpr, ...; DE_CTA of them per chunk
-            for (int k0 = 0; part + (int64_t) k0 * L.cpr < d.np; k0 += DE_CTA) {
-                __syncthreads(); // the previous chunk's work list has been consumed
-                if (tid == 0) nwork = 0;
-                __syncthreads();
-                const int64_t i = part + (int64_t) (k0 + tid) * L.cpr;
-                const bool valid = i < d.np;
-                if (L.replay) de_signature<true>(d, cj, (int) min(i, (int64_t) d.np - 1), valid, round, larch0, pre, tgt, minw, maxw, work, &nwork);
-                else de_signature<false>(d, cj, (int) min(i, (int64_t) d.np - 1), valid, round, larch0, pre, tgt, minw, maxw, work, &nwork);
-                __syncthreads();
-                fine(round, 1);
-                const int todo = nwork;
-                double *stage = stages + (size_t) g * DE_STAGES * 4 * DE_TILE;
-#define DE_CASE(ID) case ID: if (L.replay) de_build_list<ID, true>(d, L, cj, work, todo, round, g, stage, fullbar[g], uses, gredbuf[g]); \
-                             else de_build_list<ID, false>(d, L, cj, work, todo, round, g, stage, fullbar[g], uses, gredbuf[g]); break;
-                switch (L.obj_id) {
-                DE_CASE(BBGPU_OBJ_SPHERE) DE_CASE(BBGPU_OBJ_ELLIPSOID) DE_CASE(BBGPU_OBJ_ROSENBROCK)
-                DE_CASE(BBGPU_OBJ_RASTRIGIN) DE_CASE(BBGPU_OBJ_ACKLEY)
-                default: break;
-                }
-#undef DE_CASE
-            }
+            round_task(run, part, round, L.nrecomp + round);
         }
         fine(round, 2);
         grid.sync();
@@ -729,17 +781,7 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
         const int run = task / L.cpr, part = task % L.cpr;
         load_run(run);
-        int *maxw = minw + d.np;
-        unsigned short *pre = (unsigned short*) (maxw + d.np), *tgt = pre + d.np;
-        const int cj = d.kind == BBGPU_DE_JADE ? d.cur ^ 1 : d.cur;
-        const int larch0 = *d.larch;
-        de_scan_targets(d, d.st[fin], larch0, pre, tgt, minw, maxw, wsum);
-        if (part == 0) {
-            // DF / CR1 / Fm, not the fitness being replaced below, feed the adaptation
-            de_adapt_block(d, fin, d.nsucc, red);
-            if (tid == 0) *d.larch_new = d.archive ? min(d.np, larch0 + wsum[32]) : 0;
-        }
-        for (int i = part * DE_CTA + tid; i < d.np; i += L.cpr * DE_CTA) de_finalize_one(d, cj, i, fin, tgt, maxw);
+        finalize_task(part, fin);
     }
     if (blockIdx.x == 0 && tid == 0)
         for (int r = 0; r < round; r++) L.nrecomp[r] = 0;
@@ -847,7 +889,7 @@ template<typename T> int de_alloc(bbgpu_de *h, T **p, size_t count, bool zero = 
 }
 
 size_t de_smem_bytes(int np) {
-    return (size_t) DE_GROUPS * DE_STAGES * 4 * DE_TILE * sizeof(double) + (size_t) DE_CTA * sizeof(DeItem) + (size_t) np * (2 * sizeof(int) + 2 * sizeof(unsigned short));
+    return (size_t) DE_GROUPS * DE_STAGES * 4 * DE_TILE * sizeof(double) + (size_t) DE_CHUNK * sizeof(DeItem) + (size_t) np * (2 * sizeof(int) + 2 * sizeof(unsigned short));
 }
 
 // the device struct as the kernel left it (np, cur, last_fin, ...)

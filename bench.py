@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 N_DIM, LAMBDA, BOX = 1000, 4096, 10.0
 DE_N, DE_NP, DE_BOX = 1000, 1000, 5.12
-DE_BATCH = 16          # independent DE runs per launch for the HBM-resident figure
+DE_BATCH = 148         # independent DE runs per launch for the HBM-resident figure (one per SM: no grid-wide barrier)
 SEP_N = 10000          # BASELINE config 3
 SHARD_LAMBDA = 16384   # BASELINE config 4
 METRIC = "CMA-ES generations/s (n=1000, lambda=4096)"

@@ -107,15 +107,17 @@ def test_free_running_philox_de_converges(ctx, kind):
     assert np.allclose(f, (x * x).sum(1), rtol=1e-12)
 
 
-@pytest.mark.parametrize("kind,obj", [(O.JADE, O.RASTRIGIN), (O.SHADE, O.ROSENBROCK), (O.JADE, O.ACKLEY)])
-def test_batched_runs_equal_single_runs(ctx, kind, obj):
+@pytest.mark.parametrize("kind,obj,R,n,np_,gens", [(O.JADE, O.RASTRIGIN, 5, 50, 64, 12), (O.SHADE, O.ROSENBROCK, 5, 50, 64, 12),
+                                                   (O.JADE, O.ACKLEY, 5, 50, 64, 12),
+                                                   # >= one run per SM: every CTA owns whole runs, no grid-wide barrier
+                                                   (O.SHADE, O.RASTRIGIN, 160, 24, 20, 8), (O.JADE, O.ROSENBROCK, 300, 600, 12, 5)])
+def test_batched_runs_equal_single_runs(ctx, kind, obj, R, n, np_, gens):
     """bbgpu_de_generation_batch: R independent runs in one launch are bit-identical to the same runs
     stepped one handle at a time (same seeds)."""
-    n, np_, R, gens = 50, 64, 5, 12
     lo, hi = -5.0 * np.ones(n), 5.0 * np.ones(n)
     objective = _cabi.Objective(ctx, n, builtin=obj)
-    single = [_cabi.De(ctx, kind, n, np_, lo, hi, mfev=3000, seed=100 + r) for r in range(R)]
-    batch = [_cabi.De(ctx, kind, n, np_, lo, hi, mfev=3000, seed=100 + r) for r in range(R)]
+    single = [_cabi.De(ctx, kind, n, np_, lo, hi, mfev=40 * np_, seed=100 + r) for r in range(R)]
+    batch = [_cabi.De(ctx, kind, n, np_, lo, hi, mfev=40 * np_, seed=100 + r) for r in range(R)]
     for g in single + batch:
         g.init(objective)
     for gen in range(gens):
