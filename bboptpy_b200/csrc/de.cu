@@ -81,6 +81,11 @@ struct DeLaunch {
     int nruns, cpr /* CTAs per run */, kind, obj_id, replay, ntrim, npnew;
     const double *aux;
     int *nrecomp;                 // [DE_MAX_ROUNDS] rebuilds per round, over all runs of the launch
+    // objectives evaluated OUTSIDE the kernel (user device functions, the host-callback bridge): the generation is
+    // split into launches -- mode 1 begin, mode 2 one round that only builds trials and lists them in `pend`, mode 3
+    // finish -- with gather / evaluate / select between the rounds.  mode 0: the fused generation.
+    int mode, round;
+    int *pend, *pend_count;
     unsigned long long *phase_ns; // [32] %globaltimer at phase boundaries (diagnostics)
 };
 
@@ -328,7 +333,8 @@ __device__ __noinline__ void de_build_list(const DeDev &d, const DeLaunch &L, in
     const int ntiles = (n + DE_TILE - 1) / DE_TILE;
     const int U = nmine * ntiles;
     constexpr int id = ID;
-    const int nt = obj_term_count(id, n);
+    constexpr bool external = ID < 0; // the objective runs outside the kernel: only build the trial rows
+    const int nt = external ? 0 : obj_term_count(id, n);
     constexpr bool rosen = id == BBGPU_OBJ_ROSENBROCK, ackley = id == BBGPU_OBJ_ACKLEY, ellip = id == BBGPU_OBJ_ELLIPSOID;
     const unsigned base = uses;
     auto issue = [&](int u) { // elected thread: the 4 parent rows of (item u / ntiles, tile u % ntiles) -> stage (base + u) & 1
@@ -407,13 +413,15 @@ __device__ __noinline__ void de_build_list(const DeDev &d, const DeLaunch &L, in
                 const double2 ea = *(const double2*) (L.aux + j), ec = *(const double2*) (L.aux + j + 2);
                 a0 = ea.x; a1 = ea.y; a2 = ec.x; a3 = ec.y;
             }
-            t0v = obj_term(id, v0, v1, a0, e0);
-            t1v = obj_term(id, v1, v2, a1, e1);
-            t2v = obj_term(id, v2, v3, a2, e2);
-            t3v = obj_term(id, v3, v4, a3, e3);
+            if (!external) {
+                t0v = obj_term(id, v0, v1, a0, e0);
+                t1v = obj_term(id, v1, v2, a1, e1);
+                t2v = obj_term(id, v2, v3, a2, e2);
+                t3v = obj_term(id, v3, v4, a3, e3);
+            }
         }
         if (rosen) group_sync(g); // neighbours have read their look-ahead coordinate from the parent rows
-        if (mine) { // terms over the consumed rows: T1 -> pbest row, T2 -> r1 row
+        if (mine && !external) { // terms over the consumed rows: T1 -> pbest row, T2 -> r1 row
             *(double2*) (S + DE_TILE + 4 * q) = make_double2(t0v, t1v);
             *(double2*) (S + DE_TILE + 4 * q + 2) = make_double2(t2v, t3v);
             if (ackley) {
@@ -441,7 +449,17 @@ __device__ __noinline__ void de_build_list(const DeDev &d, const DeLaunch &L, in
             }
             __syncwarp();
             if (lane == 0 && u + DE_STAGES < U) issue(u + DE_STAGES); // the stage is free: refill it
-            if (last) {
+            if (last && external) {
+                if (lane == 0) { // the trial row is built; fitness and the greedy test follow in de_select_kernel
+                    double cn = 0.0, nr = 0.0;
+                    for (int w = 0; w < DE_GROUP / 32; w++) { cn += gred[8 * (u & 1) + 2 * w]; nr += gred[8 * (u & 1) + 2 * w + 1]; }
+                    d.RT[i] = sqrt(nr);
+                    d.CR1[i] = d.repaircr ? __ddiv_rn(cn, (double) n) : b.CR;
+                    *(int4*) (d.sig + 4 * i) = make_int4(it.s0, it.s1, it.s2, it.j2);
+                    d.r2[i] = it.j2;
+                    L.pend[atomicAdd(L.pend_count, 1)] = i;
+                }
+            } else if (last) {
                 const double sum1 = warp_sum(acc);
                 const double sum2 = ackley ? warp_sum(acc2) : 0.0;
                 const double ft = obj_finish(id, n, sum1, sum2);
@@ -694,7 +712,7 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
                          else de_build_list<ID, false>(d, L, cj, work, todo, round, g, stage, fullbar[g], uses, gredbuf[g], changed); break;
             switch (L.obj_id) {
             DE_CASE(BBGPU_OBJ_SPHERE) DE_CASE(BBGPU_OBJ_ELLIPSOID) DE_CASE(BBGPU_OBJ_ROSENBROCK)
-            DE_CASE(BBGPU_OBJ_RASTRIGIN) DE_CASE(BBGPU_OBJ_ACKLEY)
+            DE_CASE(BBGPU_OBJ_RASTRIGIN) DE_CASE(BBGPU_OBJ_ACKLEY) DE_CASE(-1)
             default: break;
             }
 #undef DE_CASE
@@ -716,7 +734,7 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
 
     // ---- as many runs as CTAs (or more): a CTA owns whole runs.  Nothing is shared between CTAs, so every phase
     // boundary is a CTA barrier, runs drift apart freely and no CTA ever waits for another run's slowest candidate.
-    if (L.cpr == 1 && L.nruns >= (int) gridDim.x) {
+    if (L.mode == 0 && L.cpr == 1 && L.nruns >= (int) gridDim.x) {
         __shared__ int solo_changed[2];
         for (int run = blockIdx.x; run < L.nruns; run += gridDim.x) {
             load_run(run);
@@ -749,18 +767,28 @@ __global__ void __launch_bounds__(DE_CTA, 1) de_generation_kernel(DeDev *const *
     }
 
     // ---- phase 0: JADE sorts the swarm (de/jade.cpp:101); control parameters of the generation
-    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const int run = task / L.cpr, part = task % L.cpr;
-        load_run(run);
-        if (d.kind == BBGPU_DE_JADE) de_sort_ids(d, d.cur, d.cur ^ 1, part * WARPS + warp, L.cpr * WARPS);
-        for (int i = part * DE_CTA + tid; i < d.np; i += L.cpr * DE_CTA) de_params_one(d, L.replay, i);
+    if (L.mode <= 1) {
+        for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+            const int run = task / L.cpr, part = task % L.cpr;
+            load_run(run);
+            if (d.kind == BBGPU_DE_JADE) de_sort_ids(d, d.cur, d.cur ^ 1, part * WARPS + warp, L.cpr * WARPS);
+            for (int i = part * DE_CTA + tid; i < d.np; i += L.cpr * DE_CTA) de_params_one(d, L.replay, i);
+        }
+        if (L.mode == 1) return;
+        grid.sync();
     }
-    grid.sync();
     stamp(); // 1 sorted + parameters
+    if (L.mode == 2) { // one round with the objective outside: build the changed trials, list them, stop
+        for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+            load_run(task / L.cpr);
+            round_task(task / L.cpr, task % L.cpr, L.round, nullptr);
+        }
+        return;
+    }
 
     // ---- resolution rounds
-    int round = 0;
-    while (true) {
+    int round = L.mode == 3 ? L.round : 0;
+    while (L.mode == 0) {
         for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
             const int run = task / L.cpr, part = task % L.cpr;
             load_run(run);
@@ -845,6 +873,31 @@ __global__ void __launch_bounds__(1024) de_init_sort_kernel(DeDev d) {
     de_sort_ids(d, 0, 1, threadIdx.x >> 5, 32);
 }
 
+// external-objective rounds: pool rows of the trials listed in `pend` (the buffer the candidate did NOT hold before)
+__global__ void de_pend_rows_kernel(DeDev d, int round, const int *__restrict__ pend, int count, int *__restrict__ rows) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int i = pend[k];
+    rows[k] = d.trow[1 - st_buf(d.st[round & 1][i])][i];
+}
+
+// external-objective rounds: fitness of the listed trials -> greedy test, next state word (de/jade.cpp:159-176)
+__global__ void de_select_kernel(DeDev d, int round, const int *__restrict__ pend, int count, const double *__restrict__ ft_in,
+        int *__restrict__ changed) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int i = pend[k];
+    const int cj = d.kind == BBGPU_DE_JADE ? d.cur ^ 1 : d.cur;
+    const int mine = d.st[round & 1][i];
+    const double ft = ft_in[k], fi = d.F[cj][i];
+    const int sx = ft <= fi ? (ft < fi ? 2 : 1) : 0;
+    d.FT[i] = ft;
+    d.DF[i] = fi - ft;
+    const int ver = st_ver(mine) + ((sx != st_succ(mine) || sx > 0) ? 1 : 0);
+    d.st[(round & 1) ^ 1][i] = (ver << 3) | ((1 - st_buf(mine)) << 2) | sx;
+    if (sx != st_succ(mine) || sx > 0) atomicAdd(changed, 1);
+}
+
 // members in swarm order -> contiguous staging rows (for the getters)
 __global__ void __launch_bounds__(256) de_gather_rows_kernel(const double *__restrict__ pool, const int *__restrict__ ids,
         double *__restrict__ dst, int rows, int n, int64_t ld) {
@@ -872,6 +925,9 @@ struct bbgpu_de {
     std::vector<bbgpu_de*> batch_members;
     double *stage = nullptr, *Ubuf = nullptr, *zbuf = nullptr, *cbuf = nullptr;
     int *trimbuf = nullptr, *nrecomp = nullptr;
+    int *pend = nullptr, *pend_rows = nullptr, *pend_count = nullptr; // external-objective rounds
+    double *fpend = nullptr;
+    int *h_counts = nullptr; // pinned [2]
     int trim_cap = 0;
     unsigned long long *phase_ns = nullptr;
     int blocks_per_sm = 0;
@@ -911,7 +967,8 @@ int de_npnew(const bbgpu_de *h, int fev_after) {
 }
 
 // one cooperative launch over `count` runs that share a configuration; lead = hs[0] owns the scratch
-int de_launch(bbgpu_de *const *hs, int count, bbgpu_objective *obj, DeDev **d_runs, int replay, int ntrim) {
+int de_launch(bbgpu_de *const *hs, int count, bbgpu_objective *obj, DeDev **d_runs, int replay, int ntrim, int mode = 0,
+        int round = 0) {
     bbgpu_de *lead = hs[0];
     bbgpu_ctx *ctx = lead->ctx;
     const int np = lead->np;
@@ -920,7 +977,8 @@ int de_launch(bbgpu_de *const *hs, int count, bbgpu_objective *obj, DeDev **d_ru
     const int resident = lead->blocks_per_sm * ctx->sm_count;
     const int want = ceil_div(np, DE_GROUPS);
     L.cpr = std::max(1, std::min(want, resident / count));
-    L.kind = lead->cfg.kind; L.obj_id = obj->id; L.aux = obj->d_aux; L.replay = replay; L.ntrim = ntrim;
+    L.mode = mode; L.round = round; L.pend = lead->pend; L.pend_count = lead->pend_count;
+    L.kind = lead->cfg.kind; L.obj_id = obj->mode == 0 ? obj->id : -1; L.aux = obj->d_aux; L.replay = replay; L.ntrim = ntrim;
     L.npnew = de_npnew(lead, lead->fev + np);
     L.nrecomp = lead->nrecomp;
     L.phase_ns = lead->phase_ns;
@@ -932,6 +990,7 @@ int de_launch(bbgpu_de *const *hs, int count, bbgpu_objective *obj, DeDev **d_ru
         BB_CUDA(cudaLaunchCooperativeKernel((const void*) de_generation_kernel, dim3(grid), dim3(DE_CTA), args, smem, ctx->stream));
         BB_TRY(launched(ctx, "de_generation_kernel"));
     }
+    if (mode == 1 || mode == 2) return BBGPU_OK; // the generation is not finished yet
     for (int r = 0; r < count; r++) {
         bbgpu_de *h = hs[r];
         h->fev += np;
@@ -939,6 +998,38 @@ int de_launch(bbgpu_de *const *hs, int count, bbgpu_objective *obj, DeDev **d_ru
         if (h->cfg.kind == BBGPU_DE_SHADE && L.npnew < h->np) h->np = L.npnew;
     }
     return BBGPU_OK;
+}
+
+// A generation whose objective is evaluated outside the fused kernel (user device function, host-callback bridge):
+// begin -> [round: build the changed trials -> gather -> evaluate -> greedy test] until a round changes nothing -> finish.
+// Same fixed point, same results as the fused path for the same fitness values.
+int de_generation_external(bbgpu_de *h, bbgpu_objective *obj, int replay, int ntrim) {
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    bbgpu_de *one[1] = { h };
+    BB_TRY(de_launch(one, 1, obj, h->d_self, replay, ntrim, 1));
+    BB_TRY(de_pull(h)); // the kernel-side view of cur / np for the helper kernels
+    int round = 0;
+    for (;; round++) {
+        if (round >= DE_MAX_ROUNDS) return fail(BBGPU_ERR_ARG, "DE dependency resolution did not converge");
+        BB_CUDA(cudaMemsetAsync(h->pend_count, 0, 2 * sizeof(int), st));
+        BB_TRY(de_launch(one, 1, obj, h->d_self, replay, ntrim, 2, round));
+        BB_CUDA(cudaMemcpyAsync(h->h_counts, h->pend_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        const int count = h->h_counts[0];
+        if (count == 0) { round++; break; }
+        de_pend_rows_kernel<<<ceil_div(count, 256), 256, 0, st>>>(h->d, round, h->pend, count, h->pend_rows);
+        BB_TRY(launched(ctx, "de_pend_rows_kernel"));
+        de_gather_rows_kernel<<<ceil_div(count, 8), 256, 0, st>>>(h->d.POOL, h->pend_rows, h->stage, count, h->n, h->ld);
+        BB_TRY(launched(ctx, "de_gather_rows_kernel"));
+        BB_TRY(evaluate(ctx, obj, h->stage, h->n, count, h->fpend));
+        de_select_kernel<<<ceil_div(count, 256), 256, 0, st>>>(h->d, round, h->pend, count, h->fpend, h->pend_count + 1);
+        BB_TRY(launched(ctx, "de_select_kernel"));
+        BB_CUDA(cudaMemcpyAsync(h->h_counts + 1, h->pend_count + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        if (h->h_counts[1] == 0) { round++; break; }
+    }
+    return de_launch(one, 1, obj, h->d_self, replay, ntrim, 3, round);
 }
 
 } // namespace
@@ -980,10 +1071,12 @@ int bbgpu_de_create(bbgpu_ctx *ctx, const bbgpu_de_config *cfg, const double *h_
     DA(d.larch, 1); DA(d.larch_new, 1); DA(d.nsucc, 1); DA(d.kslot, 1); DA(h->phase_ns, 64);
     DA(d.st[0], rows); DA(d.st[1], rows);
     DA(d.sig, rows * 4); DA(h->nrecomp, DE_MAX_ROUNDS);
+    DA(h->pend, rows); DA(h->pend_rows, rows); DA(h->pend_count, 2); DA(h->fpend, rows);
     DA(h->zbuf, rows); DA(h->cbuf, rows);
     DA(h->d_rep, 1); DA(h->d_dev, 1); DA(h->d_self, 1);
 #undef DA
     if (rc == BBGPU_OK && cudaMallocHost((void**) &h->h_rep, sizeof(bbgpu_de_report)) != cudaSuccess) rc = fail(BBGPU_ERR_CUDA, "pinned alloc failed");
+    if (rc == BBGPU_OK && cudaMallocHost((void**) &h->h_counts, 2 * sizeof(int)) != cudaSuccess) rc = fail(BBGPU_ERR_CUDA, "pinned alloc failed");
     if (rc != BBGPU_OK) { bbgpu_de_destroy(h); return rc; }
     d.lower = lo; d.upper = hi; d.rep = h->d_rep;
     d.zcr = h->zbuf; d.cauchy = h->cbuf;
@@ -1013,6 +1106,7 @@ int bbgpu_de_destroy(bbgpu_de *h) {
     if (h->trimbuf) cudaFree(h->trimbuf);
     if (h->d_batch) cudaFree(h->d_batch);
     if (h->h_rep) cudaFreeHost(h->h_rep);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
     delete h;
     return BBGPU_OK;
 }
@@ -1061,7 +1155,6 @@ int bbgpu_de_init(bbgpu_de *h, bbgpu_objective *obj, const double *h_x) {
 
 int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws *draws, bbgpu_de_report *out) {
     BB_ARG(h && obj && obj->n == h->n);
-    if (obj->mode != 0) return fail(BBGPU_ERR_ARG, "the fused DE generation needs a registry objective (user objectives: next round)");
     bbgpu_ctx *ctx = h->ctx;
     cudaStream_t st = ctx->stream;
     DeDev &d = h->d;
@@ -1104,8 +1197,12 @@ int bbgpu_de_generation(bbgpu_de *h, bbgpu_objective *obj, const bbgpu_de_draws 
             BB_CUDA(cudaMemcpyAsync(h->trimbuf, draws->trim, (size_t) draws->ntrim * 4, cudaMemcpyHostToDevice, st));
         }
     }
-    bbgpu_de *one[1] = { h };
-    BB_TRY(de_launch(one, 1, obj, h->d_self, draws != nullptr, draws ? draws->ntrim : 0));
+    if (obj->mode != 0) {
+        BB_TRY(de_generation_external(h, obj, draws != nullptr, draws ? draws->ntrim : 0));
+    } else {
+        bbgpu_de *one[1] = { h };
+        BB_TRY(de_launch(one, 1, obj, h->d_self, draws != nullptr, draws ? draws->ntrim : 0));
+    }
     if (out) {
         BB_CUDA(cudaMemcpyAsync(h->h_rep, h->d_rep, sizeof(bbgpu_de_report), cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaStreamSynchronize(st));
