@@ -62,6 +62,23 @@ class DeReport(ctypes.Structure):
                 ("muf", ctypes.c_double), ("fbest", ctypes.c_double), ("radius_m2", ctypes.c_double)]
 
 
+class CmabRunParams(ctypes.Structure):
+    _fields_ = [("lambda_", ctypes.c_int32), ("mu", ctypes.c_int32), ("mfev", ctypes.c_int32), ("mit", ctypes.c_int32),
+                ("hlen", ctypes.c_int32), ("ik", ctypes.c_int32), ("sigma0", ctypes.c_double), ("tol", ctypes.c_double),
+                ("cc", ctypes.c_double), ("cs", ctypes.c_double), ("c1", ctypes.c_double), ("cmu", ctypes.c_double),
+                ("mueff", ctypes.c_double), ("damps", ctypes.c_double), ("chi", ctypes.c_double),
+                ("eigenfreq", ctypes.c_double), ("seed", ctypes.c_uint64), ("weights", c_dp)]
+
+
+class CmabRunStatus(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int32), ("flag", ctypes.c_int32), ("it", ctypes.c_int32), ("fev", ctypes.c_int32),
+                ("lambda_", ctypes.c_int32), ("eig_count", ctypes.c_int32), ("eig_due", ctypes.c_int32),
+                ("hsig", ctypes.c_int32), ("ql_iters", ctypes.c_int32), ("generations_this_step", ctypes.c_int32),
+                ("ibw", ctypes.c_int32 * 4), ("ybw", ctypes.c_double * 4), ("sigma", ctypes.c_double),
+                ("fx_final", ctypes.c_double), ("pslen", ctypes.c_double), ("fkth", ctypes.c_double),
+                ("hist_best", ctypes.c_double), ("hist_worst", ctypes.c_double)]
+
+
 DEVICE_OBJECTIVE_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_dp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_dp, c_dp, c_dp)
 HOST_OBJECTIVE_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_dp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_dp, c_dp)
 
@@ -151,6 +168,18 @@ def lib():
     L.bbgpu_de_get_trace.argtypes = [vp, vp, vp, vp, vp]
     L.bbgpu_de_phase_times.argtypes = [vp, vp]
     L.bbgpu_de_generation_batch.argtypes = [vp, i, vp, vp]
+    L.bbgpu_cmab_create.argtypes = [vp, i, i, i, vp, vp, P(vp)]
+    L.bbgpu_cmab_destroy.argtypes = [vp]
+    L.bbgpu_cmab_start.argtypes = [vp, i, vp, P(CmabRunParams), vp, i]
+    L.bbgpu_cmab_step.argtypes = [vp, vp, i, vp, i, i, vp, i]
+    L.bbgpu_cmab_fetch.argtypes = [vp, P(CmabRunStatus)]
+    L.bbgpu_cmab_get_best.argtypes = [vp, i, i, vp]
+    L.bbgpu_cmab_get.argtypes = [vp, i, i, vp, i64]
+    L.bbgpu_cmab_set.argtypes = [vp, i, i, vp, i64]
+    L.bbgpu_cmab_set_sigma.argtypes = [vp, i, d]
+    L.bbgpu_cmab_get_population.argtypes = [vp, i, vp, vp, vp]
+    L.bbgpu_cmab_adopt_basis.argtypes = [vp, i, vp, vp]
+    L.bbgpu_eig_small_host.argtypes = [vp, i, i, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -198,7 +227,7 @@ class Context:
 
     # ---- measurement helpers
     PROF_TAGS = ("sample_gemm", "cov_syrk", "norm_gemm", "eval", "rank", "philox", "eig", "update_misc", "sep_sample",
-                 "de_round", "de_misc", "comm")
+                 "de_round", "de_misc", "comm", "cmab_step")
 
     def profile(self, on=True):
         check(self.L.bbgpu_ctx_profile_enable(self.h, int(on)))
@@ -253,6 +282,14 @@ class Context:
         z = np.empty((rows, cols))
         check(self.L.bbgpu_philox_normal_host(self.h, seed, generation, rows, cols, z.ctypes.data))
         return z
+
+    def eig_small(self, A):
+        """The batched engine's in-CTA tred2/tql2 on a stack of symmetric matrices [count, n, n]."""
+        A = f64(A)
+        count, n, _ = A.shape
+        B, D, info = np.empty_like(A), np.empty((count, n)), np.empty(count, dtype=np.int32)
+        check(self.L.bbgpu_eig_small_host(self.h, n, count, A.ctypes.data, B.ctypes.data, D.ctypes.data, info.ctypes.data))
+        return B, D, info
 
     def bench_dgemm(self, M, N, K, reps=10):
         ms = ctypes.c_float(0)
@@ -549,3 +586,78 @@ class De:
         ft, F, CR = np.empty(np_gen), np.empty(np_gen), np.empty(np_gen)
         check(self.L.bbgpu_de_get_trace(self.h, succ.ctypes.data, ft.ctypes.data, F.ctypes.data, CR.ctypes.data))
         return succ, ft, F, CR
+
+
+class CmaBatch:
+    """Batched small-n CMA-ES engine (include/bbgpu.h, bbgpu_cmab_*): one CTA per independent run."""
+
+    def __init__(self, ctx, n, runs, bound=False, lower=None, upper=None):
+        self.ctx, self.L, self.n, self.runs = ctx, ctx.L, n, runs
+        self.h = ctypes.c_void_p()
+        lo = f64(lower) if lower is not None else None
+        hi = f64(upper) if upper is not None else None
+        check(self.L.bbgpu_cmab_create(ctx.h, n, runs, int(bound), lo.ctypes.data if lo is not None else None,
+                                       hi.ctypes.data if hi is not None else None, ctypes.byref(self.h)))
+        self._status = (CmabRunStatus * runs)()
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.bbgpu_cmab_destroy(self.h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def run_params(n, lam, mfev, sigma0, tol, seed, eigenrate=0.25):
+        """BaseCmaes::init + Cmaes::init constants (base_cmaes.cpp:88-129, cmaes.cpp:48) for one base run."""
+        from .strategy import cma_constants
+        w, c = cma_constants(0, n, lam, eigenrate=eigenrate)
+        w = f64(w)
+        p = CmabRunParams(lam, c["mu"], mfev, mfev // lam, c["hlen"], c["ik"], sigma0, tol, c["cc"], c["cs"], c["c1"],
+                          c["cmu"], c["mueff"], c["damps"], c["chi"], c["eigenfreq"], seed, w.ctypes.data)
+        p._keep = w
+        return p
+
+    def start(self, run_ids, params, guesses, keep_offdiag=False):
+        ids = i32(run_ids)
+        arr = (CmabRunParams * len(ids))(*params)
+        g = f64(guesses).reshape(len(ids), self.n)
+        check(self.L.bbgpu_cmab_start(self.h, len(ids), ids.ctypes.data, arr, g.ctypes.data, int(keep_offdiag)))
+
+    def step(self, obj, run_ids, quantum=0, max_gens=1, z=None, eig_replay=False):
+        ids = i32(run_ids)
+        zz = f64(z) if z is not None else None
+        check(self.L.bbgpu_cmab_step(self.h, obj.h, len(ids), ids.ctypes.data, quantum, max_gens,
+                                     zz.ctypes.data if zz is not None else None, int(eig_replay)))
+
+    def fetch(self):
+        check(self.L.bbgpu_cmab_fetch(self.h, self._status))
+        return self._status
+
+    def best(self, run0=0, count=None):
+        count = self.runs - run0 if count is None else count
+        x = np.empty((count, self.n))
+        check(self.L.bbgpu_cmab_get_best(self.h, run0, count, x.ctypes.data))
+        return x
+
+    def get(self, run, field):
+        n = self.n
+        out = np.empty(n * n if field in (F_C, F_B, F_INVSQRTC) else n)
+        check(self.L.bbgpu_cmab_get(self.h, run, field, out.ctypes.data, out.size))
+        return out.reshape(n, n) if out.size == n * n else out
+
+    def set(self, run, field, a):
+        a = f64(a)
+        check(self.L.bbgpu_cmab_set(self.h, run, field, a.ctypes.data, a.size))
+
+    def set_sigma(self, run, sigma):
+        check(self.L.bbgpu_cmab_set_sigma(self.h, run, float(sigma)))
+
+    def population(self, run, lam):
+        X, f, r = np.empty((lam, self.n)), np.empty(lam), np.empty(lam, dtype=np.int32)
+        check(self.L.bbgpu_cmab_get_population(self.h, run, X.ctypes.data, f.ctypes.data, r.ctypes.data))
+        return X, f, r
+
+    def adopt_basis(self, run, B, D):
+        B, D = f64(B), f64(D)
+        check(self.L.bbgpu_cmab_adopt_basis(self.h, run, B.ctypes.data, D.ctypes.data))

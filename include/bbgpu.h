@@ -46,6 +46,7 @@ typedef struct bbgpu_ctx bbgpu_ctx;
 typedef struct bbgpu_objective bbgpu_objective;
 typedef struct bbgpu_cma bbgpu_cma;
 typedef struct bbgpu_de bbgpu_de;
+typedef struct bbgpu_cmab bbgpu_cmab;
 
 int bbgpu_version(void);
 const char *bbgpu_last_error(void);
@@ -73,7 +74,8 @@ enum bbgpu_profile_tag {
     BBGPU_PROF_DE_ROUND = 9,
     BBGPU_PROF_DE_MISC = 10,
     BBGPU_PROF_COMM = 11,       /* NCCL exchange steps of a sharded run    */
-    BBGPU_PROF_TAGS = 12
+    BBGPU_PROF_CMAB_STEP = 12,  /* batched small-n engine: whole generations */
+    BBGPU_PROF_TAGS = 13
 };
 int bbgpu_ctx_profile_enable(bbgpu_ctx *ctx, int on);
 /* synchronises, then returns summed device milliseconds and number of timed launches for tag */
@@ -330,6 +332,68 @@ int bbgpu_de_get_trace(bbgpu_de *h, int32_t *h_succ, double *h_ftrial, double *h
  * [0] start [1] sorted + parameters [2..13] rounds [16] finalized [17] L-SHADE sort [18] end;
  * [32 + 4r + k], r < 8: round r after scan / signatures / builds / grid.sync.  64 entries. */
 int bbgpu_de_phase_times(bbgpu_de *h, uint64_t *out64);
+
+/* ---- batched small-n CMA-ES engine (BASELINE config 5: thousands of independent
+ * IPOP/BIPOP runs at n <= 64).  One CTA per run; sample -> evaluate -> rank -> update -> updateSigma ->
+ * lazy eigendecomposition (the reference's tred2/tql2, inside the CTA) -> updateHistory -> converged()
+ * all run on the device, whole generations per launch (cma/base_cmaes.cpp:150-174 per run).  Only
+ * registry objectives (evaluated inside the kernel).  The restart schedule (cma/ipop_cmaes.cpp,
+ * cma/bipop_cmaes.cpp) stays with the caller: it starts base runs, steps the batch, reads the status
+ * words and restarts the runs that stopped. */
+typedef struct bbgpu_cmab_run_params { /* one base run == BaseCmaes::init + Cmaes::init */
+    int32_t lambda, mu, mfev, mit, hlen, ik; /* cma/base_cmaes.cpp:71,88-92,128-129 */
+    double sigma0, tol;
+    double cc, cs, c1, cmu, mueff, damps, chi; /* cma/base_cmaes.cpp:94-117 */
+    double eigenfreq;                          /* cma/cmaes.cpp:48 */
+    uint64_t seed;                             /* Philox key of this base run */
+    const double *weights;                     /* mu recombination weights (host; a pure function of
+                                                  lambda, cached on the device per lambda) */
+} bbgpu_cmab_run_params;
+
+typedef struct bbgpu_cmab_run_status {
+    int32_t status;  /* 0 running, 1 converged() returned true, 2 fev >= mfev, 3 decomposition failed */
+    int32_t flag;    /* Cmaes::_flag 1..9 (cma/cmaes.cpp:151-227) */
+    int32_t it, fev, lambda;
+    int32_t eig_count; /* decompositions so far */
+    int32_t eig_due;   /* replay mode: the gate fired in the last step, the caller adopts a basis */
+    int32_t hsig;
+    int32_t ql_iters;  /* QL iterations spent by the in-CTA solver so far */
+    int32_t generations_this_step;
+    int32_t ibw[4];
+    double ybw[4];
+    double sigma, fx_final /* f(bestSolution()) */, pslen, fkth, hist_best, hist_worst;
+} bbgpu_cmab_run_status;
+
+int bbgpu_cmab_create(bbgpu_ctx *ctx, int n, int runs, int bound, const double *h_lower,
+                      const double *h_upper, bbgpu_cmab **out);
+int bbgpu_cmab_destroy(bbgpu_cmab *h);
+/* (re)start `count` runs: m = guess (count*n, host), paths = 0, D = 1, C = B = C^-1/2 = I.
+ * keep_offdiag != 0: only the diagonals of B and C are reset (the reference re-inits the same object
+ * on a restart, cma/cmaes.cpp:53-60) */
+int bbgpu_cmab_start(bbgpu_cmab *h, int count, const int32_t *run_ids,
+                     const bbgpu_cmab_run_params *params, const double *h_guess, int keep_offdiag);
+/* advance the listed runs (async on the ctx stream): each run does whole generations until it stops,
+ * has spent `quantum` evaluations in this call, or has done max_gens generations.
+ * h_z != NULL (needs max_gens == 1): DRAW REPLAY, sum(lambda_r)*n standard normals, runs in list
+ * order, candidate-major.  eig_mode 0: in-CTA decomposition; 1: EIGENBASIS REPLAY -- the gate only
+ * raises status.eig_due and the caller calls bbgpu_cmab_adopt_basis. */
+int bbgpu_cmab_step(bbgpu_cmab *h, bbgpu_objective *obj, int count, const int32_t *run_ids,
+                    int quantum, int max_gens, const double *h_z, int eig_mode);
+/* synchronise; status words of ALL runs (h_out[runs]) */
+int bbgpu_cmab_fetch(bbgpu_cmab *h, bbgpu_cmab_run_status *h_out);
+/* bestSolution() of runs [run0, run0+count) (cma/base_cmaes.cpp:232-238), count*n doubles */
+int bbgpu_cmab_get_best(bbgpu_cmab *h, int run0, int count, double *h_x);
+/* per-run state, fields BBGPU_CMA_XMEAN, _XOLD, _PC, _PS, _C, _B, _D, _INVSQRTC */
+int bbgpu_cmab_get(bbgpu_cmab *h, int run, int field, double *h_dst, int64_t count);
+int bbgpu_cmab_set(bbgpu_cmab *h, int run, int field, const double *h_src, int64_t count);
+int bbgpu_cmab_set_sigma(bbgpu_cmab *h, int run, double sigma);
+/* candidates, fitness (by candidate) and ranking of the run's last generation of the last step */
+int bbgpu_cmab_get_population(bbgpu_cmab *h, int run, double *h_X, double *h_f, int32_t *h_rank);
+int bbgpu_cmab_adopt_basis(bbgpu_cmab *h, int run, const double *h_B, const double *h_D);
+/* the in-CTA solver alone (unit tests): `count` symmetric n x n matrices (lower triangles read) ->
+ * B (B[i*n+j] = component i of eigenvector j), eigenvalues ascending, info = QL iterations or -1 */
+int bbgpu_eig_small_host(bbgpu_ctx *ctx, int n, int count, const double *h_A, double *h_B,
+                         double *h_D, int32_t *h_info);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

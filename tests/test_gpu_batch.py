@@ -1,0 +1,243 @@
+"""Batched small-n CMA-ES engine (bbgpu_cmab_*, SURVEY.md 8(e) row 1 / BASELINE config 5) against the oracle.
+
+Every run of a batch is one reference `Cmaes` (cma/cmaes.cpp) whose whole generation -- sampling, evaluation, ranking,
+update, updateSigma, the lazy decomposition, the history rings and converged() -- runs inside one CTA.  Parity tiers as
+for the one-handle engine: T2 trajectories under draw replay + eigenbasis replay (state within 1e-10,
+ranking bit-exact, sigma / history / stop flags equal), T4 the in-CTA tred2/tql2 against the reference's own basis on the
+same matrix, plus free-running behaviour against free-running oracle runs."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+BOX = {O.ROSENBROCK: 10.0, O.ELLIPSOID: 10.0, O.RASTRIGIN: 5.12, O.ACKLEY: 32.768, O.SPHERE: 10.0}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from bboptpy_b200 import _cabi
+    return _cabi.Context(0)
+
+
+def _objective(ctx, obj, n):
+    from bboptpy_b200 import _cabi
+    return _cabi.Objective(ctx, n, builtin=obj)
+
+
+@pytest.mark.parametrize("n", [2, 5, 16, 40, 64])
+def test_in_cta_eigensolver_invariants(ctx, n):
+    """T4: B orthonormal, B diag(w) B^T = A, ascending, eigenvalues equal LAPACK's."""
+    rng = np.random.default_rng(n)
+    count = 12
+    A = np.empty((count, n, n))
+    for c in range(count):
+        M = rng.standard_normal((n, n))
+        S = M @ M.T / n + np.diag(rng.uniform(0.1, 3.0, n))
+        if c % 3 == 0:
+            S = np.eye(n) + 1e-3 * (S + S.T)  # nearly isotropic, the early-CMA regime
+        if c % 4 == 1:
+            S *= 10.0 ** rng.integers(-8, 8)
+        A[c] = 0.5 * (S + S.T)
+    B, w, info = ctx.eig_small(A)
+    assert (info >= 0).all()
+    for c in range(count):
+        scale = np.abs(A[c]).max()
+        assert np.all(np.diff(w[c]) >= 0)
+        assert np.abs(B[c].T @ B[c] - np.eye(n)).max() < 1e-13 * n
+        assert np.abs(B[c] @ np.diag(w[c]) @ B[c].T - A[c]).max() < 1e-13 * n * scale
+        assert_close(w[c], np.linalg.eigvalsh(A[c]), rel=1e-12, what="eigenvalues")
+
+
+def test_in_cta_eigensolver_matches_the_reference_basis(ctx, port_oracle):
+    """Same matrix in, same algorithm (cmaes.cpp:285-478): the basis agrees with the reference's own, sign included,
+    whenever the spectrum is separated.  The matrices are the covariance matrices of a real run."""
+    P = port_oracle
+    n, lam = 12, 24
+    P.seed(9)
+    h = P.cma(O.VANILLA, 10 ** 9, 1e-12, lam)
+    h.init(O.ROSENBROCK, -10 * np.ones(n), 10 * np.ones(n), P.uniform(-10, 10, n))
+    Cs, Bs, Ds = [], [], []
+    last = 0
+    for g in range(150):
+        h.iterate()
+        if h.geti("eigenlastev") != last and g > 40:
+            last = h.geti("eigenlastev")
+            Cs.append(h.mat("C").copy())
+            Bs.append(h.mat("B").copy())
+            Ds.append(h.getv("D").copy())
+        last = h.geti("eigenlastev")
+    assert len(Cs) > 20
+    B, w, info = ctx.eig_small(np.array(Cs))
+    assert (info >= 0).all()
+    for c in range(len(Cs)):
+        assert_close(np.sqrt(w[c]), Ds[c], rel=1e-11, what="D")
+        gaps = np.diff(Ds[c] ** 2).min() / (Ds[c] ** 2).max()
+        assert np.abs(B[c] - Bs[c]).max() < 1e-12 / max(gaps, 1e-6), (c, gaps)
+
+
+CASES = [  # (objective, n, lambdas of the runs of one batch, generations)
+    (O.RASTRIGIN, 40, [15, 15, 30, 120, 480], 40),
+    (O.ROSENBROCK, 10, [20, 7, 64], 120),
+    (O.ACKLEY, 64, [17, 300], 25),
+]
+
+
+@pytest.mark.parametrize("obj,n,lams,gens", CASES)
+def test_batch_trajectory_replay(ctx, port_oracle, obj, n, lams, gens):
+    """T2 for every run of a batch at once: replayed draws (the oracle's z of that generation) and replayed eigenbases;
+    everything the reference holds after a generation is compared, including what the one-handle engine leaves to the
+    host (sigma, the history extremes, the stop flag)."""
+    from bboptpy_b200 import _cabi
+    P = port_oracle
+    box = BOX[obj]
+    lo, hi = -box * np.ones(n), box * np.ones(n)
+    R = len(lams)
+    P.seed(1234)
+    guesses = [P.uniform(-box, box, n) for _ in range(R)]
+    hs = []
+    for r, lam in enumerate(lams):
+        h = P.cma(O.VANILLA, 10 ** 9, 1e-12, lam, sigma0=0.3 * box)
+        h.init(obj, lo, hi, guesses[r])
+        hs.append(h)
+    batch = _cabi.CmaBatch(ctx, n, R)
+    params = [_cabi.CmaBatch.run_params(n, lam, 10 ** 9, 0.3 * box, 1e-12, seed=r) for r, lam in enumerate(lams)]
+    for r, h in enumerate(hs):  # the host derives the same constants as the reference
+        for k in ("cc", "cs", "c1", "cmu", "mueff", "damps", "chi", "eigenfreq"):
+            assert getattr(params[r], k) == h.getd(k), k
+        assert (params[r].hlen, params[r].ik, params[r].mu) == (h.geti("hlen"), h.geti("ik"), h.geti("mu"))
+    batch.start(range(R), params, np.array(guesses))
+    objective = _objective(ctx, obj, n)
+    lastev = [0] * R
+    for g in range(gens):
+        zs = []
+        for h in hs:
+            h.iterate()
+            zs.append(h.getv("z"))
+        batch.step(objective, range(R), max_gens=1, z=np.concatenate(zs), eig_replay=True)
+        st = batch.fetch()
+        for r, h in enumerate(hs):
+            lam = lams[r]
+            what = f"gen {g} run {r} (lambda {lam})"
+            fired = h.geti("eigenlastev") != lastev[r]
+            lastev[r] = h.geti("eigenlastev")
+            assert bool(st[r].eig_due) == fired, what + ": the gate fires exactly when the reference's does"
+            X, f, rank = batch.population(r, lam)
+            assert np.array_equal(rank, h.getv("fit_idx").astype(np.int32)), what + " ranking"
+            assert_close(X, h.mat("arx"), what=what + " arx")
+            assert_close(batch.get(r, _cabi.F_XMEAN), h.getv("xmean"), what=what + " xmean")
+            assert_close(batch.get(r, _cabi.F_PS), h.getv("ps"), what=what + " ps")
+            assert_close(batch.get(r, _cabi.F_PC), h.getv("pc"), what=what + " pc")
+            low = np.tril_indices(n)
+            assert_close(batch.get(r, _cabi.F_C)[low], h.mat("C")[low], what=what + " C")
+            assert_close(st[r].sigma, h.getd("sigma"), what=what + " sigma")
+            assert (st[r].it, st[r].fev) == (h.geti("it"), h.geti("fev"))
+            if h.geti("best_len") == h.geti("hlen"):
+                assert_close([st[r].hist_best, st[r].hist_worst], [h.getd("fbest"), h.getd("fworst")], what=what + " history")
+            assert list(st[r].ibw) == [int(v) for v in h.getv("ibw")]
+            if fired:
+                batch.adopt_basis(r, h.mat("B"), h.getv("D"))
+                assert_close(batch.get(r, _cabi.F_INVSQRTC), h.mat("invsqrtC"), what=what + " invsqrtC")
+            assert (st[r].status != 0) == bool(h.converged()), what + " converged()"
+            if st[r].status != 0:
+                assert st[r].flag == h.geti("flag")
+        if any(s.status != 0 for s in st):
+            break
+
+
+def test_stop_tests_fire_like_the_reference(ctx, port_oracle):
+    """Run to the reference's own stop (TolHistFun / TolX / ...) under replay: same generation, same flag, and the
+    returned solution / evaluation count of optimize() (base_cmaes.cpp:162-174)."""
+    from bboptpy_b200 import _cabi
+    P = port_oracle
+    n, lam, obj = 8, 12, O.SPHERE
+    lo, hi = -10 * np.ones(n), 10 * np.ones(n)
+    P.seed(77)
+    guess = P.uniform(-10, 10, n)
+    h = P.cma(O.VANILLA, 100000, 1e-6, lam)
+    h.init(obj, lo, hi, guess)
+    batch = _cabi.CmaBatch(ctx, n, 1)
+    batch.start([0], [_cabi.CmaBatch.run_params(n, lam, 100000, 2.0, 1e-6, seed=1)], guess[None, :])
+    objective = _objective(ctx, obj, n)
+    lastev = 0
+    for g in range(2000):
+        h.iterate()
+        batch.step(objective, [0], max_gens=1, z=h.getv("z"), eig_replay=True)
+        st = batch.fetch()[0]
+        if h.geti("eigenlastev") != lastev:
+            lastev = h.geti("eigenlastev")
+            batch.adopt_basis(0, h.mat("B"), h.getv("D"))
+        stop = bool(h.converged())
+        assert (st.status != 0) == stop, g
+        if stop:
+            break
+    assert stop and st.status == 1 and st.flag == h.geti("flag") and st.fev == h.geti("fev")
+    x = batch.best(0, 1)[0]
+    assert_close(x, h.mat("arx")[int(h.getv("ibw")[0])], rel=1e-8, what="bestSolution")
+    assert abs(st.fx_final - P.eval(obj, x)) <= 1e-8
+
+
+def test_launch_granularity_does_not_change_a_run(ctx):
+    """Whole generations per launch: one launch of many generations == many launches of one generation, bit for bit
+    (free-running Philox draws, in-CTA decomposition)."""
+    from bboptpy_b200 import _cabi
+    n, R = 40, 6
+    lams = [15, 15, 30, 60, 15, 300]
+    objective = _objective(ctx, O.RASTRIGIN, n)
+    rng = np.random.default_rng(5)
+    guesses = rng.uniform(-5, 5, (R, n))
+    out = []
+    for mode in range(2):
+        batch = _cabi.CmaBatch(ctx, n, R)
+        params = [_cabi.CmaBatch.run_params(n, lam, 40 * lam, 2.0, 1e-12, seed=100 + r) for r, lam in enumerate(lams)]
+        batch.start(range(R), params, guesses)
+        if mode == 0:
+            for _ in range(40):
+                batch.step(objective, range(R), max_gens=1)
+        else:
+            batch.step(objective, range(R), quantum=10 ** 9, max_gens=10 ** 6)
+        st = batch.fetch()
+        assert all(s.it == 40 and s.fev == 40 * lam and s.status in (1, 2) for s, lam in zip(st, lams))
+        out.append((np.array([batch.get(r, _cabi.F_C) for r in range(R)]), np.array([batch.get(r, _cabi.F_XMEAN) for r in range(R)]),
+                    np.array([s.sigma for s in st]), batch.best()))
+        assert all(s.eig_count > 5 for s in st)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
+def test_free_running_batch_solves_like_the_reference(ctx, port_oracle):
+    """No replay at all: 96 runs on the 10-D Rosenbrock function converge like the reference's own free runs
+    (success rate and evaluations to converge), every decomposition done by the in-CTA solver."""
+    from bboptpy_b200 import _cabi
+    P = port_oracle
+    n, lam, R, mfev = 10, 20, 96, 40000
+    lo, hi = -10 * np.ones(n), 10 * np.ones(n)
+    rng = np.random.default_rng(3)
+    guesses = rng.uniform(-10, 10, (R, n))
+    batch = _cabi.CmaBatch(ctx, n, R)
+    batch.start(range(R), [_cabi.CmaBatch.run_params(n, lam, mfev, 2.0, 1e-9, seed=r) for r in range(R)], guesses)
+    objective = _objective(ctx, O.ROSENBROCK, n)
+    active = list(range(R))
+    while active:
+        batch.step(objective, active, quantum=4000, max_gens=10 ** 6)
+        st = batch.fetch()
+        active = [r for r in active if st[r].status == 0]
+    fev = np.array([s.fev for s in st])
+    fx = np.array([s.fx_final for s in st])
+    assert all(s.status in (1, 2) for s in st)
+    xs = batch.best()
+    for r in range(0, R, 7):
+        assert abs(P.eval(O.ROSENBROCK, xs[r]) - fx[r]) <= 1e-8 * max(1.0, abs(fx[r]))
+    ok = fx < 1e-8
+    # the reference, free running, same guesses
+    fev_o, ok_o = [], []
+    P.seed(11)
+    for r in range(24):
+        h = P.cma(O.VANILLA, mfev, 1e-9, lam)
+        x, fe, conv = h.optimize(O.ROSENBROCK, lo, hi, guesses[r])
+        fev_o.append(fe)
+        ok_o.append(P.eval(O.ROSENBROCK, x) < 1e-8)
+    assert ok.mean() >= np.mean(ok_o) - 0.15
+    assert abs(np.median(fev[ok]) / np.median(np.array(fev_o)[np.array(ok_o)]) - 1.0) < 0.2
