@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbbgpu.so")
+LIB_PATH = os.environ.get("BBGPU_LIB_PATH") or os.path.join(_HERE, "libbbgpu.so")  # override: A/B builds of the engine
 
 OBJ_SPHERE, OBJ_ELLIPSOID, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY = range(5)
 CMA_FULL, CMA_ACTIVE, CMA_SEP = range(3)
@@ -111,6 +111,7 @@ def lib():
     L.bbgpu_ctx_sync.argtypes = [vp]
     L.bbgpu_ctx_stream.argtypes = [vp]
     L.bbgpu_ctx_stream.restype = vp
+    L.bbgpu_ctx_device.argtypes = [vp]
     L.bbgpu_ctx_launch_count.argtypes = [vp]
     L.bbgpu_ctx_launch_count.restype = i64
     L.bbgpu_ctx_profile_enable.argtypes = [vp, i]
@@ -153,6 +154,7 @@ def lib():
     L.bbgpu_comm_world.argtypes = [vp]
     L.bbgpu_comm_allreduce_sum.argtypes = [vp, vp, i64]
     L.bbgpu_comm_best_of.argtypes = [vp, vp, vp, i, P(d), P(i)]
+    L.bbgpu_comm_best_of_host.argtypes = [vp, d, vp, i, P(d), P(i)]
     L.bbgpu_dgemm_host.argtypes = [vp, i, i, i, vp, vp, vp]
     L.bbgpu_dsyrk_host.argtypes = [vp, i, i, d, vp, vp, vp]
     L.bbgpu_rank_host.argtypes = [vp, i, vp, vp]

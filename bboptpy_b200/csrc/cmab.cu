@@ -33,10 +33,13 @@ namespace {
 constexpr int NMAX = 64;            // B (n x n) lives in shared memory; lanes own coordinates (i, i + 32)
 constexpr int HCAP = 512;           // capacity of the two fitness-history rings per run
 constexpr int THREADS = 128;
-constexpr int MIN_CTAS = 8;          // 64 registers per thread: 8 CTAs (runs) per SM
+#ifndef CMAB_MIN_CTAS
+#define CMAB_MIN_CTAS 8
+#endif
+constexpr int MIN_CTAS = CMAB_MIN_CTAS; // 8: 64 registers per thread, 8 CTAs (runs) per SM
 constexpr int GROUPS = THREADS / NMAX; // thread groups splitting the ranks of the weighted mean
 constexpr int NWARPS = THREADS / 32;
-constexpr int KC = 16;              // selected steps staged per chunk of the rank-mu update
+constexpr int KC = 8;               // selected steps staged per chunk of the rank-mu update
 constexpr int SMALL_LAMBDA = 256;   // <= : counting rank; larger: bitonic network over (key, index)
 
 enum { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BUDGET = 2, ST_FAILED = 3 };
@@ -68,6 +71,14 @@ struct StepArgs {
     int *I;
 };
 
+// 1/sqrt(t) for normal positive t: hardware seed (2^-23) + one third-order correction, ~1 ulp; no special-case path
+__device__ __forceinline__ double rsqrt_nr(double t) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
+    const double e = fma(-t * y, y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
+}
+
 __device__ __forceinline__ void tri_decode(int e, int &i, int &j) {
     // e = i (i + 1) / 2 + j, j <= i
     i = (int) ((sqrtf(8.0f * (float) e + 1.0f) - 1.0f) * 0.5f);
@@ -78,209 +89,235 @@ __device__ __forceinline__ void tri_decode(int e, int &i, int &j) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // In-CTA symmetric eigendecomposition: EISPACK tred2 + tql2 as the reference uses them (cmaes.cpp:285-478), on
-// Vt[c * ldv + r] = V[r][c] in shared memory (ldv odd: rows and columns are both conflict-free), d / e / tmp length n.
+// Vt[c * ldv + r] = V[r][c] in shared memory (ldv odd: rows and columns are both conflict-free), d / e length n.
 // On exit d holds the eigenvalues (unsorted), column c of V the eigenvector of d[c].  Returns false if the QL
 // iteration did not converge (NaN input).
+//
+// ONE WARP runs the whole decomposition (the caller's other warps wait at a CTA barrier): lane L owns rows / columns L
+// and L + 32 (n <= 64).  A batch fills the chip with runs, so what counts per run is the number of issued
+// instructions, not the latency of one decomposition: spreading these O(n^2)-per-step loops over four warps cost a
+// CTA barrier per phase, redundant reductions in every warp and -- in the QL iteration, a scalar recurrence -- three
+// idle warps polling; measured 290 k warp instructions per decomposition at n = 40 against ~90 k here
+// (profiles/r01_cmab.txt).  Only __syncwarp() orders the shared-memory traffic.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ bool cta_tred2_tql2(const int n, const int ldv, double *Vt, double *d, double *e, double *tmp, double *rc,
-        double *rs, int *ctl, int *ql_iters) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid < n) d[tid] = Vt[tid * ldv + n - 1];
-    __syncthreads();
+__device__ __noinline__ bool warp_tred2_tql2(const int n, const int ldv, double *Vt, double *d, double *e, int *ql_iters) {
+    const int lane = threadIdx.x & 31;
+    const int r0 = lane, r1 = lane + 32;
+    if (r0 < n) d[r0] = Vt[r0 * ldv + n - 1];
+    if (r1 < n) d[r1] = Vt[r1 * ldv + n - 1];
+    __syncwarp();
     // ---- Householder reduction to tridiagonal form; the active block V[0:i,0:i] is kept fully symmetric
     for (int i = n - 1; i > 0; i--) {
-        double sc = 0.0;
-        for (int k = lane; k < i; k += 32) sc += fabs(d[k]);
-        sc = bb::warp_sum(sc); // every warp computes the same bits
+        const bool a0 = r0 < i, a1 = r1 < i;
+        const double v0 = a0 ? d[r0] : 0.0, v1 = a1 ? d[r1] : 0.0;
+        const double sc = bb::warp_sum(fabs(v0) + fabs(v1));
         if (sc == 0.0) {
-            __syncthreads();
-            if (tid == 0) e[i] = d[i - 1];
-            __syncthreads();
-            if (tid < i) {
-                d[tid] = Vt[tid * ldv + i - 1];
-                Vt[tid * ldv + i] = 0.0;
-                Vt[i * ldv + tid] = 0.0;
-            }
-            if (tid == 0) d[i] = 0.0;
-            __syncthreads();
+            const double dl = d[i - 1];
+            __syncwarp();
+            if (lane == 0) e[i] = dl;
+            if (a0) { d[r0] = Vt[r0 * ldv + i - 1]; Vt[r0 * ldv + i] = 0.0; Vt[i * ldv + r0] = 0.0; }
+            if (a1) { d[r1] = Vt[r1 * ldv + i - 1]; Vt[r1 * ldv + i] = 0.0; Vt[i * ldv + r1] = 0.0; }
+            if (lane == 0) d[i] = 0.0;
+            __syncwarp();
             continue;
         }
-        double hs = 0.0;
-        for (int k = lane; k < i; k += 32) {
-            const double t = d[k] / sc;
-            hs += t * t;
-        }
-        hs = bb::warp_sum(hs);
+        const double t0 = v0 / sc, t1 = v1 / sc;
+        const double hs = bb::warp_sum(t0 * t0 + t1 * t1);
         const double f = d[i - 1] / sc;
         double g = sqrt(hs);
         if (f > 0) g = -g;
         const double h = hs - f * g;
-        __syncthreads();
-        if (tid < i) d[tid] = (tid == i - 1) ? f - g : d[tid] / sc;
-        if (tid == 0) e[i] = sc * g;
-        __syncthreads();
-        if (tid < i) { // p = A d / h;  V[j][i] = d[j]
-            double s = 0.0;
-            for (int k = 0; k < i; k++) s = fma(Vt[k * ldv + tid], d[k], s);
-            Vt[i * ldv + tid] = d[tid];
-            e[tid] = s / h;
+        __syncwarp();
+        const double dr0 = (r0 == i - 1) ? f - g : t0, dr1 = (r1 == i - 1) ? f - g : t1; // the Householder vector
+        if (a0) d[r0] = dr0;
+        if (a1) d[r1] = dr1;
+        if (lane == 0) e[i] = sc * g;
+        __syncwarp();
+        // p = A d / h (rows r0, r1), two interleaved partial sums per row; V[j][i] = d[j]
+        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+        {
+            int k = 0;
+            for (; k + 1 < i; k += 2) {
+                const double dk = d[k], dk1 = d[k + 1];
+                if (a0) { p0 = fma(Vt[k * ldv + r0], dk, p0); q0 = fma(Vt[(k + 1) * ldv + r0], dk1, q0); }
+                if (a1) { p1 = fma(Vt[k * ldv + r1], dk, p1); q1 = fma(Vt[(k + 1) * ldv + r1], dk1, q1); }
+            }
+            if (k < i) {
+                const double dk = d[k];
+                if (a0) p0 = fma(Vt[k * ldv + r0], dk, p0);
+                if (a1) p1 = fma(Vt[k * ldv + r1], dk, p1);
+            }
         }
-        __syncthreads();
-        double fs = 0.0;
-        for (int k = lane; k < i; k += 32) fs += e[k] * d[k];
-        fs = bb::warp_sum(fs);
+        p0 = (p0 + q0) / h;
+        p1 = (p1 + q1) / h;
+        if (a0) Vt[i * ldv + r0] = dr0;
+        if (a1) Vt[i * ldv + r1] = dr1;
+        const double fs = bb::warp_sum((a0 ? p0 * dr0 : 0.0) + (a1 ? p1 * dr1 : 0.0));
         const double hh = fs / (h + h);
-        __syncthreads();
-        if (tid < i) e[tid] -= hh * d[tid];
-        __syncthreads();
-        for (int j = wid; j < i; j += NWARPS) {
-            const double dj = d[j], ej = e[j];
-            for (int k = lane; k < i; k += 32) Vt[j * ldv + k] -= dj * e[k] + ej * d[k];
+        const double er0 = p0 - hh * dr0, er1 = p1 - hh * dr1;
+        if (a0) e[r0] = er0;
+        if (a1) e[r1] = er1;
+        __syncwarp();
+        // rank-2 update of rows r0, r1 over all columns of the block
+        for (int k = 0; k < i; k++) {
+            const double ek = e[k], dk = d[k];
+            if (a0) Vt[k * ldv + r0] -= dr0 * ek + er0 * dk;
+            if (a1) Vt[k * ldv + r1] -= dr1 * ek + er1 * dk;
         }
-        __syncthreads();
-        if (tid < i) {
-            d[tid] = Vt[tid * ldv + i - 1];
-            Vt[tid * ldv + i] = 0.0;
-        }
-        if (tid == 0) d[i] = h;
-        __syncthreads();
+        __syncwarp();
+        if (a0) { d[r0] = Vt[r0 * ldv + i - 1]; Vt[r0 * ldv + i] = 0.0; }
+        if (a1) { d[r1] = Vt[r1 * ldv + i - 1]; Vt[r1 * ldv + i] = 0.0; }
+        if (lane == 0) d[i] = h;
+        __syncwarp();
     }
-    // ---- accumulate the transformations
+    // ---- accumulate the transformations (lane L owns columns L, L + 32)
     for (int i = 0; i < n - 1; i++) {
-        if (tid == 0) {
+        if (lane == 0) {
             Vt[i * ldv + n - 1] = Vt[i * ldv + i];
             Vt[i * ldv + i] = 1.0;
         }
         const double h = d[i + 1];
-        __syncthreads();
+        __syncwarp();
+        const bool a0 = r0 <= i, a1 = r1 <= i;
+        double *u = Vt + (i + 1) * ldv;
         if (h != 0.0) {
-            if (tid <= i) {
-                double g = 0.0;
-                for (int k = 0; k <= i; k++) g = fma(Vt[(i + 1) * ldv + k], Vt[tid * ldv + k], g);
-                tmp[tid] = g;
-                d[tid] = Vt[(i + 1) * ldv + tid] / h;
+            double g0 = 0.0, g1 = 0.0, w0 = 0.0, w1 = 0.0;
+            const double *c0 = Vt + r0 * ldv, *c1 = Vt + r1 * ldv;
+            int k = 0;
+            for (; k + 1 <= i; k += 2) {
+                const double uk = u[k], uk1 = u[k + 1];
+                if (a0) { g0 = fma(uk, c0[k], g0); w0 = fma(uk1, c0[k + 1], w0); }
+                if (a1) { g1 = fma(uk, c1[k], g1); w1 = fma(uk1, c1[k + 1], w1); }
             }
-            __syncthreads();
-            for (int j = wid; j <= i; j += NWARPS) {
-                const double g = tmp[j];
-                for (int k = lane; k <= i; k += 32) Vt[j * ldv + k] -= g * d[k];
+            if (k <= i) {
+                const double uk = u[k];
+                if (a0) g0 = fma(uk, c0[k], g0);
+                if (a1) g1 = fma(uk, c1[k], g1);
             }
-            __syncthreads();
+            g0 += w0;
+            g1 += w1;
+            if (a0) d[r0] = u[r0] / h;
+            if (a1) d[r1] = u[r1] / h;
+            __syncwarp();
+            for (k = 0; k <= i; k++) {
+                const double dk = d[k];
+                if (a0) Vt[r0 * ldv + k] -= g0 * dk;
+                if (a1) Vt[r1 * ldv + k] -= g1 * dk;
+            }
+            __syncwarp();
         }
-        if (tid <= i) Vt[(i + 1) * ldv + tid] = 0.0;
-        __syncthreads();
+        if (a0) u[r0] = 0.0;
+        if (a1) u[r1] = 0.0;
+        __syncwarp();
     }
-    if (tid < n) {
-        d[tid] = Vt[tid * ldv + n - 1];
-        Vt[tid * ldv + n - 1] = (tid == n - 1) ? 1.0 : 0.0;
+    {
+        const double x0 = r0 < n ? Vt[r0 * ldv + n - 1] : 0.0, x1 = r1 < n ? Vt[r1 * ldv + n - 1] : 0.0;
+        const double s0 = r0 + 1 < n ? e[r0 + 1] : 0.0, s1 = r1 + 1 < n ? e[r1 + 1] : 0.0;
+        __syncwarp();
+        if (r0 < n) { d[r0] = x0; Vt[r0 * ldv + n - 1] = (r0 == n - 1) ? 1.0 : 0.0; e[r0] = s0; }
+        if (r1 < n) { d[r1] = x1; Vt[r1 * ldv + n - 1] = (r1 == n - 1) ? 1.0 : 0.0; e[r1] = s1; }
+        __syncwarp();
     }
-    double esh = 0.0;
-    if (tid < n - 1) esh = e[tid + 1];
-    __syncthreads();
-    if (tid < n) e[tid] = (tid < n - 1) ? esh : 0.0;
-    __syncthreads();
-    // ---- implicit QL with accumulation.  Thread 0 runs the scalar recurrence of one iteration (rotations into
-    // rc/rs), then the rows of V take the rotations in parallel (thread k owns row k).
+    // ---- implicit QL with accumulation (cmaes.cpp:383-463).  Every lane runs the scalar recurrence (identical values:
+    // one warp instruction either way) and applies each rotation to its own two rows of V straight from registers.
     const double eps = 2.220446049250313e-16;
+    const int rc0 = min(r0, n - 1), rc1 = r1 < n ? r1 : rc0;
     double fsh = 0.0, tst1 = 0.0;
     int iters = 0;
-    bool ok = true;
     for (int l = 0; l < n; l++) {
-        if (tid == 0) {
-            tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
-            int m = l;
-            while (m < n && !(fabs(e[m]) <= eps * tst1)) m++;
-            ctl[0] = m;
-        }
-        __syncthreads();
-        const int m = ctl[0];
-        __syncthreads();
-        if (m >= n) { // cmaes.cpp:399-401 leaves the loop here (only reachable with non-finite input)
-            ok = false;
-            break;
-        }
+        tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+        int m = l;
+        while (m < n && !(fabs(e[m]) <= eps * tst1)) m++;
+        if (m >= n) return false; // cmaes.cpp:399-401 leaves the loop here (only reachable with non-finite input)
         if (m > l) {
             while (true) {
-                if (wid == 0) {
-                    double g = d[l], hshift = 0.0, dl1 = 0.0, el1 = 0.0;
-                    if (lane == 0) {
-                        const double p0 = (d[l + 1] - g) / (2.0 * e[l]);
-                        double r0 = sqrt(fma(p0, p0, 1.0));
-                        if (p0 < 0) r0 = -r0;
-                        d[l] = e[l] / (p0 + r0);
-                        d[l + 1] = e[l] * (p0 + r0);
-                        dl1 = d[l + 1];
-                        hshift = g - d[l];
-                        el1 = e[l + 1];
-                    }
-                    hshift = __shfl_sync(0xffffffffu, hshift, 0);
-                    __syncwarp();
-                    for (int i = l + 2 + lane; i < n; i += 32) d[i] -= hshift;
-                    __syncwarp();
-                    if (lane == 0) {
-                        fsh += hshift;
-                        double p = d[m], c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
-                        for (int i = m - 1; i >= l; i--) {
-                            c3 = c2;
-                            c2 = c;
-                            s2 = s;
-                            const double ei = e[i], di = d[i];
-                            g = c * ei;
-                            const double hq = c * p;
-                            const double r = sqrt(fma(p, p, ei * ei));
-                            e[i + 1] = s * r;
-                            s = ei / r;
-                            c = p / r;
-                            p = c * di - s * g;
-                            d[i + 1] = hq + s * (c * g + s * di);
-                            rc[i] = c;
-                            rs[i] = s;
-                        }
-                        p = -s * s2 * c3 * el1 * e[l] / dl1;
-                        e[l] = s * p;
-                        d[l] = c * p;
-                        iters++;
-                        ctl[1] = (fabs(e[l]) > eps * tst1) ? 1 : 0;
-                        if (iters > 60 * n || !(p == p)) ctl[1] = 2;
-                    }
+                double g = d[l];
+                const double el = e[l];
+                const double p0 = (d[l + 1] - g) / (2.0 * el);
+                double rr = sqrt(fma(p0, p0, 1.0));
+                if (p0 < 0) rr = -rr;
+                const double dl = el / (p0 + rr), dl1 = el * (p0 + rr);
+                const double hshift = g - dl, el1 = e[l + 1];
+                __syncwarp();
+                if (lane == 0) { d[l] = dl; d[l + 1] = dl1; }
+                for (int i = l + 2 + lane; i < n; i += 32) d[i] -= hshift;
+                __syncwarp();
+                fsh += hshift;
+                // one Givens rotation per step: r = hypot(p, e_i), s = e_i / r, c = p / r (cmaes.cpp:432-437) through
+                // ONE reciprocal square root: the recurrence is a dependency chain, two divisions and a square root per
+                // step were most of its length.  The loop is branch free: pointers walk the columns, every lane stores the
+                // (identical) new d / e, and lanes without a row of their own redo row n-1 (same loads, same values).
+                double p = d[m], c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
+                const double *pe = e + (m - 1), *pd = d + (m - 1);
+                double *we = e + m, *wd = d + m;
+                double ei = *pe, di = *pd;
+                double *q0 = Vt + m * ldv + rc0, *q1 = Vt + m * ldv + rc1;
+                double h0 = *q0, h1 = *q1;
+                for (int cnt = m - l; cnt > 0; cnt--) {
+                    const int back = cnt > 1 ? -1 : 0; // next step's operands (none after the last step)
+                    const double en = pe[back], dn = pd[back];
+                    const double vi0 = q0[-ldv], vi1 = q1[-ldv];
+                    c3 = c2;
+                    c2 = c;
+                    s2 = s;
+                    g = c * ei;
+                    const double hq = c * p;
+                    const double t = fma(p, p, ei * ei);
+                    const double rinv = rsqrt_nr(t);
+                    const double enew = s * (t * rinv);
+                    s = ei * rinv;
+                    c = p * rinv;
+                    p = c * di - s * g;
+                    *we = enew;
+                    *wd = hq + s * (c * g + s * di);
+                    *q0 = fma(s, vi0, c * h0);
+                    *q1 = fma(s, vi1, c * h1);
+                    h0 = fma(c, vi0, -s * h0);
+                    h1 = fma(c, vi1, -s * h1);
+                    ei = en;
+                    di = dn;
+                    pe--; pd--; we--; wd--;
+                    q0 -= ldv;
+                    q1 -= ldv;
                 }
-                __syncthreads();
-                if (tid < n) {
-                    double h = Vt[m * ldv + tid];
-                    for (int i = m - 1; i >= l; i--) {
-                        const double c = rc[i], s = rs[i], vi = Vt[i * ldv + tid];
-                        Vt[(i + 1) * ldv + tid] = fma(s, vi, c * h);
-                        h = fma(c, vi, -s * h);
-                    }
-                    Vt[l * ldv + tid] = h;
-                }
-                const int again = ctl[1];
-                __syncthreads();
-                if (again == 2) ok = false;
-                if (again != 1) break;
+                *q0 = h0;
+                *q1 = h1;
+                __syncwarp();
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                __syncwarp();
+                if (lane == 0) { e[l] = s * p; d[l] = c * p; }
+                __syncwarp();
+                iters++;
+                if (iters > 60 * n || !(p == p)) return false;
+                if (!(fabs(s * p) > eps * tst1)) break;
             }
-            if (!ok) break;
         }
-        if (tid == 0) {
-            d[l] += fsh;
-            e[l] = 0.0;
-        }
+        __syncwarp();
+        if (lane == 0) { d[l] += fsh; e[l] = 0.0; }
+        __syncwarp();
     }
-    __syncthreads();
-    if (tid == 0) *ql_iters = iters;
-    return ok;
+    if (lane == 0) *ql_iters = iters;
+    return true;
 }
 
 // C^-1/2 = B D^-1 B^T (cmaes.cpp:273-282) from Bt (shared, Bt[c * ldv + r] = B[r][c]) and D (shared)
-__device__ void cta_invsqrt(const int n, const int ldv, const double *Vt, const double *vD, double *isC) {
+__device__ void cta_invsqrt(const int n, const int ldv, const double *Vt, const double *vD, double *rD, double *isC) {
+    if (threadIdx.x < n) rD[threadIdx.x] = 1.0 / vD[threadIdx.x];
+    __syncthreads();
     const int ne = n * (n + 1) / 2;
     for (int e = threadIdx.x; e < ne; e += THREADS) {
         int i, j;
         tri_decode(e, i, j);
-        double s = 0.0;
-        for (int k = 0; k < n; k++) s += Vt[k * ldv + i] / vD[k] * Vt[k * ldv + j];
-        isC[i * n + j] = s;
-        isC[j * n + i] = s;
+        double s0 = 0.0, s1 = 0.0;
+        int k = 0;
+        for (; k + 1 < n; k += 2) {
+            s0 = fma(Vt[k * ldv + i] * rD[k], Vt[k * ldv + j], s0);
+            s1 = fma(Vt[(k + 1) * ldv + i] * rD[k + 1], Vt[(k + 1) * ldv + j], s1);
+        }
+        if (k < n) s0 = fma(Vt[k * ldv + i] * rD[k], Vt[k * ldv + j], s0);
+        const double sum = s0 + s1;
+        isC[i * n + j] = sum;
+        isC[j * n + i] = sum;
     }
 }
 
@@ -298,8 +335,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
     RunDev *R = a.runs + run;
     double *Vt = (double*) smem_raw;
     double *xm = Vt + n * ldv, *xo = xm + n, *vpc = xo + n, *vps = vpc + n, *vD = vps + n, *ve = vD + n, *vt = ve + n;
-    double *rc = vt + n, *rs = rc + n;
-    double *xrow = rs + n;                 // NWARPS * n
+    double *xrow = vt + n;                 // NWARPS * n
     double *ysel = xrow + NWARPS * n;      // max(KC * n, GROUPS * NMAX)
     double *cw = ysel + max(KC * n, GROUPS * NMAX); // KC
     double *red = cw + KC;                 // 32
@@ -525,9 +561,16 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
                 Vt[c * ldv + r] = gC[max(r, c) * n + min(r, c)];
             }
             __syncthreads();
-            int qi = 0;
-            const bool ok = cta_tred2_tql2(n, ldv, Vt, vD, ve, vt, rc, rs, ctl, &qi);
-            if (tid == 0) S.ql_iters += qi;
+            if (wid == 0) {
+                int qi = 0;
+                const bool okw = warp_tred2_tql2(n, ldv, Vt, vD, ve, &qi);
+                if (lane == 0) {
+                    ctl[3] = okw ? 1 : 0;
+                    if (okw) S.ql_iters += qi;
+                }
+            }
+            __syncthreads();
+            const bool ok = ctl[3] != 0;
             if (!ok) {
                 __syncthreads();
                 if (tid == 0) { S.status = ST_FAILED; S.flag = -1; }
@@ -574,7 +617,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
                 Vt[c * ldv + r] = gB[idx];
             }
             __syncthreads();
-            cta_invsqrt(n, ldv, Vt, vD, gisC);
+            cta_invsqrt(n, ldv, Vt, vD, ve, gisC);
             __syncthreads();
         }
         // updateHistory (base_cmaes.cpp:191-209), _it++, converged() (cmaes.cpp:151-227): warp 0
@@ -731,7 +774,7 @@ __global__ void __launch_bounds__(THREADS) cmab_invsqrt_kernel(int n, int ldv, c
     }
     if (threadIdx.x < n) vD[threadIdx.x] = D[threadIdx.x];
     __syncthreads();
-    cta_invsqrt(n, ldv, Vt, vD, isC);
+    cta_invsqrt(n, ldv, Vt, vD, vD + n, isC);
 }
 
 // standalone decomposition of count symmetric matrices (unit tests of the in-CTA solver)
@@ -746,11 +789,16 @@ __global__ void __launch_bounds__(THREADS) cmab_eig_kernel(int n, int ldv, const
         Vt[c * ldv + r] = gA[max(r, c) * n + min(r, c)];
     }
     __syncthreads();
-    int qi = 0;
-    const bool ok = cta_tred2_tql2(n, ldv, Vt, d, e, tmp, rc, rs, ctl, &qi);
+    if (tid < 32) {
+        int qi = 0;
+        const bool okw = warp_tred2_tql2(n, ldv, Vt, d, e, &qi);
+        if (tid == 0) {
+            ctl[3] = okw ? 1 : 0;
+            info[blockIdx.x] = okw ? qi : -1;
+        }
+    }
     __syncthreads();
-    if (tid == 0) info[blockIdx.x] = ok ? qi : -1;
-    if (!ok) return;
+    if (ctl[3] == 0) return;
     int pos = 0;
     double val = 0.0;
     if (tid < n) {
@@ -764,7 +812,7 @@ __global__ void __launch_bounds__(THREADS) cmab_eig_kernel(int n, int ldv, const
 }
 
 size_t step_smem_bytes(int n, int ldv, int sort_cap) {
-    size_t doubles = (size_t) n * ldv + 9 * (size_t) n + (size_t) NWARPS * n + (size_t) std::max(KC * n, GROUPS * NMAX) + KC + 32;
+    size_t doubles = (size_t) n * ldv + 7 * (size_t) n + (size_t) NWARPS * n + (size_t) std::max(KC * n, GROUPS * NMAX) + KC + 32;
     return doubles * 8 + (size_t) sort_cap * 12;
 }
 
@@ -789,6 +837,7 @@ struct bbgpu_cmab {
     double *d_guess = nullptr;
     std::map<int, double*> weights; // lambda -> device table of mu weights (base_cmaes.cpp:94-100)
     bool attr_small = false, attr_large = false;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr; // the large-lambda class runs on the ctx's side stream
 };
 
 namespace {
@@ -881,6 +930,8 @@ int bbgpu_cmab_destroy(bbgpu_cmab *h) {
             h->B, h->isC, h->hbest, h->hkth, h->d_guess, h->lower, h->upper, h->X, h->F, h->I, h->Z };
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &kv : h->weights) cudaFree(kv.second);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return BBGPU_OK;
 }
@@ -994,6 +1045,28 @@ int bbgpu_cmab_step(bbgpu_cmab *h, bbgpu_objective *obj, int count, const int32_
     a.lower = h->lower; a.upper = h->upper; a.aux = obj->d_aux; a.Z = h_z ? h->Z : nullptr;
     a.X = h->X; a.F = h->F; a.I = h->I;
     bb::ProfScope prof(ctx, BBGPU_PROF_CMAB_STEP);
+    if (nl > 0) {
+        int P = 2;
+        while (P < maxlam) P <<= 1;
+        a.list = h->d_list + h->runs;
+        a.sort_cap = P;
+        const size_t smem = step_smem_bytes(n, h->ldv, a.sort_cap);
+        if (smem > 220 * 1024)
+            return bb::fail(BBGPU_ERR_ARG, "bbgpu_cmab_step: lambda = %d needs %zu bytes of shared memory for the ranking", maxlam, smem);
+        BB_CUDA(cudaFuncSetAttribute(cmab_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        // independent runs: the large class goes to the side stream and overlaps the small class (fork after the
+        // uploads above, join before anything later on the main stream)
+        if (!ctx->aux) BB_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+        if (!h->ev_fork) {
+            BB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            BB_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+        BB_CUDA(cudaEventRecord(h->ev_fork, st));
+        BB_CUDA(cudaStreamWaitEvent(ctx->aux, h->ev_fork, 0));
+        cmab_step_kernel<true><<<nl, THREADS, smem, ctx->aux>>>(a);
+        BB_TRY(bb::launched(ctx, "cmab_step_kernel<large>"));
+        BB_CUDA(cudaEventRecord(h->ev_join, ctx->aux));
+    }
     if (ns > 0) {
         a.list = h->d_list;
         a.sort_cap = SMALL_LAMBDA;
@@ -1005,18 +1078,7 @@ int bbgpu_cmab_step(bbgpu_cmab *h, bbgpu_objective *obj, int count, const int32_
         cmab_step_kernel<false><<<ns, THREADS, smem, st>>>(a);
         BB_TRY(bb::launched(ctx, "cmab_step_kernel<small>"));
     }
-    if (nl > 0) {
-        int P = 2;
-        while (P < maxlam) P <<= 1;
-        a.list = h->d_list + h->runs;
-        a.sort_cap = P;
-        const size_t smem = step_smem_bytes(n, h->ldv, a.sort_cap);
-        if (smem > 220 * 1024)
-            return bb::fail(BBGPU_ERR_ARG, "bbgpu_cmab_step: lambda = %d needs %zu bytes of shared memory for the ranking", maxlam, smem);
-        BB_CUDA(cudaFuncSetAttribute(cmab_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        cmab_step_kernel<true><<<nl, THREADS, smem, st>>>(a);
-        BB_TRY(bb::launched(ctx, "cmab_step_kernel<large>"));
-    }
+    if (nl > 0) BB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     obj->evals += 0; // the per-run counters live in the status words
     return BBGPU_OK;
 }
@@ -1085,7 +1147,7 @@ int bbgpu_cmab_adopt_basis(bbgpu_cmab *h, int run, const double *h_B, const doub
     const size_t vo = (size_t) run * n, mo = (size_t) run * n * n;
     BB_CUDA(cudaMemcpyAsync(h->B + mo, h_B, sizeof(double) * n * n, cudaMemcpyHostToDevice, st));
     BB_CUDA(cudaMemcpyAsync(h->D + vo, h_D, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    cmab_invsqrt_kernel<<<1, THREADS, ((size_t) n * h->ldv + n) * 8, st>>>(n, h->ldv, h->B + mo, h->D + vo, h->isC + mo);
+    cmab_invsqrt_kernel<<<1, THREADS, ((size_t) n * h->ldv + 2 * n) * 8, st>>>(n, h->ldv, h->B + mo, h->D + vo, h->isC + mo);
     BB_TRY(bb::launched(h->ctx, "cmab_invsqrt_kernel"));
     BB_CUDA(cudaStreamSynchronize(st));
     return BBGPU_OK;

@@ -190,4 +190,19 @@ int bbgpu_comm_best_of(bbgpu_comm *c, const double *d_f, double *d_x, int n, dou
     return BBGPU_OK;
 }
 
+// host-buffer form: f and x live on the host (the batched drivers keep their per-run bests there)
+int bbgpu_comm_best_of_host(bbgpu_comm *c, double f, double *h_x, int n, double *h_fbest, int *h_owner) {
+    BB_ARG(c && h_x && n > 0 && h_fbest && h_owner);
+    cudaStream_t st = c->ctx->stream;
+    void *sp = nullptr;
+    BB_TRY(c->ctx->scratch(sizeof(double) * ((size_t) n + 1), &sp));
+    double *d = (double*) sp;
+    BB_CUDA(cudaMemcpyAsync(d, &f, sizeof(double), cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(d + 1, h_x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    BB_TRY(bbgpu_comm_best_of(c, d, d + 1, n, h_fbest, h_owner));
+    BB_CUDA(cudaMemcpyAsync(h_x, d + 1, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BBGPU_OK;
+}
+
 } // extern "C"

@@ -160,6 +160,8 @@ int bbgpu_ctx_flush_l2(bbgpu_ctx *ctx) {
     return BBGPU_OK;
 }
 
+int bbgpu_ctx_device(bbgpu_ctx *ctx) { return ctx ? ctx->device : -1; }
+
 void *bbgpu_ctx_stream(bbgpu_ctx *ctx) { return ctx ? (void*) ctx->stream : nullptr; }
 
 int64_t bbgpu_ctx_launch_count(bbgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "cma.h"
+#include "schedule.h"
 
 // console table of the `print=True` mode (same column layout as the reference's Tabular)
 class RowPrinter {
@@ -22,9 +23,8 @@ public:
 
 class IPopCmaes: public MultivariateOptimizer {
 protected:
-    bool _print, _nipop, _boundlambda;
-    int _n, _mfev, _it, _fev, _lambdadef, _lambdamax, _lambda;
-    double _sigmadef, _sigma, _ksigmadec, _fbest, _fx;
+    bool _print;
+    IPopSchedule _s; // the restart bookkeeping (schedule.h), shared with the batched driver
     multivariate_problem _f;
     BaseCmaes *_base;
     RowPrinter _table;
@@ -36,19 +36,17 @@ public:
     void iterate();
     multivariate_solution solution();
     multivariate_solution optimize(const multivariate_problem &f, const double *guess);
-    int lambda() const { return _lambda; }
-    double sigma() const { return _sigma; }
-    int evaluations() const { return _fev; }
+    int lambda() const { return _s._lambda; }
+    double sigma() const { return _s._sigma; }
+    int evaluations() const { return _s._fev; }
 private:
-    int computeMaxEvaluations(const int lambda);
+    void runBase(const base_run_request &req, const double *x0);
 };
 
 class BiPopCmaes: public MultivariateOptimizer {
 protected:
-    bool _print, _nbipop;
-    int _n, _mfev, _fev, _maxlargeruns, _lambdadef, _largelambda, _smalllambda, _largebudget, _smallbudget,
-            _largerestarts, _smallrestarts, _it, _bestregime;
-    double _fx, _sigmadef, _largesigma, _smallsigma, _fxbest, _ksigmadec, _kbudget;
+    bool _print;
+    BiPopSchedule _s;
     multivariate_problem _f;
     BaseCmaes *_base;
     RowPrinter _table;
@@ -60,13 +58,12 @@ public:
     void iterate();
     multivariate_solution solution();
     multivariate_solution optimize(const multivariate_problem &f, const double *guess);
-    int evaluations() const { return _fev; }
-    int largeRestarts() const { return _largerestarts; }
-    int smallRestarts() const { return _smallrestarts; }
+    int evaluations() const { return _s._fev; }
+    int largeRestarts() const { return _s._largerestarts; }
+    int smallRestarts() const { return _s._smallrestarts; }
 private:
-    int computeMaxEvaluations(const int lambda);
-    void runFirstRegime();
-    void runSecondRegime();
+    void runBase(const base_run_request &req, const double *x0);
+    void printRow();
 };
 
 #endif

@@ -20,6 +20,7 @@
 #include "cma.h"
 #include "de.h"
 #include "restart.h"
+#include "batch.h"
 
 namespace py = pybind11;
 using namespace pybind11::literals;
@@ -184,6 +185,59 @@ PYBIND11_MODULE(_bboptpy, m) {
         .def_property_readonly("n_evals", &BiPopCmaes::evaluations)
         .def_property_readonly("large_restarts", &BiPopCmaes::largeRestarts)
         .def_property_readonly("small_restarts", &BiPopCmaes::smallRestarts);
+
+    // batches of independent IPOP / BIPOP runs on the batched small-n engine (an addition: the reference's unit of
+    // work is one optimizer object).  Keywords follow IPopCMAES / BiPopCMAES; `tol` and `eigenrate` are the base
+    // CMAES's own (its np / sigma0 / mfev are set by the restart schedule, cma/bipop_cmaes.cpp:80,215,251).
+    auto batch_optimize = [](RestartBatch &self, py::object py_f, py::array_t<double> py_lower, py::array_t<double> py_upper,
+            py::array_t<double, py::array::c_style | py::array::forcecast> py_guesses) {
+        multivariate_problem prob = make_problem(py_f, py_lower, py_upper);
+        if (py_guesses.size() != (py::ssize_t) self.totalRuns() * prob._n)
+            throw std::invalid_argument("guesses must have shape (runs, n)");
+        return self.optimize(prob, py_guesses.data());
+    };
+    py::class_<restart_batch_stats>(m, "RestartBatchStats")
+        .def_readonly("base_runs", &restart_batch_stats::base_runs)
+        .def_readonly("generations", &restart_batch_stats::generations)
+        .def_readonly("evaluations", &restart_batch_stats::evaluations)
+        .def_readonly("decompositions", &restart_batch_stats::decompositions)
+        .def_readonly("launches", &restart_batch_stats::launches)
+        .def_readonly("device_ms", &restart_batch_stats::device_ms);
+    py::class_<RestartBatch>(m, "RestartBatch")
+        .def("optimize", batch_optimize, "f"_a, "lower"_a, "upper"_a, "guesses"_a,
+             "Run every run of the batch (this rank's share of it) to completion; returns their MultivariateSolutions")
+        .def("set_communicator", [](RestartBatch &self, PyComm &c) { self.setCommunicator(c.h); }, "comm"_a, py::keep_alive<1, 2>(),
+             "Shard the runs over the ranks of `comm`: this process runs the runs r with r % world == rank")
+        .def("set_quantum", &RestartBatch::setQuantum, "evals"_a, "Evaluations a run may spend per launch")
+        .def("set_timing", &RestartBatch::setTiming, "on"_a)
+        .def("set_streams", &RestartBatch::setStreams, "streams"_a, "Concurrent streams the runs are dealt to (0 = automatic)")
+        .def_property_readonly("run_ids", [](RestartBatch &self) { return self.runIds(); })
+        .def_property_readonly("best_values", [](RestartBatch &self) { return as_array(self.bestValues()); })
+        .def_property_readonly("stats", [](RestartBatch &self) { return self.stats(); })
+        .def("best_of", [](RestartBatch &self) {
+            std::vector<double> x;
+            int owner = -1;
+            const double f = self.bestOf(x, &owner);
+            return py::make_tuple(f, owner, as_array(x));
+        }, "Best run of the whole batch over all ranks (one NCCL best-of reduce): (f, global run id, x)");
+    struct BiPopBatch: public RestartBatch { using RestartBatch::RestartBatch; };
+    struct IPopBatch: public RestartBatch { using RestartBatch::RestartBatch; };
+    py::class_<BiPopBatch, RestartBatch>(m, "BiPopCMAESBatch")
+        .def(py::init([](int runs, int mfev, double tol, double sigma0, int maxlargeruns, bool nbipop, double ksigmadec,
+                double kbudget, double eigenrate) {
+            auto *b = new BiPopBatch(RestartBatch::BIPOP, runs, mfev, tol, sigma0, eigenrate);
+            b->configureBiPop(maxlargeruns, nbipop, ksigmadec, kbudget);
+            return b;
+        }), "runs"_a, "mfev"_a, "tol"_a, "sigma0"_a = 2., "maxlargeruns"_a = 9, "nbipop"_a = true, "ksigmadec"_a = 1.6,
+            "kbudget"_a = 2., "eigenrate"_a = 0.25);
+    py::class_<IPopBatch, RestartBatch>(m, "IPopCMAESBatch")
+        .def(py::init([](int runs, int mfev, double tol, double sigma0, bool nipop, double ksigmadec, bool boundlambda,
+                double eigenrate) {
+            auto *b = new IPopBatch(RestartBatch::IPOP, runs, mfev, tol, sigma0, eigenrate);
+            b->configureIPop(nipop, ksigmadec, boundlambda);
+            return b;
+        }), "runs"_a, "mfev"_a, "tol"_a, "sigma0"_a = 2., "nipop"_a = true, "ksigmadec"_a = 1.6, "boundlambda"_a = true,
+            "eigenrate"_a = 0.25);
 
     py::class_<DeSearchBase, MultivariateOptimizer>(m, "BaseDE")
         .def("swarm", [](DeSearchBase &self) {

@@ -37,6 +37,7 @@ DE_N, DE_NP, DE_BOX = 1000, 1000, 5.12
 DE_BATCH = 148         # independent DE runs per launch for the HBM-resident figure (one per SM: no grid-wide barrier)
 SEP_N = 10000          # BASELINE config 3
 SHARD_LAMBDA = 16384   # BASELINE config 4
+BIPOP_RUNS, BIPOP_N, BIPOP_MFEV = 4096, 40, 100000  # BASELINE config 5
 METRIC = "CMA-ES generations/s (n=1000, lambda=4096)"
 UNIT = "generations/s"
 WORKLOAD = "Cmaes n=1000 lambda=4096 mu=2048 Rosenbrock box=[-10,10]^n fp64 (BASELINE.json metric config)"
@@ -140,6 +141,15 @@ def all_min_with_owner(dist, local, rank, value):
     vals = [float(g.item()) for g in gathered]
     owner = int(np.argmin(vals))
     return vals[owner], owner
+
+
+def all_sum(dist, local, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
 
 
 def barrier(dist, local):
@@ -442,6 +452,43 @@ def bench_sharded(ctx, comm, kind, lam, steps, warmup, seed):
             "shares": {k: v["ms_total"] / sum(times) for k, v in prof.items()}}
 
 
+def bench_bipop_batch(pkg, objective, box, comm, seed, runs=BIPOP_RUNS, n=BIPOP_N, mfev=BIPOP_MFEV):
+    """BASELINE config 5: `runs` independent BIPOP-CMA-ES(Cmaes) sequences at n = 40, budget mfev each, through the Python
+    API with host buffers (guesses in, solutions out).  With a communicator the runs are sharded r % world == rank and the
+    batch ends with one best-of reduce; the caller takes the max of wall_s over ranks."""
+    pkg.seed(seed)
+    guesses = np.random.default_rng(seed).uniform(-box, box, (runs, n))
+    batch = pkg.BiPopCMAESBatch(runs=runs, mfev=mfev, tol=1e-8)
+    batch.set_timing(True)
+    if comm is not None:
+        batch.set_communicator(comm)
+    t0 = time.perf_counter()
+    sols = batch.optimize(objective, -box * np.ones(n), box * np.ones(n), guesses)
+    fb, owner, xb = batch.best_of()
+    wall = time.perf_counter() - t0
+    st = batch.stats
+    return {"local_runs": len(sols), "wall_s": wall, "device_s": st.device_ms / 1e3, "launches": int(st.launches),
+            "base_runs": int(st.base_runs), "generations": int(st.generations), "evaluations": int(st.evaluations),
+            "decompositions": int(st.decompositions), "f_median": float(np.median(batch.best_values)), "f_best": float(fb),
+            "best_run": int(owner), "h2d_bytes": int(guesses.nbytes + 2 * n * 8), "d2h_bytes": int(len(sols) * n * 8)}
+
+
+def cpu_bipop_sample(o, runs=2, seed=3):
+    """The reference's own BiPopCmaes(Cmaes) on the same problem, `runs` sequences on one core."""
+    from oracle import oracle as O
+    n = BIPOP_N
+    lo, hi = -5.12 * np.ones(n), 5.12 * np.ones(n)
+    o.seed(seed)
+    t0 = time.perf_counter()
+    fev = 0
+    for _ in range(runs):
+        base = o.cma(O.VANILLA, 1000, 1e-8, 10)
+        _, fe, _ = o.restart_optimize(1, base, BIPOP_MFEV, O.RASTRIGIN, lo, hi, o.uniform(-5.12, 5.12, n))
+        fev += fe
+    dt = time.perf_counter() - t0
+    return {"runs_per_s": runs / dt, "evals_per_s": fev / dt, "runs": runs, "cores": 1}
+
+
 def bench_de_e2e(pkg, cls, gens, seed):
     lo, hi = -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N)
     if cls == "JADE":
@@ -504,12 +551,14 @@ def run_own(args):
     sep["gens_per_s"] = world * 1e3 / t_sep
     # one large-lambda run sharded by candidates over all GPUs of the job (N > 1 only)
     sharded = None
+    pycomm = None
     if world > 1:
         import torch
         import torch.distributed as tdist
-        ids = [_cabi.Comm.unique_id() if rank == 0 else None]
+        ids = [_cabi.Comm.unique_id() if rank == 0 else None, pkg.Communicator.unique_id() if rank == 0 else None]
         tdist.broadcast_object_list(ids, src=0)
         comm = _cabi.Comm(ctx, world, rank, ids[0])
+        pycomm = pkg.Communicator(world, rank, ids[1])
         sharded = {}
         for kname, kind in (("cmaes", _cabi.CMA_FULL), ("active_cmaes", _cabi.CMA_ACTIVE)):
             barrier(dist, local)
@@ -520,6 +569,23 @@ def run_own(args):
                               "scaling": "strong", "tflops": sr["flops"] * gps / 1e12, "share_of_step": sr["shares"],
                               "collectives": "ncclAllGather(fitness) + ncclAllReduce(n*ld + ld doubles) per generation"}
         del comm
+    # BASELINE config 5: a batch of independent BIPOP runs, sharded over the ranks (strong scaling: the batch is fixed)
+    bipop = {}
+    bench_bipop_batch(pkg, pkg.Rastrigin, 5.12, None, seed=5, runs=256, mfev=20000)  # first-call costs
+    for oname, objective, box in (("rastrigin", pkg.Rastrigin, 5.12), ("ackley", pkg.Ackley, 32.768)):
+        barrier(dist, local)
+        b = bench_bipop_batch(pkg, objective, box, pycomm, seed=11)
+        wall = all_max(dist, local, b["wall_s"])
+        dev_s = all_max(dist, local, b["device_s"])
+        tot = {k: int(all_sum(dist, local, b[k])) for k in ("base_runs", "generations", "evaluations", "decompositions", "launches")}
+        b.update(tot)
+        b.update({"runs": BIPOP_RUNS, "n": BIPOP_N, "mfev_per_run": BIPOP_MFEV, "gpus": world, "scaling": "strong", "wall_s": wall,
+                  "device_s": dev_s, "runs_per_s": BIPOP_RUNS / wall, "evals_per_s": tot["evaluations"] / wall,
+                  "run_generations_per_s": tot["generations"] / wall, "device_run_generations_per_s": tot["generations"] / dev_s,
+                  "note": "BiPopCMAESBatch.optimize(): host guesses in, solutions out; restart schedule on the host, base runs as "
+                          "CTAs of the batched engine (in-CTA tred2/tql2 at the reference's cadence); wall clock includes every "
+                          "host round trip; bound: per-run dependency chains (latency / issue), not HBM or tensor peak"})
+        bipop[oname] = b
     if rank != 0:
         return
     peak, peak_src = fp64_peak()
@@ -569,6 +635,7 @@ def run_own(args):
         "best_of": {"f": fbest, "rank": owner},
         "de": de,
         "sep": sep,
+        "bipop_batch": bipop,
     }
     if sharded is not None:
         line["sharded_run"] = sharded
@@ -579,7 +646,8 @@ def run_own(args):
                                 "sample": "one generation of the CPU implementation at n=1000, lambda_s=256, timed by phase; lambda-linear "
                                           "phases scaled x16 to lambda=4096, eigendecomposition counted once per generation",
                                 "gens_per_s_excl_eig": cs["gens_per_s_excl_eig"], "t_eig_s": cs["t_eig"],
-                                "de_jade_evals_per_s": cpu_de_sample(o, 0), "de_shade_evals_per_s": cpu_de_sample(o, 1)}
+                                "de_jade_evals_per_s": cpu_de_sample(o, 0), "de_shade_evals_per_s": cpu_de_sample(o, 1),
+                                "bipop_batch": cpu_bipop_sample(o)}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 

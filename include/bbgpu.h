@@ -56,6 +56,7 @@ int bbgpu_ctx_create(int device, void *cuda_stream, bbgpu_ctx **out);
 int bbgpu_ctx_destroy(bbgpu_ctx *ctx);
 int bbgpu_ctx_sync(bbgpu_ctx *ctx);
 void *bbgpu_ctx_stream(bbgpu_ctx *ctx);
+int bbgpu_ctx_device(bbgpu_ctx *ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py gpu_launches) */
 int64_t bbgpu_ctx_launch_count(bbgpu_ctx *ctx);
 
@@ -237,6 +238,9 @@ int bbgpu_comm_allreduce_sum(bbgpu_comm *comm, double *d_buf, int64_t count);
  * scalar with this rank's best fitness, d_x = its n-vector (overwritten with the winner's) */
 int bbgpu_comm_best_of(bbgpu_comm *comm, const double *d_f, double *d_x, int n, double *h_fbest,
                        int *h_owner);
+/* the same with host buffers: f by value, h_x[n] in/out */
+int bbgpu_comm_best_of_host(bbgpu_comm *comm, double f, double *h_x, int n, double *h_fbest,
+                            int *h_owner);
 int bbgpu_cma_attach_comm(bbgpu_cma *h, bbgpu_comm *comm);
 int bbgpu_cma_shard_partial(bbgpu_cma *h);
 int bbgpu_cma_shard_finish(bbgpu_cma *h, double sigma, int fev);

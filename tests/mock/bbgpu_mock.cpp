@@ -20,6 +20,7 @@ int bbgpu_ctx_create(int, void *, bbgpu_ctx **out) { *out = new bbgpu_ctx(); ret
 int bbgpu_ctx_destroy(bbgpu_ctx *c) { delete c; return 0; }
 int bbgpu_ctx_sync(bbgpu_ctx *) { return 0; }
 void *bbgpu_ctx_stream(bbgpu_ctx *) { return nullptr; }
+int bbgpu_ctx_device(bbgpu_ctx *) { return 0; }
 int64_t bbgpu_ctx_launch_count(bbgpu_ctx *c) { return c->launches; }
 int bbgpu_ctx_profile_enable(bbgpu_ctx *, int) { return 0; }
 int bbgpu_ctx_profile_read(bbgpu_ctx *, int, double *t, int64_t *c) { *t = 0; *c = 0; return 0; }
@@ -101,4 +102,43 @@ int bbgpu_cma_shard_partial(bbgpu_cma *) { return 0; }
 int bbgpu_cma_shard_finish(bbgpu_cma *, double, int) { return 0; }
 int bbgpu_cma_get_candidate(bbgpu_cma *, int, double *) { return 0; }
 int bbgpu_de_generation_batch(bbgpu_de *const *, int, bbgpu_objective *, bbgpu_de_report *) { return 0; }
+int bbgpu_comm_best_of_host(bbgpu_comm *, double f, double *, int, double *fb, int *owner) { *fb = f; *owner = 0; return 0; }
+// batched engine: a base run "converges" after 40 generations or when its budget is spent
+struct bbgpu_cmab { int n, runs; std::vector<bbgpu_cmab_run_params> p; std::vector<bbgpu_cmab_run_status> st; std::vector<double> x; };
+int bbgpu_cmab_create(bbgpu_ctx *, int n, int runs, int, const double *, const double *, bbgpu_cmab **out) {
+    bbgpu_cmab *h = new bbgpu_cmab(); h->n = n; h->runs = runs; h->p.resize(runs); h->st.resize(runs); h->x.assign((size_t) runs * n, 0.0); *out = h; return 0;
+}
+int bbgpu_cmab_destroy(bbgpu_cmab *h) { delete h; return 0; }
+int bbgpu_cmab_start(bbgpu_cmab *h, int count, const int32_t *ids, const bbgpu_cmab_run_params *p, const double *g, int) {
+    for (int q = 0; q < count; q++) {
+        h->p[ids[q]] = p[q];
+        std::memset(&h->st[ids[q]], 0, sizeof(bbgpu_cmab_run_status));
+        h->st[ids[q]].lambda = p[q].lambda; h->st[ids[q]].sigma = p[q].sigma0;
+        for (int i = 0; i < h->n; i++) h->x[(size_t) ids[q] * h->n + i] = g[(size_t) q * h->n + i];
+    }
+    return 0;
+}
+int bbgpu_cmab_step(bbgpu_cmab *h, bbgpu_objective *, int count, const int32_t *ids, int quantum, int max_gens, const double *, int) {
+    for (int q = 0; q < count; q++) {
+        bbgpu_cmab_run_status &s = h->st[ids[q]];
+        const bbgpu_cmab_run_params &p = h->p[ids[q]];
+        int spent = 0, g = 0;
+        s.generations_this_step = 0;
+        while (s.status == 0 && g < max_gens && (g == 0 || spent < quantum)) {
+            if (s.fev >= p.mfev) { s.status = 2; break; }
+            s.fev += p.lambda; s.it++; g++; spent += p.lambda; s.generations_this_step++;
+            s.fx_final = 100.0 * std::pow(0.9, s.it) / p.lambda;
+            if (s.it >= 40 || s.it >= p.mit) { s.status = 1; s.flag = s.it >= p.mit ? 1 : 2; }
+        }
+    }
+    return 0;
+}
+int bbgpu_cmab_fetch(bbgpu_cmab *h, bbgpu_cmab_run_status *out) { std::memcpy(out, h->st.data(), sizeof(bbgpu_cmab_run_status) * h->runs); return 0; }
+int bbgpu_cmab_get_best(bbgpu_cmab *h, int r0, int count, double *x) { std::memcpy(x, &h->x[(size_t) r0 * h->n], sizeof(double) * count * h->n); return 0; }
+int bbgpu_cmab_get(bbgpu_cmab *, int, int, double *, int64_t) { return 0; }
+int bbgpu_cmab_set(bbgpu_cmab *, int, int, const double *, int64_t) { return 0; }
+int bbgpu_cmab_set_sigma(bbgpu_cmab *, int, double) { return 0; }
+int bbgpu_cmab_get_population(bbgpu_cmab *, int, double *, double *, int32_t *) { return 0; }
+int bbgpu_cmab_adopt_basis(bbgpu_cmab *, int, const double *, const double *) { return 0; }
+int bbgpu_eig_small_host(bbgpu_ctx *, int, int, const double *, double *, double *, int32_t *) { return 0; }
 }

@@ -6,6 +6,7 @@
 #include "cma.h"
 #include "de.h"
 #include "restart.h"
+#include "batch.h"
 
 int main(int argc, char **argv) {
     const int n = 6;
@@ -38,5 +39,16 @@ int main(int argc, char **argv) {
     ShadeSearch shade(5000, 20, 1e-3);
     multivariate_solution s5 = shade.optimize(prob, guess.data());
     std::printf("jade fev %d conv %d, shade fev %d conv %d\n", s4._fev, (int) s4._converged, s5._fev, (int) s5._converged);
+    for (int kind = 0; kind < 2; kind++) {
+        const int runs = 37;
+        RestartBatch batch(kind == 0 ? RestartBatch::IPOP : RestartBatch::BIPOP, runs, 20000, 1e-8, 2., 0.25);
+        std::vector<double> guesses((size_t) runs * n, 1.0);
+        std::vector<multivariate_solution> sols = batch.optimize(prob, guesses.data());
+        long long fev = 0;
+        for (const multivariate_solution &s : sols) fev += s._fev;
+        std::printf("batch kind %d: %zu runs, %lld base runs, %lld evaluations (sum %lld), %lld launches\n", kind, sols.size(),
+                batch.stats().base_runs, batch.stats().evaluations, fev, batch.stats().launches);
+        if (fev != batch.stats().evaluations || (int) sols.size() != runs) return 2;
+    }
     return total > 0 ? 0 : 1;
 }

@@ -241,3 +241,71 @@ def test_free_running_batch_solves_like_the_reference(ctx, port_oracle):
         ok_o.append(P.eval(O.ROSENBROCK, x) < 1e-8)
     assert ok.mean() >= np.mean(ok_o) - 0.15
     assert abs(np.median(fev[ok]) / np.median(np.array(fev_o)[np.array(ok_o)]) - 1.0) < 0.2
+
+
+# ---- batches of IPOP / BIPOP runs through the Python API (host/batch.cpp over the batched engine) -----------------
+
+@pytest.fixture(scope="module")
+def pkg():
+    import bboptpy_b200
+    return bboptpy_b200
+
+
+def _rastrigin(x):
+    return 10 * x.size + float(np.sum(x * x - 10 * np.cos(2 * np.pi * x)))
+
+
+@pytest.mark.parametrize("driver", ["BiPopCMAESBatch", "IPopCMAESBatch"])
+def test_restart_batch_free_running(pkg, port_oracle, driver):
+    """64 independent restart sequences on the 8-D Rastrigin function: budgets respected, every returned point is what
+    it claims to be, and the batch solves the problem as well as the reference's own driver does (same budget)."""
+    P = port_oracle
+    n, R, mfev = 8, 64, 40000
+    lo, hi = -5.12 * np.ones(n), 5.12 * np.ones(n)
+    pkg.seed(21)
+    guesses = np.random.default_rng(0).uniform(-5, 5, (R, n))
+    batch = getattr(pkg, driver)(runs=R, mfev=mfev, tol=1e-8)
+    sols = batch.optimize(pkg.Rastrigin, lo, hi, guesses)
+    assert len(sols) == R and list(batch.run_ids) == list(range(R))
+    st = batch.stats
+    fvals = np.array([_rastrigin(s.x) for s in sols])
+    assert_close(batch.best_values, fvals, rel=1e-9, what="best f per run")
+    evals = np.array([s.n_evals for s in sols])
+    assert st.evaluations == evals.sum() and st.base_runs >= 2 * R and st.generations > 0
+    # a base run may overshoot its budget by less than one generation (base_cmaes.cpp:166-173), the sequence by one run
+    assert (evals >= mfev * 0.5).all() and (evals <= mfev + 10 * n * n + 1).all()
+    fb, owner, xb = batch.best_of()
+    assert fb == batch.best_values.min() and owner == int(np.argmin(batch.best_values)) and np.array_equal(xb, sols[owner].x)
+    # the reference's own driver, free running, same budget: 12 sequences
+    rk = 1 if driver.startswith("BiPop") else 0
+    ref = []
+    P.seed(5)
+    for r in range(12):
+        base_o = P.cma(O.VANILLA, 1000, 1e-8, 10)
+        x_o, fev_o, trace = P.restart_optimize(rk, base_o, mfev, O.RASTRIGIN, lo, hi, guesses[r])
+        ref.append(_rastrigin(x_o))
+    ref = np.array(ref)
+    # Rastrigin's local optima sit at integer multiples of ~0.995 per coordinate: compare the typical depth reached
+    assert np.median(fvals) <= np.median(ref) + 2.0, (np.median(fvals), np.median(ref))
+    assert (fvals < 30).all()
+
+
+def test_restart_batch_is_reproducible(pkg):
+    n, R = 6, 16
+    lo, hi = -5.12 * np.ones(n), 5.12 * np.ones(n)
+    guesses = np.random.default_rng(1).uniform(-5, 5, (R, n))
+    out = []
+    for quantum in (500, 5000):
+        pkg.seed(33)
+        batch = pkg.BiPopCMAESBatch(runs=R, mfev=15000, tol=1e-8)
+        batch.set_quantum(quantum)  # launch granularity must not change any run
+        sols = batch.optimize(pkg.Rastrigin, lo, hi, guesses)
+        out.append((np.array([s.x for s in sols]), [s.n_evals for s in sols]))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+
+
+def test_restart_batch_rejects_host_callables(pkg):
+    n = 4
+    batch = pkg.BiPopCMAESBatch(runs=2, mfev=1000, tol=1e-8)
+    with pytest.raises(RuntimeError, match="registry"):
+        batch.optimize(lambda x: float((x * x).sum()), -np.ones(n), np.ones(n), np.zeros((2, n)))
