@@ -105,6 +105,28 @@ def main():
         assert torch.equal(mine, ref), "ranks disagree after the sharded optimize()"
         if rank == 0:
             print(cls.__name__, "optimize() sharded over", world, "GPUs: ok", rosen(guess), "->", rosen(s3.x), flush=True)
+    # ---- a batch of independent BIPOP runs sharded r % world == rank: every run must come out
+    # bit-identical to the same run of the unsharded batch (run-keyed Philox streams and restart draws), and the best-of
+    # reduce must name the same winner on every rank
+    n, R = 8, 24
+    lo, hi = -5.12 * np.ones(n), 5.12 * np.ones(n)
+    guesses = np.random.default_rng(4).uniform(-5, 5, (R, n))
+    pkg.seed(99)
+    whole = pkg.BiPopCMAESBatch(runs=R, mfev=12000, tol=1e-8)
+    sols_w = whole.optimize(pkg.Rastrigin, lo, hi, guesses)
+    fw, ow, xw = whole.best_of()
+    pkg.seed(99)
+    part = pkg.BiPopCMAESBatch(runs=R, mfev=12000, tol=1e-8)
+    part.set_communicator(pcomm)
+    sols_p = part.optimize(pkg.Rastrigin, lo, hi, guesses)
+    assert list(part.run_ids) == list(range(rank, R, world))
+    for s, r in zip(sols_p, part.run_ids):
+        assert np.array_equal(s.x, sols_w[r].x) and s.n_evals == sols_w[r].n_evals, ("run", r)
+    fp, op, xp = part.best_of()
+    assert (fp, op) == (fw, ow) and np.array_equal(xp, xw), (fp, op, fw, ow)
+    if rank == 0:
+        print("BIPOP batch of", R, "runs sharded over", world, "GPUs: ok, best run", op, "f", fp, flush=True)
+    del part, whole
     del pcomm
     # best-of reduce
     f_dev = torch.tensor([10.0 - rank if rank != 1 else -5.0], dtype=torch.float64, device="cuda")
