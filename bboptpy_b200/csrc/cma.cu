@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256) recombine_partial_kernel(double *__restri
         const double wk = w[k];
         am = __dadd_rn(am, __dmul_rn(wk, x));
         if (SEP) {
-            const double y = __ddiv_rn(__dsub_rn(x, mo), sigma);
+            const double y = __ddiv_rn(__dsub_rn(x, mo), sigma); // exact like the reference: long replays stay aligned
             ac = __dadd_rn(ac, __dmul_rn(wk, __dmul_rn(y, y)));
         }
     }
