@@ -254,6 +254,7 @@ def run_reference(args):
         "eig": {"ms": float(np.mean([s["t_eig"] for s in samples])) * 1e3, "cadence_generations": 1,
                 "gens_per_s_excl_eig": float(np.mean([s["gens_per_s_excl_eig"] for s in samples]))},
         "de": de,
+        "bipop_batch": cpu_bipop_sample(o),
     }
     print(json.dumps(line))
 
