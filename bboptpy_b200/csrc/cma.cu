@@ -245,7 +245,12 @@ __global__ void __launch_bounds__(256) gather_steps_kernel(double *__restrict__ 
     const int src = r < mu ? rank_idx[r] : rank_idx[lambda - 1 - (r - mu)];
     const double *x = X + (int64_t) src * ld;
     double *y = Ysel + (int64_t) r * ld;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = __ddiv_rn(__dsub_rn(x[i], mold[i]), sigma);
+    const double rs = __drcp_rn(sigma);
+    if (div_by_ok(sigma)) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = div_by(__dsub_rn(x[i], mold[i]), sigma, rs);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = __ddiv_rn(__dsub_rn(x[i], mold[i]), sigma);
+    }
 }
 
 // Full-covariance kinds, one pass over the selected rows: writes the centred, sigma-scaled steps
@@ -261,11 +266,22 @@ __global__ void __launch_bounds__(256) select_steps_kernel(double *__restrict__ 
     const int r0 = s * per, r1 = min(nsel, r0 + per);
     const double mo = mold[i];
     double am = 0.0;
-    for (int r = r0; r < r1; r++) {
-        const int src = r < mu ? rank_idx[r] : rank_idx[lambda - 1 - (r - mu)];
-        const double x = X[(int64_t) src * ld + i];
-        Ysel[(int64_t) r * ld + i] = __ddiv_rn(__dsub_rn(x, mo), sigma);
-        if (r < mu) am = __dadd_rn(am, __dmul_rn(w[r], x));
+    const double rs = __drcp_rn(sigma);
+    if (div_by_ok(sigma)) { // the common case, without a division in the loop
+#pragma unroll 4
+        for (int r = r0; r < r1; r++) {
+            const int src = r < mu ? rank_idx[r] : rank_idx[lambda - 1 - (r - mu)];
+            const double x = X[(int64_t) src * ld + i];
+            Ysel[(int64_t) r * ld + i] = div_by(__dsub_rn(x, mo), sigma, rs);
+            if (r < mu) am = __dadd_rn(am, __dmul_rn(w[r], x));
+        }
+    } else {
+        for (int r = r0; r < r1; r++) {
+            const int src = r < mu ? rank_idx[r] : rank_idx[lambda - 1 - (r - mu)];
+            const double x = X[(int64_t) src * ld + i];
+            Ysel[(int64_t) r * ld + i] = __ddiv_rn(__dsub_rn(x, mo), sigma);
+            if (r < mu) am = __dadd_rn(am, __dmul_rn(w[r], x));
+        }
     }
     part[((int64_t) s * 2 + 0) * n + i] = am;
 }
@@ -282,13 +298,25 @@ __global__ void __launch_bounds__(256) recombine_partial_kernel(double *__restri
     const int k0 = s * per, k1 = min(mu, k0 + per);
     double am = 0.0, ac = 0.0;
     const double mo = SEP ? mold[i] : 0.0;
+    const double rs = __drcp_rn(sigma);
+    if (!SEP || div_by_ok(sigma)) {
 #pragma unroll 8
-    for (int k = k0; k < k1; k++) {
-        const double x = X[(int64_t) rank_idx[k] * ld + i];
-        const double wk = w[k];
-        am = __dadd_rn(am, __dmul_rn(wk, x));
-        if (SEP) {
-            const double y = __ddiv_rn(__dsub_rn(x, mo), sigma); // exact like the reference: long replays stay aligned
+        for (int k = k0; k < k1; k++) {
+            const double x = X[(int64_t) rank_idx[k] * ld + i];
+            const double wk = w[k];
+            am = __dadd_rn(am, __dmul_rn(wk, x));
+            if (SEP) {
+                // the reference's (x - xold) / sigma, bit for bit (long replays stay aligned), without the generic division
+                const double y = div_by(__dsub_rn(x, mo), sigma, rs);
+                ac = __dadd_rn(ac, __dmul_rn(wk, __dmul_rn(y, y)));
+            }
+        }
+    } else {
+        for (int k = k0; k < k1; k++) {
+            const double x = X[(int64_t) rank_idx[k] * ld + i];
+            const double wk = w[k];
+            am = __dadd_rn(am, __dmul_rn(wk, x));
+            const double y = __ddiv_rn(__dsub_rn(x, mo), sigma);
             ac = __dadd_rn(ac, __dmul_rn(wk, __dmul_rn(y, y)));
         }
     }

@@ -65,6 +65,8 @@ struct StepArgs {
     const long long *xoff; // per run: first candidate of its slice of the pool in this launch
     bbgpu_cmab_run_status *status;
     int n, ldv, bound, obj_id, quantum, max_gens, eig_mode, sort_cap;
+    int phase;      // 0: whole generations, objective inside; 1: sample only; 2: from the fitness on (external objectives)
+    int accumulate; // phases 1/2: keep counting generations_this_step across the launches of one step call
     double *xmean, *xold, *pc, *ps, *D, *C, *B, *isC, *xbest, *hbest, *hkth;
     const double *lower, *upper, *aux, *Z;
     double *X, *F;
@@ -358,7 +360,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
         vD[tid] = a.D[vo + tid];
     }
     __syncthreads();
-    if (tid == 0) { S.ran = 0; S.eig_due = 0; }
+    if (tid == 0) {
+        if (a.phase == 0 || (a.phase == 1 && !a.accumulate)) S.ran = 0;
+        S.eig_due = 0;
+    }
     __syncthreads();
     const int lam = S.lambda, mu = S.mu;
     const long long xoff = a.xoff[run];
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
         const unsigned long long gen = S.gen, seed = S.seed;
         // ---- sample + evaluate: one warp per candidate; lane p draws the coordinate pair (2p, 2p+1), lanes own
         // the output coordinates (lane, lane + 32); x_i = m_i + sigma sum_j B_ij (D_j z_j), j ascending (cmaes.cpp:65-80)
-        for (int k = wid; k < lam; k += NWARPS) {
+        for (int k = wid; k < lam && a.phase != 2; k += NWARPS) {
             double d0 = 0.0, d1 = 0.0;
             const int c0 = 2 * lane;
             if (c0 < n) {
@@ -397,21 +402,34 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
                 d0 = vD[c0] * z0;
                 d1 = c0 + 1 < n ? vD[c0 + 1] * z1 : 0.0;
             }
+            // D∘z of this candidate goes through the warp's row buffer: every j is then ONE broadcast load instead of
+            // two shuffles of a double; lanes without a coordinate of their own redo coordinate n-1 (branch-free loop)
+            double *xr = xrow + wid * n;
+            if (c0 < n) xr[c0] = d0;
+            if (c0 + 1 < n) xr[c0 + 1] = d1;
+            __syncwarp();
             double acc0 = 0.0, acc1 = 0.0;
             const int i0 = lane, i1 = lane + 32;
             const bool on0 = i0 < n, on1 = i1 < n;
-            for (int p = 0; 2 * p < n; p++) {
-                const double za = __shfl_sync(0xffffffffu, d0, p), zb = __shfl_sync(0xffffffffu, d1, p);
-                const double *r0 = Vt + (2 * p) * ldv;
-                if (on0) acc0 = fma(r0[i0], za, acc0);
-                if (on1) acc1 = fma(r0[i1], za, acc1);
-                if (2 * p + 1 < n) {
-                    const double *r1 = r0 + ldv;
-                    if (on0) acc0 = fma(r1[i0], zb, acc0);
-                    if (on1) acc1 = fma(r1[i1], zb, acc1);
+            {
+                const double *b0 = Vt + min(i0, n - 1), *b1 = Vt + (on1 ? i1 : min(i0, n - 1));
+                int j = 0;
+                for (; j + 1 < n; j += 2) {
+                    const double za = xr[j], zb = xr[j + 1];
+                    acc0 = fma(b0[0], za, acc0);
+                    acc1 = fma(b1[0], za, acc1);
+                    acc0 = fma(b0[ldv], zb, acc0);
+                    acc1 = fma(b1[ldv], zb, acc1);
+                    b0 += 2 * ldv;
+                    b1 += 2 * ldv;
+                }
+                if (j < n) {
+                    const double za = xr[j];
+                    acc0 = fma(b0[0], za, acc0);
+                    acc1 = fma(b1[0], za, acc1);
                 }
             }
-            double *xr = xrow + wid * n;
+            __syncwarp(); // the buffer now takes x
             if (on0) {
                 double x = xm[i0] + sigma * acc0;
                 if (a.bound) x = fmax(a.lower[i0], fmin(x, a.upper[i0]));
@@ -425,13 +443,18 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
                 Xr[(size_t) k * n + i1] = x;
             }
             __syncwarp();
-            const double f = bb::warp_objective(a.obj_id, n, xr, a.aux);
-            if (lane == 0) {
-                Fr[k] = f;
-                skey[k] = bb::sortable_key(f);
+            if (a.phase == 0) {
+                const double f = bb::warp_objective(a.obj_id, n, xr, a.aux);
+                if (lane == 0) {
+                    Fr[k] = f;
+                    skey[k] = bb::sortable_key(f);
+                }
             }
             __syncwarp();
         }
+        if (a.phase == 1) break; // the candidates are in the pool: the caller evaluates them, phase 2 takes over
+        if (a.phase == 2)
+            for (int k = tid; k < lam; k += THREADS) skey[k] = bb::sortable_key(Fr[k]);
         __syncthreads();
         // ---- rank ascending by (fitness, index) (base_cmaes.cpp:221)
         if (!LARGE) {
@@ -697,6 +720,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
     }
     // ---- write back
     __syncthreads();
+    if (a.phase == 1) { // nothing but the candidates changed (and the budget exit of the optimize loop)
+        if (tid == 0) {
+            R->status = S.status;
+            R->ran = S.ran;
+        }
+        return;
+    }
     if (tid < n) {
         a.xmean[vo + tid] = xm[tid];
         a.xold[vo + tid] = xo[tid];
@@ -705,12 +735,14 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
         a.D[vo + tid] = vD[tid];
         // bestSolution() (base_cmaes.cpp:232-238): the best candidate of the last generation, or the mean
         if (S.it <= 0) a.xbest[vo + tid] = xm[tid];
-        else if (S.ran > 0) a.xbest[vo + tid] = Xr[(size_t) S.ibw[0] * n + tid];
+        else if (spent > 0) a.xbest[vo + tid] = Xr[(size_t) S.ibw[0] * n + tid]; // a generation ran in THIS launch
     }
     if (wid == 0 && S.it <= 0) { // the restart drivers evaluate f(solution) once more (bipop_cmaes.cpp:84)
-        const double f = bb::warp_objective(a.obj_id, n, xm, a.aux);
-        if (lane == 0) S.fx_final = f;
-    } else if (tid == 0 && S.ran > 0) {
+        if (a.obj_id >= 0) {     // (an external objective: the host evaluates the mean, bbgpu_cmab_step)
+            const double f = bb::warp_objective(a.obj_id, n, xm, a.aux);
+            if (lane == 0) S.fx_final = f;
+        }
+    } else if (tid == 0 && spent > 0) {
         S.fx_final = S.ybw[0];
     }
     __syncthreads();
@@ -838,6 +870,8 @@ struct bbgpu_cmab {
     std::map<int, double*> weights; // lambda -> device table of mu weights (base_cmaes.cpp:94-100)
     bool attr_small = false, attr_large = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr; // the large-lambda class runs on the ctx's side stream
+    int last_ns = 0, last_nl = 0, last_maxlam = 0;    // lists of the last launch (phase 2 reuses its phase 1's)
+    size_t last_cands = 0;
 };
 
 namespace {
@@ -992,57 +1026,60 @@ int bbgpu_cmab_start(bbgpu_cmab *h, int count, const int32_t *run_ids, const bbg
     return BBGPU_OK;
 }
 
-int bbgpu_cmab_step(bbgpu_cmab *h, bbgpu_objective *obj, int count, const int32_t *run_ids, int quantum, int max_gens,
-                    const double *h_z, int eig_mode) {
-    BB_ARG(h != nullptr && obj != nullptr && count >= 0 && count <= h->runs);
-    if (count == 0) return BBGPU_OK;
-    BB_ARG(run_ids != nullptr && max_gens >= 1 && quantum >= 0);
-    if (obj->mode != 0)
-        return bb::fail(BBGPU_ERR_ARG, "bbgpu_cmab_step: the batched engine evaluates registry objectives inside its "
-                "kernel; user-device / host-callback objectives go through the one-handle engine (bbgpu_cma_*)");
-    BB_ARG(obj->n == h->n);
-    BB_ARG(h_z == nullptr || max_gens == 1);
+static bool g_status_needs_mean(const std::vector<bbgpu_cmab_run_status> &st, int run) {
+    return st[run].status != ST_RUNNING && st[run].it <= 0;
+}
+
+// one launch (pair) over the listed runs; phase as in StepArgs.  The candidate pool slices are (re)assigned here.
+static int cmab_launch(bbgpu_cmab *h, int obj_id, const double *aux, int count, const int32_t *run_ids, int quantum,
+        int max_gens, const double *h_z, int eig_mode, int phase, int accumulate, bool assign, size_t *cands_out) {
     bbgpu_ctx *ctx = h->ctx;
     cudaStream_t st = ctx->stream;
     const int n = h->n;
-    BB_CUDA(cudaStreamSynchronize(st));
-    void *pin = nullptr;
-    BB_TRY(ctx->pinned(sizeof(int) * 2 * (size_t) count + sizeof(long long) * (size_t) h->runs, &pin));
-    int *small = (int*) pin, *large = small + count;
-    long long *px = (long long*) (large + count);
     int ns = 0, nl = 0, maxlam = 0;
     size_t cands = 0;
-    for (int q = 0; q < count; q++) {
-        const int run = run_ids[q];
-        BB_ARG(run >= 0 && run < h->runs);
-        const int lam = h->h_runs[run].lambda;
-        if (lam < 2) return bb::fail(BBGPU_ERR_ARG, "bbgpu_cmab_step: run %d was never started", run);
-        h->h_xoff[run] = (long long) cands;
-        cands += lam;
-        maxlam = std::max(maxlam, lam);
-        if (lam <= SMALL_LAMBDA) small[ns++] = run; else large[nl++] = run;
-    }
-    memcpy(px, h->h_xoff.data(), sizeof(long long) * h->runs);
-    BB_TRY(ensure_pool(h, cands));
-    if (h_z != nullptr) {
-        if (cands * n > h->z_cap) {
-            if (h->Z) cudaFree(h->Z);
-            h->Z = nullptr;
-            BB_TRY(bb::dev_alloc(&h->Z, cands * n));
-            h->z_cap = cands * n;
+    if (assign) {
+        BB_CUDA(cudaStreamSynchronize(st));
+        void *pin = nullptr;
+        BB_TRY(ctx->pinned(sizeof(int) * 2 * (size_t) count + sizeof(long long) * (size_t) h->runs, &pin));
+        int *small = (int*) pin, *large = small + count;
+        long long *px = (long long*) (large + count);
+        for (int q = 0; q < count; q++) {
+            const int run = run_ids[q];
+            BB_ARG(run >= 0 && run < h->runs);
+            const int lam = h->h_runs[run].lambda;
+            if (lam < 2) return bb::fail(BBGPU_ERR_ARG, "bbgpu_cmab_step: run %d was never started", run);
+            h->h_xoff[run] = (long long) cands;
+            cands += lam;
+            maxlam = std::max(maxlam, lam);
+            if (lam <= SMALL_LAMBDA) small[ns++] = run; else large[nl++] = run;
         }
-        BB_CUDA(cudaMemcpyAsync(h->Z, h_z, cands * n * 8, cudaMemcpyHostToDevice, st));
+        memcpy(px, h->h_xoff.data(), sizeof(long long) * h->runs);
+        BB_TRY(ensure_pool(h, cands));
+        if (h_z != nullptr) {
+            if (cands * n > h->z_cap) {
+                if (h->Z) cudaFree(h->Z);
+                h->Z = nullptr;
+                BB_TRY(bb::dev_alloc(&h->Z, cands * n));
+                h->z_cap = cands * n;
+            }
+            BB_CUDA(cudaMemcpyAsync(h->Z, h_z, cands * n * 8, cudaMemcpyHostToDevice, st));
+        }
+        BB_CUDA(cudaMemcpyAsync(h->d_xoff, px, sizeof(long long) * h->runs, cudaMemcpyHostToDevice, st));
+        BB_CUDA(cudaMemcpyAsync(h->d_list, small, sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+        BB_CUDA(cudaMemcpyAsync(h->d_list + h->runs, large, sizeof(int) * nl, cudaMemcpyHostToDevice, st));
+        h->last_ns = ns; h->last_nl = nl; h->last_maxlam = maxlam; h->last_cands = cands;
+    } else { // phase 2 reuses the lists and pool slices of its phase 1
+        ns = h->last_ns; nl = h->last_nl; maxlam = h->last_maxlam; cands = h->last_cands;
     }
-    BB_CUDA(cudaMemcpyAsync(h->d_xoff, px, sizeof(long long) * h->runs, cudaMemcpyHostToDevice, st));
-    BB_CUDA(cudaMemcpyAsync(h->d_list, small, sizeof(int) * ns, cudaMemcpyHostToDevice, st));
-    BB_CUDA(cudaMemcpyAsync(h->d_list + h->runs, large, sizeof(int) * nl, cudaMemcpyHostToDevice, st));
+    if (cands_out) *cands_out = cands;
     StepArgs a;
     a.runs = h->d_runs; a.status = h->d_status; a.xoff = h->d_xoff;
-    a.n = n; a.ldv = h->ldv; a.bound = h->bound; a.obj_id = obj->id; a.quantum = quantum; a.max_gens = max_gens;
-    a.eig_mode = eig_mode;
+    a.n = n; a.ldv = h->ldv; a.bound = h->bound; a.obj_id = obj_id; a.quantum = quantum; a.max_gens = max_gens;
+    a.eig_mode = eig_mode; a.phase = phase; a.accumulate = accumulate;
     a.xmean = h->xmean; a.xold = h->xold; a.pc = h->pc; a.ps = h->ps; a.D = h->D; a.C = h->C; a.B = h->B; a.isC = h->isC;
     a.xbest = h->xbest; a.hbest = h->hbest; a.hkth = h->hkth;
-    a.lower = h->lower; a.upper = h->upper; a.aux = obj->d_aux; a.Z = h_z ? h->Z : nullptr;
+    a.lower = h->lower; a.upper = h->upper; a.aux = aux; a.Z = h_z ? h->Z : nullptr;
     a.X = h->X; a.F = h->F; a.I = h->I;
     bb::ProfScope prof(ctx, BBGPU_PROF_CMAB_STEP);
     if (nl > 0) {
@@ -1079,7 +1116,49 @@ int bbgpu_cmab_step(bbgpu_cmab *h, bbgpu_objective *obj, int count, const int32_
         BB_TRY(bb::launched(ctx, "cmab_step_kernel<small>"));
     }
     if (nl > 0) BB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
-    obj->evals += 0; // the per-run counters live in the status words
+    return BBGPU_OK;
+}
+
+int bbgpu_cmab_step(bbgpu_cmab *h, bbgpu_objective *obj, int count, const int32_t *run_ids, int quantum, int max_gens,
+                    const double *h_z, int eig_mode) {
+    BB_ARG(h != nullptr && obj != nullptr && count >= 0 && count <= h->runs);
+    if (count == 0) return BBGPU_OK;
+    BB_ARG(run_ids != nullptr && max_gens >= 1 && quantum >= 0);
+    BB_ARG(obj->n == h->n);
+    BB_ARG(h_z == nullptr || max_gens == 1);
+    if (obj->mode == 0) // registry objective: evaluated inside the kernel, whole generations per launch
+        return cmab_launch(h, obj->id, obj->d_aux, count, run_ids, quantum, max_gens, h_z, eig_mode, 0, 0, true, nullptr);
+    // User CUDA objective / batched host callback: a generation is sample (phase 1) -> ONE evaluate call over the
+    // candidates of all listed runs -> rank ... converged() (phase 2).  The host has to see which runs are still
+    // running before it sizes the next evaluate call, so there is one status read per generation.
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    std::vector<int32_t> active(run_ids, run_ids + count), next;
+    std::vector<int> spent(h->runs, 0);
+    std::vector<bbgpu_cmab_run_status> status(h->runs);
+    for (int g = 0; g < max_gens && !active.empty(); g++) {
+        size_t cands = 0;
+        BB_TRY(cmab_launch(h, -1, nullptr, (int) active.size(), active.data(), quantum, 1, h_z, eig_mode, 1, g > 0 ? 1 : 0, true, &cands));
+        BB_TRY(bb::evaluate(ctx, obj, h->X, h->n, (int) cands, h->F));
+        BB_TRY(cmab_launch(h, -1, nullptr, (int) active.size(), active.data(), quantum, 1, h_z, eig_mode, 2, 1, false, nullptr));
+        BB_CUDA(cudaMemcpyAsync(status.data(), h->d_status, sizeof(bbgpu_cmab_run_status) * h->runs, cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        next.clear();
+        for (int32_t run : active) {
+            spent[run] += h->h_runs[run].lambda;
+            if (status[run].status == ST_RUNNING && spent[run] < quantum) next.push_back(run);
+        }
+        active.swap(next);
+    }
+    // runs that never iterated (budget <= 0) report f(mean): the kernel cannot evaluate an external objective
+    for (int q = 0; q < count; q++) {
+        const int run = run_ids[q];
+        if (g_status_needs_mean(status, run)) {
+            BB_TRY(bb::evaluate(ctx, obj, h->xmean + (size_t) run * h->n, h->n, 1, h->F));
+            BB_CUDA(cudaMemcpyAsync((char*) (h->d_status + run) + offsetof(bbgpu_cmab_run_status, fx_final), h->F, sizeof(double),
+                    cudaMemcpyDeviceToDevice, st));
+        }
+    }
     return BBGPU_OK;
 }
 

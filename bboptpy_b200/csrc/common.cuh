@@ -131,6 +131,18 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// a / b correctly rounded from r = RN(1 / b) in three instructions (Markstein 1990: q = RN(a r), then
+// q' = RN(q + RN(a - b q) r) is the correctly rounded quotient for every b whose significand is not all ones; that one
+// significand falls back to the division).  The kernels that divide a whole row by sigma were issue-bound on the ~25
+// instructions of a generic fp64 division; the result bits are the reference's `(x - xold) / sigma` either way.
+__device__ __forceinline__ double div_by(double a, double b, double r) {
+    const double q = __dmul_rn(a, r);
+    return __fma_rn(__fma_rn(-b, q, a), r, q);
+}
+__device__ __forceinline__ bool div_by_ok(double b) {
+    return ((unsigned long long) __double_as_longlong(b) & 0x000fffffffffffffull) != 0x000fffffffffffffull && isfinite(b) && b != 0.0;
+}
+
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));

@@ -4,7 +4,11 @@
 
 int bbgpu_ctx::pinned(size_t bytes, void **out) {
     if (bytes > h_pinned_bytes) {
-        if (h_pinned) cudaFreeHost(h_pinned);
+        if (h_pinned) {
+            cudaStreamSynchronize(stream); // copies from / to the old buffer may still be in flight
+            if (aux) cudaStreamSynchronize(aux);
+            cudaFreeHost(h_pinned);
+        }
         h_pinned = nullptr;
         h_pinned_bytes = 0;
         const size_t want = bb::round_up((int64_t) bytes, 1 << 20);

@@ -116,9 +116,6 @@ std::vector<multivariate_solution> RestartBatch::optimize(const multivariate_pro
     if (f._hasc || f._hasbbc) {
         std::cerr << "Warning [CMA batch]: problem constraints will be ignored." << std::endl;
     }
-    if (f._dev._builtin < 0)
-        throw bbopt::GpuError("RestartBatch: the batched engine evaluates registry objectives inside its kernel; pass a "
-                "registry Objective (user CUDA objectives and Python callables run through the one-run classes)");
     _n = f._n;
     const int n = _n;
     bbgpu_ctx *ctx0 = bbopt::device_context();

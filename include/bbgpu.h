@@ -340,8 +340,10 @@ int bbgpu_de_phase_times(bbgpu_de *h, uint64_t *out64);
 /* ---- batched small-n CMA-ES engine (BASELINE config 5: thousands of independent
  * IPOP/BIPOP runs at n <= 64).  One CTA per run; sample -> evaluate -> rank -> update -> updateSigma ->
  * lazy eigendecomposition (the reference's tred2/tql2, inside the CTA) -> updateHistory -> converged()
- * all run on the device, whole generations per launch (cma/base_cmaes.cpp:150-174 per run).  Only
- * registry objectives (evaluated inside the kernel).  The restart schedule (cma/ipop_cmaes.cpp,
+ * all run on the device, whole generations per launch (cma/base_cmaes.cpp:150-174 per run).  Registry
+ * objectives are evaluated inside the kernel; a user CUDA objective or a batched host callback is called
+ * ONCE per generation with the candidates of all listed runs (sample launch -> evaluate -> update
+ * launch, one status read per generation).  The restart schedule (cma/ipop_cmaes.cpp,
  * cma/bipop_cmaes.cpp) stays with the caller: it starts base runs, steps the batch, reads the status
  * words and restarts the runs that stopped. */
 typedef struct bbgpu_cmab_run_params { /* one base run == BaseCmaes::init + Cmaes::init */

@@ -78,15 +78,18 @@ def test_in_cta_eigensolver_matches_the_reference_basis(ctx, port_oracle):
         assert np.abs(B[c] - Bs[c]).max() < 1e-12 / max(gaps, 1e-6), (c, gaps)
 
 
-CASES = [  # (objective, n, lambdas of the runs of one batch, generations)
-    (O.RASTRIGIN, 40, [15, 15, 30, 120, 480], 40),
-    (O.ROSENBROCK, 10, [20, 7, 64], 120),
-    (O.ACKLEY, 64, [17, 300], 25),
+CASES = [  # (objective, n, lambdas of the runs of one batch, generations, clip to the box)
+    (O.RASTRIGIN, 40, [15, 15, 30, 120, 480], 40, False),
+    (O.ROSENBROCK, 10, [20, 7, 64], 120, False),
+    (O.ACKLEY, 64, [17, 300], 25, False),
+    (O.SPHERE, 5, [8, 9, 4096], 12, False),      # odd lambda; the largest class of the ranking network (short: the mean
+                                                 # of the lambda = 4096 run collapses onto 0, where 1e-10 RELATIVE tightens fast)
+    (O.RASTRIGIN, 12, [10, 40, 300], 40, True),  # samples and mean clipped to the box (cmaes.cpp:74-77, 92-94)
 ]
 
 
-@pytest.mark.parametrize("obj,n,lams,gens", CASES)
-def test_batch_trajectory_replay(ctx, port_oracle, obj, n, lams, gens):
+@pytest.mark.parametrize("obj,n,lams,gens,bound", CASES)
+def test_batch_trajectory_replay(ctx, port_oracle, obj, n, lams, gens, bound):
     """T2 for every run of a batch at once: replayed draws (the oracle's z of that generation) and replayed eigenbases;
     everything the reference holds after a generation is compared, including what the one-handle engine leaves to the
     host (sigma, the history extremes, the stop flag)."""
@@ -94,15 +97,17 @@ def test_batch_trajectory_replay(ctx, port_oracle, obj, n, lams, gens):
     P = port_oracle
     box = BOX[obj]
     lo, hi = -box * np.ones(n), box * np.ones(n)
+    if bound:  # a tight, off-centre box so that clipping is active every generation
+        lo, hi = -0.4 * box * np.ones(n), 0.7 * box * np.ones(n)
     R = len(lams)
     P.seed(1234)
-    guesses = [P.uniform(-box, box, n) for _ in range(R)]
+    guesses = [P.uniform(lo[0], hi[0], n) for _ in range(R)]
     hs = []
     for r, lam in enumerate(lams):
-        h = P.cma(O.VANILLA, 10 ** 9, 1e-12, lam, sigma0=0.3 * box)
+        h = P.cma(O.VANILLA, 10 ** 9, 1e-12, lam, sigma0=0.3 * box, bound=bound)
         h.init(obj, lo, hi, guesses[r])
         hs.append(h)
-    batch = _cabi.CmaBatch(ctx, n, R)
+    batch = _cabi.CmaBatch(ctx, n, R, bound=bound, lower=lo, upper=hi)
     params = [_cabi.CmaBatch.run_params(n, lam, 10 ** 9, 0.3 * box, 1e-12, seed=r) for r, lam in enumerate(lams)]
     for r, h in enumerate(hs):  # the host derives the same constants as the reference
         for k in ("cc", "cs", "c1", "cmu", "mueff", "damps", "chi", "eigenfreq"):
@@ -304,8 +309,56 @@ def test_restart_batch_is_reproducible(pkg):
     assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
 
 
-def test_restart_batch_rejects_host_callables(pkg):
-    n = 4
-    batch = pkg.BiPopCMAESBatch(runs=2, mfev=1000, tol=1e-8)
-    with pytest.raises(RuntimeError, match="registry"):
-        batch.optimize(lambda x: float((x * x).sum()), -np.ones(n), np.ones(n), np.zeros((2, n)))
+# ---- objectives outside the registry: one evaluate call per generation over the candidates of all listed runs ---------
+
+def test_external_objective_equals_the_fused_kernel(ctx):
+    """A batched host callback that computes the registry objective's own values must reproduce the fused path bit for
+    bit (same draws, same fitness bits -> same ranking, same state), generation by generation and as a multi-generation
+    step; the callback sees each generation's candidates of ALL runs in one call."""
+    from bboptpy_b200 import _cabi
+    n, lams = 12, [9, 20, 300]
+    R = len(lams)
+    reg = _objective(ctx, O.RASTRIGIN, n)
+    calls = []
+
+    def cb(X):
+        calls.append(X.shape[0])
+        return reg.eval(X)
+
+    ext = _cabi.Objective.from_python(ctx, n, cb, batched=True)
+    guesses = np.random.default_rng(8).uniform(-5, 5, (R, n))
+    out = []
+    for objective in (reg, ext):
+        batch = _cabi.CmaBatch(ctx, n, R)
+        batch.start(range(R), [_cabi.CmaBatch.run_params(n, lam, 30 * lam, 2.0, 1e-12, seed=50 + r) for r, lam in enumerate(lams)], guesses)
+        for _ in range(5):
+            batch.step(objective, range(R), max_gens=1)
+        batch.step(objective, range(R), quantum=10 ** 9, max_gens=10 ** 6)  # to the end of the budgets: 30 generations each
+        st = batch.fetch()
+        assert all(s.it == 30 and s.fev == 30 * lam and s.status in (1, 2) for s, lam in zip(st, lams))
+        out.append((np.array([batch.get(r, _cabi.F_C) for r in range(R)]), np.array([batch.get(r, _cabi.F_XMEAN) for r in range(R)]),
+                    np.array([s.sigma for s in st]), batch.best(), np.array([s.fx_final for s in st]),
+                    [s.generations_this_step for s in st]))
+    for a, b in zip(out[0][:5], out[1][:5]):
+        assert np.array_equal(a, b)
+    assert out[1][5] == [25] * R  # generations_this_step accumulates over the launches of one step call
+    assert calls[:5] == [sum(lams)] * 5 and len(calls) == 30
+
+
+def test_restart_batch_with_a_python_callable(pkg):
+    """The reference's own calling convention (a Python callable f(x) -> float) through the batched driver."""
+    n, R = 5, 6
+    lo, hi = -5.12 * np.ones(n), 5.12 * np.ones(n)
+    guesses = np.random.default_rng(2).uniform(-5, 5, (R, n))
+    evals = [0]
+
+    def f(x):
+        evals[0] += 1
+        return float(np.sum(x * x))
+
+    pkg.seed(4)
+    batch = pkg.IPopCMAESBatch(runs=R, mfev=3000, tol=1e-10)
+    sols = batch.optimize(f, lo, hi, guesses)
+    assert len(sols) == R and all(float(np.sum(s.x ** 2)) < 1e-8 for s in sols)
+    # the engine calls f once per candidate; the reference counts one more evaluation per base run (ipop_cmaes.cpp:94)
+    assert evals[0] + batch.stats.base_runs == batch.stats.evaluations
