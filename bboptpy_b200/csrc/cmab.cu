@@ -32,14 +32,18 @@ namespace {
 
 constexpr int NMAX = 64;            // B (n x n) lives in shared memory; lanes own coordinates (i, i + 32)
 constexpr int HCAP = 512;           // capacity of the two fitness-history rings per run
-constexpr int THREADS = 128;
+#ifndef CMAB_THREADS
+#define CMAB_THREADS 128
+#endif
+constexpr int THREADS = CMAB_THREADS;
 #ifndef CMAB_MIN_CTAS
 #define CMAB_MIN_CTAS 8
 #endif
 constexpr int MIN_CTAS = CMAB_MIN_CTAS; // 8: 64 registers per thread, 8 CTAs (runs) per SM
-constexpr int GROUPS = THREADS / NMAX; // thread groups splitting the ranks of the weighted mean
+constexpr int GROUPS = THREADS / NMAX > 0 ? THREADS / NMAX : 1; // thread groups splitting the ranks of the weighted mean
+static_assert(THREADS >= NMAX, "a thread per coordinate");
 constexpr int NWARPS = THREADS / 32;
-constexpr int KC = 8;               // selected steps staged per chunk of the rank-mu update
+constexpr int KCMAX = 32;           // selected steps staged per chunk of the rank-mu update (as many as fit the ranking keys' space)
 constexpr int SMALL_LAMBDA = 256;   // <= : counting rank; larger: bitonic network over (key, index)
 
 enum { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BUDGET = 2, ST_FAILED = 3 };
@@ -338,11 +342,14 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
     double *Vt = (double*) smem_raw;
     double *xm = Vt + n * ldv, *xo = xm + n, *vpc = xo + n, *vps = vpc + n, *vD = vps + n, *ve = vD + n, *vt = ve + n;
     double *xrow = vt + n;                 // NWARPS * n
-    double *ysel = xrow + NWARPS * n;      // max(KC * n, GROUPS * NMAX)
-    double *cw = ysel + max(KC * n, GROUPS * NMAX); // KC
-    double *red = cw + KC;                 // 32
+    double *cw = xrow + NWARPS * n;        // KCMAX
+    double *red = cw + KCMAX;              // 32
     unsigned long long *skey = (unsigned long long*) (red + 32);
     int *sidx = (int*) (skey + a.sort_cap);
+    // the ranking keys are dead once the permutation exists: their space stages the recombination partials and the
+    // selected steps of the covariance update (sort_cap >= 256 doubles)
+    double *ysel = (double*) skey;
+    const int KC = min(KCMAX, a.sort_cap / n);
 
     for (int i = tid; i < (int) (sizeof(RunDev) / 4); i += THREADS) ((int*) &S)[i] = ((const int*) R)[i];
     const size_t vo = (size_t) run * n, mo = (size_t) run * n * n;
@@ -844,7 +851,7 @@ __global__ void __launch_bounds__(THREADS) cmab_eig_kernel(int n, int ldv, const
 }
 
 size_t step_smem_bytes(int n, int ldv, int sort_cap) {
-    size_t doubles = (size_t) n * ldv + 7 * (size_t) n + (size_t) NWARPS * n + (size_t) std::max(KC * n, GROUPS * NMAX) + KC + 32;
+    size_t doubles = (size_t) n * ldv + 7 * (size_t) n + (size_t) NWARPS * n + KCMAX + 32;
     return doubles * 8 + (size_t) sort_cap * 12;
 }
 
