@@ -34,6 +34,7 @@
 #include <cooperative_groups.h>
 
 #include "gemm_tma.cuh" // mbarrier + 1-D bulk copy helpers
+#define BB_COS2PI_TABLE 1 // cos(2 pi x) coefficients from constant memory in this translation unit (objectives.cuh)
 #include "objectives.cuh"
 #include "philox.cuh"
 #include "rank.cuh"

@@ -28,6 +28,13 @@ __device__ __forceinline__ double rint_rn(double x) {
     return fabs(x) < 4503599627370496.0 ? sub(add(x, t), t) : x;
 }
 
+// Taylor coefficients of the cosine branch [0] (t^18 .. t^2) and of the sine branch [1] (t^19 .. t^3, divided by t)
+static __constant__ double COS2PI_COEF[2][9] = {
+    { -1.5619206968586225e-16, 4.779477332387385e-14, -1.1470745597729725e-11, 2.08767569878681e-09, -2.755731922398589e-07,
+      2.48015873015873e-05, -0.001388888888888889, 0.041666666666666664, -0.5 },
+    { -8.22063524662433e-18, 2.8114572543455206e-15, -7.647163731819816e-13, 1.6059043836821613e-10, -2.505210838544172e-08,
+      2.7557319223985893e-06, -0.0001984126984126984, 0.008333333333333333, -0.16666666666666666 } };
+
 // cos(2 pi x): reduce to r = x - rint(x) in [-1/2, 1/2], fold to [0, 1/8] with the quarter- and
 // eighth-period symmetries, then a degree-18 Taylor polynomial in t = 2 pi * folded (t <= pi/4).
 __device__ __forceinline__ double cos2pi(double x) {
@@ -40,6 +47,16 @@ __device__ __forceinline__ double cos2pi(double x) {
     const bool big = a > 0.125;
     const double t = mul(big ? sub(0.25, a) : a, 6.283185307179586);
     const double u = mul(t, t);
+#ifdef BB_COS2PI_TABLE
+    // coefficient pairs from constant memory, indexed by the branch: one load per Horner step instead of materialising
+    // and selecting two 64-bit immediates.  Same bits.  Pays where the term count dominates (the DE build: the objective
+    // terms were 41 % of its instructions, +6 % evaluations/s); measured slower in the register-starved batched CMA kernel.
+    const double *c = COS2PI_COEF[big ? 1 : 0];
+    double p = c[0];
+#pragma unroll
+    for (int k = 1; k < 9; k++) p = add(mul(p, u), c[k]);
+    p = add(mul(p, u), 1.0);
+#else
     double p = big ? -8.22063524662433e-18 : -1.5619206968586225e-16;
     p = add(mul(p, u), big ? 2.8114572543455206e-15 : 4.779477332387385e-14);
     p = add(mul(p, u), big ? -7.647163731819816e-13 : -1.1470745597729725e-11);
@@ -50,6 +67,7 @@ __device__ __forceinline__ double cos2pi(double x) {
     p = add(mul(p, u), big ? 0.008333333333333333 : 0.041666666666666664);
     p = add(mul(p, u), big ? -0.16666666666666666 : -0.5);
     p = add(mul(p, u), 1.0);
+#endif
     const double v = big ? mul(p, t) : p;
     return neg ? -v : v;
 }
