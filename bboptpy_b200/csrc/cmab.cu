@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) cmab_step_kernel(const Step
     const int run = a.list[blockIdx.x];
     RunDev *R = a.runs + run;
     double *Vt = (double*) smem_raw;
-    double *xm = Vt + n * ldv, *xo = xm + n, *vpc = xo + n, *vps = vpc + n, *vD = vps + n, *ve = vD + n, *vt = ve + n;
-    double *xrow = vt + n;                 // NWARPS * n
+    double *xm = Vt + n * ldv, *xo = xm + n, *vpc = xo + n, *vps = vpc + n, *vD = vps + n, *ve = vD + n;
+    double *xrow = ve + n;                 // NWARPS * n
     double *cw = xrow + NWARPS * n;        // KCMAX
     double *red = cw + KCMAX;              // 32
     unsigned long long *skey = (unsigned long long*) (red + 32);
@@ -851,7 +851,7 @@ __global__ void __launch_bounds__(THREADS) cmab_eig_kernel(int n, int ldv, const
 }
 
 size_t step_smem_bytes(int n, int ldv, int sort_cap) {
-    size_t doubles = (size_t) n * ldv + 7 * (size_t) n + (size_t) NWARPS * n + KCMAX + 32;
+    size_t doubles = (size_t) n * ldv + 6 * (size_t) n + (size_t) NWARPS * n + KCMAX + 32;
     return doubles * 8 + (size_t) sort_cap * 12;
 }
 
