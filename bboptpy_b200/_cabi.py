@@ -144,6 +144,7 @@ def lib():
     L.bbgpu_cma_fetch.argtypes = [vp, P(CmaReport)]
     L.bbgpu_cma_generation.argtypes = [vp, vp, d, u64, i, i]
     L.bbgpu_cma_attach_comm.argtypes = [vp, vp]
+    L.bbgpu_cma_shard_uses_peer_memory.argtypes = [vp]
     L.bbgpu_cma_shard_partial.argtypes = [vp]
     L.bbgpu_cma_shard_finish.argtypes = [vp, d, i]
     L.bbgpu_cma_get_candidate.argtypes = [vp, i, vp]
@@ -476,6 +477,10 @@ class Cma:
     def attach_comm(self, comm):
         check(self.L.bbgpu_cma_attach_comm(self.h, comm.h if comm is not None else None))
         self._comm = comm
+
+    def uses_peer_memory(self):
+        """True when the rank-mu exchange runs as one kernel over NVLink peer memory (else ncclAllReduce)."""
+        return bool(self.L.bbgpu_cma_shard_uses_peer_memory(self.h))
 
     def shard_partial(self):
         check(self.L.bbgpu_cma_shard_partial(self.h))

@@ -22,6 +22,8 @@
 #include "philox.cuh"
 #include "rank.cuh"
 
+namespace bb { struct PeerRegion; }
+
 struct bbgpu_cma {
     bbgpu_ctx *ctx = nullptr;
     bbgpu_cma_config cfg;
@@ -57,6 +59,7 @@ struct bbgpu_cma {
     // [row0, row0 + lam_loc); X / Z hold only those rows, fitness and ranking cover all lambda
     int shards = 1, shard = 0, lam_loc = 0, row0 = 0;
     bbgpu_comm *comm = nullptr;
+    bb::PeerRegion *peer = nullptr; // the rank-mu partial buffers of all ranks, mapped (NVLink peer memory); null: NCCL
     double last_sigma = 0.0;
     double *Yloc = nullptr, *coef_loc = nullptr, *wm_loc = nullptr, *norm_all = nullptr, *red = nullptr, *rowsq_loc = nullptr;
     int rowsq_loc_tiles = 0;
@@ -72,6 +75,10 @@ int comm_allreduce_sum(bbgpu_comm *c, double *d_buf, size_t count);
 int comm_allgather(bbgpu_comm *c, double *d_buf, size_t per);
 int comm_allgather2(bbgpu_comm *c, double *d_a, double *d_b, size_t per);
 int comm_broadcast(bbgpu_comm *c, double *d_buf, size_t count, int root);
+struct PeerRegion;
+int comm_peer_region_create(bbgpu_comm *c, double *d_local, size_t bytes, PeerRegion **out);
+int comm_peer_region_destroy(PeerRegion *r);
+int comm_allreduce_sum_p2p(PeerRegion *r, size_t count);
 int comm_rank(const bbgpu_comm *c);
 int comm_world(const bbgpu_comm *c);
 bbgpu_ctx *comm_ctx(const bbgpu_comm *c);
@@ -879,6 +886,7 @@ static int shard_partial(bbgpu_cma *h) {
 static int shard_exchange_partials(bbgpu_cma *h) {
     if (!h->comm) return fail(BBGPU_ERR_ARG, "sharded handle without a communicator: exchange BBGPU_CMA_SHARD_RED yourself");
     ProfScope prof(h->ctx, BBGPU_PROF_COMM);
+    if (h->peer) return comm_allreduce_sum_p2p(h->peer, (size_t) h->n * h->ldn + h->ldn);
     return comm_allreduce_sum(h->comm, h->red, (size_t) h->n * h->ldn + h->ldn);
 }
 
@@ -1086,6 +1094,10 @@ int bbgpu_cma_destroy(bbgpu_cma *h) {
     if (!h) return BBGPU_OK;
     cudaStreamSynchronize(h->ctx->stream);
     if (h->ctx->aux) cudaStreamSynchronize(h->ctx->aux);
+    if (h->peer) { // collective on a sharded handle: the peers unmap this rank's buffer before it is freed
+        comm_peer_region_destroy(h->peer);
+        h->peer = nullptr;
+    }
     for (int b = 0; b < 2; b++) {
         if (h->ev_z[b]) cudaEventDestroy(h->ev_z[b]);
         if (h->ev_used[b]) cudaEventDestroy(h->ev_used[b]);
@@ -1261,9 +1273,19 @@ int bbgpu_cma_attach_comm(bbgpu_cma *h, bbgpu_comm *comm) {
         if (h->shards <= 1) return fail(BBGPU_ERR_ARG, "the handle was not created with shard_count > 1");
         BB_ARG(comm_ctx(comm) == h->ctx && comm_world(comm) == h->shards && comm_rank(comm) == h->shard);
     }
+    if (h->peer) {
+        comm_peer_region_destroy(h->peer);
+        h->peer = nullptr;
+    }
     h->comm = comm;
+    // exchange step 2 over peer memory when every rank can map every rank's buffer (BBGPU_SHARD_P2P=0: always NCCL)
+    const char *env = getenv("BBGPU_SHARD_P2P");
+    if (comm && !(env && env[0] == '0'))
+        BB_TRY(comm_peer_region_create(comm, h->red, ((size_t) h->n * h->ldn + h->ldn) * 8, &h->peer));
     return BBGPU_OK;
 }
+
+int bbgpu_cma_shard_uses_peer_memory(bbgpu_cma *h) { return h && h->peer ? 1 : 0; }
 
 int bbgpu_cma_shard_partial(bbgpu_cma *h) {
     BB_ARG(h && h->shards > 1);

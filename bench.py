@@ -568,7 +568,8 @@ def run_own(args):
             gps = len(sr["times_ms"]) / t_sh
             sharded[kname] = {"lambda": SHARD_LAMBDA, "gpus": world, "gens_per_s": gps, "ms_per_generation": 1e3 / gps,
                               "scaling": "strong", "tflops": sr["flops"] * gps / 1e12, "share_of_step": sr["shares"],
-                              "collectives": "ncclAllGather(fitness) + ncclAllReduce(n*ld + ld doubles) per generation"}
+                              "collectives": "ncclAllGather(fitness) + one peer-memory all-reduce kernel over NVLink (n*ld + ld doubles; "
+                                             "ncclAllReduce when peer mapping is unavailable) per generation"}
         del comm
     # BASELINE config 5: a batch of independent BIPOP runs, sharded over the ranks (strong scaling: the batch is fixed)
     bipop = {}

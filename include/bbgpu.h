@@ -242,6 +242,12 @@ int bbgpu_comm_best_of(bbgpu_comm *comm, const double *d_f, double *d_x, int n, 
 int bbgpu_comm_best_of_host(bbgpu_comm *comm, double f, double *h_x, int n, double *h_fbest,
                             int *h_owner);
 int bbgpu_cma_attach_comm(bbgpu_cma *h, bbgpu_comm *comm);
+/* 1 when the rank-mu exchange of this sharded handle runs as ONE kernel over NVLink peer memory (the
+ * partial buffers of all ranks mapped into every rank: arrive barrier -> each rank sums its slice from
+ * every peer in rank order and stores it into every peer -> done barrier), 0 when it is ncclAllReduce
+ * (peer mapping unavailable, or BBGPU_SHARD_P2P=0).  A handle with a peer mapping must be destroyed
+ * collectively (every rank calls bbgpu_cma_destroy). */
+int bbgpu_cma_shard_uses_peer_memory(bbgpu_cma *h);
 int bbgpu_cma_shard_partial(bbgpu_cma *h);
 int bbgpu_cma_shard_finish(bbgpu_cma *h, double sigma, int fev);
 /* candidate by GLOBAL index (bestSolution(), cma/base_cmaes.cpp:232-238); collective on a sharded

@@ -98,6 +98,7 @@ int bbgpu_comm_world(bbgpu_comm *) { return 1; }
 int bbgpu_comm_allreduce_sum(bbgpu_comm *, double *, int64_t) { return 0; }
 int bbgpu_comm_best_of(bbgpu_comm *, const double *, double *, int, double *, int *) { return 0; }
 int bbgpu_cma_attach_comm(bbgpu_cma *, bbgpu_comm *) { return 0; }
+int bbgpu_cma_shard_uses_peer_memory(bbgpu_cma *) { return 0; }
 int bbgpu_cma_shard_partial(bbgpu_cma *) { return 0; }
 int bbgpu_cma_shard_finish(bbgpu_cma *, double, int) { return 0; }
 int bbgpu_cma_get_candidate(bbgpu_cma *, int, double *) { return 0; }

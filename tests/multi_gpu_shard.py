@@ -69,7 +69,30 @@ def main():
             sh.eig()
             sigma2 = sigma1
         if rank == 0:
-            print("sharded", "active" if kind == _cabi.CMA_ACTIVE else "vanilla", "over", world, "GPUs: ok", flush=True)
+            print("sharded", "active" if kind == _cabi.CMA_ACTIVE else "vanilla", "over", world, "GPUs: ok; rank-mu exchange over",
+                  "NVLink peer memory (one kernel)" if sh.uses_peer_memory() else "ncclAllReduce", flush=True)
+        # the peer-memory all-reduce against NCCL's on the same partials: same sums up to the order of addition, and the
+        # peer-memory result bit-identical on every rank
+        peer = sh.uses_peer_memory()
+        del sh
+        os.environ["BBGPU_SHARD_P2P"] = "0"
+        nc = _cabi.Cma(ctx, kind, n, lam, w, consts, seed=2024, shard=(rank, world))
+        nc.attach_comm(comm)
+        del os.environ["BBGPU_SHARD_P2P"]
+        pm = _cabi.Cma(ctx, kind, n, lam, w, consts, seed=2024, shard=(rank, world))
+        pm.attach_comm(comm)
+        assert not nc.uses_peer_memory() and pm.uses_peer_memory() == peer
+        for hnd in (nc, pm):
+            hnd.reset(guess)
+            hnd.generation(obj, 2.0, 0, ik, lam)
+            hnd.fetch()
+        assert_close(pm.get(_cabi.F_C)[lower], nc.get(_cabi.F_C)[lower], what="C: peer-memory vs NCCL exchange")
+        assert_close(pm.get(_cabi.F_XMEAN), nc.get(_cabi.F_XMEAN), what="xmean: peer-memory vs NCCL exchange")
+        mine = torch.from_numpy(np.concatenate([pm.get(_cabi.F_C).ravel(), pm.get(_cabi.F_XMEAN)])).cuda()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(mine, ref), "peer-memory exchange: ranks disagree"
+        del nc, pm
     # ---- the same through the reference-facing Python API: CMAES.set_communicator + optimize
     os.environ["BBOPT_DEVICE"] = str(local)
     import bboptpy_b200 as pkg
