@@ -183,6 +183,7 @@ def lib():
     L.bbgpu_cmab_get_population.argtypes = [vp, i, vp, vp, vp]
     L.bbgpu_cmab_adopt_basis.argtypes = [vp, i, vp, vp]
     L.bbgpu_eig_small_host.argtypes = [vp, i, i, vp, vp, vp, vp]
+    L.bbgpu_sytrd_host.argtypes = [vp, i, vp, vp, vp, vp, vp, i, P(ctypes.c_float)]
     _lib = L
     return L
 
@@ -293,6 +294,17 @@ class Context:
         B, D, info = np.empty_like(A), np.empty((count, n)), np.empty(count, dtype=np.int32)
         check(self.L.bbgpu_eig_small_host(self.h, n, count, A.ctypes.data, B.ctypes.data, D.ctypes.data, info.ctypes.data))
         return B, D, info
+
+    def sytrd(self, A, reps=1):
+        """Cooperative-kernel tridiagonalisation: returns d, e, tau, V (column-major reflectors as an (n, n) array whose
+        [c, i] entry is component c of reflector i) and the kernel time in ms."""
+        A = f64(A)
+        n = A.shape[0]
+        d, e, tau, V = np.empty(n), np.empty(n - 1), np.empty(n - 1), np.empty((n, n))
+        ms = ctypes.c_float(0)
+        check(self.L.bbgpu_sytrd_host(self.h, n, A.ctypes.data, d.ctypes.data, e.ctypes.data, tau.ctypes.data, V.ctypes.data, reps,
+                                      ctypes.byref(ms)))
+        return d, e, tau, V.T.copy(), ms.value
 
     def bench_dgemm(self, M, N, K, reps=10):
         ms = ctypes.c_float(0)

@@ -1,0 +1,335 @@
+// Householder tridiagonalisation of one dense symmetric matrix as ONE persistent cooperative kernel.
+//
+// Why: at the headline configuration (n = 1000) the reference decomposes C after every generation, and 9.6 ms of
+// cuSOLVER's 12.0 ms go into `Dsytrd` -- 28 panel kernels, ~10 us per column, bound by launch / barrier latency and not by
+// bandwidth (DESIGN.md "The eigendecomposition at n = 1000").  This kernel is the first half of the replacement (the
+// second half, a tridiagonal divide & conquer, is next round's work; cuSOLVER exports no device-side tridiagonal solver,
+// so this kernel is measured on its own for now: bbgpu_sytrd_host, tests/test_gpu_kernels.py, tools/sytrd_probe.py).
+//
+// Layout: row r of the matrix lives in the shared memory of CTA r % gridDim (rows are dealt cyclically so the shrinking
+// trailing block stays balanced), BOTH triangles are kept up to date, so A v is row-local: no cross-CTA reduction.
+// One grid barrier per column.  Before barrier i every CTA has written y = A22 v_i for its rows, and the owner of row
+// i + 1 has published that row (its state before update i); after the barrier every CTA redundantly forms w_i (needs all
+// of y), applies update i to the published row -- that is column i + 1 of the updated matrix -- to get the next
+// Householder vector v_{i+1}, then makes ONE pass over its own rows that applies A22 -= v w^T + w v^T and accumulates
+// y = A22 v_{i+1} for the next barrier.
+// Output in LAPACK's dsytrd('L') convention: d, e, tau, and the reflectors below the subdiagonal of a column-major V
+// (what cusolverDnDormtr consumes).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace {
+
+namespace cg = cooperative_groups;
+constexpr int SY_THREADS = 256;
+
+// Grid barrier on a monotonically increasing counter (one atomic per CTA, one polling thread per CTA): the kernel is
+// launched cooperatively, so all CTAs are resident.  ~1 us at 148 CTAs against ~2.5 us for cg::grid_group::sync().
+__device__ __forceinline__ void sy_grid_barrier(unsigned *counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
+constexpr int SY_KMAX = 8;   // columns per thread: n <= 2048
+constexpr int SY_RMAX = 16;  // rows per CTA (their scalars and partial sums live in registers): n <= 16 * gridDim
+
+__global__ void __launch_bounds__(SY_THREADS, 1) sytrd_coop_kernel(const double *__restrict__ A, int n, int ldA, double *__restrict__ d,
+        double *__restrict__ e, double *__restrict__ tau, double *__restrict__ Vcm, double *ybuf, double *rowbuf, unsigned *barrier,
+        long long *prof) {
+    extern __shared__ __align__(16) double sm[];
+    const int G = gridDim.x, me = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = SY_THREADS / 32;
+    const int np = (n + 63) & ~63;                        // row pitch: whole 64-column chunks, pad columns stay zero
+    const int nrows = me < n ? (n - me + G - 1) / G : 0;  // rows me, me + G, ...
+    const int cap = (n + G - 1) / G;
+    double *rows = sm;                          // cap x np
+    double *v = rows + (size_t) cap * np;       // current reflector v_i by global row (0 for c <= i and in the padding)
+    double *w = v + np;
+    double *vn = w + np;                        // next reflector
+    double *red = vn + np;                      // 32
+    double *part = red + 32;                    // NW x cap partial row sums of the pass
+    for (int q = 0; q < cap; q++) {
+        const int r = me + q * G;
+        for (int c = tid; c < np; c += SY_THREADS)
+            rows[(size_t) q * np + c] = (r < n && c < n) ? A[(size_t) max(r, c) * ldA + min(r, c)] : 0.0;
+    }
+    // ---- reflector 0 from column 0 of the input.  Thread t owns columns t, t + 256, ... of every vector in registers.
+    double vreg[SY_KMAX];
+    double tau_i;
+    {
+        double ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < SY_KMAX; k++) {
+            const int c = tid + k * SY_THREADS;
+            vreg[k] = (c >= 1 && c < n) ? A[(size_t) c * ldA] : 0.0;
+            if (c >= 2) ss += vreg[k] * vreg[k];
+        }
+        ss = bb::block_sum(ss, red);
+        const double alpha = A[(size_t) ldA];
+        double beta = alpha, scal = 0.0;
+        tau_i = 0.0;
+        if (ss != 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+            tau_i = (beta - alpha) / beta;
+            scal = 1.0 / (alpha - beta);
+        }
+#pragma unroll
+        for (int k = 0; k < SY_KMAX; k++) {
+            const int c = tid + k * SY_THREADS;
+            vreg[k] = c == 1 ? 1.0 : vreg[k] * scal;
+            if (c < np) { v[c] = vreg[k]; w[c] = 0.0; vn[c] = 0.0; }
+        }
+        if (me == 0 && tid == 0) { d[0] = A[0]; e[0] = beta; tau[0] = tau_i; }
+    }
+    __syncthreads();
+    // y_0 = A v_0 for the own rows r > 0; the owner of row 1 publishes it
+    for (int q = wid; q < nrows; q += NW) {
+        const int r = me + q * G;
+        if (r < 1) continue;
+        const double *row = rows + (size_t) q * np;
+        double s = 0.0;
+        for (int c = 1 + lane; c < n; c += 32) s = fma(row[c], v[c], s);
+        s = bb::warp_sum(s);
+        if (lane == 0) ybuf[r] = s;
+    }
+    if (1 % G == me) {
+        const double *row = rows + (size_t) (1 / G) * np;
+        for (int c = tid; c < n; c += SY_THREADS) rowbuf[c] = row[c];
+    }
+    long long tacc[6] = { 0, 0, 0, 0, 0, 0 }, t0 = clock64(), t1;
+#define SY_TICK(k) do { t1 = clock64(); tacc[k] += t1 - t0; t0 = t1; } while (0)
+    for (int i = 0; i < n - 1; i++) {
+        const int parity = i & 1;
+        SY_TICK(5);
+        sy_grid_barrier(barrier, (unsigned) (i + 1) * (unsigned) G);
+        SY_TICK(0);
+        // y_i and row i+1 of A^(i) were written by other SMs: read them past L1 (a line of the same buffer from two steps
+        // ago may still sit there).  Everything a thread needs comes in ONE round trip: its own columns plus the three
+        // scalars every thread would otherwise wait a broadcast for.
+        const double *y = ybuf + (size_t) parity * n, *old = rowbuf + (size_t) parity * n;
+        double yk[SY_KMAX], ok[SY_KMAX];
+#pragma unroll
+        for (int k = 0; k < SY_KMAX; k++) {
+            const int c = tid + k * SY_THREADS;
+            const bool in = c > i && c < n;
+            yk[k] = in ? __ldcg(y + c) : 0.0;
+            ok[k] = in ? __ldcg(old + c) : 0.0;
+        }
+        const double y1 = __ldcg(y + i + 1), o1 = __ldcg(old + i + 1);
+        const bool more = i + 2 < n;
+        const double y2 = more ? __ldcg(y + i + 2) : 0.0, o2 = more ? __ldcg(old + i + 2) : 0.0;
+        double dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < SY_KMAX; k++) dot = fma(yk[k], vreg[k], dot);
+        dot = bb::block_sum(dot, red);
+        SY_TICK(1);
+        // w_i = tau y - (tau^2 / 2)(y . v) v, every CTA redundantly (same order, same bits)
+        const double half = 0.5 * tau_i * tau_i * dot;
+        const double wr1 = tau_i * y1 - half;  // w_i[i+1]; v_i[i+1] = 1
+        const double diag = o1 - 2.0 * wr1;    // A^(i+1)[i+1][i+1]
+        // reflector i into V (column-major; rows i+2.. hold v_i[i+2..], the leading 1 at row i+1 is implicit)
+        if (me == i % G) {
+#pragma unroll
+            for (int k = 0; k < SY_KMAX; k++) {
+                const int c = tid + k * SY_THREADS;
+                if (c >= i + 2 && c < n) Vcm[(size_t) i * n + c] = vreg[k];
+            }
+        }
+        if (!more) { // last column: only d[n-1] is left
+            if (me == 0 && tid == 0) d[n - 1] = diag;
+            break;
+        }
+        // column i+1 of A^(i+1) (= row i+1 by symmetry) from the published row, then reflector i+1
+        double xk[SY_KMAX], ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < SY_KMAX; k++) {
+            const int c = tid + k * SY_THREADS;
+            const double wc = (c > i && c < n) ? tau_i * yk[k] - half * vreg[k] : 0.0;
+            if (c < np) w[c] = wc;
+            xk[k] = (c > i + 1 && c < n) ? ok[k] - wc - wr1 * vreg[k] : 0.0;
+            if (c > i + 2) ss = fma(xk[k], xk[k], ss);
+        }
+        SY_TICK(2);
+        ss = bb::block_sum(ss, red);
+        const double v2 = v[i + 2];
+        const double alpha = o2 - (tau_i * y2 - half * v2) - wr1 * v2;
+        double beta_n = alpha, tau_n = 0.0, scal = 0.0;
+        if (ss != 0.0) {
+            beta_n = -copysign(sqrt(alpha * alpha + ss), alpha);
+            tau_n = (beta_n - alpha) / beta_n;
+            scal = 1.0 / (alpha - beta_n);
+        }
+#pragma unroll
+        for (int k = 0; k < SY_KMAX; k++) {
+            const int c = tid + k * SY_THREADS;
+            vreg[k] = c == i + 2 ? 1.0 : xk[k] * scal; // 0 for c <= i+1 and beyond n
+            if (c < np) vn[c] = vreg[k];
+        }
+        if (me == (i + 1) % G && tid == 0) { d[i + 1] = diag; e[i + 1] = beta_n; tau[i + 1] = tau_n; }
+        __syncthreads();
+        SY_TICK(3);
+        // ---- one pass over the own rows: A22 -= v w^T + w v^T and y_{i+1} = A22 v_{i+1}.  A warp takes 64-column chunks,
+        // loads w, v, v_{i+1} of the chunk once and walks the CTA's rows with them (shared-memory traffic is the bound of
+        // this phase: the vectors are read once per chunk, not once per row).  Columns <= i need no mask: w = v = 0 there.
+        {
+            double acc[SY_RMAX], vr[SY_RMAX], wr[SY_RMAX];
+            unsigned live = 0u;
+#pragma unroll
+            for (int q = 0; q < SY_RMAX; q++) {
+                acc[q] = 0.0;
+                const int r = me + q * G;
+                const bool on = q < nrows && r > i;
+                if (on) live |= 1u << q;
+                vr[q] = on ? v[r] : 0.0;
+                wr[q] = on ? w[r] : 0.0;
+            }
+            for (int c0 = ((i + 1) & ~63) + 64 * wid; c0 < np; c0 += 64 * NW) {
+                const int c = c0 + 2 * lane;
+                const double2 w2 = *reinterpret_cast<const double2*>(w + c), v2c = *reinterpret_cast<const double2*>(v + c),
+                        n2 = *reinterpret_cast<const double2*>(vn + c);
+#pragma unroll
+                for (int q = 0; q < SY_RMAX; q++) {
+                    if (live & (1u << q)) {
+                        double2 *p = reinterpret_cast<double2*>(rows + (size_t) q * np + c);
+                        double2 a2 = *p;
+                        a2.x = a2.x - vr[q] * w2.x - wr[q] * v2c.x;
+                        a2.y = a2.y - vr[q] * w2.y - wr[q] * v2c.y;
+                        *p = a2;
+                        acc[q] = fma(a2.x, n2.x, fma(a2.y, n2.y, acc[q]));
+                    }
+                }
+            }
+            // the 16 row sums of a warp in one butterfly: each level halves the values a lane carries (16 double shuffles
+            // instead of 16 x 5); lane l ends with the total of row l >> 1
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const bool up = (lane & 16) != 0;
+                const double send = up ? acc[q] : acc[q + 8], keep = up ? acc[q + 8] : acc[q];
+                acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const bool up = (lane & 8) != 0;
+                const double send = up ? acc[q] : acc[q + 4], keep = up ? acc[q + 4] : acc[q];
+                acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const bool up = (lane & 4) != 0;
+                const double send = up ? acc[q] : acc[q + 2], keep = up ? acc[q + 2] : acc[q];
+                acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {
+                const bool up = (lane & 2) != 0;
+                const double send = up ? acc[0] : acc[1], keep = up ? acc[1] : acc[0];
+                acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+            }
+            if ((lane & 1) == 0 && (lane >> 1) < nrows) part[wid * cap + (lane >> 1)] = acc[0];
+            __syncthreads();
+            if (tid < nrows) {
+                const int r = me + tid * G;
+                if (r > i + 1) {
+                    double s = 0.0;
+                    for (int u = 0; u < NW; u++) s += part[u * cap + tid];
+                    ybuf[(size_t) (parity ^ 1) * n + r] = s;
+                }
+            }
+        }
+        if ((i + 2) % G == me) { // row i+2 of A^(i+1): the source of reflector i+2
+            const double *row = rows + (size_t) ((i + 2) / G) * np;
+            for (int c = tid; c < n; c += SY_THREADS) rowbuf[(size_t) (parity ^ 1) * n + c] = row[c];
+        }
+        SY_TICK(4);
+        { double *t = v; v = vn; vn = t; } // roll: v_{i+1} becomes the current reflector
+        tau_i = tau_n;
+    }
+    if (prof != nullptr && tid == 0 && me < 4)
+        for (int k = 0; k < 6; k++) prof[me * 6 + k] = tacc[k];
+#undef SY_TICK
+}
+
+} // namespace
+
+extern "C" {
+
+// Tridiagonalise one symmetric matrix (host buffers; unit tests and the timing probe).  h_A: n*n row-major, the lower
+// triangle is read.  Outputs in LAPACK dsytrd('L') convention: d[n], e[n-1], tau[n-1], and h_V (n*n COLUMN-major) with
+// reflector i in rows i+2.. of column i (its implicit leading 1 at row i+1).  *ms receives the kernel time (CUDA events).
+int bbgpu_sytrd_host(bbgpu_ctx *ctx, int n, const double *h_A, double *h_d, double *h_e, double *h_tau, double *h_V, int reps,
+                     float *ms) {
+    BB_ARG(ctx && h_A && h_d && h_e && h_tau && n >= 3 && reps >= 1);
+    cudaStream_t st = ctx->stream;
+    const int G = ctx->sm_count;
+    const int nrows = (n + G - 1) / G;
+    const int np = (n + 63) & ~63;
+    if (n > SY_KMAX * SY_THREADS || nrows > SY_RMAX)
+        return bb::fail(BBGPU_ERR_ARG, "bbgpu_sytrd_host: n = %d is beyond this kernel (n <= %d and <= %d rows per SM)", n, SY_KMAX * SY_THREADS, SY_RMAX);
+    const size_t smem = ((size_t) nrows * np + 3 * (size_t) np + 32 + 8 * (size_t) nrows) * sizeof(double);
+    if (smem > 220 * 1024) return bb::fail(BBGPU_ERR_ARG, "bbgpu_sytrd_host: n = %d needs %zu bytes of shared memory per CTA", n, smem);
+    BB_CUDA(cudaFuncSetAttribute(sytrd_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int per_sm = 0;
+    BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sytrd_coop_kernel, SY_THREADS, smem));
+    if (per_sm < 1) return bb::fail(BBGPU_ERR_ARG, "bbgpu_sytrd_host: the kernel does not fit an SM");
+    double *dA = nullptr, *dd = nullptr, *de = nullptr, *dt = nullptr, *dV = nullptr, *dy = nullptr, *dr = nullptr;
+    BB_TRY(bb::dev_alloc(&dA, (size_t) n * n));
+    BB_TRY(bb::dev_alloc(&dV, (size_t) n * n));
+    BB_TRY(bb::dev_alloc(&dd, (size_t) n));
+    BB_TRY(bb::dev_alloc(&de, (size_t) n));
+    BB_TRY(bb::dev_alloc(&dt, (size_t) n));
+    BB_TRY(bb::dev_alloc(&dy, (size_t) 2 * n));
+    BB_TRY(bb::dev_alloc(&dr, (size_t) 2 * n));
+    BB_CUDA(cudaMemcpyAsync(dA, h_A, (size_t) n * n * 8, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemsetAsync(dV, 0, (size_t) n * n * 8, st));
+    int nn = n, ld = n;
+    unsigned *dbar = nullptr;
+    BB_TRY(bb::dev_alloc(&dbar, (size_t) 1));
+    long long *dprof = nullptr;
+    BB_TRY(bb::dev_alloc(&dprof, (size_t) 24));
+    void *args[] = { (void*) &dA, (void*) &nn, (void*) &ld, (void*) &dd, (void*) &de, (void*) &dt, (void*) &dV, (void*) &dy, (void*) &dr, (void*) &dbar, (void*) &dprof };
+    (void) 0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < reps; r++) {
+        BB_CUDA(cudaMemsetAsync(dbar, 0, sizeof(unsigned), st));
+        cudaEventRecord(e0, st);
+        BB_CUDA(cudaLaunchCooperativeKernel((const void*) sytrd_coop_kernel, dim3(G), dim3(SY_THREADS), args, smem, st));
+        BB_TRY(bb::launched(ctx, "sytrd_coop_kernel"));
+        cudaEventRecord(e1, st);
+        BB_CUDA(cudaEventSynchronize(e1));
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        best = t < best ? t : best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = best;
+    BB_CUDA(cudaMemcpyAsync(h_d, dd, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaMemcpyAsync(h_e, de, (size_t) (n - 1) * 8, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaMemcpyAsync(h_tau, dt, (size_t) (n - 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (h_V) BB_CUDA(cudaMemcpyAsync(h_V, dV, (size_t) n * n * 8, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    if (getenv("BBGPU_SYTRD_PROF")) { // cycles per phase and column (CTAs 0, 1): barrier, load + dot, w + x, reflector, pass, rest
+        long long hp[24];
+        cudaMemcpy(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost);
+        for (int b = 0; b < 2; b++)
+            fprintf(stderr, "sytrd phases (cycles per column, CTA %d): barrier %.0f load+dot %.0f w+x %.0f reflector %.0f pass %.0f other %.0f\n", b,
+                    hp[b * 6 + 0] / (double) n, hp[b * 6 + 1] / (double) n, hp[b * 6 + 2] / (double) n, hp[b * 6 + 3] / (double) n,
+                    hp[b * 6 + 4] / (double) n, hp[b * 6 + 5] / (double) n);
+    }
+    cudaFree(dA); cudaFree(dV); cudaFree(dd); cudaFree(de); cudaFree(dt); cudaFree(dy); cudaFree(dr); cudaFree(dbar); cudaFree(dprof);
+    return BBGPU_OK;
+}
+
+} // extern "C"

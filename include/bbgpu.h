@@ -402,6 +402,14 @@ int bbgpu_cmab_set_sigma(bbgpu_cmab *h, int run, double sigma);
 /* candidates, fitness (by candidate) and ranking of the run's last generation of the last step */
 int bbgpu_cmab_get_population(bbgpu_cmab *h, int run, double *h_X, double *h_f, int32_t *h_rank);
 int bbgpu_cmab_adopt_basis(bbgpu_cmab *h, int run, const double *h_B, const double *h_D);
+/* Householder tridiagonalisation of ONE dense symmetric matrix as one persistent cooperative kernel (the
+ * matrix distributed over the SMs' shared memory, one grid barrier per column): the building block of
+ * a replacement for cuSOLVER's sytrd, 80 % of the n = 1000 decomposition (cma/cmaes.cpp:285-381 is the
+ * reference's tred2).  Host buffers; h_A n*n row-major (lower triangle read); outputs in LAPACK
+ * dsytrd('L') convention: d[n], e[n-1], tau[n-1], h_V (may be NULL) n*n COLUMN-major with reflector i in
+ * rows i+2.. of column i.  *ms (may be NULL): best kernel time of `reps` launches. */
+int bbgpu_sytrd_host(bbgpu_ctx *ctx, int n, const double *h_A, double *h_d, double *h_e, double *h_tau,
+                     double *h_V, int reps, float *ms);
 /* the in-CTA solver alone (unit tests): `count` symmetric n x n matrices (lower triangles read) ->
  * B (B[i*n+j] = component i of eigenvector j), eigenvalues ascending, info = QL iterations or -1 */
 int bbgpu_eig_small_host(bbgpu_ctx *ctx, int n, int count, const double *h_A, double *h_B,

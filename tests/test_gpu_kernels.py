@@ -106,3 +106,28 @@ def test_philox_normals_are_standard_normal_and_placement_invariant(ctx):
     assert not np.array_equal(z, ctx.philox_normal(1234, 8, 512, 1001))
     # the first rows do not depend on how many rows are drawn (candidate-keyed counters)
     assert np.array_equal(z[:64], ctx.philox_normal(1234, 7, 64, 1001))
+
+
+@pytest.mark.parametrize("n", [3, 10, 149, 600, 1000])
+def test_cooperative_sytrd_matches_lapack(ctx, n):
+    """The persistent-kernel tridiagonalisation against LAPACK dsytrd('L') on the same matrix: same convention, so d, e, tau
+    agree to rounding, and the reflectors reproduce Q^T A Q = T."""
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((n, n))
+    A = np.eye(n) + 1e-2 * (M + M.T) + np.diag(rng.uniform(0, 1, n))  # a CMA-like covariance: clustered spectrum
+    d, e, tau, V, ms = ctx.sytrd(A)
+    c, d0, e0, tau0, info = lapack.dsytrd(A, lower=1)
+    assert info == 0
+    scale = np.abs(A).max()
+    assert np.abs(d - d0).max() <= 1e-11 * scale and np.abs(np.abs(e) - np.abs(e0)).max() <= 1e-11 * scale
+    # Q = H_0 H_1 ... ; H_i = I - tau_i v_i v_i^T, v_i = (0,...,0, 1, V[i+2:, i])
+    Q = np.eye(n)
+    for i in range(n - 1):
+        v = np.zeros(n)
+        v[i + 1] = 1.0
+        v[i + 2:] = V[i + 2:, i]
+        Q = Q - tau[i] * np.outer(Q @ v, v)
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    assert np.abs(Q.T @ Q - np.eye(n)).max() <= 1e-12 * n
+    assert np.abs(Q.T @ A @ Q - T).max() <= 1e-12 * n * scale
