@@ -874,7 +874,10 @@ struct bbgpu_cmab {
     std::vector<long long> h_xoff;
     RunDev *d_fresh = nullptr;  // staging for starts
     double *d_guess = nullptr;
-    std::map<int, double*> weights; // lambda -> device table of mu weights (base_cmaes.cpp:94-100)
+    std::map<int, double*> weights; // lambda -> device table of mu weights (base_cmaes.cpp:94-100), carved from slabs:
+    std::vector<double*> slabs;     // no cudaMalloc while a batch runs (it would stall on the other streams' kernels)
+    size_t slab_left = 0;
+    double *slab_next = nullptr;
     bool attr_small = false, attr_large = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr; // the large-lambda class runs on the ctx's side stream
     int last_ns = 0, last_nl = 0, last_maxlam = 0;    // lists of the last launch (phase 2 reuses its phase 1's)
@@ -890,7 +893,8 @@ int ensure_pool(bbgpu_cmab *h, size_t cands) {
     if (h->F) cudaFree(h->F);
     if (h->I) cudaFree(h->I);
     h->X = nullptr; h->F = nullptr; h->I = nullptr; h->pool_cap = 0;
-    const size_t want = cands + cands / 4 + 1024;
+    // generous: growing frees and allocates, and both stall on whatever the other streams are running
+    const size_t want = std::max(2 * cands, (size_t) h->runs * 128) + 1024;
     BB_TRY(bb::dev_alloc(&h->X, want * h->n));
     BB_TRY(bb::dev_alloc(&h->F, want));
     BB_TRY(bb::dev_alloc(&h->I, want));
@@ -970,7 +974,7 @@ int bbgpu_cmab_destroy(bbgpu_cmab *h) {
     void *ptrs[] = { h->d_runs, h->d_status, h->d_list, h->d_fresh, h->d_xoff, h->xmean, h->xold, h->pc, h->ps, h->D, h->xbest, h->C,
             h->B, h->isC, h->hbest, h->hkth, h->d_guess, h->lower, h->upper, h->X, h->F, h->I, h->Z };
     for (void *p : ptrs) if (p) cudaFree(p);
-    for (auto &kv : h->weights) cudaFree(kv.second);
+    for (double *sl : h->slabs) cudaFree(sl);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
@@ -989,10 +993,19 @@ int bbgpu_cmab_start(bbgpu_cmab *h, int count, const int32_t *run_ids, const bbg
     const size_t b_runs = sizeof(RunDev) * count, b_list = bb::round_up(sizeof(int) * count, 8), b_guess = (size_t) count * n * 8;
     void *pin = nullptr;
     BB_CUDA(cudaStreamSynchronize(st)); // the pinned staging buffer may still be in flight
-    BB_TRY(ctx->pinned(b_runs + b_list + b_guess, &pin));
+    size_t wnew = 0; // weights of the lambdas seen for the first time in this call
+    {
+        std::map<int, int> fresh;
+        for (int q = 0; q < count; q++)
+            if (params[q].lambda >= 2 && params[q].mu >= 1 && !h->weights.count(params[q].lambda)) fresh[params[q].lambda] = params[q].mu;
+        for (auto &kv : fresh) wnew += (size_t) kv.second;
+    }
+    BB_TRY(ctx->pinned(b_runs + b_list + b_guess + wnew * sizeof(double), &pin));
     RunDev *fr = (RunDev*) pin;
     int *ls = (int*) ((char*) pin + b_runs);
     double *gs = (double*) ((char*) pin + b_runs + b_list);
+    double *ws = (double*) ((char*) pin + b_runs + b_list + b_guess);
+    size_t wused = 0;
     for (int q = 0; q < count; q++) {
         const bbgpu_cmab_run_params &p = params[q];
         const int run = run_ids[q];
@@ -1002,10 +1015,22 @@ int bbgpu_cmab_start(bbgpu_cmab *h, int count, const int32_t *run_ids, const bbg
         if (hlen < 1 || hlen > HCAP)
             return bb::fail(BBGPU_ERR_ARG, "bbgpu_cmab_start: history length %d outside [1, %d]", hlen, HCAP);
         auto it = h->weights.find(p.lambda);
-        if (it == h->weights.end()) {
-            double *dw = nullptr;
-            BB_TRY(bb::dev_alloc(&dw, (size_t) p.mu));
-            BB_CUDA(cudaMemcpy(dw, p.weights, sizeof(double) * p.mu, cudaMemcpyHostToDevice));
+        if (it == h->weights.end()) { // first run at this lambda: a table from the slab, uploaded with the rest of this call
+            const size_t need = ((size_t) p.mu + 1) & ~(size_t) 1;
+            if (need > h->slab_left) {
+                const size_t slab = std::max(need, (size_t) 1 << 21); // 16 MB
+                double *sl = nullptr;
+                BB_TRY(bb::dev_alloc(&sl, slab));
+                h->slabs.push_back(sl);
+                h->slab_next = sl;
+                h->slab_left = slab;
+            }
+            double *dw = h->slab_next;
+            h->slab_next += need;
+            h->slab_left -= need;
+            memcpy(ws + wused, p.weights, sizeof(double) * p.mu);
+            BB_CUDA(cudaMemcpyAsync(dw, ws + wused, sizeof(double) * p.mu, cudaMemcpyHostToDevice, st));
+            wused += p.mu;
             it = h->weights.emplace(p.lambda, dw).first;
         }
         RunDev r;
