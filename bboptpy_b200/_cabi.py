@@ -184,6 +184,7 @@ def lib():
     L.bbgpu_cmab_adopt_basis.argtypes = [vp, i, vp, vp]
     L.bbgpu_eig_small_host.argtypes = [vp, i, i, vp, vp, vp, vp]
     L.bbgpu_sytrd_host.argtypes = [vp, i, vp, vp, vp, vp, vp, i, P(ctypes.c_float)]
+    L.bbgpu_stedc_host.argtypes = [vp, i, vp, vp, vp, vp, P(ctypes.c_float)]
     _lib = L
     return L
 
@@ -305,6 +306,16 @@ class Context:
         check(self.L.bbgpu_sytrd_host(self.h, n, A.ctypes.data, d.ctypes.data, e.ctypes.data, tau.ctypes.data, V.ctypes.data, reps,
                                       ctypes.byref(ms)))
         return d, e, tau, V.T.copy(), ms.value
+
+    def stedc(self, d, e):
+        """Tridiagonal divide & conquer on the device: eigenvalues ascending, Z with eigenvectors as COLUMNS, time in ms."""
+        d, e = f64(d), f64(e)
+        n = d.size
+        w, Zt = np.empty(n), np.empty((n, n))
+        ms = ctypes.c_float(0)
+        check(self.L.bbgpu_stedc_host(self.h, n, d.ctypes.data, e.ctypes.data if n > 1 else None, w.ctypes.data, Zt.ctypes.data,
+                                      ctypes.byref(ms)))
+        return w, Zt.T.copy(), ms.value
 
     def bench_dgemm(self, M, N, K, reps=10):
         ms = ctypes.c_float(0)

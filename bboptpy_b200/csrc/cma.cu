@@ -46,6 +46,9 @@ struct bbgpu_cma {
     // eigensolver workspace
     double *solver_work = nullptr;
     int solver_lwork = 0;
+    double *own_ws = nullptr;     // own eigensolver: d, e, tau, reflectors (n*n), sytrd workspace, ormtr workspace
+    int own_lwork = 0;
+    int *own_info = nullptr;
     int *dev_info = nullptr;
     // draw prefetch: Z is double buffered; the draws of generation g+1 are generated on the ctx's side
     // stream while generation g runs its update (counter-based Philox: they depend on nothing)
@@ -75,6 +78,11 @@ int comm_allreduce_sum(bbgpu_comm *c, double *d_buf, size_t count);
 int comm_allgather(bbgpu_comm *c, double *d_buf, size_t per);
 int comm_allgather2(bbgpu_comm *c, double *d_a, double *d_b, size_t per);
 int comm_broadcast(bbgpu_comm *c, double *d_buf, size_t count, int root);
+// sytrd.cu / stedc.cu: our own dense symmetric eigensolver (tridiagonalisation + divide & conquer)
+bool sytrd_fits(bbgpu_ctx *ctx, int n);
+size_t sytrd_workspace_doubles(int n);
+int sytrd_device(bbgpu_ctx *ctx, int n, const double *d_A, int ldA, double *d_d, double *d_e, double *d_tau, double *d_Vcm, double *ws);
+int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double *W, double *Zt_out, int ldz, int *d_info);
 struct PeerRegion;
 int comm_peer_region_create(bbgpu_comm *c, double *d_local, size_t bytes, PeerRegion **out);
 int comm_peer_region_destroy(PeerRegion *r);
@@ -938,19 +946,43 @@ static int do_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
     }
     cusolverDnHandle_t sv;
     BB_TRY(get_solver(ctx, &sv));
-    dim3 grid(ceil_div(n, 256), n);
-    symmetrize_kernel<<<grid, 256, 0, st>>>(h->C, h->Bt, n, h->ldn);
-    BB_TRY(launched(ctx, "symmetrize_kernel"));
-    if (h->solver_work == nullptr) {
-        int lwork = 0;
-        if (cusolverDnDsyevd_bufferSize(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->Bt, (int) h->ldn, h->W,
-                &lwork) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "syevd_bufferSize failed");
-        BB_TRY(dev_alloc(&h->solver_work, (size_t) lwork));
-        h->solver_lwork = lwork;
+    // Own solver where it pays and fits (cuSOLVER's syevd spends 80 % of its 12 ms at n = 1000 in a latency-bound sytrd):
+    // cooperative sytrd -> tridiagonal divide & conquer -> cuSOLVER ormtr for the back-transformation.
+    // BBGPU_EIG=cusolver forces the library path.
+    static const bool force_lib = [] { const char *e = getenv("BBGPU_EIG"); return e && e[0] == 'c'; }();
+    if (!force_lib && n >= 256 && sytrd_fits(ctx, n)) {
+        const size_t nn = (size_t) n;
+        if (h->own_ws == nullptr) {
+            int lw = 0;
+            if (cusolverDnDormtr_bufferSize(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, h->Bt, n, h->W, h->Bt,
+                    (int) h->ldn, &lw) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "ormtr_bufferSize failed");
+            h->own_lwork = lw;
+            BB_TRY(dev_alloc(&h->own_ws, 3 * nn + nn * nn + sytrd_workspace_doubles(n) + (size_t) lw + 16));
+            BB_TRY(dev_alloc(&h->own_info, (size_t) 4));
+        }
+        double *dd = h->own_ws, *de = dd + nn, *dtau = de + nn, *Vcm = dtau + nn, *ws = Vcm + nn * nn,
+                *owork = ws + sytrd_workspace_doubles(n);
+        BB_CUDA(cudaMemsetAsync(de, 0, 2 * nn * 8, st));
+        BB_TRY(sytrd_device(ctx, n, h->C, (int) h->ldn, dd, de, dtau, Vcm, ws));
+        BB_TRY(stedc_device(ctx, n, dd, de, h->W, h->Bt, (int) h->ldn, h->dev_info));
+        const cusolverStatus_t rc = cusolverDnDormtr(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, Vcm, n, dtau,
+                h->Bt, (int) h->ldn, owork, h->own_lwork, h->own_info);
+        if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDormtr failed with status %d", (int) rc);
+    } else {
+        dim3 grid(ceil_div(n, 256), n);
+        symmetrize_kernel<<<grid, 256, 0, st>>>(h->C, h->Bt, n, h->ldn);
+        BB_TRY(launched(ctx, "symmetrize_kernel"));
+        if (h->solver_work == nullptr) {
+            int lwork = 0;
+            if (cusolverDnDsyevd_bufferSize(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->Bt, (int) h->ldn, h->W,
+                    &lwork) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "syevd_bufferSize failed");
+            BB_TRY(dev_alloc(&h->solver_work, (size_t) lwork));
+            h->solver_lwork = lwork;
+        }
+        const cusolverStatus_t rc = cusolverDnDsyevd(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->Bt, (int) h->ldn,
+                h->W, h->solver_work, h->solver_lwork, h->dev_info);
+        if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDsyevd failed with status %d", (int) rc);
     }
-    const cusolverStatus_t rc = cusolverDnDsyevd(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->Bt, (int) h->ldn,
-            h->W, h->solver_work, h->solver_lwork, h->dev_info);
-    if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDsyevd failed with status %d", (int) rc);
     eig_post_kernel<<<1, 1024, 0, st>>>(h->W, h->D, h->C, n, h->ldn, h->dev_info, h->d_report);
     BB_TRY(launched(ctx, "eig_post_kernel"));
     return refresh_basis_products(h);
@@ -1104,7 +1136,8 @@ int bbgpu_cma_destroy(bbgpu_cma *h) {
     }
     double *bufs[] = { h->xmean, h->xold, h->pc, h->ps, h->D, h->dm, h->tmpn, h->W, h->weights, h->lower, h->upper, h->coef,
             h->ycoeff, h->dscal, h->X, h->Zbuf[0], h->Zbuf[1], h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
-            h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc };
+            h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc, h->own_ws };
+    if (h->own_info) cudaFree(h->own_info);
     for (double *b : bufs) if (b) cudaFree(b);
     if (h->rank_idx) cudaFree(h->rank_idx);
     if (h->dev_info) cudaFree(h->dev_info);

@@ -1,0 +1,524 @@
+// Eigen-decomposition of a symmetric tridiagonal matrix by divide & conquer (Cuppen; deflation as in LAPACK dlaed2,
+// eigenvectors through the Gu-Eisenstat / Loewner recomputation of z as in dlaed3), entirely on the device.
+// Second half of the replacement for cuSOLVER's syevd at n = 1000 (first half: sytrd.cu); cuSOLVER exports no device-side
+// tridiagonal solver.  Reference being replaced: the QL iteration of cma/cmaes.cpp:383-478 (any correct eigenbasis serves:
+// DESIGN.md "The eigendecomposition at n = 1000").
+//
+// T is torn into leaves of <= 64 rows (boundaries at multiples of 8), solved by the one-warp QL solver of eig_small.cuh;
+// every merge of two solved halves  diag(D1, D2) + rho z z^T  runs as a handful of launches over ALL merges of its level:
+//   setup    z from the touching rows of the children's eigenvectors, merge-sort of D by counting ranks, the sequential
+//            deflation scan (tiny z_j; close D with a Givens rotation) -> per position an action code and slot
+//   secular  one warp per root: the root of 1 + rho sum z_j^2 / (d_j - lambda) in its interval by bisection on
+//            mu = lambda - d_origin (origin = the nearer pole, so d_j - lambda keeps full relative accuracy)
+//   zhat     z recomputed from the roots (Loewner), one warp per component: the computed vectors are orthogonal to
+//            working precision whatever the clustering
+//   vectors  eigenvectors of the rank-one problem, one warp per root, normalised
+//   gather   one thread per row of the children's basis: permutation + the chain of Givens rotations, emitting deflated
+//            vectors to their final place and the others as the right operand of
+//   gemm     new vectors = (rank-one eigenvectors) x (gathered basis)
+// Eigenvectors are stored TRANSPOSED (row = eigenvector): that is the layout the CMA engine keeps (Bt) and what
+// cusolverDnDormtr sees as the column-major matrix to multiply by the Householder reflectors.
+#include <algorithm>
+#include <vector>
+
+#include "eig_small.cuh"
+
+namespace {
+
+constexpr int DC_LEAF = 64;
+constexpr int DC_THREADS = 256;
+
+struct DcNode { int o, k, m; }; // rows [o, o+k), children [o, o+m) and [o+m, o+k)
+
+struct DcWork { // per-position scratch (length n each) and per-node scalars
+    double *Ds, *zs, *dk, *zk, *mu, *zhat, *rc, *rs, *ddefl, *rho;
+    int *perm, *act, *slot, *org, *K, *lastslot;
+};
+
+// ---- leaves ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) dc_leaf_kernel(const DcNode *nodes, const double *dadj, const double *e, double *Zt, int ld,
+        double *lam, int *info) {
+    extern __shared__ __align__(16) double sm[];
+    const DcNode nd = nodes[blockIdx.x];
+    const int k = nd.k, o = nd.o, ldv = k | 1, lane = threadIdx.x;
+    double *Vt = sm, *d = Vt + k * ldv, *ee = d + k, *srt = ee + k;
+    for (int idx = lane; idx < k * ldv; idx += 32) Vt[idx] = 0.0;
+    __syncwarp();
+    for (int j = lane; j < k; j += 32) {
+        Vt[j * ldv + j] = 1.0;
+        d[j] = dadj[o + j];
+        ee[j] = j < k - 1 ? e[o + j] : 0.0;
+    }
+    __syncwarp();
+    int qi = 0;
+    const bool ok = k == 1 ? true : bb::warp_tred2_tql2(k, ldv, Vt, d, ee, &qi, true);
+    __syncwarp();
+    if (!ok) { if (lane == 0) *info = 1; return; }
+    for (int j = lane; j < k; j += 32) {
+        const double val = d[j];
+        int pos = 0;
+        for (int q = 0; q < k; q++) pos += (d[q] < val) || (d[q] == val && q < j);
+        srt[j] = (double) pos;
+    }
+    __syncwarp();
+    for (int j = 0; j < k; j++) {
+        const int pos = (int) srt[j];
+        if (lane == 0) lam[o + pos] = d[j];
+        for (int r = lane; r < k; r += 32) Zt[(size_t) (o + pos) * ld + o + r] = Vt[j * ldv + r];
+    }
+}
+
+__global__ void dc_adjust_kernel(const double *d, const double *e, const int *bounds, int nb, double *dadj, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = d[i];
+    for (int b = 0; b < nb; b++) { // Cuppen's tearing: both neighbours of a boundary lose |e|
+        const int p = bounds[b];
+        if (i == p - 1 || i == p) v -= fabs(e[p - 1]);
+    }
+    dadj[i] = v;
+}
+
+// ---- merge: setup + deflation scan (one CTA per merge) ---------------------------------------------------------------
+__global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *nodes, const double *e, const double *Zt, int ld,
+        const double *lam, DcWork w, double *lam_new) {
+    const DcNode nd = nodes[blockIdx.x];
+    const int k = nd.k, o = nd.o, m = nd.m, tid = threadIdx.x;
+    __shared__ double red[32];
+    __shared__ double s_tol, s_rho;
+    const double beta = e[o + m - 1];
+    const double sgn = beta < 0 ? -1.0 : 1.0;
+    // z = (last row of Q1, sign * first row of Q2); the rows of Zt are eigenvectors, so these are columns o+m-1 and o+m
+    double ss = 0.0, dmax = 0.0;
+    for (int j = tid; j < k; j += DC_THREADS) {
+        const double z = j < m ? Zt[(size_t) (o + j) * ld + o + m - 1] : sgn * Zt[(size_t) (o + j) * ld + o + m];
+        w.zk[o + j] = z; // scratch: unsorted
+        ss += z * z;
+        dmax = fmax(dmax, fabs(lam[o + j]));
+    }
+    ss = bb::block_sum(ss, red);
+    dmax = bb::block_max(dmax, red);
+    const double zn = sqrt(ss), rho = fabs(beta) * ss;
+    __syncthreads();
+    double zmax = 0.0;
+    for (int j = tid; j < k; j += DC_THREADS) { // merge the two ascending halves: rank by counting
+        const double dj = lam[o + j];
+        int pos = 0;
+        for (int q = 0; q < k; q++) {
+            const double dq = lam[o + q];
+            pos += (dq < dj) || (dq == dj && q < j);
+        }
+        const double z = w.zk[o + j] / zn;
+        w.perm[o + pos] = j;
+        w.Ds[o + pos] = dj;
+        w.zs[o + pos] = z;
+        zmax = fmax(zmax, fabs(z));
+    }
+    zmax = bb::block_max(zmax, red);
+    if (tid == 0) {
+        s_tol = 8.0 * 2.220446049250313e-16 * fmax(dmax, zmax);
+        s_rho = rho;
+        w.rho[blockIdx.x] = rho;
+    }
+    __syncthreads();
+    // The deflation scan is sequential (dlaed2: every decision changes the next comparison): thread 0 walks the sorted
+    // poles in SHARED memory (a walk over global memory cost ~2 us per pole and was most of the solver's time).
+    extern __shared__ __align__(16) double ssm[];
+    double *D = ssm, *z = D + k, *src = z + k, *srs = src + k, *sdk = srs + k, *szk = sdk + k, *sdd = szk + k;
+    int *sact = reinterpret_cast<int*>(sdd + k), *sslot = sact + k;
+    for (int j = tid; j < k; j += DC_THREADS) { D[j] = w.Ds[o + j]; z[j] = w.zs[o + j]; src[j] = 0.0; srs[j] = 0.0; }
+    __syncthreads();
+    if (tid == 0) {
+        const double tol = s_tol;
+        int K = 0, nd_ = 0, pj = -1;
+        if (rho * zmax <= tol) {
+            for (int j = 0; j < k; j++) { sact[j] = 0; sslot[j] = nd_; sdd[nd_] = D[j]; nd_++; }
+        } else {
+            for (int j = 0; j < k; j++) {
+                if (rho * fabs(z[j]) <= tol) { // the component does not feel the rank-one term
+                    sact[j] = 0; sslot[j] = nd_; sdd[nd_] = D[j]; nd_++;
+                    continue;
+                }
+                if (pj < 0) { sact[j] = 1; sslot[j] = 0; pj = j; continue; }
+                // dlaed2's test |t c s| <= tol with c = z_j / tau, s = -z_pj / tau, tau^2 = z_j^2 + z_pj^2, without forming them
+                // (the scan is one thread's dependency chain: no square root, no division unless a pole really deflates)
+                const double zp = z[pj], zj = z[j], t = D[j] - D[pj];
+                if (fabs(t * zj * zp) <= tol * (zj * zj + zp * zp)) { // two close poles: rotate the older one out
+                    const double tau = sqrt(zj * zj + zp * zp);
+                    const double c = zj / tau, s = -zp / tau;
+                    z[j] = tau;
+                    z[pj] = 0.0;
+                    const double tt = D[pj] * c * c + D[j] * s * s;
+                    D[j] = D[pj] * s * s + D[j] * c * c;
+                    D[pj] = tt;
+                    sact[j] = 2; sslot[j] = nd_; src[j] = c; srs[j] = s;
+                    sdd[nd_] = tt; nd_++;
+                } else { // the older pole stays in the secular problem
+                    sact[j] = 3; sslot[j] = K;
+                    sdk[K] = D[pj]; szk[K] = z[pj]; K++;
+                }
+                pj = j;
+            }
+            if (pj >= 0) { w.lastslot[blockIdx.x] = K; sdk[K] = D[pj]; szk[K] = z[pj]; K++; }
+        }
+        if (pj < 0) w.lastslot[blockIdx.x] = -1;
+        w.K[blockIdx.x] = K;
+    }
+    __syncthreads();
+    const int K = w.K[blockIdx.x];
+    for (int j = tid; j < k; j += DC_THREADS) {
+        w.act[o + j] = sact[j];
+        w.slot[o + j] = sslot[j];
+        w.rc[o + j] = src[j];
+        w.rs[o + j] = srs[j];
+        if (j < K) { w.dk[o + j] = sdk[j]; w.zk[o + j] = szk[j]; }
+        else lam_new[o + j] = sdd[j - K]; // deflated eigenvalues follow the K roots
+    }
+}
+
+// ---- merge: secular equation, one warp per root ----------------------------------------------------------------------
+__device__ __forceinline__ double dc_secular_f(const double *delta_src, const double *z2, int K, double dorg, double rho, double mu, int lane) {
+    double s = 0.0;
+    for (int j = lane; j < K; j += 32) s += z2[j] / ((delta_src[j] - dorg) - mu);
+    return 1.0 + rho * bb::warp_sum(s);
+}
+
+__global__ void __launch_bounds__(DC_THREADS) dc_secular_kernel(const DcNode *nodes, DcWork w, double *lam_new) {
+    extern __shared__ __align__(16) double sm[];
+    const DcNode nd = nodes[blockIdx.x];
+    const int o = nd.o, K = w.K[blockIdx.x], tid = threadIdx.x, lane = tid & 31;
+    if (K == 0) return;
+    double *dk = sm, *z2 = sm + K;
+    double zsum = 0.0;
+    for (int j = tid; j < K; j += DC_THREADS) {
+        const double z = w.zk[o + j];
+        dk[j] = w.dk[o + j];
+        z2[j] = z * z;
+    }
+    __syncthreads();
+    const double rho = w.rho[blockIdx.x];
+    const int warps = (DC_THREADS / 32) * gridDim.y, wg = blockIdx.y * (DC_THREADS / 32) + (tid >> 5);
+    for (int i = wg; i < K; i += warps) {
+        int org;
+        double lo, hi;
+        bool left;
+        if (i < K - 1) {
+            const double gap = dk[i + 1] - dk[i];
+            left = dc_secular_f(dk, z2, K, dk[i], rho, 0.5 * gap, lane) >= 0.0;
+            org = left ? i : i + 1;
+            lo = left ? 0.0 : -0.5 * gap;
+            hi = left ? 0.5 * gap : 0.0;
+        } else {
+            for (int j = lane; j < K; j += 32) zsum += z2[j];
+            zsum = bb::warp_sum(zsum);
+            left = true;
+            org = i;
+            lo = 0.0;
+            hi = rho * zsum; // the last root lies in (d_K-1, d_K-1 + rho sum z^2]
+        }
+        const double dorg = dk[org];
+        for (int it = 0; it < 400; it++) { // f increases with mu: f(lo) < 0 <= f(hi); the zero end of the bracket is a pole
+            double mid;
+            if (left) mid = lo > 0.0 ? (hi / lo < 16.0 ? 0.5 * (lo + hi) : sqrt(lo * hi)) : hi * 0.0009765625;
+            else mid = hi < 0.0 ? (lo / hi < 16.0 ? 0.5 * (lo + hi) : -sqrt(lo * hi)) : lo * 0.0009765625;
+            if (!(mid > lo && mid < hi)) break;
+            if (dc_secular_f(dk, z2, K, dorg, rho, mid, lane) >= 0.0) hi = mid; else lo = mid;
+        }
+        const double mu = 0.5 * (lo + hi);
+        if (lane == 0) {
+            w.org[o + i] = org;
+            w.mu[o + i] = mu;
+            lam_new[o + i] = dorg + mu;
+        }
+    }
+}
+
+// ---- merge: z from the roots (Loewner), one warp per component -----------------------------------------------------------
+__global__ void __launch_bounds__(DC_THREADS) dc_zhat_kernel(const DcNode *nodes, DcWork w) {
+    const DcNode nd = nodes[blockIdx.x];
+    const int o = nd.o, K = w.K[blockIdx.x], tid = threadIdx.x, lane = tid & 31;
+    const double rho = w.rho[blockIdx.x];
+    const int warps = (DC_THREADS / 32) * gridDim.y, wg = blockIdx.y * (DC_THREADS / 32) + (tid >> 5);
+    for (int j = wg; j < K; j += warps) {
+        const double dj = w.dk[o + j];
+        double p = 1.0;
+        for (int i = lane; i < K; i += 32) {
+            const double num = (w.dk[o + w.org[o + i]] - dj) + w.mu[o + i]; // lambda_i - d_j
+            const double den = i == j ? rho : w.dk[o + i] - dj;
+            p *= num / den;
+        }
+        for (int off = 16; off >= 1; off >>= 1) p *= __shfl_xor_sync(0xffffffffu, p, off);
+        if (lane == 0) w.zhat[o + j] = copysign(sqrt(fabs(p)), w.zk[o + j]);
+    }
+}
+
+// ---- merge: eigenvectors of the rank-one problem: Ut[i][j] = zhat_j / (d_j - lambda_i), rows normalised ---------------
+__global__ void __launch_bounds__(DC_THREADS) dc_vectors_kernel(const DcNode *nodes, DcWork w, double *Ut, int ld) {
+    const DcNode nd = nodes[blockIdx.x];
+    const int o = nd.o, K = w.K[blockIdx.x], tid = threadIdx.x, lane = tid & 31;
+    const int warps = (DC_THREADS / 32) * gridDim.y, wg = blockIdx.y * (DC_THREADS / 32) + (tid >> 5);
+    for (int i = wg; i < K; i += warps) {
+        const double dorg = w.dk[o + w.org[o + i]], mu = w.mu[o + i];
+        double ss = 0.0;
+        for (int j = lane; j < K; j += 32) {
+            const double v = w.zhat[o + j] / ((w.dk[o + j] - dorg) - mu);
+            ss += v * v;
+        }
+        ss = bb::warp_sum(ss);
+        const double inv = 1.0 / sqrt(ss);
+        for (int j = lane; j < K; j += 32)
+            Ut[(size_t) (o + i) * ld + o + j] = w.zhat[o + j] / ((w.dk[o + j] - dorg) - mu) * inv;
+    }
+}
+
+// ---- merge: permutation + Givens chain over the children's basis, one thread per row ----------------------------------
+__global__ void __launch_bounds__(DC_THREADS) dc_gather_kernel(const DcNode *nodes, DcWork w, const double *Zt, double *QselT,
+        double *Zt_new, int ld) {
+    const DcNode nd = nodes[blockIdx.x];
+    const int o = nd.o, k = nd.k, K = w.K[blockIdx.x];
+    const int r = blockIdx.y * DC_THREADS + threadIdx.x;
+    if (r >= k) return;
+    double carry = 0.0;
+    for (int j0 = 0; j0 < k; j0 += 8) { // the loads of 8 positions are issued together: the walk is latency-bound otherwise
+        double y[8];
+        int a[8], sl[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int j = min(j0 + u, k - 1);
+            y[u] = Zt[(size_t) (o + w.perm[o + j]) * ld + o + r];
+            a[u] = w.act[o + j];
+            sl[u] = w.slot[o + j];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int j = j0 + u;
+            if (j >= k) break;
+            if (a[u] == 0) Zt_new[(size_t) (o + K + sl[u]) * ld + o + r] = y[u];
+            else if (a[u] == 1) carry = y[u];
+            else if (a[u] == 2) {
+                const double c = w.rc[o + j], s = w.rs[o + j];
+                Zt_new[(size_t) (o + K + sl[u]) * ld + o + r] = c * carry + s * y[u];
+                carry = c * y[u] - s * carry;
+            } else {
+                QselT[(size_t) (o + sl[u]) * ld + o + r] = carry;
+                carry = y[u];
+            }
+        }
+    }
+    const int last = w.lastslot[blockIdx.x];
+    if (last >= 0) QselT[(size_t) (o + last) * ld + o + r] = carry;
+}
+
+// ---- merge: Zt_new[o+i][o+r] = sum_j Ut[o+i][o+j] QselT[o+j][o+r], i, j < K (device-side), r < k -----------------------
+__global__ void __launch_bounds__(256) dc_gemm_kernel(const DcNode *nodes, const int *Kdev, const double *Ut, const double *QselT,
+        double *Zt_new, int ld) {
+    const DcNode nd = nodes[blockIdx.z];
+    const int o = nd.o, k = nd.k, K = Kdev[blockIdx.z];
+    const int i0 = blockIdx.y * 64, r0 = blockIdx.x * 64;
+    if (i0 >= K || r0 >= k) return;
+    __shared__ double As[16][64 + 1], Bs[16][64];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // 16 x 16 threads, 4 x 4 outputs each
+    double acc[4][4] = { { 0.0 } };
+    const double *A = Ut + (size_t) o * ld + o, *B = QselT + (size_t) o * ld + o;
+    for (int j0 = 0; j0 < K; j0 += 16) {
+        for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) { // A tile: rows i0.., cols j0.. (stored k-major)
+            const int ii = idx >> 4, jj = idx & 15;
+            As[jj][ii] = (i0 + ii < K && j0 + jj < K) ? A[(size_t) (i0 + ii) * ld + j0 + jj] : 0.0;
+        }
+        for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
+            const int jj = idx >> 6, rr = idx & 63;
+            Bs[jj][rr] = (j0 + jj < K && r0 + rr < k) ? B[(size_t) (j0 + jj) * ld + r0 + rr] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < 16; jj++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { a[u] = As[jj][ty * 4 + u]; b[u] = Bs[jj][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const int i = i0 + ty * 4 + u, r = r0 + tx * 4 + v;
+            if (i < K && r < k) Zt_new[(size_t) (o + i) * ld + o + r] = acc[u][v];
+        }
+}
+
+// ---- final: ascending order ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DC_THREADS) dc_rank_kernel(const double *lam, int n, int *pos, double *W) {
+    const int j = blockIdx.x * DC_THREADS + threadIdx.x;
+    if (j >= n) return;
+    const double v = lam[j];
+    int p = 0;
+    for (int q = 0; q < n; q++) {
+        const double u = lam[q];
+        p += (u < v) || (u == v && q < j);
+    }
+    pos[j] = p;
+    W[p] = v;
+}
+
+__global__ void __launch_bounds__(DC_THREADS) dc_permute_kernel(const double *Zt, const int *pos, int n, int ld, double *out, int ldo) {
+    const int j = blockIdx.y;
+    const int r = blockIdx.x * DC_THREADS + threadIdx.x;
+    if (r < n) out[(size_t) pos[j] * ldo + r] = Zt[(size_t) j * ld + r];
+}
+
+void dc_build_tree(int o, int k, int depth, std::vector<std::vector<DcNode>> &levels, std::vector<DcNode> &leaves, std::vector<int> &bounds,
+        int &maxdepth) {
+    if (k <= DC_LEAF) {
+        leaves.push_back({ o, k, 0 });
+        return;
+    }
+    int m = ((k / 2 + 7) / 8) * 8;
+    if (m >= k) m = k / 2;
+    if ((int) levels.size() <= depth) levels.resize(depth + 1);
+    levels[depth].push_back({ o, k, m });
+    bounds.push_back(o + m);
+    maxdepth = std::max(maxdepth, depth);
+    dc_build_tree(o, m, depth + 1, levels, leaves, bounds, maxdepth);
+    dc_build_tree(o + m, k - m, depth + 1, levels, leaves, bounds, maxdepth);
+}
+
+} // namespace
+
+namespace bb {
+
+// T = tridiag(d, e) (device, n and n-1 entries) -> W[n] ascending and Zt (n x ldz, row j = eigenvector of W[j]).
+// Everything is enqueued on the ctx stream; no host synchronisation.  *d_info (device int, zeroed here) becomes 1 when a
+// leaf's QL iteration fails (non-finite input).
+int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double *W, double *Zt_out, int ldz, int *d_info) {
+    cudaStream_t st = ctx->stream;
+    std::vector<std::vector<DcNode>> levels;
+    std::vector<DcNode> leaves;
+    std::vector<int> bounds;
+    int maxdepth = -1;
+    dc_build_tree(0, n, 0, levels, leaves, bounds, maxdepth);
+    const int ld = (n + 7) & ~7;
+    // one scratch allocation: 4 matrices + per-position arrays + node tables
+    size_t nodes_total = leaves.size();
+    for (auto &lv : levels) nodes_total += lv.size();
+    const size_t mat = (size_t) n * ld;
+    const size_t bytes = (4 * mat + 12 * (size_t) n + 64) * sizeof(double) + (6 * (size_t) n + 64) * sizeof(int) +
+            nodes_total * sizeof(DcNode) + (bounds.size() + 8) * sizeof(int) + 4096;
+    void *sp = nullptr;
+    BB_TRY(ctx->scratch(bytes, &sp));
+    char *base = (char*) sp;
+    auto take = [&](size_t b) { char *p = base; base += (b + 255) & ~(size_t) 255; return p; };
+    double *ZA = (double*) take(mat * 8), *ZB = (double*) take(mat * 8), *Qs = (double*) take(mat * 8), *Ut = (double*) take(mat * 8);
+    DcWork w;
+    w.Ds = (double*) take(n * 8); w.zs = (double*) take(n * 8); w.dk = (double*) take(n * 8); w.zk = (double*) take(n * 8);
+    w.mu = (double*) take(n * 8); w.zhat = (double*) take(n * 8); w.rc = (double*) take(n * 8); w.rs = (double*) take(n * 8);
+    w.ddefl = (double*) take(n * 8); w.rho = (double*) take(n * 8);
+    double *lamA = (double*) take(n * 8), *lamB = (double*) take(n * 8), *dadj = (double*) take(n * 8);
+    w.perm = (int*) take(n * 4); w.act = (int*) take(n * 4); w.slot = (int*) take(n * 4); w.org = (int*) take(n * 4);
+    w.K = (int*) take(n * 4); w.lastslot = (int*) take(n * 4);
+    int *pos = (int*) take(n * 4);
+    DcNode *d_nodes = (DcNode*) take(nodes_total * sizeof(DcNode));
+    int *d_bounds = (int*) take((bounds.size() + 8) * sizeof(int));
+    // node tables: leaves first, then the merge levels from the deepest up
+    std::vector<DcNode> table(leaves);
+    std::vector<size_t> level_off(levels.size());
+    for (int lv = (int) levels.size() - 1; lv >= 0; lv--) {
+        level_off[lv] = table.size();
+        table.insert(table.end(), levels[lv].begin(), levels[lv].end());
+    }
+    void *pin = nullptr;
+    BB_CUDA(cudaStreamSynchronize(st)); // the pinned staging buffer
+    BB_TRY(ctx->pinned(table.size() * sizeof(DcNode) + (bounds.size() + 8) * sizeof(int), &pin));
+    memcpy(pin, table.data(), table.size() * sizeof(DcNode));
+    int *hb = (int*) ((char*) pin + table.size() * sizeof(DcNode));
+    for (size_t q = 0; q < bounds.size(); q++) hb[q] = bounds[q];
+    BB_CUDA(cudaMemcpyAsync(d_nodes, pin, table.size() * sizeof(DcNode), cudaMemcpyHostToDevice, st));
+    if (!bounds.empty()) BB_CUDA(cudaMemcpyAsync(d_bounds, hb, bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+    BB_CUDA(cudaMemsetAsync(ZA, 0, mat * 8, st));
+    dc_adjust_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d, e, d_bounds, (int) bounds.size(), dadj, n);
+    BB_TRY(launched(ctx, "dc_adjust_kernel"));
+    const size_t leaf_smem = ((size_t) DC_LEAF * (DC_LEAF | 1) + 3 * DC_LEAF) * sizeof(double);
+    BB_CUDA(cudaFuncSetAttribute(dc_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) leaf_smem));
+    dc_leaf_kernel<<<(int) leaves.size(), 32, leaf_smem, st>>>(d_nodes, dadj, e, ZA, ld, lamA, d_info);
+    BB_TRY(launched(ctx, "dc_leaf_kernel"));
+    double *Zc = ZA, *Zn = ZB, *lc = lamA, *ln = lamB;
+    for (int lv = (int) levels.size() - 1; lv >= 0; lv--) {
+        const int cnt = (int) levels[lv].size();
+        const DcNode *nodes = d_nodes + level_off[lv];
+        int kmax = 0;
+        for (auto &nd : levels[lv]) kmax = std::max(kmax, nd.k);
+        // rows outside this level's merges (none: every row belongs to exactly one node per level when the tree is
+        // balanced; unbalanced leaves that are already final are copied through)
+        BB_CUDA(cudaMemcpyAsync(Zn, Zc, mat * 8, cudaMemcpyDeviceToDevice, st));
+        BB_CUDA(cudaMemcpyAsync(ln, lc, (size_t) n * 8, cudaMemcpyDeviceToDevice, st));
+        const size_t setup_smem = (size_t) kmax * (7 * sizeof(double) + 2 * sizeof(int));
+        BB_CUDA(cudaFuncSetAttribute(dc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max(setup_smem, (size_t) 1024)));
+        dc_setup_kernel<<<cnt, DC_THREADS, setup_smem, st>>>(nodes, e, Zc, ld, lc, w, ln);
+        BB_TRY(launched(ctx, "dc_setup_kernel"));
+        const int chunks = std::max(1, std::min(512, ceil_div(kmax, DC_THREADS / 32))); // one root (component) per warp
+        dc_secular_kernel<<<dim3(cnt, chunks), DC_THREADS, 2 * (size_t) kmax * 8, st>>>(nodes, w, ln);
+        BB_TRY(launched(ctx, "dc_secular_kernel"));
+        dc_zhat_kernel<<<dim3(cnt, chunks), DC_THREADS, 0, st>>>(nodes, w);
+        BB_TRY(launched(ctx, "dc_zhat_kernel"));
+        dc_vectors_kernel<<<dim3(cnt, chunks), DC_THREADS, 0, st>>>(nodes, w, Ut, ld);
+        BB_TRY(launched(ctx, "dc_vectors_kernel"));
+        dc_gather_kernel<<<dim3(cnt, ceil_div(kmax, DC_THREADS)), DC_THREADS, 0, st>>>(nodes, w, Zc, Qs, Zn, ld);
+        BB_TRY(launched(ctx, "dc_gather_kernel"));
+        dc_gemm_kernel<<<dim3(ceil_div(kmax, 64), ceil_div(kmax, 64), cnt), 256, 0, st>>>(nodes, w.K, Ut, Qs, Zn, ld);
+        BB_TRY(launched(ctx, "dc_gemm_kernel"));
+        std::swap(Zc, Zn);
+        std::swap(lc, ln);
+    }
+    dc_rank_kernel<<<ceil_div(n, DC_THREADS), DC_THREADS, 0, st>>>(lc, n, pos, W);
+    BB_TRY(launched(ctx, "dc_rank_kernel"));
+    dc_permute_kernel<<<dim3(ceil_div(n, DC_THREADS), n), DC_THREADS, 0, st>>>(Zc, pos, n, ld, Zt_out, ldz);
+    return launched(ctx, "dc_permute_kernel");
+}
+
+} // namespace bb
+
+extern "C" {
+
+// the tridiagonal divide & conquer alone, host buffers (unit tests): d[n], e[n-1] -> w[n] ascending, Zt[n*n] row j = eigenvector j
+int bbgpu_stedc_host(bbgpu_ctx *ctx, int n, const double *h_d, const double *h_e, double *h_w, double *h_Zt, float *ms) {
+    BB_ARG(ctx && n >= 1 && h_d && h_w && h_Zt && (n == 1 || h_e));
+    cudaStream_t st = ctx->stream;
+    double *dd = nullptr, *de = nullptr, *dw = nullptr, *dz = nullptr;
+    int *dinfo = nullptr;
+    BB_TRY(bb::dev_alloc(&dd, (size_t) n));
+    BB_TRY(bb::dev_alloc(&de, (size_t) n));
+    BB_TRY(bb::dev_alloc(&dw, (size_t) n));
+    BB_TRY(bb::dev_alloc(&dz, (size_t) n * n));
+    BB_TRY(bb::dev_alloc(&dinfo, (size_t) 1));
+    BB_CUDA(cudaMemcpyAsync(dd, h_d, (size_t) n * 8, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemsetAsync(de, 0, (size_t) n * 8, st));
+    if (n > 1) BB_CUDA(cudaMemcpyAsync(de, h_e, (size_t) (n - 1) * 8, cudaMemcpyHostToDevice, st));
+    BB_TRY(bb::stedc_device(ctx, n, dd, de, dw, dz, n, dinfo)); // warm-up: scratch allocation
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    BB_TRY(bb::stedc_device(ctx, n, dd, de, dw, dz, n, dinfo));
+    cudaEventRecord(e1, st);
+    BB_CUDA(cudaEventSynchronize(e1));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    if (ms) *ms = t;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    int info = 0;
+    BB_CUDA(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaMemcpyAsync(h_w, dw, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaMemcpyAsync(h_Zt, dz, (size_t) n * n * 8, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dd); cudaFree(de); cudaFree(dw); cudaFree(dz); cudaFree(dinfo);
+    if (info != 0) return bb::fail(BBGPU_ERR_SOLVER, "bbgpu_stedc_host: the QL iteration of a leaf did not converge");
+    return BBGPU_OK;
+}
+
+} // extern "C"

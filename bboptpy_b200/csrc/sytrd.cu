@@ -260,6 +260,40 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_coop_kernel(const double 
 
 } // namespace
 
+namespace bb {
+
+// limits of the cooperative kernel on this device: shared memory for the rows of one CTA, columns per thread
+bool sytrd_fits(bbgpu_ctx *ctx, int n) {
+    const int G = ctx->sm_count, nrows = (n + G - 1) / G, np = (n + 63) & ~63;
+    const size_t smem = ((size_t) nrows * np + 3 * (size_t) np + 32 + 8 * (size_t) nrows) * sizeof(double);
+    return n >= 3 && n <= SY_KMAX * SY_THREADS && nrows <= SY_RMAX && smem <= 200 * 1024;
+}
+
+size_t sytrd_workspace_doubles(int n) { return 4 * (size_t) n + 64; } // y (2n), pivot rows (2n), barrier, profile
+
+// device form: A row-major with pitch ldA (lower triangle read) -> d, e, tau (n each) and the reflectors in Vcm (n*n,
+// column-major, LAPACK dsytrd('L') layout); ws = sytrd_workspace_doubles(n).  Enqueued on the ctx stream.
+int sytrd_device(bbgpu_ctx *ctx, int n, const double *d_A, int ldA, double *d_d, double *d_e, double *d_tau, double *d_Vcm,
+        double *ws) {
+    if (!sytrd_fits(ctx, n)) return fail(BBGPU_ERR_ARG, "sytrd_device: n = %d is beyond the cooperative kernel", n);
+    cudaStream_t st = ctx->stream;
+    const int G = ctx->sm_count, nrows = (n + G - 1) / G, np = (n + 63) & ~63;
+    const size_t smem = ((size_t) nrows * np + 3 * (size_t) np + 32 + 8 * (size_t) nrows) * sizeof(double);
+    BB_CUDA(cudaFuncSetAttribute(sytrd_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    double *dy = ws, *dr = ws + 2 * (size_t) n;
+    unsigned *dbar = reinterpret_cast<unsigned*>(ws + 4 * (size_t) n);
+    long long *dprof = nullptr;
+    BB_CUDA(cudaMemsetAsync(dbar, 0, 64, st));
+    int nn = n, ld = ldA;
+    const double *A = d_A;
+    void *args[] = { (void*) &A, (void*) &nn, (void*) &ld, (void*) &d_d, (void*) &d_e, (void*) &d_tau, (void*) &d_Vcm, (void*) &dy,
+            (void*) &dr, (void*) &dbar, (void*) &dprof };
+    BB_CUDA(cudaLaunchCooperativeKernel((const void*) sytrd_coop_kernel, dim3(G), dim3(SY_THREADS), args, smem, st));
+    return launched(ctx, "sytrd_coop_kernel");
+}
+
+} // namespace bb
+
 extern "C" {
 
 // Tridiagonalise one symmetric matrix (host buffers; unit tests and the timing probe).  h_A: n*n row-major, the lower

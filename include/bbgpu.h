@@ -410,6 +410,12 @@ int bbgpu_cmab_adopt_basis(bbgpu_cmab *h, int run, const double *h_B, const doub
  * rows i+2.. of column i.  *ms (may be NULL): best kernel time of `reps` launches. */
 int bbgpu_sytrd_host(bbgpu_ctx *ctx, int n, const double *h_A, double *h_d, double *h_e, double *h_tau,
                      double *h_V, int reps, float *ms);
+/* Divide & conquer eigensolver for ONE symmetric tridiagonal matrix, entirely on the device (leaves by the
+ * one-warp QL solver, merges = deflation scan + secular equation + Loewner vectors + one GEMM): the second
+ * half of the replacement for cuSOLVER's syevd.  Host buffers: d[n], e[n-1] -> w[n] ascending, Zt[n*n]
+ * with ROW j = eigenvector of w[j].  *ms (may be NULL): device time of one decomposition. */
+int bbgpu_stedc_host(bbgpu_ctx *ctx, int n, const double *h_d, const double *h_e, double *h_w,
+                     double *h_Zt, float *ms);
 /* the in-CTA solver alone (unit tests): `count` symmetric n x n matrices (lower triangles read) ->
  * B (B[i*n+j] = component i of eigenvector j), eigenvalues ascending, info = QL iterations or -1 */
 int bbgpu_eig_small_host(bbgpu_ctx *ctx, int n, int count, const double *h_A, double *h_B,

@@ -142,5 +142,6 @@ int bbgpu_cmab_set_sigma(bbgpu_cmab *, int, double) { return 0; }
 int bbgpu_cmab_get_population(bbgpu_cmab *, int, double *, double *, int32_t *) { return 0; }
 int bbgpu_cmab_adopt_basis(bbgpu_cmab *, int, const double *, const double *) { return 0; }
 int bbgpu_eig_small_host(bbgpu_ctx *, int, int, const double *, double *, double *, int32_t *) { return 0; }
+int bbgpu_stedc_host(bbgpu_ctx *, int, const double *, const double *, double *, double *, float *) { return 0; }
 int bbgpu_sytrd_host(bbgpu_ctx *, int, const double *, double *, double *, double *, double *, int, float *) { return 0; }
 }
