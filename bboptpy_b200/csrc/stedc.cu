@@ -4,7 +4,7 @@
 // tridiagonal solver.  Reference being replaced: the QL iteration of cma/cmaes.cpp:383-478 (any correct eigenbasis serves:
 // DESIGN.md "The eigendecomposition at n = 1000").
 //
-// T is torn into leaves of <= 64 rows (boundaries at multiples of 8), solved by the one-warp QL solver of eig_small.cuh;
+// T is torn into leaves of <= 32 rows (boundaries at multiples of 8), solved by the one-warp QL solver of eig_small.cuh;
 // every merge of two solved halves  diag(D1, D2) + rho z z^T  runs as a handful of launches over ALL merges of its level:
 //   setup    z from the touching rows of the children's eigenvectors, merge-sort of D by counting ranks, the sequential
 //            deflation scan (tiny z_j; close D with a Givens rotation) -> per position an action code and slot
@@ -22,10 +22,14 @@
 #include <vector>
 
 #include "eig_small.cuh"
+#include "gemm_tma.cuh" // the engine's TMA-fed DMMA GEMM for the merges
 
 namespace {
 
-constexpr int DC_LEAF = 64;
+#ifndef DC_LEAF_ROWS
+#define DC_LEAF_ROWS 32 // measured at n = 1000: 32-row leaves 1.93 ms, 64-row leaves 2.12 ms (the QL chain of a leaf is the longer pole)
+#endif
+constexpr int DC_LEAF = DC_LEAF_ROWS;
 constexpr int DC_THREADS = 256;
 
 struct DcNode { int o, k, m; }; // rows [o, o+k), children [o, o+m) and [o+m, o+k)
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *node
     const DcNode nd = nodes[blockIdx.x];
     const int k = nd.k, o = nd.o, m = nd.m, tid = threadIdx.x;
     __shared__ double red[32];
-    __shared__ double s_tol, s_rho;
+    __shared__ double s_tol;
     const double beta = e[o + m - 1];
     const double sgn = beta < 0 ? -1.0 : 1.0;
     // z = (last row of Q1, sign * first row of Q2); the rows of Zt are eigenvectors, so these are columns o+m-1 and o+m
@@ -117,7 +121,6 @@ __global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *node
     zmax = bb::block_max(zmax, red);
     if (tid == 0) {
         s_tol = 8.0 * 2.220446049250313e-16 * fmax(dmax, zmax);
-        s_rho = rho;
         w.rho[blockIdx.x] = rho;
     }
     __syncthreads();
@@ -351,6 +354,14 @@ __global__ void __launch_bounds__(256) dc_gemm_kernel(const DcNode *nodes, const
         }
 }
 
+// rows < K (device-side) of a node's product block into the new basis
+__global__ void __launch_bounds__(DC_THREADS) dc_copyrows_kernel(const DcNode *nodes, const int *Kdev, const double *T, double *Zt_new, int ld) {
+    const DcNode nd = nodes[blockIdx.z];
+    const int i = blockIdx.y, r = blockIdx.x * DC_THREADS + threadIdx.x;
+    if (i >= Kdev[blockIdx.z] || r >= nd.k) return;
+    Zt_new[(size_t) (nd.o + i) * ld + nd.o + r] = T[(size_t) (nd.o + i) * ld + nd.o + r];
+}
+
 // ---- final: ascending order ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DC_THREADS) dc_rank_kernel(const double *lam, int n, int *pos, double *W) {
     const int j = blockIdx.x * DC_THREADS + threadIdx.x;
@@ -406,13 +417,14 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
     size_t nodes_total = leaves.size();
     for (auto &lv : levels) nodes_total += lv.size();
     const size_t mat = (size_t) n * ld;
-    const size_t bytes = (4 * mat + 12 * (size_t) n + 64) * sizeof(double) + (6 * (size_t) n + 64) * sizeof(int) +
+    const size_t bytes = (5 * mat + 12 * (size_t) n + 64) * sizeof(double) + (6 * (size_t) n + 64) * sizeof(int) +
             nodes_total * sizeof(DcNode) + (bounds.size() + 8) * sizeof(int) + 4096;
     void *sp = nullptr;
     BB_TRY(ctx->scratch(bytes, &sp));
     char *base = (char*) sp;
     auto take = [&](size_t b) { char *p = base; base += (b + 255) & ~(size_t) 255; return p; };
-    double *ZA = (double*) take(mat * 8), *ZB = (double*) take(mat * 8), *Qs = (double*) take(mat * 8), *Ut = (double*) take(mat * 8);
+    double *ZA = (double*) take(mat * 8), *ZB = (double*) take(mat * 8), *Qs = (double*) take(mat * 8), *Ut = (double*) take(mat * 8),
+            *Tb = (double*) take(mat * 8);
     DcWork w;
     w.Ds = (double*) take(n * 8); w.zs = (double*) take(n * 8); w.dk = (double*) take(n * 8); w.zk = (double*) take(n * 8);
     w.mu = (double*) take(n * 8); w.zhat = (double*) take(n * 8); w.rc = (double*) take(n * 8); w.rs = (double*) take(n * 8);
@@ -447,6 +459,7 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
     dc_leaf_kernel<<<(int) leaves.size(), 32, leaf_smem, st>>>(d_nodes, dadj, e, ZA, ld, lamA, d_info);
     BB_TRY(launched(ctx, "dc_leaf_kernel"));
     double *Zc = ZA, *Zn = ZB, *lc = lamA, *ln = lamB;
+    static const bool use_dmma = [] { const char *ev = getenv("BBGPU_DC_GEMM"); return !(ev && ev[0] == 'f'); }(); // f: plain FMA kernel
     for (int lv = (int) levels.size() - 1; lv >= 0; lv--) {
         const int cnt = (int) levels[lv].size();
         const DcNode *nodes = d_nodes + level_off[lv];
@@ -455,6 +468,10 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
         // rows outside this level's merges (none: every row belongs to exactly one node per level when the tree is
         // balanced; unbalanced leaves that are already final are copied through)
         BB_CUDA(cudaMemcpyAsync(Zn, Zc, mat * 8, cudaMemcpyDeviceToDevice, st));
+        if (kmax >= 256 && use_dmma) {
+            BB_CUDA(cudaMemsetAsync(Ut, 0, mat * 8, st));
+            BB_CUDA(cudaMemsetAsync(Qs, 0, mat * 8, st));
+        }
         BB_CUDA(cudaMemcpyAsync(ln, lc, (size_t) n * 8, cudaMemcpyDeviceToDevice, st));
         const size_t setup_smem = (size_t) kmax * (7 * sizeof(double) + 2 * sizeof(int));
         BB_CUDA(cudaFuncSetAttribute(dc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max(setup_smem, (size_t) 1024)));
@@ -469,8 +486,21 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
         BB_TRY(launched(ctx, "dc_vectors_kernel"));
         dc_gather_kernel<<<dim3(cnt, ceil_div(kmax, DC_THREADS)), DC_THREADS, 0, st>>>(nodes, w, Zc, Qs, Zn, ld);
         BB_TRY(launched(ctx, "dc_gather_kernel"));
-        dc_gemm_kernel<<<dim3(ceil_div(kmax, 64), ceil_div(kmax, 64), cnt), 256, 0, st>>>(nodes, w.K, Ut, Qs, Zn, ld);
-        BB_TRY(launched(ctx, "dc_gemm_kernel"));
+        if (kmax >= 256 && use_dmma) {
+            // the engine's DMMA GEMM wants its sizes on the host: run it over the whole k x k x k block of each merge (the
+            // operands are zero beyond the K live rows / columns) and keep the first K rows of the product
+            for (const DcNode &nd : levels[lv]) {
+                const size_t off = (size_t) nd.o * ld + nd.o;
+                GemmArgs g {};
+                g.A = Ut + off; g.lda = ld; g.B = Qs + off; g.ldb = ld; g.M = nd.k; g.N = nd.k; g.K = nd.k; g.C = Tb + off; g.ldc = ld;
+                BB_TRY((launch_gemm<1, EPI_STORE>(ctx, g)));
+            }
+            dc_copyrows_kernel<<<dim3(ceil_div(kmax, DC_THREADS), kmax, cnt), DC_THREADS, 0, st>>>(nodes, w.K, Tb, Zn, ld);
+            BB_TRY(launched(ctx, "dc_copyrows_kernel"));
+        } else {
+            dc_gemm_kernel<<<dim3(ceil_div(kmax, 64), ceil_div(kmax, 64), cnt), 256, 0, st>>>(nodes, w.K, Ut, Qs, Zn, ld);
+            BB_TRY(launched(ctx, "dc_gemm_kernel"));
+        }
         std::swap(Zc, Zn);
         std::swap(lc, ln);
     }
