@@ -186,6 +186,22 @@ __device__ __forceinline__ double dc_secular_f(const double *delta_src, const do
     return 1.0 + rho * bb::warp_sum(s);
 }
 
+// f and f' = rho sum z_j^2 / (d_j - lambda)^2 in one pass (one division per term)
+__device__ __forceinline__ double dc_secular_fd(const double *delta_src, const double *z2, int K, double dorg, double rho, double mu, int lane,
+        double &fprime) {
+    double s = 0.0, s2 = 0.0;
+    for (int j = lane; j < K; j += 32) {
+        const double r = 1.0 / ((delta_src[j] - dorg) - mu);
+        const double t = z2[j] * r;
+        s += t;
+        s2 = fma(t, r, s2);
+    }
+    s = bb::warp_sum(s);
+    s2 = bb::warp_sum(s2);
+    fprime = rho * s2;
+    return 1.0 + rho * s;
+}
+
 __global__ void __launch_bounds__(DC_THREADS) dc_secular_kernel(const DcNode *nodes, DcWork w, double *lam_new) {
     extern __shared__ __align__(16) double sm[];
     const DcNode nd = nodes[blockIdx.x];
@@ -220,14 +236,38 @@ __global__ void __launch_bounds__(DC_THREADS) dc_secular_kernel(const DcNode *no
             hi = rho * zsum; // the last root lies in (d_K-1, d_K-1 + rho sum z^2]
         }
         const double dorg = dk[org];
-        for (int it = 0; it < 400; it++) { // f increases with mu: f(lo) < 0 <= f(hi); the zero end of the bracket is a pole
+        // f increases with mu: f(lo) < 0 <= f(hi); the zero end of the bracket is a pole.  First shrink the bracket until
+        // both ends have the pole's sign of mu and are within a factor 16 (geometric steps), then safeguarded Newton: a
+        // step that leaves the bracket, or three steps without halving it, is replaced by a bisection.
+        double mu = 0.0;
+        bool have = false;
+        for (int it = 0; it < 400; it++) {
             double mid;
-            if (left) mid = lo > 0.0 ? (hi / lo < 16.0 ? 0.5 * (lo + hi) : sqrt(lo * hi)) : hi * 0.0009765625;
-            else mid = hi < 0.0 ? (lo / hi < 16.0 ? 0.5 * (lo + hi) : -sqrt(lo * hi)) : lo * 0.0009765625;
+            const bool tight = left ? (lo > 0.0 && hi / lo < 16.0) : (hi < 0.0 && lo / hi < 16.0);
+            if (tight) break;
+            if (left) mid = lo > 0.0 ? sqrt(lo * hi) : hi * 0.0009765625;
+            else mid = hi < 0.0 ? -sqrt(lo * hi) : lo * 0.0009765625;
             if (!(mid > lo && mid < hi)) break;
             if (dc_secular_f(dk, z2, K, dorg, rho, mid, lane) >= 0.0) hi = mid; else lo = mid;
         }
-        const double mu = 0.5 * (lo + hi);
+        mu = 0.5 * (lo + hi);
+        double width = hi - lo;
+        int slow = 0;
+        for (int it = 0; it < 200; it++) {
+            if (!(mu > lo && mu < hi)) { mu = 0.5 * (lo + hi); if (!(mu > lo && mu < hi)) break; }
+            double fp;
+            const double f = dc_secular_fd(dk, z2, K, dorg, rho, mu, lane, fp);
+            if (f >= 0.0) hi = mu; else lo = mu;
+            if (f == 0.0) { have = true; break; }
+            double next = mu - f / fp;
+            const double nw = hi - lo;
+            slow = (nw > 0.5 * width) ? slow + 1 : 0;
+            if (!(next > lo && next < hi) || slow >= 3) { next = 0.5 * (lo + hi); slow = 0; }
+            width = nw;
+            if (next == mu || fabs(next - mu) <= 2.220446049250313e-16 * fabs(mu)) { mu = next; have = true; break; }
+            mu = next;
+        }
+        (void) have;
         if (lane == 0) {
             w.org[o + i] = org;
             w.mu[o + i] = mu;
@@ -274,28 +314,48 @@ __global__ void __launch_bounds__(DC_THREADS) dc_vectors_kernel(const DcNode *no
     }
 }
 
-// ---- merge: permutation + Givens chain over the children's basis, one thread per row ----------------------------------
+// ---- merge: permutation + Givens chains over the children's basis.  One thread per (row, segment of 64 sorted positions):
+// the only state that crosses a segment boundary is the "carry" (the last pole that is neither deflated nor emitted yet),
+// and it is recomputed at the segment start by walking back over the rotations that produced it (usually none).
+constexpr int DC_SEG = 64;
+
 __global__ void __launch_bounds__(DC_THREADS) dc_gather_kernel(const DcNode *nodes, DcWork w, const double *Zt, double *QselT,
         double *Zt_new, int ld) {
     const DcNode nd = nodes[blockIdx.x];
     const int o = nd.o, k = nd.k, K = w.K[blockIdx.x];
     const int r = blockIdx.y * DC_THREADS + threadIdx.x;
-    if (r >= k) return;
+    const int j0 = blockIdx.z * DC_SEG, j1 = min(k, j0 + DC_SEG);
+    if (r >= k || j0 >= k) return;
+    const int *act = w.act + o, *slot = w.slot + o, *perm = w.perm + o;
+    auto col = [&](int j) { return Zt[(size_t) (o + perm[j]) * ld + o + r]; };
     double carry = 0.0;
-    for (int j0 = 0; j0 < k; j0 += 8) { // the loads of 8 positions are issued together: the walk is latency-bound otherwise
+    {
+        int p = j0 - 1;
+        while (p >= 0 && act[p] == 0) p--; // the pole the carry belongs to
+        if (p >= 0) {
+            int q = p;
+            while (q >= 0 && (act[q] == 2 || act[q] == 0)) q--; // the plain column the chain of rotations started from
+            if (q >= 0) {
+                carry = col(q);
+                for (int t = q + 1; t <= p; t++)
+                    if (act[t] == 2) carry = w.rc[o + t] * col(t) - w.rs[o + t] * carry;
+            }
+        }
+    }
+    for (int jb = j0; jb < j1; jb += 8) { // the loads of 8 positions are issued together: the walk is latency-bound otherwise
         double y[8];
         int a[8], sl[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const int j = min(j0 + u, k - 1);
-            y[u] = Zt[(size_t) (o + w.perm[o + j]) * ld + o + r];
-            a[u] = w.act[o + j];
-            sl[u] = w.slot[o + j];
+            const int j = min(jb + u, k - 1);
+            y[u] = col(j);
+            a[u] = act[j];
+            sl[u] = slot[j];
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const int j = j0 + u;
-            if (j >= k) break;
+            const int j = jb + u;
+            if (j >= j1) break;
             if (a[u] == 0) Zt_new[(size_t) (o + K + sl[u]) * ld + o + r] = y[u];
             else if (a[u] == 1) carry = y[u];
             else if (a[u] == 2) {
@@ -309,7 +369,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_gather_kernel(const DcNode *nod
         }
     }
     const int last = w.lastslot[blockIdx.x];
-    if (last >= 0) QselT[(size_t) (o + last) * ld + o + r] = carry;
+    if (j1 == k && last >= 0) QselT[(size_t) (o + last) * ld + o + r] = carry;
 }
 
 // ---- merge: Zt_new[o+i][o+r] = sum_j Ut[o+i][o+j] QselT[o+j][o+r], i, j < K (device-side), r < k -----------------------
@@ -484,7 +544,7 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
         BB_TRY(launched(ctx, "dc_zhat_kernel"));
         dc_vectors_kernel<<<dim3(cnt, chunks), DC_THREADS, 0, st>>>(nodes, w, Ut, ld);
         BB_TRY(launched(ctx, "dc_vectors_kernel"));
-        dc_gather_kernel<<<dim3(cnt, ceil_div(kmax, DC_THREADS)), DC_THREADS, 0, st>>>(nodes, w, Zc, Qs, Zn, ld);
+        dc_gather_kernel<<<dim3(cnt, ceil_div(kmax, DC_THREADS), ceil_div(kmax, DC_SEG)), DC_THREADS, 0, st>>>(nodes, w, Zc, Qs, Zn, ld);
         BB_TRY(launched(ctx, "dc_gather_kernel"));
         if (kmax >= 256 && use_dmma) {
             // the engine's DMMA GEMM wants its sizes on the host: run it over the whole k x k x k block of each merge (the
