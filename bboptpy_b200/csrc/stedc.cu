@@ -128,21 +128,45 @@ __global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *node
     // poles in SHARED memory (a walk over global memory cost ~2 us per pole and was most of the solver's time).
     extern __shared__ __align__(16) double ssm[];
     double *D = ssm, *z = D + k, *src = z + k, *srs = src + k, *sdk = srs + k, *szk = sdk + k, *sdd = szk + k;
-    int *sact = reinterpret_cast<int*>(sdd + k), *sslot = sact + k;
+    int *sact = reinterpret_cast<int*>(sdd + k), *sslot = sact + k, *spec = sslot + k;
     for (int j = tid; j < k; j += DC_THREADS) { D[j] = w.Ds[o + j]; z[j] = w.zs[o + j]; src[j] = 0.0; srs[j] = 0.0; }
+    __syncthreads();
+    // Speculation, in parallel: the outcome of every pole's tests on the UNMODIFIED data (0 tiny, 1 stays, 2 would rotate
+    // with its predecessor).  The sequential walk below only recomputes a test when the previous step really rotated.
+    for (int j = tid; j < k; j += DC_THREADS) {
+        int sp = 0;
+        if (!(rho * fabs(z[j]) <= s_tol)) {
+            int p = j - 1;
+            while (p >= 0 && rho * fabs(z[p]) <= s_tol) p--;
+            sp = 1;
+            if (p >= 0) {
+                const double zp = z[p], zj = z[j], t = D[j] - D[p];
+                if (fabs(t * zj * zp) <= s_tol * (zj * zj + zp * zp)) sp = 2;
+            }
+        }
+        spec[j] = sp;
+    }
     __syncthreads();
     if (tid == 0) {
         const double tol = s_tol;
         int K = 0, nd_ = 0, pj = -1;
+        bool dirty = false; // the predecessor pole was changed by a rotation: its speculated test is void
         if (rho * zmax <= tol) {
             for (int j = 0; j < k; j++) { sact[j] = 0; sslot[j] = nd_; sdd[nd_] = D[j]; nd_++; }
         } else {
             for (int j = 0; j < k; j++) {
-                if (rho * fabs(z[j]) <= tol) { // the component does not feel the rank-one term
+                const int sp = spec[j];
+                if (sp == 0) { // the component does not feel the rank-one term
                     sact[j] = 0; sslot[j] = nd_; sdd[nd_] = D[j]; nd_++;
                     continue;
                 }
                 if (pj < 0) { sact[j] = 1; sslot[j] = 0; pj = j; continue; }
+                if (sp == 1 && !dirty) { // speculated on the very data the sequential walk would see: the older pole stays
+                    sact[j] = 3; sslot[j] = K;
+                    sdk[K] = D[pj]; szk[K] = z[pj]; K++;
+                    pj = j;
+                    continue;
+                }
                 // dlaed2's test |t c s| <= tol with c = z_j / tau, s = -z_pj / tau, tau^2 = z_j^2 + z_pj^2, without forming them
                 // (the scan is one thread's dependency chain: no square root, no division unless a pole really deflates)
                 const double zp = z[pj], zj = z[j], t = D[j] - D[pj];
@@ -156,9 +180,11 @@ __global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *node
                     D[pj] = tt;
                     sact[j] = 2; sslot[j] = nd_; src[j] = c; srs[j] = s;
                     sdd[nd_] = tt; nd_++;
+                    dirty = true;
                 } else { // the older pole stays in the secular problem
                     sact[j] = 3; sslot[j] = K;
                     sdk[K] = D[pj]; szk[K] = z[pj]; K++;
+                    dirty = false;
                 }
                 pj = j;
             }
@@ -533,7 +559,7 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
             BB_CUDA(cudaMemsetAsync(Qs, 0, mat * 8, st));
         }
         BB_CUDA(cudaMemcpyAsync(ln, lc, (size_t) n * 8, cudaMemcpyDeviceToDevice, st));
-        const size_t setup_smem = (size_t) kmax * (7 * sizeof(double) + 2 * sizeof(int));
+        const size_t setup_smem = (size_t) kmax * (7 * sizeof(double) + 3 * sizeof(int));
         BB_CUDA(cudaFuncSetAttribute(dc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max(setup_smem, (size_t) 1024)));
         dc_setup_kernel<<<cnt, DC_THREADS, setup_smem, st>>>(nodes, e, Zc, ld, lc, w, ln);
         BB_TRY(launched(ctx, "dc_setup_kernel"));
