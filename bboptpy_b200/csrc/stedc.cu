@@ -105,11 +105,14 @@ __global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *node
     const double zn = sqrt(ss), rho = fabs(beta) * ss;
     __syncthreads();
     double zmax = 0.0;
-    for (int j = tid; j < k; j += DC_THREADS) { // merge the two ascending halves: rank by counting
-        const double dj = lam[o + j];
+    extern __shared__ __align__(16) double ssm[];
+    for (int j = tid; j < k; j += DC_THREADS) ssm[j] = lam[o + j];
+    __syncthreads();
+    for (int j = tid; j < k; j += DC_THREADS) { // rank by counting (the halves hold roots, then deflated values: not sorted)
+        const double dj = ssm[j];
         int pos = 0;
         for (int q = 0; q < k; q++) {
-            const double dq = lam[o + q];
+            const double dq = ssm[q]; // one address per warp: a broadcast
             pos += (dq < dj) || (dq == dj && q < j);
         }
         const double z = w.zk[o + j] / zn;
@@ -124,9 +127,8 @@ __global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *node
         w.rho[blockIdx.x] = rho;
     }
     __syncthreads();
-    // The deflation scan is sequential (dlaed2: every decision changes the next comparison): thread 0 walks the sorted
-    // poles in SHARED memory (a walk over global memory cost ~2 us per pole and was most of the solver's time).
-    extern __shared__ __align__(16) double ssm[];
+    // The deflation scan is sequential in principle (dlaed2: every decision changes the next comparison); it runs over
+    // SHARED memory (a walk over global memory cost ~2 us per pole and was most of the solver's time).
     double *D = ssm, *z = D + k, *src = z + k, *srs = src + k, *sdk = srs + k, *szk = sdk + k, *sdd = szk + k;
     int *sact = reinterpret_cast<int*>(sdd + k), *sslot = sact + k, *spec = sslot + k;
     for (int j = tid; j < k; j += DC_THREADS) { D[j] = w.Ds[o + j]; z[j] = w.zs[o + j]; src[j] = 0.0; srs[j] = 0.0; }
@@ -147,51 +149,83 @@ __global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *node
         spec[j] = sp;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) { // warp 0 walks the poles 32 at a time; only a chunk that holds a rotation is walked by one lane
         const double tol = s_tol;
-        int K = 0, nd_ = 0, pj = -1;
-        bool dirty = false; // the predecessor pole was changed by a rotation: its speculated test is void
-        if (rho * zmax <= tol) {
-            for (int j = 0; j < k; j++) { sact[j] = 0; sslot[j] = nd_; sdd[nd_] = D[j]; nd_++; }
-        } else {
-            for (int j = 0; j < k; j++) {
-                const int sp = spec[j];
+        const int lane = tid;
+        const unsigned below = (1u << lane) - 1u;
+        int K = 0, nd_ = 0, pj = -1; // warp-uniform
+        int dirty = 0; // the predecessor pole was changed by a rotation: its speculated test is void
+        const bool alltiny = rho * zmax <= tol;
+        for (int base = 0; base < k; base += 32) {
+            const int j = base + lane;
+            const bool valid = j < k;
+            const int sp = valid ? (alltiny ? 0 : spec[j]) : -1;
+            const unsigned rot = __ballot_sync(0xffffffffu, sp == 2);
+            if (rot == 0u && !dirty) {
+                // no decision in this chunk depends on another one: every pole finds its slot from two prefix counts
+                const unsigned nt = __ballot_sync(0xffffffffu, sp > 0), tn = __ballot_sync(0xffffffffu, sp == 0);
                 if (sp == 0) { // the component does not feel the rank-one term
-                    sact[j] = 0; sslot[j] = nd_; sdd[nd_] = D[j]; nd_++;
-                    continue;
+                    const int r = nd_ + __popc(tn & below);
+                    sact[j] = 0; sslot[j] = r; sdd[r] = D[j];
+                } else if (sp > 0) {
+                    const unsigned prev = nt & below;
+                    const int pred = prev ? base + 31 - __clz(prev) : pj;
+                    if (pred < 0) { sact[j] = 1; sslot[j] = 0; }
+                    else { // the older pole stays in the secular problem
+                        const int slot = K + __popc(prev) - (pj < 0 ? 1 : 0);
+                        sact[j] = 3; sslot[j] = slot;
+                        sdk[slot] = D[pred]; szk[slot] = z[pred];
+                    }
                 }
-                if (pj < 0) { sact[j] = 1; sslot[j] = 0; pj = j; continue; }
-                if (sp == 1 && !dirty) { // speculated on the very data the sequential walk would see: the older pole stays
-                    sact[j] = 3; sslot[j] = K;
-                    sdk[K] = D[pj]; szk[K] = z[pj]; K++;
-                    pj = j;
-                    continue;
+                if (nt) { K += __popc(nt) - (pj < 0 ? 1 : 0); pj = base + 31 - __clz(nt); }
+                nd_ += __popc(tn);
+            } else {
+                if (lane == 0) {
+                    const int jend = min(base + 32, k);
+                    for (int q = base; q < jend; q++) {
+                        const int sq = spec[q];
+                        if (sq == 0) { sact[q] = 0; sslot[q] = nd_; sdd[nd_] = D[q]; nd_++; continue; }
+                        if (pj < 0) { sact[q] = 1; sslot[q] = 0; pj = q; continue; }
+                        if (sq == 1 && !dirty) { // speculated on the very data the walk sees
+                            sact[q] = 3; sslot[q] = K;
+                            sdk[K] = D[pj]; szk[K] = z[pj]; K++;
+                            pj = q;
+                            continue;
+                        }
+                        // dlaed2's test |t c s| <= tol with c = z_q / tau, s = -z_pj / tau, tau^2 = z_q^2 + z_pj^2, without
+                        // forming them (no square root, no division unless a pole really deflates)
+                        const double zp = z[pj], zj = z[q], t = D[q] - D[pj];
+                        if (fabs(t * zj * zp) <= tol * (zj * zj + zp * zp)) { // two close poles: rotate the older one out
+                            const double tau = sqrt(zj * zj + zp * zp);
+                            const double c = zj / tau, sn = -zp / tau;
+                            z[q] = tau;
+                            z[pj] = 0.0;
+                            const double tt = D[pj] * c * c + D[q] * sn * sn;
+                            D[q] = D[pj] * sn * sn + D[q] * c * c;
+                            D[pj] = tt;
+                            sact[q] = 2; sslot[q] = nd_; src[q] = c; srs[q] = sn;
+                            sdd[nd_] = tt; nd_++;
+                            dirty = 1;
+                        } else {
+                            sact[q] = 3; sslot[q] = K;
+                            sdk[K] = D[pj]; szk[K] = z[pj]; K++;
+                            dirty = 0;
+                        }
+                        pj = q;
+                    }
                 }
-                // dlaed2's test |t c s| <= tol with c = z_j / tau, s = -z_pj / tau, tau^2 = z_j^2 + z_pj^2, without forming them
-                // (the scan is one thread's dependency chain: no square root, no division unless a pole really deflates)
-                const double zp = z[pj], zj = z[j], t = D[j] - D[pj];
-                if (fabs(t * zj * zp) <= tol * (zj * zj + zp * zp)) { // two close poles: rotate the older one out
-                    const double tau = sqrt(zj * zj + zp * zp);
-                    const double c = zj / tau, s = -zp / tau;
-                    z[j] = tau;
-                    z[pj] = 0.0;
-                    const double tt = D[pj] * c * c + D[j] * s * s;
-                    D[j] = D[pj] * s * s + D[j] * c * c;
-                    D[pj] = tt;
-                    sact[j] = 2; sslot[j] = nd_; src[j] = c; srs[j] = s;
-                    sdd[nd_] = tt; nd_++;
-                    dirty = true;
-                } else { // the older pole stays in the secular problem
-                    sact[j] = 3; sslot[j] = K;
-                    sdk[K] = D[pj]; szk[K] = z[pj]; K++;
-                    dirty = false;
-                }
-                pj = j;
+                K = __shfl_sync(0xffffffffu, K, 0);
+                nd_ = __shfl_sync(0xffffffffu, nd_, 0);
+                pj = __shfl_sync(0xffffffffu, pj, 0);
+                dirty = __shfl_sync(0xffffffffu, dirty, 0);
             }
-            if (pj >= 0) { w.lastslot[blockIdx.x] = K; sdk[K] = D[pj]; szk[K] = z[pj]; K++; }
+            __syncwarp();
         }
-        if (pj < 0) w.lastslot[blockIdx.x] = -1;
-        w.K[blockIdx.x] = K;
+        if (lane == 0) {
+            if (pj >= 0) { w.lastslot[blockIdx.x] = K; sdk[K] = D[pj]; szk[K] = z[pj]; K++; }
+            else w.lastslot[blockIdx.x] = -1;
+            w.K[blockIdx.x] = K;
+        }
     }
     __syncthreads();
     const int K = w.K[blockIdx.x];
@@ -205,100 +239,110 @@ __global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *node
     }
 }
 
-// ---- merge: secular equation, one warp per root ----------------------------------------------------------------------
-__device__ __forceinline__ double dc_secular_f(const double *delta_src, const double *z2, int K, double dorg, double rho, double mu, int lane) {
-    double s = 0.0;
-    for (int j = lane; j < K; j += 32) s += z2[j] / ((delta_src[j] - dorg) - mu);
-    return 1.0 + rho * bb::warp_sum(s);
+// ---- merge: secular equation, one 128-thread CTA per root --------------------------------------------------------------
+// (fp64 divisions are long dependency chains on this part: a warp per root left the chip at 9 % occupancy and 18 k cycles
+// per evaluation; four warps per root and one root per CTA put ~6 warps on every scheduler.)
+constexpr int DC_SEC_THREADS = 128;
+
+__device__ __forceinline__ double dc_block_sum128(double v, double *red) { // all threads get the same bits
+    v = bb::warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return (red[0] + red[1]) + (red[2] + red[3]);
 }
 
 // f and f' = rho sum z_j^2 / (d_j - lambda)^2 in one pass (one division per term)
-__device__ __forceinline__ double dc_secular_fd(const double *delta_src, const double *z2, int K, double dorg, double rho, double mu, int lane,
-        double &fprime) {
-    double s = 0.0, s2 = 0.0;
-    for (int j = lane; j < K; j += 32) {
-        const double r = 1.0 / ((delta_src[j] - dorg) - mu);
+__device__ __forceinline__ double dc_secular_fd(const double *dk, const double *z2, int K, double dorg, double rho, double mu,
+        double *red, double &fprime) {
+    double s = 0.0, s2 = 0.0, sb = 0.0, s2b = 0.0;
+    int j = threadIdx.x;
+    for (; j + DC_SEC_THREADS < K; j += 2 * DC_SEC_THREADS) { // two reciprocals in flight
+        const double r = 1.0 / ((dk[j] - dorg) - mu), rb = 1.0 / ((dk[j + DC_SEC_THREADS] - dorg) - mu);
+        const double t = z2[j] * r, tb = z2[j + DC_SEC_THREADS] * rb;
+        s += t;
+        sb += tb;
+        s2 = fma(t, r, s2);
+        s2b = fma(tb, rb, s2b);
+    }
+    for (; j < K; j += DC_SEC_THREADS) {
+        const double r = 1.0 / ((dk[j] - dorg) - mu);
         const double t = z2[j] * r;
         s += t;
         s2 = fma(t, r, s2);
     }
-    s = bb::warp_sum(s);
-    s2 = bb::warp_sum(s2);
+    s = dc_block_sum128(s + sb, red);
+    s2 = dc_block_sum128(s2 + s2b, red + 4);
     fprime = rho * s2;
     return 1.0 + rho * s;
 }
 
-__global__ void __launch_bounds__(DC_THREADS) dc_secular_kernel(const DcNode *nodes, DcWork w, double *lam_new) {
+__global__ void __launch_bounds__(DC_SEC_THREADS) dc_secular_kernel(const DcNode *nodes, DcWork w, double *lam_new) {
     extern __shared__ __align__(16) double sm[];
+    __shared__ double red[8];
     const DcNode nd = nodes[blockIdx.x];
-    const int o = nd.o, K = w.K[blockIdx.x], tid = threadIdx.x, lane = tid & 31;
-    if (K == 0) return;
+    const int o = nd.o, K = w.K[blockIdx.x], tid = threadIdx.x, i = blockIdx.y;
+    if (i >= K) return;
     double *dk = sm, *z2 = sm + K;
-    double zsum = 0.0;
-    for (int j = tid; j < K; j += DC_THREADS) {
+    for (int j = tid; j < K; j += DC_SEC_THREADS) {
         const double z = w.zk[o + j];
         dk[j] = w.dk[o + j];
         z2[j] = z * z;
     }
     __syncthreads();
     const double rho = w.rho[blockIdx.x];
-    const int warps = (DC_THREADS / 32) * gridDim.y, wg = blockIdx.y * (DC_THREADS / 32) + (tid >> 5);
-    for (int i = wg; i < K; i += warps) {
-        int org;
-        double lo, hi;
-        bool left;
-        if (i < K - 1) {
-            const double gap = dk[i + 1] - dk[i];
-            left = dc_secular_f(dk, z2, K, dk[i], rho, 0.5 * gap, lane) >= 0.0;
-            org = left ? i : i + 1;
-            lo = left ? 0.0 : -0.5 * gap;
-            hi = left ? 0.5 * gap : 0.0;
-        } else {
-            for (int j = lane; j < K; j += 32) zsum += z2[j];
-            zsum = bb::warp_sum(zsum);
-            left = true;
-            org = i;
-            lo = 0.0;
-            hi = rho * zsum; // the last root lies in (d_K-1, d_K-1 + rho sum z^2]
-        }
-        const double dorg = dk[org];
-        // f increases with mu: f(lo) < 0 <= f(hi); the zero end of the bracket is a pole.  First shrink the bracket until
-        // both ends have the pole's sign of mu and are within a factor 16 (geometric steps), then safeguarded Newton: a
-        // step that leaves the bracket, or three steps without halving it, is replaced by a bisection.
-        double mu = 0.0;
-        bool have = false;
-        for (int it = 0; it < 400; it++) {
-            double mid;
-            const bool tight = left ? (lo > 0.0 && hi / lo < 16.0) : (hi < 0.0 && lo / hi < 16.0);
-            if (tight) break;
-            if (left) mid = lo > 0.0 ? sqrt(lo * hi) : hi * 0.0009765625;
-            else mid = hi < 0.0 ? -sqrt(lo * hi) : lo * 0.0009765625;
-            if (!(mid > lo && mid < hi)) break;
-            if (dc_secular_f(dk, z2, K, dorg, rho, mid, lane) >= 0.0) hi = mid; else lo = mid;
-        }
-        mu = 0.5 * (lo + hi);
-        double width = hi - lo;
-        int slow = 0;
-        for (int it = 0; it < 200; it++) {
-            if (!(mu > lo && mu < hi)) { mu = 0.5 * (lo + hi); if (!(mu > lo && mu < hi)) break; }
-            double fp;
-            const double f = dc_secular_fd(dk, z2, K, dorg, rho, mu, lane, fp);
-            if (f >= 0.0) hi = mu; else lo = mu;
-            if (f == 0.0) { have = true; break; }
-            double next = mu - f / fp;
-            const double nw = hi - lo;
-            slow = (nw > 0.5 * width) ? slow + 1 : 0;
-            if (!(next > lo && next < hi) || slow >= 3) { next = 0.5 * (lo + hi); slow = 0; }
-            width = nw;
-            if (next == mu || fabs(next - mu) <= 2.220446049250313e-16 * fabs(mu)) { mu = next; have = true; break; }
-            mu = next;
-        }
-        (void) have;
-        if (lane == 0) {
-            w.org[o + i] = org;
-            w.mu[o + i] = mu;
-            lam_new[o + i] = dorg + mu;
-        }
+    double fp;
+    int org;
+    double lo, hi;
+    bool left;
+    if (i < K - 1) {
+        const double gap = dk[i + 1] - dk[i];
+        left = dc_secular_fd(dk, z2, K, dk[i], rho, 0.5 * gap, red, fp) >= 0.0;
+        org = left ? i : i + 1;
+        lo = left ? 0.0 : -0.5 * gap;
+        hi = left ? 0.5 * gap : 0.0;
+    } else {
+        double zsum = 0.0;
+        for (int j = tid; j < K; j += DC_SEC_THREADS) zsum += z2[j];
+        zsum = dc_block_sum128(zsum, red);
+        left = true;
+        org = i;
+        lo = 0.0;
+        hi = rho * zsum; // the last root lies in (d_K-1, d_K-1 + rho sum z^2]
+    }
+    const double dorg = dk[org];
+    // f increases with mu: f(lo) < 0 <= f(hi); the zero end of the bracket is a pole.  First shrink the bracket until
+    // both ends have the pole's sign of mu and are within a factor 16 (geometric steps), then safeguarded Newton: a
+    // step that leaves the bracket, or three steps without halving it, is replaced by a bisection.  Every thread of the
+    // CTA takes the same decisions from the same bits.
+    for (int it = 0; it < 400; it++) {
+        double mid;
+        const bool tight = left ? (lo > 0.0 && hi / lo < 16.0) : (hi < 0.0 && lo / hi < 16.0);
+        if (tight) break;
+        if (left) mid = lo > 0.0 ? sqrt(lo * hi) : hi * 0.0009765625;
+        else mid = hi < 0.0 ? -sqrt(lo * hi) : lo * 0.0009765625;
+        if (!(mid > lo && mid < hi)) break;
+        if (dc_secular_fd(dk, z2, K, dorg, rho, mid, red, fp) >= 0.0) hi = mid; else lo = mid;
+    }
+    double mu = 0.5 * (lo + hi), width = hi - lo;
+    int slow = 0;
+    for (int it = 0; it < 200; it++) {
+        if (!(mu > lo && mu < hi)) { mu = 0.5 * (lo + hi); if (!(mu > lo && mu < hi)) break; }
+        const double f = dc_secular_fd(dk, z2, K, dorg, rho, mu, red, fp);
+        if (f >= 0.0) hi = mu; else lo = mu;
+        if (f == 0.0) break;
+        double next = mu - f / fp;
+        const double nw = hi - lo;
+        slow = (nw > 0.5 * width) ? slow + 1 : 0;
+        if (!(next > lo && next < hi) || slow >= 3) { next = 0.5 * (lo + hi); slow = 0; }
+        width = nw;
+        if (next == mu || fabs(next - mu) <= 2.220446049250313e-16 * fabs(mu)) { mu = next; break; }
+        mu = next;
+    }
+    if (tid == 0) {
+        w.org[o + i] = org;
+        w.mu[o + i] = mu;
+        lam_new[o + i] = dorg + mu;
     }
 }
 
@@ -564,7 +608,7 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
         dc_setup_kernel<<<cnt, DC_THREADS, setup_smem, st>>>(nodes, e, Zc, ld, lc, w, ln);
         BB_TRY(launched(ctx, "dc_setup_kernel"));
         const int chunks = std::max(1, std::min(512, ceil_div(kmax, DC_THREADS / 32))); // one root (component) per warp
-        dc_secular_kernel<<<dim3(cnt, chunks), DC_THREADS, 2 * (size_t) kmax * 8, st>>>(nodes, w, ln);
+        dc_secular_kernel<<<dim3(cnt, kmax), DC_SEC_THREADS, 2 * (size_t) kmax * 8, st>>>(nodes, w, ln);
         BB_TRY(launched(ctx, "dc_secular_kernel"));
         dc_zhat_kernel<<<dim3(cnt, chunks), DC_THREADS, 0, st>>>(nodes, w);
         BB_TRY(launched(ctx, "dc_zhat_kernel"));
