@@ -244,67 +244,97 @@ __global__ void __launch_bounds__(DC_THREADS) dc_setup_kernel(const DcNode *node
 // per evaluation; four warps per root and one root per CTA put ~6 warps on every scheduler.)
 constexpr int DC_SEC_THREADS = 128;
 
-__device__ __forceinline__ double dc_block_sum128(double v, double *red) { // all threads get the same bits
-    v = bb::warp_sum(v);
+// sums of three values over the CTA (one warp, or DC_SEC_THREADS threads); all threads get the same bits
+__device__ __forceinline__ void dc_cta_sum3(double &a, double &b, double &c, double *red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { // the butterflies interleave
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+        c += __shfl_xor_sync(0xffffffffu, c, off);
+    }
+    if (blockDim.x == 32) return;
+    __syncthreads(); // the previous sums have been read
+    if ((threadIdx.x & 31) == 0) {
+        const int q = threadIdx.x >> 5;
+        red[q] = a; red[4 + q] = b; red[8 + q] = c;
+    }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    return (red[0] + red[1]) + (red[2] + red[3]);
+    a = (red[0] + red[1]) + (red[2] + red[3]);
+    b = (red[4] + red[5]) + (red[6] + red[7]);
+    c = (red[8] + red[9]) + (red[10] + red[11]);
 }
 
-// f and f' = rho sum z_j^2 / (d_j - lambda)^2 in one pass (one division per term)
+// 1 / x to ~1 ulp: the 20-bit hardware seed and two Newton steps (5 instructions against ~30 of the IEEE division; the
+// root only has to be consistent with the Loewner z, not correctly rounded)
+__device__ __forceinline__ double dc_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double err = fma(-x, r, 1.0);
+    r = fma(r, err, r);
+    err = fma(-x, r, 1.0);
+    r = fma(r, err, r);
+    return fabs(r) < 1.7976931348623157e308 ? r : 1.0 / x; // seed 0 / inf (subnormal or huge x): the exact path
+}
+
+// f, f' = rho sum z_j^2 / (d_j - lambda)^2 and the size of the terms f is the difference of (its rounding noise is
+// ~eps * fabs_terms: the stopping test of dlaed4), one pass, one reciprocal per term
 __device__ __forceinline__ double dc_secular_fd(const double *dk, const double *z2, int K, double dorg, double rho, double mu,
-        double *red, double &fprime) {
-    double s = 0.0, s2 = 0.0, sb = 0.0, s2b = 0.0;
+        double *red, double &fprime, double &fabs_terms) {
+    double s = 0.0, s2 = 0.0, sa = 0.0, sb = 0.0, s2b = 0.0;
+    const int T = blockDim.x;
     int j = threadIdx.x;
-    for (; j + DC_SEC_THREADS < K; j += 2 * DC_SEC_THREADS) { // two reciprocals in flight
-        const double r = 1.0 / ((dk[j] - dorg) - mu), rb = 1.0 / ((dk[j + DC_SEC_THREADS] - dorg) - mu);
-        const double t = z2[j] * r, tb = z2[j + DC_SEC_THREADS] * rb;
+    for (; j + T < K; j += 2 * T) { // two reciprocals in flight
+        const double r = dc_rcp((dk[j] - dorg) - mu), rb = dc_rcp((dk[j + T] - dorg) - mu);
+        const double t = z2[j] * r, tb = z2[j + T] * rb;
         s += t;
         sb += tb;
+        sa += fabs(t) + fabs(tb);
         s2 = fma(t, r, s2);
         s2b = fma(tb, rb, s2b);
     }
-    for (; j < K; j += DC_SEC_THREADS) {
-        const double r = 1.0 / ((dk[j] - dorg) - mu);
+    for (; j < K; j += T) {
+        const double r = dc_rcp((dk[j] - dorg) - mu);
         const double t = z2[j] * r;
         s += t;
+        sa += fabs(t);
         s2 = fma(t, r, s2);
     }
-    s = dc_block_sum128(s + sb, red);
-    s2 = dc_block_sum128(s2 + s2b, red + 4);
+    s += sb;
+    s2 += s2b;
+    dc_cta_sum3(s, s2, sa, red);
     fprime = rho * s2;
+    fabs_terms = 1.0 + rho * sa;
     return 1.0 + rho * s;
 }
 
 __global__ void __launch_bounds__(DC_SEC_THREADS) dc_secular_kernel(const DcNode *nodes, DcWork w, double *lam_new) {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double red[8];
+    __shared__ double red[12];
     const DcNode nd = nodes[blockIdx.x];
     const int o = nd.o, K = w.K[blockIdx.x], tid = threadIdx.x, i = blockIdx.y;
     if (i >= K) return;
     double *dk = sm, *z2 = sm + K;
-    for (int j = tid; j < K; j += DC_SEC_THREADS) {
+    for (int j = tid; j < K; j += blockDim.x) {
         const double z = w.zk[o + j];
         dk[j] = w.dk[o + j];
         z2[j] = z * z;
     }
     __syncthreads();
     const double rho = w.rho[blockIdx.x];
-    double fp;
+    double fp, fa;
     int org;
     double lo, hi;
     bool left;
     if (i < K - 1) {
         const double gap = dk[i + 1] - dk[i];
-        left = dc_secular_fd(dk, z2, K, dk[i], rho, 0.5 * gap, red, fp) >= 0.0;
+        left = dc_secular_fd(dk, z2, K, dk[i], rho, 0.5 * gap, red, fp, fa) >= 0.0;
         org = left ? i : i + 1;
         lo = left ? 0.0 : -0.5 * gap;
         hi = left ? 0.5 * gap : 0.0;
     } else {
-        double zsum = 0.0;
-        for (int j = tid; j < K; j += DC_SEC_THREADS) zsum += z2[j];
-        zsum = dc_block_sum128(zsum, red);
+        double zsum = 0.0, u1 = 0.0, u2 = 0.0;
+        for (int j = tid; j < K; j += blockDim.x) zsum += z2[j];
+        dc_cta_sum3(zsum, u1, u2, red);
         left = true;
         org = i;
         lo = 0.0;
@@ -322,15 +352,15 @@ __global__ void __launch_bounds__(DC_SEC_THREADS) dc_secular_kernel(const DcNode
         if (left) mid = lo > 0.0 ? sqrt(lo * hi) : hi * 0.0009765625;
         else mid = hi < 0.0 ? -sqrt(lo * hi) : lo * 0.0009765625;
         if (!(mid > lo && mid < hi)) break;
-        if (dc_secular_fd(dk, z2, K, dorg, rho, mid, red, fp) >= 0.0) hi = mid; else lo = mid;
+        if (dc_secular_fd(dk, z2, K, dorg, rho, mid, red, fp, fa) >= 0.0) hi = mid; else lo = mid;
     }
     double mu = 0.5 * (lo + hi), width = hi - lo;
     int slow = 0;
     for (int it = 0; it < 200; it++) {
         if (!(mu > lo && mu < hi)) { mu = 0.5 * (lo + hi); if (!(mu > lo && mu < hi)) break; }
-        const double f = dc_secular_fd(dk, z2, K, dorg, rho, mu, red, fp);
+        const double f = dc_secular_fd(dk, z2, K, dorg, rho, mu, red, fp, fa);
         if (f >= 0.0) hi = mu; else lo = mu;
-        if (f == 0.0) break;
+        if (fabs(f) <= 8.0 * 2.220446049250313e-16 * fa) break; // f is zero to its rounding noise: no step can improve mu
         double next = mu - f / fp;
         const double nw = hi - lo;
         slow = (nw > 0.5 * width) ? slow + 1 : 0;
@@ -608,7 +638,7 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
         dc_setup_kernel<<<cnt, DC_THREADS, setup_smem, st>>>(nodes, e, Zc, ld, lc, w, ln);
         BB_TRY(launched(ctx, "dc_setup_kernel"));
         const int chunks = std::max(1, std::min(512, ceil_div(kmax, DC_THREADS / 32))); // one root (component) per warp
-        dc_secular_kernel<<<dim3(cnt, kmax), DC_SEC_THREADS, 2 * (size_t) kmax * 8, st>>>(nodes, w, ln);
+        dc_secular_kernel<<<dim3(cnt, kmax), kmax <= 128 ? 32 : DC_SEC_THREADS, 2 * (size_t) kmax * 8, st>>>(nodes, w, ln); // <= 4 terms per lane: one warp, no CTA barriers
         BB_TRY(launched(ctx, "dc_secular_kernel"));
         dc_zhat_kernel<<<dim3(cnt, chunks), DC_THREADS, 0, st>>>(nodes, w);
         BB_TRY(launched(ctx, "dc_zhat_kernel"));
