@@ -354,18 +354,20 @@ __global__ void __launch_bounds__(DC_SEC_THREADS) dc_secular_kernel(const DcNode
         if (!(mid > lo && mid < hi)) break;
         if (dc_secular_fd(dk, z2, K, dorg, rho, mid, red, fp, fa) >= 0.0) hi = mid; else lo = mid;
     }
-    double mu = 0.5 * (lo + hi), width = hi - lo;
+    double mu = 0.5 * (lo + hi), prev_step = hi - lo;
     int slow = 0;
     for (int it = 0; it < 200; it++) {
         if (!(mu > lo && mu < hi)) { mu = 0.5 * (lo + hi); if (!(mu > lo && mu < hi)) break; }
         const double f = dc_secular_fd(dk, z2, K, dorg, rho, mu, red, fp, fa);
         if (f >= 0.0) hi = mu; else lo = mu;
         if (fabs(f) <= 8.0 * 2.220446049250313e-16 * fa) break; // f is zero to its rounding noise: no step can improve mu
-        double next = mu - f / fp;
-        const double nw = hi - lo;
-        slow = (nw > 0.5 * width) ? slow + 1 : 0;
-        if (!(next > lo && next < hi) || slow >= 3) { next = 0.5 * (lo + hi); slow = 0; }
-        width = nw;
+        // Newton approaches the root from one side, so the bracket does not shrink while it converges: progress is
+        // measured on the step (three steps that do not halve -> one bisection), not on the bracket
+        const double step = -f / fp;
+        double next = mu + step;
+        slow = fabs(step) > 0.5 * prev_step ? slow + 1 : 0;
+        prev_step = fabs(step);
+        if (!(next > lo && next < hi) || slow >= 3) { next = 0.5 * (lo + hi); slow = 0; prev_step = hi - lo; }
         if (next == mu || fabs(next - mu) <= 2.220446049250313e-16 * fabs(mu)) { mu = next; break; }
         mu = next;
     }
