@@ -205,3 +205,32 @@ def test_sep_fused_generation_equals_phases(ctx, obj, n, lam, bound):
             X = b.get(_cabi.F_ARX)
             assert (X >= -box).all() and (X <= box).all()
         sigma *= 0.9
+
+
+@pytest.mark.parametrize("n,cond", [(256, 1e2), (300, 1e4), (777, 1e6), (1000, 1.0 + 1e-3), (1000, 1e4), (1500, 1e3)])
+def test_own_eigensolver_inside_the_handle(ctx, port_oracle, n, cond):
+    """`bbgpu_cma_eig` at n >= 256 runs our own decomposition (cooperative sytrd + tridiagonal divide & conquer + ormtr,
+    cmaes.cpp:229-283 is the contract): C = B diag(D^2) B^T with B orthogonal, D ascending, C^-1/2 C C^-1/2 = I, on
+    covariance matrices with a prescribed spectrum (nearly isotropic like early CMA generations, and graded)."""
+    P = port_oracle
+    lam = 16
+    h = P.cma(O.VANILLA, 10 ** 9, 1e-12, lam)
+    h.init(O.SPHERE, -10 * np.ones(n), 10 * np.ones(n), np.ones(n))
+    g = _cabi.Cma(ctx, O.VANILLA, n, lam, h.getv("weights"), oracle_constants(h, O.VANILLA), seed=1)
+    g.reset(np.ones(n))
+    rng = np.random.default_rng(n)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    spectrum = np.sort(np.exp(rng.uniform(0.0, np.log(cond), n)))
+    C = (Q * spectrum) @ Q.T
+    C = 0.5 * (C + C.T)
+    g.set(_cabi.F_C, C)
+    g.eig()
+    rep = g.fetch()
+    assert rep.eig_info == 0
+    B, D, inv = g.get(_cabi.F_B), g.get(_cabi.F_D), g.get(_cabi.F_INVSQRTC)
+    assert np.all(np.diff(D) >= 0)
+    assert_close(D ** 2, np.linalg.eigvalsh(C), rel=1e-10, what="eigenvalues")
+    assert np.abs(B.T @ B - np.eye(n)).max() < 1e-12
+    assert np.abs((B * D ** 2) @ B.T - C).max() < 1e-10 * spectrum[-1]
+    invf = np.tril(inv) + np.tril(inv, -1).T
+    assert np.abs(invf @ C @ invf - np.eye(n)).max() < 1e-9 * cond
