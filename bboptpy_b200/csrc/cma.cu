@@ -49,6 +49,7 @@ struct bbgpu_cma {
     double *own_ws = nullptr;     // own eigensolver: d, e, tau, reflectors (n*n), sytrd workspace, ormtr workspace
     int own_lwork = 0;
     int *own_info = nullptr;
+    cudaEvent_t ev_eig_fork = nullptr, ev_eig_join = nullptr;
     int *dev_info = nullptr;
     // draw prefetch: Z is double buffered; the draws of generation g+1 are generated on the ctx's side
     // stream while generation g runs its update (counter-based Philox: they depend on nothing)
@@ -81,6 +82,7 @@ int comm_broadcast(bbgpu_comm *c, double *d_buf, size_t count, int root);
 // sytrd.cu / stedc.cu: our own dense symmetric eigensolver (tridiagonalisation + divide & conquer)
 bool sytrd_fits(bbgpu_ctx *ctx, int n);
 size_t sytrd_workspace_doubles(int n);
+int q_rows_device(bbgpu_ctx *ctx, cudaStream_t st, int n, const double *d_Vcm, const double *d_tau, double *d_R, int ldr);
 int sytrd_device(bbgpu_ctx *ctx, int n, const double *d_A, int ldA, double *d_d, double *d_e, double *d_tau, double *d_Vcm, double *ws);
 int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double *W, double *Zt_out, int ldz, int *d_info);
 struct PeerRegion;
@@ -952,22 +954,45 @@ static int do_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
     static const bool force_lib = [] { const char *e = getenv("BBGPU_EIG"); return e && e[0] == 'c'; }();
     if (!force_lib && n >= 256 && sytrd_fits(ctx, n)) {
         const size_t nn = (size_t) n;
+        // Back-transformation: Q^T is formed row by row from the reflectors (q_rows_kernel: no exchange between CTAs) on
+        // the side stream WHILE the divide & conquer runs (its kernels are small and latency-bound), then
+        // B^T = Z^T Q^T is one DMMA GEMM.  cuSOLVER's ormtr (0.5 ms at n = 1000: 16 dependent block steps after the
+        // divide & conquer) stays as the comparison path, BBGPU_EIG_Q=ormtr.
+        static const bool use_ormtr = [] { const char *e = getenv("BBGPU_EIG_Q"); return e && e[0] == 'o'; }();
+        const size_t zt = nn * (size_t) h->ldn;
         if (h->own_ws == nullptr) {
             int lw = 0;
             if (cusolverDnDormtr_bufferSize(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, h->Bt, n, h->W, h->Bt,
                     (int) h->ldn, &lw) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "ormtr_bufferSize failed");
             h->own_lwork = lw;
-            BB_TRY(dev_alloc(&h->own_ws, 3 * nn + nn * nn + sytrd_workspace_doubles(n) + (size_t) lw + 16));
+            BB_TRY(dev_alloc(&h->own_ws, 3 * nn + nn * nn + sytrd_workspace_doubles(n) + (size_t) lw + 2 * zt + 48));
             BB_TRY(dev_alloc(&h->own_info, (size_t) 4));
+            BB_CUDA(cudaEventCreateWithFlags(&h->ev_eig_fork, cudaEventDisableTiming));
+            BB_CUDA(cudaEventCreateWithFlags(&h->ev_eig_join, cudaEventDisableTiming));
         }
         double *dd = h->own_ws, *de = dd + nn, *dtau = de + nn, *Vcm = dtau + nn, *ws = Vcm + nn * nn,
                 *owork = ws + sytrd_workspace_doubles(n);
+        double *Ztmp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(owork + h->own_lwork) + 127) & ~(uintptr_t) 127); // TMA operands
+        double *Qt = Ztmp + ((zt + 15) & ~(size_t) 15);
         BB_CUDA(cudaMemsetAsync(de, 0, 2 * nn * 8, st));
         BB_TRY(sytrd_device(ctx, n, h->C, (int) h->ldn, dd, de, dtau, Vcm, ws));
-        BB_TRY(stedc_device(ctx, n, dd, de, h->W, h->Bt, (int) h->ldn, h->dev_info));
-        const cusolverStatus_t rc = cusolverDnDormtr(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, Vcm, n, dtau,
-                h->Bt, (int) h->ldn, owork, h->own_lwork, h->own_info);
-        if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDormtr failed with status %d", (int) rc);
+        if (use_ormtr || ctx->aux == nullptr) {
+            BB_TRY(stedc_device(ctx, n, dd, de, h->W, h->Bt, (int) h->ldn, h->dev_info));
+            const cusolverStatus_t rc = cusolverDnDormtr(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, Vcm, n, dtau,
+                    h->Bt, (int) h->ldn, owork, h->own_lwork, h->own_info);
+            if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDormtr failed with status %d", (int) rc);
+        } else {
+            BB_CUDA(cudaEventRecord(h->ev_eig_fork, st));
+            BB_CUDA(cudaStreamWaitEvent(ctx->aux, h->ev_eig_fork, 0));
+            BB_TRY(q_rows_device(ctx, ctx->aux, n, Vcm, dtau, Qt, (int) h->ldn));
+            BB_CUDA(cudaEventRecord(h->ev_eig_join, ctx->aux));
+            BB_TRY(stedc_device(ctx, n, dd, de, h->W, Ztmp, (int) h->ldn, h->dev_info));
+            BB_CUDA(cudaStreamWaitEvent(st, h->ev_eig_join, 0));
+            // rows of Ztmp are the eigenvectors of T: B^T (rows = eigenvectors of C) = Z^T Q^T
+            GemmArgs g {};
+            g.A = Ztmp; g.lda = h->ldn; g.B = Qt; g.ldb = h->ldn; g.M = n; g.N = n; g.K = n; g.C = h->Bt; g.ldc = h->ldn;
+            BB_TRY((launch_gemm<1, EPI_STORE>(ctx, g)));
+        }
     } else {
         dim3 grid(ceil_div(n, 256), n);
         symmetrize_kernel<<<grid, 256, 0, st>>>(h->C, h->Bt, n, h->ldn);
@@ -1138,6 +1163,8 @@ int bbgpu_cma_destroy(bbgpu_cma *h) {
             h->ycoeff, h->dscal, h->X, h->Zbuf[0], h->Zbuf[1], h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
             h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc, h->own_ws };
     if (h->own_info) cudaFree(h->own_info);
+    if (h->ev_eig_fork) cudaEventDestroy(h->ev_eig_fork);
+    if (h->ev_eig_join) cudaEventDestroy(h->ev_eig_join);
     for (double *b : bufs) if (b) cudaFree(b);
     if (h->rank_idx) cudaFree(h->rank_idx);
     if (h->dev_info) cudaFree(h->dev_info);

@@ -271,6 +271,93 @@ bool sytrd_fits(bbgpu_ctx *ctx, int n) {
 
 size_t sytrd_workspace_doubles(int n) { return 4 * (size_t) n + 64; } // y (2n), pivot rows (2n), barrier, profile
 
+} // namespace bb
+
+namespace {
+
+// ---- Q^T from the reflectors, row by row ------------------------------------------------------------------------------
+// Row r of Q^T = e_r^T H_{n-2} ... H_1 H_0 (the H_i are symmetric).  Multiplying a ROW by H_i from the right is local to the
+// row: q <- q - tau_i (q . v_i) v_i^T, so a warp keeps one row in registers and walks the reflectors with no exchange
+// between CTAs at all; reflectors i >= r leave e_r untouched and are skipped (the 4/3 n^3 flops of orgtr, not 2 n^3).  The
+// CTA stages v_i in shared memory (double buffer, the next column is prefetched while this one is applied).  Runs on the
+// side stream WHILE the tridiagonal divide & conquer runs on the main one; the back-transformation is then one GEMM.
+constexpr int QR_THREADS = 256, QR_WARPS = QR_THREADS / 32;
+
+template<int KQ>
+__global__ void __launch_bounds__(QR_THREADS) q_rows_kernel(const double *__restrict__ Vcm, const double *__restrict__ tau, int n,
+        double *__restrict__ R, int ldr) {
+    constexpr int NP = KQ * 32;
+    __shared__ __align__(16) double vbuf[2][NP];
+    __shared__ double stau[NP];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int r = blockIdx.x + wid * gridDim.x; // the rows of a CTA are spread over the matrix: equal work per CTA
+    const int rtop = min(blockIdx.x + (QR_WARPS - 1) * (int) gridDim.x, n - 1);
+    const int istart = min(rtop - 1, n - 2);    // reflectors above leave every row of this CTA untouched
+    double q[KQ];
+#pragma unroll
+    for (int k = 0; k < KQ; k++) q[k] = (lane + 32 * k == r) ? 1.0 : 0.0;
+    for (int c = tid; c < NP; c += QR_THREADS) stau[c] = c < n - 1 ? tau[c] : 0.0;
+    // v_i by global row: 0 up to i, the implicit 1 at i+1, the stored part below
+    auto fetch = [&](int i, int c) -> double {
+        return (i < 0 || c <= i || c >= n) ? 0.0 : (c == i + 1 ? 1.0 : Vcm[(size_t) i * n + c]);
+    };
+    for (int c = tid; c < NP; c += QR_THREADS) vbuf[istart & 1][c] = fetch(istart, c);
+    __syncthreads();
+    for (int i = istart; i >= 0; i--) {
+        double nxt[NP / QR_THREADS];
+#pragma unroll
+        for (int j = 0; j < NP / QR_THREADS; j++) nxt[j] = fetch(i - 1, tid + j * QR_THREADS);
+        const double *v = vbuf[i & 1];
+        if (r < n && r > i) { // warp-uniform
+            const int k0 = (i + 1) >> 5;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < KQ; k += 4) {
+                if (k + 3 >= k0) { // v is zero up to i: whole groups of 32 below the reflector are skipped
+                    s0 = fma(q[k], v[lane + 32 * k], s0);
+                    s1 = fma(q[k + 1], v[lane + 32 * (k + 1)], s1);
+                    s2 = fma(q[k + 2], v[lane + 32 * (k + 2)], s2);
+                    s3 = fma(q[k + 3], v[lane + 32 * (k + 3)], s3);
+                }
+            }
+            const double t = stau[i] * bb::warp_sum((s0 + s1) + (s2 + s3));
+#pragma unroll
+            for (int k = 0; k < KQ; k += 4) {
+                if (k + 3 >= k0) {
+                    q[k] = fma(-t, v[lane + 32 * k], q[k]);
+                    q[k + 1] = fma(-t, v[lane + 32 * (k + 1)], q[k + 1]);
+                    q[k + 2] = fma(-t, v[lane + 32 * (k + 2)], q[k + 2]);
+                    q[k + 3] = fma(-t, v[lane + 32 * (k + 3)], q[k + 3]);
+                }
+            }
+        }
+        double *w = vbuf[(i + 1) & 1]; // read last in iteration i+1: every warp is past that iteration's barrier
+#pragma unroll
+        for (int j = 0; j < NP / QR_THREADS; j++) w[tid + j * QR_THREADS] = nxt[j];
+        __syncthreads();
+    }
+    if (r < n) {
+#pragma unroll
+        for (int k = 0; k < KQ; k++) {
+            const int c = lane + 32 * k;
+            if (c < n) R[(size_t) r * ldr + c] = q[k];
+        }
+    }
+}
+
+} // namespace
+
+namespace bb {
+
+// R (n x n, row-major, pitch ldr) = Q^T for the reflectors of sytrd_device, enqueued on `st`
+int q_rows_device(bbgpu_ctx *ctx, cudaStream_t st, int n, const double *d_Vcm, const double *d_tau, double *d_R, int ldr) {
+    if (n > 2048) return fail(BBGPU_ERR_ARG, "q_rows_device: n = %d is beyond the kernel", n);
+    const int grid = (n + QR_WARPS - 1) / QR_WARPS;
+    if (n <= 1024) q_rows_kernel<32><<<grid, QR_THREADS, 0, st>>>(d_Vcm, d_tau, n, d_R, ldr);
+    else q_rows_kernel<64><<<grid, QR_THREADS, 0, st>>>(d_Vcm, d_tau, n, d_R, ldr);
+    return launched(ctx, "q_rows_kernel");
+}
+
 // device form: A row-major with pitch ldA (lower triangle read) -> d, e, tau (n each) and the reflectors in Vcm (n*n,
 // column-major, LAPACK dsytrd('L') layout); ws = sytrd_workspace_doubles(n).  Enqueued on the ctx stream.
 int sytrd_device(bbgpu_ctx *ctx, int n, const double *d_A, int ldA, double *d_d, double *d_e, double *d_tau, double *d_Vcm,

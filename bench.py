@@ -632,7 +632,7 @@ def run_own(args):
                      "generation_tflops": step_flops / (ms_step * 1e-3) / 1e12 * world,
                      "generation_frac_of_peak": step_flops / (ms_step * 1e-3) / 1e12 / peak,
                      "kernel_share_of_step": shares},
-        "eig": {"ms": res["eig_ms"], "cadence_generations": 1, "solver": "own: cooperative sytrd kernel + tridiagonal divide & conquer + cuSOLVER ormtr, then the DMMA C^-1/2 rebuild (cuSOLVER syevd outside 256 <= n <= ~1700 or with BBGPU_EIG=cusolver)",
+        "eig": {"ms": res["eig_ms"], "cadence_generations": 1, "solver": "own: cooperative sytrd kernel + tridiagonal divide & conquer with the row-local Q^T kernel on the side stream + one DMMA GEMM, then the DMMA C^-1/2 rebuild (cuSOLVER syevd outside 256 <= n <= ~1700 or with BBGPU_EIG=cusolver)",
                 "gens_per_s_incl_eig": world / ((ms_step + res["eig_ms"]) * 1e-3)},
         "best_of": {"f": fbest, "rank": owner},
         "de": de,
