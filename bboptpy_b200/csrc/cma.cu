@@ -976,7 +976,8 @@ static int do_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
         double *Qt = Ztmp + ((zt + 15) & ~(size_t) 15);
         BB_CUDA(cudaMemsetAsync(de, 0, 2 * nn * 8, st));
         BB_TRY(sytrd_device(ctx, n, h->C, (int) h->ldn, dd, de, dtau, Vcm, ws));
-        if (use_ormtr || ctx->aux == nullptr) {
+        if (!use_ormtr && !ctx->aux) BB_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+        if (use_ormtr) {
             BB_TRY(stedc_device(ctx, n, dd, de, h->W, h->Bt, (int) h->ldn, h->dev_info));
             const cusolverStatus_t rc = cusolverDnDormtr(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, Vcm, n, dtau,
                     h->Bt, (int) h->ldn, owork, h->own_lwork, h->own_info);
