@@ -325,12 +325,15 @@ __global__ void __launch_bounds__(DC_SEC_THREADS) dc_secular_kernel(const DcNode
     int org;
     double lo, hi;
     bool left;
+    double fstart, xstart; // f at the first evaluation point, and that point relative to the origin pole
     if (i < K - 1) {
         const double gap = dk[i + 1] - dk[i];
-        left = dc_secular_fd(dk, z2, K, dk[i], rho, 0.5 * gap, red, fp, fa) >= 0.0;
+        fstart = dc_secular_fd(dk, z2, K, dk[i], rho, 0.5 * gap, red, fp, fa);
+        left = fstart >= 0.0;
         org = left ? i : i + 1;
         lo = left ? 0.0 : -0.5 * gap;
         hi = left ? 0.5 * gap : 0.0;
+        xstart = left ? 0.5 * gap : -0.5 * gap;
     } else {
         double zsum = 0.0, u1 = 0.0, u2 = 0.0;
         for (int j = tid; j < K; j += blockDim.x) zsum += z2[j];
@@ -339,13 +342,21 @@ __global__ void __launch_bounds__(DC_SEC_THREADS) dc_secular_kernel(const DcNode
         org = i;
         lo = 0.0;
         hi = rho * zsum; // the last root lies in (d_K-1, d_K-1 + rho sum z^2]
+        xstart = hi;
+        fstart = dc_secular_fd(dk, z2, K, dk[i], rho, hi, red, fp, fa);
     }
     const double dorg = dk[org];
-    // f increases with mu: f(lo) < 0 <= f(hi); the zero end of the bracket is a pole.  First shrink the bracket until
-    // both ends have the pole's sign of mu and are within a factor 16 (geometric steps), then safeguarded Newton: a
-    // step that leaves the bracket, or three steps without halving it, is replaced by a bisection.  Every thread of the
-    // CTA takes the same decisions from the same bits.
-    for (int it = 0; it < 400; it++) {
+    // f increases with mu: f(lo) < 0 <= f(hi); the zero end of the bracket is a pole.  Start: split f into the origin
+    // pole's term -rho z_o^2 / mu and the rest g, which increases with mu; freezing g at the first evaluation point gives
+    // mu0 = rho z_o^2 / g(xstart), which lies between the pole and the root -- the side from which Newton on f converges
+    // monotonically (f is concave on the right of a pole, convex on its left).  Then safeguarded Newton: a step that
+    // leaves the bracket, or three steps that do not halve, are replaced by a bisection.  When mu0 is unusable the bracket is
+    // first shrunk geometrically until both ends are within a factor 16.  Every thread of the CTA takes the same decisions
+    // from the same bits.
+    const double pole = rho * z2[org];
+    double mu0 = pole / (fstart + pole / xstart);
+    const bool good = mu0 > lo && mu0 < hi;
+    for (int it = 0; it < 400 && !good; it++) {
         double mid;
         const bool tight = left ? (lo > 0.0 && hi / lo < 16.0) : (hi < 0.0 && lo / hi < 16.0);
         if (tight) break;
@@ -354,7 +365,7 @@ __global__ void __launch_bounds__(DC_SEC_THREADS) dc_secular_kernel(const DcNode
         if (!(mid > lo && mid < hi)) break;
         if (dc_secular_fd(dk, z2, K, dorg, rho, mid, red, fp, fa) >= 0.0) hi = mid; else lo = mid;
     }
-    double mu = 0.5 * (lo + hi), prev_step = hi - lo;
+    double mu = good ? mu0 : 0.5 * (lo + hi), prev_step = 0.0;
     int slow = 0;
     for (int it = 0; it < 200; it++) {
         if (!(mu > lo && mu < hi)) { mu = 0.5 * (lo + hi); if (!(mu > lo && mu < hi)) break; }
@@ -362,12 +373,12 @@ __global__ void __launch_bounds__(DC_SEC_THREADS) dc_secular_kernel(const DcNode
         if (f >= 0.0) hi = mu; else lo = mu;
         if (fabs(f) <= 8.0 * 2.220446049250313e-16 * fa) break; // f is zero to its rounding noise: no step can improve mu
         // Newton approaches the root from one side, so the bracket does not shrink while it converges: progress is
-        // measured on the step (three steps that do not halve -> one bisection), not on the bracket
+        // measured on the step (three oscillating steps that do not halve -> one bisection), not on the bracket
         const double step = -f / fp;
         double next = mu + step;
-        slow = fabs(step) > 0.5 * prev_step ? slow + 1 : 0;
-        prev_step = fabs(step);
-        if (!(next > lo && next < hi) || slow >= 3) { next = 0.5 * (lo + hi); slow = 0; prev_step = hi - lo; }
+        slow = (fabs(step) > 0.5 * fabs(prev_step) && step * prev_step < 0.0) ? slow + 1 : 0; // oscillation, not a monotone approach
+        prev_step = step;
+        if (!(next > lo && next < hi) || slow >= 3) { next = 0.5 * (lo + hi); slow = 0; prev_step = 0.0; }
         if (next == mu || fabs(next - mu) <= 2.220446049250313e-16 * fabs(mu)) { mu = next; break; }
         mu = next;
     }
