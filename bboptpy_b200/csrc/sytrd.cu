@@ -417,7 +417,6 @@ int bbgpu_sytrd_host(bbgpu_ctx *ctx, int n, const double *h_A, double *h_d, doub
     long long *dprof = nullptr;
     BB_TRY(bb::dev_alloc(&dprof, (size_t) 24));
     void *args[] = { (void*) &dA, (void*) &nn, (void*) &ld, (void*) &dd, (void*) &de, (void*) &dt, (void*) &dV, (void*) &dy, (void*) &dr, (void*) &dbar, (void*) &dprof };
-    (void) 0;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
