@@ -173,6 +173,7 @@ def lib():
     L.bbgpu_de_generation_batch.argtypes = [vp, i, vp, vp]
     L.bbgpu_cmab_create.argtypes = [vp, i, i, i, vp, vp, P(vp)]
     L.bbgpu_cmab_destroy.argtypes = [vp]
+    L.bbgpu_cmab_limits.argtypes = [i, P(i), P(i), P(i)]
     L.bbgpu_cmab_start.argtypes = [vp, i, vp, P(CmabRunParams), vp, i]
     L.bbgpu_cmab_step.argtypes = [vp, vp, i, vp, i, i, vp, i]
     L.bbgpu_cmab_fetch.argtypes = [vp, P(CmabRunStatus)]

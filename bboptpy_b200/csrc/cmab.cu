@@ -702,6 +702,19 @@ int field_ptr(bbgpu_cmab *h, int run, int field, double **p, int64_t *len) {
 
 extern "C" {
 
+int bbgpu_cmab_limits(int n, int *max_n, int *max_lambda, int *max_hlen) {
+    BB_ARG(n >= 2);
+    if (max_n) *max_n = NMAX;
+    if (max_hlen) *max_hlen = HCAP;
+    if (max_lambda) {
+        int lam = 0;
+        if (n <= NMAX) // the bitonic ranking buffer (power of two >= lambda) must fit beside the run's state
+            for (int P = 2; P <= (1 << 20) && step_smem_bytes(n, n | 1, P) <= (size_t) 220 * 1024; P <<= 1) lam = P;
+        *max_lambda = lam;
+    }
+    return BBGPU_OK;
+}
+
 int bbgpu_cmab_create(bbgpu_ctx *ctx, int n, int runs, int bound, const double *h_lower, const double *h_upper,
                       bbgpu_cmab **out) {
     BB_ARG(ctx != nullptr && out != nullptr);

@@ -14,8 +14,11 @@
 
 namespace bb {
 
+// NaN of either sign (x86's default NaN 0xFFF8... has the sign bit set) maps to the largest key, so it sorts last and
+// can never become the best candidate; -0.0 and +0.0 share a key (f + 0.0 turns -0.0 into +0.0).
 __device__ __forceinline__ unsigned long long sortable_key(double f) {
-    const long long b = __double_as_longlong(f);
+    if (f != f) return ~0ull;
+    const long long b = __double_as_longlong(f + 0.0);
     return (unsigned long long) (b ^ ((b >> 63) | (long long) 0x8000000000000000ull));
 }
 

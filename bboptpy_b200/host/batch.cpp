@@ -5,6 +5,8 @@
 #include <iostream>
 #include <limits>
 #include <memory>
+#include <stdexcept>
+#include <string>
 
 #include "random.hpp"
 
@@ -112,6 +114,24 @@ void RestartBatch::configureBiPop(int maxlargeruns, bool nbipop, double ksigmade
     _kbudget = kbudget;
 }
 
+// The batched engine keeps a run inside one CTA: n is capped by the CTA's thread layout and lambda by the shared memory of
+// the in-CTA ranking (bbgpu_cmab_limits).  n beyond the cap is rejected here, BEFORE any compute.  The restart schedules
+// grow lambda (IPOP: doubling up to 10 n^2, ipop_cmaes.cpp:81,120-131; BIPOP: lambdadef 2^largerestarts,
+// bipop_cmaes.cpp:208), in theory past the cap; a sequence whose NEXT base run would exceed it ends there with what it
+// has (one warning per batch) instead of failing the whole batch in the middle and dropping every run's result.
+int RestartBatch::engineMaxLambda(int n) const {
+    int max_n = 0, max_lambda = 0, max_hlen = 0;
+    gpu_check(bbgpu_cmab_limits(n, &max_n, &max_lambda, &max_hlen));
+    if (n > max_n)
+        throw std::invalid_argument("restart batch: n = " + std::to_string(n) + " exceeds the batched engine's limit of " +
+                std::to_string(max_n) + "; use IPopCMAES / BiPopCMAES (one-handle engine) for larger problems");
+    const int lambdadef = 4 + static_cast<int>(3. * std::log(1. * n));
+    const int hlen = 10 + static_cast<int>(std::ceil((30. * n) / lambdadef));
+    if (hlen > max_hlen || lambdadef > max_lambda)
+        throw std::invalid_argument("restart batch: the default run at n = " + std::to_string(n) + " does not fit the batched engine");
+    return max_lambda;
+}
+
 std::vector<multivariate_solution> RestartBatch::optimize(const multivariate_problem &f, const double *guesses) {
     if (f._hasc || f._hasbbc) {
         std::cerr << "Warning [CMA batch]: problem constraints will be ignored." << std::endl;
@@ -119,6 +139,8 @@ std::vector<multivariate_solution> RestartBatch::optimize(const multivariate_pro
     _n = f._n;
     const int n = _n;
     bbgpu_ctx *ctx0 = bbopt::device_context();
+    const int max_lambda = engineMaxLambda(n);
+    bool warned_lambda = false;
     const int world = _comm ? bbgpu_comm_world(_comm) : 1, rank = _comm ? bbgpu_comm_rank(_comm) : 0;
     _ids.clear();
     for (int r = rank; r < _runs; r += world) _ids.push_back(r);
@@ -221,6 +243,17 @@ std::vector<multivariate_solution> RestartBatch::optimize(const multivariate_pro
                 _stats.evaluations += s.fev();
             } else {
                 const base_run_request req = s.next(f._lower, f._upper, x0); // fills x0
+                if (req.lambda > max_lambda) { // see engineMaxLambda(): end this sequence with what it has
+                    if (!warned_lambda) {
+                        std::cerr << "Warning [CMA batch]: a restart asked for lambda = " << req.lambda << " > " << max_lambda
+                                  << " (batched engine limit at n = " << n << "); such sequences stop early." << std::endl;
+                        warned_lambda = true;
+                    }
+                    s.finished = true;
+                    _fev[l] = s.fev();
+                    _stats.evaluations += s.fev();
+                    continue;
+                }
                 queue_start(gr, q, req, x0.data());
             }
         }

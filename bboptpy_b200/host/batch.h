@@ -29,6 +29,9 @@ struct restart_batch_stats {
     double device_ms = 0.;          // summed device time of the step launches over all streams (they overlap), if timing was on
 };
 
+// Limits (bbgpu_cmab_limits): n <= 64; lambda of a base run <= 16384 (8192 for the largest n): the ranking lives in the
+// CTA's shared memory.  optimize() rejects a larger n up front; a sequence whose next restart would exceed the lambda cap
+// (IPOP's lambda can reach 10 n^2) stops there with its best so far, with a warning.
 class RestartBatch {
 public:
     enum Kind { IPOP = 0, BIPOP = 1 };
@@ -56,6 +59,7 @@ public:
     double bestOf(std::vector<double> &x, int *owner);
 
 private:
+    int engineMaxLambda(int n) const; // validates n, returns the engine's lambda cap
     Kind _kind;
     int _runs, _mfev, _n = 0, _quantum = 3000, _streams = 0;
     struct Group;

@@ -72,6 +72,10 @@ void DeSearchBase::init(const multivariate_problem &f, const double *guess) {
     cfg.pelite = _pelite;
     cfg.cdamp = _c;
     cfg.sigma = _sigma;
+    // a fresh Philox key per init(): a second optimize()/initialize() on the same object is an independent run, as in the
+    // reference, whose process-global engine simply keeps advancing (src/random.hpp:677-680).  A key given explicitly
+    // through setStreamKey() is kept (reproducible runs).
+    if (!_stream_key_fixed) _stream_key = bbopt::Random::next_stream_key();
     cfg.seed = _stream_key;
     gpu_check(bbgpu_de_create(bbopt::device_context(), &cfg, _lower.data(), _upper.data(), &_dev));
     const bool replayInit = (int) _initial.size() == _npinit * _n;

@@ -29,6 +29,7 @@ protected:
     bbopt::ObjectiveHandle _obj;
     bbgpu_de_report _rep;
     uint64_t _stream_key;
+    bool _stream_key_fixed = false;
     de_replay_fn _replay;
     std::vector<double> _initial;
     virtual int kind() const = 0;
@@ -44,6 +45,7 @@ public:
     // additions: replay hooks and state access
     void setDrawReplay(de_replay_fn fn) { _replay = fn; }
     void setInitialPopulation(const std::vector<double> &x) { _initial = x; }
+    void setStreamKey(uint64_t key) { _stream_key = key; _stream_key_fixed = true; }
     std::vector<double> swarm();
     std::vector<double> fitness();
     const bbgpu_de_report &report() const { return _rep; }

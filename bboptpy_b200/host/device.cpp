@@ -1,9 +1,23 @@
 #include "device.h"
 
 #include <cstdlib>
+#include <exception>
 #include <mutex>
 
 namespace bbopt {
+
+// the exception a host objective threw inside the C call that is returning an error on this thread
+static thread_local std::exception_ptr pending_objective_exception;
+
+void gpu_check(int status) {
+    if (status == BBGPU_OK) return;
+    if (pending_objective_exception) {
+        std::exception_ptr e = pending_objective_exception;
+        pending_objective_exception = nullptr;
+        std::rethrow_exception(e);
+    }
+    throw GpuError(std::string("bbgpu: ") + bbgpu_last_error());
+}
 
 bbgpu_ctx *device_context() {
     static bbgpu_ctx *ctx = nullptr;
@@ -24,6 +38,7 @@ int ObjectiveHandle::bridge(const double *hX, int64_t ld, int n, int count, doub
     try {
         for (int k = 0; k < count; k++) hf[k] = self->_f(hX + (int64_t) k * ld);
     } catch (...) {
+        pending_objective_exception = std::current_exception(); // rethrown by gpu_check once the C call has returned
         return 1;
     }
     return 0;

@@ -15,9 +15,10 @@ struct GpuError: public std::runtime_error {
     explicit GpuError(const std::string &what) : std::runtime_error(what) {}
 };
 
-inline void gpu_check(int status) {
-    if (status != BBGPU_OK) throw GpuError(std::string("bbgpu: ") + bbgpu_last_error());
-}
+// Throws on a non-zero status.  When the failure is a user objective that threw inside the batched host-callback
+// bridge (e.g. a Python exception, py::error_already_set), the ORIGINAL exception is rethrown, as in the reference,
+// where the callback's exception propagates through optimize() (py/multivariate_py.cpp:385-388).
+void gpu_check(int status);
 
 // process-wide context on the selected device (env BBOPT_DEVICE or LOCAL_RANK, default 0).
 // Throws when no CUDA device is usable: there is no CPU fallback.

@@ -248,6 +248,8 @@ PYBIND11_MODULE(_bboptpy, m) {
             return a;
         })
         .def("fitness", [](DeSearchBase &self) { return as_array(self.fitness()); })
+        .def("set_stream_key", &DeSearchBase::setStreamKey, "key"_a,
+             "Fix the Philox key of the free-running draws (default: a fresh key per initialize()/optimize(), so repeated calls are independent runs)")
         .def("set_initial_population", [](DeSearchBase &self, py::array_t<double, py::array::c_style | py::array::forcecast> x) {
             self.setInitialPopulation(std::vector<double>(x.data(), x.data() + x.size()));
         }, "x"_a)

@@ -379,6 +379,10 @@ typedef struct bbgpu_cmab_run_status {
 int bbgpu_cmab_create(bbgpu_ctx *ctx, int n, int runs, int bound, const double *h_lower,
                       const double *h_upper, bbgpu_cmab **out);
 int bbgpu_cmab_destroy(bbgpu_cmab *h);
+/* engine limits at dimension n, so that a caller can validate a restart schedule BEFORE it spends compute: the largest
+ * dimension, the largest lambda whose ranking fits the CTA's shared memory, the capacity of the history rings
+ * (hlen = 10 + ceil(30 n / lambda), cma/base_cmaes.cpp:128).  Any out pointer may be NULL. */
+int bbgpu_cmab_limits(int n, int *max_n, int *max_lambda, int *max_hlen);
 /* (re)start `count` runs: m = guess (count*n, host), paths = 0, D = 1, C = B = C^-1/2 = I.
  * keep_offdiag != 0: only the diagonals of B and C are reset (the reference re-inits the same object
  * on a restart, cma/cmaes.cpp:53-60) */

@@ -56,6 +56,13 @@ int bbo_cma_getv(void *h, const char *name, double *out, int cap);
 double bbo_cma_time_eig(void *h);
 /* reset the optimizer's own normal_distribution cache (public _Z member) */
 void bbo_cma_reset_z(void *h);
+/* eigenbasis-replay feed for whole optimize() / restart-driver runs: with the log enabled, every
+ * eigenDecomposition() that fires (cma/cmaes.cpp:233-283) appends (fev, B, D) -- B n*n with
+ * B[i*n+j] = component i of eigenvector j, D n.  enable != 0 clears the log and starts recording. */
+void bbo_cma_eig_log(void *h, int enable);
+int bbo_cma_eig_log_count(void *h);
+/* event k: returns its n (0 when k is out of range); B / D may be NULL */
+int bbo_cma_eig_log_get(void *h, int k, int *fev, double *B, double *D);
 
 /* ---- restart drivers.  kind: 0 IPOP, 1 BIPOP; base = handle from bbo_cma_new.
  * trace receives up to cap rows of {lambda, sigma, fx, fev_total, regime}; returns rows */

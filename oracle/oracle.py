@@ -57,6 +57,11 @@ def _bind(lib):
     lib.bbo_cma_getd.restype = d
     lib.bbo_cma_getv.argtypes = [vp, cp, _c_dp, i]
     lib.bbo_cma_getv.restype = i
+    lib.bbo_cma_eig_log.argtypes = [vp, i]
+    lib.bbo_cma_eig_log_count.argtypes = [vp]
+    lib.bbo_cma_eig_log_count.restype = i
+    lib.bbo_cma_eig_log_get.argtypes = [vp, i, ctypes.POINTER(i), _c_dp, _c_dp]
+    lib.bbo_cma_eig_log_get.restype = i
     lib.bbo_restart_optimize.argtypes = [i, vp, i, d, i, d, i, i, d, i, i, _c_dp, _c_dp, _c_dp,
                                          _c_dp, ctypes.POINTER(i), _c_dp, i]
     lib.bbo_restart_optimize.restype = i
@@ -179,6 +184,20 @@ class OracleCma:
 
     def converged(self):
         return bool(self.lib.bbo_cma_converged(self.h))
+
+    def eig_log(self, enable=True):
+        """Record (fev, B, D) of every decomposition that fires from now on (eigenbasis-replay feed)."""
+        self.lib.bbo_cma_eig_log(self.h, int(enable))
+
+    def eig_events(self):
+        out = []
+        for k in range(self.lib.bbo_cma_eig_log_count(self.h)):
+            fev = ctypes.c_int(0)
+            n = self.lib.bbo_cma_eig_log_get(self.h, k, ctypes.byref(fev), None, None)
+            B, D = np.empty((n, n)), np.empty(n)
+            self.lib.bbo_cma_eig_log_get(self.h, k, ctypes.byref(fev), B.ctypes.data, D.ctypes.data)
+            out.append((fev.value, B, D))
+        return out
 
     def optimize(self, obj, lower, upper, guess):
         lower, upper, guess = _f64(lower), _f64(upper), _f64(guess)

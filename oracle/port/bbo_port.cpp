@@ -129,6 +129,10 @@ struct PortCma {
     /* SepCmaes state (sep_cmaes.h:39-43): C and d are length n */
     double ccov = 0;
     BboNormal Z;
+    /* eigenbasis-replay feed (bbo_cma_eig_log) */
+    struct EigEvent { int fev, n; std::vector<double> B, D; };
+    bool eiglog = false;
+    std::vector<EigEvent> eigevents;
 
     /* ---- cma/base_cmaes.cpp:54-134 */
     void base_init(const double *guess) {
@@ -628,6 +632,7 @@ struct PortCma {
                 isC[(size_t) i * n + j] = isC[(size_t) j * n + i] = sum;
             }
         }
+        if (eiglog) eigevents.push_back(EigEvent { fev, n, B, d });
     }
 
     /* ---- cma/cmaes.cpp:151-227 and cma/sep_cmaes.cpp:137-207 */
@@ -1126,6 +1131,24 @@ int bbo_cma_getv(void *h, const char *name, double *out, int cap) {
 }
 
 void bbo_cma_reset_z(void *h) { static_cast<PortCma*>(h)->Z.reset(); }
+
+void bbo_cma_eig_log(void *h, int enable) {
+    PortCma *p = static_cast<PortCma*>(h);
+    p->eigevents.clear();
+    p->eiglog = enable != 0;
+}
+
+int bbo_cma_eig_log_count(void *h) { return (int) static_cast<PortCma*>(h)->eigevents.size(); }
+
+int bbo_cma_eig_log_get(void *h, int k, int *fev, double *B, double *D) {
+    PortCma *p = static_cast<PortCma*>(h);
+    if (k < 0 || k >= (int) p->eigevents.size()) return 0;
+    const PortCma::EigEvent &e = p->eigevents[k];
+    if (fev) *fev = e.fev;
+    if (B) std::copy(e.B.begin(), e.B.end(), B);
+    if (D) std::copy(e.D.begin(), e.D.begin() + e.n, D);
+    return e.n;
+}
 
 double bbo_cma_time_eig(void *h) {
     PortCma *p = static_cast<PortCma*>(h);

@@ -78,6 +78,10 @@ struct CmaProbe {
     virtual double time_eig() { return 0.0; }
     std::vector<double> lower, upper, guess;
     multivariate_problem prob;
+    /* eigenbasis-replay feed (bbo_cma_eig_log): filled by FullProbe::iterate */
+    struct EigEvent { int fev, n; std::vector<double> B, D; };
+    bool eiglog = false;
+    std::vector<EigEvent> eigevents;
 };
 
 #define BASE_GETI(k)                                                                       \
@@ -135,6 +139,24 @@ template<class T> struct FullProbe: public T, public CmaProbe {
     using T::T;
     BaseCmaes *base() override { return this; }
     void reset_z() override { this->_Z.reset(); }
+    /* init()/iterate() are virtual in MultivariateOptimizer (multivariate.h:132-146), so the reference's own
+     * optimize() loop and its IPOP/BIPOP drivers dispatch here: record the basis whenever the decomposition fired */
+    int _eiglast = 0;
+    void init(const multivariate_problem &f, const double *guess) override {
+        T::init(f, guess);
+        _eiglast = this->_eigenlastev;
+    }
+    void iterate() override {
+        T::iterate();
+        if (this->_eigenlastev != _eiglast) {
+            _eiglast = this->_eigenlastev;
+            if (eiglog) {
+                EigEvent e { this->_eigenlastev, this->_n, {}, this->_diagd };
+                for (const auto &row : this->_b) e.B.insert(e.B.end(), row.begin(), row.end());
+                eigevents.push_back(std::move(e));
+            }
+        }
+    }
     double time_eig() override {
         this->_eigenlastev = this->_fev - static_cast<int>(this->_eigenfreq) - 1;
         const auto t0 = std::chrono::steady_clock::now();
@@ -368,6 +390,24 @@ int bbo_cma_getv(void *h, const char *name, double *out, int cap) {
 }
 void bbo_cma_reset_z(void *h) { static_cast<CmaProbe*>(h)->reset_z(); }
 double bbo_cma_time_eig(void *h) { return static_cast<CmaProbe*>(h)->time_eig(); }
+
+void bbo_cma_eig_log(void *h, int enable) {
+    CmaProbe *p = static_cast<CmaProbe*>(h);
+    p->eigevents.clear();
+    p->eiglog = enable != 0;
+}
+
+int bbo_cma_eig_log_count(void *h) { return (int) static_cast<CmaProbe*>(h)->eigevents.size(); }
+
+int bbo_cma_eig_log_get(void *h, int k, int *fev, double *B, double *D) {
+    CmaProbe *p = static_cast<CmaProbe*>(h);
+    if (k < 0 || k >= (int) p->eigevents.size()) return 0;
+    const CmaProbe::EigEvent &e = p->eigevents[k];
+    if (fev) *fev = e.fev;
+    if (B) std::copy(e.B.begin(), e.B.end(), B);
+    if (D) std::copy(e.D.begin(), e.D.begin() + e.n, D);
+    return e.n;
+}
 
 int bbo_restart_optimize(int kind, void *base, int mfev, double sigma0, int flag,
         double ksigmadec, int boundlambda, int maxlargeruns, double kbudget, int obj, int n,

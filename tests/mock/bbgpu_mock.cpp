@@ -110,6 +110,12 @@ int bbgpu_cmab_create(bbgpu_ctx *, int n, int runs, int, const double *, const d
     bbgpu_cmab *h = new bbgpu_cmab(); h->n = n; h->runs = runs; h->p.resize(runs); h->st.resize(runs); h->x.assign((size_t) runs * n, 0.0); *out = h; return 0;
 }
 int bbgpu_cmab_destroy(bbgpu_cmab *h) { delete h; return 0; }
+int bbgpu_cmab_limits(int, int *max_n, int *max_lambda, int *max_hlen) {
+    if (max_n) *max_n = 64;
+    if (max_lambda) *max_lambda = 16384;
+    if (max_hlen) *max_hlen = 512;
+    return 0;
+}
 int bbgpu_cmab_start(bbgpu_cmab *h, int count, const int32_t *ids, const bbgpu_cmab_run_params *p, const double *g, int) {
     for (int q = 0; q < count; q++) {
         h->p[ids[q]] = p[q];

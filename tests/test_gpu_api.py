@@ -147,6 +147,45 @@ def test_restart_drivers_replay_with_separable_base(pkg, port_oracle, driver, rk
     assert_close(sol.x, x_o, rel=1e-8, what="restart best x")
 
 
+@pytest.mark.parametrize("driver,rk,base_cls,base_kind", [("IPopCMAES", 0, "CMAES", O.VANILLA), ("BiPopCMAES", 1, "CMAES", O.VANILLA),
+                                                        ("BiPopCMAES", 1, "ActiveCMAES", O.ACTIVE)])
+def test_restart_drivers_replay_with_full_covariance_base(pkg, port_oracle, driver, rk, base_cls, base_kind):
+    """IPOP / BIPOP with a FULL-covariance base (cma/ipop_cmaes.cpp:65-162, cma/bipop_cmaes.cpp:61-267) under draw replay
+    + eigenbasis replay: the oracle logs (fev, B, D) at every decomposition of the whole restart sequence and the engine
+    adopts them event by event.  Exercises the re-init quirk on the device (cmaes.cpp:53-60: B and C keep their
+    off-diagonal entries across restarts of the same object, `bbgpu_cma_reset(keep_offdiag)`): the first generation of
+    every restart samples from the carried-over B before its first decomposition."""
+    P = port_oracle
+    n, budget = 6, 20000
+    lo, hi = -5.12 * np.ones(n), 5.12 * np.ones(n)
+    P.seed(5)
+    guess = P.uniform(-5, 5, n)
+    base_o = P.cma(base_kind, 1000, 1e-8, 10)
+    base_o.eig_log(True)
+    x_o, fev_o, trace = P.restart_optimize(rk, base_o, budget, O.RASTRIGIN, lo, hi, guess)
+    events = base_o.eig_events()
+    assert len(trace) >= 4 and len(events) > 100, "at least 3 restarts, each with its decompositions"
+    pkg.seed(5)
+    assert np.array_equal(pkg_uniform(pkg, -5, 5, n), guess)
+    base = getattr(pkg, base_cls)(mfev=1000, tol=1e-8, np=10)
+    base.set_draw_replay_global()
+    used = [0]
+
+    def basis(fev, n_):
+        k = used[0]
+        assert k < len(events), "the engine decomposes more often than the reference"
+        assert events[k][0] == fev, f"decomposition {k}: engine at fev {fev}, reference at {events[k][0]}"
+        used[0] += 1
+        return events[k][1], events[k][2]
+
+    base.set_eigen_replay(basis)
+    alg = getattr(pkg, driver)(base, mfev=budget)
+    sol = alg.optimize(pkg.Rastrigin, lo, hi, guess)
+    assert used[0] == len(events), "every decomposition of the reference happened on the device too"
+    assert sol.n_evals == fev_o
+    assert_close(sol.x, x_o, rel=1e-8, what="restart best x")
+
+
 def pkg_uniform(pkg, a, b, n):
     return np.array([pkg.uniform(a, b) for _ in range(n)])
 
@@ -180,6 +219,43 @@ def test_de_free_running_optimize(pkg, cls):
     sol = alg.optimize(pkg.Sphere, -5 * np.ones(n), 5 * np.ones(n), np.zeros(n))
     assert float((sol.x ** 2).sum()) < 1e-8
     assert sol.n_evals <= 60000 + 50
+
+
+@pytest.mark.parametrize("cls", ["JADE", "SHADE"])
+def test_de_repeated_optimize_calls_are_independent_runs(pkg, cls):
+    """The reference's process-global engine keeps advancing, so a second optimize() on the same object is a new run
+    (multi-start loops rely on it); a key fixed with set_stream_key() makes the run reproducible instead."""
+    n = 6
+    lo, hi = -5.12 * np.ones(n), 5.12 * np.ones(n)
+    make = (lambda: pkg.JADE(mfev=600, np=20, tol=0.0)) if cls == "JADE" else (lambda: pkg.SHADE(mfev=600, npinit=20, tol=0.0))
+    alg = make()
+    a = alg.optimize(pkg.Rastrigin, lo, hi, lo).x
+    b = alg.optimize(pkg.Rastrigin, lo, hi, lo).x
+    assert not np.array_equal(a, b)
+    fixed = make()
+    fixed.set_stream_key(12345)
+    c = fixed.optimize(pkg.Rastrigin, lo, hi, lo).x
+    d = fixed.optimize(pkg.Rastrigin, lo, hi, lo).x
+    assert np.array_equal(c, d)
+
+
+def test_python_exception_in_the_objective_propagates(pkg):
+    """py/multivariate_py.cpp:385-388: an exception raised by the user's callable surfaces as itself, not as a generic
+    engine error."""
+    class Boom(Exception):
+        pass
+
+    calls = [0]
+
+    def f(x):
+        calls[0] += 1
+        if calls[0] > 30:
+            raise Boom("objective failed")
+        return float(np.sum(x * x))
+
+    alg = pkg.CMAES(mfev=1000, tol=1e-8, np=10)
+    with pytest.raises(Boom):
+        alg.optimize(f, -np.ones(4), np.ones(4), 0.5 * np.ones(4))
 
 
 def test_bipop_free_running(pkg):

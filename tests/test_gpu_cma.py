@@ -43,6 +43,13 @@ CASES = [
     (O.VANILLA, O.ROSENBROCK, 200, 300, 4, False, 10.0),
     (O.ACTIVE, O.RASTRIGIN, 130, 257, 4, True, 5.12),
     (O.SEP, O.ELLIPSOID, 1000, 512, 4, False, 10.0),
+    # the BASELINE shapes bench.py times (configs A and S): the 128x112 sampling tile over 288 CTAs, the 64x64 SYRK at
+    # K = 2048 (4096 signed rows for Active), the ROWSQ norm GEMM, the own eigensolver at n = 1000 inside a real
+    # generation (the reference decomposes after EVERY generation here) and sep_sample at n = 10^4 -- against the oracle
+    (O.VANILLA, O.ROSENBROCK, 1000, 4096, 2, False, 10.0),
+    (O.ACTIVE, O.ROSENBROCK, 1000, 4096, 2, False, 10.0),
+    (O.VANILLA, O.ROSENBROCK, 1000, 4096, 1, True, 10.0),
+    (O.SEP, O.ELLIPSOID, 10000, 4096, 2, False, 10.0),
 ]
 
 

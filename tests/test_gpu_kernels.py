@@ -93,6 +93,11 @@ def test_rank_orders_ties_by_index_and_nan_last(ctx):
     f = np.array([3.0, 1.0, 3.0, np.nan, 1.0, -np.inf, np.inf, 2.0])
     idx = ctx.rank(f)
     assert idx.tolist() == [5, 1, 4, 7, 0, 2, 6, 3]
+    # a NaN with the sign bit set (x86's default NaN, e.g. inf - inf in a host callback) must not become the best
+    # candidate, and -0.0 / +0.0 are one key (ties by index)
+    neg_nan = np.frombuffer(np.uint64(0xFFF8000000000000).tobytes(), dtype=np.float64)[0]
+    f = np.array([0.0, neg_nan, -0.0, -1.0, np.nan, 5.0])
+    assert ctx.rank(f).tolist() == [3, 0, 2, 5, 1, 4]
 
 
 def test_philox_normals_are_standard_normal_and_placement_invariant(ctx):

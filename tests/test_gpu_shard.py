@@ -48,13 +48,16 @@ def load_state(g, s):
     g.set(_cabi.F_B, s["B"])
 
 
-@pytest.mark.parametrize("kind,obj,n,lam,G,bound", [
-    (O.VANILLA, O.ROSENBROCK, 24, 48, 2, False),
-    (O.ACTIVE, O.ROSENBROCK, 24, 48, 4, False),
-    (O.ACTIVE, O.RASTRIGIN, 130, 256, 8, True),
-    (O.VANILLA, O.ACKLEY, 200, 320, 4, True),
+@pytest.mark.parametrize("kind,obj,n,lam,G,bound,gens", [
+    (O.VANILLA, O.ROSENBROCK, 24, 48, 2, False, 6),
+    (O.ACTIVE, O.ROSENBROCK, 24, 48, 4, False, 6),
+    (O.ACTIVE, O.RASTRIGIN, 130, 256, 8, True, 6),
+    (O.VANILLA, O.ACKLEY, 200, 320, 4, True, 6),
+    # BASELINE config A8 (n = 1000, lambda = 16384 over 8 GPUs): the shapes bench.py's sharded_run times, 8 emulated shards
+    (O.VANILLA, O.ROSENBROCK, 1000, 16384, 8, False, 1),
+    (O.ACTIVE, O.ROSENBROCK, 1000, 16384, 8, False, 1),
 ])
-def test_sharded_generation_matches_oracle(ctx, port_oracle, kind, obj, n, lam, G, bound):
+def test_sharded_generation_matches_oracle(ctx, port_oracle, kind, obj, n, lam, G, bound, gens):
     """Teacher-forced against the oracle: replayed draws, oracle state in, sharded phases, exchange, state out."""
     P = port_oracle
     P.seed(11)
@@ -71,7 +74,7 @@ def test_sharded_generation_matches_oracle(ctx, port_oracle, kind, obj, n, lam, 
         s.reset(guess)
     ik = h.geti("ik")
     ll = lam // G
-    for gen in range(6):
+    for gen in range(gens):
         s0 = h.snapshot()
         h.sample()
         z = h.getv("z")

@@ -4,14 +4,29 @@ import numpy as np
 REL = 1e-10  # BASELINE.json north_star: mean, sigma, C and population within 1e-10 relative (fp64)
 
 
-def assert_close(got, want, rel=REL, what=""):
-    """Norm-wise relative agreement: max|got-want| <= rel * max|want| (arrays) or rel*|want| (scalars)."""
+ELEM_FLOOR = 1e-6   # element-wise companion: entries above ELEM_FLOOR * max|want| ...
+ELEM_REL = 1e-8     # ... agree to ELEM_REL relative, entry by entry
+
+
+def assert_close(got, want, rel=REL, what="", elem=True):
+    """Two checks.  (1) Norm-wise: max|got-want| <= rel * max|want| (arrays) or rel*|want| (scalars) -- the north
+    star's "1e-10 relative".  (2) Element-wise companion (arrays): every entry with |want| > ELEM_FLOOR * max|want| agrees
+    to max(ELEM_REL, 100 rel) of ITS OWN magnitude, so small entries (off-diagonal C entries ~1e-3 of the diagonal, mean
+    coordinates near zero) are held to a relative tolerance too.  Two fp64 implementations that sum K terms in
+    different orders differ by ~sqrt(K) eps * max|.| in every entry, hence the floor: an entry 1e-6 of the scale can
+    only be pinned to ~1e-8 of itself."""
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, (what, got.shape, want.shape)
     scale = max(float(np.max(np.abs(want))) if want.size else 0.0, 1e-300)
     err = float(np.max(np.abs(got - want))) if want.size else 0.0
     assert np.isfinite(got).all(), what
     assert err <= rel * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e} > {rel})"
+    if elem and want.ndim > 0 and want.size > 1:
+        big = np.abs(want) > ELEM_FLOOR * scale
+        if big.any():
+            erel = float(np.max(np.abs(got[big] - want[big]) / np.abs(want[big])))
+            tol = max(ELEM_REL, 100.0 * rel)
+            assert erel <= tol, f"{what}: element-wise rel err {erel:.3e} > {tol:.1e} on entries above {ELEM_FLOOR:g} * max"
 
 
 def oracle_constants(h, kind):
