@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -95,18 +96,29 @@ inline int launched(bbgpu_ctx *ctx, const char *what) {
     return BBGPU_OK;
 }
 
-// device-time accounting for one (group of) launch(es); active only in profiling mode
+// NVTX range names of the phases (bbgpu_profile_tag order): visible in nsys / ncu --nvtx timelines
+inline const char *prof_tag_name(int tag) {
+    static const char *names[] = { "bbgpu:sample_gemm", "bbgpu:cov_syrk", "bbgpu:norm_gemm", "bbgpu:evaluate", "bbgpu:rank",
+            "bbgpu:philox", "bbgpu:eig", "bbgpu:update_misc", "bbgpu:sep_sample", "bbgpu:de_round", "bbgpu:de_misc", "bbgpu:comm",
+            "bbgpu:cmab_step" };
+    return tag >= 0 && tag < (int) (sizeof(names) / sizeof(names[0])) ? names[tag] : "bbgpu:other";
+}
+
+// one phase of the path: an NVTX range around its launches (always; a no-op without an attached tool) and, in
+// profiling mode, device-time accounting with CUDA events
 struct ProfScope {
     bbgpu_ctx *ctx;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int tag;
     ProfScope(bbgpu_ctx *c, int t) : ctx(c), tag(t) {
+        nvtxRangePushA(prof_tag_name(t));
         if (!ctx->profiling) return;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0, ctx->stream);
     }
     ~ProfScope() {
+        nvtxRangePop();
         if (!e0) return;
         cudaEventRecord(e1, ctx->stream);
         ctx->prof.push_back({ tag, e0, e1 });
