@@ -78,7 +78,7 @@ def test_dsyrk_matches_numpy(ctx, n, K):
     assert np.array_equal(C[up], C0[up])  # the strict upper triangle is never written (cma/cmaes.cpp:127)
 
 
-@pytest.mark.parametrize("count", [2, 3, 20, 1000, 4096, 16384, 20000])
+@pytest.mark.parametrize("count", [2, 3, 20, 1000, 4096, 8191, 8192, 8193, 10000, 16384, 20000, 65536])
 def test_rank_is_the_sorted_permutation(ctx, count):
     rng = np.random.default_rng(count)
     f = rng.standard_normal(count) * 10.0 ** rng.integers(-3, 4, count)
@@ -100,12 +100,37 @@ def test_rank_orders_ties_by_index_and_nan_last(ctx):
     assert ctx.rank(f).tolist() == [3, 0, 2, 5, 1, 4]
 
 
+@pytest.mark.parametrize("count", [8192, 9000, 16384])
+def test_rank_chunk_path_with_heavy_ties_and_nans(ctx, count):
+    """The chunk-sort path (count >= 8192): many equal keys across chunks (ties by index), both zeros, NaNs of both signs."""
+    rng = np.random.default_rng(count)
+    f = rng.integers(0, 7, count).astype(np.float64)
+    f[rng.integers(0, count, 20)] = np.nan
+    f[rng.integers(0, count, 20)] = -0.0
+    neg_nan = np.frombuffer(np.uint64(0xFFF8000000000000).tobytes(), dtype=np.float64)[0]
+    f[rng.integers(0, count, 5)] = neg_nan
+    idx = ctx.rank(f)
+    key = np.where(np.isnan(f), np.inf, f + 0.0)
+    want = np.lexsort((np.arange(count), np.isnan(f), key))  # value, NaN last, then index
+    assert np.array_equal(idx, want)
+
+
 def test_philox_normals_are_standard_normal_and_placement_invariant(ctx):
     z = ctx.philox_normal(1234, 7, 512, 1001)
     assert np.isfinite(z).all()
     assert abs(z.mean()) < 5e-3 and abs(z.std() - 1.0) < 5e-3
     k = ((z - z.mean()) ** 4).mean() / z.var() ** 2
     assert abs(k - 3.0) < 0.05
+    # Kolmogorov-Smirnov against N(0,1), the mass in the far tail, symmetry, and no correlation between the two normals of
+    # a Philox block
+    from scipy import stats
+    big = ctx.philox_normal(99, 3, 2048, 2000)
+    assert stats.kstest(big.ravel(), "norm").pvalue > 1e-4
+    R = 3.654152885361009
+    tail = (np.abs(big) > R).mean()
+    assert abs(tail - 2 * stats.norm.sf(R)) < 4 * np.sqrt(2 * stats.norm.sf(R) / big.size)
+    assert abs((big > 0).mean() - 0.5) < 2e-3
+    assert abs(np.corrcoef(big[:, 0::2].ravel(), big[:, 1::2].ravel())[0, 1]) < 3e-3
     # same (seed, generation) -> same draws; different generation -> different draws
     assert np.array_equal(z, ctx.philox_normal(1234, 7, 512, 1001))
     assert not np.array_equal(z, ctx.philox_normal(1234, 8, 512, 1001))
