@@ -1,7 +1,7 @@
 """bboptpy_b200 -- B200-native population engine behind bboptpy's optimizer API.
 
 `from bboptpy_b200 import ActiveCMAES, ...` mirrors `from bboptpy import ...` for the classes on
-the accelerated path (CMAES, ActiveCMAES, SepCMAES, IPopCMAES, BiPopCMAES, JADE, SHADE).  The
+the accelerated path (CMAES, ActiveCMAES, SepCMAES, CholeskyCMAES, IPopCMAES, BiPopCMAES, JADE, SHADE).  The
 compute path is the C-ABI library libbbgpu.so (hand-written sm_100a CUDA); there is no CPU
 fallback -- constructing an optimizer without a usable CUDA device raises.
 """

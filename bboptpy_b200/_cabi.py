@@ -14,10 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BBGPU_LIB_PATH") or os.path.join(_HERE, "libbbgpu.so")  # override: A/B builds of the engine
 
 OBJ_SPHERE, OBJ_ELLIPSOID, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY = range(5)
-CMA_FULL, CMA_ACTIVE, CMA_SEP = range(3)
+CMA_FULL, CMA_ACTIVE, CMA_SEP, CMA_CHOLESKY = range(4)
 DE_JADE, DE_SHADE = range(2)
 (F_XMEAN, F_XOLD, F_PC, F_PS, F_C, F_B, F_D, F_INVSQRTC, F_ARX, F_Z, F_FITNESS, F_RANKVAL, F_YCOEFF,
- F_WEIGHTS, F_NORMS, F_SHARD_RED) = range(16)
+ F_WEIGHTS, F_NORMS, F_SHARD_RED, F_A) = range(17)
 COMM_ID_BYTES = 128
 
 c_dp = ctypes.c_void_p
@@ -141,6 +141,7 @@ def lib():
     L.bbgpu_cma_update.argtypes = [vp, d, i]
     L.bbgpu_cma_eig.argtypes = [vp, vp, vp]
     L.bbgpu_cma_probe.argtypes = [vp, d, i]
+    L.bbgpu_cma_swarm_radius.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.bbgpu_cma_fetch.argtypes = [vp, P(CmaReport)]
     L.bbgpu_cma_generation.argtypes = [vp, vp, d, u64, i, i]
     L.bbgpu_cma_attach_comm.argtypes = [vp, vp]
@@ -440,7 +441,7 @@ class Cma:
         ld = (n + 7) // 8 * 8
         return {F_XMEAN: n, F_XOLD: n, F_PC: n, F_PS: n, F_D: n, F_C: n * n if full else n, F_B: n * n,
                 F_INVSQRTC: n * n, F_ARX: self.lam_loc * n, F_Z: self.lam_loc * n, F_FITNESS: lam, F_RANKVAL: lam,
-                F_YCOEFF: self.mu, F_WEIGHTS: self.mu, F_NORMS: lam, F_SHARD_RED: n * ld + ld}[field]
+                F_YCOEFF: self.mu, F_WEIGHTS: self.mu, F_NORMS: lam, F_SHARD_RED: n * ld + ld, F_A: n * n}[field]
 
     def reset(self, guess, keep_offdiag=False):
         g = f64(guess)
@@ -453,7 +454,7 @@ class Cma:
     def get(self, field):
         out = np.empty(self._len(field))
         check(self.L.bbgpu_cma_get(self.h, field, out.ctypes.data, out.size))
-        if field in (F_B, F_INVSQRTC, F_ARX, F_Z) or (field == F_C and self.kind != CMA_SEP):
+        if field in (F_B, F_INVSQRTC, F_ARX, F_Z, F_A) or (field == F_C and self.kind != CMA_SEP):
             return out.reshape(-1, self.n)
         return out
 
@@ -461,6 +462,12 @@ class Cma:
         idx = np.empty(self.lam, dtype=np.int32)
         check(self.L.bbgpu_cma_get_rank(self.h, idx.ctypes.data, self.lam))
         return idx
+
+    def swarm_radius(self):
+        """Cholesky kind: (mean, M2) of the candidates' Euclidean norms (converged(), cholesky_cmaes.cpp:146-160)."""
+        mean, m2 = ctypes.c_double(0), ctypes.c_double(0)
+        check(self.L.bbgpu_cma_swarm_radius(self.h, ctypes.byref(mean), ctypes.byref(m2)))
+        return mean.value, m2.value
 
     def sample(self, sigma, generation=0, z=None):
         if z is not None:

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "chol.cuh"
 #include "gemm_tma.cuh"
 #include "objectives.cuh"
 #include "philox.cuh"
@@ -29,7 +30,11 @@ struct bbgpu_cma {
     bbgpu_cma_config cfg;
     int n = 0, lambda = 0, mu = 0, nsel = 0;
     int64_t ldn = 0;
-    bool full = false, active = false;
+    bool full = false, active = false, chol = false;
+    // Cholesky-CMA-ES (chol.cuh): stacked SYRK operand [A^T ; Y], the matrix being factored, the panel transposed, -1 coefficients,
+    // candidate radii + their statistics
+    double *Ystk = nullptr, *Mch = nullptr, *Lt = nullptr, *negone = nullptr, *rnorm = nullptr, *rstat = nullptr;
+    cudaEvent_t ev_ch_fork = nullptr, ev_ch_join = nullptr;
     // vectors
     double *xmean = nullptr, *xold = nullptr, *pc = nullptr, *ps = nullptr, *D = nullptr, *weights = nullptr,
             *lower = nullptr, *upper = nullptr, *dm = nullptr, *W = nullptr, *coef = nullptr, *ycoeff = nullptr,
@@ -690,16 +695,17 @@ static int refresh_basis_products(bbgpu_cma *h) {
 static int do_sample(bbgpu_cma *h, double sigma) {
     bbgpu_ctx *ctx = h->ctx;
     h->last_sigma = sigma;
-    ProfScope prof(ctx, h->full ? BBGPU_PROF_SAMPLE_GEMM : BBGPU_PROF_SEP_SAMPLE);
+    ProfScope prof(ctx, (h->full || h->chol) ? BBGPU_PROF_SAMPLE_GEMM : BBGPU_PROF_SEP_SAMPLE);
     const double *lo = h->cfg.bound ? h->lower : nullptr, *hi = h->cfg.bound ? h->upper : nullptr;
-    if (!h->full) {
+    if (!h->full && !h->chol) {
         dim3 grid(ceil_div(h->n, 256), std::min(h->lam_loc, 64));
         sep_sample_kernel<<<grid, 256, 0, ctx->stream>>>(h->X, h->Z, h->ldn, h->lam_loc, h->n, h->xmean, h->D, sigma, lo, hi);
         return launched(ctx, "sep_sample_kernel");
     }
     // X[k][i] = m_i + sigma * sum_j Z[k][j] * (D_j Bt[j][i]), clipped in the epilogue
     GemmArgs g {};
-    g.A = h->Z; g.lda = h->ldn; g.B = h->BDt; g.ldb = h->ldn;
+    // Cholesky kind: x = m + sigma A z, the operand is A^T (rows [0, n) of the stacked buffer; cholesky_cmaes.cpp:120-135)
+    g.A = h->Z; g.lda = h->ldn; g.B = h->chol ? h->Ystk : h->BDt; g.ldb = h->ldn;
     g.M = h->lam_loc; g.N = h->n; g.K = h->n;
     g.C = h->X; g.ldc = h->ldn; g.vec = h->xmean; g.lo = lo; g.hi = hi; g.s0 = sigma;
     return launch_gemm<1, EPI_SAMPLE>(ctx, g);
@@ -759,7 +765,80 @@ static int do_rank(bbgpu_cma *h, int ik) {
     return launched(h->ctx, "rank_report_kernel");
 }
 
+// M (lower, in Mch) -> its Cholesky factor in place: 64-column panels; the diagonal block and the panel solve in
+// chol_panel_kernel, the trailing update M22 -= L21 L21^T on the DMMA SYRK kernel (operand = the panel transposed)
+static int chol_factor(bbgpu_cma *h) {
+    bbgpu_ctx *ctx = h->ctx;
+    const int n = h->n;
+    for (int k0 = 0; k0 < n; k0 += CH_NB) {
+        const int nb = std::min(CH_NB, n - k0), rem = n - k0 - nb;
+        chol_panel_kernel<<<std::max(1, ceil_div(rem, CH_NB)), 256, 0, ctx->stream>>>(h->Mch, h->ldn, n, k0, nb, h->Lt, h->dev_info);
+        BB_TRY(launched(ctx, "chol_panel_kernel"));
+        if (rem <= 0) break;
+        GemmArgs g {};
+        g.A = h->Lt + (k0 + nb); g.lda = h->ldn; g.B = g.A; g.ldb = h->ldn;
+        g.M = rem; g.N = rem; g.K = nb; g.kscale = h->negone; g.kscale_padded = true;
+        g.C = h->Mch + (int64_t) (k0 + nb) * (h->ldn + 1); g.ldc = h->ldn; g.vec = h->pc; g.s0 = 1.0; g.s1 = 0.0; g.dscal = h->dscal;
+        BB_TRY((launch_gemm<2, EPI_SYRK>(ctx, g)));
+    }
+    return BBGPU_OK;
+}
+
+// CholeskyCmaes::updateDistribution up to and excluding updateSigma() (cholesky_cmaes.cpp:54-114)
+static int do_update_chol(bbgpu_cma *h, double sigma) {
+    bbgpu_ctx *ctx = h->ctx;
+    const bbgpu_cma_config &c = h->cfg;
+    const int n = h->n, mu = h->mu;
+    cudaStream_t st = ctx->stream;
+    const double *lo = c.bound ? h->lower : nullptr, *hi = c.bound ? h->upper : nullptr;
+    const double csc = std::sqrt(c.cs * (2.0 - c.cs) * c.mueff);
+    const double ccc = std::sqrt(c.cc * (2.0 - c.cc) * c.mueff);
+    const double acoeff = std::sqrt(1.0 - c.c1 - c.cmu);
+    if (!ctx->aux) BB_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    {
+        ProfScope prof(ctx, BBGPU_PROF_UPDATE_MISC);
+        BB_CUDA(cudaMemcpyAsync(h->xold, h->xmean, (size_t) n * 8, cudaMemcpyDeviceToDevice, st));
+        dim3 pgrid(ceil_div(n, 256), h->splits);
+        recombine_partial_kernel<false><<<pgrid, 256, 0, st>>>(h->part, h->X, h->ldn, n, mu, h->splits, h->rank_idx, h->weights,
+                h->xold, sigma);
+        BB_TRY(launched(ctx, "recombine_partial_kernel"));
+        recombine_final_kernel<false><<<ceil_div(n, 64), 256, 0, st>>>(h->part, n, h->splits, h->xmean, h->xold, h->dm, 1.0, sigma,
+                lo, hi, false, h->ps, nullptr, c.cs, csc, nullptr);
+        BB_TRY(launched(ctx, "recombine_final_kernel"));
+        const int coef_len = (int) round_up(n + mu, 32) + 32;
+        chol_paths_kernel<<<ceil_div(coef_len, 256), 256, 0, st>>>(n, mu, h->pc, h->dm, c.cc, ccc, acoeff, c.cmu, h->weights, h->coef,
+                coef_len);
+        BB_TRY(launched(ctx, "chol_paths_kernel"));
+        // p_sigma needs A(t)^-1 dmean with the OLD factor (:93-104): on the side stream, beside the SYRK and the factorisation
+        BB_CUDA(cudaEventRecord(h->ev_ch_fork, st));
+        BB_CUDA(cudaStreamWaitEvent(ctx->aux, h->ev_ch_fork, 0));
+        if ((size_t) (n + 64) * 8 > 48 * 1024)
+            BB_CUDA(cudaFuncSetAttribute(chol_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((n + 64) * 8)));
+        chol_ps_kernel<<<1, 1024, (size_t) (n + 64) * 8, ctx->aux>>>(h->Ystk, h->ldn, n, h->dm, h->ps, c.cs, csc, h->d_report);
+        BB_TRY(launched(ctx, "chol_ps_kernel"));
+        BB_CUDA(cudaEventRecord(h->ev_ch_join, ctx->aux));
+        chol_steps_kernel<<<mu, 256, 0, st>>>(h->Ystk + (int64_t) n * h->ldn, h->X, h->ldn, n, h->xmean, sigma);
+        BB_TRY(launched(ctx, "chol_steps_kernel"));
+    }
+    {
+        // M (lower) = c1 pc pc^T + sum_k coef_k Ystk[k]^T Ystk[k]  over the n columns of A and the mu steps
+        GemmArgs g {};
+        g.A = h->Ystk; g.lda = h->ldn; g.B = h->Ystk; g.ldb = h->ldn;
+        g.M = n; g.N = n; g.K = n + mu; g.kscale = h->coef; g.kscale_padded = true;
+        g.C = h->Mch; g.ldc = h->ldn; g.vec = h->pc; g.s0 = 0.0; g.s1 = c.c1; g.dscal = h->dscal;
+        ProfScope prof(ctx, BBGPU_PROF_COV_SYRK);
+        BB_TRY((launch_gemm<2, EPI_SYRK>(ctx, g)));
+    }
+    ProfScope prof(ctx, BBGPU_PROF_EIG); // the factorisation takes the decomposition's place in the accounting
+    BB_TRY(chol_factor(h));
+    BB_CUDA(cudaStreamWaitEvent(st, h->ev_ch_join, 0)); // the old factor has been read
+    dim3 tgrid(ceil_div(n, 32), ceil_div(n, 32));
+    chol_store_kernel<<<tgrid, 256, 0, st>>>(h->Mch, h->Ystk, n, h->ldn, h->dev_info, h->d_report);
+    return launched(ctx, "chol_store_kernel");
+}
+
 static int do_update(bbgpu_cma *h, double sigma, int fev) {
+    if (h->chol) return do_update_chol(h, sigma);
     bbgpu_ctx *ctx = h->ctx;
     const bbgpu_cma_config &c = h->cfg;
     const int n = h->n, mu = h->mu;
@@ -1022,8 +1101,14 @@ static int field_info(bbgpu_cma *h, int field, double **ptr, int64_t *rows, int6
     case BBGPU_CMA_XOLD: *ptr = h->xold; *rows = 1; *cols = n; break;
     case BBGPU_CMA_PC: *ptr = h->pc; *rows = 1; *cols = n; break;
     case BBGPU_CMA_PS: *ptr = h->ps; *rows = 1; *cols = n; break;
-    case BBGPU_CMA_D: *ptr = h->D; *rows = 1; *cols = n; break;
+    case BBGPU_CMA_D:
+        if (h->chol) return fail(BBGPU_ERR_ARG, "Cholesky-CMA-ES has no D");
+        *ptr = h->D; *rows = 1; *cols = n; break;
+    case BBGPU_CMA_A:
+        if (!h->chol) return fail(BBGPU_ERR_ARG, "only Cholesky-CMA-ES has a factor A");
+        *ptr = h->Ystk; *rows = n; *cols = n; *ld = h->ldn; break;
     case BBGPU_CMA_C:
+        if (h->chol) return fail(BBGPU_ERR_ARG, "Cholesky-CMA-ES keeps the factor A, not C");
         if (h->full) { *ptr = h->C; *rows = n; *cols = n; *ld = h->ldn; }
         else { *ptr = h->C; *rows = 1; *cols = n; }
         break;
@@ -1063,11 +1148,12 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
         const double *h_upper, bbgpu_cma **out) {
     BB_ARG(ctx && cfg && h_weights && out);
     BB_ARG(cfg->n >= 1 && cfg->lambda >= 2 && cfg->mu >= 1 && cfg->mu <= cfg->lambda);
-    BB_ARG(cfg->kind >= BBGPU_CMA_FULL && cfg->kind <= BBGPU_CMA_SEP);
+    BB_ARG(cfg->kind >= BBGPU_CMA_FULL && cfg->kind <= BBGPU_CMA_CHOLESKY);
     BB_ARG(!cfg->bound || (h_lower && h_upper));
     if (cfg->shard_count > 1) {
         BB_ARG(cfg->shard_rank >= 0 && cfg->shard_rank < cfg->shard_count);
-        if (cfg->kind == BBGPU_CMA_SEP) return fail(BBGPU_ERR_ARG, "candidate sharding covers the full-covariance kinds");
+        if (cfg->kind == BBGPU_CMA_SEP || cfg->kind == BBGPU_CMA_CHOLESKY)
+            return fail(BBGPU_ERR_ARG, "candidate sharding covers the full-covariance kinds");
         if (cfg->lambda % cfg->shard_count != 0 || cfg->lambda / cfg->shard_count < 2)
             return fail(BBGPU_ERR_ARG, "lambda = %d does not split into %d equal shards of at least 2", cfg->lambda, cfg->shard_count);
     }
@@ -1078,8 +1164,9 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     h->n = cfg->n;
     h->lambda = cfg->lambda;
     h->mu = cfg->mu;
-    h->full = cfg->kind != BBGPU_CMA_SEP;
+    h->full = cfg->kind == BBGPU_CMA_FULL || cfg->kind == BBGPU_CMA_ACTIVE;
     h->active = cfg->kind == BBGPU_CMA_ACTIVE;
+    h->chol = cfg->kind == BBGPU_CMA_CHOLESKY;
     h->nsel = h->active ? 2 * h->mu : h->mu;
     if (h->active && 2 * h->mu > h->lambda) { delete h; return fail(BBGPU_ERR_ARG, "active CMA-ES needs 2 mu <= lambda"); }
     h->ldn = round_up(h->n, 8);
@@ -1100,7 +1187,7 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     };
     A(&h->xmean, ldn); A(&h->xold, ldn); A(&h->pc, ldn); A(&h->ps, ldn); A(&h->D, ldn); A(&h->dm, ldn);
     A(&h->tmpn, ldn); A(&h->W, ldn); A(&h->weights, h->mu); A(&h->lower, ldn); A(&h->upper, ldn);
-    A(&h->coef, (size_t) round_up(h->nsel, 32) + 32); A(&h->ycoeff, (size_t) h->mu); A(&h->dscal, 8);
+    A(&h->coef, (size_t) round_up(h->chol ? h->n + h->mu : h->nsel, 32) + 32); A(&h->ycoeff, (size_t) h->mu); A(&h->dscal, 8);
     A(&h->X, laml * ldn); A(&h->Zbuf[0], laml * ldn); A(&h->Zbuf[1], laml * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
     A(&h->part, (size_t) h->splits * 2 * n);
     if (h->full) {
@@ -1119,6 +1206,16 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
                 h->rowsq_tiles_cap = ceil_div(n, 64);
                 A(&h->rowsq_part, (size_t) h->rowsq_tiles_cap * h->mu);
             }
+        }
+    } else if (h->chol) {
+        A(&h->Ystk, (size_t) (n + h->mu) * ldn); A(&h->Mch, (size_t) n * ldn); A(&h->Lt, (size_t) CH_NB * ldn);
+        A(&h->negone, (size_t) CH_NB + 32); A(&h->rnorm, lam); A(&h->rstat, 8);
+        if (rc == BBGPU_OK && (cudaEventCreateWithFlags(&h->ev_ch_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev_ch_join, cudaEventDisableTiming) != cudaSuccess))
+            rc = fail(BBGPU_ERR_CUDA, "cudaEventCreate failed");
+        if (rc == BBGPU_OK) {
+            fill_kernel<<<1, 64, 0, ctx->stream>>>(h->negone, CH_NB, -1.0);
+            rc = launched(ctx, "fill_kernel");
         }
     } else {
         A(&h->C, ldn);
@@ -1162,7 +1259,10 @@ int bbgpu_cma_destroy(bbgpu_cma *h) {
     }
     double *bufs[] = { h->xmean, h->xold, h->pc, h->ps, h->D, h->dm, h->tmpn, h->W, h->weights, h->lower, h->upper, h->coef,
             h->ycoeff, h->dscal, h->X, h->Zbuf[0], h->Zbuf[1], h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
-            h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc, h->own_ws };
+            h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc, h->own_ws,
+            h->Ystk, h->Mch, h->Lt, h->negone, h->rnorm, h->rstat };
+    if (h->ev_ch_fork) cudaEventDestroy(h->ev_ch_fork);
+    if (h->ev_ch_join) cudaEventDestroy(h->ev_ch_join);
     if (h->own_info) cudaFree(h->own_info);
     if (h->ev_eig_fork) cudaEventDestroy(h->ev_eig_fork);
     if (h->ev_eig_join) cudaEventDestroy(h->ev_eig_join);
@@ -1199,6 +1299,10 @@ int bbgpu_cma_reset(bbgpu_cma *h, const double *h_guess, int keep_offdiag) {
         BB_TRY(launched(ctx, "fill_identity_kernel"));
         scale_basis_kernel<<<n, 256, 0, st>>>(h->Bt, h->D, h->BDt, h->BDit, n, h->ldn);
         BB_TRY(launched(ctx, "scale_basis_kernel"));
+    } else if (h->chol) {
+        dim3 grid(ceil_div(n, 256), n);
+        fill_identity_kernel<<<grid, 256, 0, st>>>(h->Ystk, n, h->ldn, false); // A = I (cholesky_cmaes.cpp:44-51 clears it)
+        BB_TRY(launched(ctx, "fill_identity_kernel"));
     } else {
         fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(h->C, n, 1.0);
         BB_TRY(launched(ctx, "fill_kernel"));
@@ -1214,13 +1318,14 @@ int bbgpu_cma_set(bbgpu_cma *h, int field, const double *h_src, int64_t count) {
     BB_TRY(field_info(h, field, &ptr, &rows, &cols, &ld));
     BB_ARG(count == rows * cols);
     cudaStream_t st = h->ctx->stream;
-    if (field == BBGPU_CMA_B) {
+    if (field == BBGPU_CMA_B || field == BBGPU_CMA_A) { // stored transposed (k-major operand)
         std::vector<double> t((size_t) count);
         const int n = h->n;
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) t[(size_t) j * n + i] = h_src[(size_t) i * n + j];
         BB_CUDA(cudaMemcpy2DAsync(ptr, (size_t) ld * 8, t.data(), (size_t) cols * 8, (size_t) cols * 8, rows, cudaMemcpyHostToDevice, st));
         BB_CUDA(cudaStreamSynchronize(st));
+        if (field == BBGPU_CMA_A) return BBGPU_OK;
         scale_basis_kernel<<<n, 256, 0, st>>>(h->Bt, h->D, h->BDt, h->BDit, n, h->ldn);
         BB_TRY(launched(h->ctx, "scale_basis_kernel"));
         BB_CUDA(cudaStreamSynchronize(st));
@@ -1245,7 +1350,7 @@ int bbgpu_cma_get(bbgpu_cma *h, int field, double *h_dst, int64_t count) {
     cudaStream_t st = h->ctx->stream;
     BB_CUDA(cudaMemcpy2DAsync(h_dst, (size_t) cols * 8, ptr, (size_t) ld * 8, (size_t) cols * 8, rows, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
-    if (field == BBGPU_CMA_B) {
+    if (field == BBGPU_CMA_B || field == BBGPU_CMA_A) {
         const int n = h->n;
         for (int i = 0; i < n; i++)
             for (int j = i + 1; j < n; j++) std::swap(h_dst[(size_t) i * n + j], h_dst[(size_t) j * n + i]);
@@ -1261,7 +1366,7 @@ int bbgpu_cma_get_rank(bbgpu_cma *h, int32_t *h_idx, int count) {
 }
 
 int bbgpu_cma_get_rows(bbgpu_cma *h, int field, int64_t row0, int64_t rows, double *h_dst) {
-    BB_ARG(h && h_dst && field != BBGPU_CMA_B);
+    BB_ARG(h && h_dst && field != BBGPU_CMA_B && field != BBGPU_CMA_A);
     double *ptr;
     int64_t nrows, cols, ld;
     BB_TRY(field_info(h, field, &ptr, &nrows, &cols, &ld));
@@ -1382,8 +1487,25 @@ int bbgpu_cma_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
     return do_eig(h, h_B, h_D);
 }
 
+// CholeskyCmaes::converged(), the O(lambda n) part (cholesky_cmaes.cpp:146-160): mean and M2 = sum (r_k - mean)^2 of
+// the candidates' Euclidean norms
+int bbgpu_cma_swarm_radius(bbgpu_cma *h, double *h_mean, double *h_m2) {
+    BB_ARG(h && h->chol && h_mean && h_m2);
+    cudaStream_t st = h->ctx->stream;
+    row_norms_kernel<<<ceil_div(h->lambda, 8), 256, 0, st>>>(h->X, h->ldn, h->n, h->lambda, h->rnorm);
+    BB_TRY(launched(h->ctx, "row_norms_kernel"));
+    radius_stats_kernel<<<1, 1024, 0, st>>>(h->rnorm, h->lambda, h->rstat);
+    BB_TRY(launched(h->ctx, "radius_stats_kernel"));
+    double out[2];
+    BB_CUDA(cudaMemcpyAsync(out, h->rstat, 16, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    *h_mean = out[0];
+    *h_m2 = out[1];
+    return BBGPU_OK;
+}
+
 int bbgpu_cma_probe(bbgpu_cma *h, double sigma, int iaxis) {
-    BB_ARG(h && iaxis >= 0 && iaxis < h->n);
+    BB_ARG(h && iaxis >= 0 && iaxis < h->n && !h->chol);
     if (h->full) probe_kernel<false><<<1, 1024, 0, h->ctx->stream>>>(h->n, h->ldn, h->xmean, h->pc, h->C, h->D, h->Bt, sigma, iaxis, h->d_report);
     else probe_kernel<true><<<1, 1024, 0, h->ctx->stream>>>(h->n, h->ldn, h->xmean, h->pc, h->C, h->D, nullptr, sigma, iaxis, h->d_report);
     return launched(h->ctx, "probe_kernel");
@@ -1400,7 +1522,7 @@ int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *out) {
 
 int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint64_t generation, int ik, int fev_after) {
     BB_ARG(h && obj && obj->n == h->n);
-    if (!h->full && obj->mode == 0 && obj->id != BBGPU_OBJ_ROSENBROCK) {
+    if (!h->full && !h->chol && obj->mode == 0 && obj->id != BBGPU_OBJ_ROSENBROCK) {
         // separable kind, registry objective: draws, sampling and evaluation fused into one pass over X
         bbgpu_ctx *ctx = h->ctx;
         const double *lo = h->cfg.bound ? h->lower : nullptr, *hi = h->cfg.bound ? h->upper : nullptr;

@@ -111,9 +111,10 @@ void BaseCmaes::fillConfig(bbgpu_cma_config &cfg) const {
 // the diagonals are set back to 1, and `_invsqrtc` is cleared): carried over here.
 void BaseCmaes::ensureDevice() {
     bbgpu_ctx *ctx = bbopt::device_context();
-    const bool full = deviceKind() != BBGPU_CMA_SEP;
+    const bool full = deviceKind() == BBGPU_CMA_FULL || deviceKind() == BBGPU_CMA_ACTIVE;
     std::vector<double> oldC, oldB;
-    const bool carry = full && _dev != nullptr && _dev_used && _dev_n == _n && _dev_kind != BBGPU_CMA_SEP;
+    const bool carry = full && _dev != nullptr && _dev_used && _dev_n == _n &&
+            (_dev_kind == BBGPU_CMA_FULL || _dev_kind == BBGPU_CMA_ACTIVE);
     if (carry) {
         oldC.resize((size_t) _n * _n);
         oldB.resize((size_t) _n * _n);
@@ -255,7 +256,8 @@ std::vector<double> BaseCmaes::state(const std::string &name) {
             { "ps", BBGPU_CMA_PS, n }, { "D", BBGPU_CMA_D, n }, { "C", BBGPU_CMA_C, full ? n * n : n },
             { "B", BBGPU_CMA_B, n * n }, { "invsqrtC", BBGPU_CMA_INVSQRTC, n * n }, { "arx", BBGPU_CMA_ARX, lam * n },
             { "z", BBGPU_CMA_Z, lam * n }, { "fitness", BBGPU_CMA_FITNESS, lam }, { "rankval", BBGPU_CMA_RANKVAL, lam },
-            { "ycoeff", BBGPU_CMA_YCOEFF, (int64_t) _mu }, { "weights", BBGPU_CMA_WEIGHTS, (int64_t) _mu } };
+            { "ycoeff", BBGPU_CMA_YCOEFF, (int64_t) _mu }, { "weights", BBGPU_CMA_WEIGHTS, (int64_t) _mu },
+            { "A", BBGPU_CMA_A, n * n } };
     if (name == "rank") {
         std::vector<int32_t> idx(_lambda);
         gpu_check(bbgpu_cma_get_rank(_dev, idx.data(), _lambda));
@@ -410,4 +412,27 @@ bool SepCmaes::converged() {
     if (_rep.noeffect_axis) { _flag = 8; return true; }
     if (_rep.noeffect_coor) { _flag = 9; return true; }
     return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// CholeskyCmaes -- cma/cholesky_cmaes.cpp:40-52, 54-118, 137-161
+// ---------------------------------------------------------------------------------------
+void CholeskyCmaes::init(const multivariate_problem &f, const double *guess) {
+    BaseCmaes::init(f, guess);
+    ensureDevice(); // A = I: the reference clears `_a` on every init (:45-51), nothing is carried over a restart
+}
+
+void CholeskyCmaes::updateDistribution() {
+    gpu_check(bbgpu_cma_update(_dev, _sigma, _fev));
+    fetchReport();
+    updateSigma();
+}
+
+bool CholeskyCmaes::converged() {
+    if (!_rep_fresh) fetchReport();
+    if (std::abs(_ybw[0] - _ybw[3]) > _tol) return false;
+    // standard deviation of the candidates' radii (:146-160): M2 <= (lambda - 1) stol^2
+    double mean = 0., m2 = 0.;
+    gpu_check(bbgpu_cma_swarm_radius(_dev, &mean, &m2));
+    return m2 <= (_lambda - 1) * _stol * _stol;
 }

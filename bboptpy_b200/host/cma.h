@@ -2,7 +2,7 @@
 //
 // Same class names, constructor signatures, public virtuals and semantics as the reference
 // (/root/reference/src/multivariate/cma/base_cmaes.h:50-92, cmaes.h:40-70,
-// active_cmaes.h:40-56, sep_cmaes.h:37-61).  The host keeps what the reference keeps in scalars
+// active_cmaes.h:40-56, sep_cmaes.h:37-61, cholesky_cmaes.h:32-58).  The host keeps what the reference keeps in scalars
 // (sigma, counters, history rings, stop flags); the vectors and matrices live on the GPU.
 #ifndef BBOPT_HOST_CMA_H_
 #define BBOPT_HOST_CMA_H_
@@ -148,6 +148,23 @@ public:
     void updateDistribution();
     bool converged();
     int flag() const { return _flag; }
+};
+
+// cma/cholesky_cmaes.h:32-58.  The factor A lives on the device; the reference's mu + 1 sequential rank-one updates are
+// one SYRK + one Cholesky factorisation there (csrc/chol.cuh), so a generation needs no eigendecomposition.
+class CholeskyCmaes: public BaseCmaes {
+protected:
+    double _stol;
+    int deviceKind() const override { return BBGPU_CMA_CHOLESKY; }
+
+public:
+    CholeskyCmaes(int mfev, double tol, double stol, int np, double sigma0 = 2., bool bound = false) :
+            BaseCmaes(mfev, tol, np, sigma0, bound) {
+        _stol = stol;
+    }
+    void init(const multivariate_problem &f, const double *guess);
+    void updateDistribution();
+    bool converged();
 };
 
 #endif

@@ -173,6 +173,11 @@ PYBIND11_MODULE(_bboptpy, m) {
              "bound"_a = false, "adjustlr"_a = true)
         .def_property_readonly("flag", &SepCmaes::flag);
 
+    // py/multivariate_py.cpp:117-121
+    py::class_<CholeskyCmaes, BaseCmaes>(m, "CholeskyCMAES")
+        .def(py::init<int, double, double, int, double, bool>(), "mfev"_a, "tol"_a, "stol"_a, "np"_a, "sigma0"_a = 2.,
+             "bound"_a = false);
+
     py::class_<IPopCmaes, MultivariateOptimizer>(m, "IPopCMAES")
         .def(py::init<BaseCmaes*, int, bool, double, bool, double, bool>(), "base"_a, "mfev"_a, "print"_a = false,
              "sigma0"_a = 2., "nipop"_a = true, "ksigmadec"_a = 1.6, "boundlambda"_a = true, py::keep_alive<1, 2>())

@@ -9,7 +9,8 @@ import numpy as np
 
 
 def cma_constants(kind, n, lam, alphacov=2.0, adjustlr=True, eigenrate=0.25):
-    """kind: 0 Cmaes, 1 ActiveCmaes, 2 SepCmaes.  Returns (weights, constants dict)."""
+    """kind: 0 Cmaes, 1 ActiveCmaes, 2 SepCmaes, 3 CholeskyCmaes (the base constants only, cma/cholesky_cmaes.cpp:40-52).
+    Returns (weights, constants dict)."""
     mu = lam // 2
     w = np.array([math.log(0.5 * (lam + 1.0)) - math.log(i + 1.0) for i in range(mu)])
     s = 0.0
@@ -40,6 +41,8 @@ def cma_constants(kind, n, lam, alphacov=2.0, adjustlr=True, eigenrate=0.25):
         c["cneg"] = (1.0 - c["cmu"]) * (alphacov / 8.0) * mueff / (math.pow(n + 2.0, 1.5) + 2.0 * mueff)
         c["damps"] = 1.0 + c["cs"] + 2.0 * max(0.0, math.sqrt((mueff - 1.0) / (n + 1.0)) - 1.0)
         c["eigenfreq"] = eigenrate * (1.0 / (c["c1"] + c["cmu"] + c["cneg"])) / n
+    elif kind == 3:
+        pass
     else:
         c["cc"] = 4.0 / (n + 4.0)
         c["cs"] = (mueff + 2.0) / (3.0 + n + mueff)

@@ -116,7 +116,10 @@ int bbgpu_eval_host(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *h_X, int
                     double *h_f);
 
 /* ---- CMA-ES engine (Cmaes / ActiveCmaes / SepCmaes device state and phases) */
-enum bbgpu_cma_kind { BBGPU_CMA_FULL = 0, BBGPU_CMA_ACTIVE = 1, BBGPU_CMA_SEP = 2 };
+/* BBGPU_CMA_CHOLESKY: cma/cholesky_cmaes.cpp -- the factor A (C = A A^T) instead of C / B / D; sampling x = m + sigma A z on
+ * the same tensor-core GEMM, the mu + 1 sequential rank-one updates of the factor (:85-90,163-177) as one SYRK + one blocked
+ * Cholesky factorisation (the factor is unique), no eigendecomposition at all */
+enum bbgpu_cma_kind { BBGPU_CMA_FULL = 0, BBGPU_CMA_ACTIVE = 1, BBGPU_CMA_SEP = 2, BBGPU_CMA_CHOLESKY = 3 };
 
 typedef struct bbgpu_cma_config {
     int kind;       /* bbgpu_cma_kind */
@@ -152,8 +155,9 @@ enum bbgpu_cma_field {
     BBGPU_CMA_WEIGHTS = 13, /* mu */
     /* candidate-sharded handles only (the two buffers the exchange steps move) */
     BBGPU_CMA_NORMS = 14,     /* lambda, ||C^-1/2 (x_k - m)||^2 by candidate index (active) */
-    BBGPU_CMA_SHARD_RED = 15  /* n*ld + ld: this GPU's rank-mu partial (lower triangle, row pitch
+    BBGPU_CMA_SHARD_RED = 15, /* n*ld + ld: this GPU's rank-mu partial (lower triangle, row pitch
                                  ld = ceil(n/8)*8) followed by its partial sum_k w_k x_k */
+    BBGPU_CMA_A = 16          /* Cholesky kind: n*n, the lower-triangular factor `_a` (cma/cholesky_cmaes.h:36) */
 };
 
 /* everything the host class needs back per generation; filled by bbgpu_cma_fetch */
@@ -163,7 +167,7 @@ typedef struct bbgpu_cma_report {
     double f_kth;   /* fitness[_ik] for the flat-fitness test and the history ring (:183,:198) */
     double pslen;   /* ||p_sigma||_2 after the path update (dnrm2 in cma/base_cmaes.cpp:179) */
     int32_t hsig;
-    int32_t eig_info;     /* 0 = ok */
+    int32_t eig_info;     /* 0 = ok (Cholesky kind: j > 0 = pivot j of the factorisation was not positive) */
     double d_min, d_max;  /* D[0], D[n-1] after the last decomposition (sep: c-ordered ends) */
     double tolx_max;      /* max_i max(pc_i, sqrt(C_ii))        (cma/cmaes.cpp:184-194) */
     int32_t noeffect_axis;/* 1 if NoEffectAxis holds            (cma/cmaes.cpp:208-221) */
@@ -209,6 +213,9 @@ int bbgpu_cma_update(bbgpu_cma *h, double sigma, int fev);
 int bbgpu_cma_eig(bbgpu_cma *h, const double *h_B, const double *h_D);
 /* quantities for converged(): cma/cmaes.cpp:184-229, cma/sep_cmaes.cpp:170-205 */
 int bbgpu_cma_probe(bbgpu_cma *h, double sigma, int iaxis);
+/* Cholesky kind, converged() (cma/cholesky_cmaes.cpp:146-160): mean and M2 = sum_k (r_k - mean)^2 of the candidates'
+ * Euclidean norms r_k (what the reference's Welford recurrence over dnrm2(_arx[k]) accumulates); synchronises */
+int bbgpu_cma_swarm_radius(bbgpu_cma *h, double *h_mean, double *h_m2);
 /* synchronise the stream and return the report of everything enqueued so far */
 int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *out);
 /* one whole generation without host round trips in between (sample -> evaluate -> rank ->

@@ -31,7 +31,8 @@ void bbo_rng_draw(int kind, int count, double a, double b, double *out);
 /* ---- objectives (spec: oracle/objectives_ref.h) */
 double bbo_eval(int obj, int n, const double *x);
 
-/* ---- CMA-ES family.  kind: 0 Cmaes, 1 ActiveCmaes, 2 SepCmaes */
+/* ---- CMA-ES family.  kind: 0 Cmaes, 1 ActiveCmaes, 2 SepCmaes, 3 CholeskyCmaes (its `stol` travels in
+ * the eigenrate argument; cma/cholesky_cmaes.h:44-48) */
 void *bbo_cma_new(int kind, int mfev, double tol, int np, double sigma0, int bound,
                   double eigenrate, double alphacov, int adjustlr);
 void bbo_cma_free(void *h);

@@ -19,7 +19,7 @@ REF_PATH = os.path.join(_HERE, "_ref", "libbbo_ref.so")
 PORT_PATH = os.path.join(_HERE, "libbbo_port.so")
 
 SPHERE, ELLIPSOID, ROSENBROCK, RASTRIGIN, ACKLEY = range(5)
-VANILLA, ACTIVE, SEP = range(3)
+VANILLA, ACTIVE, SEP, CHOLESKY = range(4)
 JADE, SHADE = range(2)
 
 _c_dp = ctypes.c_void_p
@@ -120,7 +120,10 @@ class Oracle:
         return np.array([self.eval(obj, row) for row in X])
 
     def cma(self, kind, mfev, tol, np_, sigma0=2.0, bound=False, eigenrate=0.25, alphacov=2.0,
-            adjustlr=True):
+            adjustlr=True, stol=None):
+        """kind CHOLESKY: `stol` (cholesky_cmaes.h:44) travels in the eigenrate slot of the C API."""
+        if kind == CHOLESKY:
+            eigenrate = 1e-8 if stol is None else stol
         return OracleCma(self, kind, mfev, tol, np_, sigma0, bound, eigenrate, alphacov, adjustlr)
 
     def de(self, kind, mfev, np_, tol, archive=True, repaircr=True, pelite=0.05, cdamp=0.1,
@@ -231,9 +234,14 @@ class OracleCma:
         s = {k: self.geti(k) for k in ("n", "lambda", "mu", "it", "fev", "mit", "hlen", "ik")}
         s.update({k: self.getd(k) for k in ("sigma", "mueff", "cc", "cs", "c1", "cmu", "damps",
                                             "chi", "fbest", "fworst")})
-        for k in ("xmean", "xold", "pc", "ps", "weights", "D", "fit_val", "fit_idx"):
+        for k in ("xmean", "xold", "pc", "ps", "weights", "fit_val", "fit_idx"):
             s[k] = self.getv(k)
         s["arx"] = self.mat("arx")
+        if self.kind == CHOLESKY:
+            s["A"] = self.mat("A")
+            s["dmean"] = self.getv("dmean")
+            return s
+        s["D"] = self.getv("D")
         s["C"] = self.getv("C") if self.kind == SEP else self.mat("C")
         if self.kind != SEP:
             s["B"] = self.mat("B")

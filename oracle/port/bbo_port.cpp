@@ -128,6 +128,8 @@ struct PortCma {
     std::vector<double> ycoeff;
     /* SepCmaes state (sep_cmaes.h:39-43): C and d are length n */
     double ccov = 0;
+    /* CholeskyCmaes state (cholesky_cmaes.h:34-37); stol arrives in the eigenrate argument */
+    std::vector<double> A, mattmp, dmean;
     BboNormal Z;
     /* eigenbasis-replay feed (bbo_cma_eig_log) */
     struct EigEvent { int fev, n; std::vector<double> B, D; };
@@ -176,6 +178,14 @@ struct PortCma {
     /* ---- cma/cmaes.cpp:44-63, cma/active_cmaes.cpp:42-69, cma/sep_cmaes.cpp:40-67 */
     void init(const double *guess) {
         base_init(guess);
+        if (kind == 3) { /* cma/cholesky_cmaes.cpp:40-52 */
+            dmean.assign(n, 0.0);
+            A.assign((size_t) n * n, 0.0);
+            mattmp.assign((size_t) n * n, 0.0);
+            for (int i = 0; i < n; i++) A[(size_t) i * n + i] = 1.0;
+            flag = 0;
+            return;
+        }
         if (kind == 2) {
             cc = 4.0 / (n + 4.0);
             cs = (mueff + 2.0) / (3.0 + n + mueff);
@@ -232,7 +242,16 @@ struct PortCma {
         for (int k = 0; k < lambda; k++) {
             double *x = &arx[(size_t) k * n];
             double *zrow = &last_z[(size_t) k * n];
-            if (kind == 2) {
+            if (kind == 3) { /* cma/cholesky_cmaes.cpp:120-135: x = m + sigma A z, full rows of A */
+                for (int i = 0; i < n; i++) zrow[i] = Z.draw(eng());
+                for (int i = 0; i < n; i++) {
+                    const double *row = &A[(size_t) i * n];
+                    double s = 0.0;
+                    for (int j = 0; j < n; j++) s = s + row[j] * zrow[j];
+                    x[i] = xmean[i] + sigma * s;
+                    if (bound) x[i] = std::max(lower[i], std::min(x[i], upper[i]));
+                }
+            } else if (kind == 2) {
                 for (int i = 0; i < n; i++) {
                     zrow[i] = Z.draw(eng());
                     x[i] = xmean[i] + sigma * d[i] * zrow[i];
@@ -414,9 +433,62 @@ struct PortCma {
         update_sigma();
     }
 
+    /* ---- cma/cholesky_cmaes.cpp:163-177: rank-one update of the factor in mattmp by beta * tmp tmp^T */
+    void chol_rank1(double beta) {
+        double b = 1.0;
+        for (int j = 0; j < n; j++) {
+            const double ajj = mattmp[(size_t) j * n + j];
+            const double alfaj = tmp[j];
+            const double gam = ajj * ajj * b + beta * alfaj * alfaj;
+            const double a1jj = mattmp[(size_t) j * n + j] = std::sqrt(gam / b);
+            for (int k = j + 1; k < n; k++) {
+                tmp[k] -= (alfaj / ajj) * mattmp[(size_t) k * n + j];
+                mattmp[(size_t) k * n + j] = (a1jj / ajj) * mattmp[(size_t) k * n + j] + (a1jj * beta * alfaj) / gam * tmp[k];
+            }
+            b += beta * (alfaj / ajj) * (alfaj / ajj);
+        }
+    }
+
+    /* ---- cma/cholesky_cmaes.cpp:54-118 */
+    void update_chol() {
+        std::copy(xmean.begin(), xmean.end(), xold.begin());
+        for (int i = 0; i < n; i++) {
+            double sum = 0.0;
+            for (int k = 0; k < mu; k++) sum += weights[k] * arx[(size_t) rank[k].index * n + i];
+            xmean[i] = sum;
+            if (bound) xmean[i] = std::max(lower[i], std::min(xmean[i], upper[i]));
+            dmean[i] = (xmean[i] - xold[i]) / sigma;
+        }
+        const double ccc = std::sqrt(cc * (2.0 - cc) * mueff);
+        for (int i = 0; i < n; i++) pc[i] = (1.0 - cc) * pc[i] + ccc * dmean[i];
+        const double acoeff = std::sqrt(1.0 - c1 - cmu);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j <= i; j++) mattmp[(size_t) i * n + j] = acoeff * A[(size_t) i * n + j];
+        std::copy(pc.begin(), pc.end(), tmp.begin());
+        chol_rank1(c1);
+        /* the reference walks the FIRST mu candidates by index (not by rank) against the NEW mean (:85-90): kept */
+        for (int i = 0; i < mu; i++) {
+            for (int j = 0; j < n; j++) tmp[j] = (arx[(size_t) i * n + j] - xmean[j]) / sigma;
+            chol_rank1(cmu * weights[i]);
+        }
+        /* A(t)^-1 (m(t+1) - m(t)) / sigma with the OLD factor (:93-98) */
+        std::copy(dmean.begin(), dmean.end(), tmp.begin());
+        for (int i = 0; i < n; i++) {
+            double s = 0.0;
+            for (int j = 0; j < i; j++) s = s + A[(size_t) i * n + j] * tmp[j];
+            tmp[i] -= s;
+            tmp[i] /= A[(size_t) i * n + i];
+        }
+        const double csc = std::sqrt(cs * (2.0 - cs) * mueff);
+        for (int i = 0; i < n; i++) ps[i] = (1.0 - cs) * ps[i] + csc * tmp[i];
+        A = mattmp;
+        update_sigma();
+    }
+
     void update() {
         if (kind == 0) update_vanilla();
         else if (kind == 1) update_active();
+        else if (kind == 3) update_chol();
         else update_sep();
     }
 
@@ -637,6 +709,20 @@ struct PortCma {
 
     /* ---- cma/cmaes.cpp:151-227 and cma/sep_cmaes.cpp:137-207 */
     bool converged() {
+        if (kind == 3) { /* cma/cholesky_cmaes.cpp:137-161 */
+            if (std::fabs(ybw[0] - ybw[3]) > tol) return false;
+            int count = 0;
+            double mean = 0.0, m2 = 0.0;
+            for (int k = 0; k < lambda; k++) {
+                const double x = port_nrm2(n, &arx[(size_t) k * n]);
+                count++;
+                const double delta = x - mean;
+                mean += delta / count;
+                const double delta2 = x - mean;
+                m2 += delta * delta2;
+            }
+            return m2 <= (lambda - 1) * eigenrate * eigenrate;
+        }
         if (it >= mit) { flag = 1; return true; }
         if (it >= hlen && fworst - fbest < tol) { flag = 2; return true; }
         if (best.len >= n && kth.len >= n) {
@@ -1091,6 +1177,7 @@ double bbo_cma_getd(void *h, const char *name) {
     if (k == "cm") return p->cm;
     if (k == "alphaold") return p->alphaold;
     if (k == "ccov") return p->ccov;
+    if (k == "stol") return p->eigenrate;
     return NAN;
 }
 
@@ -1111,6 +1198,8 @@ int bbo_cma_getv(void *h, const char *name, double *out, int cap) {
     if (k == "B" && p->kind != 2) return put(p->B, out, cap);
     if (k == "invsqrtC" && p->kind != 2) return put(p->isC, out, cap);
     if (k == "ycoeff" && p->kind == 1) return put(p->ycoeff, out, cap);
+    if (k == "A" && p->kind == 3) return put(p->A, out, cap);
+    if (k == "dmean" && p->kind == 3) return put(p->dmean, out, cap);
     if (k == "ybw") {
         for (int i = 0; i < 4 && i < cap; i++) out[i] = p->ybw[i];
         return 4;

@@ -2,7 +2,7 @@
  * ORACLE (test infrastructure).  Thin C driver around the UNMODIFIED reference sources.
  *
  * Built by oracle/Makefile: this file + /root/reference/src/{blas.cpp,
- * multivariate/cma/{base_cmaes,cmaes,active_cmaes,sep_cmaes,ipop_cmaes,bipop_cmaes}.cpp,
+ * multivariate/cma/{base_cmaes,cmaes,active_cmaes,sep_cmaes,cholesky_cmaes,ipop_cmaes,bipop_cmaes}.cpp,
  * multivariate/de/{jade,shade}.cpp} compiled where they lie -> oracle/_ref/libbbo_ref.so.
  * No reference source is copied into this repository; the headers are included by path.
  *
@@ -26,6 +26,7 @@
 #include "multivariate/cma/cmaes.h"
 #include "multivariate/cma/active_cmaes.h"
 #include "multivariate/cma/sep_cmaes.h"
+#include "multivariate/cma/cholesky_cmaes.h"
 #include "multivariate/cma/ipop_cmaes.h"
 #include "multivariate/cma/bipop_cmaes.h"
 #include "multivariate/de/jade.h"
@@ -95,7 +96,8 @@ struct CmaProbe {
     if (k == "hlen") return this->_hlen;                                                   \
     if (k == "ik") return this->_ik;                                                       \
     if (k == "bound") return this->_bound ? 1 : 0;                                         \
-    if (k == "best_len") return this->_best._len;                                          \
+    if (k == "best_len") return this->_best._len;
+#define FLAG_GETI(k)                                                                       \
     if (k == "flag") return this->_flag;
 
 #define BASE_GETD(k)                                                                       \
@@ -165,6 +167,7 @@ template<class T> struct FullProbe: public T, public CmaProbe {
     }
     int geti(const std::string &k) override {
         BASE_GETI(k)
+        FLAG_GETI(k)
         if (k == "eigenlastev") return this->_eigenlastev;
         return -1;
     }
@@ -209,6 +212,7 @@ struct SepProbe: public SepCmaes, public CmaProbe {
     void reset_z() override { _Z.reset(); }
     int geti(const std::string &k) override {
         BASE_GETI(k)
+        FLAG_GETI(k)
         return -1;
     }
     double getd(const std::string &k) override {
@@ -220,6 +224,29 @@ struct SepProbe: public SepCmaes, public CmaProbe {
         BASE_GETV(k)
         if (k == "D") return copy_out(_diagd, out, cap);
         if (k == "C") return copy_out(_c, out, cap);
+        return -1;
+    }
+};
+
+/* CholeskyCmaes (cholesky_cmaes.h:34-37: _stol, _dmean, _a, _mattmp are protected); it has no _flag */
+struct CholProbe: public CholeskyCmaes, public CmaProbe {
+    using CholeskyCmaes::CholeskyCmaes;
+    BaseCmaes *base() override { return this; }
+    void reset_z() override { _Z.reset(); }
+    int geti(const std::string &k) override {
+        BASE_GETI(k)
+        if (k == "flag") return 0;
+        return -1;
+    }
+    double getd(const std::string &k) override {
+        BASE_GETD(k)
+        if (k == "stol") return _stol;
+        return NAN;
+    }
+    int getv(const std::string &k, double *out, int cap) override {
+        BASE_GETV(k)
+        if (k == "A") return copy_out2(_a, out, cap);
+        if (k == "dmean") return copy_out(_dmean, out, cap);
         return -1;
     }
 };
@@ -335,6 +362,7 @@ void *bbo_cma_new(int kind, int mfev, double tol, int np, double sigma0, int bou
     CmaProbe *p = nullptr;
     if (kind == 0) p = new VanillaProbe(mfev, tol, np, sigma0, bound != 0, eigenrate);
     else if (kind == 1) p = new ActiveProbe(mfev, tol, np, sigma0, bound != 0, alphacov, eigenrate);
+    else if (kind == 3) p = new CholProbe(mfev, tol, /*stol=*/eigenrate, np, sigma0, bound != 0);
     else p = new SepProbe(mfev, tol, np, sigma0, bound != 0, adjustlr != 0);
     return p;
 }

@@ -61,6 +61,7 @@ int bbgpu_cma_rank(bbgpu_cma *, int) { return 0; }
 int bbgpu_cma_update(bbgpu_cma *h, double, int) { h->gen++; h->f *= 0.8; return 0; }
 int bbgpu_cma_eig(bbgpu_cma *, const double *, const double *) { return 0; }
 int bbgpu_cma_probe(bbgpu_cma *, double, int) { return 0; }
+int bbgpu_cma_swarm_radius(bbgpu_cma *, double *mean, double *m2) { *mean = 1.0; *m2 = 1.0; return 0; }
 int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *r) {
     std::memset(r, 0, sizeof(*r));
     for (int q = 0; q < 4; q++) { r->ibw[q] = q; r->ybw[q] = h->f * (1 + q); }

@@ -42,6 +42,9 @@ def test_objectives(ref_oracle, port_oracle):
     (O.VANILLA, O.ROSENBROCK, 60, 128, 20, True, 10.0),
     (O.ACTIVE, O.SPHERE, 33, 64, 40, True, 10.0),
     (O.SEP, O.ELLIPSOID, 1000, 64, 20, False, 10.0),
+    (O.CHOLESKY, O.ROSENBROCK, 10, 20, 300, False, 10.0),
+    (O.CHOLESKY, O.RASTRIGIN, 40, 15, 150, True, 5.12),
+    (O.CHOLESKY, O.ELLIPSOID, 60, 128, 20, False, 10.0),
 ])
 def test_cma_every_generation(ref_oracle, port_oracle, kind, obj, n, lam, gens, bound, box):
     def make(o):
@@ -51,7 +54,9 @@ def test_cma_every_generation(ref_oracle, port_oracle, kind, obj, n, lam, gens, 
         h.init(obj, -box * np.ones(n), box * np.ones(n), guess)
         return h
     r, p = _pair(ref_oracle, port_oracle, make)
-    fields = CMA_FIELDS + (["B", "invsqrtC"] if kind != O.SEP else []) + (["ycoeff"] if kind == O.ACTIVE else [])
+    fields = CMA_FIELDS + (["B", "invsqrtC"] if kind in (O.VANILLA, O.ACTIVE) else []) + (["ycoeff"] if kind == O.ACTIVE else [])
+    if kind == O.CHOLESKY:
+        fields = [k for k in CMA_FIELDS if k not in ("C", "D")] + ["A", "dmean"]
     for g in range(gens):
         r.iterate()
         p.iterate()
@@ -143,7 +148,7 @@ def test_optimize_and_restart_drivers(ref_oracle, port_oracle):
             res.append(o.de(kind, 30000, 40, 1e-6).optimize(O.ROSENBROCK, -10 * np.ones(n), 10 * np.ones(n)))
         assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
     for rk in (0, 1):
-        for bk in (O.VANILLA, O.ACTIVE, O.SEP):
+        for bk in (O.VANILLA, O.ACTIVE, O.SEP, O.CHOLESKY):
             for flag in (True, False):
                 res = []
                 for o in (ref_oracle, port_oracle):
