@@ -20,6 +20,16 @@ namespace bb {
 
 constexpr int CH_NB = 64; // panel width
 
+// 1 / p for a positive, normal p from the 20-bit hardware seed and two Newton steps (~1 ulp): the IEEE division is ~30
+// dependent instructions, and it sits on the column-to-column chain of the factorisation
+__device__ __forceinline__ double rcp_pos(double p) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    r = fma(r, fma(-p, r, 1.0), r);
+    r = fma(r, fma(-p, r, 1.0), r);
+    return r;
+}
+
 // pc <- (1 - cc) pc + ccc dmean   (cholesky_cmaes.cpp:76-79; no hsig), and the SYRK coefficients:
 // coef[k] = acoeff^2 for the n rows of A^T, cmu w_i for the mu steps, 0 in the pad
 __global__ void __launch_bounds__(256) chol_paths_kernel(int n, int mu, double *__restrict__ pc, const double *__restrict__ dm,
@@ -38,66 +48,105 @@ __global__ void __launch_bounds__(256) chol_steps_kernel(double *__restrict__ Y,
     for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = __ddiv_rn(__dsub_rn(x[i], m[i]), sigma);
 }
 
-// One panel of the blocked Cholesky of M (lower, row-major, pitch ld): every CTA factors the nb x nb diagonal block at k0
-// redundantly in shared memory (no exchange between CTAs), CTA b then solves its 64 rows of the panel below,
+// One panel of the blocked Cholesky of M (lower, row-major, pitch ld), 256 threads per CTA.  Every CTA factors the nb x nb
+// diagonal block at k0 redundantly (no exchange between CTAs), CTA b then solves its 64 rows of the panel below,
 // X L11^T = M21, and writes them twice: in place (row-major) and transposed into Lt (k-major, the SYRK operand of the
 // trailing update).  CTA 0 writes L11 back.  info: first non-positive pivot (1-based), 0 = ok.
+// Both stages keep the rows in registers -- four threads per row, thread (i, q) owns columns 4u + q -- and are
+// right-looking, so the work between two dependent steps is a run of independent FMAs (the first version updated the
+// trailing block in shared memory: 78 us per panel of dependent shared-memory round trips; one thread per row with the
+// 64 x 64 loops unrolled: 85 us of straight-line code).  Factorisation, column j: the owners publish their still
+// unscaled entries a_i[j] (row j: the pivot p), ONE barrier, then a_i[t] -= a_i[j] a_t[j] / p for the rest of the row;
+// the scaling L[i][j] = a_i[j] / sqrt(p) happens once at the end, off the chain.
 __global__ void __launch_bounds__(256) chol_panel_kernel(double *__restrict__ M, int64_t ld, int n, int k0, int nb,
         double *__restrict__ Lt, int *__restrict__ info) {
-    __shared__ double S[CH_NB][CH_NB + 1];
+    __shared__ double S[CH_NB][CH_NB + 1]; // the factored diagonal block (lower)
+    __shared__ double col[2][CH_NB];
+    __shared__ double piv[CH_NB], invd[CH_NB];
     __shared__ int bad;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, i = tid >> 2, q = tid & 3;
+    constexpr int NU = CH_NB / 4;
+    double a[NU];
     if (tid == 0) bad = 0;
-    for (int q = tid; q < CH_NB * CH_NB; q += 256) {
-        const int i = q / CH_NB, j = q % CH_NB;
-        S[i][j] = (i < nb && j <= i) ? M[(int64_t) (k0 + i) * ld + k0 + j] : 0.0;
+    {
+        const double *row = M + (int64_t) (k0 + min(i, nb - 1)) * ld + k0;
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const int t = 4 * u + q;
+            a[u] = (i < nb && t <= i) ? row[t] : (t == i ? 1.0 : 0.0); // identity beyond nb
+        }
     }
     __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;
-    for (int j = 0; j < nb; j++) {
-        if (tid == 0) {
-            const double p = S[j][j];
-            if (!(p > 0.0)) bad = bad ? bad : j + 1;
-            const double dj = sqrt(p > 0.0 ? p : 1.0);
-            S[j][j] = dj;
+#pragma unroll
+    for (int u0 = 0; u0 < NU; u0++) {
+#pragma unroll
+        for (int q0 = 0; q0 < 4; q0++) {
+            const int j = 4 * u0 + q0;
+            double *cj = col[j & 1];
+            if (q == q0) cj[i] = a[u0];
+            __syncthreads();
+            const double p = cj[j];
+            if (tid == 0) {
+                if (!(p > 0.0) && bad == 0) bad = j + 1;
+                piv[j] = p > 0.0 ? p : 1.0;
+            }
+            const double aij = cj[i] * rcp_pos(p > 0.0 ? p : 1.0);
+#pragma unroll
+            for (int u = u0; u < NU; u++) {
+                const int t = 4 * u + q;
+                if (t > j) a[u] -= aij * cj[t];
+            }
         }
-        __syncthreads();
-        if (tid > j && tid < nb) S[tid][j] = S[tid][j] / S[j][j];
-        __syncthreads();
-        // trailing lower triangle: (i, t), j < t <= i < nb
-        for (int i = j + 1 + ty; i < nb; i += 16) {
-            const double lij = S[i][j];
-            for (int t = j + 1 + tx; t <= i; t += 16) S[i][t] -= lij * S[t][j];
-        }
-        __syncthreads();
     }
+    __syncthreads();
+    if (tid < CH_NB) {
+        const double sq = sqrt(piv[tid]);
+        piv[tid] = sq;          // now the diagonal of the factor
+        invd[tid] = 1.0 / sq;
+    }
+    __syncthreads();
     if (bad && blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, k0 + bad);
-    if (blockIdx.x == 0) {
-        for (int q = tid; q < CH_NB * CH_NB; q += 256) {
-            const int i = q / CH_NB, j = q % CH_NB;
-            if (i < nb && j <= i) M[(int64_t) (k0 + i) * ld + k0 + j] = S[i][j];
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+        const int t = 4 * u + q;
+        const double l = t < i ? a[u] * invd[t] : (t == i ? piv[t] : 0.0);
+        S[i][t] = l;
+        if (blockIdx.x == 0 && i < nb && t <= i) M[(int64_t) (k0 + i) * ld + k0 + t] = l;
+    }
+    __syncthreads();
+    // the panel below: the four threads of row r hold x; x_c comes from its owner by a shuffle inside the quad, then every
+    // thread updates its own entries with independent FMAs
+    const int r = k0 + nb + blockIdx.x * CH_NB + i;
+    const bool live = r < n;
+    double *row = M + (int64_t) (live ? r : 0) * ld + k0;
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+        const int c = 4 * u + q;
+        a[u] = (live && c < nb) ? row[c] : 0.0;
+    }
+    const int quad = (tid & 31) & ~3;
+#pragma unroll
+    for (int u0 = 0; u0 < NU; u0++) {
+#pragma unroll
+        for (int q0 = 0; q0 < 4; q0++) {
+            const int c = 4 * u0 + q0;
+            const double mine = a[u0] * invd[c];
+            const double xc = __shfl_sync(0xffffffffu, mine, quad | q0);
+            if (q == q0) a[u0] = xc;
+#pragma unroll
+            for (int u = u0; u < NU; u++) {
+                const int t = 4 * u + q;
+                if (t > c) a[u] -= xc * S[t][c];
+            }
         }
     }
-    // the panel below: thread r owns row r0 + r, its nb entries in registers; column-oriented substitution (after x_c is
-    // known the remaining entries are updated by independent FMAs)
-    const int r = k0 + nb + blockIdx.x * CH_NB + tid;
-    if (tid < CH_NB && r < n) {
-        double x[CH_NB];
-        double *row = M + (int64_t) r * ld + k0;
+    if (live) {
 #pragma unroll
-        for (int c = 0; c < CH_NB; c++) x[c] = c < nb ? row[c] : 0.0;
-#pragma unroll
-        for (int c = 0; c < CH_NB; c++) {
-            const double xc = c < nb ? x[c] / S[c][c] : 0.0;
-            x[c] = xc;
-#pragma unroll
-            for (int t = c + 1; t < CH_NB; t++) x[t] -= xc * S[t][c];
-        }
-#pragma unroll
-        for (int c = 0; c < CH_NB; c++) {
+        for (int u = 0; u < NU; u++) {
+            const int c = 4 * u + q;
             if (c < nb) {
-                row[c] = x[c];
-                Lt[(int64_t) c * ld + r] = x[c];
+                row[c] = a[u];
+                Lt[(int64_t) c * ld + r] = a[u];
             }
         }
     }
@@ -128,7 +177,7 @@ __global__ void __launch_bounds__(256) chol_store_kernel(const double *__restric
 // v = A^-1 dmean with the factor stored as At (row j = column j of A), then p_sigma <- (1 - cs) p_sigma + csc v and
 // ||p_sigma|| into the report (cholesky_cmaes.cpp:93-104, base_cmaes.cpp:179).  One CTA: 32-column blocks, the diagonal
 // triangle by warp 0, the rest of the right-hand side by all threads (coalesced along the rows of At).
-__global__ void __launch_bounds__(1024) chol_ps_kernel(const double *__restrict__ At, int64_t ld, int n, const double *__restrict__ dm,
+__global__ void __launch_bounds__(512) chol_ps_kernel(const double *__restrict__ At, int64_t ld, int n, const double *__restrict__ dm,
         double *__restrict__ ps, double cs, double csc, bbgpu_cma_report *rep) {
     extern __shared__ double rhs[]; // n, then 32 solved values, then 32 reduction slots
     double *vblk = rhs + n, *red = vblk + 32;
@@ -138,19 +187,34 @@ __global__ void __launch_bounds__(1024) chol_ps_kernel(const double *__restrict_
     for (int j0 = 0; j0 < n; j0 += 32) {
         const int nb = min(32, n - j0);
         if (tid < 32) {
+            // lane l keeps A[j0+l][j0+c], c = 0..31 (row c of the At block, element l): 32 independent loads up front, so the
+            // substitution chain below runs on registers (with the loads inside it every step paid an L2 round trip: 1 ms)
+            double acol[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) acol[c] = (c < nb && lane < nb) ? At[(int64_t) (j0 + c) * ld + j0 + lane] : (c == lane ? 1.0 : 0.0);
             double rl = lane < nb ? rhs[j0 + lane] : 0.0;
-            for (int c = 0; c < nb; c++) {
-                const double dcc = At[(int64_t) (j0 + c) * ld + j0 + c];
-                const double vc = __shfl_sync(0xffffffffu, rl, c) / dcc;
-                if (lane == c) rl = vc;
-                else if (lane > c && lane < nb) rl -= At[(int64_t) (j0 + c) * ld + j0 + lane] * vc;
+            double dgl = 1.0; // this lane's diagonal entry A[j0+lane][j0+lane]
+#pragma unroll
+            for (int c = 0; c < 32; c++) dgl = c == lane ? acol[c] : dgl;
+            const double idg = 1.0 / dgl; // one division per lane, off the chain: row l of D^-1 A v = D^-1 rhs
+            rl *= idg;
+#pragma unroll
+            for (int c = 0; c < 32; c++) acol[c] *= idg;
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const double vc = __shfl_sync(0xffffffffu, rl, c);
+                if (lane > c) rl -= acol[c] * vc;
             }
             if (lane < nb) { vblk[lane] = rl; rhs[j0 + lane] = rl; }
         }
         __syncthreads();
-        for (int i = j0 + 32 + tid; i < n; i += blockDim.x) {
+        for (int i = j0 + 32 + tid; i < n; i += blockDim.x) { // nb == 32 here (a shorter last block has nothing below it)
+            double ai[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) ai[c] = At[(int64_t) (j0 + c) * ld + i]; // 32 loads in flight, one L2 round trip
             double s = rhs[i];
-            for (int c = 0; c < nb; c++) s -= At[(int64_t) (j0 + c) * ld + i] * vblk[c];
+#pragma unroll
+            for (int c = 0; c < 32; c++) s -= ai[c] * vblk[c];
             rhs[i] = s;
         }
         __syncthreads();

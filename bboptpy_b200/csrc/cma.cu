@@ -814,7 +814,7 @@ static int do_update_chol(bbgpu_cma *h, double sigma) {
         BB_CUDA(cudaStreamWaitEvent(ctx->aux, h->ev_ch_fork, 0));
         if ((size_t) (n + 64) * 8 > 48 * 1024)
             BB_CUDA(cudaFuncSetAttribute(chol_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((n + 64) * 8)));
-        chol_ps_kernel<<<1, 1024, (size_t) (n + 64) * 8, ctx->aux>>>(h->Ystk, h->ldn, n, h->dm, h->ps, c.cs, csc, h->d_report);
+        chol_ps_kernel<<<1, 512, (size_t) (n + 64) * 8, ctx->aux>>>(h->Ystk, h->ldn, n, h->dm, h->ps, c.cs, csc, h->d_report);
         BB_TRY(launched(ctx, "chol_ps_kernel"));
         BB_CUDA(cudaEventRecord(h->ev_ch_join, ctx->aux));
         chol_steps_kernel<<<mu, 256, 0, st>>>(h->Ystk + (int64_t) n * h->ldn, h->X, h->ldn, n, h->xmean, sigma);

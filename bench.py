@@ -328,6 +328,7 @@ def run_reference(args):
         "phases_ms": {k: float(np.mean([r[k] for r in rows])) * 1e3 for k in ("t_sample", "t_evalsort", "t_update_incl_eig")},
         "timed_region_s": timed_s,
         "de": de,
+        "cholesky": {"gens_per_s": cpu_chol_sample(o), "sample": "1 whole generation of CholeskyCmaes, n=1000 lambda=4096, 1 thread"},
         "bipop_batch": cpu_bipop_sample(o),
     }
     print(json.dumps(line))
@@ -400,6 +401,71 @@ def bench_cma_e2e(pkg, gens, seed):
     h2d = (3 * n + lam // 2) * 8 / max(done, 1)           # lower, upper, guess, weights per optimize()
     d2h = 2 * 104 + n * 8 / max(done, 1)                  # report after update + after probe; final x once
     return done / dt, dt, done, h2d, d2h, alg.n_decompositions
+
+
+def bench_chol_device(ctx, steps, warmup, seed):
+    """Cholesky-CMA-ES (cma/cholesky_cmaes.cpp), the reference's eigendecomposition-free variant, at the headline shape
+    n = 1000, lambda = 4096: whole generations/s resident in HBM (sample -> evaluate -> rank -> SYRK over [A^T; Y] -> blocked
+    Cholesky factorisation -> sigma on the host)."""
+    from bboptpy_b200 import _cabi
+    from bboptpy_b200.strategy import cma_constants, update_sigma
+    n, lam = N_DIM, LAMBDA
+    w, c = cma_constants(3, n, lam)
+    g = _cabi.Cma(ctx, _cabi.CMA_CHOLESKY, n, lam, w, c, seed=seed)
+    g.reset(np.random.default_rng(seed).uniform(-BOX, BOX, n))
+    obj = _cabi.Objective(ctx, n, builtin=_cabi.OBJ_ROSENBROCK)
+    state = {"sigma": 2.0, "fev": 0, "gen": 0}
+
+    def step():
+        state["fev"] += lam
+        g.generation(obj, state["sigma"], state["gen"], c["ik"], state["fev"])
+        rep = g.fetch()
+        state["sigma"] = update_sigma(state["sigma"], rep.pslen, c, rep.ybw[0], rep.f_kth)
+        state["gen"] += 1
+        return rep
+
+    for _ in range(warmup):
+        step()
+    ctx.profile_reset()
+    ctx.profile(True)
+    times = []
+    for _ in range(steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        rep = step()
+        times.append(ctx.timer_stop())
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    assert rep.eig_info == 0
+    mu = lam // 2
+    flops = 2.0 * n * n * lam + (n + mu) * n * (n + 1.0) + n ** 3 / 3.0  # sampling GEMM, SYRK over n + mu rows, factorisation
+    ms = float(np.mean(times))
+    return {"ms_per_generation": ms, "gens_per_s": 1e3 / ms, "fbest": rep.ybw[0], "algorithmic_flops_per_generation": flops,
+            "kernel_share_of_step": {k: v["ms_total"] / sum(times) for k, v in prof.items()},
+            "factorisation_ms": prof.get("eig", {}).get("ms_total", 0.0) / max(steps, 1)}
+
+
+def bench_chol_e2e(pkg, gens, seed):
+    n, lam = N_DIM, LAMBDA
+    rng = np.random.default_rng(seed)
+    lower, upper, guess = -BOX * np.ones(n), BOX * np.ones(n), rng.uniform(-BOX, BOX, n)
+    alg = pkg.CholeskyCMAES(mfev=gens * lam, tol=0.0, stol=0.0, np=lam)
+    t0 = time.perf_counter()
+    sol = alg.optimize(pkg.Rosenbrock, lower, upper, guess)
+    dt = time.perf_counter() - t0
+    return (sol.n_evals // lam) / dt
+
+
+def cpu_chol_sample(o, seed=1):
+    """one whole generation of the reference's CholeskyCmaes at n = 1000, lambda = 4096 on one host core"""
+    from oracle import oracle as O
+    o.seed(seed)
+    n = N_DIM
+    h = o.cma(O.CHOLESKY, 10 ** 9, 1e-12, LAMBDA, stol=1e-12)
+    h.init(O.ROSENBROCK, -BOX * np.ones(n), BOX * np.ones(n), o.uniform(-BOX, BOX, n))
+    t0 = time.perf_counter()
+    h.iterate()
+    return 1.0 / (time.perf_counter() - t0)
 
 
 def bench_de_device(ctx, kind, steps, warmup, seed):
@@ -649,6 +715,12 @@ def run_own(args):
     sep = bench_sep_device(ctx, max(5, args.steps // 2), 3, seed=1 + rank)
     t_sep = all_max(dist, local, sep["ms_per_generation"])
     sep["gens_per_s"] = world * 1e3 / t_sep
+    # the reference's eigendecomposition-free variant at the headline shape
+    chol = bench_chol_device(ctx, max(5, args.steps // 2), 3, seed=1 + rank)
+    t_ch = all_max(dist, local, chol["ms_per_generation"])
+    chol["gens_per_s"] = world * 1e3 / t_ch
+    bench_chol_e2e(pkg, 2, seed=1 + rank)
+    chol["e2e_gens_per_s"] = world * 1.0 / all_max(dist, local, 1.0 / bench_chol_e2e(pkg, e2e_gens, seed=1 + rank))
     # one large-lambda run sharded by candidates over all GPUs of the job (N > 1 only)
     sharded = None
     pycomm = None
@@ -755,8 +827,11 @@ def run_own(args):
         "best_of": {"f": fbest, "rank": owner},
         "de": de,
         "sep": sep,
+        "cholesky": chol,
         "bipop_batch": bipop,
     }
+    chol["workload"] = "CholeskyCmaes n=1000 lambda=4096 Rosenbrock (cma/cholesky_cmaes.cpp; no eigendecomposition: SYRK + blocked Cholesky)"
+    chol["frac_of_fp64_peak"] = chol["algorithmic_flops_per_generation"] * chol["gens_per_s"] / world / 1e12 / peak
     if sharded is not None:
         line["sharded_run"] = sharded
     if world == 1:
@@ -769,6 +844,7 @@ def run_own(args):
                                 "gens_per_s_excl_eig": cs["gens_per_s_excl_eig"], "t_eig_s": cs["t_eig"],
                                 "t_generation_s": cs["t_generation"],
                                 "de_jade_evals_per_s": cpu_de_sample(o, 0), "de_shade_evals_per_s": cpu_de_sample(o, 1),
+                                "cholesky_gens_per_s": cpu_chol_sample(o),
                                 "bipop_batch": cpu_bipop_sample(o)}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
