@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <iostream>
 #include <limits>
 
@@ -274,6 +275,126 @@ std::vector<double> BaseCmaes::state(const std::string &name) {
 }
 
 // ---------------------------------------------------------------------------------------
+// checkpoint / resume
+// ---------------------------------------------------------------------------------------
+// One walk over the fields serves both directions: a StateIO either appends to a blob or reads from one.
+struct BaseCmaes::StateIO {
+    std::string *out = nullptr;      // writing
+    const std::string *in = nullptr; // reading
+    size_t pos = 0;
+    bool writing() const { return out != nullptr; }
+    void raw(void *p, size_t bytes) {
+        if (out) out->append(static_cast<const char*>(p), bytes);
+        else {
+            if (pos + bytes > in->size()) throw bbopt::GpuError("checkpoint: truncated blob");
+            std::memcpy(p, in->data() + pos, bytes);
+            pos += bytes;
+        }
+    }
+    template<typename T> void pod(T &v) { raw(&v, sizeof(T)); }
+    void flag(bool &b) { uint8_t v = b ? 1 : 0; pod(v); b = v != 0; }
+    template<typename T> void vec(std::vector<T> &v) {
+        uint64_t len = v.size();
+        pod(len);
+        if (!out) {
+            if (len > (in->size() - pos) / sizeof(T)) throw bbopt::GpuError("checkpoint: corrupt vector length");
+            v.resize((size_t) len);
+        }
+        if (len) raw(v.data(), (size_t) len * sizeof(T));
+    }
+    void ring(cmaes_history &h) { pod(h._cap); pod(h._buffer); pod(h._len); vec(h._hist); }
+};
+
+void BaseCmaes::extraState(StateIO &) {}
+
+namespace {
+const char CK_MAGIC[8] = { 'B', 'B', 'O', 'P', 'T', 'C', 'K', '1' };
+const uint32_t CK_VERSION = 1;
+// device fields per kind, in blob order
+std::vector<int> checkpoint_fields(int kind) {
+    std::vector<int> f = { BBGPU_CMA_XMEAN, BBGPU_CMA_XOLD, BBGPU_CMA_PC, BBGPU_CMA_PS, BBGPU_CMA_ARX, BBGPU_CMA_FITNESS };
+    if (kind == BBGPU_CMA_FULL || kind == BBGPU_CMA_ACTIVE) {
+        // D before B: the engine rebuilds its scaled copies of the basis when either arrives
+        for (int x : { BBGPU_CMA_C, BBGPU_CMA_D, BBGPU_CMA_B, BBGPU_CMA_INVSQRTC }) f.push_back(x);
+    } else if (kind == BBGPU_CMA_SEP) {
+        f.push_back(BBGPU_CMA_C);
+        f.push_back(BBGPU_CMA_D);
+    } else {
+        f.push_back(BBGPU_CMA_A);
+    }
+    return f;
+}
+int64_t field_length(int field, int kind, int64_t n, int64_t lam) {
+    switch (field) {
+    case BBGPU_CMA_ARX: return lam * n;
+    case BBGPU_CMA_FITNESS: return lam;
+    case BBGPU_CMA_C: return kind == BBGPU_CMA_SEP ? n : n * n;
+    case BBGPU_CMA_B: case BBGPU_CMA_INVSQRTC: case BBGPU_CMA_A: return n * n;
+    default: return n;
+    }
+}
+}
+
+std::string BaseCmaes::checkpoint() {
+    if (!_dev) throw bbopt::GpuError("checkpoint: the optimizer has not been initialised");
+    if (_comm && bbgpu_comm_world(_comm) > 1) throw bbopt::GpuError("checkpoint: not available for a candidate-sharded run");
+    std::string blob(CK_MAGIC, CK_MAGIC + 8);
+    StateIO io;
+    io.out = &blob;
+    uint32_t version = CK_VERSION;
+    int32_t kind = deviceKind(), n = _n, lambda = _lambda, mu = _mu;
+    io.pod(version); io.pod(kind); io.pod(n); io.pod(lambda); io.pod(mu);
+    restoreOrSaveScalars(io);
+    for (int f : checkpoint_fields(kind)) {
+        std::vector<double> v((size_t) field_length(f, kind, _n, _lambda));
+        gpu_check(bbgpu_cma_get(_dev, f, v.data(), (int64_t) v.size()));
+        io.vec(v);
+    }
+    return blob;
+}
+
+void BaseCmaes::restore(const std::string &blob) {
+    if (!_dev) throw bbopt::GpuError("restore: initialize(f, lower, upper, guess) the optimizer first");
+    if (blob.size() < 8 || std::memcmp(blob.data(), CK_MAGIC, 8) != 0) throw bbopt::GpuError("restore: not a bboptpy_b200 checkpoint");
+    StateIO io;
+    io.in = &blob;
+    io.pos = 8;
+    uint32_t version = 0;
+    int32_t kind = 0, n = 0, lambda = 0, mu = 0;
+    io.pod(version); io.pod(kind); io.pod(n); io.pod(lambda); io.pod(mu);
+    if (version != CK_VERSION) throw bbopt::GpuError("restore: unsupported checkpoint version " + std::to_string(version));
+    if (kind != deviceKind()) throw bbopt::GpuError("restore: the checkpoint is of another optimizer class");
+    if (n != _n) throw bbopt::GpuError("restore: the checkpoint has dimension " + std::to_string(n));
+    restoreOrSaveScalars(io);
+    if (_lambda != lambda || _mu != mu) throw bbopt::GpuError("restore: inconsistent checkpoint header");
+    // the device handle is keyed by the Philox stream key and sized by lambda (which differ from this object's own, e.g. a
+    // run checkpointed inside an IPOP restart): re-create it from the restored scalars
+    _dev_used = false;
+    ensureDevice();
+    for (int f : checkpoint_fields(kind)) {
+        std::vector<double> v;
+        io.vec(v);
+        if ((int64_t) v.size() != field_length(f, kind, _n, _lambda)) throw bbopt::GpuError("restore: field of the wrong length");
+        gpu_check(bbgpu_cma_set(_dev, f, v.data(), (int64_t) v.size()));
+    }
+    if (io.pos != blob.size()) throw bbopt::GpuError("restore: trailing bytes in the checkpoint");
+    _dev_used = true;
+    _rep_fresh = true; // _ibw / _ybw / _fkth came with the blob
+}
+
+void BaseCmaes::restoreOrSaveScalars(StateIO &io) {
+    io.flag(_adaptpop); io.flag(_adaptit); io.flag(_bound);
+    io.pod(_mfev); io.pod(_mit); io.pod(_lambda); io.pod(_mu); io.pod(_it); io.pod(_hlen); io.pod(_ik); io.pod(_fev);
+    io.pod(_tol); io.pod(_sigma0); io.pod(_mueff); io.pod(_cc); io.pod(_cs); io.pod(_c1); io.pod(_cmu); io.pod(_damps);
+    io.pod(_chi); io.pod(_sigma); io.pod(_fbest); io.pod(_fworst); io.pod(_fkth);
+    io.ring(_best); io.ring(_kth);
+    io.vec(_ibw); io.vec(_ybw); io.vec(_weights);
+    io.pod(_stream_key); io.pod(_gen);
+    io.pod(_rep);
+    extraState(io);
+}
+
+// ---------------------------------------------------------------------------------------
 // Cmaes
 // ---------------------------------------------------------------------------------------
 
@@ -435,4 +556,22 @@ bool CholeskyCmaes::converged() {
     double mean = 0., m2 = 0.;
     gpu_check(bbgpu_cma_swarm_radius(_dev, &mean, &m2));
     return m2 <= (_lambda - 1) * _stol * _stol;
+}
+
+// ---- subclass scalars of a checkpoint
+void Cmaes::extraState(StateIO &io) {
+    io.pod(_flag); io.pod(_eigenlastev); io.pod(_eigenfreq); io.pod(_eigenrate); io.pod(_eigcount);
+}
+
+void ActiveCmaes::extraState(StateIO &io) {
+    Cmaes::extraState(io);
+    io.pod(_alphacov); io.pod(_cm); io.pod(_cneg); io.pod(_alphaold);
+}
+
+void SepCmaes::extraState(StateIO &io) {
+    io.flag(_adjustlr); io.pod(_flag); io.pod(_ccov);
+}
+
+void CholeskyCmaes::extraState(StateIO &io) {
+    io.pod(_stol);
 }

@@ -8,6 +8,7 @@
 #define BBOPT_HOST_CMA_H_
 
 #include <functional>
+#include <string>
 #include <vector>
 
 #include "device.h"
@@ -50,6 +51,10 @@ protected:
 
     virtual int deviceKind() const = 0;
     virtual void fillConfig(bbgpu_cma_config &cfg) const;
+    // subclass scalars of a checkpoint, in a fixed order (same walk for writing and reading)
+    struct StateIO;
+    virtual void extraState(StateIO &io);
+    void restoreOrSaveScalars(StateIO &io);
     void ensureDevice();
     void fetchReport();
 
@@ -80,6 +85,15 @@ public:
         for (int i = 0; i < count; i++) u(_replay.eng());
     }
     std::vector<double> state(const std::string &name);
+    // ---- checkpoint / resume (the reference has no on-disk format: random.hpp:281-300 can serialise
+    // the engine but nobody calls it).  A versioned little-endian blob: header ("BBOPTCK1", version, kind, n, lambda, mu),
+    // every host scalar of the run (sigma, counters, strategy constants, history rings, stop flags, the Philox key and
+    // generation counter of the free-running stream) and the device state vectors / matrices of the kind.  Contract:
+    // construct an optimizer of the same class, initialize(f, lower, upper, guess) it, then restore(blob); iterate() then
+    // continues exactly where the checkpointed run stood (bit for bit with free-running draws: the Philox stream is a
+    // function of (key, generation, candidate), not of history).  Layout: INTEGRATION.md.
+    std::string checkpoint();
+    void restore(const std::string &blob);
     double sigma() const { return _sigma; }
     int evaluations() const { return _fev; }
     int iterations() const { return _it; }
@@ -101,6 +115,7 @@ protected:
     int _eigcount = 0;
     int deviceKind() const override { return BBGPU_CMA_FULL; }
     void pathsAndCovariance();
+    void extraState(StateIO &io) override;
 
 public:
     Cmaes(int mfev, double tol, int np, double sigma0 = 2., bool bound = false, double eigenrate = 0.25) :
@@ -121,6 +136,7 @@ protected:
     double _alphacov, _cm, _cneg, _alphaold;
     int deviceKind() const override { return BBGPU_CMA_ACTIVE; }
     void fillConfig(bbgpu_cma_config &cfg) const override;
+    void extraState(StateIO &io) override;
 
 public:
     ActiveCmaes(int mfev, double tol, int np, double sigma0 = 2., bool bound = false, double alphacov = 2.,
@@ -138,6 +154,7 @@ protected:
     double _ccov;
     int deviceKind() const override { return BBGPU_CMA_SEP; }
     void fillConfig(bbgpu_cma_config &cfg) const override;
+    void extraState(StateIO &io) override;
 
 public:
     SepCmaes(int mfev, double tol, int np, double sigma0 = 2., bool bound = false, bool adjustlr = false) :
@@ -156,6 +173,7 @@ class CholeskyCmaes: public BaseCmaes {
 protected:
     double _stol;
     int deviceKind() const override { return BBGPU_CMA_CHOLESKY; }
+    void extraState(StateIO &io) override;
 
 public:
     CholeskyCmaes(int mfev, double tol, double stol, int np, double sigma0 = 2., bool bound = false) :

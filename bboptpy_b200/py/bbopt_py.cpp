@@ -135,6 +135,10 @@ PYBIND11_MODULE(_bboptpy, m) {
              "Shard the candidates of this run over the ranks of `comm` (call on every rank, before optimize/initialize)")
         .def("set_stream_key", &BaseCmaes::setStreamKey, "key"_a, "Philox key of the free-running draws (default: a fresh key per object)")
         .def("state", [](BaseCmaes &self, const std::string &name) { return as_array(self.state(name)); }, "name"_a)
+        .def("checkpoint", [](BaseCmaes &self) { return py::bytes(self.checkpoint()); },
+             "Versioned state blob of the run (host scalars + device state); see INTEGRATION.md")
+        .def("restore", [](BaseCmaes &self, const py::bytes &blob) { self.restore(std::string(blob)); }, "blob"_a,
+             "Resume from checkpoint(): call after initialize(f, lower, upper, guess) on an optimizer of the same class")
         .def("set_draw_replay", &BaseCmaes::setDrawReplay, "seed"_a,
              "Draw replay: consume the reference's N(0,1) stream (std::mt19937(seed) + normal_distribution) in its own draw order")
         .def("set_draw_replay_global", &BaseCmaes::setDrawReplayGlobal)
