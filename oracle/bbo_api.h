@@ -32,7 +32,8 @@ void bbo_rng_draw(int kind, int count, double a, double b, double *out);
 double bbo_eval(int obj, int n, const double *x);
 
 /* ---- CMA-ES family.  kind: 0 Cmaes, 1 ActiveCmaes, 2 SepCmaes, 3 CholeskyCmaes (its `stol` travels in
- * the eigenrate argument; cma/cholesky_cmaes.h:44-48) */
+ * the eigenrate argument; cma/cholesky_cmaes.h:44-48), 4 LmCmaes (cma/lm_cmaes.h:62-70: `memory` travels in the eigenrate
+ * argument, `rademacher` in alphacov (0 / 1), `usenew` in adjustlr) */
 void *bbo_cma_new(int kind, int mfev, double tol, int np, double sigma0, int bound,
                   double eigenrate, double alphacov, int adjustlr);
 void bbo_cma_free(void *h);

@@ -19,7 +19,7 @@ REF_PATH = os.path.join(_HERE, "_ref", "libbbo_ref.so")
 PORT_PATH = os.path.join(_HERE, "libbbo_port.so")
 
 SPHERE, ELLIPSOID, ROSENBROCK, RASTRIGIN, ACKLEY = range(5)
-VANILLA, ACTIVE, SEP, CHOLESKY = range(4)
+VANILLA, ACTIVE, SEP, CHOLESKY, LM = range(5)
 JADE, SHADE = range(2)
 
 _c_dp = ctypes.c_void_p
@@ -120,10 +120,13 @@ class Oracle:
         return np.array([self.eval(obj, row) for row in X])
 
     def cma(self, kind, mfev, tol, np_, sigma0=2.0, bound=False, eigenrate=0.25, alphacov=2.0,
-            adjustlr=True, stol=None):
-        """kind CHOLESKY: `stol` (cholesky_cmaes.h:44) travels in the eigenrate slot of the C API."""
+            adjustlr=True, stol=None, memory=0, rademacher=True, usenew=True):
+        """kind CHOLESKY: `stol` (cholesky_cmaes.h:44) travels in the eigenrate slot of the C API; kind LM: memory /
+        rademacher / usenew (lm_cmaes.h:62-70) in the eigenrate / alphacov / adjustlr slots."""
         if kind == CHOLESKY:
             eigenrate = 1e-8 if stol is None else stol
+        if kind == LM:
+            eigenrate, alphacov, adjustlr = float(memory), float(bool(rademacher)), bool(usenew)
         return OracleCma(self, kind, mfev, tol, np_, sigma0, bound, eigenrate, alphacov, adjustlr)
 
     def de(self, kind, mfev, np_, tol, archive=True, repaircr=True, pelite=0.05, cdamp=0.1,
@@ -240,6 +243,14 @@ class OracleCma:
         if self.kind == CHOLESKY:
             s["A"] = self.mat("A")
             s["dmean"] = self.getv("dmean")
+            return s
+        if self.kind == LM:
+            for k in ("memlen", "memsize", "nsteps", "t"):
+                s[k] = self.geti(k)
+            s["s"] = self.getd("s")
+            for k in ("b", "d", "fp", "jarr", "larr"):
+                s[k] = self.getv(k)
+            s["pcmat"], s["vmat"] = self.mat("pcmat"), self.mat("vmat")
             return s
         s["D"] = self.getv("D")
         s["C"] = self.getv("C") if self.kind == SEP else self.mat("C")

@@ -130,6 +130,14 @@ struct PortCma {
     double ccov = 0;
     /* CholeskyCmaes state (cholesky_cmaes.h:34-37); stol arrives in the eigenrate argument */
     std::vector<double> A, mattmp, dmean;
+    /* LmCmaes state (lm_cmaes.h:38-46); memory / rademacher / usenew arrive in eigenrate / alphacov / adjustlr */
+    bool lm_new = true, lm_adaptmemory = true;
+    int lm_samplemode = 1, memlen = 0, memsize = 0, nsteps = 0, lm_t = 1;
+    double stolmin = 1e-16, sqrt1mc1 = 0, zstar = 0.25, lm_s = 0, lm_ccc = 0;
+    std::vector<int> jarr, larr;
+    std::vector<double> lm_b, lm_d, az, fp, pcmat, vmat;
+    std::vector<RankRec> mixed;
+    std::vector<double> last_i0; /* replay feed: the subset start of every sampled pair (selectSubset) */
     BboNormal Z;
     /* eigenbasis-replay feed (bbo_cma_eig_log) */
     struct EigEvent { int fev, n; std::vector<double> B, D; };
@@ -178,6 +186,40 @@ struct PortCma {
     /* ---- cma/cmaes.cpp:44-63, cma/active_cmaes.cpp:42-69, cma/sep_cmaes.cpp:40-67 */
     void init(const double *guess) {
         base_init(guess);
+        if (kind == 4) { /* cma/lm_cmaes.cpp:42-89 */
+            if (lm_adaptmemory) memsize = (int) (2.0 * std::sqrt(1.0 * n));
+            memlen = 0;
+            if (lm_new) {
+                nsteps = n;
+                lm_t = std::max(1, (int) std::log(1.0 * n));
+                cc = 0.5 / std::sqrt(1.0 * n);
+            } else {
+                nsteps = memsize;
+                lm_t = 1;
+                cc = 1.0 / memsize;
+            }
+            cs = 0.3;
+            c1 = 0.1 / std::log(n + 1.0);
+            cmu = NAN;
+            lm_ccc = std::sqrt(cc * (2.0 - cc) * mueff);
+            damps = 1.0;
+            sqrt1mc1 = std::sqrt(1.0 - c1);
+            zstar = 0.25;
+            lm_s = 0.0;
+            jarr.assign(memsize, 0);
+            larr.assign(memsize, 0);
+            lm_b.assign(memsize, 0.0);
+            lm_d.assign(memsize, 0.0);
+            az.assign(n, 0.0);
+            fp.assign(lambda, 0.0);
+            /* `_pcmat.resize` / `_vmat.resize` keep an already sized matrix (:82-83); every row that is read has been
+             * written since (rows jarr[0 .. memlen-1]), so stale contents are never observed */
+            pcmat.resize((size_t) memsize * n, 0.0);
+            vmat.resize((size_t) memsize * n, 0.0);
+            mixed.assign((size_t) 2 * lambda, RankRec { 0, 0.0 });
+            flag = 0;
+            return;
+        }
         if (kind == 3) { /* cma/cholesky_cmaes.cpp:40-52 */
             dmean.assign(n, 0.0);
             A.assign((size_t) n * n, 0.0);
@@ -237,7 +279,51 @@ struct PortCma {
     }
 
     /* ---- cma/cmaes.cpp:65-80 and cma/sep_cmaes.cpp:69-79 (draw order: candidate-major) */
+    /* ---- cma/lm_cmaes.cpp:308-322 (algorithm 6): draws one normal only when m > 1 */
+    int lm_select_subset(int m, int k) {
+        if (m <= 1) return 0;
+        int msigma = 4;
+        if (k == 0) msigma *= 10;
+        int mstar = (int) (msigma * std::fabs(Z.draw(eng())));
+        mstar = std::min(mstar, m);
+        return m - mstar;
+    }
+
+    /* ---- cma/lm_cmaes.cpp:91-127: mirrored sampling, one base vector per PAIR of candidates */
+    void sample_lm() {
+        const int pairs = (lambda + 1) / 2;
+        last_z.assign((size_t) pairs * n, 0.0);
+        last_i0.assign(pairs, 0.0);
+        int sign = 1;
+        for (int k = 0; k < lambda; k++) {
+            if (sign == 1) {
+                double *zrow = &last_z[(size_t) (k / 2) * n];
+                if (lm_samplemode == 0) {
+                    for (int i = 0; i < n; i++) tmp[i] = az[i] = zrow[i] = Z.draw(eng());
+                } else {
+                    for (int i = 0; i < n; i++) tmp[i] = az[i] = zrow[i] = eng().uniform_real(0.0, 1.0) < 0.5 ? 1.0 : -1.0;
+                }
+                const int i0 = lm_new ? lm_select_subset(memlen, k) : 0;
+                last_i0[k / 2] = i0;
+                for (int i = i0; i < memlen; i++) {
+                    const int j = jarr[i];
+                    const double *v = &vmat[(size_t) j * n], *p = &pcmat[(size_t) j * n];
+                    double dot = 0.0;
+                    for (int q = 0; q < n; q++) dot = dot + v[q] * tmp[q]; /* the ORIGINAL draw, not az (:117-119) */
+                    dot = lm_b[j] * dot;
+                    for (int q = 0; q < n; q++) az[q] = sqrt1mc1 * az[q];
+                    for (int q = 0; q < n; q++) az[q] = az[q] + dot * p[q];
+                }
+            }
+            double *x = &arx[(size_t) k * n];
+            const double da = sign * sigma;
+            for (int q = 0; q < n; q++) x[q] = xmean[q] + da * az[q];
+            sign = -sign;
+        }
+    }
+
     void sample() {
+        if (kind == 4) { sample_lm(); return; }
         last_z.resize((size_t) lambda * n);
         for (int k = 0; k < lambda; k++) {
             double *x = &arx[(size_t) k * n];
@@ -275,6 +361,8 @@ struct PortCma {
 
     /* ---- cma/base_cmaes.cpp:211-230 */
     void evalsort() {
+        if (kind == 4 && it > 0) /* cma/lm_cmaes.cpp:228-238 */
+            for (int k = 0; k < lambda; k++) fp[k] = rank[k].value;
         for (int k = 0; k < lambda; k++) {
             rank[k].index = k;
             rank[k].value = f(&arx[(size_t) k * n]);
@@ -485,7 +573,100 @@ struct PortCma {
         update_sigma();
     }
 
+    /* ---- cma/lm_cmaes.cpp:260-272 (algorithm 4) on tmp */
+    void lm_ainvz(int jlen) {
+        const double c = 1.0 / sqrt1mc1;
+        for (int i = 0; i < jlen; i++) {
+            const int idx = jarr[i];
+            const double *v = &vmat[(size_t) idx * n];
+            double dot = 0.0;
+            for (int q = 0; q < n; q++) dot = dot + v[q] * tmp[q];
+            dot = lm_d[idx] * dot;
+            for (int q = 0; q < n; q++) tmp[q] = c * tmp[q];
+            for (int q = 0; q < n; q++) tmp[q] = tmp[q] + (-dot) * v[q];
+        }
+    }
+
+    /* ---- cma/lm_cmaes.cpp:274-306 (algorithm 5) */
+    int lm_update_set() {
+        const int itt = it / lm_t;
+        int imin = 1;
+        if (itt < memsize) {
+            jarr[itt] = itt;
+        } else if (memsize > 1) {
+            int iminval = larr[jarr[1]] - larr[jarr[0]];
+            for (int i = 1; i < memsize - 1; i++) {
+                const int val = larr[jarr[i + 1]] - larr[jarr[i]];
+                if (val < iminval) {
+                    iminval = val;
+                    imin = i + 1;
+                }
+            }
+            if (iminval >= nsteps) imin = 0;
+            const int jtmp = jarr[imin];
+            for (int i = imin; i < memsize - 1; i++) jarr[i] = jarr[i + 1];
+            jarr[memsize - 1] = jtmp;
+        }
+        const int jcur = jarr[std::min(itt, memsize - 1)];
+        larr[jcur] = it;
+        return imin == 1 ? 0 : imin;
+    }
+
+    /* ---- cma/lm_cmaes.cpp:240-258 */
+    void lm_update_sigma() {
+        if (it == 0) return;
+        for (int k = 0; k < lambda; k++) {
+            mixed[k].index = k;
+            mixed[k].value = fp[k];
+            mixed[k + lambda].index = k + lambda;
+            mixed[k + lambda].value = rank[k].value;
+        }
+        std::sort(mixed.begin(), mixed.end(), RankRec::less);
+        double zpsr = 0.0;
+        for (int k = 0; k < (lambda << 1); k++) {
+            const double f = (1.0 * k) / lambda;
+            if (mixed[k].index < lambda) zpsr += f;
+            else zpsr -= f;
+        }
+        zpsr /= (1.0 * lambda);
+        zpsr -= zstar;
+        lm_s = (1.0 - cs) * lm_s + cs * zpsr;
+        sigma *= std::exp(lm_s / damps);
+    }
+
+    /* ---- cma/lm_cmaes.cpp:129-181 */
+    void update_lm() {
+        std::copy(xmean.begin(), xmean.end(), xold.begin());
+        std::fill(xmean.begin(), xmean.end(), 0.0);
+        for (int k = 0; k < mu; k++) {
+            const double *x = &arx[(size_t) rank[k].index * n];
+            for (int q = 0; q < n; q++) xmean[q] = xmean[q] + weights[k] * x[q];
+        }
+        if (bound)
+            for (int i = 0; i < n; i++) xmean[i] = std::max(lower[i], std::min(xmean[i], upper[i]));
+        for (int i = 0; i < n; i++) pc[i] = (1.0 - cc) * pc[i] + lm_ccc * (xmean[i] - xold[i]) / sigma;
+        if (it % lm_t == 0) {
+            const int imin = lm_update_set();
+            if (memlen < memsize) memlen++;
+            int jcur = jarr[memlen - 1];
+            std::copy(pc.begin(), pc.end(), pcmat.begin() + (size_t) jcur * n);
+            for (int i = imin; i < memlen; i++) {
+                jcur = jarr[i];
+                std::copy(pcmat.begin() + (size_t) jcur * n, pcmat.begin() + (size_t) (jcur + 1) * n, tmp.begin());
+                lm_ainvz(i);
+                std::copy(tmp.begin(), tmp.end(), vmat.begin() + (size_t) jcur * n);
+                double vnrm2 = 0.0;
+                for (int q = 0; q < n; q++) vnrm2 = vnrm2 + tmp[q] * tmp[q];
+                const double sqrtc1 = std::sqrt(1.0 + (c1 / (1.0 - c1)) * vnrm2);
+                lm_b[jcur] = (sqrt1mc1 / vnrm2) * (sqrtc1 - 1.0);
+                lm_d[jcur] = (1.0 / (sqrt1mc1 * vnrm2)) * (1.0 - 1.0 / sqrtc1);
+            }
+        }
+        lm_update_sigma();
+    }
+
     void update() {
+        if (kind == 4) { update_lm(); return; }
         if (kind == 0) update_vanilla();
         else if (kind == 1) update_active();
         else if (kind == 3) update_chol();
@@ -709,6 +890,21 @@ struct PortCma {
 
     /* ---- cma/cmaes.cpp:151-227 and cma/sep_cmaes.cpp:137-207 */
     bool converged() {
+        if (kind == 4) { /* cma/lm_cmaes.cpp:183-226 */
+            if (it >= mit) return true;
+            if (sigma < stolmin) return true;
+            if (it >= hlen && fworst - fbest < tol) return true;
+            if (best.len >= n && kth.len >= n) {
+                int eq = 0;
+                for (int i = 0; i < n; i++) {
+                    if (best.get(i) == kth.get(i)) {
+                        eq++;
+                        if (3 * eq >= n) return true;
+                    }
+                }
+            }
+            return false;
+        }
         if (kind == 3) { /* cma/cholesky_cmaes.cpp:137-161 */
             if (std::fabs(ybw[0] - ybw[3]) > tol) return false;
             int count = 0;
@@ -1101,6 +1297,12 @@ void *bbo_cma_new(int kind, int mfev, double tol, int np, double sigma0, int bou
     p->eigenrate = eigenrate;
     p->alphacov = alphacov;
     p->adjustlr = adjustlr != 0;
+    if (kind == 4) { /* LmCmaes(mfev, tol, np, memory, sigma0, bound, rademacher, usenew), lm_cmaes.h:62-70 */
+        p->memsize = (int) eigenrate;
+        p->lm_adaptmemory = p->memsize <= 0;
+        p->lm_samplemode = alphacov != 0.0 ? 1 : 0;
+        p->lm_new = adjustlr != 0;
+    }
     return p;
 }
 
@@ -1154,6 +1356,10 @@ int bbo_cma_geti(void *h, const char *name) {
     if (k == "best_len") return p->best.len;
     if (k == "flag") return p->flag;
     if (k == "eigenlastev") return p->eigenlastev;
+    if (k == "memlen") return p->memlen;
+    if (k == "memsize") return p->memsize;
+    if (k == "nsteps") return p->nsteps;
+    if (k == "t") return p->lm_t;
     return -1;
 }
 
@@ -1178,6 +1384,9 @@ double bbo_cma_getd(void *h, const char *name) {
     if (k == "alphaold") return p->alphaold;
     if (k == "ccov") return p->ccov;
     if (k == "stol") return p->eigenrate;
+    if (k == "s") return p->lm_s;
+    if (k == "ccc") return p->lm_ccc;
+    if (k == "sqrt1mc1") return p->sqrt1mc1;
     return NAN;
 }
 
@@ -1198,6 +1407,19 @@ int bbo_cma_getv(void *h, const char *name, double *out, int cap) {
     if (k == "B" && p->kind != 2) return put(p->B, out, cap);
     if (k == "invsqrtC" && p->kind != 2) return put(p->isC, out, cap);
     if (k == "ycoeff" && p->kind == 1) return put(p->ycoeff, out, cap);
+    if (p->kind == 4) {
+        if (k == "pcmat") return put(p->pcmat, out, cap);
+        if (k == "vmat") return put(p->vmat, out, cap);
+        if (k == "b") return put(p->lm_b, out, cap);
+        if (k == "d") return put(p->lm_d, out, cap);
+        if (k == "fp") return put(p->fp, out, cap);
+        if (k == "i0") return put(p->last_i0, out, cap);
+        if (k == "jarr" || k == "larr") {
+            const std::vector<int> &v = k == "jarr" ? p->jarr : p->larr;
+            for (int i = 0; i < (int) v.size() && i < cap; i++) out[i] = v[i];
+            return (int) v.size();
+        }
+    }
     if (k == "A" && p->kind == 3) return put(p->A, out, cap);
     if (k == "dmean" && p->kind == 3) return put(p->dmean, out, cap);
     if (k == "ybw") {

@@ -2,7 +2,7 @@
  * ORACLE (test infrastructure).  Thin C driver around the UNMODIFIED reference sources.
  *
  * Built by oracle/Makefile: this file + /root/reference/src/{blas.cpp,
- * multivariate/cma/{base_cmaes,cmaes,active_cmaes,sep_cmaes,cholesky_cmaes,ipop_cmaes,bipop_cmaes}.cpp,
+ * multivariate/cma/{base_cmaes,cmaes,active_cmaes,sep_cmaes,cholesky_cmaes,lm_cmaes,ipop_cmaes,bipop_cmaes}.cpp,
  * multivariate/de/{jade,shade}.cpp} compiled where they lie -> oracle/_ref/libbbo_ref.so.
  * No reference source is copied into this repository; the headers are included by path.
  *
@@ -27,6 +27,7 @@
 #include "multivariate/cma/active_cmaes.h"
 #include "multivariate/cma/sep_cmaes.h"
 #include "multivariate/cma/cholesky_cmaes.h"
+#include "multivariate/cma/lm_cmaes.h"
 #include "multivariate/cma/ipop_cmaes.h"
 #include "multivariate/cma/bipop_cmaes.h"
 #include "multivariate/de/jade.h"
@@ -251,6 +252,43 @@ struct CholProbe: public CholeskyCmaes, public CmaProbe {
     }
 };
 
+/* LmCmaes (lm_cmaes.h:38-46: everything protected) */
+struct LmProbe: public LmCmaes, public CmaProbe {
+    using LmCmaes::LmCmaes;
+    BaseCmaes *base() override { return this; }
+    void reset_z() override { _Z.reset(); }
+    int geti(const std::string &k) override {
+        BASE_GETI(k)
+        if (k == "flag") return 0;
+        if (k == "memlen") return _memlen;
+        if (k == "memsize") return _memsize;
+        if (k == "nsteps") return _nsteps;
+        if (k == "t") return _t;
+        return -1;
+    }
+    double getd(const std::string &k) override {
+        BASE_GETD(k)
+        if (k == "s") return _s;
+        if (k == "ccc") return _ccc;
+        if (k == "sqrt1mc1") return _sqrt1mc1;
+        return NAN;
+    }
+    int getv(const std::string &k, double *out, int cap) override {
+        BASE_GETV(k)
+        if (k == "pcmat") return copy_out2(_pcmat, out, cap);
+        if (k == "vmat") return copy_out2(_vmat, out, cap);
+        if (k == "b") return copy_out(_b, out, cap);
+        if (k == "d") return copy_out(_d, out, cap);
+        if (k == "fp") return copy_out(_fp, out, cap);
+        if (k == "jarr" || k == "larr") {
+            const std::vector<int> &v = k == "jarr" ? _jarr : _larr;
+            for (int i = 0; i < (int) v.size() && i < cap; i++) out[i] = v[i];
+            return (int) v.size();
+        }
+        return -1;
+    }
+};
+
 void bind_problem(CmaProbe *p, int obj, int n, const double *lower, const double *upper,
         const double *guess) {
     p->lower.assign(lower, lower + n);
@@ -363,6 +401,8 @@ void *bbo_cma_new(int kind, int mfev, double tol, int np, double sigma0, int bou
     if (kind == 0) p = new VanillaProbe(mfev, tol, np, sigma0, bound != 0, eigenrate);
     else if (kind == 1) p = new ActiveProbe(mfev, tol, np, sigma0, bound != 0, alphacov, eigenrate);
     else if (kind == 3) p = new CholProbe(mfev, tol, /*stol=*/eigenrate, np, sigma0, bound != 0);
+    else if (kind == 4) p = new LmProbe(mfev, tol, np, /*memory=*/(int) eigenrate, sigma0, bound != 0, /*rademacher=*/alphacov != 0.,
+            /*usenew=*/adjustlr != 0);
     else p = new SepProbe(mfev, tol, np, sigma0, bound != 0, adjustlr != 0);
     return p;
 }

@@ -68,6 +68,41 @@ def test_cma_every_generation(ref_oracle, port_oracle, kind, obj, n, lam, gens, 
         assert r.geti("flag") == p.geti("flag")
 
 
+@pytest.mark.parametrize("n,lam,gens,bound,kw", [
+    (10, 12, 200, False, dict()),                                      # defaults: Rademacher draws, the 2015 variant
+    (10, 12, 200, False, dict(rademacher=False)),                      # Gaussian draws share _Z with selectSubset
+    (30, 16, 150, True, dict(memory=5)),                               # a small memory: updateSet replaces vectors (algorithm 5)
+    (30, 17, 150, False, dict(memory=6, usenew=False, rademacher=False)),  # the 2014 variant, odd lambda (last pair half used)
+    (200, 24, 40, False, dict()),
+])
+def test_lm_cma_every_generation(ref_oracle, port_oracle, n, lam, gens, bound, kw):
+    """LmCmaes (cma/lm_cmaes.cpp): port bit for bit after every generation, memory bookkeeping included."""
+    def make(o):
+        o.seed(42)
+        guess = o.uniform(-5.0, 5.0, n)
+        h = o.cma(O.LM, 10 ** 9, 1e-12, lam, bound=bound, **kw)
+        h.init(O.RASTRIGIN, -5.12 * np.ones(n), 5.12 * np.ones(n), guess)
+        return h
+    r, p = _pair(ref_oracle, port_oracle, make)
+    for k in ("cc", "cs", "c1", "damps", "ccc", "sqrt1mc1", "mueff"):
+        assert r.getd(k) == p.getd(k), k
+    for k in ("memsize", "nsteps", "t"):
+        assert r.geti(k) == p.geti(k), k
+    for g in range(gens):
+        r.iterate()
+        p.iterate()
+        assert r.geti("memlen") == p.geti("memlen")
+        for k in ("xmean", "pc", "arx", "fit_val", "fit_idx", "jarr", "larr", "b", "d", "fp"):
+            assert np.array_equal(r.getv(k), p.getv(k)), (g, k)
+        ml = r.geti("memlen")
+        rows = r.getv("jarr")[:ml].astype(int)
+        assert np.array_equal(r.mat("pcmat")[rows], p.mat("pcmat")[rows]), (g, "pcmat")
+        assert np.array_equal(r.mat("vmat")[rows], p.mat("vmat")[rows]), (g, "vmat")
+        for k in ("sigma", "s", "fbest", "fworst"):
+            assert r.getd(k) == p.getd(k), (g, k)
+        assert r.converged() == p.converged()
+
+
 def test_cma_phases_one_by_one(ref_oracle, port_oracle):
     def make(o):
         o.seed(1)
@@ -148,7 +183,7 @@ def test_optimize_and_restart_drivers(ref_oracle, port_oracle):
             res.append(o.de(kind, 30000, 40, 1e-6).optimize(O.ROSENBROCK, -10 * np.ones(n), 10 * np.ones(n)))
         assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
     for rk in (0, 1):
-        for bk in (O.VANILLA, O.ACTIVE, O.SEP, O.CHOLESKY):
+        for bk in (O.VANILLA, O.ACTIVE, O.SEP, O.CHOLESKY, O.LM):
             for flag in (True, False):
                 res = []
                 for o in (ref_oracle, port_oracle):
