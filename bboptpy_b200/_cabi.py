@@ -14,10 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BBGPU_LIB_PATH") or os.path.join(_HERE, "libbbgpu.so")  # override: A/B builds of the engine
 
 OBJ_SPHERE, OBJ_ELLIPSOID, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY = range(5)
-CMA_FULL, CMA_ACTIVE, CMA_SEP, CMA_CHOLESKY = range(4)
+CMA_FULL, CMA_ACTIVE, CMA_SEP, CMA_CHOLESKY, CMA_LM = range(5)
 DE_JADE, DE_SHADE = range(2)
 (F_XMEAN, F_XOLD, F_PC, F_PS, F_C, F_B, F_D, F_INVSQRTC, F_ARX, F_Z, F_FITNESS, F_RANKVAL, F_YCOEFF,
- F_WEIGHTS, F_NORMS, F_SHARD_RED, F_A) = range(17)
+ F_WEIGHTS, F_NORMS, F_SHARD_RED, F_A, F_PCMAT, F_VMAT, F_LMB, F_LMD) = range(21)
 COMM_ID_BYTES = 128
 
 c_dp = ctypes.c_void_p
@@ -34,7 +34,8 @@ class CmaConfig(ctypes.Structure):
                 ("cc", ctypes.c_double), ("cs", ctypes.c_double), ("c1", ctypes.c_double), ("cmu", ctypes.c_double),
                 ("mueff", ctypes.c_double), ("chi", ctypes.c_double),
                 ("cneg", ctypes.c_double), ("alphaold", ctypes.c_double), ("cm", ctypes.c_double),
-                ("ccov", ctypes.c_double)]
+                ("ccov", ctypes.c_double),
+                ("lm_memory", ctypes.c_int), ("lm_rademacher", ctypes.c_int), ("lm_usenew", ctypes.c_int)]
 
 
 class CmaReport(ctypes.Structure):
@@ -142,6 +143,8 @@ def lib():
     L.bbgpu_cma_eig.argtypes = [vp, vp, vp]
     L.bbgpu_cma_probe.argtypes = [vp, d, i]
     L.bbgpu_cma_swarm_radius.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    L.bbgpu_cma_lm_sample.argtypes = [vp, d, ctypes.c_uint64, i, c_dp, c_dp, c_dp]
+    L.bbgpu_cma_lm_update.argtypes = [vp, d, i, i, i, c_dp]
     L.bbgpu_cma_fetch.argtypes = [vp, P(CmaReport)]
     L.bbgpu_cma_generation.argtypes = [vp, vp, d, u64, i, i]
     L.bbgpu_cma_attach_comm.argtypes = [vp, vp]
@@ -420,6 +423,8 @@ class Cma:
             setattr(cfg, k, float(consts.get(k, 0.0)))
         if kind == CMA_ACTIVE and "cm" not in consts:
             cfg.cm = 1.0
+        cfg.lm_memory, cfg.lm_rademacher, cfg.lm_usenew = (int(consts.get(k, 0)) for k in ("lm_memory", "lm_rademacher", "lm_usenew"))
+        self.lm_memory = cfg.lm_memory
         self.cfg = cfg
         w = f64(weights)
         lo = f64(lower) if lower is not None else None
@@ -437,11 +442,14 @@ class Cma:
 
     def _len(self, field):
         n, lam = self.n, self.lam
+        if field == F_Z and self.kind == CMA_LM:
+            return ((lam + 1) // 2) * n
         full = self.kind != CMA_SEP
         ld = (n + 7) // 8 * 8
         return {F_XMEAN: n, F_XOLD: n, F_PC: n, F_PS: n, F_D: n, F_C: n * n if full else n, F_B: n * n,
                 F_INVSQRTC: n * n, F_ARX: self.lam_loc * n, F_Z: self.lam_loc * n, F_FITNESS: lam, F_RANKVAL: lam,
-                F_YCOEFF: self.mu, F_WEIGHTS: self.mu, F_NORMS: lam, F_SHARD_RED: n * ld + ld, F_A: n * n}[field]
+                F_YCOEFF: self.mu, F_WEIGHTS: self.mu, F_NORMS: lam, F_SHARD_RED: n * ld + ld, F_A: n * n,
+                F_PCMAT: self.lm_memory * n, F_VMAT: self.lm_memory * n, F_LMB: self.lm_memory, F_LMD: self.lm_memory}[field]
 
     def reset(self, guess, keep_offdiag=False):
         g = f64(guess)
@@ -454,7 +462,7 @@ class Cma:
     def get(self, field):
         out = np.empty(self._len(field))
         check(self.L.bbgpu_cma_get(self.h, field, out.ctypes.data, out.size))
-        if field in (F_B, F_INVSQRTC, F_ARX, F_Z, F_A) or (field == F_C and self.kind != CMA_SEP):
+        if field in (F_B, F_INVSQRTC, F_ARX, F_Z, F_A, F_PCMAT, F_VMAT) or (field == F_C and self.kind != CMA_SEP):
             return out.reshape(-1, self.n)
         return out
 
@@ -462,6 +470,20 @@ class Cma:
         idx = np.empty(self.lam, dtype=np.int32)
         check(self.L.bbgpu_cma_get_rank(self.h, idx.ctypes.data, self.lam))
         return idx
+
+    def lm_sample(self, sigma, generation, jarr, memlen, z=None, i0=None):
+        """LM kind: mirrored sampling through the live memory rows jarr[:memlen]; z (pairs x n) and i0 (pairs) replay the
+        reference's base draws and subset starts."""
+        j = np.ascontiguousarray(jarr, dtype=np.int32)
+        if z is not None:
+            z, i0 = f64(z), np.ascontiguousarray(i0, dtype=np.int32)
+            assert z.size == ((self.lam + 1) // 2) * self.n and i0.size == (self.lam + 1) // 2
+        check(self.L.bbgpu_cma_lm_sample(self.h, sigma, generation, memlen, j.ctypes.data if j.size else None,
+                                         z.ctypes.data if z is not None else None, i0.ctypes.data if z is not None else None))
+
+    def lm_update(self, sigma, do_memory, imin, memlen, jarr):
+        j = np.ascontiguousarray(jarr, dtype=np.int32)
+        check(self.L.bbgpu_cma_lm_update(self.h, sigma, int(do_memory), imin, memlen, j.ctypes.data if j.size else None))
 
     def swarm_radius(self):
         """Cholesky kind: (mean, M2) of the candidates' Euclidean norms (converged(), cholesky_cmaes.cpp:146-160)."""

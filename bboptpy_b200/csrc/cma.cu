@@ -18,6 +18,7 @@
 #include <cmath>
 
 #include "chol.cuh"
+#include "lmcma.cuh"
 #include "gemm_tma.cuh"
 #include "objectives.cuh"
 #include "philox.cuh"
@@ -35,6 +36,11 @@ struct bbgpu_cma {
     // candidate radii + their statistics
     double *Ystk = nullptr, *Mch = nullptr, *Lt = nullptr, *negone = nullptr, *rnorm = nullptr, *rstat = nullptr;
     cudaEvent_t ev_ch_fork = nullptr, ev_ch_join = nullptr;
+    // LM-CMA-ES (lmcma.cuh): direction vectors and their scalars, the base draws of the pairs, live-row order, subset starts
+    bool lm = false;
+    int lm_mem = 0, lm_pairs = 0;
+    double *PCmat = nullptr, *Vmat = nullptr, *lmb = nullptr, *lmd = nullptr, *Zp = nullptr;
+    int *lm_jarr = nullptr, *lm_i0 = nullptr;
     // vectors
     double *xmean = nullptr, *xold = nullptr, *pc = nullptr, *ps = nullptr, *D = nullptr, *weights = nullptr,
             *lower = nullptr, *upper = nullptr, *dm = nullptr, *W = nullptr, *coef = nullptr, *ycoeff = nullptr,
@@ -1102,13 +1108,19 @@ static int field_info(bbgpu_cma *h, int field, double **ptr, int64_t *rows, int6
     case BBGPU_CMA_PC: *ptr = h->pc; *rows = 1; *cols = n; break;
     case BBGPU_CMA_PS: *ptr = h->ps; *rows = 1; *cols = n; break;
     case BBGPU_CMA_D:
-        if (h->chol) return fail(BBGPU_ERR_ARG, "Cholesky-CMA-ES has no D");
+        if (h->chol || h->lm) return fail(BBGPU_ERR_ARG, "this kind has no D");
         *ptr = h->D; *rows = 1; *cols = n; break;
+    case BBGPU_CMA_PCMAT: case BBGPU_CMA_VMAT:
+        if (!h->lm) return fail(BBGPU_ERR_ARG, "only LM-CMA-ES has direction vectors");
+        *ptr = field == BBGPU_CMA_PCMAT ? h->PCmat : h->Vmat; *rows = h->lm_mem; *cols = n; *ld = h->ldn; break;
+    case BBGPU_CMA_LMB: case BBGPU_CMA_LMD:
+        if (!h->lm) return fail(BBGPU_ERR_ARG, "only LM-CMA-ES has direction vectors");
+        *ptr = field == BBGPU_CMA_LMB ? h->lmb : h->lmd; *rows = 1; *cols = h->lm_mem; break;
     case BBGPU_CMA_A:
         if (!h->chol) return fail(BBGPU_ERR_ARG, "only Cholesky-CMA-ES has a factor A");
         *ptr = h->Ystk; *rows = n; *cols = n; *ld = h->ldn; break;
     case BBGPU_CMA_C:
-        if (h->chol) return fail(BBGPU_ERR_ARG, "Cholesky-CMA-ES keeps the factor A, not C");
+        if (h->chol || h->lm) return fail(BBGPU_ERR_ARG, "this kind keeps no covariance matrix");
         if (h->full) { *ptr = h->C; *rows = n; *cols = n; *ld = h->ldn; }
         else { *ptr = h->C; *rows = 1; *cols = n; }
         break;
@@ -1119,7 +1131,9 @@ static int field_info(bbgpu_cma *h, int field, double **ptr, int64_t *rows, int6
         if (!h->full) return fail(BBGPU_ERR_ARG, "separable CMA-ES has no eigenbasis");
         *ptr = h->Bt; *rows = n; *cols = n; *ld = h->ldn; break;
     case BBGPU_CMA_ARX: *ptr = h->X; *rows = h->lam_loc; *cols = n; *ld = h->ldn; break;
-    case BBGPU_CMA_Z: *ptr = h->Z; *rows = h->lam_loc; *cols = n; *ld = h->ldn; break;
+    case BBGPU_CMA_Z:
+        if (h->lm) { *ptr = h->Zp; *rows = h->lm_pairs; *cols = n; *ld = h->ldn; break; } // one base vector per pair
+        *ptr = h->Z; *rows = h->lam_loc; *cols = n; *ld = h->ldn; break;
     case BBGPU_CMA_NORMS:
         if (!(h->active && h->shards > 1)) return fail(BBGPU_ERR_ARG, "norms exist only for a sharded active CMA-ES");
         *ptr = h->norm_all; *rows = 1; *cols = h->lambda; break;
@@ -1148,11 +1162,12 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
         const double *h_upper, bbgpu_cma **out) {
     BB_ARG(ctx && cfg && h_weights && out);
     BB_ARG(cfg->n >= 1 && cfg->lambda >= 2 && cfg->mu >= 1 && cfg->mu <= cfg->lambda);
-    BB_ARG(cfg->kind >= BBGPU_CMA_FULL && cfg->kind <= BBGPU_CMA_CHOLESKY);
+    BB_ARG(cfg->kind >= BBGPU_CMA_FULL && cfg->kind <= BBGPU_CMA_LM);
+    if (cfg->kind == BBGPU_CMA_LM) BB_ARG(cfg->lm_memory >= 1 && cfg->lm_memory <= LM_MAXMEM);
     BB_ARG(!cfg->bound || (h_lower && h_upper));
     if (cfg->shard_count > 1) {
         BB_ARG(cfg->shard_rank >= 0 && cfg->shard_rank < cfg->shard_count);
-        if (cfg->kind == BBGPU_CMA_SEP || cfg->kind == BBGPU_CMA_CHOLESKY)
+        if (cfg->kind == BBGPU_CMA_SEP || cfg->kind == BBGPU_CMA_CHOLESKY || cfg->kind == BBGPU_CMA_LM)
             return fail(BBGPU_ERR_ARG, "candidate sharding covers the full-covariance kinds");
         if (cfg->lambda % cfg->shard_count != 0 || cfg->lambda / cfg->shard_count < 2)
             return fail(BBGPU_ERR_ARG, "lambda = %d does not split into %d equal shards of at least 2", cfg->lambda, cfg->shard_count);
@@ -1167,6 +1182,9 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     h->full = cfg->kind == BBGPU_CMA_FULL || cfg->kind == BBGPU_CMA_ACTIVE;
     h->active = cfg->kind == BBGPU_CMA_ACTIVE;
     h->chol = cfg->kind == BBGPU_CMA_CHOLESKY;
+    h->lm = cfg->kind == BBGPU_CMA_LM;
+    h->lm_mem = h->lm ? cfg->lm_memory : 0;
+    h->lm_pairs = (cfg->lambda + 1) / 2;
     h->nsel = h->active ? 2 * h->mu : h->mu;
     if (h->active && 2 * h->mu > h->lambda) { delete h; return fail(BBGPU_ERR_ARG, "active CMA-ES needs 2 mu <= lambda"); }
     h->ldn = round_up(h->n, 8);
@@ -1188,7 +1206,8 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     A(&h->xmean, ldn); A(&h->xold, ldn); A(&h->pc, ldn); A(&h->ps, ldn); A(&h->D, ldn); A(&h->dm, ldn);
     A(&h->tmpn, ldn); A(&h->W, ldn); A(&h->weights, h->mu); A(&h->lower, ldn); A(&h->upper, ldn);
     A(&h->coef, (size_t) round_up(h->chol ? h->n + h->mu : h->nsel, 32) + 32); A(&h->ycoeff, (size_t) h->mu); A(&h->dscal, 8);
-    A(&h->X, laml * ldn); A(&h->Zbuf[0], laml * ldn); A(&h->Zbuf[1], laml * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
+    A(&h->X, laml * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
+    if (!h->lm) { A(&h->Zbuf[0], laml * ldn); A(&h->Zbuf[1], laml * ldn); } // the LM kind draws lambda/2 base vectors (Zp)
     A(&h->part, (size_t) h->splits * 2 * n);
     if (h->full) {
         A(&h->C, (size_t) n * ldn); A(&h->Bt, (size_t) n * ldn); A(&h->BDt, (size_t) n * ldn);
@@ -1217,6 +1236,11 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
             fill_kernel<<<1, 64, 0, ctx->stream>>>(h->negone, CH_NB, -1.0);
             rc = launched(ctx, "fill_kernel");
         }
+    } else if (h->lm) {
+        A(&h->PCmat, (size_t) h->lm_mem * ldn); A(&h->Vmat, (size_t) h->lm_mem * ldn); A(&h->lmb, (size_t) h->lm_mem);
+        A(&h->lmd, (size_t) h->lm_mem); A(&h->Zp, (size_t) h->lm_pairs * ldn);
+        if (rc == BBGPU_OK) rc = dev_alloc(&h->lm_jarr, (size_t) h->lm_mem);
+        if (rc == BBGPU_OK) rc = dev_alloc(&h->lm_i0, (size_t) h->lm_pairs);
     } else {
         A(&h->C, ldn);
     }
@@ -1260,7 +1284,9 @@ int bbgpu_cma_destroy(bbgpu_cma *h) {
     double *bufs[] = { h->xmean, h->xold, h->pc, h->ps, h->D, h->dm, h->tmpn, h->W, h->weights, h->lower, h->upper, h->coef,
             h->ycoeff, h->dscal, h->X, h->Zbuf[0], h->Zbuf[1], h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
             h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc, h->own_ws,
-            h->Ystk, h->Mch, h->Lt, h->negone, h->rnorm, h->rstat };
+            h->Ystk, h->Mch, h->Lt, h->negone, h->rnorm, h->rstat, h->PCmat, h->Vmat, h->lmb, h->lmd, h->Zp };
+    if (h->lm_jarr) cudaFree(h->lm_jarr);
+    if (h->lm_i0) cudaFree(h->lm_i0);
     if (h->ev_ch_fork) cudaEventDestroy(h->ev_ch_fork);
     if (h->ev_ch_join) cudaEventDestroy(h->ev_ch_join);
     if (h->own_info) cudaFree(h->own_info);
@@ -1303,6 +1329,9 @@ int bbgpu_cma_reset(bbgpu_cma *h, const double *h_guess, int keep_offdiag) {
         dim3 grid(ceil_div(n, 256), n);
         fill_identity_kernel<<<grid, 256, 0, st>>>(h->Ystk, n, h->ldn, false); // A = I (cholesky_cmaes.cpp:44-51 clears it)
         BB_TRY(launched(ctx, "fill_identity_kernel"));
+    } else if (h->lm) { // memlen = 0: no row is live; b = d = 0 (lm_cmaes.cpp:75-78)
+        BB_CUDA(cudaMemsetAsync(h->lmb, 0, (size_t) h->lm_mem * 8, st));
+        BB_CUDA(cudaMemsetAsync(h->lmd, 0, (size_t) h->lm_mem * 8, st));
     } else {
         fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(h->C, n, 1.0);
         BB_TRY(launched(ctx, "fill_kernel"));
@@ -1387,7 +1416,7 @@ int bbgpu_cma_device_ptr(bbgpu_cma *h, int field, void **d_ptr, int64_t *ld) {
 }
 
 int bbgpu_cma_sample(bbgpu_cma *h, double sigma, uint64_t generation, const double *h_z) {
-    BB_ARG(h);
+    BB_ARG(h && !h->lm);
     if (h_z != nullptr) { // lambda*n draws; a sharded handle consumes its own candidates' rows
         BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, h_z + (size_t) h->row0 * h->n, (size_t) h->n * 8, (size_t) h->n * 8,
                 h->lam_loc, cudaMemcpyHostToDevice, h->ctx->stream));
@@ -1400,7 +1429,7 @@ int bbgpu_cma_sample(bbgpu_cma *h, double sigma, uint64_t generation, const doub
 }
 
 int bbgpu_cma_sample_dev(bbgpu_cma *h, double sigma, const double *d_z) {
-    BB_ARG(h && d_z);
+    BB_ARG(h && d_z && !h->lm);
     BB_CUDA(cudaMemcpy2DAsync(h->Z, (size_t) h->ldn * 8, d_z + (size_t) h->row0 * h->n, (size_t) h->n * 8, (size_t) h->n * 8,
             h->lam_loc, cudaMemcpyDeviceToDevice, h->ctx->stream));
     h->zgen[h->zcur] = -1;
@@ -1423,7 +1452,7 @@ int bbgpu_cma_rank(bbgpu_cma *h, int ik) {
 }
 
 int bbgpu_cma_update(bbgpu_cma *h, double sigma, int fev) {
-    BB_ARG(h && sigma > 0.0);
+    BB_ARG(h && sigma > 0.0 && !h->lm);
     if (h->shards > 1) {
         if (!h->comm) return fail(BBGPU_ERR_ARG, "sharded handle without a communicator: use bbgpu_cma_shard_partial / _finish");
         BB_TRY(shard_partial(h));
@@ -1487,6 +1516,51 @@ int bbgpu_cma_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
     return do_eig(h, h_B, h_D);
 }
 
+// LM kind: samplePopulation (lm_cmaes.cpp:91-127)
+int bbgpu_cma_lm_sample(bbgpu_cma *h, double sigma, uint64_t generation, int memlen, const int32_t *h_jarr, const double *h_z,
+        const int32_t *h_i0) {
+    BB_ARG(h && h->lm && memlen >= 0 && memlen <= h->lm_mem && (memlen == 0 || h_jarr != nullptr));
+    BB_ARG((h_z == nullptr) == (h_i0 == nullptr));
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    h->last_sigma = sigma;
+    if (memlen > 0) BB_CUDA(cudaMemcpyAsync(h->lm_jarr, h_jarr, (size_t) memlen * 4, cudaMemcpyHostToDevice, st));
+    if (h_z != nullptr) {
+        BB_CUDA(cudaMemcpy2DAsync(h->Zp, (size_t) h->ldn * 8, h_z, (size_t) h->n * 8, (size_t) h->n * 8, h->lm_pairs, cudaMemcpyHostToDevice, st));
+        BB_CUDA(cudaMemcpyAsync(h->lm_i0, h_i0, (size_t) h->lm_pairs * 4, cudaMemcpyHostToDevice, st));
+    }
+    ProfScope prof(ctx, BBGPU_PROF_SEP_SAMPLE);
+    lm_sample_kernel<<<h->lm_pairs, 256, 0, st>>>(h->X, h->Zp, h->ldn, h->n, h->lambda, h->xmean, sigma, h->PCmat, h->Vmat, h->lmb,
+            h->lm_jarr, memlen, h->lm_i0, h_z != nullptr, h->cfg.lm_rademacher, h->cfg.lm_usenew, std::sqrt(1.0 - h->cfg.c1), h->cfg.seed,
+            generation);
+    return launched(ctx, "lm_sample_kernel");
+}
+
+// LM kind: updateDistribution up to updateSigma (lm_cmaes.cpp:129-178)
+int bbgpu_cma_lm_update(bbgpu_cma *h, double sigma, int do_memory, int imin, int memlen, const int32_t *h_jarr) {
+    BB_ARG(h && h->lm && sigma > 0.0 && memlen >= 0 && memlen <= h->lm_mem);
+    BB_ARG(!do_memory || (memlen >= 1 && imin >= 0 && imin <= memlen && h_jarr != nullptr));
+    bbgpu_ctx *ctx = h->ctx;
+    const bbgpu_cma_config &c = h->cfg;
+    const int n = h->n;
+    cudaStream_t st = ctx->stream;
+    const double *lo = c.bound ? h->lower : nullptr, *hi = c.bound ? h->upper : nullptr;
+    ProfScope prof(ctx, BBGPU_PROF_UPDATE_MISC);
+    BB_CUDA(cudaMemcpyAsync(h->xold, h->xmean, (size_t) n * 8, cudaMemcpyDeviceToDevice, st));
+    if (do_memory) BB_CUDA(cudaMemcpyAsync(h->lm_jarr, h_jarr, (size_t) memlen * 4, cudaMemcpyHostToDevice, st));
+    dim3 pgrid(ceil_div(n, 256), h->splits);
+    recombine_partial_kernel<false><<<pgrid, 256, 0, st>>>(h->part, h->X, h->ldn, n, h->mu, h->splits, h->rank_idx, h->weights, h->xold,
+            sigma);
+    BB_TRY(launched(ctx, "recombine_partial_kernel"));
+    recombine_final_kernel<false><<<ceil_div(n, 64), 256, 0, st>>>(h->part, n, h->splits, h->xmean, h->xold, h->dm, 1.0, sigma, lo, hi,
+            false, h->ps, nullptr, 0.0, 0.0, nullptr);
+    BB_TRY(launched(ctx, "recombine_final_kernel"));
+    const double ccc = std::sqrt(c.cc * (2.0 - c.cc) * c.mueff);
+    lm_memory_kernel<<<1, 1024, 0, st>>>(n, h->ldn, h->pc, h->xmean, h->xold, sigma, c.cc, ccc, c.c1, std::sqrt(1.0 - c.c1), do_memory, imin,
+            memlen, h->lm_jarr, h->PCmat, h->Vmat, h->lmb, h->lmd, h->tmpn);
+    return launched(ctx, "lm_memory_kernel");
+}
+
 // CholeskyCmaes::converged(), the O(lambda n) part (cholesky_cmaes.cpp:146-160): mean and M2 = sum (r_k - mean)^2 of
 // the candidates' Euclidean norms
 int bbgpu_cma_swarm_radius(bbgpu_cma *h, double *h_mean, double *h_m2) {
@@ -1521,7 +1595,7 @@ int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *out) {
 }
 
 int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint64_t generation, int ik, int fev_after) {
-    BB_ARG(h && obj && obj->n == h->n);
+    BB_ARG(h && obj && obj->n == h->n && !h->lm);
     if (!h->full && !h->chol && obj->mode == 0 && obj->id != BBGPU_OBJ_ROSENBROCK) {
         // separable kind, registry objective: draws, sampling and evaluation fused into one pass over X
         bbgpu_ctx *ctx = h->ctx;

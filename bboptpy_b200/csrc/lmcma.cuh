@@ -1,0 +1,153 @@
+// LM-CMA-ES on the device (reference: cma/lm_cmaes.cpp, Loshchilov 2014 / 2015).
+//
+// The covariance is implicit in `memory` direction vectors: rows of PC (the stored evolution paths, `_pcmat`) and V
+// (`_vmat`) with the scalars b, d; `jarr[0 .. memlen-1]` names the live rows in application order.  The bookkeeping of
+// jarr / larr (algorithm 5) is integer control logic and stays with the host class; the O(memory n) vector work per
+// candidate and the O(memory^2 n) rebuild of V are here.
+#pragma once
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace bb {
+
+constexpr int LM_MAXMEM = 1024; // direction vectors a handle can hold (dots staged in shared memory)
+constexpr int LM_GROUP = 8;     // inner products reduced together
+
+// samplePopulation (lm_cmaes.cpp:91-127), one CTA per PAIR of candidates (mirrored sampling):
+//   z_p        the base vector: replayed, or Rademacher / Gaussian from Philox block (coordinate pair, p, generation)
+//   i0         selectSubset (algorithm 6, :308-322): replayed, or memlen - min(memlen, int(msigma |N(0,1)|))
+//   dot_i      b_j (v_j . z_p), j = jarr[i], for i = i0 .. memlen-1 -- with the ORIGINAL z_p (:117-119), so all of them
+//              are independent: LM_GROUP at a time through one block reduction
+//   az         z_p, then az <- sqrt(1-c1) az + dot_i pc_j in the order of i (algorithm 3, :120-121), element-local
+//   x_{2p}, x_{2p+1} = m +- sigma az (:124)
+__global__ void __launch_bounds__(256) lm_sample_kernel(double *__restrict__ X, double *__restrict__ Zp, int64_t ld, int n, int lambda,
+        const double *__restrict__ xmean, double sigma, const double *__restrict__ PC, const double *__restrict__ V,
+        const double *__restrict__ b, const int *__restrict__ jarr, int memlen, const int *__restrict__ i0_in, bool replay,
+        int rademacher, int usenew, double sqrt1mc1, uint64_t seed, uint64_t generation) {
+    __shared__ double dots[LM_MAXMEM];
+    __shared__ double red[LM_GROUP][8];
+    __shared__ int s_i0;
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *z = Zp + (int64_t) p * ld;
+    if (!replay) {
+        for (int jp = tid; 2 * jp < n; jp += blockDim.x) {
+            const Philox4 r = philox4x32_10((uint32_t) jp, (uint32_t) p, (uint32_t) generation, (uint32_t) (generation >> 32) ^ 0x4c4d0000u,
+                    (uint32_t) seed, (uint32_t) (seed >> 32));
+            double z0, z1;
+            if (rademacher) {
+                z0 = (r.x & 1u) ? 1.0 : -1.0;
+                z1 = (r.z & 1u) ? 1.0 : -1.0;
+            } else {
+                normal_pair(r, z0, z1);
+            }
+            z[2 * jp] = z0;
+            if (2 * jp + 1 < n) z[2 * jp + 1] = z1;
+        }
+    }
+    if (tid == 0) {
+        int i0 = 0;
+        if (replay) i0 = i0_in[p];
+        else if (usenew && memlen > 1) {
+            const Philox4 r = philox4x32_10(0xffffffffu, (uint32_t) p, (uint32_t) generation, (uint32_t) (generation >> 32) ^ 0x4c4d0000u,
+                    (uint32_t) seed, (uint32_t) (seed >> 32));
+            double g0, g1;
+            normal_pair(r, g0, g1);
+            const int msigma = p == 0 ? 40 : 4; // k == 0: the first candidate of the generation (:313-316)
+            const double m = (double) msigma * fabs(g0);
+            const int mstar = m >= (double) memlen ? memlen : (int) m;
+            i0 = memlen - mstar;
+        }
+        s_i0 = i0;
+    }
+    __syncthreads();
+    const int i0 = s_i0;
+    for (int g0 = i0; g0 < memlen; g0 += LM_GROUP) {
+        double acc[LM_GROUP];
+        const double *vr[LM_GROUP];
+#pragma unroll
+        for (int u = 0; u < LM_GROUP; u++) {
+            acc[u] = 0.0;
+            vr[u] = V + (int64_t) jarr[min(g0 + u, memlen - 1)] * ld;
+        }
+        for (int e = tid; e < n; e += blockDim.x) {
+            const double ze = z[e];
+#pragma unroll
+            for (int u = 0; u < LM_GROUP; u++) acc[u] = fma(vr[u][e], ze, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < LM_GROUP; u++) {
+            const double s = warp_sum(acc[u]);
+            if (lane == 0) red[u][warp] = s;
+        }
+        __syncthreads();
+        if (tid < LM_GROUP && g0 + tid < memlen) {
+            double s = 0.0;
+            for (int w = 0; w < 8; w++) s += red[tid][w];
+            dots[g0 + tid] = __dmul_rn(b[jarr[g0 + tid]], s);
+        }
+        __syncthreads();
+    }
+    const bool second = 2 * p + 1 < lambda;
+    double *x0 = X + (int64_t) (2 * p) * ld, *x1 = X + (int64_t) (2 * p + 1) * ld;
+    for (int e = tid; e < n; e += blockDim.x) {
+        double a = z[e];
+        for (int i = i0; i < memlen; i++)
+            a = __dadd_rn(__dmul_rn(sqrt1mc1, a), __dmul_rn(dots[i], PC[(int64_t) jarr[i] * ld + e]));
+        const double me = xmean[e];
+        x0[e] = __dadd_rn(me, __dmul_rn(sigma, a));
+        if (second) x1[e] = __dadd_rn(me, __dmul_rn(-sigma, a));
+    }
+}
+
+// p_c (lm_cmaes.cpp:146-149: (1 - cc) pc + (ccc (m - m_old)) / sigma, no hsig) and, when the memory is due (:151-177):
+// PC[jarr[memlen-1]] <- p_c; for i = imin .. memlen-1: t <- PC[jarr[i]], pushed through the inverse transforms of rows
+// jarr[0 .. i-1] (algorithm 4, `ainvz`: every inner product uses the UPDATED t, a genuine chain), V[jarr[i]] <- t, then
+// b, d from |t|^2.  One CTA: the chain is up to memory^2 / 2 dependent reductions of length n.
+__global__ void __launch_bounds__(1024) lm_memory_kernel(int n, int64_t ld, double *__restrict__ pc, const double *__restrict__ xmean,
+        const double *__restrict__ xold, double sigma, double cc, double ccc, double c1, double sqrt1mc1, int do_memory, int imin,
+        int memlen, const int *__restrict__ jarr, double *__restrict__ PC, double *__restrict__ V, double *__restrict__ b,
+        double *__restrict__ d, double *__restrict__ t) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < n; e += blockDim.x)
+        pc[e] = __dadd_rn(__dmul_rn(1.0 - cc, pc[e]), __ddiv_rn(__dmul_rn(ccc, __dsub_rn(xmean[e], xold[e])), sigma));
+    if (!do_memory) return;
+    __syncthreads();
+    {
+        double *dst = PC + (int64_t) jarr[memlen - 1] * ld;
+        for (int e = tid; e < n; e += blockDim.x) dst[e] = pc[e];
+    }
+    __syncthreads();
+    const double c = 1.0 / sqrt1mc1;
+    for (int i = imin; i < memlen; i++) {
+        const int jcur = jarr[i];
+        const double *src = PC + (int64_t) jcur * ld;
+        for (int e = tid; e < n; e += blockDim.x) t[e] = src[e];
+        for (int k = 0; k < i; k++) {
+            const int idx = jarr[k];
+            const double *v = V + (int64_t) idx * ld;
+            double s = 0.0;
+            for (int e = tid; e < n; e += blockDim.x) s = fma(v[e], t[e], s);
+            s = block_sum(s, red);
+            const double dot = __dmul_rn(d[idx], s);
+            for (int e = tid; e < n; e += blockDim.x) t[e] = __dadd_rn(__dmul_rn(c, t[e]), __dmul_rn(-dot, v[e]));
+        }
+        double *vdst = V + (int64_t) jcur * ld;
+        double s = 0.0;
+        for (int e = tid; e < n; e += blockDim.x) {
+            const double te = t[e];
+            vdst[e] = te;
+            s = fma(te, te, s);
+        }
+        s = block_sum(s, red);
+        if (tid == 0) {
+            const double sqrtc1 = sqrt(1.0 + (c1 / (1.0 - c1)) * s);
+            b[jcur] = (sqrt1mc1 / s) * (sqrtc1 - 1.0);
+            d[jcur] = (1.0 / (sqrt1mc1 * s)) * (1.0 - 1.0 / sqrtc1);
+        }
+        __syncthreads(); // b / d / V of this row are read by the next rows' chains
+    }
+}
+
+} // namespace bb

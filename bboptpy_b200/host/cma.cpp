@@ -256,9 +256,10 @@ std::vector<double> BaseCmaes::state(const std::string &name) {
     const Entry table[] = { { "xmean", BBGPU_CMA_XMEAN, n }, { "xold", BBGPU_CMA_XOLD, n }, { "pc", BBGPU_CMA_PC, n },
             { "ps", BBGPU_CMA_PS, n }, { "D", BBGPU_CMA_D, n }, { "C", BBGPU_CMA_C, full ? n * n : n },
             { "B", BBGPU_CMA_B, n * n }, { "invsqrtC", BBGPU_CMA_INVSQRTC, n * n }, { "arx", BBGPU_CMA_ARX, lam * n },
-            { "z", BBGPU_CMA_Z, lam * n }, { "fitness", BBGPU_CMA_FITNESS, lam }, { "rankval", BBGPU_CMA_RANKVAL, lam },
+            { "z", BBGPU_CMA_Z, (deviceKind() == BBGPU_CMA_LM ? (lam + 1) / 2 : lam) * n }, { "fitness", BBGPU_CMA_FITNESS, lam }, { "rankval", BBGPU_CMA_RANKVAL, lam },
             { "ycoeff", BBGPU_CMA_YCOEFF, (int64_t) _mu }, { "weights", BBGPU_CMA_WEIGHTS, (int64_t) _mu },
-            { "A", BBGPU_CMA_A, n * n } };
+            { "A", BBGPU_CMA_A, n * n }, { "pcmat", BBGPU_CMA_PCMAT, memoryRows() * n }, { "vmat", BBGPU_CMA_VMAT, memoryRows() * n },
+            { "b", BBGPU_CMA_LMB, (int64_t) memoryRows() }, { "d", BBGPU_CMA_LMD, (int64_t) memoryRows() } };
     if (name == "rank") {
         std::vector<int32_t> idx(_lambda);
         gpu_check(bbgpu_cma_get_rank(_dev, idx.data(), _lambda));
@@ -319,13 +320,17 @@ std::vector<int> checkpoint_fields(int kind) {
     } else if (kind == BBGPU_CMA_SEP) {
         f.push_back(BBGPU_CMA_C);
         f.push_back(BBGPU_CMA_D);
+    } else if (kind == BBGPU_CMA_LM) {
+        for (int x : { BBGPU_CMA_PCMAT, BBGPU_CMA_VMAT, BBGPU_CMA_LMB, BBGPU_CMA_LMD }) f.push_back(x);
     } else {
         f.push_back(BBGPU_CMA_A);
     }
     return f;
 }
-int64_t field_length(int field, int kind, int64_t n, int64_t lam) {
+int64_t field_length(int field, int kind, int64_t n, int64_t lam, int64_t mem = 0) {
     switch (field) {
+    case BBGPU_CMA_PCMAT: case BBGPU_CMA_VMAT: return mem * n;
+    case BBGPU_CMA_LMB: case BBGPU_CMA_LMD: return mem;
     case BBGPU_CMA_ARX: return lam * n;
     case BBGPU_CMA_FITNESS: return lam;
     case BBGPU_CMA_C: return kind == BBGPU_CMA_SEP ? n : n * n;
@@ -346,7 +351,7 @@ std::string BaseCmaes::checkpoint() {
     io.pod(version); io.pod(kind); io.pod(n); io.pod(lambda); io.pod(mu);
     restoreOrSaveScalars(io);
     for (int f : checkpoint_fields(kind)) {
-        std::vector<double> v((size_t) field_length(f, kind, _n, _lambda));
+        std::vector<double> v((size_t) field_length(f, kind, _n, _lambda, memoryRows()));
         gpu_check(bbgpu_cma_get(_dev, f, v.data(), (int64_t) v.size()));
         io.vec(v);
     }
@@ -374,7 +379,7 @@ void BaseCmaes::restore(const std::string &blob) {
     for (int f : checkpoint_fields(kind)) {
         std::vector<double> v;
         io.vec(v);
-        if ((int64_t) v.size() != field_length(f, kind, _n, _lambda)) throw bbopt::GpuError("restore: field of the wrong length");
+        if ((int64_t) v.size() != field_length(f, kind, _n, _lambda, memoryRows())) throw bbopt::GpuError("restore: field of the wrong length");
         gpu_check(bbgpu_cma_set(_dev, f, v.data(), (int64_t) v.size()));
     }
     if (io.pos != blob.size()) throw bbopt::GpuError("restore: trailing bytes in the checkpoint");
@@ -574,4 +579,165 @@ void SepCmaes::extraState(StateIO &io) {
 
 void CholeskyCmaes::extraState(StateIO &io) {
     io.pod(_stol);
+}
+
+// ---------------------------------------------------------------------------------------
+// LmCmaes -- cma/lm_cmaes.cpp
+// ---------------------------------------------------------------------------------------
+void LmCmaes::init(const multivariate_problem &f, const double *guess) { // :42-89
+    BaseCmaes::init(f, guess);
+    if (_adaptmemory) _memsize = large_size(_n);
+    _memlen = 0;
+    if (_new) {
+        _nsteps = _n;
+        _t = std::max(1, static_cast<int>(std::log(1. * _n)));
+        _cc = 0.5 / std::sqrt(1. * _n);
+    } else {
+        _nsteps = _memsize;
+        _t = 1;
+        _cc = 1. / _memsize;
+    }
+    _cs = 0.3;
+    _c1 = 0.1 / std::log(_n + 1.);
+    _cmu = NAN;
+    _ccc = std::sqrt(_cc * (2. - _cc) * _mueff);
+    _damps = 1.;
+    _sqrt1mc1 = std::sqrt(1. - _c1);
+    _zstar = 0.25;
+    _s = 0.;
+    _jarr.assign(_memsize, 0);
+    _larr.assign(_memsize, 0);
+    _fp.assign(_lambda, 0.);
+    _fcur.assign(_lambda, 0.);
+    ensureDevice();
+}
+
+void LmCmaes::fillConfig(bbgpu_cma_config &cfg) const {
+    BaseCmaes::fillConfig(cfg);
+    cfg.cmu = 0.; // NAN in the reference (:65), never used
+    cfg.lm_memory = _memsize;
+    cfg.lm_rademacher = _samplemode;
+    cfg.lm_usenew = _new ? 1 : 0;
+}
+
+// :91-127.  Replay: per pair of candidates n base draws -- N(0,1) from _Z or Rademacher signs from uniform_real(0,1) < 0.5 --
+// then, in the 2015 variant with more than one live vector, the one normal of selectSubset (:308-322); all on the same
+// engine, in this order.
+void LmCmaes::samplePopulation() {
+    _dev_used = true;
+    if (_replay.enabled) {
+        const int pairs = (_lambda + 1) / 2;
+        _zbuf.resize((size_t) pairs * _n);
+        std::vector<int32_t> i0(pairs, 0);
+        std::uniform_real_distribution<double> u01(0., 1.);
+        for (int p = 0; p < pairs; p++) {
+            double *z = _zbuf.data() + (size_t) p * _n;
+            if (_samplemode == 0) {
+                for (int i = 0; i < _n; i++) z[i] = _replay.normal(_replay.eng());
+            } else {
+                for (int i = 0; i < _n; i++) z[i] = u01(_replay.eng()) < 0.5 ? 1. : -1.;
+            }
+            if (_new && _memlen > 1) {
+                const int msigma = p == 0 ? 40 : 4;
+                int mstar = static_cast<int>(msigma * std::abs(_replay.normal(_replay.eng())));
+                mstar = std::min(mstar, _memlen);
+                i0[p] = _memlen - mstar;
+            }
+        }
+        gpu_check(bbgpu_cma_lm_sample(_dev, _sigma, _gen, _memlen, _jarr.data(), _zbuf.data(), i0.data()));
+    } else {
+        gpu_check(bbgpu_cma_lm_sample(_dev, _sigma, _gen, _memlen, _jarr.data(), nullptr, nullptr));
+    }
+    _gen++;
+}
+
+// :228-238: the previous generation's sorted fitness is kept for the pooled ranking
+void LmCmaes::evaluateAndSortPopulation() {
+    if (_it > 0) _fp = _fcur;
+    BaseCmaes::evaluateAndSortPopulation();
+    gpu_check(bbgpu_cma_get(_dev, BBGPU_CMA_RANKVAL, _fcur.data(), _lambda));
+}
+
+// :274-306 (algorithm 5)
+int LmCmaes::updateSet() {
+    const int it = _it / _t;
+    int imin = 1;
+    if (it < _memsize) {
+        _jarr[it] = it;
+    } else if (_memsize > 1) {
+        int iminval = _larr[_jarr[1]] - _larr[_jarr[0]];
+        for (int i = 1; i < _memsize - 1; i++) {
+            const int val = _larr[_jarr[i + 1]] - _larr[_jarr[i]];
+            if (val < iminval) {
+                iminval = val;
+                imin = i + 1;
+            }
+        }
+        if (iminval >= _nsteps) imin = 0;
+        const int jtmp = _jarr[imin];
+        for (int i = imin; i < _memsize - 1; i++) _jarr[i] = _jarr[i + 1];
+        _jarr[_memsize - 1] = jtmp;
+    }
+    const int jcur = _jarr[std::min(it, _memsize - 1)];
+    _larr[jcur] = _it;
+    return imin == 1 ? 0 : imin;
+}
+
+// :129-181
+void LmCmaes::updateDistribution() {
+    const bool due = _it % _t == 0;
+    int imin = 0;
+    if (due) {
+        imin = updateSet();
+        if (_memlen < _memsize) _memlen++;
+    }
+    gpu_check(bbgpu_cma_lm_update(_dev, _sigma, due ? 1 : 0, imin, _memlen, _jarr.data()));
+    fetchReport();
+    updateSigma();
+}
+
+// :240-258: rank-based success rule on the pooled previous + current fitness
+void LmCmaes::updateSigma() {
+    if (_it == 0) return;
+    struct pooled { int _index; double _value; }; // cmaes_index, base_cmaes.h:30-38
+    std::vector<pooled> mixed(2 * (size_t) _lambda);
+    for (int n = 0; n < _lambda; n++) {
+        mixed[n] = pooled { n, _fp[n] };
+        mixed[n + _lambda] = pooled { n + _lambda, _fcur[n] };
+    }
+    std::sort(mixed.begin(), mixed.end(), [](const pooled &x, const pooled &y) { return x._value < y._value; });
+    double zpsr = 0.;
+    for (int n = 0; n < (_lambda << 1); n++) {
+        const double f = (1. * n) / _lambda;
+        if (mixed[n]._index < _lambda) zpsr += f;
+        else zpsr -= f;
+    }
+    zpsr /= (1. * _lambda);
+    zpsr -= _zstar;
+    _s = (1. - _cs) * _s + _cs * zpsr;
+    _sigma *= std::exp(_s / _damps);
+}
+
+// :183-226
+bool LmCmaes::converged() {
+    if (_it >= _mit) return true;
+    if (_sigma < _stolmin) return true;
+    if (_it >= _hlen && _fworst - _fbest < _tol) return true;
+    if (_best._len >= _n && _kth._len >= _n) {
+        int countEq = 0;
+        for (int i = 0; i < _n; i++) {
+            if (_best.get(i) == _kth.get(i)) {
+                countEq++;
+                if (3 * countEq >= _n) return true;
+            }
+        }
+    }
+    return false;
+}
+
+void LmCmaes::extraState(StateIO &io) {
+    io.flag(_new); io.flag(_adaptmemory);
+    io.pod(_samplemode); io.pod(_memlen); io.pod(_memsize); io.pod(_nsteps); io.pod(_t);
+    io.pod(_stolmin); io.pod(_sqrt1mc1); io.pod(_zstar); io.pod(_s); io.pod(_ccc);
+    io.vec(_jarr); io.vec(_larr); io.vec(_fp); io.vec(_fcur);
 }

@@ -7,6 +7,7 @@
 #ifndef BBOPT_HOST_CMA_H_
 #define BBOPT_HOST_CMA_H_
 
+#include <cmath>
 #include <functional>
 #include <string>
 #include <vector>
@@ -55,6 +56,7 @@ protected:
     struct StateIO;
     virtual void extraState(StateIO &io);
     void restoreOrSaveScalars(StateIO &io);
+    virtual int memoryRows() const { return 0; } // LM kind: rows of the direction-vector matrices
     void ensureDevice();
     void fetchReport();
 
@@ -183,6 +185,44 @@ public:
     void init(const multivariate_problem &f, const double *guess);
     void updateDistribution();
     bool converged();
+};
+
+// cma/lm_cmaes.h:36-92 (Loshchilov 2014 / 2015).  Host: the memory bookkeeping (jarr / larr, algorithm 5), the pooled-ranking
+// step size (:240-258) and the stop tests; device: mirrored sampling through the direction vectors and their rebuild.
+class LmCmaes: public BaseCmaes {
+protected:
+    bool _new, _adaptmemory;
+    int _samplemode, _memlen, _memsize, _nsteps, _t;
+    double _stolmin, _sqrt1mc1, _zstar, _s, _ccc;
+    std::vector<int> _jarr, _larr;
+    std::vector<double> _fp, _fcur;
+    int deviceKind() const override { return BBGPU_CMA_LM; }
+    int memoryRows() const override { return _memsize; }
+    void fillConfig(bbgpu_cma_config &cfg) const override;
+    void extraState(StateIO &io) override;
+    int updateSet();
+
+public:
+    LmCmaes(int mfev, double tol, int np, int memory = 0, double sigma0 = 2., bool bound = false, bool rademacher = true,
+            bool usenew = true) :
+            BaseCmaes(mfev, tol, np, sigma0, bound) {
+        _samplemode = rademacher ? 1 : 0;
+        _new = usenew;
+        _stolmin = 1e-16;
+        _memsize = memory;
+        _adaptmemory = memory <= 0;
+        _memlen = _nsteps = 0;
+        _t = 1;
+        _sqrt1mc1 = _zstar = _s = _ccc = 0.;
+    }
+    static int large_size(const int x) { return static_cast<int>(2. * std::sqrt(1. * x)); }
+    void init(const multivariate_problem &f, const double *guess);
+    void samplePopulation();
+    void updateDistribution();
+    bool converged();
+    void evaluateAndSortPopulation();
+    void updateSigma();
+    int memoryLength() const { return _memlen; }
 };
 
 #endif

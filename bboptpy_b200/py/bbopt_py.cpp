@@ -182,6 +182,12 @@ PYBIND11_MODULE(_bboptpy, m) {
         .def(py::init<int, double, double, int, double, bool>(), "mfev"_a, "tol"_a, "stol"_a, "np"_a, "sigma0"_a = 2.,
              "bound"_a = false);
 
+    // py/multivariate_py.cpp:123-128
+    py::class_<LmCmaes, BaseCmaes>(m, "LmCMAES")
+        .def(py::init<int, double, int, int, double, bool, bool, bool>(), "mfev"_a, "tol"_a, "np"_a, "memory"_a = 0, "sigma0"_a = 2.,
+             "bound"_a = false, "rademacher"_a = true, "usenew"_a = true)
+        .def_property_readonly("memory_length", &LmCmaes::memoryLength);
+
     py::class_<IPopCmaes, MultivariateOptimizer>(m, "IPopCMAES")
         .def(py::init<BaseCmaes*, int, bool, double, bool, double, bool>(), "base"_a, "mfev"_a, "print"_a = false,
              "sigma0"_a = 2., "nipop"_a = true, "ksigmadec"_a = 1.6, "boundlambda"_a = true, py::keep_alive<1, 2>())

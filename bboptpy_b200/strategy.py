@@ -43,6 +43,8 @@ def cma_constants(kind, n, lam, alphacov=2.0, adjustlr=True, eigenrate=0.25):
         c["eigenfreq"] = eigenrate * (1.0 / (c["c1"] + c["cmu"] + c["cneg"])) / n
     elif kind == 3:
         pass
+    elif kind == 4:
+        raise ValueError("LM-CMA-ES constants depend on its constructor arguments: see host/cma.cpp LmCmaes::init")
     else:
         c["cc"] = 4.0 / (n + 4.0)
         c["cs"] = (mueff + 2.0) / (3.0 + n + mueff)

@@ -119,7 +119,10 @@ int bbgpu_eval_host(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *h_X, int
 /* BBGPU_CMA_CHOLESKY: cma/cholesky_cmaes.cpp -- the factor A (C = A A^T) instead of C / B / D; sampling x = m + sigma A z on
  * the same tensor-core GEMM, the mu + 1 sequential rank-one updates of the factor (:85-90,163-177) as one SYRK + one blocked
  * Cholesky factorisation (the factor is unique), no eigendecomposition at all */
-enum bbgpu_cma_kind { BBGPU_CMA_FULL = 0, BBGPU_CMA_ACTIVE = 1, BBGPU_CMA_SEP = 2, BBGPU_CMA_CHOLESKY = 3 };
+/* BBGPU_CMA_LM: cma/lm_cmaes.cpp (Loshchilov 2014/2015) -- the covariance is implicit in `memory` direction vectors: rows of
+ * PCMAT / VMAT with the coefficients LMB / LMD; mirrored sampling of lambda/2 base vectors (bbgpu_cma_lm_sample), the memory
+ * bookkeeping (which rows are live, in which order: `jarr`) stays with the host class */
+enum bbgpu_cma_kind { BBGPU_CMA_FULL = 0, BBGPU_CMA_ACTIVE = 1, BBGPU_CMA_SEP = 2, BBGPU_CMA_CHOLESKY = 3, BBGPU_CMA_LM = 4 };
 
 typedef struct bbgpu_cma_config {
     int kind;       /* bbgpu_cma_kind */
@@ -135,6 +138,9 @@ typedef struct bbgpu_cma_config {
     double cc, cs, c1, cmu, mueff, chi;
     double cneg, alphaold, cm; /* active only */
     double ccov;               /* sep only */
+    /* LM only (cma/lm_cmaes.cpp:42-66): number of direction vectors, Rademacher (1) or Gaussian (0) base draws, the 2015
+     * variant with a random subset of the vectors per sample (algorithm 6) */
+    int lm_memory, lm_rademacher, lm_usenew;
 } bbgpu_cma_config;
 
 enum bbgpu_cma_field {
@@ -157,7 +163,11 @@ enum bbgpu_cma_field {
     BBGPU_CMA_NORMS = 14,     /* lambda, ||C^-1/2 (x_k - m)||^2 by candidate index (active) */
     BBGPU_CMA_SHARD_RED = 15, /* n*ld + ld: this GPU's rank-mu partial (lower triangle, row pitch
                                  ld = ceil(n/8)*8) followed by its partial sum_k w_k x_k */
-    BBGPU_CMA_A = 16          /* Cholesky kind: n*n, the lower-triangular factor `_a` (cma/cholesky_cmaes.h:36) */
+    BBGPU_CMA_A = 16,         /* Cholesky kind: n*n, the lower-triangular factor `_a` (cma/cholesky_cmaes.h:36) */
+    BBGPU_CMA_PCMAT = 17,     /* LM kind: memory*n, `_pcmat` (cma/lm_cmaes.h:44) */
+    BBGPU_CMA_VMAT = 18,      /* LM kind: memory*n, `_vmat` */
+    BBGPU_CMA_LMB = 19,       /* LM kind: memory, `_b` */
+    BBGPU_CMA_LMD = 20        /* LM kind: memory, `_d` */
 };
 
 /* everything the host class needs back per generation; filled by bbgpu_cma_fetch */
@@ -213,6 +223,16 @@ int bbgpu_cma_update(bbgpu_cma *h, double sigma, int fev);
 int bbgpu_cma_eig(bbgpu_cma *h, const double *h_B, const double *h_D);
 /* quantities for converged(): cma/cmaes.cpp:184-229, cma/sep_cmaes.cpp:170-205 */
 int bbgpu_cma_probe(bbgpu_cma *h, double sigma, int iaxis);
+/* LM kind, samplePopulation() (cma/lm_cmaes.cpp:91-127): candidates 2p and 2p+1 are m +- sigma Az_p, Az_p = the base vector
+ * z_p pushed through live memory rows jarr[i0_p .. memlen-1] (algorithm 3; the inner products use the ORIGINAL z_p, :117).
+ * h_z / h_i0 == NULL: base vectors (Rademacher or Gaussian) and subset starts from the Philox stream; otherwise DRAW REPLAY:
+ * ceil(lambda/2)*n base values and ceil(lambda/2) subset starts in the reference's order.  No box clipping (:124). */
+int bbgpu_cma_lm_sample(bbgpu_cma *h, double sigma, uint64_t generation, int memlen, const int32_t *h_jarr,
+                        const double *h_z, const int32_t *h_i0);
+/* LM kind, updateDistribution() up to updateSigma() (cma/lm_cmaes.cpp:129-178): mean, p_c, and -- when do_memory
+ * (it % t == 0) -- p_c stored as row jarr[memlen-1] of PCMAT and rows jarr[imin .. memlen-1] of VMAT / LMB / LMD rebuilt
+ * (algorithm 4).  jarr / memlen / imin AFTER the host's updateSet() (algorithm 5, :274-306). */
+int bbgpu_cma_lm_update(bbgpu_cma *h, double sigma, int do_memory, int imin, int memlen, const int32_t *h_jarr);
 /* Cholesky kind, converged() (cma/cholesky_cmaes.cpp:146-160): mean and M2 = sum_k (r_k - mean)^2 of the candidates'
  * Euclidean norms r_k (what the reference's Welford recurrence over dnrm2(_arx[k]) accumulates); synchronises */
 int bbgpu_cma_swarm_radius(bbgpu_cma *h, double *h_mean, double *h_m2);
