@@ -329,6 +329,7 @@ def run_reference(args):
         "timed_region_s": timed_s,
         "de": de,
         "cholesky": {"gens_per_s": cpu_chol_sample(o), "sample": "1 whole generation of CholeskyCmaes, n=1000 lambda=4096, 1 thread"},
+        "lm_cma": {"gens_per_s": cpu_lm_sample(o), "sample": f"40 generations of LmCmaes, n={LM_N} lambda={LM_LAMBDA}, 1 thread"},
         "bipop_batch": cpu_bipop_sample(o),
     }
     print(json.dumps(line))
@@ -466,6 +467,33 @@ def cpu_chol_sample(o, seed=1):
     t0 = time.perf_counter()
     h.iterate()
     return 1.0 / (time.perf_counter() - t0)
+
+
+LM_N, LM_LAMBDA = 10000, 64
+
+
+def bench_lm_e2e(pkg, gens, seed):
+    """LM-CMA-ES (cma/lm_cmaes.cpp), the reference's large-n variant: n = 10^4, lambda = 64, default memory (2 sqrt(n) = 200
+    direction vectors), Ellipsoid, through the Python API (host buffers in, solution out)."""
+    n, lam = LM_N, LM_LAMBDA
+    lower, upper, guess = -BOX * np.ones(n), BOX * np.ones(n), np.random.default_rng(seed).uniform(-BOX, BOX, n)
+    alg = pkg.LmCMAES(mfev=gens * lam, tol=0.0, np=lam)
+    t0 = time.perf_counter()
+    sol = alg.optimize(pkg.Ellipsoid, lower, upper, guess)
+    dt = time.perf_counter() - t0
+    return (sol.n_evals // lam) / dt
+
+
+def cpu_lm_sample(o, gens=40, seed=1):
+    from oracle import oracle as O
+    o.seed(seed)
+    n = LM_N
+    h = o.cma(O.LM, 10 ** 9, 0.0, LM_LAMBDA)
+    h.init(O.ELLIPSOID, -BOX * np.ones(n), BOX * np.ones(n), o.uniform(-BOX, BOX, n))
+    t0 = time.perf_counter()
+    for _ in range(gens):
+        h.iterate()
+    return gens / (time.perf_counter() - t0)
 
 
 def bench_de_device(ctx, kind, steps, warmup, seed):
@@ -721,6 +749,10 @@ def run_own(args):
     chol["gens_per_s"] = world * 1e3 / t_ch
     bench_chol_e2e(pkg, 2, seed=1 + rank)
     chol["e2e_gens_per_s"] = world * 1.0 / all_max(dist, local, 1.0 / bench_chol_e2e(pkg, e2e_gens, seed=1 + rank))
+    bench_lm_e2e(pkg, 20, seed=1 + rank)
+    lm = {"e2e_gens_per_s": world * 1.0 / all_max(dist, local, 1.0 / bench_lm_e2e(pkg, 400, seed=1 + rank)),
+          "workload": f"LmCMAES n={LM_N} lambda={LM_LAMBDA} memory=200 Ellipsoid, 400 generations through the Python API "
+                      "(cma/lm_cmaes.cpp; the memory fills during the run)"}
     # one large-lambda run sharded by candidates over all GPUs of the job (N > 1 only)
     sharded = None
     pycomm = None
@@ -828,6 +860,7 @@ def run_own(args):
         "de": de,
         "sep": sep,
         "cholesky": chol,
+        "lm_cma": lm,
         "bipop_batch": bipop,
     }
     chol["workload"] = "CholeskyCmaes n=1000 lambda=4096 Rosenbrock (cma/cholesky_cmaes.cpp; no eigendecomposition: SYRK + blocked Cholesky)"
@@ -845,6 +878,7 @@ def run_own(args):
                                 "t_generation_s": cs["t_generation"],
                                 "de_jade_evals_per_s": cpu_de_sample(o, 0), "de_shade_evals_per_s": cpu_de_sample(o, 1),
                                 "cholesky_gens_per_s": cpu_chol_sample(o),
+                                "lm_cma_gens_per_s": cpu_lm_sample(o),
                                 "bipop_batch": cpu_bipop_sample(o)}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 

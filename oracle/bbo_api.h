@@ -87,6 +87,20 @@ int bbo_de_geti(void *h, const char *name);
 double bbo_de_getd(void *h, const char *name);
 int bbo_de_getv(void *h, const char *name, double *out, int cap);
 
+/* ---- xNES (nes/xnes.cpp): exponential natural evolution strategy; np = 4 + floor(3 ln n) points, the mean starts at
+ * the origin (the guess is ignored, :82).  getv: "u", "mu", "B" (n*n), "Gdelta", and -- in sorted order after iterate() --
+ * "x" (np*n), "z" (np*n), "f" (np) */
+void *bbo_xnes_new(int mfev, double tol, double a0, double etamu);
+void bbo_xnes_free(void *h);
+void bbo_xnes_init(void *h, int obj, int n, const double *lower, const double *upper, const double *guess);
+void bbo_xnes_iterate(void *h);
+int bbo_xnes_converged(void *h);
+int bbo_xnes_optimize(void *h, int obj, int n, const double *lower, const double *upper, const double *guess,
+                      double *xout, int *fev);
+int bbo_xnes_geti(void *h, const char *name);
+double bbo_xnes_getd(void *h, const char *name);
+int bbo_xnes_getv(void *h, const char *name, double *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,21 @@ def _bind(lib):
     lib.bbo_restart_optimize.argtypes = [i, vp, i, d, i, d, i, i, d, i, i, _c_dp, _c_dp, _c_dp,
                                          _c_dp, ctypes.POINTER(i), _c_dp, i]
     lib.bbo_restart_optimize.restype = i
+    lib.bbo_xnes_new.restype = vp
+    lib.bbo_xnes_new.argtypes = [i, d, d, d]
+    lib.bbo_xnes_free.argtypes = [vp]
+    lib.bbo_xnes_init.argtypes = [vp, i, i, _c_dp, _c_dp, _c_dp]
+    lib.bbo_xnes_iterate.argtypes = [vp]
+    lib.bbo_xnes_converged.argtypes = [vp]
+    lib.bbo_xnes_converged.restype = i
+    lib.bbo_xnes_optimize.argtypes = [vp, i, i, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.POINTER(i)]
+    lib.bbo_xnes_optimize.restype = i
+    lib.bbo_xnes_geti.argtypes = [vp, cp]
+    lib.bbo_xnes_geti.restype = i
+    lib.bbo_xnes_getd.argtypes = [vp, cp]
+    lib.bbo_xnes_getd.restype = d
+    lib.bbo_xnes_getv.argtypes = [vp, cp, _c_dp, i]
+    lib.bbo_xnes_getv.restype = i
     lib.bbo_de_new.restype = vp
     lib.bbo_de_new.argtypes = [i, i, i, d, i, i, d, d, d, i, i]
     lib.bbo_de_free.argtypes = [vp]
@@ -128,6 +143,9 @@ class Oracle:
         if kind == LM:
             eigenrate, alphacov, adjustlr = float(memory), float(bool(rademacher)), bool(usenew)
         return OracleCma(self, kind, mfev, tol, np_, sigma0, bound, eigenrate, alphacov, adjustlr)
+
+    def xnes(self, mfev, tol, a0=1.0, etamu=1.0):
+        return OracleXnes(self, mfev, tol, a0, etamu)
 
     def de(self, kind, mfev, np_, tol, archive=True, repaircr=True, pelite=0.05, cdamp=0.1,
            sigma=0.07, h=100, npmin=4):
@@ -265,6 +283,55 @@ class OracleCma:
         if self.kind == SEP:
             s["ccov"] = self.getd("ccov")
         return s
+
+
+class OracleXnes:
+    """nes/xnes.cpp behind bbo_xnes_*."""
+
+    def __init__(self, o, mfev, tol, a0, etamu):
+        self.o, self.lib = o, o.lib
+        self.h = self.lib.bbo_xnes_new(mfev, tol, a0, etamu)
+
+    def __del__(self):
+        try:
+            self.lib.bbo_xnes_free(self.h)
+        except Exception:
+            pass
+
+    def init(self, obj, lower, upper, guess):
+        lower, upper, guess = _f64(lower), _f64(upper), _f64(guess)
+        self.lib.bbo_xnes_init(self.h, obj, lower.size, lower.ctypes.data, upper.ctypes.data, guess.ctypes.data)
+
+    def iterate(self):
+        self.lib.bbo_xnes_iterate(self.h)
+
+    def converged(self):
+        return bool(self.lib.bbo_xnes_converged(self.h))
+
+    def optimize(self, obj, lower, upper, guess):
+        lower, upper, guess = _f64(lower), _f64(upper), _f64(guess)
+        x = np.empty(lower.size)
+        fev = ctypes.c_int(0)
+        conv = self.lib.bbo_xnes_optimize(self.h, obj, lower.size, lower.ctypes.data, upper.ctypes.data, guess.ctypes.data,
+                                          x.ctypes.data, ctypes.byref(fev))
+        return x, fev.value, bool(conv)
+
+    def geti(self, name):
+        return self.lib.bbo_xnes_geti(self.h, name.encode())
+
+    def getd(self, name):
+        return self.lib.bbo_xnes_getd(self.h, name.encode())
+
+    def getv(self, name):
+        n = self.lib.bbo_xnes_getv(self.h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype=np.float64)
+        self.lib.bbo_xnes_getv(self.h, name.encode(), out.ctypes.data, n)
+        return out
+
+    def mat(self, name):
+        return self.getv(name).reshape(-1, self.geti("n"))
 
 
 class OracleDe:

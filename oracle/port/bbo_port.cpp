@@ -982,6 +982,123 @@ struct PortCma {
     }
 };
 
+/* ---- nes/xnes.cpp.  Its tred2 / tql2 (:255-449) are the same EISPACK / JAMA routines as Cmaes's (cmaes.cpp:285-478, equal
+ * line for line), so the eigensolver of PortCma is reused as a workspace. */
+struct XnesPoint {
+    double f;
+    std::vector<double> x, z;
+    static bool less(const XnesPoint &a, const XnesPoint &b) { return a.f < b.f; }
+};
+
+struct PortXnes {
+    int mfev = 0, n = 0, np = 0, fev = 0;
+    double tol = 0, a0 = 1, etamu = 1, etasigma = 0, etab = 0, sigma = 0, Gsigma = 0;
+    Objective f;
+    std::vector<double> lower, upper, u, mu, Gdelta, B, G, c;
+    std::vector<XnesPoint> points;
+    BboNormal Z;
+    PortCma eig; /* eig.B = matrix in / eigenvectors out, eig.d = eigenvalues, eig.tmp = off-diagonal workspace */
+
+    void init() { /* :50-108; the guess is not used (:82: `_mu` starts at the origin) */
+        np = 4 + (int) (3.0 * std::log(n));
+        etasigma = 3.0 * (3.0 + std::log(n)) / (5.0 * n * std::sqrt(n));
+        etab = etasigma;
+        u.assign(np, 0.0);
+        double sumu = 0.0;
+        for (int i = 1; i <= np; i++) {
+            const double ui = std::max(0.0, std::log(1 + 0.5 * np) - std::log(i));
+            u[i - 1] = ui;
+            sumu += ui;
+        }
+        for (int i = 0; i < np; i++) u[i] = u[i] / sumu - (1.0 / np);
+        mu.assign(n, 0.0);
+        sigma = a0;
+        B.assign((size_t) n * n, 0.0);
+        for (int i = 0; i < n; i++) B[(size_t) i * n + i] = a0 / sigma;
+        points.assign(np, XnesPoint { 0.0, std::vector<double>(n), std::vector<double>(n) });
+        fev = 0;
+        Gdelta.assign(n, 0.0);
+        G.assign((size_t) n * n, 0.0);
+        c.assign((size_t) n * n, 0.0);
+        eig.n = n;
+        eig.B.assign((size_t) n * n, 0.0);
+        eig.d.assign(n, 0.0);
+        eig.tmp.assign(n, 0.0);
+    }
+
+    void exponential() { /* :227-253 */
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j <= i; j++) eig.B[(size_t) i * n + j] = eig.B[(size_t) j * n + i] = c[(size_t) i * n + j];
+        eig.tridiagonalize();
+        eig.ql_implicit();
+        for (int i = 0; i < n; i++) eig.d[i] = std::exp(eig.d[i]);
+        for (int i = 0; i < n; i++) {
+            for (int j = 0; j <= i; j++) {
+                double sum = 0.0;
+                for (int k = 0; k < n; k++) sum += eig.B[(size_t) i * n + k] * eig.d[k] * eig.B[(size_t) j * n + k];
+                c[(size_t) i * n + j] = c[(size_t) j * n + i] = sum;
+            }
+        }
+    }
+
+    void iterate() { /* :110-191 */
+        for (int i = 0; i < np; i++) {
+            XnesPoint &p = points[i];
+            for (int d = 0; d < n; d++) p.z[d] = Z.draw(eng());
+            for (int d = 0; d < n; d++) {
+                p.x[d] = mu[d];
+                for (int j = 0; j < n; j++) p.x[d] += sigma * B[(size_t) d * n + j] * p.z[j];
+            }
+            p.f = f(p.x.data());
+        }
+        fev += np;
+        std::sort(points.begin(), points.end(), XnesPoint::less);
+        for (int d = 0; d < n; d++) {
+            Gdelta[d] = 0.0;
+            for (int i = 0; i < np; i++) Gdelta[d] += u[i] * points[i].z[d];
+        }
+        for (int d1 = 0; d1 < n; d1++) {
+            for (int d2 = 0; d2 < n; d2++) {
+                double g = 0.0;
+                for (int i = 0; i < np; i++) {
+                    const double z1 = points[i].z[d1], z2 = points[i].z[d2];
+                    g += u[i] * (z1 * z2 - ((d1 == d2) ? 1.0 : 0.0));
+                }
+                G[(size_t) d1 * n + d2] = g;
+            }
+        }
+        Gsigma = 0.0;
+        for (int d = 0; d < n; d++) Gsigma += G[(size_t) d * n + d] / n;
+        for (int d = 0; d < n; d++) G[(size_t) d * n + d] -= Gsigma * 1.0;
+        for (int d = 0; d < n; d++)
+            for (int j = 0; j < n; j++) mu[d] += etamu * sigma * B[(size_t) d * n + j] * Gdelta[j];
+        sigma *= std::exp(0.5 * etasigma * Gsigma);
+        for (size_t q = 0; q < (size_t) n * n; q++) c[q] = 0.5 * etab * G[q];
+        exponential();
+        for (int d1 = 0; d1 < n; d1++) {
+            for (int d2 = 0; d2 < n; d2++) {
+                double g = 0.0;
+                for (int j = 0; j < n; j++) g += B[(size_t) d1 * n + j] * c[(size_t) j * n + d2];
+                G[(size_t) d1 * n + d2] = g;
+            }
+        }
+        B = G;
+    }
+
+    bool converged() const { return std::fabs(points[0].f - points[np - 1].f) < tol; } /* :211-219 */
+
+    bool optimize(std::vector<double> &xout) { /* :197-209 */
+        init();
+        bool conv = false;
+        while (fev < mfev) {
+            iterate();
+            if (converged()) { conv = true; break; }
+        }
+        xout = points[0].x;
+        return conv;
+    }
+};
+
 void cma_bind(PortCma *p, int obj, int n, const double *lower, const double *upper) {
     p->n = n;
     p->f.bind(obj, n);
@@ -1578,6 +1695,87 @@ int bbo_restart_optimize(int kind, void *base, int mfev, double sigma0, int flag
     for (int i = 0; i < n; i++) xout[i] = xbest[i];
     *fevout = fev;
     return rows;
+}
+
+void *bbo_xnes_new(int mfev, double tol, double a0, double etamu) {
+    PortXnes *p = new PortXnes();
+    p->mfev = mfev;
+    p->tol = tol;
+    p->a0 = a0;
+    p->etamu = etamu;
+    return p;
+}
+void bbo_xnes_free(void *h) { delete static_cast<PortXnes*>(h); }
+
+static void xnes_bind(PortXnes *p, int obj, int n, const double *lower, const double *upper) {
+    p->n = n;
+    p->f.bind(obj, n);
+    p->lower.assign(lower, lower + n);
+    p->upper.assign(upper, upper + n);
+}
+
+void bbo_xnes_init(void *h, int obj, int n, const double *lower, const double *upper, const double *guess) {
+    (void) guess;
+    PortXnes *p = static_cast<PortXnes*>(h);
+    xnes_bind(p, obj, n, lower, upper);
+    p->init();
+}
+void bbo_xnes_iterate(void *h) { static_cast<PortXnes*>(h)->iterate(); }
+int bbo_xnes_converged(void *h) { return static_cast<PortXnes*>(h)->converged() ? 1 : 0; }
+
+int bbo_xnes_optimize(void *h, int obj, int n, const double *lower, const double *upper, const double *guess, double *xout,
+        int *fev) {
+    (void) guess;
+    PortXnes *p = static_cast<PortXnes*>(h);
+    xnes_bind(p, obj, n, lower, upper);
+    std::vector<double> x;
+    const bool conv = p->optimize(x);
+    for (int i = 0; i < n; i++) xout[i] = x[i];
+    *fev = p->fev;
+    return conv ? 1 : 0;
+}
+
+int bbo_xnes_geti(void *h, const char *name) {
+    PortXnes *p = static_cast<PortXnes*>(h);
+    const std::string k(name);
+    if (k == "n") return p->n;
+    if (k == "np") return p->np;
+    if (k == "fev") return p->fev;
+    return -1;
+}
+
+double bbo_xnes_getd(void *h, const char *name) {
+    PortXnes *p = static_cast<PortXnes*>(h);
+    const std::string k(name);
+    if (k == "sigma") return p->sigma;
+    if (k == "etasigma") return p->etasigma;
+    if (k == "etab") return p->etab;
+    if (k == "etamu") return p->etamu;
+    if (k == "Gsigma") return p->Gsigma;
+    return NAN;
+}
+
+int bbo_xnes_getv(void *h, const char *name, double *out, int cap) {
+    PortXnes *p = static_cast<PortXnes*>(h);
+    const std::string k(name);
+    if (k == "u") return put(p->u, out, cap);
+    if (k == "mu") return put(p->mu, out, cap);
+    if (k == "B") return put(p->B, out, cap);
+    if (k == "Gdelta") return put(p->Gdelta, out, cap);
+    if (k == "x" || k == "z") {
+        int len = 0;
+        for (const XnesPoint &pt : p->points)
+            for (double v : (k == "x" ? pt.x : pt.z)) {
+                if (len < cap) out[len] = v;
+                len++;
+            }
+        return len;
+    }
+    if (k == "f") {
+        for (int i = 0; i < (int) p->points.size() && i < cap; i++) out[i] = p->points[i].f;
+        return (int) p->points.size();
+    }
+    return -1;
 }
 
 void *bbo_de_new(int kind, int mfev, int np, double tol, int archive, int repaircr,

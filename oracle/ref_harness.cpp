@@ -3,7 +3,7 @@
  *
  * Built by oracle/Makefile: this file + /root/reference/src/{blas.cpp,
  * multivariate/cma/{base_cmaes,cmaes,active_cmaes,sep_cmaes,cholesky_cmaes,lm_cmaes,ipop_cmaes,bipop_cmaes}.cpp,
- * multivariate/de/{jade,shade}.cpp} compiled where they lie -> oracle/_ref/libbbo_ref.so.
+ * multivariate/de/{jade,shade}.cpp, multivariate/nes/xnes.cpp} compiled where they lie -> oracle/_ref/libbbo_ref.so.
  * No reference source is copied into this repository; the headers are included by path.
  *
  * State is reached without patching the reference: every member is `protected`
@@ -32,6 +32,7 @@
 #include "multivariate/cma/bipop_cmaes.h"
 #include "multivariate/de/jade.h"
 #include "multivariate/de/shade.h"
+#include "multivariate/nes/xnes.h"
 #include "random.hpp"
 
 #include "bbo_api.h"
@@ -367,6 +368,47 @@ struct ShadeProbe: public ShadeSearch, public DeProbe {
     }
 };
 
+/* xNES (nes/xnes.h:50-57: state is protected) */
+struct XnesProbe: public xNES {
+    using xNES::xNES;
+    std::vector<double> lower, upper, guess;
+    multivariate_problem prob;
+    int geti(const std::string &k) {
+        if (k == "n") return _n;
+        if (k == "np") return _np;
+        if (k == "fev") return _fev;
+        return -1;
+    }
+    double getd(const std::string &k) {
+        if (k == "sigma") return _sigma;
+        if (k == "etasigma") return _etasigma;
+        if (k == "etab") return _etab;
+        if (k == "etamu") return _etamu;
+        if (k == "Gsigma") return _Gsigma;
+        return NAN;
+    }
+    int getv(const std::string &k, double *out, int cap) {
+        if (k == "u") return copy_out(_u, out, cap);
+        if (k == "mu") return copy_out(_mu, out, cap);
+        if (k == "B") return copy_out2(_B, out, cap);
+        if (k == "Gdelta") return copy_out(_Gdelta, out, cap);
+        if (k == "x" || k == "z") {
+            int len = 0;
+            for (const auto &pt : _points)
+                for (double v : (k == "x" ? pt._x : pt._z)) {
+                    if (len < cap) out[len] = v;
+                    len++;
+                }
+            return len;
+        }
+        if (k == "f") {
+            for (int i = 0; i < (int) _points.size() && i < cap; i++) out[i] = _points[i]._f;
+            return (int) _points.size();
+        }
+        return -1;
+    }
+};
+
 std::normal_distribution<> g_normal { 0., 1. };
 
 } // namespace
@@ -499,6 +541,40 @@ int bbo_restart_optimize(int kind, void *base, int mfev, double sigma0, int flag
     }
     return 0; /* the reference exposes no per-restart trace */
 }
+
+void *bbo_xnes_new(int mfev, double tol, double a0, double etamu) { return new XnesProbe(mfev, tol, a0, etamu); }
+void bbo_xnes_free(void *h) { delete static_cast<XnesProbe*>(h); }
+
+static void xnes_bind(XnesProbe *p, int obj, int n, const double *lower, const double *upper, const double *guess) {
+    p->lower.assign(lower, lower + n);
+    p->upper.assign(upper, upper + n);
+    p->guess.assign(guess, guess + n);
+    p->prob = multivariate_problem(make_objective(obj, n), n, p->lower.data(), p->upper.data());
+}
+
+void bbo_xnes_init(void *h, int obj, int n, const double *lower, const double *upper, const double *guess) {
+    XnesProbe *p = static_cast<XnesProbe*>(h);
+    xnes_bind(p, obj, n, lower, upper, guess);
+    p->init(p->prob, p->guess.data());
+}
+
+void bbo_xnes_iterate(void *h) { static_cast<XnesProbe*>(h)->iterate(); }
+/* converged() is private in the reference; solution() reports it (xnes.cpp:193-195) */
+int bbo_xnes_converged(void *h) { return static_cast<XnesProbe*>(h)->solution()._converged ? 1 : 0; }
+
+int bbo_xnes_optimize(void *h, int obj, int n, const double *lower, const double *upper, const double *guess, double *xout,
+        int *fev) {
+    XnesProbe *p = static_cast<XnesProbe*>(h);
+    xnes_bind(p, obj, n, lower, upper, guess);
+    multivariate_solution sol = p->optimize(p->prob, p->guess.data());
+    for (int i = 0; i < n; i++) xout[i] = sol._sol[i];
+    *fev = sol._fev;
+    return sol._converged ? 1 : 0;
+}
+
+int bbo_xnes_geti(void *h, const char *name) { return static_cast<XnesProbe*>(h)->geti(name); }
+double bbo_xnes_getd(void *h, const char *name) { return static_cast<XnesProbe*>(h)->getd(name); }
+int bbo_xnes_getv(void *h, const char *name, double *out, int cap) { return static_cast<XnesProbe*>(h)->getv(name, out, cap); }
 
 void *bbo_de_new(int kind, int mfev, int np, double tol, int archive, int repaircr,
         double pelite, double cdamp, double sigma, int h, int npmin) {

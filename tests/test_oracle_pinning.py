@@ -103,6 +103,33 @@ def test_lm_cma_every_generation(ref_oracle, port_oracle, n, lam, gens, bound, k
         assert r.converged() == p.converged()
 
 
+@pytest.mark.parametrize("obj,n,gens,a0,etamu", [(O.ROSENBROCK, 10, 300, 1.0, 1.0), (O.RASTRIGIN, 40, 100, 2.0, 0.5),
+                                                  (O.ELLIPSOID, 100, 15, 1.0, 1.0)])
+def test_xnes_every_generation(ref_oracle, port_oracle, obj, n, gens, a0, etamu):
+    """xNES (nes/xnes.cpp): port bit for bit after every generation, matrix exponential (tred2 / tql2) included."""
+    hs = []
+    for o in (ref_oracle, port_oracle):
+        o.seed(42)
+        h = o.xnes(10 ** 9, 1e-12, a0, etamu)
+        h.init(obj, -5 * np.ones(n), 5 * np.ones(n), np.ones(n))
+        hs.append(h)
+    r, p = hs
+    assert np.array_equal(r.getv("u"), p.getv("u")) and r.geti("np") == p.geti("np")
+    for g in range(gens):
+        r.iterate()
+        p.iterate()
+        for k in ("mu", "B", "x", "z", "f", "Gdelta"):
+            assert np.array_equal(r.getv(k), p.getv(k)), (g, k)
+        for k in ("sigma", "Gsigma"):
+            assert r.getd(k) == p.getd(k), (g, k)
+        assert r.converged() == p.converged()
+    res = []
+    for o in (ref_oracle, port_oracle):
+        o.seed(7)
+        res.append(o.xnes(3000, 1e-9).optimize(O.SPHERE, -5 * np.ones(6), 5 * np.ones(6), np.ones(6)))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
+
+
 def test_cma_phases_one_by_one(ref_oracle, port_oracle):
     def make(o):
         o.seed(1)
