@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BBGPU_LIB_PATH") or os.path.join(_HERE, "libbbgpu.so")  # override: A/B builds of the engine
 
 OBJ_SPHERE, OBJ_ELLIPSOID, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY = range(5)
-CMA_FULL, CMA_ACTIVE, CMA_SEP, CMA_CHOLESKY, CMA_LM = range(5)
+CMA_FULL, CMA_ACTIVE, CMA_SEP, CMA_CHOLESKY, CMA_LM, CMA_XNES = range(6)
 DE_JADE, DE_SHADE = range(2)
 (F_XMEAN, F_XOLD, F_PC, F_PS, F_C, F_B, F_D, F_INVSQRTC, F_ARX, F_Z, F_FITNESS, F_RANKVAL, F_YCOEFF,
  F_WEIGHTS, F_NORMS, F_SHARD_RED, F_A, F_PCMAT, F_VMAT, F_LMB, F_LMD) = range(21)
@@ -143,6 +143,7 @@ def lib():
     L.bbgpu_cma_eig.argtypes = [vp, vp, vp]
     L.bbgpu_cma_probe.argtypes = [vp, d, i]
     L.bbgpu_cma_swarm_radius.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    L.bbgpu_cma_xnes_update.argtypes = [vp, d, d, d, ctypes.POINTER(ctypes.c_double)]
     L.bbgpu_cma_lm_sample.argtypes = [vp, d, ctypes.c_uint64, i, c_dp, c_dp, c_dp]
     L.bbgpu_cma_lm_update.argtypes = [vp, d, i, i, i, c_dp]
     L.bbgpu_cma_fetch.argtypes = [vp, P(CmaReport)]
@@ -470,6 +471,12 @@ class Cma:
         idx = np.empty(self.lam, dtype=np.int32)
         check(self.L.bbgpu_cma_get_rank(self.h, idx.ctypes.data, self.lam))
         return idx
+
+    def xnes_update(self, sigma, etamu, etab):
+        """xNES: natural-gradient update of mu and B after sample / evaluate / rank; returns G_sigma."""
+        gs = ctypes.c_double(0)
+        check(self.L.bbgpu_cma_xnes_update(self.h, sigma, etamu, etab, ctypes.byref(gs)))
+        return gs.value
 
     def lm_sample(self, sigma, generation, jarr, memlen, z=None, i0=None):
         """LM kind: mirrored sampling through the live memory rows jarr[:memlen]; z (pairs x n) and i0 (pairs) replay the

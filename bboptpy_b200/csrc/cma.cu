@@ -19,6 +19,7 @@
 
 #include "chol.cuh"
 #include "lmcma.cuh"
+#include "xnes.cuh"
 #include "gemm_tma.cuh"
 #include "objectives.cuh"
 #include "philox.cuh"
@@ -37,6 +38,7 @@ struct bbgpu_cma {
     double *Ystk = nullptr, *Mch = nullptr, *Lt = nullptr, *negone = nullptr, *rnorm = nullptr, *rstat = nullptr;
     cudaEvent_t ev_ch_fork = nullptr, ev_ch_join = nullptr;
     // LM-CMA-ES (lmcma.cuh): direction vectors and their scalars, the base draws of the pairs, live-row order, subset starts
+    bool xnes = false; // xNES (xnes.cuh): Bt = the transform B (transposed), C = G / its scaled form, BDt / BDit / isC scratch
     bool lm = false;
     int lm_mem = 0, lm_pairs = 0;
     double *PCmat = nullptr, *Vmat = nullptr, *lmb = nullptr, *lmd = nullptr, *Zp = nullptr;
@@ -701,9 +703,9 @@ static int refresh_basis_products(bbgpu_cma *h) {
 static int do_sample(bbgpu_cma *h, double sigma) {
     bbgpu_ctx *ctx = h->ctx;
     h->last_sigma = sigma;
-    ProfScope prof(ctx, (h->full || h->chol) ? BBGPU_PROF_SAMPLE_GEMM : BBGPU_PROF_SEP_SAMPLE);
+    ProfScope prof(ctx, (h->full || h->chol || h->xnes) ? BBGPU_PROF_SAMPLE_GEMM : BBGPU_PROF_SEP_SAMPLE);
     const double *lo = h->cfg.bound ? h->lower : nullptr, *hi = h->cfg.bound ? h->upper : nullptr;
-    if (!h->full && !h->chol) {
+    if (!h->full && !h->chol && !h->xnes) {
         dim3 grid(ceil_div(h->n, 256), std::min(h->lam_loc, 64));
         sep_sample_kernel<<<grid, 256, 0, ctx->stream>>>(h->X, h->Z, h->ldn, h->lam_loc, h->n, h->xmean, h->D, sigma, lo, hi);
         return launched(ctx, "sep_sample_kernel");
@@ -711,7 +713,7 @@ static int do_sample(bbgpu_cma *h, double sigma) {
     // X[k][i] = m_i + sigma * sum_j Z[k][j] * (D_j Bt[j][i]), clipped in the epilogue
     GemmArgs g {};
     // Cholesky kind: x = m + sigma A z, the operand is A^T (rows [0, n) of the stacked buffer; cholesky_cmaes.cpp:120-135)
-    g.A = h->Z; g.lda = h->ldn; g.B = h->chol ? h->Ystk : h->BDt; g.ldb = h->ldn;
+    g.A = h->Z; g.lda = h->ldn; g.B = h->chol ? h->Ystk : (h->xnes ? h->Bt : h->BDt); g.ldb = h->ldn;
     g.M = h->lam_loc; g.N = h->n; g.K = h->n;
     g.C = h->X; g.ldc = h->ldn; g.vec = h->xmean; g.lo = lo; g.hi = hi; g.s0 = sigma;
     return launch_gemm<1, EPI_SAMPLE>(ctx, g);
@@ -1011,6 +1013,78 @@ static int shard_finish(bbgpu_cma *h, double sigma, int fev) {
     return launched(ctx, "shard_cov_finish_kernel");
 }
 
+// Symmetric eigendecomposition of Cin (n x n, pitch ldn, lower triangle read): eigenvalues ascending in Wout, eigenvectors
+// as the ROWS of Vt.  Own solver at 256 <= n <= ~1700, cuSOLVER syevd otherwise; no clamping of the spectrum.
+static int eig_core(bbgpu_cma *h, const double *Cin, double *Vt, double *Wout) {
+    bbgpu_ctx *ctx = h->ctx;
+    const int n = h->n;
+    cudaStream_t st = ctx->stream;
+    cusolverDnHandle_t sv;
+    BB_TRY(get_solver(ctx, &sv));
+    // Own solver where it pays and fits (cuSOLVER's syevd spends 80 % of its 12 ms at n = 1000 in a latency-bound sytrd):
+    // cooperative sytrd -> tridiagonal divide & conquer -> cuSOLVER ormtr for the back-transformation.
+    // BBGPU_EIG=cusolver forces the library path.
+    static const bool force_lib = [] { const char *e = getenv("BBGPU_EIG"); return e && e[0] == 'c'; }();
+    if (!force_lib && n >= 256 && sytrd_fits(ctx, n)) {
+        const size_t nn = (size_t) n;
+        // Back-transformation: Q^T is formed row by row from the reflectors (q_rows_kernel: no exchange between CTAs) on
+        // the side stream WHILE the divide & conquer runs (its kernels are small and latency-bound), then
+        // B^T = Z^T Q^T is one DMMA GEMM.  cuSOLVER's ormtr (0.5 ms at n = 1000: 16 dependent block steps after the
+        // divide & conquer) stays as the comparison path, BBGPU_EIG_Q=ormtr.
+        static const bool use_ormtr = [] { const char *e = getenv("BBGPU_EIG_Q"); return e && e[0] == 'o'; }();
+        const size_t zt = nn * (size_t) h->ldn;
+        if (h->own_ws == nullptr) {
+            int lw = 0;
+            if (cusolverDnDormtr_bufferSize(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, Vt, n, Wout, Vt,
+                    (int) h->ldn, &lw) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "ormtr_bufferSize failed");
+            h->own_lwork = lw;
+            BB_TRY(dev_alloc(&h->own_ws, 3 * nn + nn * nn + sytrd_workspace_doubles(n) + (size_t) lw + 2 * zt + 48));
+            BB_TRY(dev_alloc(&h->own_info, (size_t) 4));
+            BB_CUDA(cudaEventCreateWithFlags(&h->ev_eig_fork, cudaEventDisableTiming));
+            BB_CUDA(cudaEventCreateWithFlags(&h->ev_eig_join, cudaEventDisableTiming));
+        }
+        double *dd = h->own_ws, *de = dd + nn, *dtau = de + nn, *Vcm = dtau + nn, *ws = Vcm + nn * nn,
+                *owork = ws + sytrd_workspace_doubles(n);
+        double *Ztmp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(owork + h->own_lwork) + 127) & ~(uintptr_t) 127); // TMA operands
+        double *Qt = Ztmp + ((zt + 15) & ~(size_t) 15);
+        BB_CUDA(cudaMemsetAsync(de, 0, 2 * nn * 8, st));
+        BB_TRY(sytrd_device(ctx, n, Cin, (int) h->ldn, dd, de, dtau, Vcm, ws));
+        if (!use_ormtr && !ctx->aux) BB_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+        if (use_ormtr) {
+            BB_TRY(stedc_device(ctx, n, dd, de, Wout, Vt, (int) h->ldn, h->dev_info));
+            const cusolverStatus_t rc = cusolverDnDormtr(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, Vcm, n, dtau,
+                    Vt, (int) h->ldn, owork, h->own_lwork, h->own_info);
+            if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDormtr failed with status %d", (int) rc);
+        } else {
+            BB_CUDA(cudaEventRecord(h->ev_eig_fork, st));
+            BB_CUDA(cudaStreamWaitEvent(ctx->aux, h->ev_eig_fork, 0));
+            BB_TRY(q_rows_device(ctx, ctx->aux, n, Vcm, dtau, Qt, (int) h->ldn));
+            BB_CUDA(cudaEventRecord(h->ev_eig_join, ctx->aux));
+            BB_TRY(stedc_device(ctx, n, dd, de, Wout, Ztmp, (int) h->ldn, h->dev_info));
+            BB_CUDA(cudaStreamWaitEvent(st, h->ev_eig_join, 0));
+            // rows of Ztmp are the eigenvectors of T: B^T (rows = eigenvectors of C) = Z^T Q^T
+            GemmArgs g {};
+            g.A = Ztmp; g.lda = h->ldn; g.B = Qt; g.ldb = h->ldn; g.M = n; g.N = n; g.K = n; g.C = Vt; g.ldc = h->ldn;
+            BB_TRY((launch_gemm<1, EPI_STORE>(ctx, g)));
+        }
+    } else {
+        dim3 grid(ceil_div(n, 256), n);
+        symmetrize_kernel<<<grid, 256, 0, st>>>(Cin, Vt, n, h->ldn);
+        BB_TRY(launched(ctx, "symmetrize_kernel"));
+        if (h->solver_work == nullptr) {
+            int lwork = 0;
+            if (cusolverDnDsyevd_bufferSize(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, Vt, (int) h->ldn, Wout,
+                    &lwork) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "syevd_bufferSize failed");
+            BB_TRY(dev_alloc(&h->solver_work, (size_t) lwork));
+            h->solver_lwork = lwork;
+        }
+        const cusolverStatus_t rc = cusolverDnDsyevd(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, Vt, (int) h->ldn,
+                Wout, h->solver_work, h->solver_lwork, h->dev_info);
+        if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDsyevd failed with status %d", (int) rc);
+    }
+    return BBGPU_OK;
+}
+
 static int do_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
     bbgpu_ctx *ctx = h->ctx;
     ProfScope prof(ctx, BBGPU_PROF_EIG);
@@ -1031,69 +1105,7 @@ static int do_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
         BB_TRY(launched(ctx, "ends_report_kernel"));
         return refresh_basis_products(h);
     }
-    cusolverDnHandle_t sv;
-    BB_TRY(get_solver(ctx, &sv));
-    // Own solver where it pays and fits (cuSOLVER's syevd spends 80 % of its 12 ms at n = 1000 in a latency-bound sytrd):
-    // cooperative sytrd -> tridiagonal divide & conquer -> cuSOLVER ormtr for the back-transformation.
-    // BBGPU_EIG=cusolver forces the library path.
-    static const bool force_lib = [] { const char *e = getenv("BBGPU_EIG"); return e && e[0] == 'c'; }();
-    if (!force_lib && n >= 256 && sytrd_fits(ctx, n)) {
-        const size_t nn = (size_t) n;
-        // Back-transformation: Q^T is formed row by row from the reflectors (q_rows_kernel: no exchange between CTAs) on
-        // the side stream WHILE the divide & conquer runs (its kernels are small and latency-bound), then
-        // B^T = Z^T Q^T is one DMMA GEMM.  cuSOLVER's ormtr (0.5 ms at n = 1000: 16 dependent block steps after the
-        // divide & conquer) stays as the comparison path, BBGPU_EIG_Q=ormtr.
-        static const bool use_ormtr = [] { const char *e = getenv("BBGPU_EIG_Q"); return e && e[0] == 'o'; }();
-        const size_t zt = nn * (size_t) h->ldn;
-        if (h->own_ws == nullptr) {
-            int lw = 0;
-            if (cusolverDnDormtr_bufferSize(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, h->Bt, n, h->W, h->Bt,
-                    (int) h->ldn, &lw) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "ormtr_bufferSize failed");
-            h->own_lwork = lw;
-            BB_TRY(dev_alloc(&h->own_ws, 3 * nn + nn * nn + sytrd_workspace_doubles(n) + (size_t) lw + 2 * zt + 48));
-            BB_TRY(dev_alloc(&h->own_info, (size_t) 4));
-            BB_CUDA(cudaEventCreateWithFlags(&h->ev_eig_fork, cudaEventDisableTiming));
-            BB_CUDA(cudaEventCreateWithFlags(&h->ev_eig_join, cudaEventDisableTiming));
-        }
-        double *dd = h->own_ws, *de = dd + nn, *dtau = de + nn, *Vcm = dtau + nn, *ws = Vcm + nn * nn,
-                *owork = ws + sytrd_workspace_doubles(n);
-        double *Ztmp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(owork + h->own_lwork) + 127) & ~(uintptr_t) 127); // TMA operands
-        double *Qt = Ztmp + ((zt + 15) & ~(size_t) 15);
-        BB_CUDA(cudaMemsetAsync(de, 0, 2 * nn * 8, st));
-        BB_TRY(sytrd_device(ctx, n, h->C, (int) h->ldn, dd, de, dtau, Vcm, ws));
-        if (!use_ormtr && !ctx->aux) BB_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
-        if (use_ormtr) {
-            BB_TRY(stedc_device(ctx, n, dd, de, h->W, h->Bt, (int) h->ldn, h->dev_info));
-            const cusolverStatus_t rc = cusolverDnDormtr(sv, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, n, Vcm, n, dtau,
-                    h->Bt, (int) h->ldn, owork, h->own_lwork, h->own_info);
-            if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDormtr failed with status %d", (int) rc);
-        } else {
-            BB_CUDA(cudaEventRecord(h->ev_eig_fork, st));
-            BB_CUDA(cudaStreamWaitEvent(ctx->aux, h->ev_eig_fork, 0));
-            BB_TRY(q_rows_device(ctx, ctx->aux, n, Vcm, dtau, Qt, (int) h->ldn));
-            BB_CUDA(cudaEventRecord(h->ev_eig_join, ctx->aux));
-            BB_TRY(stedc_device(ctx, n, dd, de, h->W, Ztmp, (int) h->ldn, h->dev_info));
-            BB_CUDA(cudaStreamWaitEvent(st, h->ev_eig_join, 0));
-            // rows of Ztmp are the eigenvectors of T: B^T (rows = eigenvectors of C) = Z^T Q^T
-            GemmArgs g {};
-            g.A = Ztmp; g.lda = h->ldn; g.B = Qt; g.ldb = h->ldn; g.M = n; g.N = n; g.K = n; g.C = h->Bt; g.ldc = h->ldn;
-            BB_TRY((launch_gemm<1, EPI_STORE>(ctx, g)));
-        }
-    } else {
-        dim3 grid(ceil_div(n, 256), n);
-        symmetrize_kernel<<<grid, 256, 0, st>>>(h->C, h->Bt, n, h->ldn);
-        BB_TRY(launched(ctx, "symmetrize_kernel"));
-        if (h->solver_work == nullptr) {
-            int lwork = 0;
-            if (cusolverDnDsyevd_bufferSize(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->Bt, (int) h->ldn, h->W,
-                    &lwork) != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "syevd_bufferSize failed");
-            BB_TRY(dev_alloc(&h->solver_work, (size_t) lwork));
-            h->solver_lwork = lwork;
-        }
-        const cusolverStatus_t rc = cusolverDnDsyevd(sv, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->Bt, (int) h->ldn,
-                h->W, h->solver_work, h->solver_lwork, h->dev_info);
-        if (rc != CUSOLVER_STATUS_SUCCESS) return fail(BBGPU_ERR_SOLVER, "cusolverDnDsyevd failed with status %d", (int) rc);
-    }
+    BB_TRY(eig_core(h, h->C, h->Bt, h->W));
     eig_post_kernel<<<1, 1024, 0, st>>>(h->W, h->D, h->C, n, h->ldn, h->dev_info, h->d_report);
     BB_TRY(launched(ctx, "eig_post_kernel"));
     return refresh_basis_products(h);
@@ -1108,7 +1120,7 @@ static int field_info(bbgpu_cma *h, int field, double **ptr, int64_t *rows, int6
     case BBGPU_CMA_PC: *ptr = h->pc; *rows = 1; *cols = n; break;
     case BBGPU_CMA_PS: *ptr = h->ps; *rows = 1; *cols = n; break;
     case BBGPU_CMA_D:
-        if (h->chol || h->lm) return fail(BBGPU_ERR_ARG, "this kind has no D");
+        if (h->chol || h->lm || h->xnes) return fail(BBGPU_ERR_ARG, "this kind has no D");
         *ptr = h->D; *rows = 1; *cols = n; break;
     case BBGPU_CMA_PCMAT: case BBGPU_CMA_VMAT:
         if (!h->lm) return fail(BBGPU_ERR_ARG, "only LM-CMA-ES has direction vectors");
@@ -1120,7 +1132,7 @@ static int field_info(bbgpu_cma *h, int field, double **ptr, int64_t *rows, int6
         if (!h->chol) return fail(BBGPU_ERR_ARG, "only Cholesky-CMA-ES has a factor A");
         *ptr = h->Ystk; *rows = n; *cols = n; *ld = h->ldn; break;
     case BBGPU_CMA_C:
-        if (h->chol || h->lm) return fail(BBGPU_ERR_ARG, "this kind keeps no covariance matrix");
+        if (h->chol || h->lm || h->xnes) return fail(BBGPU_ERR_ARG, "this kind keeps no covariance matrix");
         if (h->full) { *ptr = h->C; *rows = n; *cols = n; *ld = h->ldn; }
         else { *ptr = h->C; *rows = 1; *cols = n; }
         break;
@@ -1128,7 +1140,7 @@ static int field_info(bbgpu_cma *h, int field, double **ptr, int64_t *rows, int6
         if (!h->full) return fail(BBGPU_ERR_ARG, "separable CMA-ES has no C^-1/2");
         *ptr = h->isC; *rows = n; *cols = n; *ld = h->ldn; break;
     case BBGPU_CMA_B:
-        if (!h->full) return fail(BBGPU_ERR_ARG, "separable CMA-ES has no eigenbasis");
+        if (!h->full && !h->xnes) return fail(BBGPU_ERR_ARG, "this kind has no matrix B");
         *ptr = h->Bt; *rows = n; *cols = n; *ld = h->ldn; break;
     case BBGPU_CMA_ARX: *ptr = h->X; *rows = h->lam_loc; *cols = n; *ld = h->ldn; break;
     case BBGPU_CMA_Z:
@@ -1162,12 +1174,13 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
         const double *h_upper, bbgpu_cma **out) {
     BB_ARG(ctx && cfg && h_weights && out);
     BB_ARG(cfg->n >= 1 && cfg->lambda >= 2 && cfg->mu >= 1 && cfg->mu <= cfg->lambda);
-    BB_ARG(cfg->kind >= BBGPU_CMA_FULL && cfg->kind <= BBGPU_CMA_LM);
+    BB_ARG(cfg->kind >= BBGPU_CMA_FULL && cfg->kind <= BBGPU_CMA_XNES);
+    if (cfg->kind == BBGPU_CMA_XNES) BB_ARG(cfg->lambda <= XN_MAXNP && cfg->mu == cfg->lambda && !cfg->bound);
     if (cfg->kind == BBGPU_CMA_LM) BB_ARG(cfg->lm_memory >= 1 && cfg->lm_memory <= LM_MAXMEM);
     BB_ARG(!cfg->bound || (h_lower && h_upper));
     if (cfg->shard_count > 1) {
         BB_ARG(cfg->shard_rank >= 0 && cfg->shard_rank < cfg->shard_count);
-        if (cfg->kind == BBGPU_CMA_SEP || cfg->kind == BBGPU_CMA_CHOLESKY || cfg->kind == BBGPU_CMA_LM)
+        if (cfg->kind != BBGPU_CMA_FULL && cfg->kind != BBGPU_CMA_ACTIVE)
             return fail(BBGPU_ERR_ARG, "candidate sharding covers the full-covariance kinds");
         if (cfg->lambda % cfg->shard_count != 0 || cfg->lambda / cfg->shard_count < 2)
             return fail(BBGPU_ERR_ARG, "lambda = %d does not split into %d equal shards of at least 2", cfg->lambda, cfg->shard_count);
@@ -1183,6 +1196,7 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     h->active = cfg->kind == BBGPU_CMA_ACTIVE;
     h->chol = cfg->kind == BBGPU_CMA_CHOLESKY;
     h->lm = cfg->kind == BBGPU_CMA_LM;
+    h->xnes = cfg->kind == BBGPU_CMA_XNES;
     h->lm_mem = h->lm ? cfg->lm_memory : 0;
     h->lm_pairs = (cfg->lambda + 1) / 2;
     h->nsel = h->active ? 2 * h->mu : h->mu;
@@ -1209,10 +1223,12 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
     A(&h->X, laml * ldn); A(&h->fit, lam); A(&h->rank_val, lam);
     if (!h->lm) { A(&h->Zbuf[0], laml * ldn); A(&h->Zbuf[1], laml * ldn); } // the LM kind draws lambda/2 base vectors (Zp)
     A(&h->part, (size_t) h->splits * 2 * n);
-    if (h->full) {
+    if (h->full || h->xnes) {
         A(&h->C, (size_t) n * ldn); A(&h->Bt, (size_t) n * ldn); A(&h->BDt, (size_t) n * ldn);
         A(&h->BDit, (size_t) n * ldn); A(&h->isC, (size_t) n * ldn);
-        if (h->shards > 1) {
+        if (h->xnes) {
+            // nothing else: the utilities live in `weights`
+        } else if (h->shards > 1) {
             A(&h->Yloc, laml * ldn); A(&h->coef_loc, (size_t) round_up(h->lam_loc, 32) + 32); A(&h->wm_loc, laml);
             A(&h->red, (size_t) n * ldn + ldn);
             if (h->active) {
@@ -1329,6 +1345,10 @@ int bbgpu_cma_reset(bbgpu_cma *h, const double *h_guess, int keep_offdiag) {
         dim3 grid(ceil_div(n, 256), n);
         fill_identity_kernel<<<grid, 256, 0, st>>>(h->Ystk, n, h->ldn, false); // A = I (cholesky_cmaes.cpp:44-51 clears it)
         BB_TRY(launched(ctx, "fill_identity_kernel"));
+    } else if (h->xnes) { // B = (a0 / sigma) I = I (xnes.cpp:83-88)
+        dim3 grid(ceil_div(n, 256), n);
+        fill_identity_kernel<<<grid, 256, 0, st>>>(h->Bt, n, h->ldn, false);
+        BB_TRY(launched(ctx, "fill_identity_kernel"));
     } else if (h->lm) { // memlen = 0: no row is live; b = d = 0 (lm_cmaes.cpp:75-78)
         BB_CUDA(cudaMemsetAsync(h->lmb, 0, (size_t) h->lm_mem * 8, st));
         BB_CUDA(cudaMemsetAsync(h->lmd, 0, (size_t) h->lm_mem * 8, st));
@@ -1354,7 +1374,7 @@ int bbgpu_cma_set(bbgpu_cma *h, int field, const double *h_src, int64_t count) {
             for (int j = 0; j < n; j++) t[(size_t) j * n + i] = h_src[(size_t) i * n + j];
         BB_CUDA(cudaMemcpy2DAsync(ptr, (size_t) ld * 8, t.data(), (size_t) cols * 8, (size_t) cols * 8, rows, cudaMemcpyHostToDevice, st));
         BB_CUDA(cudaStreamSynchronize(st));
-        if (field == BBGPU_CMA_A) return BBGPU_OK;
+        if (field == BBGPU_CMA_A || h->xnes) return BBGPU_OK;
         scale_basis_kernel<<<n, 256, 0, st>>>(h->Bt, h->D, h->BDt, h->BDit, n, h->ldn);
         BB_TRY(launched(h->ctx, "scale_basis_kernel"));
         BB_CUDA(cudaStreamSynchronize(st));
@@ -1452,7 +1472,7 @@ int bbgpu_cma_rank(bbgpu_cma *h, int ik) {
 }
 
 int bbgpu_cma_update(bbgpu_cma *h, double sigma, int fev) {
-    BB_ARG(h && sigma > 0.0 && !h->lm);
+    BB_ARG(h && sigma > 0.0 && !h->lm && !h->xnes);
     if (h->shards > 1) {
         if (!h->comm) return fail(BBGPU_ERR_ARG, "sharded handle without a communicator: use bbgpu_cma_shard_partial / _finish");
         BB_TRY(shard_partial(h));
@@ -1514,6 +1534,49 @@ int bbgpu_cma_eig(bbgpu_cma *h, const double *h_B, const double *h_D) {
     BB_ARG(h && h->full);
     BB_ARG((h_B == nullptr) == (h_D == nullptr));
     return do_eig(h, h_B, h_D);
+}
+
+// xNES: everything after the ranking (xnes.cpp:130-190); sigma is the value the points were sampled with
+int bbgpu_cma_xnes_update(bbgpu_cma *h, double sigma, double etamu, double etab, double *h_gsigma) {
+    BB_ARG(h && h->xnes && sigma > 0.0 && h_gsigma);
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    const int n = h->n, np = h->lambda;
+    {
+        ProfScope prof(ctx, BBGPU_PROF_UPDATE_MISC);
+        xnes_gdelta_kernel<<<ceil_div(n, 256), 256, 0, st>>>(h->dm, h->Z, h->ldn, n, np, h->rank_idx, h->weights);
+        BB_TRY(launched(ctx, "xnes_gdelta_kernel"));
+        dim3 tgrid(ceil_div(n, 32), ceil_div(n, 32));
+        xnes_gm_kernel<<<tgrid, 256, 0, st>>>(h->C, h->Z, h->ldn, n, np, h->rank_idx, h->weights);
+        BB_TRY(launched(ctx, "xnes_gm_kernel"));
+        xnes_trace_kernel<<<1, 1024, 0, st>>>(h->C, h->ldn, n, h->dscal);
+        BB_TRY(launched(ctx, "xnes_trace_kernel"));
+        dim3 sgrid(ceil_div(n, 256), n);
+        xnes_scale_kernel<<<sgrid, 256, 0, st>>>(h->C, h->ldn, n, h->dscal, 0.5 * etab);
+        BB_TRY(launched(ctx, "xnes_scale_kernel"));
+        xnes_mean_kernel<<<ceil_div(n, 256), 256, 0, st>>>(h->xmean, h->Bt, h->ldn, n, h->dm, etamu * sigma);
+        BB_TRY(launched(ctx, "xnes_mean_kernel"));
+        BB_CUDA(cudaMemcpyAsync(h_gsigma, h->dscal, 8, cudaMemcpyDeviceToHost, st));
+    }
+    {
+        ProfScope prof(ctx, BBGPU_PROF_EIG);
+        BB_TRY(eig_core(h, h->C, h->BDt, h->W)); // rows of BDt: eigenvectors of C
+        xnes_info_kernel<<<1, 32, 0, st>>>(h->dev_info, h->d_report);
+        BB_TRY(launched(ctx, "xnes_info_kernel"));
+        xnes_expscale_kernel<<<n, 256, 0, st>>>(h->BDt, h->W, h->BDit, n, h->ldn);
+        BB_TRY(launched(ctx, "xnes_expscale_kernel"));
+        // expm(C)[i][l] = sum_j V[j][i] (exp(w_j) V[j][l])
+        GemmArgs g {};
+        g.A = h->BDt; g.lda = h->ldn; g.B = h->BDit; g.ldb = h->ldn; g.M = n; g.N = n; g.K = n; g.C = h->isC; g.ldc = h->ldn;
+        BB_TRY((launch_gemm<2, EPI_STORE>(ctx, g)));
+        // B <- B expm(C)  <=>  B^T <- expm(C) B^T (expm(C) is symmetric)
+        GemmArgs q {};
+        q.A = h->isC; q.lda = h->ldn; q.B = h->Bt; q.ldb = h->ldn; q.M = n; q.N = n; q.K = n; q.C = h->BDt; q.ldc = h->ldn;
+        BB_TRY((launch_gemm<1, EPI_STORE>(ctx, q)));
+        std::swap(h->Bt, h->BDt);
+    }
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BBGPU_OK;
 }
 
 // LM kind: samplePopulation (lm_cmaes.cpp:91-127)
@@ -1579,7 +1642,7 @@ int bbgpu_cma_swarm_radius(bbgpu_cma *h, double *h_mean, double *h_m2) {
 }
 
 int bbgpu_cma_probe(bbgpu_cma *h, double sigma, int iaxis) {
-    BB_ARG(h && iaxis >= 0 && iaxis < h->n && !h->chol);
+    BB_ARG(h && iaxis >= 0 && iaxis < h->n && !h->chol && !h->lm && !h->xnes);
     if (h->full) probe_kernel<false><<<1, 1024, 0, h->ctx->stream>>>(h->n, h->ldn, h->xmean, h->pc, h->C, h->D, h->Bt, sigma, iaxis, h->d_report);
     else probe_kernel<true><<<1, 1024, 0, h->ctx->stream>>>(h->n, h->ldn, h->xmean, h->pc, h->C, h->D, nullptr, sigma, iaxis, h->d_report);
     return launched(h->ctx, "probe_kernel");
@@ -1595,7 +1658,7 @@ int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *out) {
 }
 
 int bbgpu_cma_generation(bbgpu_cma *h, bbgpu_objective *obj, double sigma, uint64_t generation, int ik, int fev_after) {
-    BB_ARG(h && obj && obj->n == h->n && !h->lm);
+    BB_ARG(h && obj && obj->n == h->n && !h->lm && !h->xnes);
     if (!h->full && !h->chol && obj->mode == 0 && obj->id != BBGPU_OBJ_ROSENBROCK) {
         // separable kind, registry objective: draws, sampling and evaluation fused into one pass over X
         bbgpu_ctx *ctx = h->ctx;

@@ -19,6 +19,7 @@
 
 #include "cma.h"
 #include "de.h"
+#include "xnes.h"
 #include "restart.h"
 #include "batch.h"
 
@@ -253,6 +254,17 @@ PYBIND11_MODULE(_bboptpy, m) {
             return b;
         }), "runs"_a, "mfev"_a, "tol"_a, "sigma0"_a = 2., "nipop"_a = true, "ksigmadec"_a = 1.6, "boundlambda"_a = true,
             "eigenrate"_a = 0.25);
+
+    // py/multivariate_py.cpp:153-157
+    py::class_<xNES, MultivariateOptimizer>(m, "xNES")
+        .def(py::init<int, double, double, double>(), "mfev"_a, "tol"_a, "a0"_a = 1., "etamu"_a = 1.)
+        .def("set_draw_replay", &xNES::setDrawReplay, "seed"_a)
+        .def("state", [](xNES &self, const std::string &name) { return as_array(self.state(name)); }, "name"_a)
+        .def("converged", &xNES::isConverged)
+        .def_property_readonly("sigma", &xNES::sigma)
+        .def_property_readonly("gsigma", &xNES::gsigma)
+        .def_property_readonly("n_evals", &xNES::evaluations)
+        .def_property_readonly("np", &xNES::population);
 
     py::class_<DeSearchBase, MultivariateOptimizer>(m, "BaseDE")
         .def("swarm", [](DeSearchBase &self) {

@@ -330,6 +330,7 @@ def run_reference(args):
         "de": de,
         "cholesky": {"gens_per_s": cpu_chol_sample(o), "sample": "1 whole generation of CholeskyCmaes, n=1000 lambda=4096, 1 thread"},
         "lm_cma": {"gens_per_s": cpu_lm_sample(o), "sample": f"40 generations of LmCmaes, n={LM_N} lambda={LM_LAMBDA}, 1 thread"},
+        "xnes": {"gens_per_s": cpu_xnes_sample(o), "sample": "1 generation of xNES, n=1000, 1 thread"},
         "bipop_batch": cpu_bipop_sample(o),
     }
     print(json.dumps(line))
@@ -494,6 +495,29 @@ def cpu_lm_sample(o, gens=40, seed=1):
     for _ in range(gens):
         h.iterate()
     return gens / (time.perf_counter() - t0)
+
+
+def bench_xnes_e2e(pkg, gens, seed):
+    """xNES (nes/xnes.cpp) at n = 1000 (np = 24 points), Rosenbrock, through the Python API: per generation one eigendecomposition
+    (the reference's matrix exponential) and two n^3 tensor-core GEMMs."""
+    n = N_DIM
+    lower, upper = -BOX * np.ones(n), BOX * np.ones(n)
+    alg = pkg.xNES(mfev=gens * (4 + int(3 * math.log(n))), tol=0.0)
+    t0 = time.perf_counter()
+    sol = alg.optimize(pkg.Rosenbrock, lower, upper, np.zeros(n))
+    dt = time.perf_counter() - t0
+    return (sol.n_evals // alg.np) / dt
+
+
+def cpu_xnes_sample(o, seed=1):
+    from oracle import oracle as O
+    o.seed(seed)
+    n = N_DIM
+    h = o.xnes(10 ** 9, 0.0)
+    h.init(O.ROSENBROCK, -BOX * np.ones(n), BOX * np.ones(n), np.zeros(n))
+    t0 = time.perf_counter()
+    h.iterate()
+    return 1.0 / (time.perf_counter() - t0)
 
 
 def bench_de_device(ctx, kind, steps, warmup, seed):
@@ -753,6 +777,9 @@ def run_own(args):
     lm = {"e2e_gens_per_s": world * 1.0 / all_max(dist, local, 1.0 / bench_lm_e2e(pkg, 400, seed=1 + rank)),
           "workload": f"LmCMAES n={LM_N} lambda={LM_LAMBDA} memory=200 Ellipsoid, 400 generations through the Python API "
                       "(cma/lm_cmaes.cpp; the memory fills during the run)"}
+    bench_xnes_e2e(pkg, 3, seed=1 + rank)
+    xn = {"e2e_gens_per_s": world * 1.0 / all_max(dist, local, 1.0 / bench_xnes_e2e(pkg, e2e_gens, seed=1 + rank)),
+          "workload": "xNES n=1000 np=24 Rosenbrock through the Python API (nes/xnes.cpp; one eigendecomposition + two n^3 GEMMs per generation)"}
     # one large-lambda run sharded by candidates over all GPUs of the job (N > 1 only)
     sharded = None
     pycomm = None
@@ -861,6 +888,7 @@ def run_own(args):
         "sep": sep,
         "cholesky": chol,
         "lm_cma": lm,
+        "xnes": xn,
         "bipop_batch": bipop,
     }
     chol["workload"] = "CholeskyCmaes n=1000 lambda=4096 Rosenbrock (cma/cholesky_cmaes.cpp; no eigendecomposition: SYRK + blocked Cholesky)"
@@ -879,6 +907,7 @@ def run_own(args):
                                 "de_jade_evals_per_s": cpu_de_sample(o, 0), "de_shade_evals_per_s": cpu_de_sample(o, 1),
                                 "cholesky_gens_per_s": cpu_chol_sample(o),
                                 "lm_cma_gens_per_s": cpu_lm_sample(o),
+                                "xnes_gens_per_s": cpu_xnes_sample(o),
                                 "bipop_batch": cpu_bipop_sample(o)}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 

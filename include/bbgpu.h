@@ -122,7 +122,11 @@ int bbgpu_eval_host(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *h_X, int
 /* BBGPU_CMA_LM: cma/lm_cmaes.cpp (Loshchilov 2014/2015) -- the covariance is implicit in `memory` direction vectors: rows of
  * PCMAT / VMAT with the coefficients LMB / LMD; mirrored sampling of lambda/2 base vectors (bbgpu_cma_lm_sample), the memory
  * bookkeeping (which rows are live, in which order: `jarr`) stays with the host class */
-enum bbgpu_cma_kind { BBGPU_CMA_FULL = 0, BBGPU_CMA_ACTIVE = 1, BBGPU_CMA_SEP = 2, BBGPU_CMA_CHOLESKY = 3, BBGPU_CMA_LM = 4 };
+/* BBGPU_CMA_XNES: nes/xnes.cpp -- the same handle with lambda = mu = np points, `weights` = the np rank utilities (they sum to
+ * zero), BBGPU_CMA_B = the transform B (x = mu + sigma B z) and BBGPU_CMA_XMEAN = mu; sample / evaluate / rank as for the
+ * other kinds, then bbgpu_cma_xnes_update */
+enum bbgpu_cma_kind { BBGPU_CMA_FULL = 0, BBGPU_CMA_ACTIVE = 1, BBGPU_CMA_SEP = 2, BBGPU_CMA_CHOLESKY = 3, BBGPU_CMA_LM = 4,
+                      BBGPU_CMA_XNES = 5 };
 
 typedef struct bbgpu_cma_config {
     int kind;       /* bbgpu_cma_kind */
@@ -223,6 +227,11 @@ int bbgpu_cma_update(bbgpu_cma *h, double sigma, int fev);
 int bbgpu_cma_eig(bbgpu_cma *h, const double *h_B, const double *h_D);
 /* quantities for converged(): cma/cmaes.cpp:184-229, cma/sep_cmaes.cpp:170-205 */
 int bbgpu_cma_probe(bbgpu_cma *h, double sigma, int iaxis);
+/* xNES, everything after the ranking (nes/xnes.cpp:130-190): natural-gradient terms G_delta / G_M / G_sigma from the ranked
+ * draws, mu += eta_mu sigma B G_delta, B <- B expm(eta_B (G_M - G_sigma I) / 2) with the reference's eigendecomposition-based
+ * matrix exponential (:227-253) as two tensor-core GEMMs around the eigensolver.  Returns G_sigma (the host applies
+ * sigma *= exp(eta_sigma G_sigma / 2), :171); synchronises. */
+int bbgpu_cma_xnes_update(bbgpu_cma *h, double sigma, double etamu, double etab, double *h_gsigma);
 /* LM kind, samplePopulation() (cma/lm_cmaes.cpp:91-127): candidates 2p and 2p+1 are m +- sigma Az_p, Az_p = the base vector
  * z_p pushed through live memory rows jarr[i0_p .. memlen-1] (algorithm 3; the inner products use the ORIGINAL z_p, :117).
  * h_z / h_i0 == NULL: base vectors (Rademacher or Gaussian) and subset starts from the Philox stream; otherwise DRAW REPLAY:

@@ -62,6 +62,7 @@ int bbgpu_cma_update(bbgpu_cma *h, double, int) { h->gen++; h->f *= 0.8; return 
 int bbgpu_cma_eig(bbgpu_cma *, const double *, const double *) { return 0; }
 int bbgpu_cma_probe(bbgpu_cma *, double, int) { return 0; }
 int bbgpu_cma_swarm_radius(bbgpu_cma *, double *mean, double *m2) { *mean = 1.0; *m2 = 1.0; return 0; }
+int bbgpu_cma_xnes_update(bbgpu_cma *h, double, double, double, double *g) { h->gen++; *g = 0.0; return 0; }
 int bbgpu_cma_lm_sample(bbgpu_cma *, double, uint64_t, int, const int32_t *, const double *, const int32_t *) { return 0; }
 int bbgpu_cma_lm_update(bbgpu_cma *h, double, int, int, int, const int32_t *) { h->gen++; h->f *= 0.8; return 0; }
 int bbgpu_cma_fetch(bbgpu_cma *h, bbgpu_cma_report *r) {
