@@ -17,6 +17,8 @@
 // (what cusolverDnDormtr consumes).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -258,6 +260,227 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_coop_kernel(const double 
 #undef SY_TICK
 }
 
+
+// ---- register-resident variant (n <= 1024, at most SR_RQ rows per CTA: n <= 1036 on 148 SMs) ---------------------------
+// Same algorithm, same exchange, same outputs as sytrd_coop_kernel; what changes is where the matrix lives.  Thread t already
+// keeps columns t, t + 256, ... of every VECTOR in registers; here it also keeps those columns of the CTA's (at most 7)
+// ROWS: 28 doubles.  The pass of a column -- A22 -= v w^T + w v^T, y = A22 v_next -- is then 84 register FMAs per thread
+// with the reflector columns it already holds, instead of a sweep over 54 KB of shared memory (2 160 of the 7 850 cycles of
+// a column, profiles/r01_ncu_eig_own.txt).  The two block-wide sums on the column's dependency chain use a flat second
+// stage (eight partials read back by every thread) and the reflector scalars come from a fast reciprocal.
+constexpr int SR_RQ = 7;  // rows per CTA
+constexpr int SR_KQ = 4;  // columns per thread
+
+__device__ __forceinline__ double sr_block_sum(double v, double *red8, int lane, int wid) {
+    v = bb::warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red8[wid] = v;
+    __syncthreads();
+    const double4 lo = *reinterpret_cast<const double4*>(red8), hi = *reinterpret_cast<const double4*>(red8 + 4);
+    return ((lo.x + lo.y) + (lo.z + lo.w)) + ((hi.x + hi.y) + (hi.z + hi.w));
+}
+
+__device__ __forceinline__ double sr_rcp(double p) { // 1 / p, ~1 ulp, for a normal non-zero p
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    r = fma(r, fma(-p, r, 1.0), r);
+    r = fma(r, fma(-p, r, 1.0), r);
+    return r;
+}
+
+__global__ void __launch_bounds__(SY_THREADS, 1) sytrd_reg_kernel(const double *__restrict__ A, int n, int ldA, double *__restrict__ d,
+        double *__restrict__ e, double *__restrict__ tau, double *__restrict__ Vcm, double *ybuf, double *rowbuf, unsigned *barrier) {
+    __shared__ __align__(16) double v[SR_KQ * SY_THREADS], w[SR_KQ * SY_THREADS];
+    __shared__ __align__(32) double red8[8];
+    __shared__ double part[8][8];
+    const int G = gridDim.x, me = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nrows = me < n ? (n - me + G - 1) / G : 0;
+    double a[SR_RQ][SR_KQ];
+#pragma unroll
+    for (int q = 0; q < SR_RQ; q++) {
+        const int r = me + q * G;
+#pragma unroll
+        for (int k = 0; k < SR_KQ; k++) {
+            const int c = tid + k * SY_THREADS;
+            a[q][k] = (r < n && c < n) ? A[(size_t) max(r, c) * ldA + min(r, c)] : 0.0;
+        }
+    }
+    // ---- reflector 0 from column 0 of the input
+    double vreg[SR_KQ];
+    double tau_i;
+    {
+        double ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < SR_KQ; k++) {
+            const int c = tid + k * SY_THREADS;
+            vreg[k] = (c >= 1 && c < n) ? A[(size_t) c * ldA] : 0.0;
+            if (c >= 2) ss += vreg[k] * vreg[k];
+        }
+        ss = sr_block_sum(ss, red8, lane, wid);
+        const double alpha = A[(size_t) ldA];
+        double beta = alpha, scal = 0.0;
+        tau_i = 0.0;
+        if (ss != 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+            tau_i = (beta - alpha) / beta;
+            scal = 1.0 / (alpha - beta);
+        }
+#pragma unroll
+        for (int k = 0; k < SR_KQ; k++) {
+            const int c = tid + k * SY_THREADS;
+            vreg[k] = c == 1 ? 1.0 : vreg[k] * scal;
+            v[c] = vreg[k];
+            w[c] = 0.0;
+        }
+        if (me == 0 && tid == 0) { d[0] = A[0]; e[0] = beta; tau[0] = tau_i; }
+    }
+    __syncthreads();
+    // y_0 = A v_0 for the own rows r > 0 (row sums over the thread-owned columns), and the pivot row 1
+    auto row_sums = [&](const double (&vn)[SR_KQ], int i_done, int parity_out) {
+        // acc[q] = sum over this thread's columns of a[q][k] * vn[k]; eight values (7 rows + a zero) reduced over the warp by
+        // a butterfly that halves the values a lane carries, then over the eight warps through shared memory
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            acc[q] = 0.0;
+            if (q < SR_RQ) {
+#pragma unroll
+                for (int k = 0; k < SR_KQ; k++) acc[q] = fma(a[q][k], vn[k], acc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool up = (lane & 16) != 0;
+            const double send = up ? acc[q] : acc[q + 4], keep = up ? acc[q + 4] : acc[q];
+            acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const bool up = (lane & 8) != 0;
+            const double send = up ? acc[q] : acc[q + 2], keep = up ? acc[q + 2] : acc[q];
+            acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const bool up = (lane & 4) != 0;
+            const double send = up ? acc[0] : acc[1], keep = up ? acc[1] : acc[0];
+            acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
+            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+        }
+        if ((lane & 3) == 0) part[wid][lane >> 2] = acc[0]; // row lane >> 2
+        __syncthreads();
+        if (tid < nrows) {
+            const int r = me + tid * G;
+            if (r > i_done) {
+                double s = 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) s += part[u][tid];
+                ybuf[(size_t) parity_out * n + r] = s;
+            }
+        }
+    };
+    auto publish_row = [&](int r, int parity_out) { // row r (owned by this CTA) into the exchange buffer
+        const int qp = r / G;
+#pragma unroll
+        for (int q = 0; q < SR_RQ; q++) {
+            if (q == qp) {
+#pragma unroll
+                for (int k = 0; k < SR_KQ; k++) {
+                    const int c = tid + k * SY_THREADS;
+                    if (c < n) rowbuf[(size_t) parity_out * n + c] = a[q][k];
+                }
+            }
+        }
+    };
+    row_sums(vreg, 0, 0);
+    if (1 % G == me) publish_row(1, 0);
+    for (int i = 0; i < n - 1; i++) {
+        const int parity = i & 1;
+        sy_grid_barrier(barrier, (unsigned) (i + 1) * (unsigned) G);
+        const double *y = ybuf + (size_t) parity * n, *old = rowbuf + (size_t) parity * n;
+        double yk[SR_KQ], ok[SR_KQ];
+#pragma unroll
+        for (int k = 0; k < SR_KQ; k++) {
+            const int c = tid + k * SY_THREADS;
+            const bool in = c > i && c < n;
+            yk[k] = in ? __ldcg(y + c) : 0.0;
+            ok[k] = in ? __ldcg(old + c) : 0.0;
+        }
+        const double y1 = __ldcg(y + i + 1), o1 = __ldcg(old + i + 1);
+        const bool more = i + 2 < n;
+        const double y2 = more ? __ldcg(y + i + 2) : 0.0, o2 = more ? __ldcg(old + i + 2) : 0.0;
+        double dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < SR_KQ; k++) dot = fma(yk[k], vreg[k], dot);
+        dot = sr_block_sum(dot, red8, lane, wid);
+        const double half = 0.5 * tau_i * tau_i * dot;
+        const double wr1 = tau_i * y1 - half;
+        const double diag = o1 - 2.0 * wr1;
+        if (me == i % G) {
+#pragma unroll
+            for (int k = 0; k < SR_KQ; k++) {
+                const int c = tid + k * SY_THREADS;
+                if (c >= i + 2 && c < n) Vcm[(size_t) i * n + c] = vreg[k];
+            }
+        }
+        if (!more) {
+            if (me == 0 && tid == 0) d[n - 1] = diag;
+            break;
+        }
+        const double v2 = v[i + 2]; // v_i[i+2], before w / v are overwritten below
+        double wk[SR_KQ], xk[SR_KQ], ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < SR_KQ; k++) {
+            const int c = tid + k * SY_THREADS;
+            wk[k] = (c > i && c < n) ? tau_i * yk[k] - half * vreg[k] : 0.0;
+            xk[k] = (c > i + 1 && c < n) ? ok[k] - wk[k] - wr1 * vreg[k] : 0.0;
+            if (c > i + 2) ss = fma(xk[k], xk[k], ss);
+        }
+        ss = sr_block_sum(ss, red8, lane, wid); // its barriers also order the reads of v above against the writes below
+        const double alpha = o2 - (tau_i * y2 - half * v2) - wr1 * v2;
+        double beta_n = alpha, tau_n = 0.0, scal = 0.0;
+        if (ss != 0.0) {
+            beta_n = -copysign(sqrt(alpha * alpha + ss), alpha);
+            tau_n = (beta_n - alpha) * sr_rcp(beta_n);
+            scal = sr_rcp(alpha - beta_n);
+        }
+        // the rows of this CTA need v_i and w_i at THEIR column index: through shared memory (v still holds v_i)
+#pragma unroll
+        for (int k = 0; k < SR_KQ; k++) w[tid + k * SY_THREADS] = wk[k];
+        __syncthreads();
+        double vr[SR_RQ], wr[SR_RQ];
+#pragma unroll
+        for (int q = 0; q < SR_RQ; q++) {
+            const int r = me + q * G;
+            const bool on = q < nrows && r > i;
+            vr[q] = on ? v[r] : 0.0;
+            wr[q] = on ? w[r] : 0.0;
+        }
+        double vnk[SR_KQ];
+#pragma unroll
+        for (int k = 0; k < SR_KQ; k++) {
+            const int c = tid + k * SY_THREADS;
+            vnk[k] = c == i + 2 ? 1.0 : xk[k] * scal; // 0 for c <= i+1 and beyond n
+        }
+        if (me == (i + 1) % G && tid == 0) { d[i + 1] = diag; e[i + 1] = beta_n; tau[i + 1] = tau_n; }
+        // ---- the pass, in registers: A22 -= v w^T + w v^T on the own rows (columns <= i: w = v = 0, nothing changes)
+#pragma unroll
+        for (int q = 0; q < SR_RQ; q++) {
+#pragma unroll
+            for (int k = 0; k < SR_KQ; k++) a[q][k] = a[q][k] - vr[q] * wk[k] - wr[q] * vreg[k];
+        }
+        __syncthreads(); // every thread has read v_i[r] / w_i[r]
+#pragma unroll
+        for (int k = 0; k < SR_KQ; k++) {
+            vreg[k] = vnk[k];
+            v[tid + k * SY_THREADS] = vnk[k];
+        }
+        row_sums(vreg, i + 1, parity ^ 1);
+        if ((i + 2) % G == me) publish_row(i + 2, parity ^ 1);
+        tau_i = tau_n;
+    }
+}
+
 } // namespace
 
 namespace bb {
@@ -365,6 +588,19 @@ int sytrd_device(bbgpu_ctx *ctx, int n, const double *d_A, int ldA, double *d_d,
     if (!sytrd_fits(ctx, n)) return fail(BBGPU_ERR_ARG, "sytrd_device: n = %d is beyond the cooperative kernel", n);
     cudaStream_t st = ctx->stream;
     const int G = ctx->sm_count, nrows = (n + G - 1) / G, np = (n + 63) & ~63;
+    // the register-resident kernel where the rows of a CTA fit its registers (BBGPU_SYTRD=smem keeps the other one)
+    static const bool force_smem = [] { const char *e = getenv("BBGPU_SYTRD"); return e && e[0] == 's'; }();
+    if (!force_smem && n <= SR_KQ * SY_THREADS && nrows <= SR_RQ) {
+        double *dy = ws, *dr = ws + 2 * (size_t) n;
+        unsigned *dbar = reinterpret_cast<unsigned*>(ws + 4 * (size_t) n);
+        BB_CUDA(cudaMemsetAsync(dbar, 0, 64, st));
+        int nn = n, ld = ldA;
+        const double *A = d_A;
+        void *args[] = { (void*) &A, (void*) &nn, (void*) &ld, (void*) &d_d, (void*) &d_e, (void*) &d_tau, (void*) &d_Vcm, (void*) &dy,
+                (void*) &dr, (void*) &dbar };
+        BB_CUDA(cudaLaunchCooperativeKernel((const void*) sytrd_reg_kernel, dim3(G), dim3(SY_THREADS), args, 0, st));
+        return launched(ctx, "sytrd_reg_kernel");
+    }
     const size_t smem = ((size_t) nrows * np + 3 * (size_t) np + 32 + 8 * (size_t) nrows) * sizeof(double);
     BB_CUDA(cudaFuncSetAttribute(sytrd_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     double *dy = ws, *dr = ws + 2 * (size_t) n;
@@ -421,11 +657,20 @@ int bbgpu_sytrd_host(bbgpu_ctx *ctx, int n, const double *h_A, double *h_d, doub
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     float best = 1e30f;
+    // the kernel the engine would pick for this n (register-resident up to n = 1024) unless the per-phase profile of the
+    // shared-memory kernel is asked for
+    const bool prof_run = getenv("BBGPU_SYTRD_PROF") != nullptr;
+    double *ws = nullptr;
+    BB_TRY(bb::dev_alloc(&ws, bb::sytrd_workspace_doubles(n)));
     for (int r = 0; r < reps; r++) {
         BB_CUDA(cudaMemsetAsync(dbar, 0, sizeof(unsigned), st));
         cudaEventRecord(e0, st);
-        BB_CUDA(cudaLaunchCooperativeKernel((const void*) sytrd_coop_kernel, dim3(G), dim3(SY_THREADS), args, smem, st));
-        BB_TRY(bb::launched(ctx, "sytrd_coop_kernel"));
+        if (prof_run || !bb::sytrd_fits(ctx, n)) { // (this entry accepts sizes up to the hard shared-memory limit)
+            BB_CUDA(cudaLaunchCooperativeKernel((const void*) sytrd_coop_kernel, dim3(G), dim3(SY_THREADS), args, smem, st));
+            BB_TRY(bb::launched(ctx, "sytrd_coop_kernel"));
+        } else {
+            BB_TRY(bb::sytrd_device(ctx, n, dA, n, dd, de, dt, dV, ws));
+        }
         cudaEventRecord(e1, st);
         BB_CUDA(cudaEventSynchronize(e1));
         float t = 0.f;
@@ -449,6 +694,7 @@ int bbgpu_sytrd_host(bbgpu_ctx *ctx, int n, const double *h_A, double *h_d, doub
                     hp[b * 6 + 4] / (double) n, hp[b * 6 + 5] / (double) n);
     }
     cudaFree(dA); cudaFree(dV); cudaFree(dd); cudaFree(de); cudaFree(dt); cudaFree(dy); cudaFree(dr); cudaFree(dbar); cudaFree(dprof);
+    cudaFree(ws);
     return BBGPU_OK;
 }
 

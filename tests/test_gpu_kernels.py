@@ -138,7 +138,7 @@ def test_philox_normals_are_standard_normal_and_placement_invariant(ctx):
     assert np.array_equal(z[:64], ctx.philox_normal(1234, 7, 64, 1001))
 
 
-@pytest.mark.parametrize("n", [3, 10, 149, 600, 1000, 1700])
+@pytest.mark.parametrize("n", [3, 10, 149, 300, 600, 1000, 1024, 1025, 1036, 1700])
 def test_cooperative_sytrd_matches_lapack(ctx, n):
     """The persistent-kernel tridiagonalisation against LAPACK dsytrd('L') on the same matrix: same convention, so d, e, tau
     agree to rounding, and the reflectors reproduce Q^T A Q = T."""
