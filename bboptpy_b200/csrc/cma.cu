@@ -79,6 +79,8 @@ struct bbgpu_cma {
     bb::PeerRegion *peer = nullptr; // the rank-mu partial buffers of all ranks, mapped (NVLink peer memory); null: NCCL
     double last_sigma = 0.0;
     double *Yloc = nullptr, *coef_loc = nullptr, *wm_loc = nullptr, *norm_all = nullptr, *red = nullptr, *rowsq_loc = nullptr;
+    double *Ycomp = nullptr, *coef_comp = nullptr; // the selected local steps, compacted (non-active kind: half the rows carry no weight)
+    int *sel_idx = nullptr, *ksel = nullptr;
     int rowsq_loc_tiles = 0;
     // report
     bbgpu_cma_report *d_report = nullptr;
@@ -522,6 +524,62 @@ __global__ void __launch_bounds__(256) shard_coef_kernel(const int *__restrict__
     else if (worst) c = -__dmul_rn(__dmul_rn(cneg, w[i]), yc);
     coef_loc[loc] = c;
     wm_loc[loc] = wm;
+}
+
+// Compaction of the local selection (non-active kind): candidates with a non-zero covariance coefficient, in local order,
+// get consecutive positions; their coefficients follow, the tail of the coefficient array is zeroed, the count goes to
+// *ksel.  One CTA: an inclusive scan over at most 64 K flags in chunks of 1024.
+__global__ void __launch_bounds__(1024) shard_compact_kernel(const double *__restrict__ coef_loc, int rows, int *__restrict__ sel_idx,
+        double *__restrict__ coef_comp, int coef_cap, int *__restrict__ ksel) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < rows; k0 += 1024) {
+        const int k = k0 + tid;
+        const double c = k < rows ? coef_loc[k] : 0.0;
+        const int flag = c != 0.0 ? 1 : 0;
+        int x = flag;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int s = wsum[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, s, off);
+                if (lane >= off) s += y;
+            }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const int pos = base_s + (wid ? wsum[wid - 1] : 0) + x - flag;
+        if (flag) {
+            sel_idx[pos] = k;
+            coef_comp[pos] = c;
+        }
+        __syncthreads();
+        if (tid == 0) base_s += wsum[31];
+        __syncthreads();
+    }
+    const int total = base_s;
+    for (int q = total + tid; q < coef_cap; q += 1024) coef_comp[q] = 0.0;
+    if (tid == 0) *ksel = total;
+}
+
+// Ycomp[r][:] = Y[sel_idx[r]][:] for r < *ksel
+__global__ void __launch_bounds__(256) shard_gather_kernel(double *__restrict__ Ycomp, const double *__restrict__ Y, int64_t ld, int n,
+        const int *__restrict__ sel_idx, const int *__restrict__ ksel) {
+    const int r = blockIdx.x;
+    if (r >= *ksel) return;
+    const double2 *src = reinterpret_cast<const double2*>(Y + (int64_t) sel_idx[r] * ld);
+    double2 *dst = reinterpret_cast<double2*>(Ycomp + (int64_t) r * ld);
+    for (int i = threadIdx.x; 2 * i < n; i += blockDim.x) dst[i] = src[i]; // ld is a multiple of 8: pad columns copy as zeros
 }
 
 // part[s][i] = sum over the local rows k of split s of wm[k] X[k][i]
@@ -970,10 +1028,21 @@ static int shard_partial(bbgpu_cma *h) {
         BB_TRY(launched(ctx, "shard_mean_final_kernel"));
         BB_CUDA(cudaMemsetAsync(h->red, 0, (size_t) n * h->ldn * 8, st));
     }
-    // S_local (lower) = sum_k coef_k y_k y_k^T over the local candidates (zero coefficient: not selected)
+    // S_local (lower) = sum_k coef_k y_k y_k^T over the local candidates.  Active: every candidate carries a coefficient.
+    // Otherwise only the best mu of all lambda do -- about half of the local rows --, so they are compacted first (their
+    // number is data dependent: it reaches the kernel through device memory) and the SYRK runs over them alone.
     GemmArgs g {};
     g.A = h->Yloc; g.lda = h->ldn; g.B = h->Yloc; g.ldb = h->ldn;
     g.M = n; g.N = n; g.K = h->lam_loc; g.kscale = h->coef_loc; g.kscale_padded = true;
+    if (h->Ycomp != nullptr) {
+        ProfScope prof(ctx, BBGPU_PROF_UPDATE_MISC);
+        shard_compact_kernel<<<1, 1024, 0, st>>>(h->coef_loc, h->lam_loc, h->sel_idx, h->coef_comp, (int) round_up(h->lam_loc, 32) + 32,
+                h->ksel);
+        BB_TRY(launched(ctx, "shard_compact_kernel"));
+        shard_gather_kernel<<<h->lam_loc, 256, 0, st>>>(h->Ycomp, h->Yloc, h->ldn, n, h->sel_idx, h->ksel);
+        BB_TRY(launched(ctx, "shard_gather_kernel"));
+        g.A = h->Ycomp; g.B = h->Ycomp; g.kscale = h->coef_comp; g.Kdev = h->ksel;
+    }
     g.C = h->red; g.ldc = h->ldn; g.vec = h->pc; g.s0 = 0.0; g.s1 = 0.0; g.dscal = h->dscal;
     ProfScope prof(ctx, BBGPU_PROF_COV_SYRK);
     return launch_gemm<2, EPI_SYRK>(ctx, g);
@@ -1231,6 +1300,12 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
         } else if (h->shards > 1) {
             A(&h->Yloc, laml * ldn); A(&h->coef_loc, (size_t) round_up(h->lam_loc, 32) + 32); A(&h->wm_loc, laml);
             A(&h->red, (size_t) n * ldn + ldn);
+            static const bool no_compact = [] { const char *e = getenv("BBGPU_SHARD_COMPACT"); return e && e[0] == '0'; }();
+            if (!h->active && !no_compact) {
+                A(&h->Ycomp, laml * ldn); A(&h->coef_comp, (size_t) round_up(h->lam_loc, 32) + 32);
+                if (rc == BBGPU_OK) rc = dev_alloc(&h->sel_idx, laml);
+                if (rc == BBGPU_OK) rc = dev_alloc(&h->ksel, (size_t) 1);
+            }
             if (h->active) {
                 h->rowsq_loc_tiles = ceil_div(n, 64);
                 A(&h->norm_all, lam); A(&h->rowsq_loc, (size_t) h->rowsq_loc_tiles * laml);
@@ -1300,7 +1375,9 @@ int bbgpu_cma_destroy(bbgpu_cma *h) {
     double *bufs[] = { h->xmean, h->xold, h->pc, h->ps, h->D, h->dm, h->tmpn, h->W, h->weights, h->lower, h->upper, h->coef,
             h->ycoeff, h->dscal, h->X, h->Zbuf[0], h->Zbuf[1], h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
             h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc, h->own_ws,
-            h->Ystk, h->Mch, h->Lt, h->negone, h->rnorm, h->rstat, h->PCmat, h->Vmat, h->lmb, h->lmd, h->Zp };
+            h->Ystk, h->Mch, h->Lt, h->negone, h->rnorm, h->rstat, h->PCmat, h->Vmat, h->lmb, h->lmd, h->Zp, h->Ycomp, h->coef_comp };
+    if (h->sel_idx) cudaFree(h->sel_idx);
+    if (h->ksel) cudaFree(h->ksel);
     if (h->lm_jarr) cudaFree(h->lm_jarr);
     if (h->lm_i0) cudaFree(h->lm_i0);
     if (h->ev_ch_fork) cudaEventDestroy(h->ev_ch_fork);

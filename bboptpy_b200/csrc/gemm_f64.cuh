@@ -48,6 +48,8 @@ struct GemmArgs {
     double s0, s1;        // SAMPLE: s0 = sigma; SYRK: s0 = decay, s1 = c1
     const double *dscal;  // SYRK: device scalar c2 = (1-hsig) cc (2-cc)
     double *partial;      // ROWSQ: partial[tileN * M + row]
+    const int *Kdev;      // optional: the reduction length on the DEVICE (<= K); rows [*Kdev, K) are not visited.  Lets a
+                          // data-dependent row count (compacted selections) reach the kernel without a host round trip
 };
 
 // CTA = 8 warps as 4 (M) x 2 (N); a warp owns MA x NA DMMA atoms -> CTA tile (32 MA) x (16 NA)
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_f64_kernel(const GemmArgs p
 #pragma unroll
         for (int j = 0; j < NA; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    const int nk = (p.K + G_BK - 1) / G_BK;
+    const int nk = ((p.Kdev ? min(*p.Kdev, p.K) : p.K) + G_BK - 1) / G_BK;
 
     auto issue = [&](int kc) {
         if (kc < nk) {

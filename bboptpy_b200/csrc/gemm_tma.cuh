@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
     }
     __syncthreads();
 
-    const int nk = (p.K + BK - 1) / BK;
+    const int nk = ((p.Kdev ? min(*p.Kdev, p.K) : p.K) + BK - 1) / BK;
 
     if (warp == T_CONSUMERS / 32) {
         // ===== TMA producer (one elected lane) =====
