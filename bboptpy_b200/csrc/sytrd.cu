@@ -31,8 +31,7 @@ constexpr int SY_THREADS = 256;
 __device__ __forceinline__ void sy_grid_barrier(unsigned *counter, unsigned target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory"); // release: the CTA's stores first
         unsigned seen;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
