@@ -101,6 +101,22 @@ int bbo_xnes_geti(void *h, const char *name);
 double bbo_xnes_getd(void *h, const char *name);
 int bbo_xnes_getv(void *h, const char *name, double *out, int cap);
 
+/* ---- SaNSDE (de/sansde.cpp): self-adaptive DE with neighbourhood search, in-place (asynchronous) like JADE.
+ * geti: "n", "np", "fev", "it", "pns0", "pns1", "pnf0", "pnf1";  getd: "p", "fp", "crm", "crrec", "crdeltaf", "fpns0", ...;
+ * getv: "swarm_x" (np*n), "swarm_f", "swarm_cr" (np) in the order the reference holds them, and -- port only -- the tagged
+ * draws of the generation just run: "t_zcr" (NaN when CR was not refreshed), "t_ifstrat", "t_F", "t_r1", "t_r2", "t_r3",
+ * "t_istrat", "t_jrand", "t_u" (np*n), plus its outcome "t_succ", "t_ftrial", "t_cr1" */
+void *bbo_sansde_new(int mfev, int np, double tol, int repaircr, int crref, int pupdate, int crupdate);
+void bbo_sansde_free(void *h);
+void bbo_sansde_init(void *h, int obj, int n, const double *lower, const double *upper, const double *guess);
+void bbo_sansde_iterate(void *h);
+int bbo_sansde_converged(void *h);
+int bbo_sansde_optimize(void *h, int obj, int n, const double *lower, const double *upper, const double *guess,
+                        double *xout, int *fev);
+int bbo_sansde_geti(void *h, const char *name);
+double bbo_sansde_getd(void *h, const char *name);
+int bbo_sansde_getv(void *h, const char *name, double *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

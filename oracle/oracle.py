@@ -80,6 +80,21 @@ def _bind(lib):
     lib.bbo_xnes_getd.restype = d
     lib.bbo_xnes_getv.argtypes = [vp, cp, _c_dp, i]
     lib.bbo_xnes_getv.restype = i
+    lib.bbo_sansde_new.restype = vp
+    lib.bbo_sansde_new.argtypes = [i, i, d, i, i, i, i]
+    lib.bbo_sansde_free.argtypes = [vp]
+    lib.bbo_sansde_init.argtypes = [vp, i, i, _c_dp, _c_dp, _c_dp]
+    lib.bbo_sansde_iterate.argtypes = [vp]
+    lib.bbo_sansde_converged.argtypes = [vp]
+    lib.bbo_sansde_converged.restype = i
+    lib.bbo_sansde_optimize.argtypes = [vp, i, i, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.POINTER(i)]
+    lib.bbo_sansde_optimize.restype = i
+    lib.bbo_sansde_geti.argtypes = [vp, cp]
+    lib.bbo_sansde_geti.restype = i
+    lib.bbo_sansde_getd.argtypes = [vp, cp]
+    lib.bbo_sansde_getd.restype = d
+    lib.bbo_sansde_getv.argtypes = [vp, cp, _c_dp, i]
+    lib.bbo_sansde_getv.restype = i
     lib.bbo_de_new.restype = vp
     lib.bbo_de_new.argtypes = [i, i, i, d, i, i, d, d, d, i, i]
     lib.bbo_de_free.argtypes = [vp]
@@ -143,6 +158,9 @@ class Oracle:
         if kind == LM:
             eigenrate, alphacov, adjustlr = float(memory), float(bool(rademacher)), bool(usenew)
         return OracleCma(self, kind, mfev, tol, np_, sigma0, bound, eigenrate, alphacov, adjustlr)
+
+    def sansde(self, mfev, np_, tol, repaircr=True, crref=5, pupdate=50, crupdate=25):
+        return OracleGeneric(self, "sansde", self.lib.bbo_sansde_new(mfev, np_, tol, int(repaircr), crref, pupdate, crupdate))
 
     def xnes(self, mfev, tol, a0=1.0, etamu=1.0):
         return OracleXnes(self, mfev, tol, a0, etamu)
@@ -283,6 +301,59 @@ class OracleCma:
         if self.kind == SEP:
             s["ccov"] = self.getd("ccov")
         return s
+
+
+class OracleGeneric:
+    """An optimizer behind a bbo_<prefix>_{free,init,iterate,converged,optimize,geti,getd,getv} family."""
+
+    def __init__(self, o, prefix, handle):
+        self.o, self.lib, self.prefix, self.h = o, o.lib, prefix, handle
+
+    def _fn(self, name):
+        return getattr(self.lib, f"bbo_{self.prefix}_{name}")
+
+    def __del__(self):
+        try:
+            self._fn("free")(self.h)
+        except Exception:
+            pass
+
+    def init(self, obj, lower, upper, guess=None):
+        lower, upper = _f64(lower), _f64(upper)
+        guess = _f64(guess) if guess is not None else lower
+        self._fn("init")(self.h, obj, lower.size, lower.ctypes.data, upper.ctypes.data, guess.ctypes.data)
+
+    def iterate(self):
+        self._fn("iterate")(self.h)
+
+    def converged(self):
+        return bool(self._fn("converged")(self.h))
+
+    def optimize(self, obj, lower, upper, guess=None):
+        lower, upper = _f64(lower), _f64(upper)
+        guess = _f64(guess) if guess is not None else lower
+        x = np.empty(lower.size)
+        fev = ctypes.c_int(0)
+        conv = self._fn("optimize")(self.h, obj, lower.size, lower.ctypes.data, upper.ctypes.data, guess.ctypes.data,
+                                    x.ctypes.data, ctypes.byref(fev))
+        return x, fev.value, bool(conv)
+
+    def geti(self, name):
+        return self._fn("geti")(self.h, name.encode())
+
+    def getd(self, name):
+        return self._fn("getd")(self.h, name.encode())
+
+    def getv(self, name):
+        n = self._fn("getv")(self.h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype=np.float64)
+        self._fn("getv")(self.h, name.encode(), out.ctypes.data, n)
+        return out
+
+    def mat(self, name):
+        return self.getv(name).reshape(-1, self.geti("n"))
 
 
 class OracleXnes:

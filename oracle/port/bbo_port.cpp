@@ -1099,6 +1099,179 @@ struct PortXnes {
     }
 };
 
+/* ---- de/sansde.cpp (Yang, Tang, Yao 2008: self-adaptive DE with neighbourhood search) */
+struct PortSansde {
+    int mfev = 0, np = 0, ncrref = 5, npup = 50, ncrup = 25;
+    double tol = 0;
+    bool repaircr = true;
+    Objective f;
+    int n = 0, it = 0, fev = 0;
+    double p = 0.5, fp = 0.5, crrec = 0, crdeltaf = 0, crm = 0.5;
+    int pns[2] = { 0, 0 }, pnf[2] = { 0, 0 };
+    double fpns[2] = { 0, 0 }, fpnf[2] = { 0, 0 };
+    std::vector<double> lower, upper, work, sw_x, sw_f, sw_cr;
+    BboNormal Z;
+    /* tagged draws + outcome of the last generation (the GPU engine replays the draws) */
+    std::vector<double> t_zcr, t_ifstrat, t_F, t_r1, t_r2, t_r3, t_istrat, t_jrand, t_u, t_succ, t_ftrial, t_cr1;
+
+    void init() { /* :54-92 */
+        fev = 0;
+        it = 0;
+        p = 0.5;
+        fp = 0.5;
+        crrec = crdeltaf = 0.0;
+        crm = 0.5;
+        pns[0] = pns[1] = pnf[0] = pnf[1] = 0;
+        fpns[0] = fpns[1] = fpnf[0] = fpnf[1] = 0.0;
+        work.assign(n, 0.0);
+        sw_x.assign((size_t) np * n, 0.0);
+        sw_f.assign(np, 0.0);
+        sw_cr.assign(np, 0.5);
+        for (int i = 0; i < np; i++) {
+            double *x = &sw_x[(size_t) i * n];
+            for (int j = 0; j < n; j++) x[j] = eng().uniform_real(lower[j], upper[j]);
+            sw_f[i] = f(x);
+            fev++;
+        }
+    }
+
+    void sort_swarm() { /* std::sort(_swarm, compare_fitness): whole points move, their CR with them */
+        struct Rec { double f; int pos; };
+        std::vector<Rec> rec(np);
+        for (int i = 0; i < np; i++) rec[i] = Rec { sw_f[i], i };
+        std::sort(rec.begin(), rec.end(), [](const Rec &a, const Rec &b) { return a.f < b.f; });
+        std::vector<double> nx((size_t) np * n), nf(np), nc(np);
+        for (int i = 0; i < np; i++) {
+            nf[i] = rec[i].f;
+            nc[i] = sw_cr[rec[i].pos];
+            std::copy(sw_x.begin() + (size_t) rec[i].pos * n, sw_x.begin() + (size_t) (rec[i].pos + 1) * n, nx.begin() + (size_t) i * n);
+        }
+        sw_x.swap(nx);
+        sw_f.swap(nf);
+        sw_cr.swap(nc);
+    }
+
+    void iterate() { /* :94-212 */
+        sort_swarm();
+        for (auto *v : { &t_zcr, &t_ifstrat, &t_F, &t_r1, &t_r2, &t_r3, &t_istrat, &t_jrand, &t_succ, &t_ftrial, &t_cr1 }) v->assign(np, 0.0);
+        t_u.assign((size_t) np * n, 0.0);
+        for (int i = 0; i < np; i++) {
+            t_zcr[i] = NAN;
+            if (it % ncrref == 0) {
+                const double z = Z.draw(eng());
+                t_zcr[i] = z;
+                sw_cr[i] = z * 0.1 + crm;
+                sw_cr[i] = std::max(0.0, std::min(sw_cr[i], 1.0));
+            }
+            const int ifstrat = eng().uniform_real(0.0, 1.0) < fp ? 0 : 1;
+            double F = -1.0;
+            while (F < 0.0) {
+                if (ifstrat == 0) F = Z.draw(eng()) * 0.3 + 0.5;
+                else F = std::tan(M_PI * (eng().uniform_real(0.0, 1.0) - 0.5)); /* sampleCauchy, :288-290 */
+                F = std::min(F, 1.0);
+            }
+            int r1 = i;
+            while (r1 == i) r1 = eng().uniform_int(0, np - 1);
+            int r2 = i;
+            while (r2 == i || r2 == r1) r2 = eng().uniform_int(0, np - 1);
+            int r3 = i;
+            while (r3 == i || r3 == r1 || r3 == r2) r3 = eng().uniform_int(0, np - 1);
+            const int istrat = eng().uniform_real(0.0, 1.0) < p ? 0 : 1;
+            /* mutate(), :250-286 */
+            const double *x = &sw_x[(size_t) i * n], *best = &sw_x[0], *x1 = &sw_x[(size_t) r1 * n], *x2 = &sw_x[(size_t) r2 * n],
+                    *x3 = &sw_x[(size_t) r3 * n];
+            if (istrat == 0) {
+                for (int q = 0; q < n; q++) work[q] = x1[q] + F * (x2[q] - x3[q]);
+            } else {
+                for (int q = 0; q < n; q++) work[q] = x[q] + F * (best[q] - x[q]) + F * (x1[q] - x2[q]);
+            }
+            const int irand = eng().uniform_int(0, n - 1);
+            double cr1 = 0.0;
+            const double CR = sw_cr[i];
+            for (int q = 0; q < n; q++) {
+                const double u = eng().uniform_real(0.0, 1.0);
+                t_u[(size_t) i * n + q] = u;
+                if (u <= CR || q == irand) cr1 += 1.0;
+                else work[q] = x[q];
+            }
+            cr1 = repaircr ? cr1 / n : CR;
+            for (int q = 0; q < n; q++) {
+                if (work[q] < lower[q]) work[q] = (lower[q] + x[q]) / 2.0;
+                else if (work[q] > upper[q]) work[q] = (upper[q] + x[q]) / 2.0;
+            }
+            const double fwork = f(work.data());
+            fev++;
+            t_ifstrat[i] = ifstrat; t_F[i] = F; t_r1[i] = r1; t_r2[i] = r2; t_r3[i] = r3; t_istrat[i] = istrat; t_jrand[i] = irand;
+            t_ftrial[i] = fwork; t_cr1[i] = cr1;
+            if (fwork < sw_f[i]) {
+                t_succ[i] = 1.0;
+                pns[istrat]++;
+                const double deltaf = sw_f[i] - fwork;
+                crrec += cr1 * deltaf;
+                crdeltaf += deltaf;
+                fpns[ifstrat] += F;
+                sw_f[i] = fwork;
+                std::copy(work.begin(), work.end(), sw_x.begin() + (size_t) i * n);
+            } else {
+                pnf[istrat]++;
+                fpnf[ifstrat] += F;
+            }
+        }
+        it++;
+        if (it > 0 && it % npup == 0) {
+            const int pnsf0 = pns[0] + pnf[0], pnsf1 = pns[1] + pnf[1];
+            p = (1.0 * pns[0] * pnsf1) / (pns[1] * pnsf0 + pns[0] * pnsf1);
+            pns[0] = pns[1] = pnf[0] = pnf[1] = 0;
+        }
+        if (it > 0 && it % ncrup == 0) {
+            if (crdeltaf > 0) crm = crrec / crdeltaf;
+            crrec = crdeltaf = 0.0;
+        }
+        if (it > 0 && it % ncrup == 0) {
+            const double fpnsf0 = fpns[0] + fpnf[0], fpnsf1 = fpns[1] + fpnf[1];
+            fp = (1.0 * fpns[0] * fpnsf1) / (fpns[1] * fpnsf0 + fpns[0] * fpnsf1);
+            fpns[0] = fpns[1] = fpnf[0] = fpnf[1] = 0.0;
+        }
+    }
+
+    bool converged() { /* through solution(), which sorts first (:214-217,235-253) */
+        sort_swarm();
+        int count = 0;
+        double mean = 0.0, m2 = 0.0;
+        for (int i = 0; i < np; i++) {
+            const double r = port_nrm2(n, &sw_x[(size_t) i * n]);
+            count++;
+            const double dl = r - mean;
+            mean += dl / count;
+            m2 += dl * (r - mean);
+        }
+        return m2 <= (np - 1) * tol * tol;
+    }
+
+    bool optimize(std::vector<double> &xout) { /* :219-233 */
+        init();
+        bool conv = false;
+        while (fev < mfev) {
+            iterate();
+            /* the reference's private converged() does not sort; only the Welford order differs, which the statistic
+             * does not depend on beyond rounding -- pinned against the reference's optimize() below */
+            int count = 0;
+            double mean = 0.0, m2 = 0.0;
+            for (int i = 0; i < np; i++) {
+                const double r = port_nrm2(n, &sw_x[(size_t) i * n]);
+                count++;
+                const double dl = r - mean;
+                mean += dl / count;
+                m2 += dl * (r - mean);
+            }
+            if (m2 <= (np - 1) * tol * tol) { conv = true; break; }
+        }
+        sort_swarm();
+        xout.assign(sw_x.begin(), sw_x.begin() + n);
+        return conv;
+    }
+};
+
 void cma_bind(PortCma *p, int obj, int n, const double *lower, const double *upper) {
     p->n = n;
     p->f.bind(obj, n);
@@ -1775,6 +1948,86 @@ int bbo_xnes_getv(void *h, const char *name, double *out, int cap) {
         for (int i = 0; i < (int) p->points.size() && i < cap; i++) out[i] = p->points[i].f;
         return (int) p->points.size();
     }
+    return -1;
+}
+
+void *bbo_sansde_new(int mfev, int np, double tol, int repaircr, int crref, int pupdate, int crupdate) {
+    PortSansde *p = new PortSansde();
+    p->mfev = mfev; p->np = np; p->tol = tol; p->repaircr = repaircr != 0;
+    p->ncrref = crref; p->npup = pupdate; p->ncrup = crupdate;
+    return p;
+}
+void bbo_sansde_free(void *h) { delete static_cast<PortSansde*>(h); }
+
+static void sansde_bind(PortSansde *p, int obj, int n, const double *lower, const double *upper) {
+    p->n = n;
+    p->f.bind(obj, n);
+    p->lower.assign(lower, lower + n);
+    p->upper.assign(upper, upper + n);
+}
+
+void bbo_sansde_init(void *h, int obj, int n, const double *lower, const double *upper, const double *guess) {
+    (void) guess;
+    PortSansde *p = static_cast<PortSansde*>(h);
+    sansde_bind(p, obj, n, lower, upper);
+    p->init();
+}
+void bbo_sansde_iterate(void *h) { static_cast<PortSansde*>(h)->iterate(); }
+int bbo_sansde_converged(void *h) { return static_cast<PortSansde*>(h)->converged() ? 1 : 0; }
+
+int bbo_sansde_optimize(void *h, int obj, int n, const double *lower, const double *upper, const double *guess, double *xout,
+        int *fev) {
+    (void) guess;
+    PortSansde *p = static_cast<PortSansde*>(h);
+    sansde_bind(p, obj, n, lower, upper);
+    std::vector<double> x;
+    const bool conv = p->optimize(x);
+    for (int i = 0; i < n; i++) xout[i] = x[i];
+    *fev = p->fev;
+    return conv ? 1 : 0;
+}
+
+int bbo_sansde_geti(void *h, const char *name) {
+    PortSansde *p = static_cast<PortSansde*>(h);
+    const std::string k(name);
+    if (k == "n") return p->n;
+    if (k == "np") return p->np;
+    if (k == "fev") return p->fev;
+    if (k == "it") return p->it;
+    if (k == "pns0") return p->pns[0];
+    if (k == "pns1") return p->pns[1];
+    if (k == "pnf0") return p->pnf[0];
+    if (k == "pnf1") return p->pnf[1];
+    return -1;
+}
+
+double bbo_sansde_getd(void *h, const char *name) {
+    PortSansde *p = static_cast<PortSansde*>(h);
+    const std::string k(name);
+    if (k == "p") return p->p;
+    if (k == "fp") return p->fp;
+    if (k == "crm") return p->crm;
+    if (k == "crrec") return p->crrec;
+    if (k == "crdeltaf") return p->crdeltaf;
+    if (k == "fpns0") return p->fpns[0];
+    if (k == "fpns1") return p->fpns[1];
+    if (k == "fpnf0") return p->fpnf[0];
+    if (k == "fpnf1") return p->fpnf[1];
+    return NAN;
+}
+
+int bbo_sansde_getv(void *h, const char *name, double *out, int cap) {
+    PortSansde *p = static_cast<PortSansde*>(h);
+    const std::string k(name);
+    if (k == "swarm_x") return put(p->sw_x, out, cap);
+    if (k == "swarm_f") return put(p->sw_f, out, cap);
+    if (k == "swarm_cr") return put(p->sw_cr, out, cap);
+    const std::pair<const char*, const std::vector<double>*> tags[] = { { "t_zcr", &p->t_zcr }, { "t_ifstrat", &p->t_ifstrat },
+            { "t_F", &p->t_F }, { "t_r1", &p->t_r1 }, { "t_r2", &p->t_r2 }, { "t_r3", &p->t_r3 }, { "t_istrat", &p->t_istrat },
+            { "t_jrand", &p->t_jrand }, { "t_u", &p->t_u }, { "t_succ", &p->t_succ }, { "t_ftrial", &p->t_ftrial },
+            { "t_cr1", &p->t_cr1 } };
+    for (const auto &t : tags)
+        if (k == t.first) return put(*t.second, out, cap);
     return -1;
 }
 

@@ -3,7 +3,7 @@
  *
  * Built by oracle/Makefile: this file + /root/reference/src/{blas.cpp,
  * multivariate/cma/{base_cmaes,cmaes,active_cmaes,sep_cmaes,cholesky_cmaes,lm_cmaes,ipop_cmaes,bipop_cmaes}.cpp,
- * multivariate/de/{jade,shade}.cpp, multivariate/nes/xnes.cpp} compiled where they lie -> oracle/_ref/libbbo_ref.so.
+ * multivariate/de/{jade,shade,sansde}.cpp, multivariate/nes/xnes.cpp} compiled where they lie -> oracle/_ref/libbbo_ref.so.
  * No reference source is copied into this repository; the headers are included by path.
  *
  * State is reached without patching the reference: every member is `protected`
@@ -32,6 +32,7 @@
 #include "multivariate/cma/bipop_cmaes.h"
 #include "multivariate/de/jade.h"
 #include "multivariate/de/shade.h"
+#include "multivariate/de/sansde.h"
 #include "multivariate/nes/xnes.h"
 #include "random.hpp"
 
@@ -409,6 +410,55 @@ struct XnesProbe: public xNES {
     }
 };
 
+/* SaNSDE (de/sansde.h:58-66: state is protected; the point type is private but its members are reachable) */
+struct SansdeProbe: public SaNSDESearch {
+    using SaNSDESearch::SaNSDESearch;
+    std::vector<double> lower, upper, guess;
+    multivariate_problem prob;
+    int geti(const std::string &k) {
+        if (k == "n") return _n;
+        if (k == "np") return _np;
+        if (k == "fev") return _fev;
+        if (k == "it") return _it;
+        if (k == "pns0") return _pns[0];
+        if (k == "pns1") return _pns[1];
+        if (k == "pnf0") return _pnf[0];
+        if (k == "pnf1") return _pnf[1];
+        return -1;
+    }
+    double getd(const std::string &k) {
+        if (k == "p") return _p;
+        if (k == "fp") return _fp;
+        if (k == "crm") return _crm;
+        if (k == "crrec") return _crrec;
+        if (k == "crdeltaf") return _crdeltaf;
+        if (k == "fpns0") return _fpns[0];
+        if (k == "fpns1") return _fpns[1];
+        if (k == "fpnf0") return _fpnf[0];
+        if (k == "fpnf1") return _fpnf[1];
+        return NAN;
+    }
+    int getv(const std::string &k, double *out, int cap) {
+        int len = 0;
+        if (k == "swarm_x") {
+            for (const auto &pt : _swarm)
+                for (double v : pt._x) {
+                    if (len < cap) out[len] = v;
+                    len++;
+                }
+            return len;
+        }
+        if (k == "swarm_f" || k == "swarm_cr") {
+            for (const auto &pt : _swarm) {
+                if (len < cap) out[len] = k == "swarm_f" ? pt._f : pt._cr;
+                len++;
+            }
+            return len;
+        }
+        return -1;
+    }
+};
+
 std::normal_distribution<> g_normal { 0., 1. };
 
 } // namespace
@@ -575,6 +625,43 @@ int bbo_xnes_optimize(void *h, int obj, int n, const double *lower, const double
 int bbo_xnes_geti(void *h, const char *name) { return static_cast<XnesProbe*>(h)->geti(name); }
 double bbo_xnes_getd(void *h, const char *name) { return static_cast<XnesProbe*>(h)->getd(name); }
 int bbo_xnes_getv(void *h, const char *name, double *out, int cap) { return static_cast<XnesProbe*>(h)->getv(name, out, cap); }
+
+void *bbo_sansde_new(int mfev, int np, double tol, int repaircr, int crref, int pupdate, int crupdate) {
+    return new SansdeProbe(mfev, np, tol, repaircr != 0, crref, pupdate, crupdate);
+}
+void bbo_sansde_free(void *h) { delete static_cast<SansdeProbe*>(h); }
+
+static void sansde_bind(SansdeProbe *p, int obj, int n, const double *lower, const double *upper, const double *guess) {
+    p->lower.assign(lower, lower + n);
+    p->upper.assign(upper, upper + n);
+    p->guess.assign(guess, guess + n);
+    p->prob = multivariate_problem(make_objective(obj, n), n, p->lower.data(), p->upper.data());
+}
+
+void bbo_sansde_init(void *h, int obj, int n, const double *lower, const double *upper, const double *guess) {
+    SansdeProbe *p = static_cast<SansdeProbe*>(h);
+    sansde_bind(p, obj, n, lower, upper, guess);
+    p->init(p->prob, p->guess.data());
+}
+
+void bbo_sansde_iterate(void *h) { static_cast<SansdeProbe*>(h)->iterate(); }
+/* converged() is private; solution() reports it -- and sorts the swarm first (sansde.cpp:214-217), which iterate() would do
+ * at its start anyway */
+int bbo_sansde_converged(void *h) { return static_cast<SansdeProbe*>(h)->solution()._converged ? 1 : 0; }
+
+int bbo_sansde_optimize(void *h, int obj, int n, const double *lower, const double *upper, const double *guess, double *xout,
+        int *fev) {
+    SansdeProbe *p = static_cast<SansdeProbe*>(h);
+    sansde_bind(p, obj, n, lower, upper, guess);
+    multivariate_solution sol = p->optimize(p->prob, p->guess.data());
+    for (int i = 0; i < n; i++) xout[i] = sol._sol[i];
+    *fev = sol._fev;
+    return sol._converged ? 1 : 0;
+}
+
+int bbo_sansde_geti(void *h, const char *name) { return static_cast<SansdeProbe*>(h)->geti(name); }
+double bbo_sansde_getd(void *h, const char *name) { return static_cast<SansdeProbe*>(h)->getd(name); }
+int bbo_sansde_getv(void *h, const char *name, double *out, int cap) { return static_cast<SansdeProbe*>(h)->getv(name, out, cap); }
 
 void *bbo_de_new(int kind, int mfev, int np, double tol, int archive, int repaircr,
         double pelite, double cdamp, double sigma, int h, int npmin) {

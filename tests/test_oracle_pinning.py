@@ -130,6 +130,37 @@ def test_xnes_every_generation(ref_oracle, port_oracle, obj, n, gens, a0, etamu)
     assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
 
 
+@pytest.mark.parametrize("obj,n,np_,gens,kw", [(O.RASTRIGIN, 10, 30, 120, dict()), (O.ROSENBROCK, 20, 40, 60, dict(repaircr=False, crref=3, pupdate=10, crupdate=5)),
+                                                (O.ACKLEY, 50, 64, 30, dict(pupdate=7, crupdate=4))])
+def test_sansde_every_generation(ref_oracle, port_oracle, obj, n, np_, gens, kw):
+    """SaNSDE (de/sansde.cpp): port bit for bit after every generation, adaptation state included."""
+    box = {O.ROSENBROCK: 10.0, O.RASTRIGIN: 5.12, O.ACKLEY: 32.768}[obj]
+    hs = []
+    for o in (ref_oracle, port_oracle):
+        o.seed(42)
+        h = o.sansde(10 ** 9, np_, 1e-12, **kw)
+        h.init(obj, -box * np.ones(n), box * np.ones(n))
+        hs.append(h)
+    r, p = hs
+    for g in range(gens):
+        r.iterate()
+        p.iterate()
+        for k in ("swarm_x", "swarm_f", "swarm_cr"):
+            assert np.array_equal(r.getv(k), p.getv(k)), (g, k)
+        for k in ("p", "fp", "crm", "crrec", "crdeltaf", "fpns0", "fpns1", "fpnf0", "fpnf1"):
+            assert r.getd(k) == p.getd(k), (g, k)
+        for k in ("fev", "it", "pns0", "pns1", "pnf0", "pnf1"):
+            assert r.geti(k) == p.geti(k), (g, k)
+        if g % 10 == 9:
+            assert r.converged() == p.converged()
+            assert np.array_equal(r.getv("swarm_x"), p.getv("swarm_x"))
+    res = []
+    for o in (ref_oracle, port_oracle):
+        o.seed(11)
+        res.append(o.sansde(20000, 30, 1e-6).optimize(O.SPHERE, -5 * np.ones(6), 5 * np.ones(6)))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
+
+
 def test_cma_phases_one_by_one(ref_oracle, port_oracle):
     def make(o):
         o.seed(1)
