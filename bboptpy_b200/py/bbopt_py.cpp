@@ -19,6 +19,7 @@
 
 #include "cma.h"
 #include "de.h"
+#include "sansde.h"
 #include "xnes.h"
 #include "restart.h"
 #include "batch.h"
@@ -265,6 +266,61 @@ PYBIND11_MODULE(_bboptpy, m) {
         .def_property_readonly("gsigma", &xNES::gsigma)
         .def_property_readonly("n_evals", &xNES::evaluations)
         .def_property_readonly("np", &xNES::population);
+
+    // py/multivariate_py.cpp:173-178
+    py::class_<SaNSDESearch, MultivariateOptimizer>(m, "SANSDE")
+        .def(py::init<int, int, double, bool, int, int, int>(), "mfev"_a, "np"_a, "tol"_a, "repaircr"_a = true, "crref"_a = 5,
+             "pupdate"_a = 50, "crupdate"_a = 25)
+        .def("swarm", [](SaNSDESearch &self) {
+            std::vector<double> x = self.swarm();
+            const int np = self.population();
+            py::array_t<double> a({ (py::ssize_t) np, (py::ssize_t) (np ? x.size() / np : 0) });
+            std::copy(x.begin(), x.end(), a.mutable_data());
+            return a;
+        })
+        .def("fitness", [](SaNSDESearch &self) { return as_array(self.fitness()); })
+        .def("crossover_rates", [](SaNSDESearch &self) { return as_array(self.crossoverRates()); })
+        .def("set_stream_key", &SaNSDESearch::setStreamKey, "key"_a)
+        .def("set_initial_population", [](SaNSDESearch &self, py::array_t<double, py::array::c_style | py::array::forcecast> x) {
+            self.setInitialPopulation(std::vector<double>(x.data(), x.data() + x.size()));
+        }, "x"_a)
+        .def("set_draw_replay", [](SaNSDESearch &self, py::object fn) {
+            if (fn.is_none()) { self.setDrawReplay(nullptr); return; }
+            self.setDrawReplay([fn](int gen, sansde_generation_draws &d) {
+                py::object r = fn(gen);
+                if (r.is_none()) return false;
+                py::dict t = r.cast<py::dict>();
+                auto dv = [&](const char *k, std::vector<double> &out) {
+                    if (!t.contains(k)) return;
+                    auto a = t[k].cast<py::array_t<double, py::array::c_style | py::array::forcecast>>();
+                    out.assign(a.data(), a.data() + a.size());
+                };
+                auto iv = [&](const char *k, std::vector<int32_t> &out) {
+                    if (!t.contains(k)) return;
+                    auto a = t[k].cast<py::array_t<double, py::array::c_style | py::array::forcecast>>();
+                    out.resize(a.size());
+                    for (py::ssize_t i = 0; i < a.size(); i++) out[i] = (int32_t) a.data()[i];
+                };
+                dv("zcr", d.zcr); dv("F", d.F); dv("u", d.u);
+                iv("ifstrat", d.ifstrat); iv("r1", d.r1); iv("r2", d.r2); iv("r3", d.r3); iv("istrat", d.istrat); iv("jrand", d.jrand);
+                return true;
+            });
+        }, "fn"_a)
+        .def("converged", &SaNSDESearch::isConverged)
+        .def("sums", [](SaNSDESearch &self) {
+            const bbgpu_sde_accum &a = self.sums();
+            py::dict d;
+            d["pns0"] = a.pns[0]; d["pns1"] = a.pns[1]; d["pnf0"] = a.pnf[0]; d["pnf1"] = a.pnf[1];
+            d["crrec"] = a.crrec; d["crdeltaf"] = a.crdeltaf; d["fpns0"] = a.fpns[0]; d["fpns1"] = a.fpns[1];
+            d["fpnf0"] = a.fpnf[0]; d["fpnf1"] = a.fpnf[1]; d["nsucc"] = a.nsucc;
+            return d;
+        })
+        .def_property_readonly("p", &SaNSDESearch::p)
+        .def_property_readonly("fp", &SaNSDESearch::fp)
+        .def_property_readonly("crm", &SaNSDESearch::crm)
+        .def_property_readonly("rounds", &SaNSDESearch::rounds)
+        .def_property_readonly("n_evals", &SaNSDESearch::evaluations)
+        .def_property_readonly("popsize", &SaNSDESearch::population);
 
     py::class_<DeSearchBase, MultivariateOptimizer>(m, "BaseDE")
         .def("swarm", [](DeSearchBase &self) {

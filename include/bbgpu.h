@@ -379,6 +379,42 @@ int bbgpu_de_get_trace(bbgpu_de *h, int32_t *h_succ, double *h_ftrial, double *h
  * [32 + 4r + k], r < 8: round r after scan / signatures / builds / grid.sync.  64 entries. */
 int bbgpu_de_phase_times(bbgpu_de *h, uint64_t *out64);
 
+/* ---- SaNSDE engine (de/sansde.cpp:94-212): self-adaptive DE with neighbourhood search.  Same in-place sequential semantics
+ * as JADE, resolved by parallel fixed-point rounds; the draws of a candidate do not depend on the history of the
+ * generation, so they are generated (Philox) or replayed up front. */
+typedef struct bbgpu_sde bbgpu_sde;
+/* tagged draws of one generation, host arrays of length np unless noted (DRAW REPLAY; the oracle's recorder tags them) */
+typedef struct bbgpu_sde_draws {
+    const double *zcr;      /* N(0,1) behind a refreshed CR (de/sansde.cpp:108-111); may be NULL when CR is not refreshed */
+    const int32_t *ifstrat; /* which F distribution: 0 normal, 1 Cauchy (:114-119) */
+    const double *F;        /* the accepted F (:120-128) */
+    const int32_t *r1, *r2, *r3; /* :131-142 */
+    const int32_t *istrat;  /* mutation strategy: 0 rand/1, 1 current-to-best/2 (:145-150) */
+    const int32_t *jrand;   /* :269 */
+    const double *u;        /* np*n crossover uniforms (:271-272; drawn for every coordinate) */
+} bbgpu_sde_draws;
+/* the adaptation sums the candidate loop accumulates (:160-176), carried by the host between generations */
+typedef struct bbgpu_sde_accum {
+    int32_t pns[2], pnf[2];
+    double crrec, crdeltaf, fpns[2], fpnf[2];
+    int32_t nsucc, pad; /* out: trials accepted in this generation */
+} bbgpu_sde_accum;
+int bbgpu_sde_create(bbgpu_ctx *ctx, int n, int np, int repaircr, uint64_t seed, const double *h_lower, const double *h_upper,
+                     bbgpu_sde **out);
+int bbgpu_sde_destroy(bbgpu_sde *h);
+/* init(): de/sansde.cpp:54-92.  h_x == NULL: uniform Philox points; else np*n replayed points.  Evaluates the swarm. */
+int bbgpu_sde_init(bbgpu_sde *h, bbgpu_objective *obj, const double *h_x);
+/* iterate() up to the periodic adaptation (:94-177): sort, CR refresh (refresh_cr = it % crref == 0, around crm), F / parents /
+ * strategy draws (fp, p), mutation + crossover + bound control, greedy selection in place, the adaptation sums (acc in/out).
+ * draws == NULL -> Philox.  *rounds_out (may be NULL): dependency-resolution rounds the generation needed. */
+int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, double crm, double fp, double p,
+                         const bbgpu_sde_draws *draws, bbgpu_sde_accum *acc, int *rounds_out);
+int bbgpu_sde_sort(bbgpu_sde *h); /* std::sort(_swarm) as solution() does (:214-217) */
+int bbgpu_sde_get_swarm(bbgpu_sde *h, double *h_x, double *h_f, double *h_cr);
+int bbgpu_sde_get_trace(bbgpu_sde *h, int32_t *h_succ, double *h_ftrial, double *h_cr1);
+int bbgpu_sde_radius(bbgpu_sde *h, double *h_mean, double *h_m2); /* converged(), :235-253 */
+int bbgpu_sde_evaluations(bbgpu_sde *h);
+
 /* ---- batched small-n CMA-ES engine (BASELINE config 5: thousands of independent
  * IPOP/BIPOP runs at n <= 64).  One CTA per run; sample -> evaluate -> rank -> update -> updateSigma ->
  * lazy eigendecomposition (the reference's tred2/tql2, inside the CTA) -> updateHistory -> converged()

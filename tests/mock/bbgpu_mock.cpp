@@ -155,3 +155,15 @@ int bbgpu_eig_small_host(bbgpu_ctx *, int, int, const double *, double *, double
 int bbgpu_stedc_host(bbgpu_ctx *, int, const double *, const double *, double *, double *, float *) { return 0; }
 int bbgpu_sytrd_host(bbgpu_ctx *, int, const double *, double *, double *, double *, double *, int, float *) { return 0; }
 }
+
+/* SaNSDE entry points (link-time only: the host test does not drive this class) */
+struct bbgpu_sde { int n, np; };
+int bbgpu_sde_create(bbgpu_ctx *, int n, int np, int, uint64_t, const double *, const double *, bbgpu_sde **out) { *out = new bbgpu_sde { n, np }; return 0; }
+int bbgpu_sde_destroy(bbgpu_sde *h) { delete h; return 0; }
+int bbgpu_sde_init(bbgpu_sde *, bbgpu_objective *, const double *) { return 0; }
+int bbgpu_sde_generation(bbgpu_sde *, bbgpu_objective *, int, double, double, double, const bbgpu_sde_draws *, bbgpu_sde_accum *, int *r) { if (r) *r = 1; return 0; }
+int bbgpu_sde_sort(bbgpu_sde *) { return 0; }
+int bbgpu_sde_get_swarm(bbgpu_sde *, double *, double *, double *) { return 0; }
+int bbgpu_sde_get_trace(bbgpu_sde *, int32_t *, double *, double *) { return 0; }
+int bbgpu_sde_radius(bbgpu_sde *, double *m, double *m2) { *m = 1; *m2 = 1; return 0; }
+int bbgpu_sde_evaluations(bbgpu_sde *) { return 0; }

@@ -1,0 +1,111 @@
+"""SaNSDE (de/sansde.cpp) on the device against the oracle: tagged-draw replay (tier T3).
+
+The reference updates the swarm in place inside the candidate loop; the engine resolves a generation by parallel fixed-point
+rounds (csrc/sansde.cu).  With the oracle's tagged draws replayed, the arithmetic of a trial is the reference's operation
+for operation and the registry objectives are bit-exact, so everything is compared BIT FOR BIT: the swarm in the reference's
+order, fitness, the members' CR, the success flags, and the adaptation state (p, fp, crm and the sums behind them, which one
+thread accumulates in candidate order)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import bboptpy_b200
+    return bboptpy_b200
+
+
+def tags(h):
+    t = {k: h.getv("t_" + k) for k in ("zcr", "ifstrat", "F", "r1", "r2", "r3", "istrat", "jrand", "u")}
+    if np.isnan(t["zcr"]).all():
+        del t["zcr"]
+    return t
+
+
+@pytest.mark.parametrize("obj,n,np_,gens,kw", [
+    (O.RASTRIGIN, 10, 30, 150, dict()),
+    (O.ROSENBROCK, 20, 40, 80, dict(repaircr=False, crref=3, pupdate=10, crupdate=5)),
+    (O.ACKLEY, 50, 64, 40, dict(pupdate=7, crupdate=4)),
+    (O.RASTRIGIN, 1000, 1000, 4, dict()),   # BASELINE config 2's shape
+])
+def test_replay_every_generation(pkg, port_oracle, obj, n, np_, gens, kw):
+    P = port_oracle
+    box = {O.ROSENBROCK: 10.0, O.RASTRIGIN: 5.12, O.ACKLEY: 32.768}[obj]
+    lo, hi = -box * np.ones(n), box * np.ones(n)
+    P.seed(7)
+    h = P.sansde(10 ** 9, np_, 1e-12, **kw)
+    h.init(obj, lo, hi)
+    alg = pkg.SANSDE(mfev=10 ** 9, np=np_, tol=1e-12, **kw)
+    alg.set_initial_population(h.mat("swarm_x"))
+    alg.set_draw_replay(lambda gen: tags(h))
+    alg.initialize(pkg.Objective.builtin(obj), lo, hi, lo)
+    assert np.array_equal(alg.fitness(), h.getv("swarm_f"))
+    deepest = 0
+    for g in range(gens):
+        h.iterate()
+        alg.iterate()
+        deepest = max(deepest, alg.rounds)
+        assert np.array_equal(alg.fitness(), h.getv("swarm_f")), f"gen {g} fitness"
+        assert np.array_equal(alg.swarm(), h.mat("swarm_x")), f"gen {g} swarm"
+        assert np.array_equal(alg.crossover_rates(), h.getv("swarm_cr")), f"gen {g} CR"
+        s = alg.sums()
+        assert s["nsucc"] == int(h.getv("t_succ").sum())
+        for k in ("pns0", "pns1", "pnf0", "pnf1"):
+            assert s[k] == h.geti(k), (g, k)
+        for k in ("crrec", "crdeltaf", "fpns0", "fpns1", "fpnf0", "fpnf1"):
+            assert s[k] == h.getd(k), (g, k)
+        assert (alg.p, alg.fp, alg.crm) == (h.getd("p"), h.getd("fp"), h.getd("crm")), f"gen {g} adaptation"
+        assert alg.n_evals == h.geti("fev")
+    assert deepest >= 2, "the in-place dependencies were exercised"
+
+
+def test_optimize_to_the_reference_stop(pkg, port_oracle):
+    P = port_oracle
+    n, np_ = 6, 30
+    lo, hi = -5 * np.ones(n), 5 * np.ones(n)
+    P.seed(11)
+    h = P.sansde(20000, np_, 1e-6)
+    h.init(O.SPHERE, lo, hi)
+    alg = pkg.SANSDE(mfev=20000, np=np_, tol=1e-6)
+    alg.set_initial_population(h.mat("swarm_x"))
+    alg.set_draw_replay(lambda gen: tags(h))
+    alg.initialize(pkg.Sphere, lo, hi, lo)
+    done = False
+    while alg.n_evals < 20000:
+        h.iterate()
+        alg.iterate()
+        co, cg = h.converged(), alg.converged()   # the oracle's goes through solution(): it sorts first
+        assert co == cg
+        if cg:
+            done = True
+            break
+    assert done and alg.n_evals == h.geti("fev")
+    assert_close(alg.solution().x, h.mat("swarm_x")[0], rel=1e-12, what="best member")
+
+
+def test_free_running(pkg):
+    n = 10
+    pkg.seed(11)
+    alg = pkg.SANSDE(mfev=80000, np=50, tol=1e-7)
+    sol = alg.optimize(pkg.Sphere, -5 * np.ones(n), 5 * np.ones(n), np.zeros(n))
+    assert float((sol.x ** 2).sum()) < 1e-6 and sol.n_evals <= 80000 + 50
+    a = alg.optimize(pkg.Rastrigin, -5 * np.ones(n), 5 * np.ones(n), np.zeros(n)).x
+    b = alg.optimize(pkg.Rastrigin, -5 * np.ones(n), 5 * np.ones(n), np.zeros(n)).x
+    assert not np.array_equal(a, b), "a second optimize() is a new run, as with the reference's global engine"
+    fixed = pkg.SANSDE(mfev=3000, np=20, tol=0.0)
+    fixed.set_stream_key(99)
+    c = fixed.optimize(pkg.Rastrigin, -5 * np.ones(n), 5 * np.ones(n), np.zeros(n)).x
+    d = fixed.optimize(pkg.Rastrigin, -5 * np.ones(n), 5 * np.ones(n), np.zeros(n)).x
+    assert np.array_equal(c, d)
+
+
+def test_python_callable_objective(pkg):
+    n = 5
+    alg = pkg.SANSDE(mfev=6000, np=20, tol=0.0)
+    sol = alg.optimize(lambda x: float(np.sum((x - 1.0) ** 2)), -5 * np.ones(n), 5 * np.ones(n), np.zeros(n))
+    assert float(np.sum((sol.x - 1.0) ** 2)) < 1e-2
