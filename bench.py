@@ -308,7 +308,8 @@ def run_reference(args):
     t_eig = run.time_eig()
     t_gen = timed_s / len(rows)
     value = 1.0 / t_gen
-    de = {"jade_evals_per_s": cpu_de_sample(o, 0), "shade_evals_per_s": cpu_de_sample(o, 1), "unit": "candidate-evals/s",
+    de = {"jade_evals_per_s": cpu_de_sample(o, 0), "shade_evals_per_s": cpu_de_sample(o, 1), "sansde_evals_per_s": cpu_sansde_sample(o),
+          "unit": "candidate-evals/s",
           "sample": "3 generations each, n=1000 np=1000 Rastrigin, 1 thread"}
     sample = (f"{len(rows)} whole generations at n=1000, lambda=4096 through the reference's own phases (sample, evaluate+sort, "
               "update incl. sigma and the eigendecomposition, which fires every generation here), after "
@@ -495,6 +496,28 @@ def cpu_lm_sample(o, gens=40, seed=1):
     for _ in range(gens):
         h.iterate()
     return gens / (time.perf_counter() - t0)
+
+
+def bench_sansde_e2e(pkg, gens, seed):
+    """SaNSDE (de/sansde.cpp), n = 1000, np = 1000, Rastrigin through the Python API: candidate-evaluations/s (the reference's
+    count: one per candidate and generation)."""
+    lower, upper = -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N)
+    alg = pkg.SANSDE(mfev=DE_NP * (gens + 1), np=DE_NP, tol=0.0)
+    t0 = time.perf_counter()
+    sol = alg.optimize(pkg.Rastrigin, lower, upper, lower)
+    dt = time.perf_counter() - t0
+    return sol.n_evals / dt, alg.rounds
+
+
+def cpu_sansde_sample(o, gens=3, seed=1):
+    from oracle import oracle as O
+    o.seed(seed)
+    h = o.sansde(10 ** 9, DE_NP, 0.0)
+    h.init(O.RASTRIGIN, -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N))
+    t0 = time.perf_counter()
+    for _ in range(gens):
+        h.iterate()
+    return gens * DE_NP / (time.perf_counter() - t0)
 
 
 def bench_xnes_e2e(pkg, gens, seed):
@@ -777,6 +800,11 @@ def run_own(args):
     lm = {"e2e_gens_per_s": world * 1.0 / all_max(dist, local, 1.0 / bench_lm_e2e(pkg, 400, seed=1 + rank)),
           "workload": f"LmCMAES n={LM_N} lambda={LM_LAMBDA} memory=200 Ellipsoid, 400 generations through the Python API "
                       "(cma/lm_cmaes.cpp; the memory fills during the run)"}
+    bench_sansde_e2e(pkg, 5, seed=1 + rank)
+    sd_rate, sd_rounds = bench_sansde_e2e(pkg, 200, seed=1 + rank)
+    de["sansde"] = {"e2e_evals_per_s": world * DE_NP * 1.0 / all_max(dist, local, DE_NP / sd_rate), "rounds_last": sd_rounds,
+                    "workload": "SANSDE n=1000 np=1000 Rastrigin, 200 generations through the Python API (de/sansde.cpp; one host "
+                                "round trip per dependency round)"}
     bench_xnes_e2e(pkg, 3, seed=1 + rank)
     xn = {"e2e_gens_per_s": world * 1.0 / all_max(dist, local, 1.0 / bench_xnes_e2e(pkg, e2e_gens, seed=1 + rank)),
           "workload": "xNES n=1000 np=24 Rosenbrock through the Python API (nes/xnes.cpp; one eigendecomposition + two n^3 GEMMs per generation)"}
@@ -908,6 +936,7 @@ def run_own(args):
                                 "cholesky_gens_per_s": cpu_chol_sample(o),
                                 "lm_cma_gens_per_s": cpu_lm_sample(o),
                                 "xnes_gens_per_s": cpu_xnes_sample(o),
+                                "de_sansde_evals_per_s": cpu_sansde_sample(o),
                                 "bipop_batch": cpu_bipop_sample(o)}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
