@@ -117,6 +117,23 @@ int bbo_sansde_geti(void *h, const char *name);
 double bbo_sansde_getd(void *h, const char *name);
 int bbo_sansde_getv(void *h, const char *name, double *out, int cap);
 
+/* ---- SSDE (de/ssde.cpp): spherical search (+ optionally a DE stage for the failures), success-history memory, linear
+ * population reduction.  geti: "n", "np", "fev", "convcount", "k", "kcr";  getv: "swarm_x", "swarm_f", "L1", "L2", "LCR", "iwork"
+ * and -- port only -- the tagged draws of the generation just run: "t_iwork" (n, the permutation behind A), per candidate
+ * "t_iL", "t_zrank", "t_p", "t_q", "t_r", "t_pbest", "t_cauchy" (the accepted variate), "t_ub" (np*n), outcome "t_succ"
+ * (0 fail, 1 first stage, 2 DE stage), "t_f" (fitness of the accepted or last trial); with usede also "t_zcr", "t_j0",
+ * "t_ucr" (np*n), "t_redraw" (np*n, NaN where no coordinate was redrawn) */
+void *bbo_ssde_new(int mfev, int npinit, double tol, int patience, int npmin, double ptop, int h, int usede, int repaircr);
+void bbo_ssde_free(void *h);
+void bbo_ssde_init(void *h, int obj, int n, const double *lower, const double *upper, const double *guess);
+void bbo_ssde_iterate(void *h);
+int bbo_ssde_converged(void *h);
+int bbo_ssde_optimize(void *h, int obj, int n, const double *lower, const double *upper, const double *guess,
+                      double *xout, int *fev);
+int bbo_ssde_geti(void *h, const char *name);
+double bbo_ssde_getd(void *h, const char *name);
+int bbo_ssde_getv(void *h, const char *name, double *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,21 @@ def _bind(lib):
     lib.bbo_sansde_getd.restype = d
     lib.bbo_sansde_getv.argtypes = [vp, cp, _c_dp, i]
     lib.bbo_sansde_getv.restype = i
+    lib.bbo_ssde_new.restype = vp
+    lib.bbo_ssde_new.argtypes = [i, i, d, i, i, d, i, i, i]
+    lib.bbo_ssde_free.argtypes = [vp]
+    lib.bbo_ssde_init.argtypes = [vp, i, i, _c_dp, _c_dp, _c_dp]
+    lib.bbo_ssde_iterate.argtypes = [vp]
+    lib.bbo_ssde_converged.argtypes = [vp]
+    lib.bbo_ssde_converged.restype = i
+    lib.bbo_ssde_optimize.argtypes = [vp, i, i, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.POINTER(i)]
+    lib.bbo_ssde_optimize.restype = i
+    lib.bbo_ssde_geti.argtypes = [vp, cp]
+    lib.bbo_ssde_geti.restype = i
+    lib.bbo_ssde_getd.argtypes = [vp, cp]
+    lib.bbo_ssde_getd.restype = d
+    lib.bbo_ssde_getv.argtypes = [vp, cp, _c_dp, i]
+    lib.bbo_ssde_getv.restype = i
     lib.bbo_de_new.restype = vp
     lib.bbo_de_new.argtypes = [i, i, i, d, i, i, d, d, d, i, i]
     lib.bbo_de_free.argtypes = [vp]
@@ -161,6 +176,9 @@ class Oracle:
 
     def sansde(self, mfev, np_, tol, repaircr=True, crref=5, pupdate=50, crupdate=25):
         return OracleGeneric(self, "sansde", self.lib.bbo_sansde_new(mfev, np_, tol, int(repaircr), crref, pupdate, crupdate))
+
+    def ssde(self, mfev, npinit, tol, patience=1000, npmin=4, ptop=0.11, h=100, usede=False, repaircr=True):
+        return OracleGeneric(self, "ssde", self.lib.bbo_ssde_new(mfev, npinit, tol, patience, npmin, ptop, h, int(usede), int(repaircr)))
 
     def xnes(self, mfev, tol, a0=1.0, etamu=1.0):
         return OracleXnes(self, mfev, tol, a0, etamu)

@@ -1272,6 +1272,296 @@ struct PortSansde {
     }
 };
 
+/* ---- de/ssde.cpp (Zhao et al. 2022: spherical search with DE) */
+struct PortSsde {
+    int mfev = 0, npinit = 0, patience = 1000, npmin = 4, H = 100;
+    double tol = 0, ptop = 0.11;
+    bool usede = true, repaircr = true;
+    Objective f;
+    int n = 0, np = 0, fev = 0, convcount = 0, k = 1, kCR = 1;
+    std::vector<int> iwork, partner; /* partner[d]: the index paired with d by randA(), -1 when unpaired */
+    std::vector<double> lower, upper, b, z, y, work, L1, L2, LCR, SR, SC, SCR, w, wCR, sw_x, sw_f;
+    double sinv = 0, cosv = 0;
+    BboNormal Z;
+    std::vector<double> t_iwork, t_iL, t_zrank, t_p, t_q, t_r, t_pbest, t_cauchy, t_ub, t_succ, t_f, t_zcr, t_j0, t_ucr, t_redraw;
+
+    double cauchy() { return std::tan(M_PI * (eng().uniform_real(0.0, 1.0) - 0.5)); } /* :459-461 */
+
+    void sort_swarm() { /* std::sort(_swarm, point::compare_fitness) */
+        struct Rec { double f; int pos; };
+        const int cnt = (int) sw_f.size();
+        std::vector<Rec> rec(cnt);
+        for (int i = 0; i < cnt; i++) rec[i] = Rec { sw_f[i], i };
+        std::sort(rec.begin(), rec.end(), [](const Rec &a, const Rec &c) { return a.f < c.f; });
+        std::vector<double> nx((size_t) cnt * n), nf(cnt);
+        for (int i = 0; i < cnt; i++) {
+            nf[i] = rec[i].f;
+            std::copy(sw_x.begin() + (size_t) rec[i].pos * n, sw_x.begin() + (size_t) (rec[i].pos + 1) * n, nx.begin() + (size_t) i * n);
+        }
+        sw_x.swap(nx);
+        sw_f.swap(nf);
+    }
+
+    void init() { /* :58-131 */
+        fev = 0;
+        convcount = 0;
+        b.assign(n, 0.0); z.assign(n, 0.0); y.assign(n, 0.0); work.assign(n, 0.0);
+        iwork.resize(n);
+        for (int i = 0; i < n; i++) iwork[i] = i;
+        partner.assign(n, -1);
+        np = npinit;
+        sw_x.assign((size_t) np * n, 0.0);
+        sw_f.assign(np, 0.0);
+        for (int i = 0; i < np; i++) {
+            double *x = &sw_x[(size_t) i * n];
+            for (int j = 0; j < n; j++) x[j] = eng().uniform_real(lower[j], upper[j]);
+            sw_f[i] = f(x);
+            ++fev;
+        }
+        if (usede) { /* opposition-based points */
+            sw_x.resize((size_t) 2 * np * n);
+            sw_f.resize((size_t) 2 * np);
+            for (int i = 0; i < np; i++) {
+                double *x = &sw_x[(size_t) (np + i) * n];
+                for (int j = 0; j < n; j++) x[j] = lower[j] + upper[j] - sw_x[(size_t) i * n + j];
+                sw_f[np + i] = f(x);
+                ++fev;
+            }
+        }
+        sort_swarm();
+        sw_x.resize((size_t) npinit * n);
+        sw_f.resize(npinit);
+        L1.assign(H, 0.5); L2.assign(H, 0.5); LCR.assign(H, 0.5);
+        SR.clear(); SC.clear(); SCR.clear(); w.clear(); wCR.clear();
+        k = 1;
+        kCR = 1;
+    }
+
+    /* std::shuffle of libstdc++ 13 (bits/stl_algo.h:3742-3805) on the global engine: two swap positions per draw */
+    void shuffle_iwork() {
+        const uint64_t urange = (uint64_t) n;
+        if (n == 0) return;
+        if (0xffffffffull / urange >= urange) {
+            int i = 1;
+            if ((urange % 2) == 0) {
+                const int pos = eng().uniform_int(0, 1);
+                std::swap(iwork[i++], iwork[pos]);
+            }
+            while (i != n) {
+                const uint64_t swap_range = (uint64_t) i + 1;
+                const uint64_t b1 = swap_range + 1;
+                const uint64_t x = (uint64_t) (uint32_t) eng().uniform_int(0, (int) (swap_range * b1 - 1));
+                std::swap(iwork[i++], iwork[x / b1]);
+                std::swap(iwork[i++], iwork[x % b1]);
+            }
+            return;
+        }
+        for (int i = 1; i < n; i++) std::swap(iwork[i], iwork[eng().uniform_int(0, i)]);
+    }
+
+    void rand_a() { /* :394-433: identity, then every consecutive pair of the shuffled indices becomes a rotation block */
+        shuffle_iwork();
+        partner.assign(n, -1);
+        sinv = std::sin(1e-12);
+        cosv = std::cos(1e-12);
+        for (int ii = 1; ii <= n / 2; ii++) {
+            const int i = 2 * (ii - 1);
+            partner[iwork[i]] = iwork[i + 1];
+            partner[iwork[i + 1]] = iwork[i];
+        }
+    }
+    /* A[d][k] for the two structurally non-zero columns of row d */
+    double a_entry(int d, int kk) const {
+        if (partner[d] < 0) return d == kk ? 1.0 : 0.0;
+        if (d == kk) return sinv;
+        /* A[first][second] = cos, A[second][first] = -cos, first = the one earlier in iwork */
+        return first_of_pair[d] ? cosv : -cosv;
+    }
+    std::vector<char> first_of_pair;
+
+    void trial_point(int i, double ci) { /* :435-457, the dense loops restricted to the non-zero entries in column order */
+        for (int d = 0; d < n; d++) {
+            double s = 0.0;
+            const int q = partner[d];
+            if (q < 0) s = s + 1.0 * z[d];
+            else {
+                const int k1 = std::min(d, q), k2 = std::max(d, q);
+                s = s + a_entry(d, k1) * z[k1];
+                s = s + a_entry(d, k2) * z[k2];
+            }
+            work[d] = s * b[d];
+        }
+        const double *x = &sw_x[(size_t) i * n];
+        for (int d = 0; d < n; d++) {
+            double v = x[d];
+            const int q = partner[d];
+            if (q < 0) v = v + ci * 1.0 * work[d];
+            else {
+                const int k1 = std::min(d, q), k2 = std::max(d, q);
+                v = v + ci * a_entry(k1, d) * work[k1];
+                v = v + ci * a_entry(k2, d) * work[k2];
+            }
+            y[d] = std::max(lower[d], std::min(upper[d], v));
+        }
+    }
+
+    void iterate() { /* :134-339 */
+        const double oldbestf = sw_f[0];
+        rand_a();
+        first_of_pair.assign(n, 0);
+        for (int ii = 1; ii <= n / 2; ii++) first_of_pair[iwork[2 * (ii - 1)]] = 1;
+        t_iwork.assign(iwork.begin(), iwork.end());
+        SR.clear(); SC.clear(); SCR.clear(); w.clear(); wCR.clear();
+        for (auto *v : { &t_iL, &t_zrank, &t_p, &t_q, &t_r, &t_pbest, &t_cauchy, &t_succ, &t_f, &t_zcr, &t_j0 }) v->assign(np, 0.0);
+        t_ub.assign((size_t) np * n, 0.0);
+        t_ucr.assign(usede ? (size_t) np * n : 0, NAN);
+        t_redraw.assign(usede ? (size_t) np * n : 0, NAN);
+        for (int i = 0; i < np; i++) {
+            const int iL = eng().uniform_int(0, H - 1);
+            const double zr = Z.draw(eng());
+            double prank = zr * 0.1 + L1[iL];
+            prank = std::max(0.0, std::min(1.0, prank));
+            for (int r = 0; r < n; r++) {
+                const double u = eng().uniform_real(0.0, 1.0);
+                t_ub[(size_t) i * n + r] = u;
+                b[r] = u < prank ? 1.0 : 0.0;
+            }
+            int pi = i, qi = i, ri = i;
+            while (pi == i) pi = eng().uniform_int(0, np - 1);
+            while (qi == i || qi == pi) qi = eng().uniform_int(0, np - 1);
+            while (ri == i || ri == pi || ri == qi) ri = eng().uniform_int(0, np - 1);
+            const int itop = std::max(1, (int) (ptop * np));
+            const int pbest = eng().uniform_int(0, itop);
+            const double R = (1.0 * fev) / mfev;
+            const double *xp = &sw_x[(size_t) pi * n], *xq = &sw_x[(size_t) qi * n], *xr = &sw_x[(size_t) ri * n],
+                    *xi = &sw_x[(size_t) i * n], *xb = &sw_x[(size_t) pbest * n], *x0 = &sw_x[0];
+            if (usede) {
+                const double *lead = R < 0.333 ? xp : (R < 0.666 ? xb : x0);
+                for (int d = 0; d < n; d++) z[d] = lead[d] + xq[d] - xr[d] - xi[d] + R * (xb[d] - xq[d]);
+            } else {
+                const double *lead = i < 0.5 * np ? xp : xb;
+                for (int d = 0; d < n; d++) z[d] = lead[d] + xq[d] - xr[d] - xi[d];
+            }
+            double cv = cauchy();
+            double ci = cv * 0.1 + L2[iL];
+            while (ci <= 0.0) {
+                cv = cauchy();
+                ci = cv * 0.1 + L2[iL];
+            }
+            ci = std::min(1.0, ci);
+            trial_point(i, ci);
+            const double fy = f(y.data());
+            ++fev;
+            t_iL[i] = iL; t_zrank[i] = zr; t_p[i] = pi; t_q[i] = qi; t_r[i] = ri; t_pbest[i] = pbest; t_cauchy[i] = cv; t_f[i] = fy;
+            if (fy <= sw_f[i]) {
+                t_succ[i] = 1.0;
+                if (fy < sw_f[i]) {
+                    SR.push_back(prank);
+                    SC.push_back(ci);
+                    w.push_back(sw_f[i] - fy);
+                }
+                std::copy(y.begin(), y.end(), sw_x.begin() + (size_t) i * n);
+                sw_f[i] = fy;
+            } else if (usede) {
+                const double zc = Z.draw(eng());
+                const double CRi = std::max(0.0, std::min(1.0, zc * 0.1 + LCR[iL]));
+                double cr1 = 0.0;
+                const int j0 = eng().uniform_int(0, n - 1);
+                t_zcr[i] = zc; t_j0[i] = j0;
+                for (int d = 0; d < n; d++) {
+                    bool take = d == j0;
+                    if (!take) {
+                        const double u = eng().uniform_real(0.0, 1.0);
+                        t_ucr[(size_t) i * n + d] = u;
+                        take = u <= CRi;
+                    }
+                    if (take) {
+                        work[d] = xp[d] + R * (x0[d] - xq[d]) + R * (x0[d] - xr[d]);
+                        if (work[d] < lower[d] || work[d] > upper[d]) {
+                            work[d] = eng().uniform_real(lower[d], upper[d]);
+                            t_redraw[(size_t) i * n + d] = work[d];
+                        }
+                        cr1 += 1.0;
+                    } else {
+                        work[d] = xi[d];
+                    }
+                }
+                cr1 = repaircr ? cr1 / n : CRi;
+                const double fu = f(work.data());
+                ++fev;
+                t_f[i] = fu;
+                if (fu <= sw_f[i]) {
+                    t_succ[i] = 2.0;
+                    if (fu < sw_f[i]) {
+                        SCR.push_back(cr1);
+                        wCR.push_back(sw_f[i] - fu);
+                    }
+                    std::copy(work.begin(), work.end(), sw_x.begin() + (size_t) i * n);
+                    sw_f[i] = fu;
+                }
+            }
+        }
+        const int lenS = (int) SR.size();
+        if (lenS > 0) {
+            double rn = 0.0, rd = 0.0, cn = 0.0, cd = 0.0;
+            for (int i = 0; i < lenS; i++) {
+                rn += w[i] * SR[i] * SR[i];
+                rd += w[i] * SR[i];
+                cn += w[i] * SC[i] * SC[i];
+                cd += w[i] * SC[i];
+            }
+            L1[k - 1] = rn / rd;
+            L2[k - 1] = cn / cd;
+            ++k;
+            if (k > H) k = 1;
+        }
+        const int lenSCR = (int) SCR.size();
+        if (usede && lenSCR > 0) {
+            double cn = 0.0, cd = 0.0;
+            for (int i = 0; i < lenSCR; i++) {
+                cn += wCR[i] * SCR[i] * SCR[i];
+                cd += wCR[i] * SCR[i];
+            }
+            LCR[kCR - 1] = cn / cd;
+            ++kCR;
+            if (kCR > H) kCR = 1;
+        }
+        sort_swarm();
+        if (sw_f[0] < oldbestf) convcount = 0;
+        else ++convcount;
+        const int npnew = (int) (npinit + (npmin - npinit) * (1.0 * fev) / mfev);
+        while (np > npnew) --np;
+        sw_x.resize((size_t) np * n);
+        sw_f.resize(np);
+    }
+
+    bool converged() const { /* :370-392 */
+        int count = 0;
+        double mean = 0.0, m2 = 0.0;
+        for (int i = 0; i < np; i++) {
+            const double r = port_nrm2(n, &sw_x[(size_t) i * n]);
+            count++;
+            const double dl = r - mean;
+            mean += dl / count;
+            m2 += dl * (r - mean);
+        }
+        if (m2 <= (np - 1) * tol * tol) return true;
+        return convcount > patience;
+    }
+
+    bool optimize(std::vector<double> &xout) { /* :346-360 */
+        init();
+        bool conv = false;
+        while (fev < mfev) {
+            iterate();
+            if (converged()) { conv = true; break; }
+        }
+        sort_swarm();
+        xout.assign(sw_x.begin(), sw_x.begin() + n);
+        return conv;
+    }
+};
+
 void cma_bind(PortCma *p, int obj, int n, const double *lower, const double *upper) {
     p->n = n;
     p->f.bind(obj, n);
@@ -2026,6 +2316,77 @@ int bbo_sansde_getv(void *h, const char *name, double *out, int cap) {
             { "t_F", &p->t_F }, { "t_r1", &p->t_r1 }, { "t_r2", &p->t_r2 }, { "t_r3", &p->t_r3 }, { "t_istrat", &p->t_istrat },
             { "t_jrand", &p->t_jrand }, { "t_u", &p->t_u }, { "t_succ", &p->t_succ }, { "t_ftrial", &p->t_ftrial },
             { "t_cr1", &p->t_cr1 } };
+    for (const auto &t : tags)
+        if (k == t.first) return put(*t.second, out, cap);
+    return -1;
+}
+
+void *bbo_ssde_new(int mfev, int npinit, double tol, int patience, int npmin, double ptop, int h, int usede, int repaircr) {
+    PortSsde *p = new PortSsde();
+    p->mfev = mfev; p->npinit = npinit; p->tol = tol; p->patience = patience; p->npmin = npmin; p->ptop = ptop; p->H = h;
+    p->usede = usede != 0; p->repaircr = repaircr != 0;
+    return p;
+}
+void bbo_ssde_free(void *h) { delete static_cast<PortSsde*>(h); }
+
+static void ssde_bind(PortSsde *p, int obj, int n, const double *lower, const double *upper) {
+    p->n = n;
+    p->f.bind(obj, n);
+    p->lower.assign(lower, lower + n);
+    p->upper.assign(upper, upper + n);
+}
+
+void bbo_ssde_init(void *h, int obj, int n, const double *lower, const double *upper, const double *guess) {
+    (void) guess;
+    PortSsde *p = static_cast<PortSsde*>(h);
+    ssde_bind(p, obj, n, lower, upper);
+    p->init();
+}
+void bbo_ssde_iterate(void *h) { static_cast<PortSsde*>(h)->iterate(); }
+int bbo_ssde_converged(void *h) { return static_cast<PortSsde*>(h)->converged() ? 1 : 0; }
+
+int bbo_ssde_optimize(void *h, int obj, int n, const double *lower, const double *upper, const double *guess, double *xout,
+        int *fev) {
+    (void) guess;
+    PortSsde *p = static_cast<PortSsde*>(h);
+    ssde_bind(p, obj, n, lower, upper);
+    std::vector<double> x;
+    const bool conv = p->optimize(x);
+    for (int i = 0; i < n; i++) xout[i] = x[i];
+    *fev = p->fev;
+    return conv ? 1 : 0;
+}
+
+int bbo_ssde_geti(void *h, const char *name) {
+    PortSsde *p = static_cast<PortSsde*>(h);
+    const std::string k(name);
+    if (k == "n") return p->n;
+    if (k == "np") return p->np;
+    if (k == "fev") return p->fev;
+    if (k == "convcount") return p->convcount;
+    if (k == "k") return p->k;
+    if (k == "kcr") return p->kCR;
+    return -1;
+}
+
+double bbo_ssde_getd(void *, const char *) { return NAN; }
+
+int bbo_ssde_getv(void *h, const char *name, double *out, int cap) {
+    PortSsde *p = static_cast<PortSsde*>(h);
+    const std::string k(name);
+    if (k == "swarm_x") return put(p->sw_x, out, cap);
+    if (k == "swarm_f") return put(p->sw_f, out, cap);
+    if (k == "L1") return put(p->L1, out, cap);
+    if (k == "L2") return put(p->L2, out, cap);
+    if (k == "LCR") return put(p->LCR, out, cap);
+    if (k == "iwork") {
+        for (int i = 0; i < (int) p->iwork.size() && i < cap; i++) out[i] = p->iwork[i];
+        return (int) p->iwork.size();
+    }
+    const std::pair<const char*, const std::vector<double>*> tags[] = { { "t_iwork", &p->t_iwork }, { "t_iL", &p->t_iL },
+            { "t_zrank", &p->t_zrank }, { "t_p", &p->t_p }, { "t_q", &p->t_q }, { "t_r", &p->t_r }, { "t_pbest", &p->t_pbest },
+            { "t_cauchy", &p->t_cauchy }, { "t_ub", &p->t_ub }, { "t_succ", &p->t_succ }, { "t_f", &p->t_f }, { "t_zcr", &p->t_zcr },
+            { "t_j0", &p->t_j0 }, { "t_ucr", &p->t_ucr }, { "t_redraw", &p->t_redraw } };
     for (const auto &t : tags)
         if (k == t.first) return put(*t.second, out, cap);
     return -1;

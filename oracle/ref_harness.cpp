@@ -3,7 +3,7 @@
  *
  * Built by oracle/Makefile: this file + /root/reference/src/{blas.cpp,
  * multivariate/cma/{base_cmaes,cmaes,active_cmaes,sep_cmaes,cholesky_cmaes,lm_cmaes,ipop_cmaes,bipop_cmaes}.cpp,
- * multivariate/de/{jade,shade,sansde}.cpp, multivariate/nes/xnes.cpp} compiled where they lie -> oracle/_ref/libbbo_ref.so.
+ * multivariate/de/{jade,shade,sansde,ssde}.cpp, multivariate/nes/xnes.cpp} compiled where they lie -> oracle/_ref/libbbo_ref.so.
  * No reference source is copied into this repository; the headers are included by path.
  *
  * State is reached without patching the reference: every member is `protected`
@@ -33,6 +33,7 @@
 #include "multivariate/de/jade.h"
 #include "multivariate/de/shade.h"
 #include "multivariate/de/sansde.h"
+#include "multivariate/de/ssde.h"
 #include "multivariate/nes/xnes.h"
 #include "random.hpp"
 
@@ -459,6 +460,49 @@ struct SansdeProbe: public SaNSDESearch {
     }
 };
 
+/* SSDE (de/ssde.h:44-58: state is protected) */
+struct SsdeProbe: public SSDESearch {
+    using SSDESearch::SSDESearch;
+    std::vector<double> lower, upper, guess;
+    multivariate_problem prob;
+    int geti(const std::string &k) {
+        if (k == "n") return _n;
+        if (k == "np") return _np;
+        if (k == "fev") return _fev;
+        if (k == "convcount") return _convcount;
+        if (k == "k") return _k;
+        if (k == "kcr") return _kCR;
+        return -1;
+    }
+    double getd(const std::string &) { return NAN; }
+    int getv(const std::string &k, double *out, int cap) {
+        int len = 0;
+        if (k == "swarm_x") {
+            for (const auto &pt : _swarm)
+                for (double v : pt._x) {
+                    if (len < cap) out[len] = v;
+                    len++;
+                }
+            return len;
+        }
+        if (k == "swarm_f") {
+            for (const auto &pt : _swarm) {
+                if (len < cap) out[len] = pt._f;
+                len++;
+            }
+            return len;
+        }
+        if (k == "L1") return copy_out(_L1, out, cap);
+        if (k == "L2") return copy_out(_L2, out, cap);
+        if (k == "LCR") return copy_out(_LCR, out, cap);
+        if (k == "iwork") {
+            for (int i = 0; i < (int) _iwork.size() && i < cap; i++) out[i] = _iwork[i];
+            return (int) _iwork.size();
+        }
+        return -1;
+    }
+};
+
 std::normal_distribution<> g_normal { 0., 1. };
 
 } // namespace
@@ -662,6 +706,42 @@ int bbo_sansde_optimize(void *h, int obj, int n, const double *lower, const doub
 int bbo_sansde_geti(void *h, const char *name) { return static_cast<SansdeProbe*>(h)->geti(name); }
 double bbo_sansde_getd(void *h, const char *name) { return static_cast<SansdeProbe*>(h)->getd(name); }
 int bbo_sansde_getv(void *h, const char *name, double *out, int cap) { return static_cast<SansdeProbe*>(h)->getv(name, out, cap); }
+
+void *bbo_ssde_new(int mfev, int npinit, double tol, int patience, int npmin, double ptop, int h, int usede, int repaircr) {
+    return new SsdeProbe(mfev, npinit, tol, patience, npmin, ptop, h, usede != 0, repaircr != 0);
+}
+void bbo_ssde_free(void *h) { delete static_cast<SsdeProbe*>(h); }
+
+static void ssde_bind(SsdeProbe *p, int obj, int n, const double *lower, const double *upper, const double *guess) {
+    p->lower.assign(lower, lower + n);
+    p->upper.assign(upper, upper + n);
+    p->guess.assign(guess, guess + n);
+    p->prob = multivariate_problem(make_objective(obj, n), n, p->lower.data(), p->upper.data());
+}
+
+void bbo_ssde_init(void *h, int obj, int n, const double *lower, const double *upper, const double *guess) {
+    SsdeProbe *p = static_cast<SsdeProbe*>(h);
+    ssde_bind(p, obj, n, lower, upper, guess);
+    p->init(p->prob, p->guess.data());
+}
+
+void bbo_ssde_iterate(void *h) { static_cast<SsdeProbe*>(h)->iterate(); }
+/* converged() is private; solution() reports it (its sort is a no-op: iterate() leaves the swarm sorted, ssde.cpp:322) */
+int bbo_ssde_converged(void *h) { return static_cast<SsdeProbe*>(h)->solution()._converged ? 1 : 0; }
+
+int bbo_ssde_optimize(void *h, int obj, int n, const double *lower, const double *upper, const double *guess, double *xout,
+        int *fev) {
+    SsdeProbe *p = static_cast<SsdeProbe*>(h);
+    ssde_bind(p, obj, n, lower, upper, guess);
+    multivariate_solution sol = p->optimize(p->prob, p->guess.data());
+    for (int i = 0; i < n; i++) xout[i] = sol._sol[i];
+    *fev = sol._fev;
+    return sol._converged ? 1 : 0;
+}
+
+int bbo_ssde_geti(void *h, const char *name) { return static_cast<SsdeProbe*>(h)->geti(name); }
+double bbo_ssde_getd(void *h, const char *name) { return static_cast<SsdeProbe*>(h)->getd(name); }
+int bbo_ssde_getv(void *h, const char *name, double *out, int cap) { return static_cast<SsdeProbe*>(h)->getv(name, out, cap); }
 
 void *bbo_de_new(int kind, int mfev, int np, double tol, int archive, int repaircr,
         double pelite, double cdamp, double sigma, int h, int npmin) {

@@ -161,6 +161,40 @@ def test_sansde_every_generation(ref_oracle, port_oracle, obj, n, np_, gens, kw)
     assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
 
 
+@pytest.mark.parametrize("obj,n,np_,gens,kw", [(O.RASTRIGIN, 10, 30, 150, dict()), (O.RASTRIGIN, 11, 30, 100, dict(usede=True, h=5)),
+                                                (O.ROSENBROCK, 20, 40, 80, dict(usede=True, repaircr=False, ptop=0.3)),
+                                                (O.ACKLEY, 51, 64, 40, dict(h=7, npmin=8)), (O.ROSENBROCK, 2, 12, 60, dict(usede=True))])
+def test_ssde_every_generation(ref_oracle, port_oracle, obj, n, np_, gens, kw):
+    """SSDE (de/ssde.cpp): port bit for bit after every generation -- libstdc++'s std::shuffle behind the random rotation,
+    the dense transform restricted to its non-zero entries, both stages, memories, population reduction."""
+    box = {O.ROSENBROCK: 10.0, O.RASTRIGIN: 5.12, O.ACKLEY: 32.768}[obj]
+    mfev = np_ * (gens + 4) * (2 if kw.get("usede") else 1)
+    hs = []
+    for o in (ref_oracle, port_oracle):
+        o.seed(42)
+        h = o.ssde(mfev, np_, 1e-12, **kw)
+        h.init(obj, -box * np.ones(n), box * np.ones(n))
+        hs.append(h)
+    r, p = hs
+    assert np.array_equal(r.getv("swarm_x"), p.getv("swarm_x")) and r.geti("fev") == p.geti("fev")
+    g = 0
+    while r.geti("fev") < mfev and g < gens:
+        r.iterate()
+        p.iterate()
+        g += 1
+        for k in ("iwork", "swarm_f", "swarm_x", "L1", "L2", "LCR"):
+            assert np.array_equal(r.getv(k), p.getv(k)), (g, k)
+        for k in ("np", "fev", "convcount", "k", "kcr"):
+            assert r.geti(k) == p.geti(k), (g, k)
+        assert r.converged() == p.converged()
+    assert r.geti("np") < np_, "the population reduction was exercised"
+    res = []
+    for o in (ref_oracle, port_oracle):
+        o.seed(11)
+        res.append(o.ssde(20000, 30, 1e-6, usede=True).optimize(O.SPHERE, -5 * np.ones(6), 5 * np.ones(6)))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
+
+
 def test_cma_phases_one_by_one(ref_oracle, port_oracle):
     def make(o):
         o.seed(1)
