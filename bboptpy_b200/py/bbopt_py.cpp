@@ -20,6 +20,7 @@
 #include "cma.h"
 #include "de.h"
 #include "sansde.h"
+#include "ssde.h"
 #include "xnes.h"
 #include "restart.h"
 #include "batch.h"
@@ -321,6 +322,62 @@ PYBIND11_MODULE(_bboptpy, m) {
         .def_property_readonly("rounds", &SaNSDESearch::rounds)
         .def_property_readonly("n_evals", &SaNSDESearch::evaluations)
         .def_property_readonly("popsize", &SaNSDESearch::population);
+
+    // py/multivariate_py.cpp:180-186 of the reference (note its Python default usede = False)
+    py::class_<SSDESearch, MultivariateOptimizer>(m, "SSDE")
+        .def(py::init<int, int, double, int, int, double, int, bool, bool>(), "mfev"_a, "npinit"_a, "tol"_a, "patience"_a = 1000,
+             "npmin"_a = 4, "ptop"_a = 0.11, "h"_a = 100, "usede"_a = false, "repaircr"_a = true)
+        .def("swarm", [](SSDESearch &self) {
+            std::vector<double> x = self.swarm();
+            const int np = self.population();
+            py::array_t<double> a({ (py::ssize_t) np, (py::ssize_t) (np ? x.size() / np : 0) });
+            std::copy(x.begin(), x.end(), a.mutable_data());
+            return a;
+        })
+        .def("fitness", [](SSDESearch &self) { return as_array(self.fitness()); })
+        .def("memory", [](SSDESearch &self, int which) { return as_array(self.memory(which)); }, "which"_a)
+        .def("trace", [](SSDESearch &self) {
+            std::vector<int32_t> succ;
+            std::vector<double> ft;
+            self.trace(succ, ft);
+            py::array_t<int32_t> s((py::ssize_t) succ.size());
+            std::copy(succ.begin(), succ.end(), s.mutable_data());
+            return py::make_tuple(s, as_array(ft));
+        })
+        .def("set_stream_key", &SSDESearch::setStreamKey, "key"_a)
+        .def("set_initial_population", [](SSDESearch &self, py::array_t<double, py::array::c_style | py::array::forcecast> x) {
+            self.setInitialPopulation(std::vector<double>(x.data(), x.data() + x.size()));
+        }, "x"_a)
+        .def("set_draw_replay", [](SSDESearch &self, py::object fn) {
+            if (fn.is_none()) { self.setDrawReplay(nullptr); return; }
+            self.setDrawReplay([fn](int gen, ssde_generation_draws &d) {
+                py::object r = fn(gen);
+                if (r.is_none()) return false;
+                py::dict t = r.cast<py::dict>();
+                auto dv = [&](const char *k, std::vector<double> &out) {
+                    if (!t.contains(k)) return;
+                    auto a = t[k].cast<py::array_t<double, py::array::c_style | py::array::forcecast>>();
+                    out.assign(a.data(), a.data() + a.size());
+                };
+                auto iv = [&](const char *k, std::vector<int32_t> &out) {
+                    if (!t.contains(k)) return;
+                    auto a = t[k].cast<py::array_t<double, py::array::c_style | py::array::forcecast>>();
+                    out.resize(a.size());
+                    for (py::ssize_t i = 0; i < a.size(); i++) out[i] = (int32_t) a.data()[i];
+                };
+                iv("iwork", d.iwork); iv("iL", d.iL); iv("p", d.p); iv("q", d.q); iv("r", d.r); iv("pbest", d.pbest); iv("j0", d.j0);
+                dv("zrank", d.zrank); dv("ub", d.ub); dv("cauchy", d.cauchy); dv("zcr", d.zcr); dv("ucr", d.ucr); dv("redraw", d.redraw);
+                return true;
+            });
+        }, "fn"_a)
+        .def("converged", &SSDESearch::isConverged)
+        .def_property_readonly("rounds", &SSDESearch::rounds)
+        .def_property_readonly("accepted", &SSDESearch::accepted)
+        .def_property_readonly("convcount", &SSDESearch::convcount)
+        .def_property_readonly("k", &SSDESearch::k)
+        .def_property_readonly("kCR", &SSDESearch::kCR)
+        .def_property_readonly("n_evals", &SSDESearch::evaluations)
+        .def_property_readonly("popsize", &SSDESearch::population);
 
     py::class_<DeSearchBase, MultivariateOptimizer>(m, "BaseDE")
         .def("swarm", [](DeSearchBase &self) {

@@ -309,6 +309,7 @@ def run_reference(args):
     t_gen = timed_s / len(rows)
     value = 1.0 / t_gen
     de = {"jade_evals_per_s": cpu_de_sample(o, 0), "shade_evals_per_s": cpu_de_sample(o, 1), "sansde_evals_per_s": cpu_sansde_sample(o),
+          "ssde_evals_per_s": cpu_ssde_sample(o),
           "unit": "candidate-evals/s",
           "sample": "3 generations each, n=1000 np=1000 Rastrigin, 1 thread"}
     sample = (f"{len(rows)} whole generations at n=1000, lambda=4096 through the reference's own phases (sample, evaluate+sort, "
@@ -518,6 +519,29 @@ def cpu_sansde_sample(o, gens=3, seed=1):
     for _ in range(gens):
         h.iterate()
     return gens * DE_NP / (time.perf_counter() - t0)
+
+
+def bench_ssde_e2e(pkg, gens, seed, usede=False):
+    """SSDE (de/ssde.cpp), n = 1000, npinit = 1000, Rastrigin through the Python API: objective evaluations/s (the reference's
+    own count; with `usede` a failed first trial costs a second evaluation)."""
+    lower, upper = -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N)
+    alg = pkg.SSDE(mfev=DE_NP * (gens + 1) * (2 if usede else 1), npinit=DE_NP, tol=0.0, patience=10 ** 9, usede=usede)
+    t0 = time.perf_counter()
+    sol = alg.optimize(pkg.Rastrigin, lower, upper, lower)
+    dt = time.perf_counter() - t0
+    return sol.n_evals / dt, alg.rounds
+
+
+def cpu_ssde_sample(o, gens=2, seed=1, usede=False):
+    from oracle import oracle as O
+    o.seed(seed)
+    h = o.ssde(10 ** 9, DE_NP, 0.0, usede=usede)
+    h.init(O.RASTRIGIN, -DE_BOX * np.ones(DE_N), DE_BOX * np.ones(DE_N))
+    f0 = h.geti("fev")
+    t0 = time.perf_counter()
+    for _ in range(gens):
+        h.iterate()
+    return (h.geti("fev") - f0) / (time.perf_counter() - t0)
 
 
 def bench_xnes_e2e(pkg, gens, seed):
@@ -805,6 +829,13 @@ def run_own(args):
     de["sansde"] = {"e2e_evals_per_s": world * DE_NP * 1.0 / all_max(dist, local, DE_NP / sd_rate), "rounds_last": sd_rounds,
                     "workload": "SANSDE n=1000 np=1000 Rastrigin, 200 generations through the Python API (de/sansde.cpp; one host "
                                 "round trip per dependency round)"}
+    bench_ssde_e2e(pkg, 5, seed=1 + rank)
+    ss_rate, ss_rounds = bench_ssde_e2e(pkg, 200, seed=1 + rank)
+    ss2_rate, ss2_rounds = bench_ssde_e2e(pkg, 100, seed=1 + rank, usede=True)
+    de["ssde"] = {"e2e_evals_per_s": world * DE_NP * 1.0 / all_max(dist, local, DE_NP / ss_rate), "rounds_last": ss_rounds,
+                  "usede_e2e_evals_per_s": world * DE_NP * 1.0 / all_max(dist, local, DE_NP / ss2_rate), "usede_rounds_last": ss2_rounds,
+                  "workload": "SSDE n=1000 npinit=1000 Rastrigin, 200 generations (100 with usede) through the Python API "
+                              "(de/ssde.cpp; linear population reduction; one host round trip per dependency round)"}
     bench_xnes_e2e(pkg, 3, seed=1 + rank)
     xn = {"e2e_gens_per_s": world * 1.0 / all_max(dist, local, 1.0 / bench_xnes_e2e(pkg, e2e_gens, seed=1 + rank)),
           "workload": "xNES n=1000 np=24 Rosenbrock through the Python API (nes/xnes.cpp; one eigendecomposition + two n^3 GEMMs per generation)"}
@@ -937,6 +968,8 @@ def run_own(args):
                                 "lm_cma_gens_per_s": cpu_lm_sample(o),
                                 "xnes_gens_per_s": cpu_xnes_sample(o),
                                 "de_sansde_evals_per_s": cpu_sansde_sample(o),
+                                "de_ssde_evals_per_s": cpu_ssde_sample(o),
+                                "de_ssde_usede_evals_per_s": cpu_ssde_sample(o, gens=1, usede=True),
                                 "bipop_batch": cpu_bipop_sample(o)}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 

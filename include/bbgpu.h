@@ -415,6 +415,47 @@ int bbgpu_sde_get_trace(bbgpu_sde *h, int32_t *h_succ, double *h_ftrial, double 
 int bbgpu_sde_radius(bbgpu_sde *h, double *h_mean, double *h_m2); /* converged(), :235-253 */
 int bbgpu_sde_evaluations(bbgpu_sde *h);
 
+/* ---- SSDE engine (de/ssde.cpp:134-339): spherical search with an optional DE stage and linear population reduction.  The
+ * generation depends on its own history through the live rows and -- with usede -- through R = fev / mfev, which advances with
+ * the second-stage evaluations of the earlier candidates; both are resolved by parallel fixed-point rounds.  The random
+ * rotation A (randA, :410-432) is never formed: it has at most two non-zeros per row. */
+typedef struct bbgpu_ssde bbgpu_ssde;
+/* tagged draws of one generation, host arrays of length np unless noted (DRAW REPLAY; the oracle's recorder tags them) */
+typedef struct bbgpu_ssde_draws {
+    const int32_t *iL;      /* memory slot (:151) */
+    const double *zrank;    /* N(0,1) behind the mask probability (:154-155) */
+    const double *ub;       /* np*n mask uniforms (:156-162) */
+    const int32_t *p, *q, *r, *pbest; /* :165-170 */
+    const double *cauchy;   /* the accepted Cauchy value behind c_i (:225-229) */
+    /* second stage, usede only; entries of candidates that did not reach it are ignored */
+    const double *zcr;      /* N(0,1) behind CR_i (:253-254) */
+    const int32_t *j0;      /* :258 */
+    const double *ucr;      /* np*n crossover uniforms, NaN where the reference drew none (:260) */
+    const double *redraw;   /* np*n uniform replacements of coordinates that left the box, NaN elsewhere (:264-266) */
+} bbgpu_ssde_draws;
+typedef struct bbgpu_ssde_state {
+    int32_t k, kcr;   /* cursors of the success memories (:309-314, :335-340), 1-based as in the reference */
+    int32_t evals;    /* evaluations this generation spent (np + second-stage trials) */
+    int32_t nsucc;    /* trials accepted */
+} bbgpu_ssde_state;
+int bbgpu_ssde_create(bbgpu_ctx *ctx, int n, int npinit, int h_mem, int usede, int repaircr, uint64_t seed, const double *h_lower,
+                      const double *h_upper, bbgpu_ssde **out);
+int bbgpu_ssde_destroy(bbgpu_ssde *h);
+/* init(): de/ssde.cpp:59-132.  h_x == NULL: uniform Philox points; else npinit*n replayed points.  With usede the opposite
+ * points are added, everything is evaluated and sorted and the best npinit stay.  *fev_out: evaluations spent. */
+int bbgpu_ssde_init(bbgpu_ssde *h, bbgpu_objective *obj, const double *h_x, int *fev_out);
+/* iterate() up to and including the sort (:134-345).  h_iwork: the shuffled index list behind A (n entries; consecutive pairs
+ * rotate).  fev / mfev: evaluations before the generation and the budget.  draws == NULL -> Philox. */
+int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_iwork, int fev, int mfev, double ptop,
+                          const bbgpu_ssde_draws *draws, bbgpu_ssde_state *state, int *rounds_out);
+int bbgpu_ssde_set_population(bbgpu_ssde *h, int np); /* linear population reduction (:354-360): keep the best np */
+int bbgpu_ssde_get_swarm(bbgpu_ssde *h, double *h_x, double *h_f);
+int bbgpu_ssde_get_memory(bbgpu_ssde *h, double *h_L1, double *h_L2, double *h_LCR); /* H doubles each; any may be NULL */
+/* outcome of the last generation by candidate (before the sort): 0 rejected, 1 first stage, 2 second stage; the fitness of the
+ * last trial the candidate evaluated */
+int bbgpu_ssde_get_trace(bbgpu_ssde *h, int32_t *h_succ, double *h_ftrial);
+int bbgpu_ssde_radius(bbgpu_ssde *h, double *h_mean, double *h_m2); /* converged(), :383-408 */
+
 /* ---- batched small-n CMA-ES engine (BASELINE config 5: thousands of independent
  * IPOP/BIPOP runs at n <= 64).  One CTA per run; sample -> evaluate -> rank -> update -> updateSigma ->
  * lazy eigendecomposition (the reference's tred2/tql2, inside the CTA) -> updateHistory -> converged()

@@ -1283,9 +1283,10 @@ struct PortSsde {
     std::vector<double> lower, upper, b, z, y, work, L1, L2, LCR, SR, SC, SCR, w, wCR, sw_x, sw_f;
     double sinv = 0, cosv = 0;
     BboNormal Z;
-    std::vector<double> t_iwork, t_iL, t_zrank, t_p, t_q, t_r, t_pbest, t_cauchy, t_ub, t_succ, t_f, t_zcr, t_j0, t_ucr, t_redraw;
+    std::vector<double> t_iwork, t_iL, t_zrank, t_p, t_q, t_r, t_pbest, t_cauchy, t_ub, t_succ, t_f, t_zcr, t_j0, t_ucr, t_redraw,
+            t_x0; /* the uniform points init() drew, before the opposition step and the sort */
 
-    double cauchy() { return std::tan(M_PI * (eng().uniform_real(0.0, 1.0) - 0.5)); } /* :459-461 */
+    double cauchy() { return std::tan(M_PI * (eng().uniform_real(0.0, 1.0) - 0.5)); } /* :455-457 */
 
     void sort_swarm() { /* std::sort(_swarm, point::compare_fitness) */
         struct Rec { double f; int pos; };
@@ -1318,6 +1319,7 @@ struct PortSsde {
             sw_f[i] = f(x);
             ++fev;
         }
+        t_x0 = sw_x;
         if (usede) { /* opposition-based points */
             sw_x.resize((size_t) 2 * np * n);
             sw_f.resize((size_t) 2 * np);
@@ -2386,7 +2388,7 @@ int bbo_ssde_getv(void *h, const char *name, double *out, int cap) {
     const std::pair<const char*, const std::vector<double>*> tags[] = { { "t_iwork", &p->t_iwork }, { "t_iL", &p->t_iL },
             { "t_zrank", &p->t_zrank }, { "t_p", &p->t_p }, { "t_q", &p->t_q }, { "t_r", &p->t_r }, { "t_pbest", &p->t_pbest },
             { "t_cauchy", &p->t_cauchy }, { "t_ub", &p->t_ub }, { "t_succ", &p->t_succ }, { "t_f", &p->t_f }, { "t_zcr", &p->t_zcr },
-            { "t_j0", &p->t_j0 }, { "t_ucr", &p->t_ucr }, { "t_redraw", &p->t_redraw } };
+            { "t_j0", &p->t_j0 }, { "t_ucr", &p->t_ucr }, { "t_redraw", &p->t_redraw }, { "t_x0", &p->t_x0 } };
     for (const auto &t : tags)
         if (k == t.first) return put(*t.second, out, cap);
     return -1;

@@ -1,0 +1,122 @@
+"""SSDE (de/ssde.cpp) on the device against the oracle: tagged-draw replay (tier T3).
+
+The reference updates the swarm in place inside the candidate loop and -- with `usede` -- reads R = fev / mfev while the
+second-stage evaluations of earlier candidates advance fev; the engine resolves both dependencies by parallel fixed-point
+rounds (csrc/ssde.cu).  The random rotation is applied through its two non-zeros per row, which adds the same terms in the
+same order as the reference's dense loops (the skipped terms are exact zeros).  With the oracle's tagged draws replayed
+everything is compared BIT FOR BIT: swarm, fitness, the three success memories and their cursors, the evaluation count, the
+patience counter and the population-reduction schedule.
+
+The boxes are asymmetric on purpose: with `usede` init() adds the opposite point lower + upper - x of every member, and on a
+symmetric box a symmetric objective gives both exactly the same fitness -- which of the two std::sort keeps is then a
+property of libstdc++'s introsort, not of the algorithm."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+INT_TAGS = ("iwork", "iL", "p", "q", "r", "pbest", "j0")
+DBL_TAGS = ("zrank", "ub", "cauchy", "zcr", "ucr", "redraw")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import bboptpy_b200
+    return bboptpy_b200
+
+
+def tags(h):
+    return {k: h.getv("t_" + k) for k in INT_TAGS + DBL_TAGS}
+
+
+def box_of(obj, n):
+    b = {O.ROSENBROCK: 10.0, O.RASTRIGIN: 5.12, O.ACKLEY: 32.768, O.SPHERE: 5.0}[obj]
+    return -b * np.ones(n), 0.8 * b * np.ones(n)
+
+
+def pair(pkg, P, obj, n, npinit, mfev, seed=7, tol=1e-12, **kw):
+    lo, hi = box_of(obj, n)
+    P.seed(seed)
+    h = P.ssde(mfev, npinit, tol, **kw)
+    h.init(obj, lo, hi)
+    alg = pkg.SSDE(mfev=mfev, npinit=npinit, tol=tol, **kw)
+    alg.set_initial_population(h.getv("t_x0").reshape(npinit, n))
+    alg.set_draw_replay(lambda gen: tags(h))
+    alg.initialize(pkg.Objective.builtin(obj), lo, hi, lo)
+    return h, alg
+
+
+@pytest.mark.parametrize("obj,n,npinit,gens,kw", [
+    (O.RASTRIGIN, 10, 30, 120, dict()),
+    (O.ROSENBROCK, 21, 40, 60, dict(ptop=0.2, h=5)),          # odd n: one unpaired coordinate in the rotation
+    (O.ACKLEY, 50, 64, 30, dict(usede=True)),
+    (O.RASTRIGIN, 12, 36, 150, dict(usede=True, repaircr=False, h=7, npmin=6)),
+    (O.ROSENBROCK, 16, 48, 100, dict(usede=True, ptop=0.3)),
+    (O.RASTRIGIN, 1000, 1000, 3, dict()),                     # BASELINE config 2's shape
+    (O.RASTRIGIN, 1000, 1000, 2, dict(usede=True)),
+])
+def test_replay_every_generation(pkg, port_oracle, obj, n, npinit, gens, kw):
+    mfev = npinit * (gens + 4) * (2 if kw.get("usede") else 1)
+    h, alg = pair(pkg, port_oracle, obj, n, npinit, mfev, **kw)
+    assert alg.n_evals == h.geti("fev") and alg.popsize == h.geti("np")
+    assert np.array_equal(alg.fitness(), h.getv("swarm_f"))
+    assert np.array_equal(alg.swarm().ravel(), h.getv("swarm_x"))
+    deepest, g = 0, 0
+    while h.geti("fev") < mfev and g < gens:
+        h.iterate()
+        alg.iterate()
+        g += 1
+        deepest = max(deepest, alg.rounds)
+        assert alg.accepted == int((h.getv("t_succ") > 0).sum()), f"gen {g} accepted"
+        assert alg.n_evals == h.geti("fev"), f"gen {g} evaluations"
+        assert alg.popsize == h.geti("np"), f"gen {g} population"
+        assert np.array_equal(alg.fitness(), h.getv("swarm_f")), f"gen {g} fitness"
+        assert np.array_equal(alg.swarm().ravel(), h.getv("swarm_x")), f"gen {g} swarm"
+        for which, name in enumerate(("L1", "L2", "LCR")):
+            # equal_nan: without repaircr a success with CR_i = 0 makes the weighted Lehmer mean 0 / 0, in the reference too
+            assert np.array_equal(alg.memory(which), h.getv(name), equal_nan=True), f"gen {g} {name}"
+        assert (alg.k, alg.kCR, alg.convcount) == (h.geti("k"), h.geti("kcr"), h.geti("convcount")), f"gen {g} counters"
+        assert alg.converged() == h.converged()
+    assert deepest >= 2, "the in-place dependencies were exercised"
+    if gens >= 30:
+        assert alg.popsize < npinit, "the population reduction was exercised"
+
+
+@pytest.mark.parametrize("usede", [False, True])
+def test_optimize_to_the_reference_stop(pkg, port_oracle, usede):
+    n, npinit, mfev = 6, 30, 20000
+    h, alg = pair(pkg, port_oracle, O.SPHERE, n, npinit, mfev, seed=11, tol=1e-6, usede=usede)
+    done = False
+    while alg.n_evals < mfev:
+        h.iterate()
+        alg.iterate()
+        co, cg = h.converged(), alg.converged()
+        assert co == cg
+        if cg:
+            done = True
+            break
+    assert alg.n_evals == h.geti("fev")
+    assert done or alg.n_evals >= mfev
+    assert_close(alg.solution().x, h.getv("swarm_x")[:n], rel=1e-12, what="best member")
+
+
+@pytest.mark.parametrize("usede", [False, True])
+def test_free_running(pkg, usede):
+    n = 10
+    pkg.seed(11)
+    alg = pkg.SSDE(mfev=60000, npinit=60, tol=1e-7, usede=usede)
+    sol = alg.optimize(pkg.Sphere, -5 * np.ones(n), 4 * np.ones(n), np.zeros(n))
+    assert float((sol.x ** 2).sum()) < 1e-6 and sol.n_evals <= 60000 + 2 * 60
+    a = alg.optimize(pkg.Rastrigin, -5 * np.ones(n), 4 * np.ones(n), np.zeros(n)).x
+    b = alg.optimize(pkg.Rastrigin, -5 * np.ones(n), 4 * np.ones(n), np.zeros(n)).x
+    assert not np.array_equal(a, b), "a second optimize() is a new run, as with the reference's global engine"
+
+
+def test_python_callable_objective(pkg):
+    n = 5
+    alg = pkg.SSDE(mfev=8000, npinit=24, tol=0.0, usede=True)
+    sol = alg.optimize(lambda x: float(np.sum((x - 1.0) ** 2)), -5 * np.ones(n), 5 * np.ones(n), np.zeros(n))
+    assert float(np.sum((sol.x - 1.0) ** 2)) < 1e-2
