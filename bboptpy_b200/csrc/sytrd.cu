@@ -287,11 +287,41 @@ __device__ __forceinline__ double sr_rcp(double p) { // 1 / p, ~1 ulp, for a nor
     return r;
 }
 
+// ---- data-carrying exchange (FLAGS variant of the register-resident kernel) ---------------------------------------------------
+// With the counter barrier a column pays three dependent L2 round trips between the last store of y and the first use of it:
+// the release of the arrive (the stores must be performed first), the poll of the counter, the loads of y and the pivot row.
+// Here an exchanged double is its own flag: the slot holds a sentinel (all bits set: a NaN no arithmetic produces) until the
+// value lands, and readers poll the slots they need -- no barrier, no fence, one round trip; an aligned 8-byte access is
+// single-copy atomic.  Slots are recycled through FOUR buffers: the data of step s lives in buffer s % 4, its owner resets
+// the slots to the sentinel at its own step s - 3 (followed by a fence) and writes them at step s - 1 (same thread, same address).
+// A CTA can be at most one step ahead of another (it cannot finish the poll of step i + 1 before every CTA has published for
+// it, which each does after its own poll of step i), so at the owner's step s - 3 every reader of step s - 4 is done with the
+// buffer.  The exchange area is filled with the sentinel before the launch (cudaMemset 0xFF).
+// (A first form with {32 data bits, 32-bit tag} words, NCCL-LL style, doubled the bytes every CTA polls -- 4.7 MB per column
+// over all CTAs -- and lost to the barrier at n = 1000: 3.33 against 2.99 ms.)
+constexpr unsigned long long XQ_EMPTY = ~0ull;
+__device__ __forceinline__ void xq_store(double *p, double val) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(p), "d"(val) : "memory");
+}
+__device__ __forceinline__ void xq_reset(double *p) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(XQ_EMPTY) : "memory");
+}
+__device__ __forceinline__ bool xq_load(const double *p, double &val) {
+    unsigned long long b;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(b) : "l"(p) : "memory");
+    if (b == XQ_EMPTY) return false;
+    val = __longlong_as_double((long long) b);
+    return true;
+}
+constexpr int XQ_SPIN_CAP = 1 << 22; // polls before a thread gives up and raises barrier[1] (a lost CTA must not hang the device)
+
+template<bool FLAGS>
 __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_reg_kernel(const double *__restrict__ A, int n, int ldA, double *__restrict__ d,
         double *__restrict__ e, double *__restrict__ tau, double *__restrict__ Vcm, double *ybuf, double *rowbuf, unsigned *barrier) {
     __shared__ __align__(16) double v[SR_KQ * SY_THREADS], w[SR_KQ * SY_THREADS];
     __shared__ __align__(32) double red8[8];
     __shared__ double part[8][8];
+    __shared__ double s_sc[4]; // FLAGS: y[i+1], row[i+1], y[i+2], row[i+2] from the threads that own those columns
     const int G = gridDim.x, me = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nrows = me < n ? (n - me + G - 1) / G : 0;
     double a[SR_RQ][SR_KQ];
@@ -374,7 +404,8 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_reg_kernel(const double *
                 double s = 0.0;
 #pragma unroll
                 for (int u = 0; u < 8; u++) s += part[u][tid];
-                ybuf[(size_t) parity_out * n + r] = s;
+                if (FLAGS) xq_store(ybuf + (size_t) (i_done & 3) * n + r, s); // consumed by step i_done
+                else ybuf[(size_t) parity_out * n + r] = s;
             }
         }
     };
@@ -386,7 +417,10 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_reg_kernel(const double *
 #pragma unroll
                 for (int k = 0; k < SR_KQ; k++) {
                     const int c = tid + k * SY_THREADS;
-                    if (c < n) rowbuf[(size_t) parity_out * n + c] = a[q][k];
+                    if (c < n) {
+                        if (FLAGS) xq_store(rowbuf + (size_t) ((r - 1) & 3) * n + c, a[q][k]); // row r: consumed by step r - 1
+                        else rowbuf[(size_t) parity_out * n + c] = a[q][k];
+                    }
                 }
             }
         }
@@ -395,23 +429,73 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_reg_kernel(const double *
     if (1 % G == me) publish_row(1, 0);
     for (int i = 0; i < n - 1; i++) {
         const int parity = i & 1;
-        sy_grid_barrier(barrier, (unsigned) (i + 1) * (unsigned) G);
-        const double *y = ybuf + (size_t) parity * n, *old = rowbuf + (size_t) parity * n;
-        double yk[SR_KQ], ok[SR_KQ];
-#pragma unroll
-        for (int k = 0; k < SR_KQ; k++) {
-            const int c = tid + k * SY_THREADS;
-            const bool in = c > i && c < n;
-            yk[k] = in ? __ldcg(y + c) : 0.0;
-            ok[k] = in ? __ldcg(old + c) : 0.0;
-        }
-        const double y1 = __ldcg(y + i + 1), o1 = __ldcg(old + i + 1);
         const bool more = i + 2 < n;
-        const double y2 = more ? __ldcg(y + i + 2) : 0.0, o2 = more ? __ldcg(old + i + 2) : 0.0;
+        double yk[SR_KQ], ok[SR_KQ];
+        double y1, o1, y2, o2;
+        if (FLAGS) {
+            const double *yp = ybuf + (size_t) (i & 3) * n, *rp = rowbuf + (size_t) (i & 3) * n;
+            unsigned pend = 0u;
+#pragma unroll
+            for (int k = 0; k < SR_KQ; k++) {
+                const int c = tid + k * SY_THREADS;
+                yk[k] = 0.0;
+                ok[k] = 0.0;
+                if (c > i && c < n) pend |= (1u << k) | (16u << k);
+            }
+            int spins = 0;
+            // quiet wait on ONE entry (the others arrive within the same microsecond), then sweep what is still missing
+            if (pend && lane == (i & 31)) {
+                const int k0 = __ffs(pend) - 1;
+                bool got = false;
+                while (!got) {
+#pragma unroll
+                    for (int k = 0; k < SR_KQ; k++)
+                        if (k == k0) got = xq_load(yp + tid + k * SY_THREADS, yk[k]);
+                    if (++spins > XQ_SPIN_CAP) { barrier[1] = 1u; break; }
+                }
+                pend &= ~(1u << k0);
+            }
+            __syncwarp();
+            while (pend) {
+#pragma unroll
+                for (int k = 0; k < SR_KQ; k++) {
+                    const int c = tid + k * SY_THREADS;
+                    if ((pend & (1u << k)) && xq_load(yp + c, yk[k])) pend &= ~(1u << k);
+                    if ((pend & (16u << k)) && xq_load(rp + c, ok[k])) pend &= ~(16u << k);
+                }
+                if (++spins > XQ_SPIN_CAP) { barrier[1] = 1u; break; }
+            }
+#pragma unroll
+            for (int k = 0; k < SR_KQ; k++) {
+                const int c = tid + k * SY_THREADS;
+                if (c == i + 1) { s_sc[0] = yk[k]; s_sc[1] = ok[k]; }
+                if (c == i + 2 && more) { s_sc[2] = yk[k]; s_sc[3] = ok[k]; }
+            }
+        } else {
+            sy_grid_barrier(barrier, (unsigned) (i + 1) * (unsigned) G);
+            const double *y = ybuf + (size_t) parity * n, *old = rowbuf + (size_t) parity * n;
+#pragma unroll
+            for (int k = 0; k < SR_KQ; k++) {
+                const int c = tid + k * SY_THREADS;
+                const bool in = c > i && c < n;
+                yk[k] = in ? __ldcg(y + c) : 0.0;
+                ok[k] = in ? __ldcg(old + c) : 0.0;
+            }
+            y1 = __ldcg(y + i + 1);
+            o1 = __ldcg(old + i + 1);
+            y2 = more ? __ldcg(y + i + 2) : 0.0;
+            o2 = more ? __ldcg(old + i + 2) : 0.0;
+        }
         double dot = 0.0;
 #pragma unroll
         for (int k = 0; k < SR_KQ; k++) dot = fma(yk[k], vreg[k], dot);
-        dot = sr_block_sum(dot, red8, lane, wid);
+        dot = sr_block_sum(dot, red8, lane, wid); // (its barriers publish s_sc)
+        if (FLAGS) {
+            y1 = s_sc[0];
+            o1 = s_sc[1];
+            y2 = more ? s_sc[2] : 0.0;
+            o2 = more ? s_sc[3] : 0.0;
+        }
         const double half = 0.5 * tau_i * tau_i * dot;
         const double wr1 = tau_i * y1 - half;
         const double diag = o1 - 2.0 * wr1;
@@ -476,6 +560,26 @@ __global__ void __launch_bounds__(SY_THREADS, 1) sytrd_reg_kernel(const double *
         }
         row_sums(vreg, i + 1, parity ^ 1);
         if ((i + 2) % G == me) publish_row(i + 2, parity ^ 1);
+        if (FLAGS) {
+            // recycle the slots of step i + 3 (buffer (i + 3) & 3 held step i - 1, which every CTA has consumed: see above): our y
+            // slots, and the pivot row if that row (i + 4) is ours.  We fill them two steps from now.  The fence is off the
+            // critical path -- the next thing these threads do is wait for the other CTAs -- and makes sure an empty slot is in L2
+            // before anything this CTA publishes later can be seen.
+            bool any = false;
+            if (tid < nrows) {
+                xq_reset(ybuf + (size_t) ((i + 3) & 3) * n + me + tid * G);
+                any = true;
+            }
+            if ((i + 4) % G == me) {
+#pragma unroll
+                for (int k = 0; k < SR_KQ; k++) {
+                    const int c = tid + k * SY_THREADS;
+                    if (c < n) xq_reset(rowbuf + (size_t) ((i + 3) & 3) * n + c);
+                }
+                any = true;
+            }
+            if (any) __threadfence();
+        }
         tau_i = tau_n;
     }
 }
@@ -491,7 +595,7 @@ bool sytrd_fits(bbgpu_ctx *ctx, int n) {
     return n >= 3 && n <= SY_KMAX * SY_THREADS && nrows <= SY_RMAX && smem <= 200 * 1024;
 }
 
-size_t sytrd_workspace_doubles(int n) { return 4 * (size_t) n + 64; } // y (2n), pivot rows (2n), barrier, profile
+size_t sytrd_workspace_doubles(int n) { return 8 * (size_t) n + 64; } // y and pivot rows: 4 buffers x n slots each; barrier words
 
 } // namespace bb
 
@@ -590,14 +694,22 @@ int sytrd_device(bbgpu_ctx *ctx, int n, const double *d_A, int ldA, double *d_d,
     // the register-resident kernel where the rows of a CTA fit its registers (BBGPU_SYTRD=smem keeps the other one)
     static const bool force_smem = [] { const char *e = getenv("BBGPU_SYTRD"); return e && e[0] == 's'; }();
     if (!force_smem && n <= SR_KQ * SY_THREADS && nrows <= SR_RQ) {
-        double *dy = ws, *dr = ws + 2 * (size_t) n;
-        unsigned *dbar = reinterpret_cast<unsigned*>(ws + 4 * (size_t) n);
-        BB_CUDA(cudaMemsetAsync(dbar, 0, 64, st));
+        // exchange: counter barrier + plain doubles (BBGPU_SYTRD=barrier), or tagged entries without a barrier (default)
+        if (reinterpret_cast<uintptr_t>(ws) & 15) return fail(BBGPU_ERR_ARG, "sytrd_device: the workspace must be 16-byte aligned");
+        static const bool use_barrier = [] { const char *e = getenv("BBGPU_SYTRD"); return e && e[0] == 'b'; }();
+        double *dy = ws, *dr = ws + 4 * (size_t) n; // 4 buffers x n slots each (the barrier variant uses two)
+        unsigned *dbar = reinterpret_cast<unsigned*>(ws + 8 * (size_t) n);
+        if (use_barrier) BB_CUDA(cudaMemsetAsync(dbar, 0, 64, st));
+        else {
+            BB_CUDA(cudaMemsetAsync(ws, 0xFF, 8 * (size_t) n * sizeof(double), st)); // every slot empty
+            BB_CUDA(cudaMemsetAsync(dbar, 0, 64, st));
+        }
         int nn = n, ld = ldA;
         const double *A = d_A;
         void *args[] = { (void*) &A, (void*) &nn, (void*) &ld, (void*) &d_d, (void*) &d_e, (void*) &d_tau, (void*) &d_Vcm, (void*) &dy,
                 (void*) &dr, (void*) &dbar };
-        BB_CUDA(cudaLaunchCooperativeKernel((const void*) sytrd_reg_kernel, dim3(G), dim3(SY_THREADS), args, 0, st));
+        const void *fn = use_barrier ? (const void*) sytrd_reg_kernel<false> : (const void*) sytrd_reg_kernel<true>;
+        BB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(SY_THREADS), args, 0, st));
         return launched(ctx, "sytrd_reg_kernel");
     }
     const size_t smem = ((size_t) nrows * np + 3 * (size_t) np + 32 + 8 * (size_t) nrows) * sizeof(double);
