@@ -297,8 +297,9 @@ __device__ __forceinline__ double sr_rcp(double p) { // 1 / p, ~1 ulp, for a nor
 // A CTA can be at most one step ahead of another (it cannot finish the poll of step i + 1 before every CTA has published for
 // it, which each does after its own poll of step i), so at the owner's step s - 3 every reader of step s - 4 is done with the
 // buffer.  The exchange area is filled with the sentinel before the launch (cudaMemset 0xFF).
-// (A first form with {32 data bits, 32-bit tag} words, NCCL-LL style, doubled the bytes every CTA polls -- 4.7 MB per column
-// over all CTAs -- and lost to the barrier at n = 1000: 3.33 against 2.99 ms.)
+// MEASURED AND NOT USED BY DEFAULT (profiles/r02_sytrd_flags_rejected.txt): 3.45 ms against 2.95 ms for the barrier at n = 1000.
+// 38 000 threads polling L2 cost more than the round trip they save; a first form with {32 data bits, 32-bit tag} words,
+// NCCL-LL style, doubled the polled bytes and measured 3.33 ms.
 constexpr unsigned long long XQ_EMPTY = ~0ull;
 __device__ __forceinline__ void xq_store(double *p, double val) {
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(p), "d"(val) : "memory");
@@ -694,9 +695,10 @@ int sytrd_device(bbgpu_ctx *ctx, int n, const double *d_A, int ldA, double *d_d,
     // the register-resident kernel where the rows of a CTA fit its registers (BBGPU_SYTRD=smem keeps the other one)
     static const bool force_smem = [] { const char *e = getenv("BBGPU_SYTRD"); return e && e[0] == 's'; }();
     if (!force_smem && n <= SR_KQ * SY_THREADS && nrows <= SR_RQ) {
-        // exchange: counter barrier + plain doubles (BBGPU_SYTRD=barrier), or tagged entries without a barrier (default)
+        // exchange: counter barrier + plain doubles (default), or self-validating slots without a barrier (BBGPU_SYTRD=flags:
+        // measured slower, profiles/r02_sytrd_flags_rejected.txt)
         if (reinterpret_cast<uintptr_t>(ws) & 15) return fail(BBGPU_ERR_ARG, "sytrd_device: the workspace must be 16-byte aligned");
-        static const bool use_barrier = [] { const char *e = getenv("BBGPU_SYTRD"); return e && e[0] == 'b'; }();
+        static const bool use_barrier = [] { const char *e = getenv("BBGPU_SYTRD"); return !(e && e[0] == 'f'); }();
         double *dy = ws, *dr = ws + 4 * (size_t) n; // 4 buffers x n slots each (the barrier variant uses two)
         unsigned *dbar = reinterpret_cast<unsigned*>(ws + 8 * (size_t) n);
         if (use_barrier) BB_CUDA(cudaMemsetAsync(dbar, 0, 64, st));
