@@ -156,7 +156,7 @@ int bbgpu_stedc_host(bbgpu_ctx *, int, const double *, const double *, double *,
 int bbgpu_sytrd_host(bbgpu_ctx *, int, const double *, double *, double *, double *, double *, int, float *) { return 0; }
 }
 
-/* SaNSDE entry points (link-time only: the host test does not drive this class) */
+/* SaNSDE / SSDE entry points: np evaluations per generation, nothing accepted, radius statistic 1 */
 struct bbgpu_sde { int n, np; };
 int bbgpu_sde_create(bbgpu_ctx *, int n, int np, int, uint64_t, const double *, const double *, bbgpu_sde **out) { *out = new bbgpu_sde { n, np }; return 0; }
 int bbgpu_sde_destroy(bbgpu_sde *h) { delete h; return 0; }

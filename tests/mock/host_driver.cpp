@@ -7,6 +7,8 @@
 #include "de.h"
 #include "restart.h"
 #include "batch.h"
+#include "sansde.h"
+#include "ssde.h"
 
 int main(int argc, char **argv) {
     const int n = 6;
@@ -39,6 +41,23 @@ int main(int argc, char **argv) {
     ShadeSearch shade(5000, 20, 1e-3);
     multivariate_solution s5 = shade.optimize(prob, guess.data());
     std::printf("jade fev %d conv %d, shade fev %d conv %d\n", s4._fev, (int) s4._converged, s5._fev, (int) s5._converged);
+    {   // SaNSDE / SSDE: budgets and the population-reduction schedule (de/ssde.cpp:354-360) with the stand-in's np evaluations per generation
+        SaNSDESearch sde(3000, 20, 0.0);
+        multivariate_solution s6 = sde.optimize(prob, guess.data());
+        const int npinit = 40, npmin = 4, mfev = 2000;
+        SSDESearch ssde(mfev, npinit, 0.0, 1000000, npmin, 0.11, 10, false, true);
+        multivariate_solution s7 = ssde.optimize(prob, guess.data());
+        int np = npinit, fev = npinit, gens = 0;
+        while (fev < mfev) {
+            fev += np;
+            gens++;
+            const int npnew = static_cast<int>(npinit + (npmin - npinit) * (1. * fev) / mfev);
+            if (np > npnew) np = npnew;
+        }
+        std::printf("sansde fev %d, ssde fev %d (expected %d) final population %d (expected %d) after %d generations\n", s6._fev, s7._fev, fev,
+                ssde.population(), np, gens);
+        if (s7._fev != fev || ssde.population() != np || s6._fev < 3000) return 3;
+    }
     for (int kind = 0; kind < 2; kind++) {
         const int runs = 37;
         RestartBatch batch(kind == 0 ? RestartBatch::IPOP : RestartBatch::BIPOP, runs, 20000, 1e-8, 2., 0.25);
