@@ -337,6 +337,10 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
     if (draws) {
         BB_ARG(draws->ifstrat && draws->F && draws->r1 && draws->r2 && draws->r3 && draws->istrat && draws->jrand && draws->u);
         BB_ARG(!refresh_cr || draws->zcr);
+        for (int i = 0; i < np; i++) { // replayed indices address device rows and the two-entry sums: check them here
+            BB_ARG(draws->r1[i] >= 0 && draws->r1[i] < np && draws->r2[i] >= 0 && draws->r2[i] < np && draws->r3[i] >= 0 && draws->r3[i] < np);
+            BB_ARG((draws->ifstrat[i] | 1) == 1 && (draws->istrat[i] | 1) == 1 && draws->jrand[i] >= 0 && draws->jrand[i] < n);
+        }
         if (draws->zcr) BB_CUDA(cudaMemcpyAsync(h->zcr, draws->zcr, (size_t) np * 8, cudaMemcpyHostToDevice, st));
         BB_CUDA(cudaMemcpyAsync(h->F, draws->F, (size_t) np * 8, cudaMemcpyHostToDevice, st));
         const struct { int *d; const int32_t *s; } iv[] = { { h->ifs, draws->ifstrat }, { h->r1, draws->r1 }, { h->r2, draws->r2 },

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) ss_draws_kernel(int np, int n, int H, int
     while (b == i || b == a) b = s.index(np);
     while (c == i || c == a || c == b) c = s.index(np);
     pp[i] = a; qq[i] = b; rr[i] = c;
-    pb[i] = s.index(itop + 1);
+    pb[i] = min(np - 1, s.index(itop + 1)); // (the reference's Random::get(0, itop) reads past the swarm when ptop * np >= np)
     double v = tan(3.14159265358979323846 * (s.uniform() - 0.5));
     while (!(v * 0.1 + L2[l] > 0.0)) v = tan(3.14159265358979323846 * (s.uniform() - 0.5));
     cv[i] = v;
@@ -506,6 +506,12 @@ int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_
     if (draws) {
         BB_ARG(draws->iL && draws->zrank && draws->p && draws->q && draws->r && draws->pbest && draws->cauchy && draws->ub);
         BB_ARG(!h->usede || (draws->zcr && draws->j0 && draws->ucr && draws->redraw));
+        for (int i = 0; i < np; i++) { // replayed indices address device rows: check them here
+            BB_ARG(draws->iL[i] >= 0 && draws->iL[i] < h->H);
+            BB_ARG(draws->p[i] >= 0 && draws->p[i] < np && draws->q[i] >= 0 && draws->q[i] < np && draws->r[i] >= 0 && draws->r[i] < np);
+            BB_ARG(draws->pbest[i] >= 0 && draws->pbest[i] < np);
+            BB_ARG(!h->usede || (draws->j0[i] >= 0 && draws->j0[i] < n));
+        }
         const struct { int *d; const int32_t *s; } iv[] = { { h->iL, draws->iL }, { h->pp, draws->p }, { h->qq, draws->q }, { h->rr, draws->r },
                 { h->pb, draws->pbest }, { h->j0, draws->j0 } };
         for (const auto &v : iv) if (v.s) BB_CUDA(cudaMemcpyAsync(v.d, v.s, (size_t) np * 4, cudaMemcpyHostToDevice, st));

@@ -791,10 +791,13 @@ def run_own(args):
     value = world * args.steps / t_max
     fbest, owner = all_min_with_owner(dist, local, rank, res["fbest"])
     # e2e through the public API
-    e2e_gens = max(3, min(2 * args.steps, 40))  # enough generations to amortise optimize()'s allocations and uploads
+    e2e_gens = max(3, min(5 * args.steps, 100))  # enough generations to amortise optimize()'s allocations and uploads (~10 ms per call)
     bench_cma_e2e(pkg, 2, seed=1 + rank)  # first-call costs (cuSOLVER handle, workspace) are not part of a step
     barrier(dist, local)
-    e_val, e_dt, e_done, h2d, d2h, ndec = bench_cma_e2e(pkg, e2e_gens, seed=1 + rank)
+    # the host side of optimize() (handle set-up, allocations, report reads) jitters by +-5 % from call to call and an
+    # occasional call takes 30 % longer: five calls, the median one is reported, all five are listed
+    e_runs = sorted((bench_cma_e2e(pkg, e2e_gens, seed=1 + rank) for _ in range(5)), key=lambda r: r[1])
+    e_val, e_dt, e_done, h2d, d2h, ndec = e_runs[2]
     e_dt_max = all_max(dist, local, e_dt)
     e2e_value = world * e_done / e_dt_max
     # DE half of the metric
@@ -924,7 +927,8 @@ def run_own(args):
         "clocks": clocks, "gpu_launches": int(res["launches"]),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": f"optimize(f, lower, upper, guess) through the pybind API, {e_done} generations, "
-                        f"{ndec} eigendecompositions inside the timed region (reference cadence)"},
+                        f"{ndec} eigendecompositions inside the timed region (reference cadence); median of five calls",
+                "calls_gens_per_s": [round(r[2] / r[1], 2) for r in e_runs]},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": (rd + wr) if rd is not None and wr is not None else None,
