@@ -81,6 +81,9 @@ struct bbgpu_ctx {
     void *d_flush = nullptr;
     void *d_ranks = nullptr;        // persistent zeroed counting-rank buffer (rank.cuh)
     cudaStream_t aux = nullptr;     // side stream: next generation's draws overlap the covariance update
+    void *dc_tables = nullptr;      // node tables of the tridiagonal divide & conquer (stedc.cu): a function of n alone
+    size_t dc_tables_bytes = 0;
+    int dc_tables_n = 0;
 
     int pinned(size_t bytes, void **out);
     int scratch(size_t bytes, void **out);

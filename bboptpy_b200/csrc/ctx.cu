@@ -88,6 +88,7 @@ int bbgpu_ctx_destroy(bbgpu_ctx *ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
     if (ctx->d_ranks) cudaFree(ctx->d_ranks);
+    if (ctx->dc_tables) cudaFree(ctx->dc_tables);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     for (auto &r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }

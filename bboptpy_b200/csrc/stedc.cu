@@ -486,45 +486,67 @@ __global__ void __launch_bounds__(DC_THREADS) dc_gather_kernel(const DcNode *nod
 }
 
 // ---- merge: Zt_new[o+i][o+r] = sum_j Ut[o+i][o+j] QselT[o+j][o+r], i, j < K (device-side), r < k -----------------------
+// All merges of a level in ONE launch, with the live size K read on the device: deflation shrinks the product by (K / k)^2 and
+// no operand has to be zero-padded.  32 x 32 output tiles (2 x 2 per thread), 32-deep steps, the next step's tiles are in
+// flight (registers) while this one is multiplied, one barrier per step.  Up to k = 256 this beats one TMA/DMMA launch per
+// merge (23 us against 4 x 12.6 us at k = 256 under ncu: the launches run one after the other and each multiplies the full
+// k^3); at k = 504 it does not (72 us against 2 x 21.5), so the two upper levels keep the tensor-core GEMM.
+constexpr int GS_T = 32, GS_LD = GS_T + 2;
+
 __global__ void __launch_bounds__(256) dc_gemm_kernel(const DcNode *nodes, const int *Kdev, const double *Ut, const double *QselT,
         double *Zt_new, int ld) {
     const DcNode nd = nodes[blockIdx.z];
     const int o = nd.o, k = nd.k, K = Kdev[blockIdx.z];
-    const int i0 = blockIdx.y * 64, r0 = blockIdx.x * 64;
+    const int i0 = blockIdx.y * GS_T, r0 = blockIdx.x * GS_T;
     if (i0 >= K || r0 >= k) return;
-    __shared__ double As[16][64 + 1], Bs[16][64];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // 16 x 16 threads, 4 x 4 outputs each
-    double acc[4][4] = { { 0.0 } };
+    __shared__ __align__(16) double As[2][GS_T][GS_LD], Bs[2][GS_T][GS_LD]; // [step parity][j][i or r]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int lj = tid & 31, li = tid >> 5; // loader: column lj of rows li, li + 8, li + 16, li + 24 of a tile
     const double *A = Ut + (size_t) o * ld + o, *B = QselT + (size_t) o * ld + o;
-    for (int j0 = 0; j0 < K; j0 += 16) {
-        for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) { // A tile: rows i0.., cols j0.. (stored k-major)
-            const int ii = idx >> 4, jj = idx & 15;
-            As[jj][ii] = (i0 + ii < K && j0 + jj < K) ? A[(size_t) (i0 + ii) * ld + j0 + jj] : 0.0;
+    double pa[4], pb[4];
+    auto fetch = [&](int j0) {
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int ii = li + 8 * t;
+            pa[t] = (i0 + ii < K && j0 + lj < K) ? A[(size_t) (i0 + ii) * ld + j0 + lj] : 0.0;  // A[i][j]
+            pb[t] = (j0 + ii < K && r0 + lj < k) ? B[(size_t) (j0 + ii) * ld + r0 + lj] : 0.0;  // B[j][r]
         }
-        for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
-            const int jj = idx >> 6, rr = idx & 63;
-            Bs[jj][rr] = (j0 + jj < K && r0 + rr < k) ? B[(size_t) (j0 + jj) * ld + r0 + rr] : 0.0;
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            As[buf][lj][li + 8 * t] = pa[t];
+            Bs[buf][li + 8 * t][lj] = pb[t];
         }
-        __syncthreads();
+    };
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    const int nsteps = (K + GS_T - 1) / GS_T;
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int st = 0; st < nsteps; st++) {
+        const int buf = st & 1;
+        if (st + 1 < nsteps) fetch((st + 1) * GS_T);
 #pragma unroll
-        for (int jj = 0; jj < 16; jj++) {
-            double a[4], b[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) { a[u] = As[jj][ty * 4 + u]; b[u] = Bs[jj][tx * 4 + u]; }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-#pragma unroll
-                for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        for (int jj = 0; jj < GS_T; jj++) {
+            const double2 a = *reinterpret_cast<const double2*>(&As[buf][jj][ty * 2]);
+            const double2 b = *reinterpret_cast<const double2*>(&Bs[buf][jj][tx * 2]);
+            c00 = fma(a.x, b.x, c00); c01 = fma(a.x, b.y, c01);
+            c10 = fma(a.y, b.x, c10); c11 = fma(a.y, b.y, c11);
         }
+        if (st + 1 < nsteps) stash(buf ^ 1); // last read two steps ago: every thread is past that step's barrier
         __syncthreads();
     }
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const int i = i0 + ty * 4 + u, r = r0 + tx * 4 + v;
-            if (i < K && r < k) Zt_new[(size_t) (o + i) * ld + o + r] = acc[u][v];
-        }
+    const int i = i0 + ty * 2, r = r0 + tx * 2;
+    double *out = Zt_new + (size_t) (o + i) * ld + o + r;
+    if (i < K) {
+        if (r < k) out[0] = c00;
+        if (r + 1 < k) out[1] = c01;
+    }
+    if (i + 1 < K) {
+        if (r < k) out[ld] = c10;
+        if (r + 1 < k) out[ld + 1] = c11;
+    }
 }
 
 // rows < K (device-side) of a node's product block into the new basis
@@ -536,17 +558,22 @@ __global__ void __launch_bounds__(DC_THREADS) dc_copyrows_kernel(const DcNode *n
 }
 
 // ---- final: ascending order ----------------------------------------------------------------------------------------------
+// one warp per eigenvalue (a thread per eigenvalue walked all n values alone: 25 us at n = 1000)
 __global__ void __launch_bounds__(DC_THREADS) dc_rank_kernel(const double *lam, int n, int *pos, double *W) {
-    const int j = blockIdx.x * DC_THREADS + threadIdx.x;
+    const int j = blockIdx.x * (DC_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= n) return;
     const double v = lam[j];
     int p = 0;
-    for (int q = 0; q < n; q++) {
+    for (int q = lane; q < n; q += 32) {
         const double u = lam[q];
         p += (u < v) || (u == v && q < j);
     }
-    pos[j] = p;
-    W[p] = v;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+    if (lane == 0) {
+        pos[j] = p;
+        W[p] = v;
+    }
 }
 
 __global__ void __launch_bounds__(DC_THREADS) dc_permute_kernel(const double *Zt, const int *pos, int n, int ld, double *out, int ldo) {
@@ -555,9 +582,19 @@ __global__ void __launch_bounds__(DC_THREADS) dc_permute_kernel(const double *Zt
     if (r < n) out[(size_t) pos[j] * ldo + r] = Zt[(size_t) j * ld + r];
 }
 
+// rows of a leaf: DC_LEAF unless BBGPU_DC_LEAF (8, 16, 24: a comparison switch) asks for smaller ones
+int dc_leaf_rows() {
+    static const int rows = [] {
+        const char *ev = getenv("BBGPU_DC_LEAF");
+        const int v = ev ? atoi(ev) : DC_LEAF;
+        return (v >= 8 && v <= DC_LEAF) ? v : DC_LEAF;
+    }();
+    return rows;
+}
+
 void dc_build_tree(int o, int k, int depth, std::vector<std::vector<DcNode>> &levels, std::vector<DcNode> &leaves, std::vector<int> &bounds,
         int &maxdepth) {
-    if (k <= DC_LEAF) {
+    if (k <= dc_leaf_rows()) {
         leaves.push_back({ o, k, 0 });
         return;
     }
@@ -591,7 +628,7 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
     for (auto &lv : levels) nodes_total += lv.size();
     const size_t mat = (size_t) n * ld;
     const size_t bytes = (5 * mat + 12 * (size_t) n + 64) * sizeof(double) + (6 * (size_t) n + 64) * sizeof(int) +
-            nodes_total * sizeof(DcNode) + (bounds.size() + 8) * sizeof(int) + 4096;
+            4096;
     void *sp = nullptr;
     BB_TRY(ctx->scratch(bytes, &sp));
     char *base = (char*) sp;
@@ -606,8 +643,22 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
     w.perm = (int*) take(n * 4); w.act = (int*) take(n * 4); w.slot = (int*) take(n * 4); w.org = (int*) take(n * 4);
     w.K = (int*) take(n * 4); w.lastslot = (int*) take(n * 4);
     int *pos = (int*) take(n * 4);
-    DcNode *d_nodes = (DcNode*) take(nodes_total * sizeof(DcNode));
-    int *d_bounds = (int*) take((bounds.size() + 8) * sizeof(int));
+    // The node tables are a function of n alone: they live in their own allocation and are uploaded when n changes, so a
+    // decomposition enqueues without a host synchronisation -- its ~35 launches are issued while the tridiagonalisation
+    // is still running.
+    const size_t nodes_bytes = (nodes_total * sizeof(DcNode) + 255) & ~(size_t) 255, tables_bytes = nodes_bytes + (bounds.size() + 8) * sizeof(int);
+    bool upload = ctx->dc_tables == nullptr || ctx->dc_tables_n != n;
+    if (ctx->dc_tables_bytes < tables_bytes) {
+        upload = true;
+        BB_CUDA(cudaStreamSynchronize(st));
+        if (ctx->dc_tables) cudaFree(ctx->dc_tables);
+        ctx->dc_tables = nullptr;
+        ctx->dc_tables_bytes = 0;
+        BB_CUDA(cudaMalloc(&ctx->dc_tables, tables_bytes));
+        ctx->dc_tables_bytes = tables_bytes;
+    }
+    DcNode *d_nodes = (DcNode*) ctx->dc_tables;
+    int *d_bounds = (int*) ((char*) ctx->dc_tables + nodes_bytes);
     // node tables: leaves first, then the merge levels from the deepest up
     std::vector<DcNode> table(leaves);
     std::vector<size_t> level_off(levels.size());
@@ -615,16 +666,21 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
         level_off[lv] = table.size();
         table.insert(table.end(), levels[lv].begin(), levels[lv].end());
     }
-    void *pin = nullptr;
-    BB_CUDA(cudaStreamSynchronize(st)); // the pinned staging buffer
-    BB_TRY(ctx->pinned(table.size() * sizeof(DcNode) + (bounds.size() + 8) * sizeof(int), &pin));
-    memcpy(pin, table.data(), table.size() * sizeof(DcNode));
-    int *hb = (int*) ((char*) pin + table.size() * sizeof(DcNode));
-    for (size_t q = 0; q < bounds.size(); q++) hb[q] = bounds[q];
-    BB_CUDA(cudaMemcpyAsync(d_nodes, pin, table.size() * sizeof(DcNode), cudaMemcpyHostToDevice, st));
-    if (!bounds.empty()) BB_CUDA(cudaMemcpyAsync(d_bounds, hb, bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (upload) {
+        void *pin = nullptr;
+        BB_CUDA(cudaStreamSynchronize(st)); // the pinned staging buffer; earlier decompositions still reading the old tables
+        BB_TRY(ctx->pinned(table.size() * sizeof(DcNode) + (bounds.size() + 8) * sizeof(int), &pin));
+        memcpy(pin, table.data(), table.size() * sizeof(DcNode));
+        int *hb = (int*) ((char*) pin + table.size() * sizeof(DcNode));
+        for (size_t q = 0; q < bounds.size(); q++) hb[q] = bounds[q];
+        BB_CUDA(cudaMemcpyAsync(d_nodes, pin, table.size() * sizeof(DcNode), cudaMemcpyHostToDevice, st));
+        if (!bounds.empty()) BB_CUDA(cudaMemcpyAsync(d_bounds, hb, bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        BB_CUDA(cudaStreamSynchronize(st)); // (the staging buffer may be reused by the caller right away)
+        ctx->dc_tables_n = n;
+    }
     BB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
     BB_CUDA(cudaMemsetAsync(ZA, 0, mat * 8, st));
+    BB_CUDA(cudaMemsetAsync(ZB, 0, mat * 8, st)); // entries outside a node's block are never written: zero in both buffers
     dc_adjust_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d, e, d_bounds, (int) bounds.size(), dadj, n);
     BB_TRY(launched(ctx, "dc_adjust_kernel"));
     const size_t leaf_smem = ((size_t) DC_LEAF * (DC_LEAF | 1) + 3 * DC_LEAF) * sizeof(double);
@@ -633,6 +689,8 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
     BB_TRY(launched(ctx, "dc_leaf_kernel"));
     double *Zc = ZA, *Zn = ZB, *lc = lamA, *ln = lamB;
     static const bool use_dmma = [] { const char *ev = getenv("BBGPU_DC_GEMM"); return !(ev && ev[0] == 'f'); }(); // f: plain FMA kernel
+    // merges larger than this take the tensor-core GEMM (BBGPU_DC_GEMM=d: from 256 rows, the round-1 setting)
+    static const int dmma_from = [] { const char *ev = getenv("BBGPU_DC_GEMM"); return (ev && ev[0] == 'd') ? 255 : 256; }();
     for (int lv = (int) levels.size() - 1; lv >= 0; lv--) {
         const int cnt = (int) levels[lv].size();
         const DcNode *nodes = d_nodes + level_off[lv];
@@ -640,8 +698,12 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
         for (auto &nd : levels[lv]) kmax = std::max(kmax, nd.k);
         // rows outside this level's merges (none: every row belongs to exactly one node per level when the tree is
         // balanced; unbalanced leaves that are already final are copied through)
-        BB_CUDA(cudaMemcpyAsync(Zn, Zc, mat * 8, cudaMemcpyDeviceToDevice, st));
-        if (kmax >= 256 && use_dmma) {
+        // (a level whose nodes cover every row rewrites every block entry of the new basis: nothing to carry over)
+        int covered = 0;
+        for (auto &nd : levels[lv]) covered += nd.k;
+        if (covered != n) BB_CUDA(cudaMemcpyAsync(Zn, Zc, mat * 8, cudaMemcpyDeviceToDevice, st));
+        const bool tensor = kmax > dmma_from && use_dmma;
+        if (tensor) {
             BB_CUDA(cudaMemsetAsync(Ut, 0, mat * 8, st));
             BB_CUDA(cudaMemsetAsync(Qs, 0, mat * 8, st));
         }
@@ -659,7 +721,7 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
         BB_TRY(launched(ctx, "dc_vectors_kernel"));
         dc_gather_kernel<<<dim3(cnt, ceil_div(kmax, DC_THREADS), ceil_div(kmax, DC_SEG)), DC_THREADS, 0, st>>>(nodes, w, Zc, Qs, Zn, ld);
         BB_TRY(launched(ctx, "dc_gather_kernel"));
-        if (kmax >= 256 && use_dmma) {
+        if (tensor) {
             // the engine's DMMA GEMM wants its sizes on the host: run it over the whole k x k x k block of each merge (the
             // operands are zero beyond the K live rows / columns) and keep the first K rows of the product
             for (const DcNode &nd : levels[lv]) {
@@ -671,13 +733,13 @@ int stedc_device(bbgpu_ctx *ctx, int n, const double *d, const double *e, double
             dc_copyrows_kernel<<<dim3(ceil_div(kmax, DC_THREADS), kmax, cnt), DC_THREADS, 0, st>>>(nodes, w.K, Tb, Zn, ld);
             BB_TRY(launched(ctx, "dc_copyrows_kernel"));
         } else {
-            dc_gemm_kernel<<<dim3(ceil_div(kmax, 64), ceil_div(kmax, 64), cnt), 256, 0, st>>>(nodes, w.K, Ut, Qs, Zn, ld);
+            dc_gemm_kernel<<<dim3(ceil_div(kmax, GS_T), ceil_div(kmax, GS_T), cnt), 256, 0, st>>>(nodes, w.K, Ut, Qs, Zn, ld);
             BB_TRY(launched(ctx, "dc_gemm_kernel"));
         }
         std::swap(Zc, Zn);
         std::swap(lc, ln);
     }
-    dc_rank_kernel<<<ceil_div(n, DC_THREADS), DC_THREADS, 0, st>>>(lc, n, pos, W);
+    dc_rank_kernel<<<ceil_div(n, DC_THREADS / 32), DC_THREADS, 0, st>>>(lc, n, pos, W);
     BB_TRY(launched(ctx, "dc_rank_kernel"));
     dc_permute_kernel<<<dim3(ceil_div(n, DC_THREADS), n), DC_THREADS, 0, st>>>(Zc, pos, n, ld, Zt_out, ldz);
     return launched(ctx, "dc_permute_kernel");
