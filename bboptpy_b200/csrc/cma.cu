@@ -40,7 +40,8 @@ struct bbgpu_cma {
     // LM-CMA-ES (lmcma.cuh): direction vectors and their scalars, the base draws of the pairs, live-row order, subset starts
     bool xnes = false; // xNES (xnes.cuh): Bt = the transform B (transposed), C = G / its scaled form, BDt / BDit / isC scratch
     bool lm = false;
-    int lm_mem = 0, lm_pairs = 0;
+    int lm_mem = 0, lm_pairs = 0, lm_slabs = 1, lm_part_ld = 0;
+    double *lm_part = nullptr;    // partial inner products of the slab-split sampling: pairs x slabs x lm_part_ld
     double *PCmat = nullptr, *Vmat = nullptr, *lmb = nullptr, *lmd = nullptr, *Zp = nullptr;
     int *lm_jarr = nullptr, *lm_i0 = nullptr;
     // vectors
@@ -1332,6 +1333,10 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
         A(&h->lmd, (size_t) h->lm_mem); A(&h->Zp, (size_t) h->lm_pairs * ldn);
         if (rc == BBGPU_OK) rc = dev_alloc(&h->lm_jarr, (size_t) h->lm_mem);
         if (rc == BBGPU_OK) rc = dev_alloc(&h->lm_i0, (size_t) h->lm_pairs);
+        // slabs: enough CTAs for two per SM, at least 512 columns each
+        h->lm_slabs = std::max(1, std::min(std::min((int) LM_MAXSLABS, (int) ceil_div(2 * ctx->sm_count, h->lm_pairs)), n / 512));
+        h->lm_part_ld = (int) round_up(std::max(h->lm_mem, 1), 8);
+        A(&h->lm_part, (size_t) h->lm_pairs * h->lm_slabs * h->lm_part_ld);
     } else {
         A(&h->C, ldn);
     }
@@ -1375,7 +1380,7 @@ int bbgpu_cma_destroy(bbgpu_cma *h) {
     double *bufs[] = { h->xmean, h->xold, h->pc, h->ps, h->D, h->dm, h->tmpn, h->W, h->weights, h->lower, h->upper, h->coef,
             h->ycoeff, h->dscal, h->X, h->Zbuf[0], h->Zbuf[1], h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
             h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc, h->own_ws,
-            h->Ystk, h->Mch, h->Lt, h->negone, h->rnorm, h->rstat, h->PCmat, h->Vmat, h->lmb, h->lmd, h->Zp, h->Ycomp, h->coef_comp };
+            h->Ystk, h->Mch, h->Lt, h->negone, h->rnorm, h->rstat, h->PCmat, h->Vmat, h->lmb, h->lmd, h->Zp, h->Ycomp, h->coef_comp, h->lm_part };
     if (h->sel_idx) cudaFree(h->sel_idx);
     if (h->ksel) cudaFree(h->ksel);
     if (h->lm_jarr) cudaFree(h->lm_jarr);
@@ -1670,10 +1675,21 @@ int bbgpu_cma_lm_sample(bbgpu_cma *h, double sigma, uint64_t generation, int mem
         BB_CUDA(cudaMemcpyAsync(h->lm_i0, h_i0, (size_t) h->lm_pairs * 4, cudaMemcpyHostToDevice, st));
     }
     ProfScope prof(ctx, BBGPU_PROF_SEP_SAMPLE);
-    lm_sample_kernel<<<h->lm_pairs, 256, 0, st>>>(h->X, h->Zp, h->ldn, h->n, h->lambda, h->xmean, sigma, h->PCmat, h->Vmat, h->lmb,
-            h->lm_jarr, memlen, h->lm_i0, h_z != nullptr, h->cfg.lm_rademacher, h->cfg.lm_usenew, std::sqrt(1.0 - h->cfg.c1), h->cfg.seed,
-            generation);
-    return launched(ctx, "lm_sample_kernel");
+    static const bool one_cta = [] { const char *e = getenv("BBGPU_LM_SAMPLE"); return e && e[0] == '1'; }(); // 1: a pair per CTA
+    if (h->lm_slabs == 1 || one_cta) {
+        lm_sample_kernel<<<h->lm_pairs, 256, 0, st>>>(h->X, h->Zp, h->ldn, h->n, h->lambda, h->xmean, sigma, h->PCmat, h->Vmat, h->lmb,
+                h->lm_jarr, memlen, h->lm_i0, h_z != nullptr, h->cfg.lm_rademacher, h->cfg.lm_usenew, std::sqrt(1.0 - h->cfg.c1),
+                h->cfg.seed, generation);
+        return launched(ctx, "lm_sample_kernel");
+    }
+    const int slab_len = (int) round_up(ceil_div(h->n, h->lm_slabs), 2);
+    const dim3 grid(h->lm_pairs, h->lm_slabs);
+    lm_dots_kernel<<<grid, 256, 0, st>>>(h->Zp, h->ldn, h->n, slab_len, h->Vmat, h->lm_jarr, memlen, h->lm_i0, h_z != nullptr,
+            h->cfg.lm_rademacher, h->cfg.lm_usenew, h->cfg.seed, generation, h->lm_part, h->lm_part_ld);
+    BB_TRY(launched(ctx, "lm_dots_kernel"));
+    lm_apply_kernel<<<grid, 256, 0, st>>>(h->X, h->Zp, h->ldn, h->n, h->lambda, slab_len, h->xmean, sigma, h->PCmat, h->lmb, h->lm_jarr,
+            memlen, h->lm_i0, std::sqrt(1.0 - h->cfg.c1), h->lm_part, h->lm_part_ld);
+    return launched(ctx, "lm_apply_kernel");
 }
 
 // LM kind: updateDistribution up to updateSigma (lm_cmaes.cpp:129-178)

@@ -100,6 +100,108 @@ __global__ void __launch_bounds__(256) lm_sample_kernel(double *__restrict__ X, 
     }
 }
 
+// ---- the same sampling, split over column slabs -------------------------------------------------------------------------
+// lm_sample_kernel gives a pair to ONE CTA: lambda = 64 puts 32 CTAs on 148 SMs, each streaming all of V and PC (2 x 16 MB at
+// n = 10^4, memory 200) -- 250 us of a 330 us generation.  Split: grid (pair, slab).  lm_dots_kernel draws the slab's part of
+// z_p and writes the partial inner products of its columns, lm_apply_kernel adds the partials in slab order (deterministic),
+// scales them by b_j and runs the element-local recurrence on its slab.  Same arithmetic per element; the inner products are
+// summed in a different (still fixed) order.
+constexpr int LM_MAXSLABS = 16;
+
+// i0 of pair p (selectSubset, algorithm 6, :308-322) from the pair's own Philox block
+__device__ __forceinline__ int lm_draw_i0(int p, int memlen, int usenew, uint64_t seed, uint64_t generation) {
+    if (!(usenew && memlen > 1)) return 0;
+    const Philox4 r = philox4x32_10(0xffffffffu, (uint32_t) p, (uint32_t) generation, (uint32_t) (generation >> 32) ^ 0x4c4d0000u,
+            (uint32_t) seed, (uint32_t) (seed >> 32));
+    double g0, g1;
+    normal_pair(r, g0, g1);
+    const int msigma = p == 0 ? 40 : 4; // k == 0: the first candidate of the generation (:313-316)
+    const double m = (double) msigma * fabs(g0);
+    const int mstar = m >= (double) memlen ? memlen : (int) m;
+    return memlen - mstar;
+}
+
+__global__ void __launch_bounds__(256) lm_dots_kernel(double *__restrict__ Zp, int64_t ld, int n, int slab_len, const double *__restrict__ V,
+        const int *__restrict__ jarr, int memlen, int *__restrict__ i0_io, bool replay, int rademacher, int usenew, uint64_t seed,
+        uint64_t generation, double *__restrict__ part, int part_ld) {
+    __shared__ double red[LM_GROUP][8];
+    const int p = blockIdx.x, sl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int e0 = sl * slab_len, e1 = min(n, e0 + slab_len); // slab_len is even: Philox pairs never straddle slabs
+    double *z = Zp + (int64_t) p * ld;
+    if (!replay) {
+        for (int jp = e0 / 2 + tid; 2 * jp < e1; jp += blockDim.x) {
+            const Philox4 r = philox4x32_10((uint32_t) jp, (uint32_t) p, (uint32_t) generation, (uint32_t) (generation >> 32) ^ 0x4c4d0000u,
+                    (uint32_t) seed, (uint32_t) (seed >> 32));
+            double z0, z1;
+            if (rademacher) {
+                z0 = (r.x & 1u) ? 1.0 : -1.0;
+                z1 = (r.z & 1u) ? 1.0 : -1.0;
+            } else {
+                normal_pair(r, z0, z1);
+            }
+            z[2 * jp] = z0;
+            if (2 * jp + 1 < n) z[2 * jp + 1] = z1;
+        }
+    }
+    const int i0 = replay ? i0_io[p] : lm_draw_i0(p, memlen, usenew, seed, generation);
+    if (!replay && sl == 0 && tid == 0) i0_io[p] = i0;
+    __syncthreads();
+    double *out = part + ((int64_t) p * gridDim.y + sl) * part_ld;
+    for (int g0 = i0; g0 < memlen; g0 += LM_GROUP) {
+        double acc[LM_GROUP];
+        const double *vr[LM_GROUP];
+#pragma unroll
+        for (int u = 0; u < LM_GROUP; u++) {
+            acc[u] = 0.0;
+            vr[u] = V + (int64_t) jarr[min(g0 + u, memlen - 1)] * ld;
+        }
+        for (int e = e0 + tid; e < e1; e += blockDim.x) {
+            const double ze = z[e];
+#pragma unroll
+            for (int u = 0; u < LM_GROUP; u++) acc[u] = fma(vr[u][e], ze, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < LM_GROUP; u++) {
+            const double s = warp_sum(acc[u]);
+            if (lane == 0) red[u][warp] = s;
+        }
+        __syncthreads();
+        if (tid < LM_GROUP && g0 + tid < memlen) {
+            double s = 0.0;
+            for (int w = 0; w < 8; w++) s += red[tid][w];
+            out[g0 + tid] = s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) lm_apply_kernel(double *__restrict__ X, const double *__restrict__ Zp, int64_t ld, int n, int lambda,
+        int slab_len, const double *__restrict__ xmean, double sigma, const double *__restrict__ PC, const double *__restrict__ b,
+        const int *__restrict__ jarr, int memlen, const int *__restrict__ i0_arr, double sqrt1mc1, const double *__restrict__ part,
+        int part_ld) {
+    __shared__ double dots[LM_MAXMEM];
+    const int p = blockIdx.x, sl = blockIdx.y, slabs = gridDim.y, tid = threadIdx.x;
+    const int e0 = sl * slab_len, e1 = min(n, e0 + slab_len);
+    const int i0 = i0_arr[p];
+    for (int i = i0 + tid; i < memlen; i += blockDim.x) {
+        double s = 0.0;
+        for (int t = 0; t < slabs; t++) s = __dadd_rn(s, part[((int64_t) p * slabs + t) * part_ld + i]);
+        dots[i] = __dmul_rn(b[jarr[i]], s);
+    }
+    __syncthreads();
+    const double *z = Zp + (int64_t) p * ld;
+    const bool second = 2 * p + 1 < lambda;
+    double *x0 = X + (int64_t) (2 * p) * ld, *x1 = X + (int64_t) (2 * p + 1) * ld;
+    for (int e = e0 + tid; e < e1; e += blockDim.x) {
+        double a = z[e];
+        for (int i = i0; i < memlen; i++)
+            a = __dadd_rn(__dmul_rn(sqrt1mc1, a), __dmul_rn(dots[i], PC[(int64_t) jarr[i] * ld + e]));
+        const double me = xmean[e];
+        x0[e] = __dadd_rn(me, __dmul_rn(sigma, a));
+        if (second) x1[e] = __dadd_rn(me, __dmul_rn(-sigma, a));
+    }
+}
+
 // p_c (lm_cmaes.cpp:146-149: (1 - cc) pc + (ccc (m - m_old)) / sigma, no hsig) and, when the memory is due (:151-177):
 // PC[jarr[memlen-1]] <- p_c; for i = imin .. memlen-1: t <- PC[jarr[i]], pushed through the inverse transforms of rows
 // jarr[0 .. i-1] (algorithm 4, `ainvz`: every inner product uses the UPDATED t, a genuine chain), V[jarr[i]] <- t, then

@@ -655,7 +655,7 @@ void LmCmaes::samplePopulation() {
 void LmCmaes::evaluateAndSortPopulation() {
     if (_it > 0) _fp = _fcur;
     BaseCmaes::evaluateAndSortPopulation();
-    gpu_check(bbgpu_cma_get(_dev, BBGPU_CMA_RANKVAL, _fcur.data(), _lambda));
+    // (the sorted fitness is read in updateDistribution, together with the report: one host round trip per generation)
 }
 
 // :274-306 (algorithm 5)
@@ -692,6 +692,7 @@ void LmCmaes::updateDistribution() {
         if (_memlen < _memsize) _memlen++;
     }
     gpu_check(bbgpu_cma_lm_update(_dev, _sigma, due ? 1 : 0, imin, _memlen, _jarr.data()));
+    gpu_check(bbgpu_cma_get(_dev, BBGPU_CMA_RANKVAL, _fcur.data(), _lambda)); // this generation's sorted fitness (:228-238)
     fetchReport();
     updateSigma();
 }
