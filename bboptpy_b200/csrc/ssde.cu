@@ -380,6 +380,39 @@ __global__ void __launch_bounds__(1024) ss_radius_kernel(const double *__restric
     if (threadIdx.x == 0) { out2[0] = mean; out2[1] = m2; }
 }
 
+// end of a generation, one CTA: the population the schedule leaves (:354-360, the host's own formula on the evaluation count
+// the memory kernel produced), the best fitness and the radius statistic of converged() (:383-408) over the members that stay
+// -- everything the host needs from a generation comes back in ONE read
+__global__ void __launch_bounds__(1024) ss_finish_kernel(const double *__restrict__ r, const double *__restrict__ fsorted, int np, int npinit,
+        int npmin, int fev0, int mfev, bbgpu_ssde_state *st) {
+    __shared__ double red[32];
+    __shared__ int s_keep;
+    if (threadIdx.x == 0) {
+        const int fev = fev0 + st->evals;
+        const int npnew = static_cast<int>(npinit + (npmin - npinit) * (1. * fev) / mfev);
+        s_keep = np > npnew ? max(1, npnew) : np;
+    }
+    __syncthreads();
+    const int keep = s_keep;
+    double s = 0.0;
+    for (int k = threadIdx.x; k < keep; k += blockDim.x) s += r[k];
+    s = block_sum(s, red);
+    const double mean = s / keep;
+    __syncthreads();
+    double m2 = 0.0;
+    for (int k = threadIdx.x; k < keep; k += blockDim.x) {
+        const double dlt = r[k] - mean;
+        m2 = fma(dlt, dlt, m2);
+    }
+    m2 = block_sum(m2, red);
+    if (threadIdx.x == 0) {
+        st->np_next = keep;
+        st->fbest = fsorted[0];
+        st->rmean = mean;
+        st->rm2 = m2;
+    }
+}
+
 // sort `count` members of buffer cur into the other buffer
 int ss_sort(bbgpu_ssde *h, int count) {
     bbgpu_ctx *ctx = h->ctx;
@@ -419,9 +452,9 @@ int bbgpu_ssde_create(bbgpu_ctx *ctx, int n, int npinit, int h_mem, int usede, i
     A(&h->L1, (size_t) h_mem); A(&h->L2, (size_t) h_mem); A(&h->LCR, (size_t) h_mem); A(&h->rnorm, rows2); A(&h->rstat, 8);
     I(&h->iL, rows); I(&h->pp, rows); I(&h->qq, rows); I(&h->rr, rows); I(&h->pb, rows); I(&h->j0, rows); I(&h->partner, ld); I(&h->first, ld);
     I(&h->out, rows); I(&h->changed, rows); I(&h->dirty, rows); I(&h->rebuilt, rows); I(&h->nf2, rows); I(&h->nf2_prev, rows);
-    I(&h->sortidx, rows2); I(&h->ndirty, 1);
+    I(&h->sortidx, rows2); I(&h->ndirty, 8);
     if (rc == BBGPU_OK) rc = dev_alloc(&h->d_state, 1);
-    if (rc == BBGPU_OK && (cudaMallocHost((void**) &h->h_ndirty, sizeof(int)) != cudaSuccess ||
+    if (rc == BBGPU_OK && (cudaMallocHost((void**) &h->h_ndirty, 8 * sizeof(int)) != cudaSuccess ||
             cudaMallocHost((void**) &h->h_state, sizeof(bbgpu_ssde_state)) != cudaSuccess)) rc = fail(BBGPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc != BBGPU_OK) { bbgpu_ssde_destroy(h); return rc; }
     cudaMemcpyAsync(h->lower, h_lower, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -481,13 +514,13 @@ int bbgpu_ssde_init(bbgpu_ssde *h, bbgpu_objective *obj, const double *h_x, int 
     return BBGPU_OK;
 }
 
-// One generation (ssde.cpp:134-345) up to and including the sort; the host shrinks the population afterwards
-// (bbgpu_ssde_set_population, :354-360).  h_iwork: the shuffled index list behind A (randA, :413; n entries).  fev / mfev: the
+// One generation (ssde.cpp:134-361): up to the sort as the reference runs it, then the population reduction (:354-360,
+// npmin: its floor) and the statistics the host's tests need, all returned in `state`.  h_iwork: the shuffled index list behind A (randA, :413; n entries).  fev / mfev: the
 // evaluation count at the start of the generation and the budget (R = fev / mfev is read inside the candidate loop).
 // draws == NULL -> Philox.  state (out): memory cursors, evaluations spent, trials accepted.
-int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_iwork, int fev, int mfev, double ptop,
+int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_iwork, int fev, int mfev, double ptop, int npmin,
         const bbgpu_ssde_draws *draws, bbgpu_ssde_state *state, int *rounds_out) {
-    BB_ARG(h && obj && obj->n == h->n && h_iwork && state && mfev > 0);
+    BB_ARG(h && obj && obj->n == h->n && h_iwork && state && mfev > 0 && npmin >= 1);
     bbgpu_ctx *ctx = h->ctx;
     cudaStream_t st = ctx->stream;
     const int np = h->np, n = h->n, c = h->cur;
@@ -548,8 +581,11 @@ int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_
     a.usede = h->usede; a.repaircr = h->repaircr; a.fev0 = fev; a.mfev = mfev; a.sinv = std::sin(1e-12); a.cosv = std::cos(1e-12);
     const size_t smem = (size_t) 2 * n * 8;
     if (smem > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(ss_build1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    int rounds = 0;
-    for (;;) {
+    // Rounds.  A round past the fixed point changes nothing (no candidate is dirty: the builds return at once, the evaluation
+    // and the selection reproduce their outputs), so the first SS_SPEC rounds -- what a generation usually needs -- are enqueued
+    // back to back and the host reads their dirty counts in one go; further rounds, if any, one at a time.
+    constexpr int SS_SPEC = 3;
+    auto enqueue_round = [&](int slot) -> int {
         ss_build1_kernel<<<np, 128, smem, st>>>(a);
         BB_TRY(launched(ctx, "ss_build1_kernel"));
         BB_TRY(evaluate(ctx, obj, h->Y, h->ld, np, h->fy));
@@ -559,12 +595,24 @@ int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_
             BB_TRY(evaluate(ctx, obj, h->W, h->ld, np, h->fu));
         }
         ss_select_kernel<<<1, 1024, 0, st>>>(np, h->usede, h->f[c], h->fy, h->fu, h->pp, h->qq, h->rr, h->pb, h->out, h->changed, h->dirty,
-                h->rebuilt, h->nf2, h->nf2_prev, h->ndirty);
-        BB_TRY(launched(ctx, "ss_select_kernel"));
+                h->rebuilt, h->nf2, h->nf2_prev, h->ndirty + slot);
+        return launched(ctx, "ss_select_kernel");
+    };
+    int rounds = 0;
+    bool fixed = false;
+    for (int r = 0; r < SS_SPEC; r++) BB_TRY(enqueue_round(r));
+    BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, SS_SPEC * sizeof(int), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < SS_SPEC && !fixed; r++) {
+        rounds++;
+        fixed = h->h_ndirty[r] == 0;
+    }
+    while (!fixed) {
+        BB_TRY(enqueue_round(0));
         BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, sizeof(int), cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaStreamSynchronize(st));
         rounds++;
-        if (*h->h_ndirty == 0) break;
+        fixed = h->h_ndirty[0] == 0;
         if (rounds > 2 * np + 2) return fail(BBGPU_ERR_CUDA, "SSDE rounds did not reach a fixed point");
     }
     ss_memory_kernel<<<1, 32, 0, st>>>(np, h->usede, h->H, h->f[c], h->fy, h->fu, h->out, h->prank, h->ci, h->cr1, h->L1, h->L2, h->LCR, h->d_state);
@@ -572,9 +620,14 @@ int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_
     ss_commit_kernel<<<np, 128, 0, st>>>(h->X[c], h->f[c], h->Y, h->W, h->fy, h->fu, h->out, h->ld, n);
     BB_TRY(launched(ctx, "ss_commit_kernel"));
     BB_TRY(ss_sort(h, np));
+    ss_norms_kernel<<<ceil_div(np, 8), 256, 0, st>>>(h->X[h->cur], h->ld, n, np, h->rnorm);
+    BB_TRY(launched(ctx, "ss_norms_kernel"));
+    ss_finish_kernel<<<1, 1024, 0, st>>>(h->rnorm, h->f[h->cur], np, h->npinit, npmin, fev, mfev, h->d_state);
+    BB_TRY(launched(ctx, "ss_finish_kernel"));
     BB_CUDA(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(bbgpu_ssde_state), cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
     *state = *h->h_state;
+    h->np = state->np_next; // the swarm is sorted: the worst members drop off the end
     if (rounds_out) *rounds_out = rounds;
     return BBGPU_OK;
 }

@@ -57,6 +57,7 @@ void SSDESearch::init(const multivariate_problem &f, const double *guess) {
     gpu_check(bbgpu_ssde_init(_dev, _obj.get(), have ? _initial.data() : nullptr, &_fev));
     std::vector<double> fit = fitness();
     _bestf = fit[0];
+    _radius_fresh = false;
 }
 
 // :134-361
@@ -75,32 +76,32 @@ void SSDESearch::iterate() {
         raw.iL = d.iL.data(); raw.zrank = d.zrank.data(); raw.ub = d.ub.data(); raw.p = d.p.data(); raw.q = d.q.data(); raw.r = d.r.data();
         raw.pbest = d.pbest.data(); raw.cauchy = d.cauchy.data();
         if (_usede) { raw.zcr = d.zcr.data(); raw.j0 = d.j0.data(); raw.ucr = d.ucr.data(); raw.redraw = d.redraw.data(); }
-        gpu_check(bbgpu_ssde_generation(_dev, _obj.get(), _iwork.data(), _fev, _mfev, _ptop, &raw, &st, &_rounds));
+        gpu_check(bbgpu_ssde_generation(_dev, _obj.get(), _iwork.data(), _fev, _mfev, _ptop, _npmin, &raw, &st, &_rounds));
     } else {
         std::shuffle(_iwork.begin(), _iwork.end(), bbopt::Random::engine()); // :413
-        gpu_check(bbgpu_ssde_generation(_dev, _obj.get(), _iwork.data(), _fev, _mfev, _ptop, nullptr, &st, &_rounds));
+        gpu_check(bbgpu_ssde_generation(_dev, _obj.get(), _iwork.data(), _fev, _mfev, _ptop, _npmin, nullptr, &st, &_rounds));
     }
     _fev += st.evals;
     _k = st.k;
     _kCR = st.kcr;
     _nsucc = st.nsucc;
     _it++;
-    const double best = fitness()[0]; // the swarm is sorted
-    _bestf = best;
-    if (best < oldbestf) _convcount = 0; // :347-351
+    _bestf = st.fbest; // the swarm is sorted
+    if (_bestf < oldbestf) _convcount = 0; // :347-351
     else ++_convcount;
-    const int npnew = static_cast<int>(_npinit + (_npmin - _npinit) * (1. * _fev) / _mfev); // :354-360
-    if (_np > npnew) {
-        _np = std::max(1, npnew);
-        gpu_check(bbgpu_ssde_set_population(_dev, _np));
-    }
+    _np = st.np_next; // :354-360, applied on the device with this very formula on _fev
+    _rmean = st.rmean;
+    _rm2 = st.rm2;
+    _radius_fresh = true;
 }
 
 // :383-408: standard deviation of the members' radii, or no improvement for `patience` generations
 bool SSDESearch::converged() {
-    double mean = 0., m2 = 0.;
-    gpu_check(bbgpu_ssde_radius(_dev, &mean, &m2));
-    if (m2 <= (_np - 1) * _tol * _tol) return true;
+    if (!_radius_fresh) { // (after a generation the statistic came back with its state)
+        gpu_check(bbgpu_ssde_radius(_dev, &_rmean, &_rm2));
+        _radius_fresh = true;
+    }
+    if (_rm2 <= (_np - 1) * _tol * _tol) return true;
     return _convcount > _patience;
 }
 

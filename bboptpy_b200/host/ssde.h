@@ -23,7 +23,8 @@ class SSDESearch: public MultivariateOptimizer {
 protected:
     bool _usede, _repaircr;
     int _n, _np, _npmin, _npinit, _mfev, _fev, _patience, _convcount, _H, _k, _kCR, _it;
-    double _tol, _ptop, _bestf;
+    double _tol, _ptop, _bestf, _rmean = 0., _rm2 = 0.;
+    bool _radius_fresh = false;
     multivariate_problem _f;
     std::vector<int32_t> _iwork;
     std::vector<double> _lower, _upper;

@@ -437,6 +437,10 @@ typedef struct bbgpu_ssde_state {
     int32_t k, kcr;   /* cursors of the success memories (:309-314, :335-340), 1-based as in the reference */
     int32_t evals;    /* evaluations this generation spent (np + second-stage trials) */
     int32_t nsucc;    /* trials accepted */
+    int32_t np_next;  /* population after the linear reduction (:354-360); the handle has already dropped the others */
+    int32_t pad;
+    double fbest;     /* best fitness after the generation (the patience counter, :347-351) */
+    double rmean, rm2;/* converged() (:383-408) over the members that stay: mean radius and sum of squared deviations */
 } bbgpu_ssde_state;
 int bbgpu_ssde_create(bbgpu_ctx *ctx, int n, int npinit, int h_mem, int usede, int repaircr, uint64_t seed, const double *h_lower,
                       const double *h_upper, bbgpu_ssde **out);
@@ -444,11 +448,11 @@ int bbgpu_ssde_destroy(bbgpu_ssde *h);
 /* init(): de/ssde.cpp:59-132.  h_x == NULL: uniform Philox points; else npinit*n replayed points.  With usede the opposite
  * points are added, everything is evaluated and sorted and the best npinit stay.  *fev_out: evaluations spent. */
 int bbgpu_ssde_init(bbgpu_ssde *h, bbgpu_objective *obj, const double *h_x, int *fev_out);
-/* iterate() up to and including the sort (:134-345).  h_iwork: the shuffled index list behind A (n entries; consecutive pairs
+/* iterate() (:134-361) including the population reduction (npmin: its floor).  h_iwork: the shuffled index list behind A (n entries; consecutive pairs
  * rotate).  fev / mfev: evaluations before the generation and the budget.  draws == NULL -> Philox. */
-int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_iwork, int fev, int mfev, double ptop,
+int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_iwork, int fev, int mfev, double ptop, int npmin,
                           const bbgpu_ssde_draws *draws, bbgpu_ssde_state *state, int *rounds_out);
-int bbgpu_ssde_set_population(bbgpu_ssde *h, int np); /* linear population reduction (:354-360): keep the best np */
+int bbgpu_ssde_set_population(bbgpu_ssde *h, int np); /* keep the best np (the generation applies the schedule itself) */
 int bbgpu_ssde_get_swarm(bbgpu_ssde *h, double *h_x, double *h_f);
 int bbgpu_ssde_get_memory(bbgpu_ssde *h, double *h_L1, double *h_L2, double *h_LCR); /* H doubles each; any may be NULL */
 /* outcome of the last generation by candidate (before the sort): 0 rejected, 1 first stage, 2 second stage; the fitness of the

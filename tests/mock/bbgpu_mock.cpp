@@ -167,12 +167,15 @@ int bbgpu_sde_get_swarm(bbgpu_sde *, double *, double *, double *) { return 0; }
 int bbgpu_sde_get_trace(bbgpu_sde *, int32_t *, double *, double *) { return 0; }
 int bbgpu_sde_radius(bbgpu_sde *, double *m, double *m2) { *m = 1; *m2 = 1; return 0; }
 int bbgpu_sde_evaluations(bbgpu_sde *) { return 0; }
-struct bbgpu_ssde { int n, np; };
-int bbgpu_ssde_create(bbgpu_ctx *, int n, int np, int, int, int, uint64_t, const double *, const double *, bbgpu_ssde **out) { *out = new bbgpu_ssde { n, np }; return 0; }
+struct bbgpu_ssde { int n, np, np0; };
+int bbgpu_ssde_create(bbgpu_ctx *, int n, int np, int, int, int, uint64_t, const double *, const double *, bbgpu_ssde **out) { *out = new bbgpu_ssde { n, np, np }; return 0; }
 int bbgpu_ssde_destroy(bbgpu_ssde *h) { delete h; return 0; }
 int bbgpu_ssde_init(bbgpu_ssde *h, bbgpu_objective *, const double *, int *fev) { *fev = h->np; return 0; }
-int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *, const int32_t *, int, int, double, const bbgpu_ssde_draws *, bbgpu_ssde_state *s, int *r) {
+int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *, const int32_t *, int fev, int mfev, double, int npmin, const bbgpu_ssde_draws *, bbgpu_ssde_state *s, int *r) {
     s->k = s->kcr = 1; s->evals = h->np; s->nsucc = 0;
+    const int npnew = static_cast<int>(h->np0 + (npmin - h->np0) * (1. * (fev + h->np)) / mfev);
+    if (h->np > npnew) h->np = npnew < 1 ? 1 : npnew;
+    s->np_next = h->np; s->fbest = 1.0; s->rmean = 1.0; s->rm2 = 1.0;
     if (r) *r = 1;
     return 0;
 }
