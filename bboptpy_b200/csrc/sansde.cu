@@ -273,9 +273,9 @@ int bbgpu_sde_create(bbgpu_ctx *ctx, int n, int np, int repaircr, uint64_t seed,
     A(&h->T, rows * ld); A(&h->U, rows * ld); A(&h->ftrial, rows); A(&h->lower, ld); A(&h->upper, ld);
     A(&h->zcr, rows); A(&h->F, rows); A(&h->cr1, rows); A(&h->sortval, rows); A(&h->rnorm, rows); A(&h->rstat, 8);
     I(&h->ifs, rows); I(&h->r1, rows); I(&h->r2, rows); I(&h->r3, rows); I(&h->ist, rows); I(&h->jrand, rows); I(&h->sortidx, rows);
-    I(&h->succ, rows); I(&h->changed, rows); I(&h->dirty, rows); I(&h->rebuilt, rows); I(&h->ndirty, 1);
+    I(&h->succ, rows); I(&h->changed, rows); I(&h->dirty, rows); I(&h->rebuilt, rows); I(&h->ndirty, 8);
     if (rc == BBGPU_OK) rc = dev_alloc(&h->d_acc, 1);
-    if (rc == BBGPU_OK && (cudaMallocHost((void**) &h->h_ndirty, sizeof(int)) != cudaSuccess ||
+    if (rc == BBGPU_OK && (cudaMallocHost((void**) &h->h_ndirty, 8 * sizeof(int)) != cudaSuccess ||
             cudaMallocHost((void**) &h->h_acc, sizeof(bbgpu_sde_accum)) != cudaSuccess)) rc = fail(BBGPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc != BBGPU_OK) { bbgpu_sde_destroy(h); return rc; }
     cudaMemcpyAsync(h->lower, h_lower, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -358,19 +358,34 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
     h->gen++;
     sde_begin_kernel<<<ceil_div(np, 256), 256, 0, st>>>(np, refresh_cr, crm, h->zcr, h->cr[c], h->succ, h->changed, h->dirty);
     BB_TRY(launched(ctx, "sde_begin_kernel"));
-    int rounds = 0;
-    for (;;) {
+    // Rounds.  A round past the fixed point changes nothing (no candidate is dirty: the builds return at once, the evaluation
+    // and the selection reproduce their outputs), so the first SDE_SPEC rounds -- what a generation usually needs -- are enqueued
+    // back to back and the host reads their dirty counts in one go; further rounds, if any, one at a time.
+    constexpr int SDE_SPEC = 3;
+    auto enqueue_round = [&](int slot) -> int {
         sde_build_kernel<<<np, 128, 0, st>>>(h->T, h->X[c], h->U, h->ld, n, h->lower, h->upper, h->cr[c], h->F, h->r1, h->r2, h->r3, h->ist,
                 h->jrand, h->succ, h->dirty, h->rebuilt, h->cr1, h->repaircr);
         BB_TRY(launched(ctx, "sde_build_kernel"));
         BB_TRY(evaluate(ctx, obj, h->T, h->ld, np, h->ftrial));
         sde_select_kernel<<<1, 1024, 0, st>>>(np, h->f[c], h->ftrial, h->r1, h->r2, h->r3, h->ist, h->succ, h->changed, h->dirty, h->rebuilt,
-                h->ndirty);
-        BB_TRY(launched(ctx, "sde_select_kernel"));
+                h->ndirty + slot);
+        return launched(ctx, "sde_select_kernel");
+    };
+    int rounds = 0;
+    bool fixed = false;
+    for (int r = 0; r < SDE_SPEC; r++) BB_TRY(enqueue_round(r));
+    BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, SDE_SPEC * sizeof(int), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < SDE_SPEC && !fixed; r++) {
+        rounds++;
+        fixed = h->h_ndirty[r] == 0;
+    }
+    while (!fixed) {
+        BB_TRY(enqueue_round(0));
         BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, sizeof(int), cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaStreamSynchronize(st));
         rounds++;
-        if (*h->h_ndirty == 0) break;
+        fixed = h->h_ndirty[0] == 0;
         if (rounds > np + 1) return fail(BBGPU_ERR_CUDA, "SaNSDE rounds did not reach a fixed point");
     }
     *h->h_acc = *acc;
@@ -379,6 +394,11 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
     BB_TRY(launched(ctx, "sde_accumulate_kernel"));
     sde_commit_kernel<<<np, 128, 0, st>>>(h->X[c], h->f[c], h->T, h->ftrial, h->succ, h->ld, n);
     BB_TRY(launched(ctx, "sde_commit_kernel"));
+    // converged() (:235-253) reads the swarm as this generation leaves it: its statistic travels with the sums
+    sde_norms_kernel<<<ceil_div(np, 8), 256, 0, st>>>(h->X[c], h->ld, n, np, h->rnorm);
+    BB_TRY(launched(ctx, "sde_norms_kernel"));
+    sde_radius_kernel<<<1, 1024, 0, st>>>(h->rnorm, np, &h->d_acc->rmean);
+    BB_TRY(launched(ctx, "sde_radius_kernel"));
     BB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(bbgpu_sde_accum), cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
     *acc = *h->h_acc;

@@ -50,6 +50,7 @@ void SaNSDESearch::init(const multivariate_problem &f, const double *guess) {
     const bool have = (int) _initial.size() == _np * _n;
     gpu_check(bbgpu_sde_init(_dev, _obj.get(), have ? _initial.data() : nullptr));
     _fev = _np;
+    _radius_fresh = false;
 }
 
 // :94-212
@@ -68,6 +69,7 @@ void SaNSDESearch::iterate() {
     }
     _fev += _np;
     _it++;
+    _radius_fresh = true;
     if (_it > 0 && _it % _npup == 0) { // :180-187
         const int pnsf0 = _acc.pns[0] + _acc.pnf[0];
         const int pnsf1 = _acc.pns[1] + _acc.pnf[1];
@@ -88,9 +90,11 @@ void SaNSDESearch::iterate() {
 
 // :235-253: standard deviation of the members' radii
 bool SaNSDESearch::converged() {
-    double mean = 0., m2 = 0.;
-    gpu_check(bbgpu_sde_radius(_dev, &mean, &m2));
-    return m2 <= (_np - 1) * _tol * _tol;
+    if (!_radius_fresh) { // (after a generation the statistic came back with the sums)
+        gpu_check(bbgpu_sde_radius(_dev, &_acc.rmean, &_acc.rm2));
+        _radius_fresh = true;
+    }
+    return _acc.rm2 <= (_np - 1) * _tol * _tol;
 }
 
 multivariate_solution SaNSDESearch::solution() { // :214-217: sorts, then the best member

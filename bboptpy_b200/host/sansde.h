@@ -34,6 +34,7 @@ protected:
     sansde_replay_fn _replay;
     std::vector<double> _initial;
     int _rounds = 0;
+    bool _radius_fresh = false;
     bool converged();
 
 public:

@@ -398,6 +398,7 @@ typedef struct bbgpu_sde_accum {
     int32_t pns[2], pnf[2];
     double crrec, crdeltaf, fpns[2], fpnf[2];
     int32_t nsucc, pad; /* out: trials accepted in this generation */
+    double rmean, rm2;  /* out: converged() (:235-253) on the swarm this generation leaves: mean radius, sum of squared deviations */
 } bbgpu_sde_accum;
 int bbgpu_sde_create(bbgpu_ctx *ctx, int n, int np, int repaircr, uint64_t seed, const double *h_lower, const double *h_upper,
                      bbgpu_sde **out);

@@ -161,7 +161,7 @@ struct bbgpu_sde { int n, np; };
 int bbgpu_sde_create(bbgpu_ctx *, int n, int np, int, uint64_t, const double *, const double *, bbgpu_sde **out) { *out = new bbgpu_sde { n, np }; return 0; }
 int bbgpu_sde_destroy(bbgpu_sde *h) { delete h; return 0; }
 int bbgpu_sde_init(bbgpu_sde *, bbgpu_objective *, const double *) { return 0; }
-int bbgpu_sde_generation(bbgpu_sde *, bbgpu_objective *, int, double, double, double, const bbgpu_sde_draws *, bbgpu_sde_accum *, int *r) { if (r) *r = 1; return 0; }
+int bbgpu_sde_generation(bbgpu_sde *, bbgpu_objective *, int, double, double, double, const bbgpu_sde_draws *, bbgpu_sde_accum *a, int *r) { a->rmean = 1; a->rm2 = 1; if (r) *r = 1; return 0; }
 int bbgpu_sde_sort(bbgpu_sde *) { return 0; }
 int bbgpu_sde_get_swarm(bbgpu_sde *, double *, double *, double *) { return 0; }
 int bbgpu_sde_get_trace(bbgpu_sde *, int32_t *, double *, double *) { return 0; }
