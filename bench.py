@@ -830,15 +830,14 @@ def run_own(args):
     bench_sansde_e2e(pkg, 5, seed=1 + rank)
     sd_rate, sd_rounds = bench_sansde_e2e(pkg, 200, seed=1 + rank)
     de["sansde"] = {"e2e_evals_per_s": world * DE_NP * 1.0 / all_max(dist, local, DE_NP / sd_rate), "rounds_last": sd_rounds,
-                    "workload": "SANSDE n=1000 np=1000 Rastrigin, 200 generations through the Python API (de/sansde.cpp; one host "
-                                "round trip per dependency round)"}
+                    "workload": "SANSDE n=1000 np=1000 Rastrigin, 200 generations through the Python API (de/sansde.cpp)"}
     bench_ssde_e2e(pkg, 5, seed=1 + rank)
     ss_rate, ss_rounds = bench_ssde_e2e(pkg, 200, seed=1 + rank)
     ss2_rate, ss2_rounds = bench_ssde_e2e(pkg, 100, seed=1 + rank, usede=True)
     de["ssde"] = {"e2e_evals_per_s": world * DE_NP * 1.0 / all_max(dist, local, DE_NP / ss_rate), "rounds_last": ss_rounds,
                   "usede_e2e_evals_per_s": world * DE_NP * 1.0 / all_max(dist, local, DE_NP / ss2_rate), "usede_rounds_last": ss2_rounds,
                   "workload": "SSDE n=1000 npinit=1000 Rastrigin, 200 generations (100 with usede) through the Python API "
-                              "(de/ssde.cpp; linear population reduction; one host round trip per dependency round)"}
+                              "(de/ssde.cpp; linear population reduction: the run ends in thousands of generations of a handful of candidates)"}
     bench_xnes_e2e(pkg, 3, seed=1 + rank)
     xn = {"e2e_gens_per_s": world * 1.0 / all_max(dist, local, 1.0 / bench_xnes_e2e(pkg, e2e_gens, seed=1 + rank)),
           "workload": "xNES n=1000 np=24 Rosenbrock through the Python API (nes/xnes.cpp; one eigendecomposition + two n^3 GEMMs per generation)"}
