@@ -85,6 +85,30 @@ def test_replay_every_generation(pkg, port_oracle, obj, n, npinit, gens, kw):
         assert alg.popsize < npinit, "the population reduction was exercised"
 
 
+@pytest.mark.parametrize("n,npinit,kw", [
+    (2, 8, dict(usede=True)),                 # one rotation pair, nothing else
+    (3, 8, dict()),                           # one pair + one unpaired coordinate
+    (1, 6, dict(usede=True)),                 # no pair at all: A is the identity
+    (5, 4, dict(usede=True, npmin=4)),        # the smallest population sample3() accepts, no reduction
+    (7, 12, dict(ptop=0.9, h=1)),             # top-p range over almost the whole swarm, a single memory slot
+])
+def test_replay_small_shapes(pkg, port_oracle, n, npinit, kw):
+    gens = 40
+    mfev = npinit * (gens + 2) * (2 if kw.get("usede") else 1)
+    h, alg = pair(pkg, port_oracle, O.ROSENBROCK if n > 1 else O.SPHERE, n, npinit, mfev, seed=3, **kw)
+    g = 0
+    while h.geti("fev") < mfev and g < gens and h.geti("np") >= 4:
+        h.iterate()
+        alg.iterate()
+        g += 1
+        assert alg.n_evals == h.geti("fev") and alg.popsize == h.geti("np"), f"gen {g}"
+        assert np.array_equal(alg.fitness(), h.getv("swarm_f")), f"gen {g} fitness"
+        assert np.array_equal(alg.swarm().ravel(), h.getv("swarm_x")), f"gen {g} swarm"
+        for which, name in enumerate(("L1", "L2", "LCR")):
+            assert np.array_equal(alg.memory(which), h.getv(name), equal_nan=True), f"gen {g} {name}"
+    assert g >= 10
+
+
 @pytest.mark.parametrize("usede", [False, True])
 def test_optimize_to_the_reference_stop(pkg, port_oracle, usede):
     n, npinit, mfev = 6, 30, 20000
