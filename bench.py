@@ -331,7 +331,7 @@ def run_reference(args):
         "timed_region_s": timed_s,
         "de": de,
         "cholesky": {"gens_per_s": cpu_chol_sample(o), "sample": "1 whole generation of CholeskyCmaes, n=1000 lambda=4096, 1 thread"},
-        "lm_cma": {"gens_per_s": cpu_lm_sample(o), "sample": f"40 generations of LmCmaes, n={LM_N} lambda={LM_LAMBDA}, 1 thread"},
+        "lm_cma": {"gens_per_s": cpu_lm_sample(o), "sample": f"400 generations of LmCmaes (the memory fills during the run), n={LM_N} lambda={LM_LAMBDA}, 1 thread"},
         "xnes": {"gens_per_s": cpu_xnes_sample(o), "sample": "1 generation of xNES, n=1000, 1 thread"},
         "bipop_batch": cpu_bipop_sample(o),
     }
@@ -487,7 +487,7 @@ def bench_lm_e2e(pkg, gens, seed):
     return (sol.n_evals // lam) / dt
 
 
-def cpu_lm_sample(o, gens=40, seed=1):
+def cpu_lm_sample(o, gens=400, seed=1):  # the same 400 generations as bench_lm_e2e: the memory fills during the run
     from oracle import oracle as O
     o.seed(seed)
     n = LM_N
