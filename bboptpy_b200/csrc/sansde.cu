@@ -36,6 +36,15 @@ struct bbgpu_sde {
     int *h_ndirty = nullptr; // pinned
     bbgpu_sde_accum *h_acc = nullptr; // pinned
     int fev = 0;
+    // the scalars of a generation live in device memory, so that a generation is the same work every time and can be replayed
+    // as a CUDA graph
+    struct Params { double crm, fp, p; unsigned long long gen; int refresh, pad; };
+    Params *d_par = nullptr, *h_par = nullptr; // device / pinned
+    // two captured halves of a free-running generation (up to the dirty counts of the speculative rounds; from the adaptation
+    // sums to the radius statistic), per parity of the swarm buffer the generation starts from
+    cudaGraphExec_t g_head[2] = { nullptr, nullptr }, g_tail[2] = { nullptr, nullptr };
+    int64_t g_head_kernels[2] = { 0, 0 }, g_tail_kernels[2] = { 0, 0 }, g_head_evals[2] = { 0, 0 };
+    bbgpu_objective *g_obj = nullptr;
 };
 
 namespace {
@@ -74,11 +83,13 @@ struct SdeStream {
     __device__ int index(int count) { const Philox4 r = block(); return min(count - 1, (int) (u53(r.x, r.y) * count)); }
 };
 
-__global__ void __launch_bounds__(256) sde_draws_kernel(int np, int n, uint64_t seed, uint64_t gen, double fp, double p, double *__restrict__ zcr,
-        int *__restrict__ ifs, double *__restrict__ F, int *__restrict__ r1, int *__restrict__ r2, int *__restrict__ r3, int *__restrict__ ist,
-        int *__restrict__ jrand) {
+__global__ void __launch_bounds__(256) sde_draws_kernel(int np, int n, uint64_t seed, const bbgpu_sde::Params *__restrict__ par,
+        double *__restrict__ zcr, int *__restrict__ ifs, double *__restrict__ F, int *__restrict__ r1, int *__restrict__ r2,
+        int *__restrict__ r3, int *__restrict__ ist, int *__restrict__ jrand) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
+    const uint64_t gen = par->gen;
+    const double fp = par->fp, p = par->p;
     SdeStream s { (uint32_t) i, (uint32_t) gen, (uint32_t) (gen >> 32), (uint32_t) seed, (uint32_t) (seed >> 32), 0u };
     zcr[i] = s.normal();
     const int ifstrat = s.uniform() < fp ? 0 : 1;
@@ -97,7 +108,9 @@ __global__ void __launch_bounds__(256) sde_draws_kernel(int np, int n, uint64_t 
 }
 
 // crossover uniforms of the generation (free-running)
-__global__ void __launch_bounds__(256) sde_u_kernel(double *__restrict__ U, int64_t ld, int n, int np, uint64_t seed, uint64_t gen) {
+__global__ void __launch_bounds__(256) sde_u_kernel(double *__restrict__ U, int64_t ld, int n, int np, uint64_t seed,
+        const bbgpu_sde::Params *__restrict__ par) {
+    const uint64_t gen = par->gen;
     const int64_t gid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     const int pairs = (n + 1) >> 1;
     if (gid >= (int64_t) np * pairs) return;
@@ -109,11 +122,12 @@ __global__ void __launch_bounds__(256) sde_u_kernel(double *__restrict__ U, int6
 }
 
 // start of a generation: CR refresh (:108-111) and the round state
-__global__ void __launch_bounds__(256) sde_begin_kernel(int np, int refresh, double crm, const double *__restrict__ zcr, double *__restrict__ cr,
-        int *__restrict__ succ, int *__restrict__ changed, int *__restrict__ dirty) {
+__global__ void __launch_bounds__(256) sde_begin_kernel(int np, const bbgpu_sde::Params *__restrict__ par, const double *__restrict__ zcr,
+        double *__restrict__ cr, int *__restrict__ succ, int *__restrict__ changed, int *__restrict__ dirty) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
-    if (refresh) cr[i] = fmax(0.0, fmin(__dadd_rn(__dmul_rn(zcr[i], 0.1), crm), 1.0));
+    const double crm = par->crm;
+    if (par->refresh) cr[i] = fmax(0.0, fmin(__dadd_rn(__dmul_rn(zcr[i], 0.1), crm), 1.0));
     succ[i] = 0;
     changed[i] = 0;
     dirty[i] = 1;
@@ -275,8 +289,10 @@ int bbgpu_sde_create(bbgpu_ctx *ctx, int n, int np, int repaircr, uint64_t seed,
     I(&h->ifs, rows); I(&h->r1, rows); I(&h->r2, rows); I(&h->r3, rows); I(&h->ist, rows); I(&h->jrand, rows); I(&h->sortidx, rows);
     I(&h->succ, rows); I(&h->changed, rows); I(&h->dirty, rows); I(&h->rebuilt, rows); I(&h->ndirty, 8);
     if (rc == BBGPU_OK) rc = dev_alloc(&h->d_acc, 1);
+    if (rc == BBGPU_OK) rc = dev_alloc(&h->d_par, 1);
     if (rc == BBGPU_OK && (cudaMallocHost((void**) &h->h_ndirty, 8 * sizeof(int)) != cudaSuccess ||
-            cudaMallocHost((void**) &h->h_acc, sizeof(bbgpu_sde_accum)) != cudaSuccess)) rc = fail(BBGPU_ERR_CUDA, "cudaMallocHost failed");
+            cudaMallocHost((void**) &h->h_acc, sizeof(bbgpu_sde_accum)) != cudaSuccess ||
+            cudaMallocHost((void**) &h->h_par, sizeof(bbgpu_sde::Params)) != cudaSuccess)) rc = fail(BBGPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc != BBGPU_OK) { bbgpu_sde_destroy(h); return rc; }
     cudaMemcpyAsync(h->lower, h_lower, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(h->upper, h_upper, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -294,6 +310,12 @@ int bbgpu_sde_destroy(bbgpu_sde *h) {
     int *ibufs[] = { h->ifs, h->r1, h->r2, h->r3, h->ist, h->jrand, h->sortidx, h->succ, h->changed, h->dirty, h->rebuilt, h->ndirty };
     for (int *b : ibufs) if (b) cudaFree(b);
     if (h->d_acc) cudaFree(h->d_acc);
+    if (h->d_par) cudaFree(h->d_par);
+    if (h->h_par) cudaFreeHost(h->h_par);
+    for (int q = 0; q < 2; q++) {
+        if (h->g_head[q]) cudaGraphExecDestroy(h->g_head[q]);
+        if (h->g_tail[q]) cudaGraphExecDestroy(h->g_tail[q]);
+    }
     if (h->h_ndirty) cudaFreeHost(h->h_ndirty);
     if (h->h_acc) cudaFreeHost(h->h_acc);
     delete h;
@@ -325,6 +347,110 @@ int bbgpu_sde_init(bbgpu_sde *h, bbgpu_objective *obj, const double *h_x) {
 
 // One generation (sansde.cpp:94-177) with the reference's sequential in-place semantics.  acc: the running adaptation sums,
 // in and out (the host applies the periodic updates :180-211).  draws == NULL: Philox.
+//
+// A free-running generation with a registry objective is the same ~25 launches every time -- only four scalars and the Philox
+// counter change, and those sit in device memory -- so it is captured ONCE per parity of the swarm buffer as two CUDA graphs
+// (head: sort, draws, the speculative rounds, the dirty counts; tail: adaptation sums, commit, radius statistic) and replayed:
+// two graph launches and two host reads per generation instead of ~25 launches.  Replayed draws, user objectives and profiled
+// runs take the launch-by-launch path (BBGPU_SDE_GRAPH=0 forces it).
+} // extern "C"
+
+namespace {
+
+constexpr int SDE_SPEC = 3; // rounds enqueued before the host looks at the dirty counts
+
+int sde_enqueue_round(bbgpu_sde *h, bbgpu_objective *obj, int c, int slot) {
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    const int np = h->np, n = h->n;
+    sde_build_kernel<<<np, 128, 0, st>>>(h->T, h->X[c], h->U, h->ld, n, h->lower, h->upper, h->cr[c], h->F, h->r1, h->r2, h->r3, h->ist,
+            h->jrand, h->succ, h->dirty, h->rebuilt, h->cr1, h->repaircr);
+    BB_TRY(launched(ctx, "sde_build_kernel"));
+    BB_TRY(evaluate(ctx, obj, h->T, h->ld, np, h->ftrial));
+    sde_select_kernel<<<1, 1024, 0, st>>>(np, h->f[c], h->ftrial, h->r1, h->r2, h->r3, h->ist, h->succ, h->changed, h->dirty, h->rebuilt,
+            h->ndirty + slot);
+    return launched(ctx, "sde_select_kernel");
+}
+
+// head of a generation: parameters, sort, draws (Philox, unless replayed ones were uploaded), round state, the speculative rounds
+int sde_enqueue_head(bbgpu_sde *h, bbgpu_objective *obj, bool philox) {
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    const int np = h->np, n = h->n;
+    BB_CUDA(cudaMemcpyAsync(h->d_par, h->h_par, sizeof(bbgpu_sde::Params), cudaMemcpyHostToDevice, st));
+    BB_TRY(sde_sort(h));
+    const int c = h->cur;
+    if (philox) {
+        sde_draws_kernel<<<ceil_div(np, 256), 256, 0, st>>>(np, n, h->seed, h->d_par, h->zcr, h->ifs, h->F, h->r1, h->r2, h->r3, h->ist,
+                h->jrand);
+        BB_TRY(launched(ctx, "sde_draws_kernel"));
+        const int64_t total = (int64_t) np * ((n + 1) / 2);
+        sde_u_kernel<<<ceil_div(total, 256), 256, 0, st>>>(h->U, h->ld, n, np, h->seed, h->d_par);
+        BB_TRY(launched(ctx, "sde_u_kernel"));
+    }
+    sde_begin_kernel<<<ceil_div(np, 256), 256, 0, st>>>(np, h->d_par, h->zcr, h->cr[c], h->succ, h->changed, h->dirty);
+    BB_TRY(launched(ctx, "sde_begin_kernel"));
+    // Rounds.  A round past the fixed point changes nothing (no candidate is dirty: the builds return at once, the evaluation
+    // and the selection reproduce their outputs), so the first SDE_SPEC rounds -- what a generation usually needs -- are enqueued
+    // back to back and the host reads their dirty counts in one go; further rounds, if any, one at a time.
+    for (int r = 0; r < SDE_SPEC; r++) BB_TRY(sde_enqueue_round(h, obj, c, r));
+    BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, SDE_SPEC * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return BBGPU_OK;
+}
+
+// tail: the adaptation sums in candidate order, the accepted trials, the radius statistic of converged()
+int sde_enqueue_tail(bbgpu_sde *h) {
+    bbgpu_ctx *ctx = h->ctx;
+    cudaStream_t st = ctx->stream;
+    const int np = h->np, n = h->n, c = h->cur;
+    BB_CUDA(cudaMemcpyAsync(h->d_acc, h->h_acc, sizeof(bbgpu_sde_accum), cudaMemcpyHostToDevice, st));
+    sde_accumulate_kernel<<<1, 32, 0, st>>>(np, h->f[c], h->ftrial, h->succ, h->ist, h->ifs, h->F, h->cr1, h->d_acc);
+    BB_TRY(launched(ctx, "sde_accumulate_kernel"));
+    sde_commit_kernel<<<np, 128, 0, st>>>(h->X[c], h->f[c], h->T, h->ftrial, h->succ, h->ld, n);
+    BB_TRY(launched(ctx, "sde_commit_kernel"));
+    // converged() (:235-253) reads the swarm as this generation leaves it: its statistic travels with the sums
+    sde_norms_kernel<<<ceil_div(np, 8), 256, 0, st>>>(h->X[c], h->ld, n, np, h->rnorm);
+    BB_TRY(launched(ctx, "sde_norms_kernel"));
+    sde_radius_kernel<<<1, 1024, 0, st>>>(h->rnorm, np, &h->d_acc->rmean);
+    BB_TRY(launched(ctx, "sde_radius_kernel"));
+    BB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(bbgpu_sde_accum), cudaMemcpyDeviceToHost, st));
+    return BBGPU_OK;
+}
+
+// capture `enqueue` on the ctx stream into an executable graph; *kernels: launches it holds
+template<typename F>
+int sde_capture(bbgpu_sde *h, F enqueue, cudaGraphExec_t *exec, int64_t *kernels) {
+    bbgpu_ctx *ctx = h->ctx;
+    const int64_t before = ctx->launches;
+    BB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    *kernels = ctx->launches - before;
+    ctx->launches = before; // nothing ran yet: the replays are counted
+    if (rc != BBGPU_OK || e != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc != BBGPU_OK ? rc : fail(BBGPU_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+    }
+    const cudaError_t ei = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return fail(BBGPU_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+    return BBGPU_OK;
+}
+
+void sde_drop_graphs(bbgpu_sde *h) {
+    for (int q = 0; q < 2; q++) {
+        if (h->g_head[q]) cudaGraphExecDestroy(h->g_head[q]);
+        if (h->g_tail[q]) cudaGraphExecDestroy(h->g_tail[q]);
+        h->g_head[q] = h->g_tail[q] = nullptr;
+    }
+    h->g_obj = nullptr;
+}
+
+} // namespace
+
+extern "C" {
+
 int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, double crm, double fp, double p, const bbgpu_sde_draws *draws,
         bbgpu_sde_accum *acc, int *rounds_out) {
     BB_ARG(h && obj && obj->n == h->n && acc);
@@ -332,8 +458,10 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
     cudaStream_t st = ctx->stream;
     const int np = h->np, n = h->n;
     ProfScope prof(ctx, BBGPU_PROF_DE_ROUND);
-    BB_TRY(sde_sort(h));
-    const int c = h->cur;
+    static const bool graphs_on = [] { const char *e = getenv("BBGPU_SDE_GRAPH"); return !(e && e[0] == '0'); }();
+    // (the first two generations run launch by launch: lazily created buffers of the ranking exist afterwards)
+    const bool graph = graphs_on && draws == nullptr && obj->mode == 0 && !ctx->profiling && h->gen >= 2;
+    *h->h_par = bbgpu_sde::Params { crm, fp, p, (unsigned long long) h->gen, refresh_cr, 0 };
     if (draws) {
         BB_ARG(draws->ifstrat && draws->F && draws->r1 && draws->r2 && draws->r3 && draws->istrat && draws->jrand && draws->u);
         BB_ARG(!refresh_cr || draws->zcr);
@@ -347,41 +475,36 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
                 { h->r3, draws->r3 }, { h->ist, draws->istrat }, { h->jrand, draws->jrand } };
         for (const auto &v : iv) BB_CUDA(cudaMemcpyAsync(v.d, v.s, (size_t) np * 4, cudaMemcpyHostToDevice, st));
         BB_CUDA(cudaMemcpy2DAsync(h->U, (size_t) h->ld * 8, draws->u, (size_t) n * 8, (size_t) n * 8, np, cudaMemcpyHostToDevice, st));
+    }
+    if (graph && h->g_obj != obj) sde_drop_graphs(h); // another objective: the evaluation launches differ
+    const int c0 = h->cur;
+    if (graph) {
+        if (h->g_head[c0] == nullptr) {
+            const int64_t evals0 = obj->evals;
+            BB_TRY(sde_capture(h, [&] { return sde_enqueue_head(h, obj, true); }, &h->g_head[c0], &h->g_head_kernels[c0]));
+            h->g_head_evals[c0] = obj->evals - evals0;
+            obj->evals = evals0;
+            h->g_obj = obj;
+            h->cur = c0; // the capture walked through the sort
+        }
+        BB_CUDA(cudaGraphLaunch(h->g_head[c0], st));
+        ctx->launches += h->g_head_kernels[c0];
+        obj->evals += h->g_head_evals[c0];
+        h->cur = c0 ^ 1;
     } else {
-        sde_draws_kernel<<<ceil_div(np, 256), 256, 0, st>>>(np, n, h->seed, h->gen, fp, p, h->zcr, h->ifs, h->F, h->r1, h->r2, h->r3, h->ist,
-                h->jrand);
-        BB_TRY(launched(ctx, "sde_draws_kernel"));
-        const int64_t total = (int64_t) np * ((n + 1) / 2);
-        sde_u_kernel<<<ceil_div(total, 256), 256, 0, st>>>(h->U, h->ld, n, np, h->seed, h->gen);
-        BB_TRY(launched(ctx, "sde_u_kernel"));
+        BB_TRY(sde_enqueue_head(h, obj, draws == nullptr));
     }
     h->gen++;
-    sde_begin_kernel<<<ceil_div(np, 256), 256, 0, st>>>(np, refresh_cr, crm, h->zcr, h->cr[c], h->succ, h->changed, h->dirty);
-    BB_TRY(launched(ctx, "sde_begin_kernel"));
-    // Rounds.  A round past the fixed point changes nothing (no candidate is dirty: the builds return at once, the evaluation
-    // and the selection reproduce their outputs), so the first SDE_SPEC rounds -- what a generation usually needs -- are enqueued
-    // back to back and the host reads their dirty counts in one go; further rounds, if any, one at a time.
-    constexpr int SDE_SPEC = 3;
-    auto enqueue_round = [&](int slot) -> int {
-        sde_build_kernel<<<np, 128, 0, st>>>(h->T, h->X[c], h->U, h->ld, n, h->lower, h->upper, h->cr[c], h->F, h->r1, h->r2, h->r3, h->ist,
-                h->jrand, h->succ, h->dirty, h->rebuilt, h->cr1, h->repaircr);
-        BB_TRY(launched(ctx, "sde_build_kernel"));
-        BB_TRY(evaluate(ctx, obj, h->T, h->ld, np, h->ftrial));
-        sde_select_kernel<<<1, 1024, 0, st>>>(np, h->f[c], h->ftrial, h->r1, h->r2, h->r3, h->ist, h->succ, h->changed, h->dirty, h->rebuilt,
-                h->ndirty + slot);
-        return launched(ctx, "sde_select_kernel");
-    };
+    const int c = h->cur;
+    BB_CUDA(cudaStreamSynchronize(st));
     int rounds = 0;
     bool fixed = false;
-    for (int r = 0; r < SDE_SPEC; r++) BB_TRY(enqueue_round(r));
-    BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, SDE_SPEC * sizeof(int), cudaMemcpyDeviceToHost, st));
-    BB_CUDA(cudaStreamSynchronize(st));
     for (int r = 0; r < SDE_SPEC && !fixed; r++) {
         rounds++;
         fixed = h->h_ndirty[r] == 0;
     }
     while (!fixed) {
-        BB_TRY(enqueue_round(0));
+        BB_TRY(sde_enqueue_round(h, obj, c, 0));
         BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, sizeof(int), cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaStreamSynchronize(st));
         rounds++;
@@ -389,17 +512,13 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
         if (rounds > np + 1) return fail(BBGPU_ERR_CUDA, "SaNSDE rounds did not reach a fixed point");
     }
     *h->h_acc = *acc;
-    BB_CUDA(cudaMemcpyAsync(h->d_acc, h->h_acc, sizeof(bbgpu_sde_accum), cudaMemcpyHostToDevice, st));
-    sde_accumulate_kernel<<<1, 32, 0, st>>>(np, h->f[c], h->ftrial, h->succ, h->ist, h->ifs, h->F, h->cr1, h->d_acc);
-    BB_TRY(launched(ctx, "sde_accumulate_kernel"));
-    sde_commit_kernel<<<np, 128, 0, st>>>(h->X[c], h->f[c], h->T, h->ftrial, h->succ, h->ld, n);
-    BB_TRY(launched(ctx, "sde_commit_kernel"));
-    // converged() (:235-253) reads the swarm as this generation leaves it: its statistic travels with the sums
-    sde_norms_kernel<<<ceil_div(np, 8), 256, 0, st>>>(h->X[c], h->ld, n, np, h->rnorm);
-    BB_TRY(launched(ctx, "sde_norms_kernel"));
-    sde_radius_kernel<<<1, 1024, 0, st>>>(h->rnorm, np, &h->d_acc->rmean);
-    BB_TRY(launched(ctx, "sde_radius_kernel"));
-    BB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(bbgpu_sde_accum), cudaMemcpyDeviceToHost, st));
+    if (graph) {
+        if (h->g_tail[c] == nullptr) BB_TRY(sde_capture(h, [&] { return sde_enqueue_tail(h); }, &h->g_tail[c], &h->g_tail_kernels[c]));
+        BB_CUDA(cudaGraphLaunch(h->g_tail[c], st));
+        ctx->launches += h->g_tail_kernels[c];
+    } else {
+        BB_TRY(sde_enqueue_tail(h));
+    }
     BB_CUDA(cudaStreamSynchronize(st));
     *acc = *h->h_acc;
     h->fev += np;
