@@ -149,57 +149,72 @@ __device__ __forceinline__ const double *ss_row(const SsArgs &a, int p, int i) {
     return a.X + (int64_t) p * a.ld;
 }
 
-// A[d][k] for a structurally non-zero entry (k == d or k == partner[d])
-__device__ __forceinline__ double ss_a(const SsArgs &a, int d, int k) {
-    if (a.partner[d] < 0) return 1.0;
-    if (d == k) return a.sinv;
-    return a.first[d] ? a.cosv : -a.cosv;
-}
+// stage 1 (:173-234, computeTrialPoint :434-453): z, work = diag(b) A z, y = clip(x_i + c A^T work).  Everything the three
+// phases need from global memory is fetched in the FIRST one (the kernel is a chain of dependent load latencies otherwise:
+// 29 us for 1000 candidates, profiles/r02_ncu_new_kernels.txt): z, x_i and a packed word per coordinate -- partner index + 1,
+// orientation of the pair, mask bit -- go to shared memory, the later phases read only that.
+constexpr unsigned SS_FIRST = 1u << 30, SS_MASK = 1u << 31, SS_PARTNER = (1u << 30) - 1u;
 
-// stage 1 (:173-234, computeTrialPoint :434-453): z, work = diag(b) A z (staged in shared memory), y = clip(x_i + c A^T work)
 __global__ void __launch_bounds__(128) ss_build1_kernel(const SsArgs a) {
-    extern __shared__ double sh[]; // z[n], work[n]
-    double *z = sh, *work = sh + a.n;
+    extern __shared__ double sh[]; // z[n], work[n], x_i[n], n packed words
+    const int n = a.n;
+    double *z = sh, *work = sh + n, *xs = sh + 2 * n;
+    unsigned *code = reinterpret_cast<unsigned*>(sh + 3 * n);
     const int i = blockIdx.x;
     if (threadIdx.x == 0) a.rebuilt[i] = a.dirty[i];
     if (!a.dirty[i]) return;
-    const int n = a.n;
     const double R = (1.0 * (a.fev0 + i + a.nf2[i])) / a.mfev;
     const double *xi = a.X + (int64_t) i * a.ld, *xp = ss_row(a, a.pp[i], i), *xq = ss_row(a, a.qq[i], i), *xr = ss_row(a, a.rr[i], i),
             *xb = ss_row(a, a.pb[i], i), *x0 = ss_row(a, 0, i);
     const double *lead;
     if (a.usede) lead = R < 0.333 ? xp : (R < 0.666 ? xb : x0);
     else lead = i < 0.5 * a.np ? xp : xb;
-    for (int d = threadIdx.x; d < n; d += blockDim.x) {
-        double v = __dsub_rn(__dsub_rn(__dadd_rn(lead[d], xq[d]), xr[d]), xi[d]);
-        if (a.usede) v = __dadd_rn(v, __dmul_rn(R, __dsub_rn(xb[d], xq[d])));
-        z[d] = v;
-    }
-    __syncthreads();
-    const double pr = a.prank[i];
+    const double pr = a.prank[i], c = a.ci[i];
     const double *ub = a.UB + (int64_t) i * a.ld;
     for (int d = threadIdx.x; d < n; d += blockDim.x) {
-        double s = 0.0;
-        const int q = a.partner[d];
-        if (q < 0) s = __dadd_rn(s, __dmul_rn(1.0, z[d]));
-        else {
-            const int k1 = min(d, q), k2 = max(d, q);
-            s = __dadd_rn(s, __dmul_rn(ss_a(a, d, k1), z[k1]));
-            s = __dadd_rn(s, __dmul_rn(ss_a(a, d, k2), z[k2]));
-        }
-        work[d] = __dmul_rn(s, ub[d] < pr ? 1.0 : 0.0);
+        const double xv = xi[d];
+        double v = __dsub_rn(__dsub_rn(__dadd_rn(lead[d], xq[d]), xr[d]), xv);
+        if (a.usede) v = __dadd_rn(v, __dmul_rn(R, __dsub_rn(xb[d], xq[d])));
+        z[d] = v;
+        xs[d] = xv;
+        code[d] = (unsigned) (a.partner[d] + 1) | (a.first[d] ? SS_FIRST : 0u) | (ub[d] < pr ? SS_MASK : 0u);
     }
     __syncthreads();
-    const double c = a.ci[i];
+    // row d of A: sin e on the diagonal, +cos e (first of its pair) or -cos e at the partner; ascending column order
+    for (int d = threadIdx.x; d < n; d += blockDim.x) {
+        const unsigned cd = code[d];
+        const int q = (int) (cd & SS_PARTNER) - 1;
+        double s = 0.0;
+        if (q < 0) s = __dadd_rn(s, __dmul_rn(1.0, z[d]));
+        else {
+            const double aq = (cd & SS_FIRST) ? a.cosv : -a.cosv;
+            if (d < q) {
+                s = __dadd_rn(s, __dmul_rn(a.sinv, z[d]));
+                s = __dadd_rn(s, __dmul_rn(aq, z[q]));
+            } else {
+                s = __dadd_rn(s, __dmul_rn(aq, z[q]));
+                s = __dadd_rn(s, __dmul_rn(a.sinv, z[d]));
+            }
+        }
+        work[d] = __dmul_rn(s, (cd & SS_MASK) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    // column d of A (= row d of A^T): sin e on the diagonal; the partner's row holds -cos e if d is the first of the pair
     double *y = a.Y + (int64_t) i * a.ld;
     for (int d = threadIdx.x; d < n; d += blockDim.x) {
-        double v = xi[d];
-        const int q = a.partner[d];
+        const unsigned cd = code[d];
+        const int q = (int) (cd & SS_PARTNER) - 1;
+        double v = xs[d];
         if (q < 0) v = __dadd_rn(v, __dmul_rn(__dmul_rn(c, 1.0), work[d]));
         else {
-            const int k1 = min(d, q), k2 = max(d, q);
-            v = __dadd_rn(v, __dmul_rn(__dmul_rn(c, ss_a(a, k1, d)), work[k1]));
-            v = __dadd_rn(v, __dmul_rn(__dmul_rn(c, ss_a(a, k2, d)), work[k2]));
+            const double aq = (cd & SS_FIRST) ? -a.cosv : a.cosv; // A[q][d]
+            if (d < q) {
+                v = __dadd_rn(v, __dmul_rn(__dmul_rn(c, a.sinv), work[d]));
+                v = __dadd_rn(v, __dmul_rn(__dmul_rn(c, aq), work[q]));
+            } else {
+                v = __dadd_rn(v, __dmul_rn(__dmul_rn(c, aq), work[q]));
+                v = __dadd_rn(v, __dmul_rn(__dmul_rn(c, a.sinv), work[d]));
+            }
         }
         y[d] = ref_clamp(a.lo[d], a.hi[d], v);
     }
@@ -579,7 +594,8 @@ int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_
     a.Y = h->Y; a.W = h->W; a.cr1 = h->cr1; a.pp = h->pp; a.qq = h->qq; a.rr = h->rr; a.pb = h->pb; a.j0 = h->j0; a.partner = h->partner;
     a.first = h->first; a.out = h->out; a.dirty = h->dirty; a.nf2 = h->nf2; a.rebuilt = h->rebuilt; a.ld = h->ld; a.n = n; a.np = np;
     a.usede = h->usede; a.repaircr = h->repaircr; a.fev0 = fev; a.mfev = mfev; a.sinv = std::sin(1e-12); a.cosv = std::cos(1e-12);
-    const size_t smem = (size_t) 2 * n * 8;
+    const size_t smem = (size_t) 3 * n * 8 + (size_t) n * 4;
+    if (smem > 200 * 1024) return fail(BBGPU_ERR_ARG, "SSDE: n = %d is beyond the shared memory of a CTA (%zu bytes)", n, smem);
     if (smem > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(ss_build1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     // Rounds.  A round past the fixed point changes nothing (no candidate is dirty: the builds return at once, the evaluation
     // and the selection reproduce their outputs), so the first SS_SPEC rounds -- what a generation usually needs -- are enqueued
