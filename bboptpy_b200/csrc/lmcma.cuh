@@ -124,7 +124,6 @@ __device__ __forceinline__ int lm_draw_i0(int p, int memlen, int usenew, uint64_
 __global__ void __launch_bounds__(256) lm_dots_kernel(double *__restrict__ Zp, int64_t ld, int n, int slab_len, const double *__restrict__ V,
         const int *__restrict__ jarr, int memlen, int *__restrict__ i0_io, bool replay, int rademacher, int usenew, uint64_t seed,
         uint64_t generation, double *__restrict__ part, int part_ld) {
-    __shared__ double red[LM_GROUP][8];
     const int p = blockIdx.x, sl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int e0 = sl * slab_len, e1 = min(n, e0 + slab_len); // slab_len is even: Philox pairs never straddle slabs
     double *z = Zp + (int64_t) p * ld;
@@ -146,32 +145,28 @@ __global__ void __launch_bounds__(256) lm_dots_kernel(double *__restrict__ Zp, i
     const int i0 = replay ? i0_io[p] : lm_draw_i0(p, memlen, usenew, seed, generation);
     if (!replay && sl == 0 && tid == 0) i0_io[p] = i0;
     __syncthreads();
+    // A warp per direction vector, four vectors in flight: no block-wide reduction, no barrier.  (The first version reduced
+    // eight inner products at a time over the whole CTA: 25 rounds of load latency + two barriers each at memory 200.)
     double *out = part + ((int64_t) p * gridDim.y + sl) * part_ld;
-    for (int g0 = i0; g0 < memlen; g0 += LM_GROUP) {
-        double acc[LM_GROUP];
-        const double *vr[LM_GROUP];
+    constexpr int NW = 8, VPW = 4;
+    for (int g0 = i0 + warp * VPW; g0 < memlen; g0 += NW * VPW) {
+        const double *vr[VPW];
+        double acc[VPW];
 #pragma unroll
-        for (int u = 0; u < LM_GROUP; u++) {
+        for (int u = 0; u < VPW; u++) {
             acc[u] = 0.0;
             vr[u] = V + (int64_t) jarr[min(g0 + u, memlen - 1)] * ld;
         }
-        for (int e = e0 + tid; e < e1; e += blockDim.x) {
+        for (int e = e0 + lane; e < e1; e += 32) {
             const double ze = z[e];
 #pragma unroll
-            for (int u = 0; u < LM_GROUP; u++) acc[u] = fma(vr[u][e], ze, acc[u]);
+            for (int u = 0; u < VPW; u++) acc[u] = fma(vr[u][e], ze, acc[u]);
         }
 #pragma unroll
-        for (int u = 0; u < LM_GROUP; u++) {
-            const double s = warp_sum(acc[u]);
-            if (lane == 0) red[u][warp] = s;
+        for (int u = 0; u < VPW; u++) {
+            const double sum = warp_sum(acc[u]);
+            if (lane == 0 && g0 + u < memlen) out[g0 + u] = sum;
         }
-        __syncthreads();
-        if (tid < LM_GROUP && g0 + tid < memlen) {
-            double s = 0.0;
-            for (int w = 0; w < 8; w++) s += red[tid][w];
-            out[g0 + tid] = s;
-        }
-        __syncthreads();
     }
 }
 
@@ -180,25 +175,48 @@ __global__ void __launch_bounds__(256) lm_apply_kernel(double *__restrict__ X, c
         const int *__restrict__ jarr, int memlen, const int *__restrict__ i0_arr, double sqrt1mc1, const double *__restrict__ part,
         int part_ld) {
     __shared__ double dots[LM_MAXMEM];
+    __shared__ int srow[LM_MAXMEM];
     const int p = blockIdx.x, sl = blockIdx.y, slabs = gridDim.y, tid = threadIdx.x;
     const int e0 = sl * slab_len, e1 = min(n, e0 + slab_len);
     const int i0 = i0_arr[p];
     for (int i = i0 + tid; i < memlen; i += blockDim.x) {
         double s = 0.0;
         for (int t = 0; t < slabs; t++) s = __dadd_rn(s, part[((int64_t) p * slabs + t) * part_ld + i]);
-        dots[i] = __dmul_rn(b[jarr[i]], s);
+        const int j = jarr[i];
+        dots[i] = __dmul_rn(b[j], s);
+        srow[i] = j;
     }
     __syncthreads();
     const double *z = Zp + (int64_t) p * ld;
     const bool second = 2 * p + 1 < lambda;
     double *x0 = X + (int64_t) (2 * p) * ld, *x1 = X + (int64_t) (2 * p + 1) * ld;
-    for (int e = e0 + tid; e < e1; e += blockDim.x) {
-        double a = z[e];
-        for (int i = i0; i < memlen; i++)
-            a = __dadd_rn(__dmul_rn(sqrt1mc1, a), __dmul_rn(dots[i], PC[(int64_t) jarr[i] * ld + e]));
-        const double me = xmean[e];
-        x0[e] = __dadd_rn(me, __dmul_rn(sigma, a));
-        if (second) x1[e] = __dadd_rn(me, __dmul_rn(-sigma, a));
+    // the recurrence is a dependent chain per element: a thread runs EPT elements side by side so that their loads overlap
+    constexpr int EPT = 4;
+    for (int base = e0; base < e1; base += EPT * 256) {
+        double a[EPT];
+        int e[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; k++) {
+            e[k] = base + tid + k * 256;
+            a[k] = e[k] < e1 ? z[e[k]] : 0.0;
+            e[k] = min(e[k], e1 - 1); // lanes past the end redo the last element (same loads), they do not store
+        }
+#pragma unroll 2
+        for (int i = i0; i < memlen; i++) {
+            const double di = dots[i];
+            const double *row = PC + (int64_t) srow[i] * ld;
+#pragma unroll
+            for (int k = 0; k < EPT; k++) a[k] = __dadd_rn(__dmul_rn(sqrt1mc1, a[k]), __dmul_rn(di, row[e[k]]));
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; k++) {
+            const int ek = base + tid + k * 256;
+            if (ek < e1) {
+                const double me = xmean[ek];
+                x0[ek] = __dadd_rn(me, __dmul_rn(sigma, a[k]));
+                if (second) x1[ek] = __dadd_rn(me, __dmul_rn(-sigma, a[k]));
+            }
+        }
     }
 }
 
