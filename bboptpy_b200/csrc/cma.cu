@@ -42,6 +42,8 @@ struct bbgpu_cma {
     bool lm = false;
     int lm_mem = 0, lm_pairs = 0, lm_slabs = 1, lm_part_ld = 0;
     double *lm_part = nullptr;    // partial inner products of the slab-split sampling: pairs x slabs x lm_part_ld
+    int *lm_flags = nullptr;      // rebuild wavefront: one flag per memory row + a give-up word
+    double *lm_tglob = nullptr;   // rebuild scratch (one row per CTA) when a row does not fit the registers of a CTA
     double *PCmat = nullptr, *Vmat = nullptr, *lmb = nullptr, *lmd = nullptr, *Zp = nullptr;
     int *lm_jarr = nullptr, *lm_i0 = nullptr;
     // vectors
@@ -1333,6 +1335,8 @@ int bbgpu_cma_create(bbgpu_ctx *ctx, const bbgpu_cma_config *cfg, const double *
         A(&h->lmd, (size_t) h->lm_mem); A(&h->Zp, (size_t) h->lm_pairs * ldn);
         if (rc == BBGPU_OK) rc = dev_alloc(&h->lm_jarr, (size_t) h->lm_mem);
         if (rc == BBGPU_OK) rc = dev_alloc(&h->lm_i0, (size_t) h->lm_pairs);
+        if (rc == BBGPU_OK) rc = dev_alloc(&h->lm_flags, (size_t) h->lm_mem + 8);
+        if (n > LM_TP * 1024) A(&h->lm_tglob, (size_t) ctx->sm_count * ldn);
         // slabs: enough CTAs for two per SM, at least 512 columns each
         h->lm_slabs = std::max(1, std::min(std::min((int) LM_MAXSLABS, (int) ceil_div(2 * ctx->sm_count, h->lm_pairs)), n / 512));
         h->lm_part_ld = (int) round_up(std::max(h->lm_mem, 1), 8);
@@ -1380,11 +1384,12 @@ int bbgpu_cma_destroy(bbgpu_cma *h) {
     double *bufs[] = { h->xmean, h->xold, h->pc, h->ps, h->D, h->dm, h->tmpn, h->W, h->weights, h->lower, h->upper, h->coef,
             h->ycoeff, h->dscal, h->X, h->Zbuf[0], h->Zbuf[1], h->fit, h->rank_val, h->part, h->C, h->Bt, h->BDt, h->BDit, h->isC, h->Ysel,
             h->rowsq_part, h->solver_work, h->ssq, h->Yloc, h->coef_loc, h->wm_loc, h->norm_all, h->red, h->rowsq_loc, h->own_ws,
-            h->Ystk, h->Mch, h->Lt, h->negone, h->rnorm, h->rstat, h->PCmat, h->Vmat, h->lmb, h->lmd, h->Zp, h->Ycomp, h->coef_comp, h->lm_part };
+            h->Ystk, h->Mch, h->Lt, h->negone, h->rnorm, h->rstat, h->PCmat, h->Vmat, h->lmb, h->lmd, h->Zp, h->Ycomp, h->coef_comp, h->lm_part, h->lm_tglob };
     if (h->sel_idx) cudaFree(h->sel_idx);
     if (h->ksel) cudaFree(h->ksel);
     if (h->lm_jarr) cudaFree(h->lm_jarr);
     if (h->lm_i0) cudaFree(h->lm_i0);
+    if (h->lm_flags) cudaFree(h->lm_flags);
     if (h->ev_ch_fork) cudaEventDestroy(h->ev_ch_fork);
     if (h->ev_ch_join) cudaEventDestroy(h->ev_ch_join);
     if (h->own_info) cudaFree(h->own_info);
@@ -1712,9 +1717,27 @@ int bbgpu_cma_lm_update(bbgpu_cma *h, double sigma, int do_memory, int imin, int
             false, h->ps, nullptr, 0.0, 0.0, nullptr);
     BB_TRY(launched(ctx, "recombine_final_kernel"));
     const double ccc = std::sqrt(c.cc * (2.0 - c.cc) * c.mueff);
-    lm_memory_kernel<<<1, 1024, 0, st>>>(n, h->ldn, h->pc, h->xmean, h->xold, sigma, c.cc, ccc, c.c1, std::sqrt(1.0 - c.c1), do_memory, imin,
-            memlen, h->lm_jarr, h->PCmat, h->Vmat, h->lmb, h->lmd, h->tmpn);
-    return launched(ctx, "lm_memory_kernel");
+    // the rebuild of rows imin.. as a wavefront over the SMs (lm_rebuild_kernel) unless BBGPU_LM_REBUILD=1 keeps it in the one CTA
+    static const bool one_cta = [] { const char *e = getenv("BBGPU_LM_REBUILD"); return e && e[0] == '1'; }();
+    const int rows = do_memory ? memlen - imin : 0;
+    const bool wave = do_memory && !one_cta && rows >= 2;
+    lm_memory_kernel<<<1, 1024, 0, st>>>(n, h->ldn, h->pc, h->xmean, h->xold, sigma, c.cc, ccc, c.c1, std::sqrt(1.0 - c.c1),
+            wave ? 2 : do_memory, imin, memlen, h->lm_jarr, h->PCmat, h->Vmat, h->lmb, h->lmd, h->tmpn);
+    BB_TRY(launched(ctx, "lm_memory_kernel"));
+    if (wave) {
+        BB_CUDA(cudaMemsetAsync(h->lm_flags, 0, ((size_t) memlen + 1) * sizeof(int), st));
+        int nn = n, im = imin, ml = memlen;
+        int64_t ldn = h->ldn;
+        double c1 = c.c1, s1 = std::sqrt(1.0 - c.c1);
+        const int *jarr = h->lm_jarr;
+        const double *PC = h->PCmat;
+        double *V = h->Vmat, *bb_ = h->lmb, *dd_ = h->lmd, *tg = h->lm_tglob;
+        int *flags = h->lm_flags;
+        void *args[] = { &nn, &ldn, &c1, &s1, &im, &ml, &jarr, &PC, &V, &bb_, &dd_, &flags, &tg };
+        BB_CUDA(cudaLaunchCooperativeKernel((const void*) lm_rebuild_kernel, dim3(std::min(rows, ctx->sm_count)), dim3(1024), args, 0, st));
+        BB_TRY(launched(ctx, "lm_rebuild_kernel"));
+    }
+    return BBGPU_OK;
 }
 
 // CholeskyCmaes::converged(), the O(lambda n) part (cholesky_cmaes.cpp:146-160): mean and M2 = sum (r_k - mean)^2 of

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(1024) lm_memory_kernel(int n, int64_t ld, doub
         double *dst = PC + (int64_t) jarr[memlen - 1] * ld;
         for (int e = tid; e < n; e += blockDim.x) dst[e] = pc[e];
     }
+    if (do_memory == 2) return; // the rebuild runs in lm_rebuild_kernel
     __syncthreads();
     const double c = 1.0 / sqrt1mc1;
     for (int i = imin; i < memlen; i++) {
@@ -267,6 +268,103 @@ __global__ void __launch_bounds__(1024) lm_memory_kernel(int n, int64_t ld, doub
             d[jcur] = (1.0 / (sqrt1mc1 * s)) * (1.0 - 1.0 / sqrtc1);
         }
         __syncthreads(); // b / d / V of this row are read by the next rows' chains
+    }
+}
+
+// ---- the rebuild as a wavefront over the SMs ---------------------------------------------------------------------------------
+// lm_memory_kernel walks the rebuilt rows one after the other: row i is a chain of i dependent n-reductions (≈215 cycles each,
+// the floor of a block-wide sum), 20 000 of them for a full rebuild at memory 200: 2.2 ms, every few generations.  But row i
+// needs the NEW row k only at its step k, and the rows below imin never change: with one row per CTA, every row runs the steps
+// k < imin at once and then follows the row in front of it one step behind -- the critical path is one step + one finalisation
+// per rebuilt row instead of i steps.  Rows imin + me, imin + me + G, ... belong to CTA me; a finished row is published by a
+// flag (release after the CTA's stores; the consumer's thread 0 acquires it, the barrier carries it to the others; the row
+// itself is read past L1).  Dependencies only point to smaller rows and every CTA takes its rows in increasing order, so the
+// cooperative launch (all CTAs resident) cannot deadlock.  Arithmetic per row as in lm_memory_kernel: same element-to-thread
+// assignment, same block sum.
+constexpr int LM_TP = 12; // elements of t a thread keeps in registers: n <= 12288, beyond that t lives in global scratch
+
+__global__ void __launch_bounds__(1024, 1) lm_rebuild_kernel(int n, int64_t ld, double c1, double sqrt1mc1, int imin, int memlen,
+        const int *__restrict__ jarr, const double *__restrict__ PC, double *V, double *b, double *d, int *flags, double *tglob) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x, G = gridDim.x, me = blockIdx.x;
+    const double c = 1.0 / sqrt1mc1;
+    const bool inreg = n <= LM_TP * 1024;
+    double *tg = tglob ? tglob + (int64_t) me * ld : nullptr;
+    for (int i = imin + me; i < memlen; i += G) {
+        const int jcur = jarr[i];
+        const double *src = PC + (int64_t) jcur * ld;
+        double t[LM_TP];
+        if (inreg) {
+#pragma unroll
+            for (int q = 0; q < LM_TP; q++) {
+                const int e = tid + q * 1024;
+                t[q] = e < n ? src[e] : 0.0;
+            }
+        } else {
+            for (int e = tid; e < n; e += 1024) tg[e] = src[e];
+        }
+        for (int k = 0; k < i; k++) {
+            const int idx = jarr[k];
+            if (k >= imin) { // rebuilt by this launch: wait for its owner
+                if (tid == 0) {
+                    int seen = 0, spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + k) : "memory");
+                    } while (seen == 0 && ++spins < (1 << 24));
+                    if (seen == 0) flags[memlen] = 1; // gave up (a lost CTA must not hang the device); the word is there for a debugger
+                }
+                __syncthreads();
+            }
+            const double *v = V + (int64_t) idx * ld;
+            double s = 0.0;
+            if (inreg) {
+                double vk[LM_TP];
+#pragma unroll
+                for (int q = 0; q < LM_TP; q++) {
+                    const int e = tid + q * 1024;
+                    vk[q] = e < n ? __ldcg(v + e) : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < LM_TP; q++)
+                    if (tid + q * 1024 < n) s = fma(vk[q], t[q], s);
+                s = block_sum(s, red);
+                const double dot = __dmul_rn(__ldcg(d + idx), s);
+#pragma unroll
+                for (int q = 0; q < LM_TP; q++) t[q] = __dadd_rn(__dmul_rn(c, t[q]), __dmul_rn(-dot, vk[q]));
+            } else {
+                for (int e = tid; e < n; e += 1024) s = fma(__ldcg(v + e), tg[e], s);
+                s = block_sum(s, red);
+                const double dot = __dmul_rn(__ldcg(d + idx), s);
+                for (int e = tid; e < n; e += 1024) tg[e] = __dadd_rn(__dmul_rn(c, tg[e]), __dmul_rn(-dot, __ldcg(v + e)));
+            }
+        }
+        double *vdst = V + (int64_t) jcur * ld;
+        double s = 0.0;
+        if (inreg) {
+#pragma unroll
+            for (int q = 0; q < LM_TP; q++) {
+                const int e = tid + q * 1024;
+                if (e < n) {
+                    vdst[e] = t[q];
+                    s = fma(t[q], t[q], s);
+                }
+            }
+        } else {
+            for (int e = tid; e < n; e += 1024) {
+                const double te = tg[e];
+                vdst[e] = te;
+                s = fma(te, te, s);
+            }
+        }
+        s = block_sum(s, red);
+        if (tid == 0) {
+            const double sqrtc1 = sqrt(1.0 + (c1 / (1.0 - c1)) * s);
+            b[jcur] = (sqrt1mc1 / s) * (sqrtc1 - 1.0);
+            d[jcur] = (1.0 / (sqrt1mc1 * s)) * (1.0 - 1.0 / sqrtc1);
+        }
+        __threadfence(); // this thread's part of the row (and b / d) before the flag
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(flags + i), "r"(1) : "memory");
     }
 }
 
