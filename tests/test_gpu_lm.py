@@ -56,6 +56,8 @@ CASES = [
     (30, 16, 80, True, dict(memory=5)),
     (30, 17, 80, False, dict(memory=6, usenew=False, rademacher=False)),
     (1000, 64, 12, False, dict()),
+    (4096, 16, 14, False, dict(memory=6, rademacher=False)),   # sampling split over 8 column slabs, rebuild wavefront
+    (12500, 8, 12, True, dict(memory=5)),                      # a row beyond the registers of a CTA: rebuild scratch in global memory
 ]
 
 
