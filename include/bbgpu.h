@@ -2,8 +2,9 @@
  * bbgpu.h -- C ABI of the B200 population engine (libbbgpu.so).
  *
  * This is the drop-in boundary for the reference's data-parallel hot path: the
- * per-generation sample -> evaluate -> rank -> update loop of the CMA-ES family and the
- * JADE / L-SHADE generation.  The reference has no FFI for this path (it is straight C++
+ * per-generation sample -> evaluate -> rank -> update loop of the CMA-ES family (Vanilla,
+ * Active, Separable, Cholesky, LM; xNES shares the handle) and the generation of the DE family
+ * (JADE / L-SHADE: bbgpu_de_*, SaNSDE: bbgpu_sde_*, SSDE: bbgpu_ssde_*).  The reference has no FFI for this path (it is straight C++
  * behind pybind11), so each entry point below names the reference code it replaces
  * (paths relative to /root/reference).  The host classes in bboptpy_b200/host/ keep the
  * reference's MultivariateOptimizer interface (src/multivariate/multivariate.h:132-146) and
