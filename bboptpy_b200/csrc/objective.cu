@@ -11,14 +11,65 @@ __global__ void __launch_bounds__(256) eval_rows_kernel(int id, int n, int count
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= count) return;
     const double *x = X + (int64_t) row * ld;
-    const double v = warp_objective(id, n, x, aux);
+    double v;
+    switch (id) { // (warp-uniform)
+    case BBGPU_OBJ_SPHERE: v = warp_objective_id<BBGPU_OBJ_SPHERE>(n, x, aux); break;
+    case BBGPU_OBJ_ELLIPSOID: v = warp_objective_id<BBGPU_OBJ_ELLIPSOID>(n, x, aux); break;
+    case BBGPU_OBJ_ROSENBROCK: v = warp_objective_id<BBGPU_OBJ_ROSENBROCK>(n, x, aux); break;
+    case BBGPU_OBJ_RASTRIGIN: v = warp_objective_id<BBGPU_OBJ_RASTRIGIN>(n, x, aux); break;
+    case BBGPU_OBJ_ACKLEY: v = warp_objective_id<BBGPU_OBJ_ACKLEY>(n, x, aux); break;
+    default: v = warp_objective(id, n, x, aux); break;
+    }
     if ((threadIdx.x & 31) == 0) f[row] = v;
+}
+
+// Few long rows (LM-CMA-ES: 64 candidates of 10^4 coordinates put 64 warps on the whole GPU): a CTA per row computes the terms
+// into shared memory with all its threads, one warp then adds them in the objective's order (warp_reduce_terms: same bits).
+template<int ID>
+__global__ void __launch_bounds__(256) eval_rows_wide_kernel(int n, int count, const double *__restrict__ X, int64_t ld,
+        const double *__restrict__ aux, double *__restrict__ f) {
+    extern __shared__ double terms[]; // t1[nt], Ackley: t2[nt]
+    const int row = blockIdx.x;
+    const double *x = X + (int64_t) row * ld;
+    const int nt = obj_term_count(ID, n);
+    double *t1 = terms, *t2 = terms + nt;
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+        const double v = x[i];
+        const double xn = ID == BBGPU_OBJ_ROSENBROCK ? x[i + 1] : 0.0;
+        const double a = ID == BBGPU_OBJ_ELLIPSOID ? aux[i] : 0.0;
+        double s2 = 0.0;
+        t1[i] = obj_term(ID, v, xn, a, s2);
+        if (ID == BBGPU_OBJ_ACKLEY) t2[i] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const double v = warp_reduce_terms(ID, n, t1, t2);
+        if (threadIdx.x == 0) f[row] = v;
+    }
+}
+
+template<int ID>
+static int launch_wide(bbgpu_ctx *ctx, int n, int count, const double *d_X, int64_t ld, const double *aux, double *d_f, size_t smem) {
+    if (smem > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(eval_rows_wide_kernel<ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    eval_rows_wide_kernel<ID><<<count, 256, smem, ctx->stream>>>(n, count, d_X, ld, aux, d_f);
+    return launched(ctx, "eval_rows_wide_kernel");
 }
 
 int evaluate(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *d_X, int64_t ld, int count, double *d_f) {
     if (count <= 0) return BBGPU_OK;
     obj->evals += count;
     if (obj->mode == 0) {
+        const size_t smem = (size_t) obj->n * 8 * (obj->id == BBGPU_OBJ_ACKLEY ? 2 : 1);
+        if (count <= 2 * ctx->sm_count && obj->n >= 2048 && smem <= 200 * 1024) {
+            switch (obj->id) {
+            case BBGPU_OBJ_SPHERE: return launch_wide<BBGPU_OBJ_SPHERE>(ctx, obj->n, count, d_X, ld, obj->d_aux, d_f, smem);
+            case BBGPU_OBJ_ELLIPSOID: return launch_wide<BBGPU_OBJ_ELLIPSOID>(ctx, obj->n, count, d_X, ld, obj->d_aux, d_f, smem);
+            case BBGPU_OBJ_ROSENBROCK: return launch_wide<BBGPU_OBJ_ROSENBROCK>(ctx, obj->n, count, d_X, ld, obj->d_aux, d_f, smem);
+            case BBGPU_OBJ_RASTRIGIN: return launch_wide<BBGPU_OBJ_RASTRIGIN>(ctx, obj->n, count, d_X, ld, obj->d_aux, d_f, smem);
+            case BBGPU_OBJ_ACKLEY: return launch_wide<BBGPU_OBJ_ACKLEY>(ctx, obj->n, count, d_X, ld, obj->d_aux, d_f, smem);
+            default: break;
+            }
+        }
         eval_rows_kernel<<<ceil_div(count, 8), 256, 0, ctx->stream>>>(obj->id, obj->n, count, d_X, ld,
                 obj->d_aux, d_f);
         return launched(ctx, "eval_rows_kernel");

@@ -160,6 +160,47 @@ __device__ __forceinline__ double warp_objective(int id, int n, Ptr x, const dou
     return obj_finish(id, n, s1, s2);
 }
 
+// The same value with the objective known at compile time: the term loop unrolls, four rows' worth of loads and term chains
+// are in flight, and the accumulation keeps its order (the bits are those of warp_objective).  For the standalone evaluation
+// kernel, where a generic loop left every iteration waiting for its own loads (41 us for 64 rows of 10^4 coordinates).
+template<int ID, typename Ptr>
+__device__ __forceinline__ double warp_objective_id(int n, Ptr x, const double *__restrict__ aux) {
+    const int lane = threadIdx.x & 31;
+    const int nt = obj_term_count(ID, n);
+    double acc = 0.0, acc2 = 0.0;
+    int i = lane;
+    for (; i + 96 < nt; i += 128) {
+        double v[4], xn[4], a[4], t1[4], t2[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            v[u] = x[i + 32 * u];
+            xn[u] = ID == BBGPU_OBJ_ROSENBROCK ? x[i + 32 * u + 1] : 0.0;
+            a[u] = ID == BBGPU_OBJ_ELLIPSOID ? aux[i + 32 * u] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            t2[u] = 0.0;
+            t1[u] = obj_term(ID, v[u], xn[u], a[u], t2[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            acc = add(acc, t1[u]);
+            if (ID == BBGPU_OBJ_ACKLEY) acc2 = add(acc2, t2[u]);
+        }
+    }
+    for (; i < nt; i += 32) {
+        const double v = x[i];
+        const double xn = ID == BBGPU_OBJ_ROSENBROCK ? x[i + 1] : 0.0;
+        const double a = ID == BBGPU_OBJ_ELLIPSOID ? aux[i] : 0.0;
+        double t2 = 0.0;
+        acc = add(acc, obj_term(ID, v, xn, a, t2));
+        if (ID == BBGPU_OBJ_ACKLEY) acc2 = add(acc2, t2);
+    }
+    const double s1 = warp_sum(acc);
+    const double s2 = ID == BBGPU_OBJ_ACKLEY ? warp_sum(acc2) : 0.0;
+    return obj_finish(ID, n, s1, s2);
+}
+
 // The same value from per-term buffers in shared memory (terms computed by a whole CTA in parallel):
 // called by ONE warp; t1/t2 hold term(i) for i < obj_term_count.  Same accumulation order as above.
 __device__ __forceinline__ double warp_reduce_terms(int id, int n, const double *t1, const double *t2) {
