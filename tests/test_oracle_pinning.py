@@ -183,7 +183,7 @@ def test_ssde_every_generation(ref_oracle, port_oracle, obj, n, np_, gens, kw):
         p.iterate()
         g += 1
         for k in ("iwork", "swarm_f", "swarm_x", "L1", "L2", "LCR"):
-            assert np.array_equal(r.getv(k), p.getv(k)), (g, k)
+            assert np.array_equal(r.getv(k), p.getv(k), equal_nan=True), (g, k)
         for k in ("np", "fev", "convcount", "k", "kcr"):
             assert r.geti(k) == p.geti(k), (g, k)
         assert r.converged() == p.converged()
@@ -285,3 +285,30 @@ def test_optimize_and_restart_drivers(ref_oracle, port_oracle):
                     res.append(o.restart_optimize(rk, base, 20000, O.RASTRIGIN, -5.12 * np.ones(n),
                                                   5.12 * np.ones(n), guess, flag=flag))
                 assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+
+
+def test_ssde_nan_memory_slot(ref_oracle, port_oracle):
+    """Without repaircr the reference stores CR_i itself as the successful rate: CR_i = 0 makes the weighted Lehmer mean 0 / 0,
+    and every later candidate that reads that slot crosses over with std::max(0., std::min(1., NaN)) = 1.  The port (and the
+    device engine, tests/test_gpu_ssde.py) must walk through that state exactly as the reference does."""
+    n, np_, gens = 12, 36, 150
+    kw = dict(usede=True, repaircr=False, h=7, npmin=6)
+    lo, hi = -5.12 * np.ones(n), 0.8 * 5.12 * np.ones(n)
+    mfev = np_ * (gens + 4) * 2
+    hs = []
+    for o in (ref_oracle, port_oracle):
+        o.seed(7)
+        h = o.ssde(mfev, np_, 1e-12, **kw)
+        h.init(O.RASTRIGIN, lo, hi)
+        hs.append(h)
+    r, p = hs
+    seen_nan, g = False, 0
+    while r.geti("fev") < mfev and g < gens:
+        r.iterate()
+        p.iterate()
+        g += 1
+        seen_nan = seen_nan or bool(np.isnan(r.getv("LCR")).any())
+        for k in ("swarm_f", "swarm_x", "L1", "L2", "LCR"):
+            assert np.array_equal(r.getv(k), p.getv(k), equal_nan=True), (g, k)
+        assert r.geti("fev") == p.geti("fev") and r.geti("np") == p.geti("np")
+    assert seen_nan, "the run reaches a NaN memory slot (generation 96 with this seed)"
