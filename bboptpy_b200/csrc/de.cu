@@ -144,7 +144,13 @@ __device__ __noinline__ void de_params_one(const DeDev &d, int replay, int i) {
         d.jrand[i] = de_int(d, i, 0, TAG_JRAND, d.n);
         d.slot[i] = de_int(d, i, 0, TAG_SLOT, d.np);
     }
-    d.CR[i] = fmax(0.0, fmin(__dadd_rn(__dmul_rn(z, 0.1), mcr), 1.0));
+    {
+        // std::max(0., std::min(v, 1.)) (jade.cpp:109, shade.cpp:106-107): a NaN v -- an L-SHADE memory slot that became 0 / 0
+        // without repaircr -- passes std::min unchanged and std::max returns 0.  Explicit, because nvcc reorders min / max
+        // chains (profiles/r02_nan_clamp.txt).
+        const double v = __dadd_rn(__dmul_rn(z, 0.1), mcr);
+        d.CR[i] = v != v ? 0.0 : fmax(0.0, fmin(v, 1.0));
+    }
     d.Fm[i] = F;
     d.sig[4 * i + 0] = INT_MIN; // force a build in round 0
     d.st[0][i] = 0;
