@@ -45,6 +45,8 @@ struct bbgpu_sde {
     cudaGraphExec_t g_head[2] = { nullptr, nullptr }, g_tail[2] = { nullptr, nullptr };
     int64_t g_head_kernels[2] = { 0, 0 }, g_tail_kernels[2] = { 0, 0 }, g_head_evals[2] = { 0, 0 };
     bbgpu_objective *g_obj = nullptr;
+    int g_obj_id = -1;            // (a new objective handle can reuse the address of a destroyed one)
+    const double *g_obj_aux = nullptr;
 };
 
 namespace {
@@ -476,7 +478,7 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
         for (const auto &v : iv) BB_CUDA(cudaMemcpyAsync(v.d, v.s, (size_t) np * 4, cudaMemcpyHostToDevice, st));
         BB_CUDA(cudaMemcpy2DAsync(h->U, (size_t) h->ld * 8, draws->u, (size_t) n * 8, (size_t) n * 8, np, cudaMemcpyHostToDevice, st));
     }
-    if (graph && h->g_obj != obj) sde_drop_graphs(h); // another objective: the evaluation launches differ
+    if (graph && (h->g_obj != obj || h->g_obj_id != obj->id || h->g_obj_aux != obj->d_aux)) sde_drop_graphs(h); // another objective: the evaluation launches differ
     const int c0 = h->cur;
     if (graph) {
         if (h->g_head[c0] == nullptr) {
@@ -485,6 +487,8 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
             h->g_head_evals[c0] = obj->evals - evals0;
             obj->evals = evals0;
             h->g_obj = obj;
+            h->g_obj_id = obj->id;
+            h->g_obj_aux = obj->d_aux;
             h->cur = c0; // the capture walked through the sort
         }
         BB_CUDA(cudaGraphLaunch(h->g_head[c0], st));
