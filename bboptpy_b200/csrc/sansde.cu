@@ -395,8 +395,9 @@ int sde_enqueue_head(bbgpu_sde *h, bbgpu_objective *obj, bool philox) {
     // Rounds.  A round past the fixed point changes nothing (no candidate is dirty: the builds return at once, the evaluation
     // and the selection reproduce their outputs), so the first SDE_SPEC rounds -- what a generation usually needs -- are enqueued
     // back to back and the host reads their dirty counts in one go; further rounds, if any, one at a time.
-    for (int r = 0; r < SDE_SPEC; r++) BB_TRY(sde_enqueue_round(h, obj, c, r));
-    BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, SDE_SPEC * sizeof(int), cudaMemcpyDeviceToHost, st));
+    const int spec = obj->mode == 0 ? SDE_SPEC : 1; // a user objective is not evaluated on speculation
+    for (int r = 0; r < spec; r++) BB_TRY(sde_enqueue_round(h, obj, c, r));
+    BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, spec * sizeof(int), cudaMemcpyDeviceToHost, st));
     return BBGPU_OK;
 }
 
@@ -503,7 +504,7 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
     BB_CUDA(cudaStreamSynchronize(st));
     int rounds = 0;
     bool fixed = false;
-    for (int r = 0; r < SDE_SPEC && !fixed; r++) {
+    for (int r = 0; r < (obj->mode == 0 ? SDE_SPEC : 1) && !fixed; r++) {
         rounds++;
         fixed = h->h_ndirty[r] == 0;
     }

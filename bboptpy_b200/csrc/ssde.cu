@@ -616,10 +616,11 @@ int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_
     };
     int rounds = 0;
     bool fixed = false;
-    for (int r = 0; r < SS_SPEC; r++) BB_TRY(enqueue_round(r));
-    BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, SS_SPEC * sizeof(int), cudaMemcpyDeviceToHost, st));
+    const int spec = obj->mode == 0 ? SS_SPEC : 1; // a user objective is not evaluated on speculation
+    for (int r = 0; r < spec; r++) BB_TRY(enqueue_round(r));
+    BB_CUDA(cudaMemcpyAsync(h->h_ndirty, h->ndirty, spec * sizeof(int), cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
-    for (int r = 0; r < SS_SPEC && !fixed; r++) {
+    for (int r = 0; r < spec && !fixed; r++) {
         rounds++;
         fixed = h->h_ndirty[r] == 0;
     }
