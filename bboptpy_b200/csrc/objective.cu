@@ -94,6 +94,80 @@ int evaluate(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *d_X, int64_t ld
     return BBGPU_OK;
 }
 
+// ---- evaluation of the rows a mask names (round engines of SaNSDE / SSDE with a user objective) --------------------------------
+// A registry objective is a cheap kernel: all rows are evaluated and the mask is ignored.  A user objective -- a CUDA function or
+// a Python callable behind the host bridge, usually the expensive part of the whole optimisation -- is called for the marked rows
+// only: their indices are listed, the rows gathered into a dense staging block, evaluated, and the values scattered back.
+__global__ void __launch_bounds__(1024) mask_list_kernel(const int *__restrict__ mask, int count, int *__restrict__ list, int *__restrict__ nlist) {
+    __shared__ int wsum[32], carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < count; k0 += 1024) {
+        const int i = k0 + tid;
+        const int flag = (i < count && mask[i] != 0) ? 1 : 0;
+        int x = flag;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int sacc = wsum[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, sacc, off);
+                if (lane >= off) sacc += y;
+            }
+            wsum[lane] = sacc;
+        }
+        __syncthreads();
+        if (flag) list[carry + (wid ? wsum[wid - 1] : 0) + x - 1] = i;
+        __syncthreads();
+        if (tid == 0) carry += wsum[31];
+        __syncthreads();
+    }
+    if (tid == 0) *nlist = carry;
+}
+
+__global__ void __launch_bounds__(256) rows_gather_kernel(const double *__restrict__ X, int64_t ld, int n, const int *__restrict__ list, int rows,
+        double *__restrict__ dst, int64_t ldd) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const double *src = X + (int64_t) list[r] * ld;
+    double *t = dst + (int64_t) r * ldd;
+    for (int c = threadIdx.x & 31; c < n; c += 32) t[c] = src[c];
+}
+
+__global__ void __launch_bounds__(256) values_scatter_kernel(const double *__restrict__ v, const int *__restrict__ list, int rows, double *__restrict__ f) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) f[list[r]] = v[r];
+}
+
+// work: device scratch of the caller, at least count ints + 8 ints + count * (round_up(n, 8) + 1) doubles (layout below)
+int evaluate_masked(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *d_X, int64_t ld, int count, double *d_f, const int *d_mask,
+        void *work) {
+    if (count <= 0) return BBGPU_OK;
+    if (obj->mode == 0 || d_mask == nullptr || work == nullptr) return evaluate(ctx, obj, d_X, ld, count, d_f);
+    cudaStream_t st = ctx->stream;
+    const int64_t ldd = round_up(obj->n, 8);
+    double *stage = (double*) work, *vals = stage + (size_t) count * ldd;
+    int *list = (int*) (vals + count), *nlist = list + count;
+    mask_list_kernel<<<1, 1024, 0, st>>>(d_mask, count, list, nlist);
+    BB_TRY(launched(ctx, "mask_list_kernel"));
+    int rows = 0;
+    BB_CUDA(cudaMemcpyAsync(&rows, nlist, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    if (rows == 0) return BBGPU_OK;
+    rows_gather_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(d_X, ld, obj->n, list, rows, stage, ldd);
+    BB_TRY(launched(ctx, "rows_gather_kernel"));
+    BB_TRY(evaluate(ctx, obj, stage, ldd, rows, vals));
+    values_scatter_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(vals, list, rows, d_f);
+    return launched(ctx, "values_scatter_kernel");
+}
+
 } // namespace bb
 
 extern "C" {

@@ -234,4 +234,11 @@ struct bbgpu_objective {
 namespace bb {
 // enqueue evaluation of `count` rows (leading dimension ld) on the ctx stream
 int evaluate(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *d_X, int64_t ld, int count, double *d_f);
+// the same for the rows with mask[i] != 0 when the objective is a user function (a registry objective evaluates every row);
+// work: count * (round_up(n, 8) + 1) doubles + count + 8 ints of device scratch; synchronises the stream for a user objective
+int evaluate_masked(bbgpu_ctx *ctx, bbgpu_objective *obj, const double *d_X, int64_t ld, int count, double *d_f, const int *d_mask,
+        void *work);
+inline size_t evaluate_masked_work_bytes(int n, int count) {
+    return (size_t) count * ((size_t) round_up(n, 8) + 1) * sizeof(double) + ((size_t) count + 8) * sizeof(int);
+}
 }

@@ -46,6 +46,7 @@ struct bbgpu_sde {
     int64_t g_head_kernels[2] = { 0, 0 }, g_tail_kernels[2] = { 0, 0 }, g_head_evals[2] = { 0, 0 };
     bbgpu_objective *g_obj = nullptr;
     int g_obj_id = -1;            // (a new objective handle can reuse the address of a destroyed one)
+    void *evwork = nullptr;       // scratch of evaluate_masked (user objectives only; allocated on first use)
     const double *g_obj_aux = nullptr;
 };
 
@@ -313,6 +314,7 @@ int bbgpu_sde_destroy(bbgpu_sde *h) {
     for (int *b : ibufs) if (b) cudaFree(b);
     if (h->d_acc) cudaFree(h->d_acc);
     if (h->d_par) cudaFree(h->d_par);
+    if (h->evwork) cudaFree(h->evwork);
     if (h->h_par) cudaFreeHost(h->h_par);
     for (int q = 0; q < 2; q++) {
         if (h->g_head[q]) cudaGraphExecDestroy(h->g_head[q]);
@@ -368,7 +370,7 @@ int sde_enqueue_round(bbgpu_sde *h, bbgpu_objective *obj, int c, int slot) {
     sde_build_kernel<<<np, 128, 0, st>>>(h->T, h->X[c], h->U, h->ld, n, h->lower, h->upper, h->cr[c], h->F, h->r1, h->r2, h->r3, h->ist,
             h->jrand, h->succ, h->dirty, h->rebuilt, h->cr1, h->repaircr);
     BB_TRY(launched(ctx, "sde_build_kernel"));
-    BB_TRY(evaluate(ctx, obj, h->T, h->ld, np, h->ftrial));
+    BB_TRY(evaluate_masked(ctx, obj, h->T, h->ld, np, h->ftrial, h->rebuilt, h->evwork)); // a user objective sees the rebuilt trials only
     sde_select_kernel<<<1, 1024, 0, st>>>(np, h->f[c], h->ftrial, h->r1, h->r2, h->r3, h->ist, h->succ, h->changed, h->dirty, h->rebuilt,
             h->ndirty + slot);
     return launched(ctx, "sde_select_kernel");
@@ -461,6 +463,7 @@ int bbgpu_sde_generation(bbgpu_sde *h, bbgpu_objective *obj, int refresh_cr, dou
     cudaStream_t st = ctx->stream;
     const int np = h->np, n = h->n;
     ProfScope prof(ctx, BBGPU_PROF_DE_ROUND);
+    if (obj->mode != 0 && h->evwork == nullptr) BB_CUDA(cudaMalloc(&h->evwork, evaluate_masked_work_bytes(n, np)));
     static const bool graphs_on = [] { const char *e = getenv("BBGPU_SDE_GRAPH"); return !(e && e[0] == '0'); }();
     // (the first two generations run launch by launch: lazily created buffers of the ranking exist afterwards)
     const bool graph = graphs_on && draws == nullptr && obj->mode == 0 && !ctx->profiling && h->gen >= 2;

@@ -31,8 +31,9 @@ struct bbgpu_ssde {
     double *zrank = nullptr, *cv = nullptr, *zcr = nullptr, *prank = nullptr, *ci = nullptr, *cri = nullptr, *cr1 = nullptr;
     double *L1 = nullptr, *L2 = nullptr, *LCR = nullptr, *rnorm = nullptr, *rstat = nullptr;
     int *iL = nullptr, *pp = nullptr, *qq = nullptr, *rr = nullptr, *pb = nullptr, *j0 = nullptr, *partner = nullptr, *first = nullptr;
-    int *out = nullptr, *changed = nullptr, *dirty = nullptr, *rebuilt = nullptr, *nf2 = nullptr, *nf2_prev = nullptr, *sortidx = nullptr,
-        *ndirty = nullptr;
+    int *out = nullptr, *changed = nullptr, *dirty = nullptr, *rebuilt = nullptr, *rebuilt2 = nullptr, *nf2 = nullptr, *nf2_prev = nullptr,
+        *sortidx = nullptr, *ndirty = nullptr;
+    void *evwork = nullptr; // scratch of evaluate_masked (user objectives only; allocated on first use)
     bbgpu_ssde_state *d_state = nullptr, *h_state = nullptr; // k, kCR, counters (pinned host copy)
     int *h_ndirty = nullptr;
 };
@@ -133,7 +134,7 @@ struct SsArgs {
     const double *X, *lo, *hi, *UB, *UCR, *RED, *prank, *ci, *cri;
     double *Y, *W, *cr1;
     const int *pp, *qq, *rr, *pb, *j0, *partner, *first, *out, *dirty, *nf2;
-    int *rebuilt;
+    int *rebuilt, *rebuilt2;
     int64_t ld;
     int n, np, usede, repaircr, fev0, mfev;
     double sinv, cosv;
@@ -225,9 +226,10 @@ __global__ void __launch_bounds__(128) ss_build1_kernel(const SsArgs a) {
 __global__ void __launch_bounds__(128) ss_build2_kernel(const SsArgs a, const double *__restrict__ f, const double *__restrict__ fy) {
     __shared__ double red[32];
     const int i = blockIdx.x;
-    if (!a.rebuilt[i]) return;
+    const bool second = a.rebuilt[i] && !(fy[i] <= f[i]); // rebuilt this round and the first stage was not accepted
+    if (threadIdx.x == 0) a.rebuilt2[i] = second ? 1 : 0;
+    if (!second) return;
     double *wout = a.W + (int64_t) i * a.ld;
-    if (fy[i] <= f[i]) return; // first stage accepted: no second trial
     const int n = a.n;
     const double R = (1.0 * (a.fev0 + i + a.nf2[i])) / a.mfev;
     const double *xi = a.X + (int64_t) i * a.ld, *xp = ss_row(a, a.pp[i], i), *xq = ss_row(a, a.qq[i], i), *xr = ss_row(a, a.rr[i], i),
@@ -466,7 +468,7 @@ int bbgpu_ssde_create(bbgpu_ctx *ctx, int n, int npinit, int h_mem, int usede, i
     A(&h->zrank, rows); A(&h->cv, rows); A(&h->zcr, rows); A(&h->prank, rows); A(&h->ci, rows); A(&h->cri, rows); A(&h->cr1, rows);
     A(&h->L1, (size_t) h_mem); A(&h->L2, (size_t) h_mem); A(&h->LCR, (size_t) h_mem); A(&h->rnorm, rows2); A(&h->rstat, 8);
     I(&h->iL, rows); I(&h->pp, rows); I(&h->qq, rows); I(&h->rr, rows); I(&h->pb, rows); I(&h->j0, rows); I(&h->partner, ld); I(&h->first, ld);
-    I(&h->out, rows); I(&h->changed, rows); I(&h->dirty, rows); I(&h->rebuilt, rows); I(&h->nf2, rows); I(&h->nf2_prev, rows);
+    I(&h->out, rows); I(&h->changed, rows); I(&h->dirty, rows); I(&h->rebuilt, rows); I(&h->rebuilt2, rows); I(&h->nf2, rows); I(&h->nf2_prev, rows);
     I(&h->sortidx, rows2); I(&h->ndirty, 8);
     if (rc == BBGPU_OK) rc = dev_alloc(&h->d_state, 1);
     if (rc == BBGPU_OK && (cudaMallocHost((void**) &h->h_ndirty, 8 * sizeof(int)) != cudaSuccess ||
@@ -485,10 +487,11 @@ int bbgpu_ssde_destroy(bbgpu_ssde *h) {
     double *bufs[] = { h->X[0], h->X[1], h->f[0], h->f[1], h->Y, h->W, h->fy, h->fu, h->lower, h->upper, h->UB, h->UCR, h->RED, h->zrank, h->cv,
             h->zcr, h->prank, h->ci, h->cri, h->cr1, h->L1, h->L2, h->LCR, h->rnorm, h->rstat };
     for (double *b : bufs) if (b) cudaFree(b);
-    int *ibufs[] = { h->iL, h->pp, h->qq, h->rr, h->pb, h->j0, h->partner, h->first, h->out, h->changed, h->dirty, h->rebuilt, h->nf2, h->nf2_prev,
+    int *ibufs[] = { h->iL, h->pp, h->qq, h->rr, h->pb, h->j0, h->partner, h->first, h->out, h->changed, h->dirty, h->rebuilt, h->rebuilt2, h->nf2, h->nf2_prev,
             h->sortidx, h->ndirty };
     for (int *b : ibufs) if (b) cudaFree(b);
     if (h->d_state) cudaFree(h->d_state);
+    if (h->evwork) cudaFree(h->evwork);
     if (h->h_ndirty) cudaFreeHost(h->h_ndirty);
     if (h->h_state) cudaFreeHost(h->h_state);
     delete h;
@@ -551,6 +554,7 @@ int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_
     BB_CUDA(cudaMemcpyAsync(h->partner, partner.data(), (size_t) n * 4, cudaMemcpyHostToDevice, st));
     BB_CUDA(cudaMemcpyAsync(h->first, first.data(), (size_t) n * 4, cudaMemcpyHostToDevice, st));
     const int itop = std::max(1, (int) (ptop * np));
+    if (obj->mode != 0 && h->evwork == nullptr) BB_CUDA(cudaMalloc(&h->evwork, evaluate_masked_work_bytes(n, h->npinit)));
     if (draws) {
         BB_ARG(draws->iL && draws->zrank && draws->p && draws->q && draws->r && draws->pbest && draws->cauchy && draws->ub);
         BB_ARG(!h->usede || (draws->zcr && draws->j0 && draws->ucr && draws->redraw));
@@ -592,7 +596,7 @@ int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_
     SsArgs a {};
     a.X = h->X[c]; a.lo = h->lower; a.hi = h->upper; a.UB = h->UB; a.UCR = h->UCR; a.RED = h->RED; a.prank = h->prank; a.ci = h->ci; a.cri = h->cri;
     a.Y = h->Y; a.W = h->W; a.cr1 = h->cr1; a.pp = h->pp; a.qq = h->qq; a.rr = h->rr; a.pb = h->pb; a.j0 = h->j0; a.partner = h->partner;
-    a.first = h->first; a.out = h->out; a.dirty = h->dirty; a.nf2 = h->nf2; a.rebuilt = h->rebuilt; a.ld = h->ld; a.n = n; a.np = np;
+    a.first = h->first; a.out = h->out; a.dirty = h->dirty; a.nf2 = h->nf2; a.rebuilt = h->rebuilt; a.rebuilt2 = h->rebuilt2; a.ld = h->ld; a.n = n; a.np = np;
     a.usede = h->usede; a.repaircr = h->repaircr; a.fev0 = fev; a.mfev = mfev; a.sinv = std::sin(1e-12); a.cosv = std::cos(1e-12);
     const size_t smem = (size_t) 3 * n * 8 + (size_t) n * 4;
     if (smem > 200 * 1024) return fail(BBGPU_ERR_ARG, "SSDE: n = %d is beyond the shared memory of a CTA (%zu bytes)", n, smem);
@@ -604,11 +608,11 @@ int bbgpu_ssde_generation(bbgpu_ssde *h, bbgpu_objective *obj, const int32_t *h_
     auto enqueue_round = [&](int slot) -> int {
         ss_build1_kernel<<<np, 128, smem, st>>>(a);
         BB_TRY(launched(ctx, "ss_build1_kernel"));
-        BB_TRY(evaluate(ctx, obj, h->Y, h->ld, np, h->fy));
+        BB_TRY(evaluate_masked(ctx, obj, h->Y, h->ld, np, h->fy, h->rebuilt, h->evwork)); // a user objective sees the rebuilt trials only
         if (h->usede) {
             ss_build2_kernel<<<np, 128, 0, st>>>(a, h->f[c], h->fy);
             BB_TRY(launched(ctx, "ss_build2_kernel"));
-            BB_TRY(evaluate(ctx, obj, h->W, h->ld, np, h->fu));
+            BB_TRY(evaluate_masked(ctx, obj, h->W, h->ld, np, h->fu, h->rebuilt2, h->evwork));
         }
         ss_select_kernel<<<1, 1024, 0, st>>>(np, h->usede, h->f[c], h->fy, h->fu, h->pp, h->qq, h->rr, h->pb, h->out, h->changed, h->dirty,
                 h->rebuilt, h->nf2, h->nf2_prev, h->ndirty + slot);

@@ -141,6 +141,17 @@ def test_free_running(pkg, usede):
 
 def test_python_callable_objective(pkg):
     n = 5
+    calls = [0]
+
+    def f(x):
+        calls[0] += 1
+        return float(np.sum((x - 1.0) ** 2))
+
     alg = pkg.SSDE(mfev=8000, npinit=24, tol=0.0, usede=True)
-    sol = alg.optimize(lambda x: float(np.sum((x - 1.0) ** 2)), -5 * np.ones(n), 5 * np.ones(n), np.zeros(n))
+    sol = alg.optimize(f, -5 * np.ones(n), 5 * np.ones(n), np.zeros(n))
     assert float(np.sum((sol.x - 1.0) ** 2)) < 1e-2
+    # a user objective is called for the trials a dependency round REBUILT (first stage) and for the second-stage trials of the
+    # candidates that reached it.  With usede that is most of the swarm in every round: R = fev / mfev moves for every candidate
+    # behind a changed outcome (3.0 calls per counted evaluation here; SaNSDE, without that coupling, stays below 2.5)
+    print(f"SSDE: {calls[0]} objective calls for {sol.n_evals} counted evaluations")
+    assert sol.n_evals <= calls[0] < 4 * sol.n_evals
